@@ -1,0 +1,329 @@
+"""ctypes binding of libdlsm.so (include/dlsm.h) and a thin numpy-facing ``Engine``.
+
+There is no CPU fallback: importing this module works anywhere (so host logic can be tested on
+CPU), but creating an ``Engine`` without the built extension or without a CUDA device raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "libdlsm.so")
+SRC = [os.path.join(HERE, "csrc", f) for f in ("dlsm.cu", "dlsm_kernels.cuh", "dlsm_device.cuh")]
+SRC.append(os.path.join(ROOT, "include", "dlsm.h"))
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+class DlsmError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "libdlsm error %d: %s" % (code, msg))
+        self.code = code
+
+
+def build(force=False, verbose=False):
+    """Compile libdlsm.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    if (not force and os.path.exists(LIB_PATH) and
+            all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in SRC)):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SRC[0]]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+class Config(C.Structure):
+    _fields_ = [("n_chains", C.c_int32), ("T", C.c_int32), ("n", C.c_int32), ("d", C.c_int32),
+                ("K", C.c_int32), ("is_directed", C.c_int32), ("likelihood", C.c_int32),
+                ("prior", C.c_int32), ("device", C.c_int32), ("tune", C.c_int32),
+                ("tune_interval", C.c_int32), ("intercept_tune_interval", C.c_int32 * 2),
+                ("radii_tune", C.c_int32), ("radii_tune_interval", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
+
+
+class Hyper(C.Structure):
+    _fields_ = [("tau_sq", C.c_double), ("sigma_sq", C.c_double),
+                ("intercept_prior", C.c_double * 2), ("intercept_variance_prior", C.c_double)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("node_updates", C.c_uint64),
+                ("sweeps", C.c_uint64), ("latent_ms", C.c_double), ("other_ms", C.c_double),
+                ("ub_flags", C.c_uint64)]
+
+
+# every symbol include/dlsm.h declares
+EXPORTS = [
+    "dlsm_abi_version", "dlsm_device_count", "dlsm_create", "dlsm_destroy", "dlsm_last_error",
+    "dlsm_set_stream", "dlsm_synchronize", "dlsm_set_network_dense", "dlsm_set_edge_lists",
+    "dlsm_set_controls", "dlsm_set_state", "dlsm_get_state", "dlsm_set_hyper", "dlsm_set_rng",
+    "dlsm_sweep_latent", "dlsm_center", "dlsm_sample_intercepts", "dlsm_sample_radii",
+    "dlsm_sample_labels", "dlsm_run_sweeps", "dlsm_loglik_partial", "dlsm_loglik_full",
+    "dlsm_gaussian_likelihood", "dlsm_debug_draws", "dlsm_enable_timing", "dlsm_get_counters",
+]
+
+F_X, F_INTERCEPT, F_RADII, F_Z, F_MU, F_SIGMA, F_LAMBDA, F_WEIGHTS = range(8)
+F_X_STEP, F_X_NACC, F_X_NSTEPS, F_X_UNTIL = 8, 9, 10, 11
+F_B_STEP, F_B_NACC, F_B_NSTEPS, F_B_UNTIL = 12, 13, 14, 15
+F_R_STEP, F_R_NACC, F_R_NSTEPS, F_R_UNTIL = 16, 17, 18, 19
+F_NCOUNT, F_NK = 20, 21
+_INT_FIELDS = {F_Z, F_X_NACC, F_X_NSTEPS, F_X_UNTIL, F_B_NACC, F_B_NSTEPS, F_B_UNTIL, F_R_NACC,
+               F_R_NSTEPS, F_R_UNTIL, F_NK}
+
+_lib = None
+
+
+def load():
+    """Load libdlsm.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("dynetlsm_b200: %s is missing -- build it with `python -c \"import "
+                          "__graft_entry__ as g; g.build()\"` (there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    L.dlsm_last_error.restype = C.c_char_p
+    L.dlsm_last_error.argtypes = [vp]
+    L.dlsm_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.dlsm_destroy.argtypes = [vp]
+    L.dlsm_destroy.restype = None
+    L.dlsm_set_stream.argtypes = [vp, vp]
+    L.dlsm_synchronize.argtypes = [vp]
+    L.dlsm_set_network_dense.argtypes = [vp, dp]
+    L.dlsm_set_edge_lists.argtypes = [vp, ip, ip, C.c_int32, ip, C.c_int32]
+    L.dlsm_set_controls.argtypes = [vp, ip, ip, C.c_int32, C.c_int32]
+    L.dlsm_set_state.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.dlsm_get_state.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.dlsm_set_hyper.argtypes = [vp, C.POINTER(Hyper)]
+    L.dlsm_set_rng.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64]
+    L.dlsm_sweep_latent.argtypes = [vp, dp, dp, ip, dp]
+    L.dlsm_center.argtypes = [vp]
+    L.dlsm_sample_intercepts.argtypes = [vp, dp, dp, ip, dp]
+    L.dlsm_sample_radii.argtypes = [vp, dp, dp, ip, dp]
+    L.dlsm_sample_labels.argtypes = [vp, dp]
+    L.dlsm_run_sweeps.argtypes = [vp, C.c_int32, C.c_uint32]
+    L.dlsm_loglik_partial.argtypes = [vp, dp]
+    L.dlsm_loglik_full.argtypes = [vp, dp]
+    L.dlsm_gaussian_likelihood.argtypes = [vp, dp]
+    L.dlsm_debug_draws.argtypes = [vp, dp, dp]
+    L.dlsm_enable_timing.argtypes = [vp, C.c_int]
+    L.dlsm_get_counters.argtypes = [vp, C.POINTER(Counters)]
+    _lib = L
+    return L
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != tuple(shape):
+        raise ValueError("expected shape %s, got %s" % (tuple(shape), a.shape))
+    return a
+
+
+def _i32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    if shape is not None and a.shape != tuple(shape):
+        raise ValueError("expected shape %s, got %s" % (tuple(shape), a.shape))
+    return a
+
+
+class Engine(object):
+    """Device-resident sampler state for ``n_chains`` chains sharing one dynamic network."""
+
+    def __init__(self, T, n, d, n_chains=1, K=0, is_directed=False, case_control=False,
+                 mixture=False, device=0, tune=500, tune_interval=100,
+                 intercept_tune_interval=(100, 100), radii_tune=None, radii_tune_interval=100):
+        self.L = load()
+        cfg = Config()
+        cfg.n_chains, cfg.T, cfg.n, cfg.d, cfg.K = n_chains, T, n, d, K
+        cfg.is_directed = int(is_directed)
+        cfg.likelihood = 1 if case_control else 0
+        cfg.prior = 1 if mixture else 0
+        cfg.device = device
+        cfg.tune = -1 if tune is None else int(tune)
+        cfg.tune_interval = int(tune_interval)
+        cfg.intercept_tune_interval[0] = int(intercept_tune_interval[0])
+        cfg.intercept_tune_interval[1] = int(intercept_tune_interval[1])
+        cfg.radii_tune = -1 if radii_tune is None else int(radii_tune)
+        cfg.radii_tune_interval = int(radii_tune_interval)
+        self.cfg = cfg
+        self.C, self.T, self.n, self.d, self.K = n_chains, T, n, d, K
+        self.is_directed, self.case_control, self.mixture = bool(is_directed), bool(case_control), bool(mixture)
+        self.m = 2 if is_directed else 1
+        self.h = C.c_void_p()
+        rc = self.L.dlsm_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            self.h = None
+            raise DlsmError(rc, self.L.dlsm_last_error(None).decode())
+
+    # -- plumbing ------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise DlsmError(rc, self.L.dlsm_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dlsm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shape_of(self, f):
+        C_, T, n, d, K = self.C, self.T, self.n, self.d, self.K
+        return {F_X: (C_, T, n, d), F_INTERCEPT: (C_, 2), F_RADII: (C_, n), F_Z: (C_, T, n),
+                F_MU: (C_, K, d), F_SIGMA: (C_, K), F_LAMBDA: (C_,), F_WEIGHTS: (C_, T, K, K),
+                F_X_STEP: (C_, T, n), F_X_NACC: (C_, T, n), F_X_NSTEPS: (C_, T, n),
+                F_X_UNTIL: (C_, T, n), F_B_STEP: (C_, 2), F_B_NACC: (C_, 2), F_B_NSTEPS: (C_, 2),
+                F_B_UNTIL: (C_, 2), F_R_STEP: (C_,), F_R_NACC: (C_,), F_R_NSTEPS: (C_,),
+                F_R_UNTIL: (C_,), F_NCOUNT: (C_, T, K, K), F_NK: (C_, T, K)}[f]
+
+    def set(self, f, a):
+        a = (_i32 if f in _INT_FIELDS else _f64)(a, self.shape_of(f))
+        self._ck(self.L.dlsm_set_state(self.h, f, a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    def get(self, f):
+        a = np.empty(self.shape_of(f), dtype=np.int32 if f in _INT_FIELDS else np.float64)
+        self._ck(self.L.dlsm_get_state(self.h, f, a.ctypes.data_as(C.c_void_p), a.nbytes))
+        return a
+
+    def set_stream(self, cuda_stream):
+        self._ck(self.L.dlsm_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._ck(self.L.dlsm_synchronize(self.h))
+
+    # -- inputs --------------------------------------------------------------------------
+    def set_network(self, Y):
+        Y = _f64(Y, (self.T, self.n, self.n))
+        self._ck(self.L.dlsm_set_network_dense(self.h, _dp(Y)))
+
+    def set_edge_lists(self, degrees, in_edges, out_edges):
+        dg = _i32(degrees, (self.T, self.n, 2))
+        ie, oe = _i32(in_edges), _i32(out_edges)
+        self._ck(self.L.dlsm_set_edge_lists(self.h, _ip(dg), _ip(ie), ie.shape[2], _ip(oe), oe.shape[2]))
+
+    def set_controls(self, ctrl_in, ctrl_out):
+        ci, co = _i32(ctrl_in), _i32(ctrl_out)
+        if ci.ndim == 3:
+            ci, co = ci[None], co[None]
+        self._ck(self.L.dlsm_set_controls(self.h, _ip(ci), _ip(co), ci.shape[3], ci.shape[0]))
+
+    def set_hyper(self, tau_sq=2.0, sigma_sq=0.1, intercept_prior=(0.0, 0.0),
+                  intercept_variance_prior=2.0):
+        hy = Hyper()
+        hy.tau_sq, hy.sigma_sq = float(tau_sq), float(sigma_sq)
+        ip = np.atleast_1d(np.asarray(intercept_prior, dtype=np.float64))
+        hy.intercept_prior[0] = float(ip[0])
+        hy.intercept_prior[1] = float(ip[1]) if ip.size > 1 else 0.0
+        hy.intercept_variance_prior = float(intercept_variance_prior)
+        self._ck(self.L.dlsm_set_hyper(self.h, C.byref(hy)))
+
+    def set_rng(self, seed, chain_offset=0, sweep_index=0):
+        self._ck(self.L.dlsm_set_rng(self.h, int(seed), int(chain_offset), int(sweep_index)))
+
+    def set_tuner(self, step_X, step_intercept=0.1, step_radii=175000.0):
+        """Fresh Metropolis objects (metropolis.py:86-94): zero counters, until = tune_interval."""
+        C_, T, n = self.C, self.T, self.n
+        self.set(F_X_STEP, np.full((C_, T, n), float(step_X)))
+        self.set(F_X_NACC, np.zeros((C_, T, n), np.int32))
+        self.set(F_X_NSTEPS, np.zeros((C_, T, n), np.int32))
+        self.set(F_X_UNTIL, np.full((C_, T, n), self.cfg.tune_interval, np.int32))
+        self.set(F_B_STEP, np.full((C_, 2), float(step_intercept)))
+        self.set(F_B_NACC, np.zeros((C_, 2), np.int32))
+        self.set(F_B_NSTEPS, np.zeros((C_, 2), np.int32))
+        self.set(F_B_UNTIL, np.tile(np.array(list(self.cfg.intercept_tune_interval), np.int32), (C_, 1)))
+        self.set(F_R_STEP, np.full((C_,), float(step_radii)))
+        self.set(F_R_NACC, np.zeros((C_,), np.int32))
+        self.set(F_R_NSTEPS, np.zeros((C_,), np.int32))
+        self.set(F_R_UNTIL, np.full((C_,), self.cfg.radii_tune_interval, np.int32))
+
+    # -- hot path ------------------------------------------------------------------------
+    def sweep_latent(self, eps=None, logu=None, want_stats=False):
+        C_, T, n, d = self.C, self.T, self.n, self.d
+        if eps is not None:
+            eps, logu = _f64(eps, (C_, T, n, d)), _f64(logu, (C_, T, n))
+        acc = np.empty((C_, T, n), np.int32) if want_stats else None
+        rat = np.empty((C_, T, n)) if want_stats else None
+        self._ck(self.L.dlsm_sweep_latent(self.h, _dp(eps), _dp(logu), _ip(acc), _dp(rat)))
+        return (acc, rat) if want_stats else None
+
+    def center(self):
+        self._ck(self.L.dlsm_center(self.h))
+
+    def sample_intercepts(self, eps=None, logu=None, want_stats=False):
+        if eps is not None:
+            eps, logu = _f64(eps, (self.C, self.m)), _f64(logu, (self.C, self.m))
+        acc = np.empty((self.C, self.m), np.int32) if want_stats else None
+        rat = np.empty((self.C, self.m)) if want_stats else None
+        self._ck(self.L.dlsm_sample_intercepts(self.h, _dp(eps), _dp(logu), _ip(acc), _dp(rat)))
+        return (acc, rat) if want_stats else None
+
+    def sample_radii(self, proposal=None, logu=None, want_stats=False):
+        if proposal is not None:
+            proposal, logu = _f64(proposal, (self.C, self.n)), _f64(logu, (self.C,))
+        acc = np.empty((self.C,), np.int32) if want_stats else None
+        rat = np.empty((self.C,)) if want_stats else None
+        self._ck(self.L.dlsm_sample_radii(self.h, _dp(proposal), _dp(logu), _ip(acc), _dp(rat)))
+        return (acc, rat) if want_stats else None
+
+    def sample_labels(self, U=None):
+        if U is not None:
+            U = _f64(U, (self.C, self.n, self.T))
+        self._ck(self.L.dlsm_sample_labels(self.h, _dp(U)))
+
+    def run_sweeps(self, n_sweeps, skip_center=False, skip_intercepts=False, skip_radii=False,
+                   skip_labels=False):
+        flags = (1 if skip_center else 0) | (2 if skip_intercepts else 0) | \
+                (4 if skip_radii else 0) | (8 if skip_labels else 0)
+        self._ck(self.L.dlsm_run_sweeps(self.h, int(n_sweeps), flags))
+
+    # -- probes --------------------------------------------------------------------------
+    def loglik_partial(self):
+        out = np.empty((self.C, self.T, self.n))
+        self._ck(self.L.dlsm_loglik_partial(self.h, _dp(out)))
+        return out
+
+    def loglik_full(self):
+        out = np.empty((self.C,))
+        self._ck(self.L.dlsm_loglik_full(self.h, _dp(out)))
+        return out
+
+    def gaussian_likelihood(self):
+        out = np.empty((self.C, self.n, self.T, self.K))
+        self._ck(self.L.dlsm_gaussian_likelihood(self.h, _dp(out)))
+        return out
+
+    def debug_draws(self):
+        eps = np.empty((self.C, self.T, self.n, self.d))
+        logu = np.empty((self.C, self.T, self.n))
+        self._ck(self.L.dlsm_debug_draws(self.h, _dp(eps), _dp(logu)))
+        return eps, logu
+
+    def enable_timing(self, on=True):
+        self._ck(self.L.dlsm_enable_timing(self.h, int(on)))
+
+    def counters(self):
+        c = Counters()
+        self._ck(self.L.dlsm_get_counters(self.h, C.byref(c)))
+        return dict(kernel_launches=c.kernel_launches, node_updates=c.node_updates, sweeps=c.sweeps,
+                    latent_ms=c.latent_ms, other_ms=c.other_ms, ub_flags=c.ub_flags)
+
+
+def device_count():
+    return load().dlsm_device_count()

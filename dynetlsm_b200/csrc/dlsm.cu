@@ -1,0 +1,885 @@
+// dlsm.cu -- C-ABI (include/dlsm.h) over the sm_100a kernels in dlsm_kernels.cuh.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include "../../include/dlsm.h"
+#include "dlsm_kernels.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace dlsm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct EventPair { cudaEvent_t a, b; int cat; };
+
+} // namespace
+
+struct dlsm_handle {
+    dlsm_config cfg;
+    dlsm_hyper hy;
+    int lk;                 // Lik
+    int W;                  // words per adjacency row
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    // network
+    uint32_t *rowbits = nullptr, *colbits = nullptr;
+    int32_t *deg = nullptr, *in_edges = nullptr, *out_edges = nullptr;
+    int32_t *ctrl_in = nullptr, *ctrl_out = nullptr;
+    int max_in = 0, max_out = 0, n_control = 0, ctrl_sets = 0;
+    bool have_net = false, have_edges = false, have_ctrl = false;
+    // state
+    void *field[DLSM_F_COUNT_] = {nullptr};
+    size_t field_bytes[DLSM_F_COUNT_] = {0};
+    double *rinv = nullptr;
+    // scratch
+    double *d_eps = nullptr, *d_logu = nullptr, *d_ratio = nullptr, *d_out = nullptr;
+    int32_t *d_acc = nullptr;
+    double *d_partial = nullptr, *d_bvar = nullptr, *d_prop = nullptr, *d_ll2 = nullptr;
+    double *d_rprop = nullptr, *d_rprop_inv = nullptr;
+    double *d_small = nullptr;   // [C][4] replay scalars
+    int32_t *d_small_i = nullptr;
+    unsigned int *d_flags = nullptr;
+    int *d_bad = nullptr;
+    int full_tiles = 1, full_nblk = 1;
+    // rng
+    uint64_t seed = 0, chain_offset = 0;
+    uint32_t sweep_idx[4] = {0, 0, 0, 0};
+    // counters
+    dlsm_counters ctr;
+    bool timing = false;
+    std::vector<EventPair> events;
+};
+
+#define FAIL(h, code, ...)                                          \
+    do {                                                            \
+        char _b[512];                                               \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                      \
+        (h)->err = _b;                                              \
+        return (code);                                              \
+    } while (0)
+
+#define CU(h, x)                                                                              \
+    do {                                                                                      \
+        cudaError_t _e = (x);                                                                 \
+        if (_e != cudaSuccess)                                                                \
+            FAIL(h, DLSM_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, \
+                 __LINE__);                                                                   \
+    } while (0)
+
+#define CHECK_LAUNCH(h) CU(h, cudaGetLastError())
+
+namespace {
+
+size_t elem_size(int f)
+{
+    switch (f) {
+    case DLSM_F_Z: case DLSM_F_X_NACC: case DLSM_F_X_NSTEPS: case DLSM_F_X_UNTIL:
+    case DLSM_F_B_NACC: case DLSM_F_B_NSTEPS: case DLSM_F_B_UNTIL: case DLSM_F_R_NACC:
+    case DLSM_F_R_NSTEPS: case DLSM_F_R_UNTIL: case DLSM_F_NK:
+        return 4;
+    default:
+        return 8;
+    }
+}
+
+size_t field_elems(const dlsm_config &c, int f)
+{
+    const size_t C = c.n_chains, T = c.T, n = c.n, d = c.d, K = c.K;
+    switch (f) {
+    case DLSM_F_X: return C * T * n * d;
+    case DLSM_F_INTERCEPT: case DLSM_F_B_STEP: case DLSM_F_B_NACC: case DLSM_F_B_NSTEPS:
+    case DLSM_F_B_UNTIL: return C * 2;
+    case DLSM_F_RADII: return C * n;
+    case DLSM_F_Z: return C * T * n;
+    case DLSM_F_MU: return C * K * d;
+    case DLSM_F_SIGMA: return C * K;
+    case DLSM_F_LAMBDA: return C;
+    case DLSM_F_WEIGHTS: case DLSM_F_NCOUNT: return C * T * K * K;
+    case DLSM_F_X_STEP: case DLSM_F_X_NACC: case DLSM_F_X_NSTEPS: case DLSM_F_X_UNTIL:
+        return C * T * n;
+    case DLSM_F_R_STEP: case DLSM_F_R_NACC: case DLSM_F_R_NSTEPS: case DLSM_F_R_UNTIL: return C;
+    case DLSM_F_NK: return C * T * K;
+    default: return 0;
+    }
+}
+
+template <typename T> T *F(dlsm_handle *h, int f) { return static_cast<T *>(h->field[f]); }
+
+void begin_phase(dlsm_handle *h, int cat)
+{
+    if (!h->timing) return;
+    EventPair e;
+    cudaEventCreate(&e.a);
+    cudaEventCreate(&e.b);
+    e.cat = cat;
+    cudaEventRecord(e.a, h->stream);
+    h->events.push_back(e);
+}
+
+void flush_events(dlsm_handle *h)
+{
+    if (h->events.empty()) return;
+    cudaStreamSynchronize(h->stream);
+    for (auto &e : h->events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+            if (e.cat == 0) h->ctr.latent_ms += ms; else h->ctr.other_ms += ms;
+        }
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    h->events.clear();
+}
+
+void end_phase(dlsm_handle *h)
+{
+    if (!h->timing) return;
+    cudaEventRecord(h->events.back().b, h->stream);
+    if (h->events.size() > 2048) flush_events(h);
+}
+
+NetView net_view(const dlsm_handle *h)
+{
+    NetView v;
+    v.T = h->cfg.T; v.n = h->cfg.n; v.d = h->cfg.d; v.W = h->W;
+    v.rowbits = h->rowbits; v.colbits = h->colbits;
+    v.deg = h->deg; v.in_edges = h->in_edges; v.out_edges = h->out_edges;
+    v.ctrl_in = h->ctrl_in; v.ctrl_out = h->ctrl_out;
+    v.max_in = h->max_in; v.max_out = h->max_out; v.n_control = h->n_control;
+    v.ctrl_per_chain = h->ctrl_sets > 1 ? 1 : 0;
+    return v;
+}
+
+int need_inputs(dlsm_handle *h)
+{
+    if (h->lk == kCaseControl) {
+        if (!h->have_edges || !h->have_ctrl)
+            FAIL(h, DLSM_ERR_NOTSET, "case-control likelihood needs dlsm_set_edge_lists + dlsm_set_controls");
+    } else if (!h->have_net) {
+        FAIL(h, DLSM_ERR_NOTSET, "network not set (dlsm_set_network_dense)");
+    }
+    return DLSM_OK;
+}
+
+SweepParams sweep_params(dlsm_handle *h)
+{
+    SweepParams p;
+    memset(&p, 0, sizeof(p));
+    p.net = net_view(h);
+    p.C = h->cfg.n_chains; p.K = h->cfg.K; p.prior = h->cfg.prior;
+    p.tune = h->cfg.tune; p.tune_interval = h->cfg.tune_interval;
+    p.X = F<double>(h, DLSM_F_X);
+    p.intercept = F<double>(h, DLSM_F_INTERCEPT);
+    p.rinv = h->rinv;
+    p.z = F<int32_t>(h, DLSM_F_Z);
+    p.mu = F<double>(h, DLSM_F_MU);
+    p.sigma = F<double>(h, DLSM_F_SIGMA);
+    p.lambda = F<double>(h, DLSM_F_LAMBDA);
+    p.tau_sq = h->hy.tau_sq; p.sigma_sq = h->hy.sigma_sq;
+    p.step = F<double>(h, DLSM_F_X_STEP);
+    p.nacc = F<int32_t>(h, DLSM_F_X_NACC);
+    p.nsteps = F<int32_t>(h, DLSM_F_X_NSTEPS);
+    p.until = F<int32_t>(h, DLSM_F_X_UNTIL);
+    p.seed = h->seed;
+    p.sweep = h->sweep_idx[kRngLatent];
+    p.chain_offset = (uint32_t)h->chain_offset;
+    p.flags = h->d_flags;
+    return p;
+}
+
+size_t sweep_smem(const dlsm_handle *h, bool xs)
+{
+    const size_t x = (size_t)h->cfg.T * h->cfg.n * h->cfg.d * sizeof(double);
+    return (xs ? x : 0) + (size_t)h->cfg.T * sizeof(int) + 16;
+}
+
+constexpr size_t kMaxSmem = 227 * 1024;
+
+template <int LK, int D, bool XS>
+int launch_sweep_t(dlsm_handle *h, const SweepParams &p)
+{
+    const size_t smem = sweep_smem(h, XS);
+    auto kern = k_sweep<LK, D, XS>;
+    CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int warps = h->cfg.T < 16 ? h->cfg.T : 16;
+    kern<<<h->cfg.n_chains, warps * 32, smem, h->stream>>>(p);
+    CHECK_LAUNCH(h);
+    return DLSM_OK;
+}
+
+template <int LK>
+int launch_sweep_lk(dlsm_handle *h, const SweepParams &p)
+{
+    const bool xs = sweep_smem(h, true) <= kMaxSmem;
+    if (h->cfg.d == 2) return xs ? launch_sweep_t<LK, 2, true>(h, p) : launch_sweep_t<LK, 2, false>(h, p);
+    return xs ? launch_sweep_t<LK, 0, true>(h, p) : launch_sweep_t<LK, 0, false>(h, p);
+}
+
+int launch_sweep(dlsm_handle *h, const SweepParams &p)
+{
+    begin_phase(h, 0);
+    int rc;
+    if (h->lk == kUndirected) rc = launch_sweep_lk<kUndirected>(h, p);
+    else if (h->lk == kDirected) rc = launch_sweep_lk<kDirected>(h, p);
+    else rc = launch_sweep_lk<kCaseControl>(h, p);
+    end_phase(h);
+    if (rc == DLSM_OK) {
+        h->ctr.kernel_launches += 1;
+        h->ctr.sweeps += 1;
+        h->ctr.node_updates += (uint64_t)h->cfg.n_chains * h->cfg.T * h->cfg.n;
+    }
+    return rc;
+}
+
+template <typename K, typename... A>
+int launch_simple(dlsm_handle *h, K kern, dim3 grid, dim3 block, size_t smem, A... args)
+{
+    kern<<<grid, block, smem, h->stream>>>(args...);
+    CHECK_LAUNCH(h);
+    h->ctr.kernel_launches += 1;
+    return DLSM_OK;
+}
+
+// full-network log-likelihood for two variants -> h->d_partial
+int launch_full(dlsm_handle *h, const double *rinv0, const double *rinv1)
+{
+    FullParams p;
+    memset(&p, 0, sizeof(p));
+    p.net = net_view(h);
+    p.C = h->cfg.n_chains; p.tiles = h->full_tiles;
+    p.X = F<double>(h, DLSM_F_X);
+    p.bvar = h->d_bvar;
+    p.rinv0 = rinv0; p.rinv1 = rinv1;
+    p.partial = h->d_partial;
+    p.flags = h->d_flags;
+    dim3 grid(h->cfg.T * h->full_tiles, h->cfg.n_chains);
+    const size_t smem = (h->lk == kCaseControl) ? 0 : (size_t)h->cfg.n * h->cfg.d * sizeof(double);
+    const bool d2 = h->cfg.d == 2;
+#define LAUNCH_FULL(LK)                                                                          \
+    do {                                                                                         \
+        if (d2) {                                                                                \
+            CU(h, cudaFuncSetAttribute(k_full<LK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_full<LK, 2><<<grid, 256, smem, h->stream>>>(p);                                    \
+        } else {                                                                                 \
+            CU(h, cudaFuncSetAttribute(k_full<LK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_full<LK, 0><<<grid, 256, smem, h->stream>>>(p);                                    \
+        }                                                                                        \
+    } while (0)
+    if (smem > kMaxSmem) FAIL(h, DLSM_ERR_UNSUPPORTED, "n too large for the exact full-network kernel");
+    if (h->lk == kUndirected) LAUNCH_FULL(kUndirected);
+    else if (h->lk == kDirected) LAUNCH_FULL(kDirected);
+    else LAUNCH_FULL(kCaseControl);
+#undef LAUNCH_FULL
+    CHECK_LAUNCH(h);
+    h->ctr.kernel_launches += 1;
+    return DLSM_OK;
+}
+
+int check_flags(dlsm_handle *h)
+{
+    unsigned int f = 0;
+    CU(h, cudaMemcpyAsync(&f, h->d_flags, sizeof(f), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (f & 2u) h->ctr.ub_flags += 1;
+    if (f) CU(h, cudaMemsetAsync(h->d_flags, 0, sizeof(unsigned int), h->stream));
+    if (f & 1u) FAIL(h, DLSM_ERR_NONFINITE, "a log-likelihood ratio evaluated to NaN/inf");
+    return DLSM_OK;
+}
+
+int upload(dlsm_handle *h, void *dst, const void *src, size_t bytes)
+{
+    CU(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return DLSM_OK;
+}
+
+int download(dlsm_handle *h, void *dst, const void *src, size_t bytes)
+{
+    CU(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return DLSM_OK;
+}
+
+int update_rinv(dlsm_handle *h)
+{
+    const size_t total = (size_t)h->cfg.n_chains * h->cfg.n;
+    return launch_simple(h, k_rinv, dim3((unsigned)((total + 255) / 256)), dim3(256), 0,
+                         (const double *)F<double>(h, DLSM_F_RADII), h->rinv, total);
+}
+
+} // namespace
+
+extern "C" {
+
+int dlsm_abi_version(void) { return DLSM_ABI_VERSION; }
+
+int dlsm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *dlsm_last_error(const dlsm_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int dlsm_create(const dlsm_config *cfg, dlsm_handle **out)
+{
+    if (!cfg || !out) { g_create_error = "null argument"; return DLSM_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->n_chains < 1 || cfg->T < 1 || cfg->n < 2 || cfg->d < 1 || cfg->d > kMaxD || cfg->K < 0) {
+        g_create_error = "invalid shape (need n_chains>=1, T>=1, n>=2, 1<=d<=8, K>=0)";
+        return DLSM_ERR_INVALID;
+    }
+    if (cfg->likelihood == DLSM_LIK_CASE_CONTROL && !cfg->is_directed) {
+        // lsm.py:425-427
+        g_create_error = "The case-control likelihood currently only supported for directed networks.";
+        return DLSM_ERR_INVALID;
+    }
+    if (cfg->prior == DLSM_PRIOR_MIXTURE && cfg->K < 1) {
+        g_create_error = "mixture prior needs K >= 1";
+        return DLSM_ERR_INVALID;
+    }
+    if (dlsm_device_count() <= cfg->device) {
+        g_create_error = "no CUDA device available (libdlsm has no CPU fallback)";
+        return DLSM_ERR_CUDA;
+    }
+    dlsm_handle *h = new dlsm_handle();
+    h->cfg = *cfg;
+    memset(&h->ctr, 0, sizeof(h->ctr));
+    h->hy.tau_sq = 2.0; h->hy.sigma_sq = 0.1;
+    h->hy.intercept_prior[0] = h->hy.intercept_prior[1] = 0.0;
+    h->hy.intercept_variance_prior = 2.0;
+    h->lk = cfg->likelihood == DLSM_LIK_CASE_CONTROL ? kCaseControl
+                                                      : (cfg->is_directed ? kDirected : kUndirected);
+    h->W = ((cfg->n + 31) / 32 + 3) / 4 * 4;
+    auto fail = [&](const char *what, cudaError_t e) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
+        dlsm_destroy(h);
+        return DLSM_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return fail("cudaStreamCreate", e);
+    h->stream = h->own_stream;
+    for (int f = 0; f < DLSM_F_COUNT_; f++) {
+        const size_t bytes = field_elems(*cfg, f) * elem_size(f);
+        h->field_bytes[f] = bytes;
+        if (bytes == 0) continue;
+        if ((e = cudaMalloc(&h->field[f], bytes)) != cudaSuccess) return fail("cudaMalloc(state)", e);
+        cudaMemsetAsync(h->field[f], 0, bytes, h->stream);
+    }
+    const size_t C = cfg->n_chains, n = cfg->n, T = cfg->T;
+    h->full_tiles = (int)((n + 63) / 64);
+    h->full_nblk = cfg->T * h->full_tiles;
+#define ALLOC(ptr, bytes)                                                              \
+    if ((e = cudaMalloc((void **)&(ptr), (bytes))) != cudaSuccess) return fail("cudaMalloc", e)
+    ALLOC(h->rinv, C * n * 8);
+    ALLOC(h->d_partial, C * h->full_nblk * 2 * 8);
+    ALLOC(h->d_bvar, C * 4 * 8);
+    ALLOC(h->d_prop, C * 8);
+    ALLOC(h->d_ll2, C * 2 * 8);
+    ALLOC(h->d_small, C * 4 * 8);
+    ALLOC(h->d_small_i, C * 4 * 4);
+    ALLOC(h->d_flags, 4);
+    ALLOC(h->d_bad, 4);
+    if (cfg->is_directed) {
+        ALLOC(h->d_rprop, C * n * 8);
+        ALLOC(h->d_rprop_inv, C * n * 8);
+    }
+#undef ALLOC
+    cudaMemsetAsync(h->d_flags, 0, 4, h->stream);
+    cudaMemsetAsync(h->rinv, 0, C * n * 8, h->stream);
+    (void)T;
+    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return fail("init", e);
+    *out = h;
+    return DLSM_OK;
+}
+
+void dlsm_destroy(dlsm_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto &e : h->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (int f = 0; f < DLSM_F_COUNT_; f++) cudaFree(h->field[f]);
+    void *ptrs[] = {h->rowbits, h->colbits, h->deg, h->in_edges, h->out_edges, h->ctrl_in,
+                    h->ctrl_out, h->rinv, h->d_eps, h->d_logu, h->d_ratio, h->d_out, h->d_acc,
+                    h->d_partial, h->d_bvar, h->d_prop, h->d_ll2, h->d_rprop, h->d_rprop_inv,
+                    h->d_small, h->d_small_i, h->d_flags, h->d_bad};
+    for (void *p : ptrs) cudaFree(p);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int dlsm_set_stream(dlsm_handle *h, void *s)
+{
+    if (!h) return DLSM_ERR_INVALID;
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->stream = s ? static_cast<cudaStream_t>(s) : h->own_stream;
+    return DLSM_OK;
+}
+
+int dlsm_synchronize(dlsm_handle *h)
+{
+    if (!h) return DLSM_ERR_INVALID;
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return DLSM_OK;
+}
+
+int dlsm_set_network_dense(dlsm_handle *h, const double *Y)
+{
+    if (!h || !Y) return DLSM_ERR_INVALID;
+    CU(h, cudaSetDevice(h->cfg.device));
+    const size_t T = h->cfg.T, n = h->cfg.n, W = h->W;
+    if (!h->rowbits) CU(h, cudaMalloc((void **)&h->rowbits, T * n * W * 4));
+    if (h->cfg.is_directed && !h->colbits) CU(h, cudaMalloc((void **)&h->colbits, T * n * W * 4));
+    double *slice = nullptr;
+    CU(h, cudaMalloc((void **)&slice, n * n * 8));
+    CU(h, cudaMemsetAsync(h->d_bad, 0, 4, h->stream));
+    for (size_t t = 0; t < T; t++) {
+        CU(h, cudaMemcpyAsync(slice, Y + t * n * n, n * n * 8, cudaMemcpyHostToDevice, h->stream));
+        const size_t warps = n * W;
+        k_pack_rows<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, h->stream>>>(
+            slice, (int)n, (int)W, h->rowbits + t * n * W, h->d_bad);
+        if (h->cfg.is_directed)
+            k_pack_cols<<<(unsigned)((n * W + 255) / 256), 256, 0, h->stream>>>(
+                slice, (int)n, (int)W, h->colbits + t * n * W);
+        h->ctr.kernel_launches += h->cfg.is_directed ? 2 : 1;
+    }
+    int bad = 0;
+    cudaError_t e = cudaMemcpyAsync(&bad, h->d_bad, 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(slice);
+    CU(h, e);
+    CHECK_LAUNCH(h);
+    if (bad) FAIL(h, DLSM_ERR_NONBINARY, "adjacency must be 0/1 (weighted or missing (-1) dyads are not supported on the device path)");
+    h->have_net = true;
+    return DLSM_OK;
+}
+
+int dlsm_set_edge_lists(dlsm_handle *h, const int32_t *degrees, const int32_t *in_edges,
+                        int32_t max_in, const int32_t *out_edges, int32_t max_out)
+{
+    if (!h || !degrees || max_in < 0 || max_out < 0) return DLSM_ERR_INVALID;
+    if ((max_in > 0 && !in_edges) || (max_out > 0 && !out_edges)) return DLSM_ERR_INVALID;
+    CU(h, cudaSetDevice(h->cfg.device));
+    const size_t TN = (size_t)h->cfg.T * h->cfg.n;
+    cudaFree(h->deg); cudaFree(h->in_edges); cudaFree(h->out_edges);
+    h->deg = h->in_edges = h->out_edges = nullptr;
+    CU(h, cudaMalloc((void **)&h->deg, TN * 2 * 4));
+    CU(h, cudaMalloc((void **)&h->in_edges, (TN * (size_t)max_in + 1) * 4));
+    CU(h, cudaMalloc((void **)&h->out_edges, (TN * (size_t)max_out + 1) * 4));
+    int rc = upload(h, h->deg, degrees, TN * 2 * 4);
+    if (rc == DLSM_OK && max_in) rc = upload(h, h->in_edges, in_edges, TN * max_in * 4);
+    if (rc == DLSM_OK && max_out) rc = upload(h, h->out_edges, out_edges, TN * max_out * 4);
+    if (rc != DLSM_OK) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->max_in = max_in; h->max_out = max_out;
+    h->have_edges = true;
+    return DLSM_OK;
+}
+
+int dlsm_set_controls(dlsm_handle *h, const int32_t *ctrl_in, const int32_t *ctrl_out,
+                      int32_t n_control, int32_t n_sets)
+{
+    if (!h || !ctrl_in || !ctrl_out || n_control < 1) return DLSM_ERR_INVALID;
+    if (n_sets != 1 && n_sets != h->cfg.n_chains)
+        FAIL(h, DLSM_ERR_INVALID, "n_sets must be 1 or n_chains");
+    CU(h, cudaSetDevice(h->cfg.device));
+    const size_t bytes = (size_t)n_sets * h->cfg.T * h->cfg.n * n_control * 4;
+    if (n_control != h->n_control || n_sets != h->ctrl_sets) {
+        cudaFree(h->ctrl_in); cudaFree(h->ctrl_out);
+        h->ctrl_in = h->ctrl_out = nullptr;
+        CU(h, cudaMalloc((void **)&h->ctrl_in, bytes));
+        CU(h, cudaMalloc((void **)&h->ctrl_out, bytes));
+    }
+    int rc = upload(h, h->ctrl_in, ctrl_in, bytes);
+    if (rc == DLSM_OK) rc = upload(h, h->ctrl_out, ctrl_out, bytes);
+    if (rc != DLSM_OK) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->n_control = n_control; h->ctrl_sets = n_sets;
+    h->have_ctrl = true;
+    return DLSM_OK;
+}
+
+int dlsm_set_state(dlsm_handle *h, int field, const void *host, size_t bytes)
+{
+    if (!h || !host || field < 0 || field >= DLSM_F_COUNT_) return DLSM_ERR_INVALID;
+    if (field == DLSM_F_NCOUNT || field == DLSM_F_NK) FAIL(h, DLSM_ERR_INVALID, "read-only field");
+    if (bytes != h->field_bytes[field] || bytes == 0)
+        FAIL(h, DLSM_ERR_INVALID, "field %d expects %zu bytes, got %zu", field, h->field_bytes[field], bytes);
+    CU(h, cudaSetDevice(h->cfg.device));
+    int rc = upload(h, h->field[field], host, bytes);
+    if (rc != DLSM_OK) return rc;
+    if (field == DLSM_F_RADII) rc = update_rinv(h);
+    if (rc != DLSM_OK) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return DLSM_OK;
+}
+
+int dlsm_get_state(dlsm_handle *h, int field, void *host, size_t bytes)
+{
+    if (!h || !host || field < 0 || field >= DLSM_F_COUNT_) return DLSM_ERR_INVALID;
+    if (bytes != h->field_bytes[field] || bytes == 0)
+        FAIL(h, DLSM_ERR_INVALID, "field %d expects %zu bytes, got %zu", field, h->field_bytes[field], bytes);
+    CU(h, cudaSetDevice(h->cfg.device));
+    return download(h, host, h->field[field], bytes);
+}
+
+int dlsm_set_hyper(dlsm_handle *h, const dlsm_hyper *hy)
+{
+    if (!h || !hy) return DLSM_ERR_INVALID;
+    h->hy = *hy;
+    return DLSM_OK;
+}
+
+int dlsm_set_rng(dlsm_handle *h, uint64_t seed, uint64_t chain_offset, uint64_t sweep_index)
+{
+    if (!h) return DLSM_ERR_INVALID;
+    h->seed = seed;
+    h->chain_offset = chain_offset;
+    for (int k = 0; k < 4; k++) h->sweep_idx[k] = (uint32_t)sweep_index;
+    return DLSM_OK;
+}
+
+static int ensure_replay_buffers(dlsm_handle *h)
+{
+    const size_t N = (size_t)h->cfg.n_chains * h->cfg.T * h->cfg.n;
+    if (!h->d_eps) CU(h, cudaMalloc((void **)&h->d_eps, N * h->cfg.d * 8));
+    if (!h->d_logu) CU(h, cudaMalloc((void **)&h->d_logu, N * 8));
+    if (!h->d_ratio) CU(h, cudaMalloc((void **)&h->d_ratio, N * 8));
+    if (!h->d_acc) CU(h, cudaMalloc((void **)&h->d_acc, N * 4));
+    return DLSM_OK;
+}
+
+int dlsm_sweep_latent(dlsm_handle *h, const double *eps, const double *logu, int32_t *accepted,
+                      double *ratio)
+{
+    if (!h) return DLSM_ERR_INVALID;
+    if ((eps == nullptr) != (logu == nullptr)) FAIL(h, DLSM_ERR_INVALID, "eps and logu must both be given (replay) or both NULL (native)");
+    CU(h, cudaSetDevice(h->cfg.device));
+    int rc = need_inputs(h);
+    if (rc != DLSM_OK) return rc;
+    const size_t N = (size_t)h->cfg.n_chains * h->cfg.T * h->cfg.n;
+    SweepParams p = sweep_params(h);
+    if (eps || accepted || ratio) {
+        rc = ensure_replay_buffers(h);
+        if (rc != DLSM_OK) return rc;
+    }
+    if (eps) {
+        if ((rc = upload(h, h->d_eps, eps, N * h->cfg.d * 8)) != DLSM_OK) return rc;
+        if ((rc = upload(h, h->d_logu, logu, N * 8)) != DLSM_OK) return rc;
+        p.eps = h->d_eps; p.logu = h->d_logu;
+    }
+    if (accepted) p.accepted = h->d_acc;
+    if (ratio) p.ratio = h->d_ratio;
+    if ((rc = launch_sweep(h, p)) != DLSM_OK) return rc;
+    if (!eps) h->sweep_idx[kRngLatent] += 1;
+    if (accepted) CU(h, cudaMemcpyAsync(accepted, h->d_acc, N * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (ratio) CU(h, cudaMemcpyAsync(ratio, h->d_ratio, N * 8, cudaMemcpyDeviceToHost, h->stream));
+    return check_flags(h);
+}
+
+static int center_async(dlsm_handle *h)
+{
+    begin_phase(h, 1);
+    int rc = launch_simple(h, k_center, dim3(h->cfg.n_chains), dim3(256), 0, F<double>(h, DLSM_F_X),
+                           h->cfg.T, h->cfg.n, h->cfg.d);
+    end_phase(h);
+    return rc;
+}
+
+int dlsm_center(dlsm_handle *h)
+{
+    if (!h) return DLSM_ERR_INVALID;
+    CU(h, cudaSetDevice(h->cfg.device));
+    int rc = center_async(h);
+    if (rc != DLSM_OK) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return DLSM_OK;
+}
+
+// device-side part of sample_intercepts; d_eps/d_logu are device pointers or null (native)
+static int intercepts_async(dlsm_handle *h, const double *d_eps, const double *d_logu,
+                            int32_t *d_acc, double *d_ratio)
+{
+    const int C = h->cfg.n_chains, m = h->cfg.is_directed ? 2 : 1;
+    const dim3 g1((C + 127) / 128), b1(128);
+    begin_phase(h, 1);
+    for (int i = 0; i < m; i++) {
+        ScalarMH p;
+        memset(&p, 0, sizeof(p));
+        p.C = C; p.which = i; p.nblk = h->full_nblk;
+        p.tune = h->cfg.tune; p.tune_interval = h->cfg.intercept_tune_interval[i];
+        p.intercept = F<double>(h, DLSM_F_INTERCEPT);
+        p.bvar = h->d_bvar; p.prop = h->d_prop; p.partial = h->d_partial;
+        p.prior_mean = h->hy.intercept_prior[i]; p.prior_var = h->hy.intercept_variance_prior;
+        p.step = F<double>(h, DLSM_F_B_STEP);
+        p.nacc = F<int32_t>(h, DLSM_F_B_NACC);
+        p.nsteps = F<int32_t>(h, DLSM_F_B_NSTEPS);
+        p.until = F<int32_t>(h, DLSM_F_B_UNTIL);
+        p.eps = d_eps; p.logu = d_logu; p.m = m;
+        p.seed = h->seed; p.sweep = h->sweep_idx[kRngIntercept];
+        p.chain_offset = (uint32_t)h->chain_offset;
+        p.site = (uint32_t)((size_t)h->cfg.T * h->cfg.n);
+        p.accepted = d_acc; p.ratio = d_ratio; p.flags = h->d_flags;
+        int rc = launch_simple(h, k_intercept_propose, g1, b1, 0, p);
+        if (rc != DLSM_OK) return rc;
+        if ((rc = launch_full(h, h->rinv, h->rinv)) != DLSM_OK) return rc;
+        if ((rc = launch_simple(h, k_intercept_finalize, g1, b1, 0, p)) != DLSM_OK) return rc;
+    }
+    end_phase(h);
+    if (!d_eps) h->sweep_idx[kRngIntercept] += 1;
+    return DLSM_OK;
+}
+
+int dlsm_sample_intercepts(dlsm_handle *h, const double *eps, const double *logu,
+                           int32_t *accepted, double *ratio)
+{
+    if (!h) return DLSM_ERR_INVALID;
+    if ((eps == nullptr) != (logu == nullptr)) FAIL(h, DLSM_ERR_INVALID, "eps and logu must both be given or both NULL");
+    CU(h, cudaSetDevice(h->cfg.device));
+    int rc = need_inputs(h);
+    if (rc != DLSM_OK) return rc;
+    const size_t C = h->cfg.n_chains, m = h->cfg.is_directed ? 2 : 1;
+    double *d_eps = nullptr, *d_logu = nullptr;
+    if (eps) {
+        d_eps = h->d_small; d_logu = h->d_small + C * 2;
+        if ((rc = upload(h, d_eps, eps, C * m * 8)) != DLSM_OK) return rc;
+        if ((rc = upload(h, d_logu, logu, C * m * 8)) != DLSM_OK) return rc;
+    }
+    if ((rc = intercepts_async(h, d_eps, d_logu, accepted ? h->d_small_i : nullptr,
+                               ratio ? h->d_ll2 : nullptr)) != DLSM_OK)
+        return rc;
+    if (accepted) CU(h, cudaMemcpyAsync(accepted, h->d_small_i, C * m * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (ratio) CU(h, cudaMemcpyAsync(ratio, h->d_ll2, C * m * 8, cudaMemcpyDeviceToHost, h->stream));
+    return check_flags(h);
+}
+
+static int radii_async(dlsm_handle *h, bool native, const double *d_logu, int32_t *d_acc,
+                       double *d_ratio)
+{
+    const int C = h->cfg.n_chains, n = h->cfg.n;
+    begin_phase(h, 1);
+    int rc;
+    const uint32_t site0 = (uint32_t)((size_t)h->cfg.T * n + 8);
+    if (native) {
+        rc = launch_simple(h, k_radii_propose, dim3(C), dim3(256), 0, n,
+                           (const double *)F<double>(h, DLSM_F_RADII),
+                           (const double *)F<double>(h, DLSM_F_R_STEP), h->d_rprop, h->d_rprop_inv,
+                           h->seed, h->sweep_idx[kRngRadii], (uint32_t)h->chain_offset, site0);
+    } else {
+        const size_t total = (size_t)C * n;
+        rc = launch_simple(h, k_rinv, dim3((unsigned)((total + 255) / 256)), dim3(256), 0,
+                           (const double *)h->d_rprop, h->d_rprop_inv, total);
+    }
+    if (rc != DLSM_OK) return rc;
+    rc = launch_simple(h, k_bvar_current, dim3((C + 127) / 128), dim3(128), 0, C,
+                       (const double *)F<double>(h, DLSM_F_INTERCEPT), h->d_bvar);
+    if (rc != DLSM_OK) return rc;
+    if ((rc = launch_full(h, h->d_rprop_inv, h->rinv)) != DLSM_OK) return rc;
+    RadiiMH p;
+    memset(&p, 0, sizeof(p));
+    p.C = C; p.n = n; p.nblk = h->full_nblk;
+    p.tune = h->cfg.radii_tune; p.tune_interval = h->cfg.radii_tune_interval;
+    p.radii = F<double>(h, DLSM_F_RADII); p.rinv = h->rinv;
+    p.prop = h->d_rprop; p.prop_rinv = h->d_rprop_inv; p.partial = h->d_partial;
+    p.step = F<double>(h, DLSM_F_R_STEP);
+    p.nacc = F<int32_t>(h, DLSM_F_R_NACC);
+    p.nsteps = F<int32_t>(h, DLSM_F_R_NSTEPS);
+    p.until = F<int32_t>(h, DLSM_F_R_UNTIL);
+    p.logu = d_logu;
+    p.seed = h->seed; p.sweep = h->sweep_idx[kRngRadii];
+    p.chain_offset = (uint32_t)h->chain_offset; p.site = site0;
+    p.accepted = d_acc; p.ratio = d_ratio; p.flags = h->d_flags;
+    rc = launch_simple(h, k_radii_finalize, dim3(C), dim3(256), 0, p);
+    end_phase(h);
+    if (native) h->sweep_idx[kRngRadii] += 1;
+    return rc;
+}
+
+int dlsm_sample_radii(dlsm_handle *h, const double *proposal, const double *logu,
+                      int32_t *accepted, double *ratio)
+{
+    if (!h) return DLSM_ERR_INVALID;
+    if (!h->cfg.is_directed) FAIL(h, DLSM_ERR_INVALID, "radii exist only for directed networks");
+    if ((proposal == nullptr) != (logu == nullptr)) FAIL(h, DLSM_ERR_INVALID, "proposal and logu must both be given or both NULL");
+    CU(h, cudaSetDevice(h->cfg.device));
+    int rc = need_inputs(h);
+    if (rc != DLSM_OK) return rc;
+    const size_t C = h->cfg.n_chains, n = h->cfg.n;
+    if (proposal) {
+        if ((rc = upload(h, h->d_rprop, proposal, C * n * 8)) != DLSM_OK) return rc;
+        if ((rc = upload(h, h->d_small, logu, C * 8)) != DLSM_OK) return rc;
+    }
+    rc = radii_async(h, proposal == nullptr, proposal ? h->d_small : nullptr,
+                     accepted ? h->d_small_i : nullptr, ratio ? h->d_ll2 : nullptr);
+    if (rc != DLSM_OK) return rc;
+    if (accepted) CU(h, cudaMemcpyAsync(accepted, h->d_small_i, C * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (ratio) CU(h, cudaMemcpyAsync(ratio, h->d_ll2, C * 8, cudaMemcpyDeviceToHost, h->stream));
+    return check_flags(h);
+}
+
+static int labels_async(dlsm_handle *h, const double *d_U, double *lik_out, int sample)
+{
+    const dlsm_config &c = h->cfg;
+    LabelParams p;
+    memset(&p, 0, sizeof(p));
+    p.C = c.n_chains; p.T = c.T; p.n = c.n; p.d = c.d; p.K = c.K;
+    p.X = F<double>(h, DLSM_F_X); p.mu = F<double>(h, DLSM_F_MU);
+    p.sigma = F<double>(h, DLSM_F_SIGMA); p.lambda = F<double>(h, DLSM_F_LAMBDA);
+    p.w = F<double>(h, DLSM_F_WEIGHTS);
+    p.U = d_U;
+    p.seed = h->seed; p.sweep = h->sweep_idx[kRngLabels]; p.chain_offset = (uint32_t)h->chain_offset;
+    p.z = F<int32_t>(h, DLSM_F_Z);
+    p.ncount = F<double>(h, DLSM_F_NCOUNT); p.nk = F<int32_t>(h, DLSM_F_NK);
+    p.lik_out = lik_out; p.sample = sample;
+    const int wpb = 4;
+    const size_t per_warp = ((size_t)c.T * c.K + 3 * c.K) * sizeof(double);
+    const size_t smem = per_warp * wpb;
+    if (smem > kMaxSmem) FAIL(h, DLSM_ERR_UNSUPPORTED, "T*K too large for the label kernel");
+    CU(h, cudaFuncSetAttribute(k_ffbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (sample) {
+        CU(h, cudaMemsetAsync(p.ncount, 0, h->field_bytes[DLSM_F_NCOUNT], h->stream));
+        CU(h, cudaMemsetAsync(p.nk, 0, h->field_bytes[DLSM_F_NK], h->stream));
+    }
+    const size_t warps = (size_t)c.n_chains * c.n;
+    begin_phase(h, 1);
+    int rc = launch_simple(h, k_ffbs, dim3((unsigned)((warps + wpb - 1) / wpb)), dim3(wpb * 32), smem, p);
+    end_phase(h);
+    if (sample && !d_U) h->sweep_idx[kRngLabels] += 1;
+    return rc;
+}
+
+int dlsm_sample_labels(dlsm_handle *h, const double *U)
+{
+    if (!h) return DLSM_ERR_INVALID;
+    if (h->cfg.prior != DLSM_PRIOR_MIXTURE) FAIL(h, DLSM_ERR_INVALID, "labels exist only with the mixture prior");
+    CU(h, cudaSetDevice(h->cfg.device));
+    const size_t N = (size_t)h->cfg.n_chains * h->cfg.n * h->cfg.T;
+    double *d_U = nullptr;
+    if (U) {
+        int rc = ensure_replay_buffers(h);
+        if (rc != DLSM_OK) return rc;
+        d_U = h->d_logu; // same element count (C*T*n)
+        if ((rc = upload(h, d_U, U, N * 8)) != DLSM_OK) return rc;
+    }
+    int rc = labels_async(h, d_U, nullptr, 1);
+    if (rc != DLSM_OK) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return DLSM_OK;
+}
+
+int dlsm_run_sweeps(dlsm_handle *h, int32_t n_sweeps, uint32_t flags)
+{
+    if (!h || n_sweeps < 0) return DLSM_ERR_INVALID;
+    CU(h, cudaSetDevice(h->cfg.device));
+    int rc = need_inputs(h);
+    if (rc != DLSM_OK) return rc;
+    for (int s = 0; s < n_sweeps; s++) {
+        SweepParams p = sweep_params(h);
+        if ((rc = launch_sweep(h, p)) != DLSM_OK) return rc;
+        h->sweep_idx[kRngLatent] += 1;
+        if (!(flags & 1u) && (rc = center_async(h)) != DLSM_OK) return rc;
+        if (!(flags & 2u) && (rc = intercepts_async(h, nullptr, nullptr, nullptr, nullptr)) != DLSM_OK) return rc;
+        if (h->cfg.is_directed && !(flags & 4u) &&
+            (rc = radii_async(h, true, nullptr, nullptr, nullptr)) != DLSM_OK)
+            return rc;
+        if (h->cfg.prior == DLSM_PRIOR_MIXTURE && !(flags & 8u) &&
+            (rc = labels_async(h, nullptr, nullptr, 1)) != DLSM_OK)
+            return rc;
+    }
+    return check_flags(h);
+}
+
+int dlsm_loglik_partial(dlsm_handle *h, double *out)
+{
+    if (!h || !out) return DLSM_ERR_INVALID;
+    CU(h, cudaSetDevice(h->cfg.device));
+    int rc = need_inputs(h);
+    if (rc != DLSM_OK) return rc;
+    if ((rc = ensure_replay_buffers(h)) != DLSM_OK) return rc;
+    const size_t N = (size_t)h->cfg.n_chains * h->cfg.T * h->cfg.n;
+    SweepParams p = sweep_params(h);
+    const dim3 grid((unsigned)((N * 32 + 255) / 256)), block(256);
+    const bool d2 = h->cfg.d == 2;
+    if (h->lk == kUndirected) rc = d2 ? launch_simple(h, k_partial<kUndirected, 2>, grid, block, 0, p, h->d_ratio) : launch_simple(h, k_partial<kUndirected, 0>, grid, block, 0, p, h->d_ratio);
+    else if (h->lk == kDirected) rc = d2 ? launch_simple(h, k_partial<kDirected, 2>, grid, block, 0, p, h->d_ratio) : launch_simple(h, k_partial<kDirected, 0>, grid, block, 0, p, h->d_ratio);
+    else rc = d2 ? launch_simple(h, k_partial<kCaseControl, 2>, grid, block, 0, p, h->d_ratio) : launch_simple(h, k_partial<kCaseControl, 0>, grid, block, 0, p, h->d_ratio);
+    if (rc != DLSM_OK) return rc;
+    return download(h, out, h->d_ratio, N * 8);
+}
+
+int dlsm_loglik_full(dlsm_handle *h, double *out)
+{
+    if (!h || !out) return DLSM_ERR_INVALID;
+    CU(h, cudaSetDevice(h->cfg.device));
+    int rc = need_inputs(h);
+    if (rc != DLSM_OK) return rc;
+    const int C = h->cfg.n_chains;
+    rc = launch_simple(h, k_bvar_current, dim3((C + 127) / 128), dim3(128), 0, C,
+                       (const double *)F<double>(h, DLSM_F_INTERCEPT), h->d_bvar);
+    if (rc != DLSM_OK) return rc;
+    if ((rc = launch_full(h, h->rinv, h->rinv)) != DLSM_OK) return rc;
+    rc = launch_simple(h, k_sum_partials, dim3((C + 127) / 128), dim3(128), 0, C, h->full_nblk,
+                       (const double *)h->d_partial, h->d_ll2);
+    if (rc != DLSM_OK) return rc;
+    std::vector<double> tmp((size_t)C * 2);
+    if ((rc = download(h, tmp.data(), h->d_ll2, (size_t)C * 16)) != DLSM_OK) return rc;
+    for (int c = 0; c < C; c++) out[c] = tmp[(size_t)c * 2 + 1];
+    return DLSM_OK;
+}
+
+int dlsm_gaussian_likelihood(dlsm_handle *h, double *out)
+{
+    if (!h || !out) return DLSM_ERR_INVALID;
+    if (h->cfg.prior != DLSM_PRIOR_MIXTURE) FAIL(h, DLSM_ERR_INVALID, "needs the mixture prior");
+    CU(h, cudaSetDevice(h->cfg.device));
+    const size_t N = (size_t)h->cfg.n_chains * h->cfg.n * h->cfg.T * h->cfg.K;
+    double *d = nullptr;
+    CU(h, cudaMalloc((void **)&d, N * 8));
+    int rc = labels_async(h, nullptr, d, 0);
+    if (rc == DLSM_OK) rc = download(h, out, d, N * 8);
+    cudaFree(d);
+    return rc;
+}
+
+int dlsm_debug_draws(dlsm_handle *h, double *eps, double *logu)
+{
+    if (!h || !eps || !logu) return DLSM_ERR_INVALID;
+    CU(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_replay_buffers(h);
+    if (rc != DLSM_OK) return rc;
+    const size_t N = (size_t)h->cfg.n_chains * h->cfg.T * h->cfg.n;
+    SweepParams p = sweep_params(h);
+    const dim3 grid((unsigned)((N + 255) / 256)), block(256);
+    rc = (h->cfg.d == 2) ? launch_simple(h, k_debug_draws<2>, grid, block, 0, p, h->d_eps, h->d_logu)
+                         : launch_simple(h, k_debug_draws<0>, grid, block, 0, p, h->d_eps, h->d_logu);
+    if (rc != DLSM_OK) return rc;
+    if ((rc = download(h, eps, h->d_eps, N * h->cfg.d * 8)) != DLSM_OK) return rc;
+    return download(h, logu, h->d_logu, N * 8);
+}
+
+int dlsm_enable_timing(dlsm_handle *h, int on)
+{
+    if (!h) return DLSM_ERR_INVALID;
+    flush_events(h);
+    h->timing = on != 0;
+    return DLSM_OK;
+}
+
+int dlsm_get_counters(dlsm_handle *h, dlsm_counters *out)
+{
+    if (!h || !out) return DLSM_ERR_INVALID;
+    CU(h, cudaSetDevice(h->cfg.device));
+    flush_events(h);
+    *out = h->ctr;
+    return DLSM_OK;
+}
+
+} // extern "C"

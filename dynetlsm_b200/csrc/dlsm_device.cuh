@@ -1,0 +1,188 @@
+// dlsm_device.cuh -- device-side building blocks shared by every kernel of libdlsm.so.
+//
+// fp64 throughout (the reference's arithmetic type).  Rounding-sensitive steps
+// (proposal, squared distance, priors) use the explicit-rounding intrinsics so that nvcc cannot
+// contract them into FMAs: the reference (Cython built for baseline x86-64, numpy elementwise
+// ops) rounds every multiply and add separately, and accepted states must be bit-identical.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace dlsm {
+
+constexpr int kMaxD = 8;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  Counter = (site, sweep, chain, (kind<<24)|block),
+// key = 64-bit seed.  Each call yields two 52-bit uniforms in (0,1).
+// ---------------------------------------------------------------------------------------------
+enum RngKind : uint32_t { kRngLatent = 0, kRngIntercept = 1, kRngRadii = 2, kRngLabels = 3 };
+
+__host__ __device__ inline void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2,
+                                             uint32_t &c3, uint32_t k0, uint32_t k1)
+{
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+
+struct U2 { double a, b; };
+
+__host__ __device__ inline U2 philox_u2(uint64_t seed, uint32_t site, uint32_t sweep,
+                                        uint32_t chain, uint32_t kind, uint32_t block)
+{
+    uint32_t c0 = site, c1 = sweep, c2 = chain, c3 = (kind << 24) | (block & 0xffffffu);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    const double s = 2.220446049250313e-16; // 2^-52
+    U2 u;
+    u.a = ((double)(((uint64_t)c0 << 20) | (c1 >> 12)) + 0.5) * s;
+    u.b = ((double)(((uint64_t)c2 << 20) | (c3 >> 12)) + 0.5) * s;
+    return u;
+}
+
+// Box-Muller pair from two uniforms in (0,1)
+__device__ inline void box_muller(const U2 u, double &z0, double &z1)
+{
+    const double r = sqrt(-2.0 * log(u.a));
+    double s, c;
+    sincospi(2.0 * u.b, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+// the draws of one latent node-update: eps[0..d) and log(u)
+template <int DM>
+__device__ inline void latent_draws(uint64_t seed, uint32_t site, uint32_t sweep, uint32_t chain,
+                                    int d, double (&eps)[DM], double &logu)
+{
+    const U2 ua = philox_u2(seed, site, sweep, chain, kRngLatent, 0);
+    logu = log(ua.a);
+#pragma unroll
+    for (int p = 0; p < (DM + 1) / 2; p++) {
+        if (2 * p < d) {
+            double z0, z1;
+            box_muller(philox_u2(seed, site, sweep, chain, kRngLatent, 1 + p), z0, z1);
+            eps[2 * p] = z0;
+            if (2 * p + 1 < DM) eps[2 * p + 1] = z1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// log(1 + exp(eta)) exactly as the reference writes it (static_network_fast.pyx:42,
+// directed_likelihoods_fast.pyx:73): no softplus guard, overflow to +inf above eta ~ 709.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double log1pexp(double eta) { return log(1.0 + exp(eta)); }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// numpy pairwise_sum for n <= 8 (d <= 8 reductions in the priors): serial below 8, the
+// 8-accumulator tree at exactly 8.
+template <int DM>
+__device__ __forceinline__ double np_sum_small(const double (&a)[DM], int d)
+{
+    if (DM == 8 && d == 8) {
+        return __dadd_rn(__dadd_rn(__dadd_rn(a[0], a[1]), __dadd_rn(a[2], a[3])),
+                         __dadd_rn(__dadd_rn(a[4 % DM], a[5 % DM]), __dadd_rn(a[6 % DM], a[7 % DM])));
+    }
+    double s = -0.0;
+#pragma unroll
+    for (int k = 0; k < DM; k++)
+        if (k < d) s = __dadd_rn(s, a[k]);
+    return s;
+}
+
+// 0.5 * np.sum(v*v) / s
+template <int DM>
+__device__ __forceinline__ double half_sumsq_over(const double (&v)[DM], int d, double s)
+{
+    double sq[DM];
+#pragma unroll
+    for (int k = 0; k < DM; k++) sq[k] = (k < d) ? __dmul_rn(v[k], v[k]) : 0.0;
+    return __ddiv_rn(__dmul_rn(0.5, np_sum_small<DM>(sq, d)), s);
+}
+
+// squared Euclidean distance with the reference's rounding: dist += (a - b) ** 2, serial in k
+template <int DM>
+__device__ __forceinline__ double sqdist(const double (&a)[DM], const double (&b)[DM], int d)
+{
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < DM; k++)
+        if (k < d) {
+            const double df = __dsub_rn(a[k], b[k]);
+            s = __dadd_rn(s, __dmul_rn(df, df));
+        }
+    return s;
+}
+
+template <int DM>
+__device__ __forceinline__ void load_pos(const double *p, int d, double (&x)[DM])
+{
+    if (DM == 2) {
+        const double2 v = *reinterpret_cast<const double2 *>(p);
+        x[0] = v.x;
+        x[1 % DM] = v.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < DM; k++) x[k] = (k < d) ? p[k] : 0.0;
+    }
+}
+
+// Metropolis tuner (metropolis.py:5-37, :113-136); tune < 0 means tune=None
+__device__ inline double tune_random_walk(double s, double r)
+{
+    if (r < 0.001) s *= 0.1;
+    else if (r < 0.05) s *= 0.5;
+    else if (r < 0.25) s *= 0.9;
+    else if (r > 0.95) s *= 10.0;
+    else if (r > 0.75) s *= 2.0;
+    else if (r > 0.4) s *= 1.1;
+    return s;
+}
+
+__device__ inline double tune_dirichlet(double s, double r)
+{
+    if (r < 0.001) s *= 10.0;
+    else if (r < 0.05) s *= 2.0;
+    else if (r < 0.25) s *= 1.1;
+    else if (r > 0.95) s *= 0.1;
+    else if (r > 0.75) s *= 0.5;
+    else if (r > 0.4) s *= 0.9;
+    return s;
+}
+
+__device__ inline void metropolis_bookkeep(double &step, int &n_accepted, int &n_steps, int &until,
+                                           int tune, int tune_interval, int accepted,
+                                           bool dirichlet)
+{
+    n_accepted += accepted;
+    n_steps += 1;
+    if (tune < 0) return;
+    if (n_steps < tune && until == 0) {
+        const double rate = (double)n_accepted / (double)tune_interval;
+        step = dirichlet ? tune_dirichlet(step, rate) : tune_random_walk(step, rate);
+        n_accepted = 0;
+        until = tune_interval;
+    } else {
+        until -= 1;
+    }
+}
+
+} // namespace dlsm

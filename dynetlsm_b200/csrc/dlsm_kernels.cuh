@@ -1,0 +1,963 @@
+// dlsm_kernels.cuh -- the sm_100a kernels of the MH-within-Gibbs hot path.
+//
+// Mapping (DESIGN.md has the full rationale):
+//   k_sweep      one CTA per chain, one warp per time slice, slices run as a bit-exact wavefront:
+//                slice t updates node j once slice t-1 has finished node j (then X[t-1,j] is new
+//                and X[t+1,j] is still old, exactly the reference's lexicographic (t,j) order,
+//                sample_latent_positions.py:98-99).  Positions live in shared memory when the
+//                chain fits (T*n*d*8 B), otherwise they stay in global/L2.  The j-reduction of the
+//                pairwise logistic log-likelihood is 32 lanes wide, fp64, warp-shuffle tree; both
+//                MH evaluations (proposal and current) share one pass over the row.
+//   k_full_*     O(T n^2) full-network log-likelihood for two parameter variants in one pass
+//                (intercept / radii MH evaluate logp(x) and logp(x0) on the same distances).
+//   k_ffbs       one warp per (chain, node): emission densities, backward messages, forward draws.
+#pragma once
+#include "dlsm_device.cuh"
+
+namespace dlsm {
+
+enum Lik : int { kUndirected = 0, kDirected = 1, kCaseControl = 2 };
+
+struct NetView {
+    int T, n, d, W;             // W = 32-bit words per adjacency row (multiple of 4)
+    const uint32_t *rowbits;    // [T][n][W]  bit i of row j = Y[t, j, i]
+    const uint32_t *colbits;    // [T][n][W]  bit i of row j = Y[t, i, j]   (directed only)
+    // case-control lists (int32; -1 sentinels in the control sets)
+    const int32_t *deg;         // [T][n][2]  in, out
+    const int32_t *in_edges;    // [T][n][max_in]
+    const int32_t *out_edges;   // [T][n][max_out]
+    const int32_t *ctrl_in;     // [S][T][n][n_control]
+    const int32_t *ctrl_out;
+    int max_in, max_out, n_control, ctrl_per_chain;
+};
+
+struct SweepParams {
+    NetView net;
+    int C, K, prior, tune, tune_interval;
+    double *X;                 // [C][T][n][d]
+    const double *intercept;   // [C][2]
+    const double *rinv;        // [C][n]   1 / radii
+    const int32_t *z;          // [C][T][n]
+    const double *mu;          // [C][K][d]
+    const double *sigma;       // [C][K]
+    const double *lambda;      // [C]
+    double tau_sq, sigma_sq;
+    double *step;              // [C][T][n]
+    int32_t *nacc, *nsteps, *until;
+    const double *eps;         // replay: [C][T][n][d]  (nullptr -> Philox)
+    const double *logu;        // replay: [C][T][n]
+    uint64_t seed;
+    uint32_t sweep, chain_offset;
+    int32_t *accepted;         // optional [C][T][n]
+    double *ratio;             // optional [C][T][n]
+    unsigned int *flags;       // bit0 non-finite ratio, bit1 case-control out-of-bounds quirk
+};
+
+// eta of a directed dyad given dist and the two reciprocal radii
+//   sender s -> receiver r :  b_in * (1 - dist / r_r) + b_out * (1 - dist / r_s)
+__device__ __forceinline__ double eta_directed(double b_in, double b_out, double dist,
+                                               double rinv_recv, double rinv_send)
+{
+    return b_in * (1.0 - dist * rinv_recv) + b_out * (1.0 - dist * rinv_send);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-node pairwise sums for the proposal (xn) and the current position (xo) of node j in slice
+// t, executed by one warp.  Returns the two log-likelihoods (warp-uniform).
+// ---------------------------------------------------------------------------------------------
+template <int LK, int DM>
+__device__ __forceinline__ void node_loglik2(const NetView &net, const double *Xt /* [n][d] */,
+                                             const double *rinv /* [n] */, int chain, int t, int j,
+                                             const double (&xn)[DM], const double (&xo)[DM],
+                                             double b0, double b1, int lane, double &ll_new,
+                                             double &ll_old, unsigned int *flags)
+{
+    const int n = net.n, d = net.d;
+    if (LK == kUndirected) {
+        // K1 static_network_fast.pyx:17-44
+        const uint32_t *row = net.rowbits + ((size_t)t * n + j) * net.W;
+        double an = 0.0, ao = 0.0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const uint32_t w = __ldg(row + (base >> 5));
+            if (i < n && i != j) {
+                double xi[DM];
+                load_pos<DM>(Xt + (size_t)i * d, d, xi);
+                const double en = b0 - sqrt(sqdist<DM>(xi, xn, d));
+                const double eo = b0 - sqrt(sqdist<DM>(xi, xo, d));
+                if ((w >> lane) & 1u) { an += en; ao += eo; }
+                an -= log1pexp(en);
+                ao -= log1pexp(eo);
+            }
+        }
+        ll_new = warp_sum(an);
+        ll_old = warp_sum(ao);
+    } else if (LK == kDirected) {
+        // K2 directed_likelihoods_fast.pyx:46-80
+        const uint32_t *row = net.rowbits + ((size_t)t * n + j) * net.W;
+        const uint32_t *col = net.colbits + ((size_t)t * n + j) * net.W;
+        const double rj = rinv[j];
+        double an = 0.0, ao = 0.0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const uint32_t wr = __ldg(row + (base >> 5));
+            const uint32_t wc = __ldg(col + (base >> 5));
+            if (i < n && i != j) {
+                double xi[DM];
+                load_pos<DM>(Xt + (size_t)i * d, d, xi);
+                const double ri = rinv[i];
+                const bool y_ji = (wr >> lane) & 1u; // Y[node, i]: node sends, i receives
+                const bool y_ij = (wc >> lane) & 1u; // Y[i, node]: i sends, node receives
+#pragma unroll
+                for (int v = 0; v < 2; v++) {
+                    const double dist = sqrt(sqdist<DM>(xi, v == 0 ? xn : xo, d));
+                    const double e1 = eta_directed(b0, b1, dist, ri, rj);
+                    const double e2 = eta_directed(b0, b1, dist, rj, ri);
+                    double acc = (y_ji ? e1 : 0.0) - log1pexp(e1);
+                    acc += (y_ij ? e2 : 0.0) - log1pexp(e2);
+                    if (v == 0) an += acc; else ao += acc;
+                }
+            }
+        }
+        ll_new = warp_sum(an);
+        ll_old = warp_sum(ao);
+    } else {
+        // K3 directed_likelihoods_fast.pyx:83-182 (case-control estimator)
+        const size_t r = (size_t)t * n + j;
+        const int indeg = net.deg[r * 2 + 0], outdeg = net.deg[r * 2 + 1];
+        const int32_t *ie = net.in_edges + r * net.max_in;
+        const int32_t *oe = net.out_edges + r * net.max_out;
+        const size_t coff =
+            ((size_t)(net.ctrl_per_chain ? chain : 0) * net.T * n + r) * net.n_control;
+        const int32_t *ci = net.ctrl_in + coff;
+        const int32_t *co = net.ctrl_out + coff;
+        const double rj = rinv[j];
+        double e_n = 0.0, e_o = 0.0;     // edge terms
+        double ci_n = 0.0, ci_o = 0.0;   // control sums over the in lists
+        double co_n = 0.0, co_o = 0.0;   // control sums over the out lists
+        auto eta_pair = [&](int k, bool k_sends, double &vn, double &vo) {
+            double xk[DM];
+            load_pos<DM>(Xt + (size_t)k * d, d, xk);
+            const double rk = rinv[k];
+            const double dn = sqrt(sqdist<DM>(xk, xn, d));
+            const double dd = sqrt(sqdist<DM>(xk, xo, d));
+            const double r_recv = k_sends ? rj : rk, r_send = k_sends ? rk : rj;
+            vn = eta_directed(b0, b1, dn, r_recv, r_send);
+            vo = eta_directed(b0, b1, dd, r_recv, r_send);
+        };
+        for (int q = lane; q < indeg; q += 32) { // :108-119
+            double vn, vo;
+            eta_pair(ie[q], true, vn, vo);
+            e_n += vn - log1pexp(vn);
+            e_o += vo - log1pexp(vo);
+        }
+        for (int q = lane; q < outdeg; q += 32) { // :122-133
+            double vn, vo;
+            eta_pair(oe[q], false, vn, vo);
+            e_n += vn - log1pexp(vn);
+            e_o += vo - log1pexp(vo);
+        }
+        // usable controls = prefix of ctrl_in before its first -1 (:137; and :161, which tests the
+        // IN list while walking the OUT list)
+        int m = net.n_control;
+        for (int base = 0; base < net.n_control; base += 32) {
+            const int q = base + lane;
+            const bool stop = (q < net.n_control) && (ci[q] == -1);
+            const unsigned bal = __ballot_sync(kFull, stop);
+            if (bal) { m = base + __ffs(bal) - 1; break; }
+        }
+        int m_out = m;
+        for (int base = 0; base < m; base += 32) { // the reference reads X[-1] here: flag + stop
+            const int q = base + lane;
+            const bool bad = (q < m) && (co[q] < 0);
+            const unsigned bal = __ballot_sync(kFull, bad);
+            if (bal) {
+                m_out = base + __ffs(bal) - 1;
+                if (lane == 0) atomicOr(flags, 2u);
+                break;
+            }
+        }
+        for (int q = lane; q < m; q += 32) { // :136-152
+            double vn, vo;
+            eta_pair(ci[q], true, vn, vo);
+            ci_n += log1pexp(vn);
+            ci_o += log1pexp(vo);
+        }
+        for (int q = lane; q < m_out; q += 32) { // :160-176
+            double vn, vo;
+            eta_pair(co[q], false, vn, vo);
+            co_n += log1pexp(vn);
+            co_o += log1pexp(vo);
+        }
+        e_n = warp_sum(e_n); e_o = warp_sum(e_o);
+        ci_n = warp_sum(ci_n); ci_o = warp_sum(ci_o);
+        co_n = warp_sum(co_n); co_o = warp_sum(co_o);
+        const double adj_in = (double)(n - indeg - 1) / (double)m;       // :155
+        const double adj_out = (double)(n - outdeg - 1) / (double)m_out; // :179
+        ll_new = (e_n - adj_in * ci_n) - adj_out * co_n;
+        ll_old = (e_o - adj_in * ci_o) - adj_out * co_o;
+    }
+}
+
+// closure `logp` = loglik minus the prior terms, subtracted one after the other
+// (sample_latent_positions.py:131-140 LSM, :187-199 mixture).  xprev/xnext may be null at the ends.
+template <int DM>
+__device__ __forceinline__ double apply_prior(const SweepParams &p, int c, int t, int j,
+                                              double loglik, const double (&x)[DM],
+                                              const double (&xprev)[DM], const double (&xnext)[DM])
+{
+    const int d = p.net.d, T = p.net.T, n = p.net.n;
+    double diff[DM];
+    if (p.prior == 0) {
+        if (t == 0) {
+            loglik = __dsub_rn(loglik, half_sumsq_over<DM>(x, d, p.tau_sq));
+        } else {
+#pragma unroll
+            for (int k = 0; k < DM; k++) diff[k] = (k < d) ? __dsub_rn(x[k], xprev[k]) : 0.0;
+            loglik = __dsub_rn(loglik, half_sumsq_over<DM>(diff, d, p.sigma_sq));
+        }
+        if (t < T - 1) {
+#pragma unroll
+            for (int k = 0; k < DM; k++) diff[k] = (k < d) ? __dsub_rn(xnext[k], x[k]) : 0.0;
+            loglik = __dsub_rn(loglik, half_sumsq_over<DM>(diff, d, p.sigma_sq));
+        }
+    } else {
+        const double lm = p.lambda[c], oml = __dsub_rn(1.0, lm);
+        const int32_t *z = p.z + (size_t)c * T * n;
+        const double *mu = p.mu + (size_t)c * p.K * d;
+        const double *sg = p.sigma + (size_t)c * p.K;
+        const int zc = z[(size_t)t * n + j];
+        if (t == 0) {
+#pragma unroll
+            for (int k = 0; k < DM; k++) diff[k] = (k < d) ? __dsub_rn(x[k], mu[zc * d + k]) : 0.0;
+        } else {
+#pragma unroll
+            for (int k = 0; k < DM; k++)
+                diff[k] = (k < d) ? __dsub_rn(__dsub_rn(x[k], __dmul_rn(oml, xprev[k])),
+                                              __dmul_rn(lm, mu[zc * d + k]))
+                                  : 0.0;
+        }
+        loglik = __dsub_rn(loglik, half_sumsq_over<DM>(diff, d, sg[zc]));
+        if (t < T - 1) {
+            const int zn = z[(size_t)(t + 1) * n + j];
+#pragma unroll
+            for (int k = 0; k < DM; k++)
+                diff[k] = (k < d) ? __dsub_rn(__dsub_rn(xnext[k], __dmul_rn(oml, x[k])),
+                                              __dmul_rn(lm, mu[zn * d + k]))
+                                  : 0.0;
+            loglik = __dsub_rn(loglik, half_sumsq_over<DM>(diff, d, sg[zn]));
+        }
+    }
+    return loglik;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_sweep: one latent-position sweep of every chain.
+// grid = C chains, block = 32 * min(T, 16) threads, dynamic smem = [T*n*d doubles if XS] + T ints
+// ---------------------------------------------------------------------------------------------
+template <int LK, int D, bool XS>
+__global__ void __launch_bounds__(512) k_sweep(const SweepParams p)
+{
+    constexpr int DM = (D == 0) ? kMaxD : D;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = p.net.T, n = p.net.n, d = (D == 0) ? p.net.d : D;
+    const int c = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const size_t chain_elems = (size_t)T * n * d;
+    double *Xg = p.X + (size_t)c * chain_elems;
+    double *Xc;
+    volatile int *progress;
+    if (XS) {
+        Xc = reinterpret_cast<double *>(smem_raw);
+        progress = reinterpret_cast<volatile int *>(smem_raw + chain_elems * sizeof(double));
+        for (size_t e = threadIdx.x; e < chain_elems; e += blockDim.x) Xc[e] = Xg[e];
+    } else {
+        Xc = Xg;
+        progress = reinterpret_cast<volatile int *>(smem_raw);
+    }
+    for (int t = threadIdx.x; t < T; t += blockDim.x) progress[t] = 0;
+    __syncthreads();
+
+    const double b0 = p.intercept[c * 2 + 0], b1 = p.intercept[c * 2 + 1];
+    const double *rinv = (LK == kUndirected) ? nullptr : p.rinv + (size_t)c * n;
+    const uint32_t chain_id = (uint32_t)c + p.chain_offset;
+
+    for (int t = warp; t < T; t += nwarps) {
+        double *Xt = Xc + (size_t)t * n * d;
+        for (int j = 0; j < n; j++) {
+            const size_t site = (size_t)t * n + j;
+            const size_t gs = (size_t)c * T * n + site;
+            // ---- proposal (metropolis.py:44): x = x0 + step * randn(d), separate roundings
+            double x0[DM], x[DM], eps[DM], logu;
+            load_pos<DM>(Xt + (size_t)j * d, d, x0);
+            const double step = p.step[gs];
+            if (p.eps) {
+#pragma unroll
+                for (int k = 0; k < DM; k++) eps[k] = (k < d) ? p.eps[gs * d + k] : 0.0;
+                logu = p.logu[gs];
+            } else {
+                latent_draws<DM>(p.seed, (uint32_t)site, p.sweep, chain_id, d, eps, logu);
+            }
+#pragma unroll
+            for (int k = 0; k < DM; k++) x[k] = (k < d) ? __dadd_rn(x0[k], __dmul_rn(step, eps[k])) : 0.0;
+
+            // ---- likelihood at x and x0: one pass over the row
+            double ll_new, ll_old;
+            node_loglik2<LK, DM>(p.net, Xt, rinv, c, t, j, x, x0, b0, b1, lane, ll_new, ll_old,
+                                 p.flags);
+
+            // ---- wavefront: X[t-1, j] must be this sweep's value
+            if (t > 0) {
+                if (lane == 0)
+                    while (progress[t - 1] <= j) { /* spin on shared memory */ }
+                __threadfence_block();
+                __syncwarp();
+            }
+            double xp[DM], xnx[DM];
+#pragma unroll
+            for (int k = 0; k < DM; k++) { xp[k] = 0.0; xnx[k] = 0.0; }
+            if (t > 0) {
+                const volatile double *q = Xc + ((size_t)(t - 1) * n + j) * d;
+#pragma unroll
+                for (int k = 0; k < DM; k++) if (k < d) xp[k] = q[k];
+            }
+            if (t < T - 1) {
+                const volatile double *q = Xc + ((size_t)(t + 1) * n + j) * d;
+#pragma unroll
+                for (int k = 0; k < DM; k++) if (k < d) xnx[k] = q[k];
+            }
+            const double lp_new = apply_prior<DM>(p, c, t, j, ll_new, x, xp, xnx);
+            const double lp_old = apply_prior<DM>(p, c, t, j, ll_old, x0, xp, xnx);
+            const double ratio = __dsub_rn(lp_new, lp_old);
+            const int acc = (logu >= ratio) ? 0 : 1; // metropolis.py:50 (NaN ratio accepts)
+            if (lane == 0) {
+                if (acc) {
+#pragma unroll
+                    for (int k = 0; k < DM; k++) if (k < d) Xt[(size_t)j * d + k] = x[k];
+                }
+                double st = step;
+                int na = p.nacc[gs], ns = p.nsteps[gs], un = p.until[gs];
+                metropolis_bookkeep(st, na, ns, un, p.tune, p.tune_interval, acc, false);
+                p.step[gs] = st; p.nacc[gs] = na; p.nsteps[gs] = ns; p.until[gs] = un;
+                if (p.accepted) p.accepted[gs] = acc;
+                if (p.ratio) p.ratio[gs] = ratio;
+                if (!(ratio == ratio) || ratio - ratio != 0.0) atomicOr(p.flags, 1u);
+                __threadfence_block();
+                progress[t] = j + 1;
+            }
+            __syncwarp();
+        }
+    }
+    if (XS) {
+        __syncthreads();
+        for (size_t e = threadIdx.x; e < chain_elems; e += blockDim.x) Xg[e] = Xc[e];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// parity probe: per-node log-likelihood at the current state, one warp per (c, t, j)
+// ---------------------------------------------------------------------------------------------
+template <int LK, int D>
+__global__ void k_partial(const SweepParams p, double *out)
+{
+    constexpr int DM = (D == 0) ? kMaxD : D;
+    const int T = p.net.T, n = p.net.n, d = (D == 0) ? p.net.d : D;
+    const size_t gw = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= (size_t)p.C * T * n) return;
+    const int c = (int)(gw / ((size_t)T * n));
+    const int t = (int)((gw / n) % T), j = (int)(gw % n);
+    const double *Xt = p.X + ((size_t)c * T + t) * n * d;
+    double x0[DM];
+    load_pos<DM>(Xt + (size_t)j * d, d, x0);
+    double a, b;
+    node_loglik2<LK, DM>(p.net, Xt, (LK == kUndirected) ? nullptr : p.rinv + (size_t)c * n, c, t,
+                         j, x0, x0, p.intercept[c * 2], p.intercept[c * 2 + 1], lane, a, b,
+                         p.flags);
+    if (lane == 0) out[gw] = b;
+}
+
+// the raw Philox draws of the next native sweep (parity probe for the device RNG path)
+template <int D>
+__global__ void k_debug_draws(const SweepParams p, double *eps_out, double *logu_out)
+{
+    constexpr int DM = (D == 0) ? kMaxD : D;
+    const int T = p.net.T, n = p.net.n, d = (D == 0) ? p.net.d : D;
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)p.C * T * n) return;
+    const int c = (int)(g / ((size_t)T * n));
+    const uint32_t site = (uint32_t)(g % ((size_t)T * n));
+    double eps[DM], logu;
+    latent_draws<DM>(p.seed, site, p.sweep, (uint32_t)c + p.chain_offset, d, eps, logu);
+    for (int k = 0; k < d; k++) eps_out[g * d + k] = eps[k];
+    logu_out[g] = logu;
+}
+
+// ---------------------------------------------------------------------------------------------
+// X -= np.mean(X, axis=(0,1))  (lsm.py:501): serial accumulation per column = numpy's order
+// ---------------------------------------------------------------------------------------------
+__global__ void k_center(double *X, int T, int n, int d)
+{
+    __shared__ double mean[kMaxD];
+    double *Xc = X + (size_t)blockIdx.x * T * n * d;
+    const size_t rows = (size_t)T * n;
+    if ((int)threadIdx.x < d) {
+        double s = 0.0;
+        for (size_t r = 0; r < rows; r++) s = __dadd_rn(s, Xc[r * d + threadIdx.x]);
+        mean[threadIdx.x] = __ddiv_rn(s, (double)rows);
+    }
+    __syncthreads();
+    for (size_t e = threadIdx.x; e < rows * d; e += blockDim.x)
+        Xc[e] = __dsub_rn(Xc[e], mean[e % d]);
+}
+
+__global__ void k_rinv(const double *radii, double *rinv, size_t total)
+{
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < total) rinv[g] = 1.0 / radii[g];
+}
+
+// ---------------------------------------------------------------------------------------------
+// adjacency bit-packing from the dense fp64 Y the reference's fit() takes (lsm.py:319-343)
+// one warp per 32-column word, ballot over the lanes; bad[0] set if an entry is not 0/1
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack_rows(const double *Y, int n, int W, uint32_t *bits, int *bad)
+{
+    // Y: one time slice [n][n]; bits [n][W]
+    const size_t gw = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= (size_t)n * W) return;
+    const int i = (int)(gw / W), w = (int)(gw % W);
+    const int j = w * 32 + lane;
+    double v = 0.0;
+    if (j < n) v = Y[(size_t)i * n + j];
+    if (v != 0.0 && v != 1.0) *bad = 1;
+    const unsigned word = __ballot_sync(kFull, v == 1.0);
+    if (lane == 0) bits[(size_t)i * W + w] = word;
+}
+
+__global__ void k_pack_cols(const double *Y, int n, int W, uint32_t *bits)
+{
+    // bits[i][w] bit b = Y[w*32+b][i]; thread per (w, i) with i fastest (coalesced reads)
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)n * W) return;
+    const int i = (int)(g % n), w = (int)(g / n);
+    uint32_t word = 0;
+    for (int b = 0; b < 32; b++) {
+        const int j = w * 32 + b;
+        if (j < n && Y[(size_t)j * n + i] == 1.0) word |= (1u << b);
+    }
+    bits[(size_t)i * W + w] = word;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Full-network log-likelihood, two parameter variants per pass.
+//   variant v uses intercepts bvar[c][v][0..1] and reciprocal radii rinv_v[c][:]
+// grid = (T * tiles, C), block = 256; CTA (t, tile) stages X[c, t] in shared memory and its warps
+// take rows i = tile + k * tiles.  Output: partial[c][blockIdx.x][v].
+// ---------------------------------------------------------------------------------------------
+struct FullParams {
+    NetView net;
+    int C, tiles;
+    const double *X;        // [C][T][n][d]
+    const double *bvar;     // [C][2][2]
+    const double *rinv0;    // [C][n] variant 0
+    const double *rinv1;    // [C][n] variant 1
+    double *partial;        // [C][T*tiles][2]
+    unsigned int *flags;
+};
+
+template <int LK, int D>
+__global__ void __launch_bounds__(256) k_full(const FullParams p)
+{
+    constexpr int DM = (D == 0) ? kMaxD : D;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[2][8];
+    const int T = p.net.T, n = p.net.n, d = (D == 0) ? p.net.d : D, W = p.net.W;
+    const int c = blockIdx.y;
+    const int t = blockIdx.x / p.tiles, tile = blockIdx.x % p.tiles;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const double *Xg = p.X + ((size_t)c * T + t) * n * d;
+    const double *Xt;
+    if (LK != kCaseControl) {
+        double *Xs = reinterpret_cast<double *>(smem_raw);
+        for (int e = threadIdx.x; e < n * d; e += blockDim.x) Xs[e] = Xg[e];
+        __syncthreads();
+        Xt = Xs;
+    } else {
+        Xt = Xg;
+    }
+    const double *bv = p.bvar + (size_t)c * 4;
+    const double b00 = bv[0], b01 = bv[1], b10 = bv[2], b11 = bv[3];
+    const double *r0 = p.rinv0 ? p.rinv0 + (size_t)c * n : nullptr;
+    const double *r1 = p.rinv1 ? p.rinv1 + (size_t)c * n : nullptr;
+    double a0 = 0.0, a1 = 0.0;
+
+    for (int i = tile + warp * p.tiles; i < n; i += nwarps * p.tiles) {
+        double xi[DM];
+        load_pos<DM>(Xt + (size_t)i * d, d, xi);
+        if (LK == kUndirected) {
+            // K5 network_likelihoods.py:26-33: pairs j > i, eta = beta - dist
+            const uint32_t *row = p.net.rowbits + ((size_t)t * n + i) * W;
+            for (int base = ((i + 1) >> 5) << 5; base < n; base += 32) {
+                const int j = base + lane;
+                const uint32_t w = __ldg(row + (base >> 5));
+                if (j < n && j > i) {
+                    double xj[DM];
+                    load_pos<DM>(Xt + (size_t)j * d, d, xj);
+                    const double dist = sqrt(sqdist<DM>(xj, xi, d));
+                    const double e0 = b00 - dist, e1 = b10 - dist;
+                    if ((w >> lane) & 1u) { a0 += e0; a1 += e1; }
+                    a0 -= log1pexp(e0);
+                    a1 -= log1pexp(e1);
+                }
+            }
+        } else if (LK == kDirected) {
+            // K4 directed_likelihoods_fast.pyx:185-205: ordered pairs, visited as unordered pairs
+            // j > i with both directions sharing one distance
+            const uint32_t *row = p.net.rowbits + ((size_t)t * n + i) * W;
+            const uint32_t *col = p.net.colbits + ((size_t)t * n + i) * W;
+            const double ri0 = r0[i], ri1 = r1[i];
+            for (int base = ((i + 1) >> 5) << 5; base < n; base += 32) {
+                const int j = base + lane;
+                const uint32_t wr = __ldg(row + (base >> 5));
+                const uint32_t wc = __ldg(col + (base >> 5));
+                if (j < n && j > i) {
+                    double xj[DM];
+                    load_pos<DM>(Xt + (size_t)j * d, d, xj);
+                    const double dist = sqrt(sqdist<DM>(xj, xi, d));
+                    const bool y_ij = (wr >> lane) & 1u, y_ji = (wc >> lane) & 1u;
+                    {
+                        const double rj = r0[j];
+                        const double e_ij = eta_directed(b00, b01, dist, rj, ri0);
+                        const double e_ji = eta_directed(b00, b01, dist, ri0, rj);
+                        a0 += (y_ij ? e_ij : 0.0) - log1pexp(e_ij);
+                        a0 += (y_ji ? e_ji : 0.0) - log1pexp(e_ji);
+                    }
+                    {
+                        const double rj = r1[j];
+                        const double e_ij = eta_directed(b10, b11, dist, rj, ri1);
+                        const double e_ji = eta_directed(b10, b11, dist, ri1, rj);
+                        a1 += (y_ij ? e_ij : 0.0) - log1pexp(e_ij);
+                        a1 += (y_ji ? e_ji : 0.0) - log1pexp(e_ji);
+                    }
+                }
+            }
+        } else {
+            // K6 directed_likelihoods_fast.pyx:208-270: out-edges and out-controls only
+            const size_t r = (size_t)t * n + i;
+            const int outdeg = p.net.deg[r * 2 + 1];
+            const int32_t *oe = p.net.out_edges + r * p.net.max_out;
+            const int32_t *co = p.net.ctrl_out +
+                                ((size_t)(p.net.ctrl_per_chain ? c : 0) * T * n + r) * p.net.n_control;
+            const double ri0 = r0[i], ri1 = r1[i];
+            double e0 = 0.0, e1 = 0.0, c0 = 0.0, c1 = 0.0;
+            for (int q = lane; q < outdeg; q += 32) {
+                const int k = oe[q];
+                double xk[DM];
+                load_pos<DM>(Xt + (size_t)k * d, d, xk);
+                const double dist = sqrt(sqdist<DM>(xk, xi, d));
+                const double v0 = eta_directed(b00, b01, dist, r0[k], ri0);
+                const double v1 = eta_directed(b10, b11, dist, r1[k], ri1);
+                e0 += v0 - log1pexp(v0);
+                e1 += v1 - log1pexp(v1);
+            }
+            int m = p.net.n_control;
+            for (int base = 0; base < p.net.n_control; base += 32) {
+                const int q = base + lane;
+                const bool stop = (q < p.net.n_control) && (co[q] == -1);
+                const unsigned bal = __ballot_sync(kFull, stop);
+                if (bal) { m = base + __ffs(bal) - 1; break; }
+            }
+            for (int q = lane; q < m; q += 32) {
+                const int k = co[q];
+                double xk[DM];
+                load_pos<DM>(Xt + (size_t)k * d, d, xk);
+                const double dist = sqrt(sqdist<DM>(xk, xi, d));
+                c0 += log1pexp(eta_directed(b00, b01, dist, r0[k], ri0));
+                c1 += log1pexp(eta_directed(b10, b11, dist, r1[k], ri1));
+            }
+            e0 = warp_sum(e0); e1 = warp_sum(e1);
+            c0 = warp_sum(c0); c1 = warp_sum(c1);
+            if (lane == 0) {
+                const double adj = (double)(n - outdeg - 1) / (double)m;
+                a0 += e0 - adj * c0;
+                a1 += e1 - adj * c1;
+            }
+        }
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    if (lane == 0) { red[0][warp] = a0; red[1][warp] = a1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; w++) s += red[threadIdx.x][w];
+        p.partial[((size_t)c * gridDim.x + blockIdx.x) * 2 + threadIdx.x] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scalar MH on the full-network likelihood: propose / finalize (one thread per chain)
+// ---------------------------------------------------------------------------------------------
+struct ScalarMH {
+    int C, which, nblk, tune, tune_interval;
+    double *intercept;       // [C][2]
+    double *bvar;            // [C][2][2]
+    double *prop;            // [C]
+    const double *partial;   // [C][nblk][2]
+    double prior_mean, prior_var;
+    double *step;            // [C][2]
+    int32_t *nacc, *nsteps, *until;
+    const double *eps, *logu;   // replay [C][m] with stride m (nullptr -> Philox)
+    int m;
+    uint64_t seed;
+    uint32_t sweep, chain_offset, site;
+    int32_t *accepted;       // optional [C][m]
+    double *ratio;           // optional [C][m]
+    double *ll_out;          // optional [C][2] (variant sums) for probes
+    unsigned int *flags;
+};
+
+__global__ void k_intercept_propose(const ScalarMH p)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.C) return;
+    const double b0 = p.intercept[c * 2], b1 = p.intercept[c * 2 + 1];
+    double eps;
+    if (p.eps) {
+        eps = p.eps[(size_t)c * p.m + p.which];
+    } else {
+        double z0, z1;
+        box_muller(philox_u2(p.seed, p.site + p.which, p.sweep, (uint32_t)c + p.chain_offset,
+                             kRngIntercept, 1), z0, z1);
+        eps = z0;
+    }
+    const double x0 = p.which == 0 ? b0 : b1;
+    const double x = __dadd_rn(x0, __dmul_rn(p.step[c * 2 + p.which], eps));
+    p.prop[c] = x;
+    double *bv = p.bvar + (size_t)c * 4;
+    bv[0] = p.which == 0 ? x : b0; bv[1] = p.which == 1 ? x : b1; // variant 0: proposal
+    bv[2] = b0; bv[3] = b1;                                       // variant 1: current
+}
+
+__global__ void k_intercept_finalize(const ScalarMH p)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.C) return;
+    double s0 = 0.0, s1 = 0.0;
+    const double *pp = p.partial + (size_t)c * p.nblk * 2;
+    for (int b = 0; b < p.nblk; b++) { s0 += pp[b * 2]; s1 += pp[b * 2 + 1]; }
+    const double x = p.prop[c], x0 = p.intercept[c * 2 + p.which];
+    // sample_coefficients.py:39-41 / :84-85:  loglik -= (x - prior) ** 2 / (2 * variance)
+    double df = __dsub_rn(x, p.prior_mean);
+    const double lp_new = __dsub_rn(s0, __ddiv_rn(__dmul_rn(df, df), __dmul_rn(2.0, p.prior_var)));
+    df = __dsub_rn(x0, p.prior_mean);
+    const double lp_old = __dsub_rn(s1, __ddiv_rn(__dmul_rn(df, df), __dmul_rn(2.0, p.prior_var)));
+    const double ratio = __dsub_rn(lp_new, lp_old);
+    double logu;
+    if (p.logu) logu = p.logu[(size_t)c * p.m + p.which];
+    else logu = log(philox_u2(p.seed, p.site + p.which, p.sweep, (uint32_t)c + p.chain_offset,
+                              kRngIntercept, 0).a);
+    const int acc = (logu >= ratio) ? 0 : 1;
+    if (acc) p.intercept[c * 2 + p.which] = x;
+    const int o = c * 2 + p.which;
+    double st = p.step[o];
+    int na = p.nacc[o], ns = p.nsteps[o], un = p.until[o];
+    metropolis_bookkeep(st, na, ns, un, p.tune, p.tune_interval, acc, false);
+    p.step[o] = st; p.nacc[o] = na; p.nsteps[o] = ns; p.until[o] = un;
+    if (p.accepted) p.accepted[(size_t)c * p.m + p.which] = acc;
+    if (p.ratio) p.ratio[(size_t)c * p.m + p.which] = ratio;
+    if (p.ll_out) { p.ll_out[c * 2] = s0; p.ll_out[c * 2 + 1] = s1; }
+    if (!(ratio == ratio) || ratio - ratio != 0.0) atomicOr(p.flags, 1u);
+}
+
+// current-state probe: bvar = current intercepts for both variants
+__global__ void k_bvar_current(int C, const double *intercept, double *bvar)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    bvar[c * 4 + 0] = bvar[c * 4 + 2] = intercept[c * 2];
+    bvar[c * 4 + 1] = bvar[c * 4 + 3] = intercept[c * 2 + 1];
+}
+
+__global__ void k_sum_partials(int C, int nblk, const double *partial, double *out2)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s0 = 0.0, s1 = 0.0;
+    for (int b = 0; b < nblk; b++) { s0 += partial[((size_t)c * nblk + b) * 2]; s1 += partial[((size_t)c * nblk + b) * 2 + 1]; }
+    out2[c * 2] = s0; out2[c * 2 + 1] = s1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// radii MH (sample_coefficients.py:91-121 + metropolis.py:57-82): one CTA per chain finalises:
+// Hastings correction log Dir(r; s r') - log Dir(r'; s r), accept, copy
+// ---------------------------------------------------------------------------------------------
+struct RadiiMH {
+    int C, n, nblk, tune, tune_interval;
+    double *radii, *rinv;            // [C][n] current
+    const double *prop, *prop_rinv;  // [C][n] proposal
+    const double *partial;           // [C][nblk][2]  variant 0 = proposal, 1 = current
+    double *step;                    // [C]
+    int32_t *nacc, *nsteps, *until;
+    const double *logu;              // replay [C] or nullptr
+    uint64_t seed;
+    uint32_t sweep, chain_offset, site;
+    int32_t *accepted;
+    double *ratio;
+    unsigned int *flags;
+};
+
+__device__ __forceinline__ double block_sum(double v, double *sh)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < nw; w++) s += sh[w];
+    return s;
+}
+
+__global__ void __launch_bounds__(256) k_radii_finalize(const RadiiMH p)
+{
+    __shared__ double sh[8];
+    __shared__ int s_acc;
+    const int c = blockIdx.x, n = p.n;
+    double *r = p.radii + (size_t)c * n;
+    const double *q = p.prop + (size_t)c * n;
+    const double s = p.step[c];
+    // scipy.stats.dirichlet.logpdf(x, alpha) = -[sum lgamma(alpha) - lgamma(sum alpha)]
+    //                                          + sum (alpha - 1) log x
+    double sa_f = 0, sl_f = 0, sx_f = 0; // forward:  x = r (current), alpha = s * q
+    double sa_b = 0, sl_b = 0, sx_b = 0; // backward: x = q (proposal), alpha = s * r
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double af = s * q[i], ab = s * r[i];
+        sa_f += af; sl_f += lgamma(af); sx_f += (af - 1.0) * log(r[i]);
+        sa_b += ab; sl_b += lgamma(ab); sx_b += (ab - 1.0) * log(q[i]);
+    }
+    sa_f = block_sum(sa_f, sh); sl_f = block_sum(sl_f, sh); sx_f = block_sum(sx_f, sh);
+    sa_b = block_sum(sa_b, sh); sl_b = block_sum(sl_b, sh); sx_b = block_sum(sx_b, sh);
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0;
+        const double *pp = p.partial + (size_t)c * p.nblk * 2;
+        for (int b = 0; b < p.nblk; b++) { s0 += pp[b * 2]; s1 += pp[b * 2 + 1]; }
+        const double lf = -(sl_f - lgamma(sa_f)) + sx_f;
+        const double lb = -(sl_b - lgamma(sa_b)) + sx_b;
+        const double ratio = (s0 - s1) + (lf - lb);
+        double logu;
+        if (p.logu) logu = p.logu[c];
+        else logu = log(philox_u2(p.seed, p.site, p.sweep, (uint32_t)c + p.chain_offset, kRngRadii, 0).a);
+        const int acc = (logu >= ratio) ? 0 : 1;
+        s_acc = acc;
+        double st = s;
+        int na = p.nacc[c], ns = p.nsteps[c], un = p.until[c];
+        metropolis_bookkeep(st, na, ns, un, p.tune, p.tune_interval, acc, true);
+        p.step[c] = st; p.nacc[c] = na; p.nsteps[c] = ns; p.until[c] = un;
+        if (p.accepted) p.accepted[c] = acc;
+        if (p.ratio) p.ratio[c] = ratio;
+        if (!(ratio == ratio) || ratio - ratio != 0.0) atomicOr(p.flags, 1u);
+    }
+    __syncthreads();
+    if (s_acc) {
+        double *ri = p.rinv + (size_t)c * n;
+        const double *qi = p.prop_rinv + (size_t)c * n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { r[i] = q[i]; ri[i] = qi[i]; }
+    }
+}
+
+// native Dirichlet proposal r' ~ Dir(s * r) via Marsaglia-Tsang gamma variates (one thread per
+// node, Philox stream per (chain, node)); zero guard of metropolis.py:65-67
+__device__ inline double gamma_mt(double shape, uint64_t seed, uint32_t site, uint32_t sweep,
+                                  uint32_t chain)
+{
+    uint32_t blk = 1;
+    double boost = 1.0;
+    if (shape < 1.0) {
+        const U2 u = philox_u2(seed, site, sweep, chain, kRngRadii, blk++);
+        boost = pow(u.a, 1.0 / shape);
+        shape += 1.0;
+    }
+    const double dd = shape - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * dd);
+    for (int it = 0; it < 64; it++) {
+        double z0, z1;
+        box_muller(philox_u2(seed, site, sweep, chain, kRngRadii, blk++), z0, z1);
+        const U2 u = philox_u2(seed, site, sweep, chain, kRngRadii, blk++);
+        double v = 1.0 + cc * z0;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        if (log(u.a) < 0.5 * z0 * z0 + dd - dd * v + dd * log(v)) return boost * dd * v;
+    }
+    return boost * dd;
+}
+
+__global__ void __launch_bounds__(256) k_radii_propose(int n, const double *radii,
+                                                       const double *step, double *prop,
+                                                       double *prop_rinv, uint64_t seed,
+                                                       uint32_t sweep, uint32_t chain_offset,
+                                                       uint32_t site0)
+{
+    __shared__ double sh[8];
+    __shared__ int any_zero;
+    const int c = blockIdx.x;
+    const double *r = radii + (size_t)c * n;
+    double *q = prop + (size_t)c * n;
+    if (threadIdx.x == 0) any_zero = 0;
+    double tot = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double g = gamma_mt(step[c] * r[i], seed, site0 + 1 + i, sweep,
+                                  (uint32_t)c + chain_offset);
+        q[i] = g;
+        tot += g;
+    }
+    tot = block_sum(tot, sh);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        q[i] = q[i] / tot;
+        if (q[i] == 0.0) any_zero = 1;
+    }
+    __syncthreads();
+    if (any_zero) {
+        double t2 = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { q[i] += 1e-5; t2 += q[i]; }
+        t2 = block_sum(t2, sh);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) q[i] /= t2;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) prop_rinv[(size_t)c * n + i] = 1.0 / q[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_ffbs: HDP-HMM label block sampler, one warp per (chain, node)
+// (sample_labels.py:134-190 + gaussian_likelihood_fast.pyx:17-54)
+// dynamic smem per warp: (T*K + 3*K) doubles
+// ---------------------------------------------------------------------------------------------
+struct LabelParams {
+    int C, T, n, d, K;
+    const double *X;        // [C][T][n][d]
+    const double *mu;       // [C][K][d]
+    const double *sigma;    // [C][K]
+    const double *lambda;   // [C]
+    const double *w;        // [C][T][K][K]
+    const double *U;        // replay [C][n][T] or nullptr
+    uint64_t seed;
+    uint32_t sweep, chain_offset;
+    int32_t *z;             // [C][T][n]  out
+    double *ncount;         // [C][T][K][K] out (zeroed by the caller)
+    int32_t *nk;            // [C][T][K]  out (zeroed by the caller)
+    double *lik_out;        // optional probe [C][n][T][K]
+    int sample;             // 0: emission densities only
+};
+
+// numpy pairwise_sum restricted to n <= 128 (K <= 128)
+__device__ inline double np_sum_k(const double *a, int n)
+{
+    if (n < 8) {
+        double r = -0.0;
+        for (int i = 0; i < n; i++) r = __dadd_rn(r, a[i]);
+        return r;
+    }
+    double r[8];
+    for (int k = 0; k < 8; k++) r[k] = a[k];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int k = 0; k < 8; k++) r[k] = __dadd_rn(r[k], a[i + k]);
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; i++) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
+__global__ void __launch_bounds__(128) k_ffbs(const LabelParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = p.T, n = p.n, d = p.d, K = p.K;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t gw = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (gw >= (size_t)p.C * n) return;
+    const int c = (int)(gw / n), i = (int)(gw % n);
+    double *pm = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (T * K + 3 * K);
+    double *bw0 = pm + T * K, *bw1 = bw0 + K, *cdf = bw1 + K;
+    const double *X = p.X + (size_t)c * T * n * d;
+    const double *mu = p.mu + (size_t)c * K * d;
+    const double *sg = p.sigma + (size_t)c * K;
+    const double *w = p.w + (size_t)c * T * K * K;
+    const double lm = p.lambda[c], oml = __dsub_rn(1.0, lm);
+
+    // K7: emission densities exp(loglik), un-normalised (normalize=False, sample_labels.py:159)
+    for (int idx = lane; idx < T * K; idx += 32) {
+        const int t = idx / K, k = idx % K;
+        const double *x = X + ((size_t)t * n + i) * d;
+        const double *xp = X + ((size_t)(t > 0 ? t - 1 : 0) * n + i) * d;
+        double sum_sq = 0.0;
+        for (int q = 0; q < d; q++) {
+            const double mean = (t == 0) ? mu[k * d + q]
+                                         : __dadd_rn(__dmul_rn(lm, mu[k * d + q]),
+                                                     __dmul_rn(oml, xp[q]));
+            const double df = __dsub_rn(x[q], mean);
+            sum_sq = __dadd_rn(sum_sq, __dmul_rn(df, df));
+        }
+        const double var = sg[k];
+        sum_sq = __dmul_rn(sum_sq, __dmul_rn(0.5, __ddiv_rn(1.0, var)));
+        const double ll = __dsub_rn(
+            __dmul_rn(__dmul_rn(-0.5, (double)d), log(__dmul_rn(6.283185307179586, var))), sum_sq);
+        const double L = exp(ll);
+        pm[idx] = L;
+        if (p.lik_out) p.lik_out[(((size_t)c * n + i) * T + t) * K + k] = L;
+    }
+    __syncwarp();
+    if (!p.sample) return;
+
+    // backward messages (:164-169); bwds_msg[T-1] is all ones (allocated once, never written)
+    double *bcur = bw0, *bprev = bw1;
+    for (int k = lane; k < K; k += 32) bcur[k] = 1.0;
+    __syncwarp();
+    for (int t = T - 1; t > 0; t--) {
+        for (int k = lane; k < K; k += 32) pm[t * K + k] = __dmul_rn(pm[t * K + k], bcur[k]);
+        __syncwarp();
+        for (int j = lane; j < K; j += 32) {
+            const double *wr = w + ((size_t)t * K + j) * K;
+            double s = 0.0;
+            for (int k = 0; k < K; k++) s = __dadd_rn(s, __dmul_rn(wr[k], pm[t * K + k]));
+            bprev[j] = s;
+        }
+        __syncwarp();
+        const double tot = np_sum_k(bprev, K);
+        __syncwarp();
+        for (int j = lane; j < K; j += 32) bprev[j] = __ddiv_rn(bprev[j], tot);
+        __syncwarp();
+        double *tmp = bcur; bcur = bprev; bprev = tmp;
+    }
+    for (int k = lane; k < K; k += 32) pm[k] = __dmul_rn(pm[k], bcur[k]);
+    __syncwarp();
+
+    // forward sampling (:173-188); cumsum and the comparison are serial, lane 0
+    if (lane == 0) {
+        int zp = 0;
+        for (int t = 0; t < T; t++) {
+            const double *wr = (t == 0) ? w : w + ((size_t)t * K + zp) * K;
+            double cs = 0.0;
+            for (int k = 0; k < K; k++) {
+                const double pr = __dmul_rn(wr[k], pm[t * K + k]);
+                cs = (k == 0) ? pr : __dadd_rn(cs, pr);
+                cdf[k] = cs;
+            }
+            double U;
+            if (p.U) U = p.U[((size_t)c * n + i) * T + t];
+            else U = philox_u2(p.seed, (uint32_t)(i * T + t), p.sweep, (uint32_t)c + p.chain_offset,
+                               kRngLabels, 0).a;
+            const double u = __dmul_rn(cdf[K - 1], U);
+            int zz = 0;
+            for (int k = 0; k < K; k++) zz += (u > cdf[k]) ? 1 : 0;
+            if (zz >= K) zz = K - 1;
+            p.z[((size_t)c * T + t) * n + i] = zz;
+            if (t == 0) atomicAdd(&p.ncount[(size_t)c * T * K * K + zz], 1.0);
+            else atomicAdd(&p.ncount[(((size_t)c * T + t) * K + zp) * K + zz], 1.0);
+            atomicAdd(&p.nk[((size_t)c * T + t) * K + zz], 1);
+            zp = zz;
+        }
+    }
+}
+
+} // namespace dlsm

@@ -1,0 +1,192 @@
+/*
+ * dlsm.h -- C-ABI of libdlsm.so: the B200 (sm_100a) implementation of dynetlsm's blocked
+ * Metropolis-Hastings-within-Gibbs hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own for
+ * this path -- its "native boundary" is Python -> Cython `def` functions on typed memoryviews --
+ * so each entry point below names the reference interface it replaces (paths relative to the
+ * reference root).  The binding a maintainer would add to the reference is a ctypes stub; see
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every array is C-contiguous; fp64 unless noted; label and
+ *     index arrays are int32 on this side (the reference uses int64; the host layer converts).
+ *   - host pointers are borrowed for the duration of the call; the handle owns all device memory.
+ *   - every call returns 0 on success or a negative dlsm_status; dlsm_last_error() gives text.
+ *   - there is NO CPU fallback: every compute entry point fails with DLSM_ERR_CUDA when no CUDA
+ *     device / sm_100 image is available.
+ *   - calls on one handle must be serialised by the caller; one CUDA stream per handle.
+ *   - all per-chain arrays carry a leading chain axis C = cfg.n_chains.
+ */
+#ifndef DLSM_H
+#define DLSM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLSM_ABI_VERSION 1
+
+typedef struct dlsm_handle dlsm_handle;
+
+typedef enum {
+    DLSM_OK = 0,
+    DLSM_ERR_INVALID = -1,   /* bad argument / shape / state */
+    DLSM_ERR_CUDA = -2,      /* CUDA runtime error or no device */
+    DLSM_ERR_NONBINARY = -3, /* adjacency holds a value other than 0/1 (weights, -1 missing) */
+    DLSM_ERR_NOTSET = -4,    /* a required input (network, case-control lists, ...) is missing */
+    DLSM_ERR_NONFINITE = -5, /* a log-likelihood evaluated to NaN/inf */
+    DLSM_ERR_UNSUPPORTED = -6
+} dlsm_status;
+
+/* likelihood kinds */
+#define DLSM_LIK_EXACT 0        /* static_network_fast.pyx:17 / directed_likelihoods_fast.pyx:46 */
+#define DLSM_LIK_CASE_CONTROL 1 /* directed_likelihoods_fast.pyx:83 (directed only, lsm.py:425) */
+/* latent-position priors */
+#define DLSM_PRIOR_LSM 0     /* sample_latent_positions.py:131-140 */
+#define DLSM_PRIOR_MIXTURE 1 /* sample_latent_positions.py:187-199 */
+
+typedef struct {
+    int32_t n_chains;     /* independent chains sharing one network */
+    int32_t T, n, d;      /* time steps, nodes, latent dimension (d <= 8) */
+    int32_t K;            /* mixture components (0 for the plain LSM) */
+    int32_t is_directed;  /* lsm.py:236 */
+    int32_t likelihood;   /* DLSM_LIK_* */
+    int32_t prior;        /* DLSM_PRIOR_* */
+    int32_t device;       /* CUDA device ordinal */
+    /* Metropolis tuner wiring (metropolis.py:85-94).  tune < 0 means tune=None. */
+    int32_t tune;                 /* latent + intercept samplers */
+    int32_t tune_interval;        /* latent samplers */
+    int32_t intercept_tune_interval[2];
+    int32_t radii_tune;           /* lsm.py:470 passes None, hdp_lpcm.py:745 passes tune */
+    int32_t radii_tune_interval;
+    int32_t reserved[4];
+} dlsm_config;
+
+/* state fields for dlsm_set_state / dlsm_get_state; shapes with leading chain axis C */
+typedef enum {
+    DLSM_F_X = 0,          /* f64 (C,T,n,d)  latent positions */
+    DLSM_F_INTERCEPT = 1,  /* f64 (C,2)      [beta] or [beta_in, beta_out] */
+    DLSM_F_RADII = 2,      /* f64 (C,n) */
+    DLSM_F_Z = 3,          /* i32 (C,T,n)    labels */
+    DLSM_F_MU = 4,         /* f64 (C,K,d) */
+    DLSM_F_SIGMA = 5,      /* f64 (C,K)      variances */
+    DLSM_F_LAMBDA = 6,     /* f64 (C,) */
+    DLSM_F_WEIGHTS = 7,    /* f64 (C,T,K,K)  w[0,0,:] = initial distribution (hdp_lpcm.py:123) */
+    DLSM_F_X_STEP = 8,     /* f64 (C,T,n)    Metropolis.step_size of each latent sampler */
+    DLSM_F_X_NACC = 9,     /* i32 (C,T,n)    n_accepted */
+    DLSM_F_X_NSTEPS = 10,  /* i32 (C,T,n)    n_steps */
+    DLSM_F_X_UNTIL = 11,   /* i32 (C,T,n)    steps_until_tune */
+    DLSM_F_B_STEP = 12,    /* f64 (C,2)      intercept samplers */
+    DLSM_F_B_NACC = 13,    /* i32 (C,2) */
+    DLSM_F_B_NSTEPS = 14,  /* i32 (C,2) */
+    DLSM_F_B_UNTIL = 15,   /* i32 (C,2) */
+    DLSM_F_R_STEP = 16,    /* f64 (C,)       radii sampler (Dirichlet concentration scale) */
+    DLSM_F_R_NACC = 17,    /* i32 (C,) */
+    DLSM_F_R_NSTEPS = 18,  /* i32 (C,) */
+    DLSM_F_R_UNTIL = 19,   /* i32 (C,) */
+    DLSM_F_NCOUNT = 20,    /* f64 (C,T,K,K)  transition counts of the last label draw (read-only) */
+    DLSM_F_NK = 21,        /* i32 (C,T,K)    occupancy counts of the last label draw (read-only) */
+    DLSM_F_COUNT_
+} dlsm_field;
+
+/* hyper-parameters of the MH targets */
+typedef struct {
+    double tau_sq;            /* lsm.py:241 */
+    double sigma_sq;          /* lsm.py:242 */
+    double intercept_prior[2];        /* prior means (lsm.py:239 'auto' resolved by the host) */
+    double intercept_variance_prior;  /* lsm.py:240 */
+} dlsm_hyper;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int dlsm_abi_version(void);
+int dlsm_device_count(void); /* 0 when no usable CUDA device */
+int dlsm_create(const dlsm_config *cfg, dlsm_handle **out);
+void dlsm_destroy(dlsm_handle *h);
+const char *dlsm_last_error(const dlsm_handle *h); /* h may be NULL: last creation error */
+/* run on a caller-provided cudaStream_t (e.g. the framework's current stream); NULL restores
+ * the handle's own stream */
+int dlsm_set_stream(dlsm_handle *h, void *cuda_stream);
+int dlsm_synchronize(dlsm_handle *h);
+
+/* ---- network -------------------------------------------------------------------------- */
+/* Y (T,n,n) fp64 0/1 as passed to DynamicNetworkLSM.fit (lsm.py:319-343).  Bit-packed on the
+ * device: row-major always, transposed too when is_directed. */
+int dlsm_set_network_dense(dlsm_handle *h, const double *Y);
+/* Sparse input for networks whose dense Y cannot exist (cfg 5).  Replaces
+ * DirectedCaseControlSampler.init (case_control_likelihood.py:37-73): degrees (T,n,2) [in,out],
+ * in_edges (T,n,max_in), out_edges (T,n,max_out), zero-padded. */
+int dlsm_set_edge_lists(dlsm_handle *h, const int32_t *degrees, const int32_t *in_edges,
+                        int32_t max_in, const int32_t *out_edges, int32_t max_out);
+/* control sets (case_control_likelihood.py:75-112): (S,T,n,n_control), -1 padded, where S = 1
+ * (shared by all chains) or S = n_chains */
+int dlsm_set_controls(dlsm_handle *h, const int32_t *ctrl_in, const int32_t *ctrl_out,
+                      int32_t n_control, int32_t n_sets);
+
+/* ---- chain state ----------------------------------------------------------------------- */
+int dlsm_set_state(dlsm_handle *h, int field, const void *host, size_t bytes);
+int dlsm_get_state(dlsm_handle *h, int field, void *host, size_t bytes);
+int dlsm_set_hyper(dlsm_handle *h, const dlsm_hyper *hy);
+/* device Philox4x32-10 streams: key = seed, counters = (site, sweep, chain+chain_offset, draw) */
+int dlsm_set_rng(dlsm_handle *h, uint64_t seed, uint64_t chain_offset, uint64_t sweep_index);
+
+/* ---- hot path -------------------------------------------------------------------------- */
+/* One latent-position sweep for every chain: for t asc, j asc a random-walk MH update of X[t,j]
+ * (sample_latent_positions.py:92-146 / :149-206 + metropolis.py:40-54,96-136), executed as a
+ * bit-exact time-slice wavefront.
+ *   replay:  eps (C,T,n,d) recorded standard normals, logu (C,T,n) recorded log-uniforms.
+ *   native:  eps == logu == NULL -> device Philox streams (dlsm_set_rng).
+ * Optional outputs (host, may be NULL): accepted (C,T,n) i32, ratio (C,T,n) f64. */
+int dlsm_sweep_latent(dlsm_handle *h, const double *eps, const double *logu, int32_t *accepted,
+                      double *ratio);
+/* X -= mean(X, axis=(time, node))  (lsm.py:501, hdp_lpcm.py:852), numpy summation order */
+int dlsm_center(dlsm_handle *h);
+/* sample_intercepts (sample_coefficients.py:12-88): m = 1 (undirected) or 2 (directed) MH steps
+ * on the full-network log-likelihood.  replay: eps (C,m), logu (C,m); native: NULL. */
+int dlsm_sample_intercepts(dlsm_handle *h, const double *eps, const double *logu,
+                           int32_t *accepted, double *ratio);
+/* sample_radii (sample_coefficients.py:91-121 + metropolis.py:57-82).  replay: proposal (C,n) =
+ * the recorded Dirichlet draw after the zero guard, logu (C,); native: NULL (device gamma
+ * variates). */
+int dlsm_sample_radii(dlsm_handle *h, const double *proposal, const double *logu,
+                      int32_t *accepted, double *ratio);
+/* sample_labels_block (sample_labels.py:134-190 + gaussian_likelihood_fast.pyx:30-54): HDP-HMM
+ * forward-filter/backward-sample per node.  replay: U (C,n,T) raw uniforms, node-major;
+ * native: NULL.  Updates DLSM_F_Z, DLSM_F_NCOUNT, DLSM_F_NK. */
+int dlsm_sample_labels(dlsm_handle *h, const double *U);
+/* n_sweeps x [latent -> center -> intercepts -> (radii) -> (labels)] with device RNG, no host
+ * round trip (the loop bodies lsm.py:483-523 / hdp_lpcm.py:840-878 minus the host-side blocks).
+ * flags: bit0 skip center, bit1 skip intercepts, bit2 skip radii, bit3 skip labels. */
+int dlsm_run_sweeps(dlsm_handle *h, int32_t n_sweeps, uint32_t flags);
+
+/* ---- parity probes --------------------------------------------------------------------- */
+/* per-node log-likelihood at the current state, out (C,T,n):
+ * partial_loglikelihood / directed_partial_loglikelihood / approx_directed_partial_loglikelihood */
+int dlsm_loglik_partial(dlsm_handle *h, double *out);
+/* full-network log-likelihood at the current state, out (C,):
+ * network_likelihoods.py:16-33 / directed_likelihoods_fast.pyx:185-270 */
+int dlsm_loglik_full(dlsm_handle *h, double *out);
+/* emission densities of compute_gaussian_likelihood(normalize=False), out (C,n,T,K) */
+int dlsm_gaussian_likelihood(dlsm_handle *h, double *out);
+/* the raw draws the NEXT native latent sweep will consume: eps (C,T,n,d), logu (C,T,n) */
+int dlsm_debug_draws(dlsm_handle *h, double *eps, double *logu);
+
+/* ---- counters -------------------------------------------------------------------------- */
+typedef struct {
+    uint64_t kernel_launches;  /* kernels of this library launched on the handle so far */
+    uint64_t node_updates;     /* latent MH node-updates executed */
+    uint64_t sweeps;           /* latent sweeps executed (per chain) */
+    double latent_ms;          /* device time in the latent sweep kernel (when timing enabled) */
+    double other_ms;           /* device time in the other hot-path kernels */
+    uint64_t ub_flags;         /* case-control lists that hit the reference's out-of-bounds quirk */
+} dlsm_counters;
+int dlsm_enable_timing(dlsm_handle *h, int on); /* CUDA events around every phase */
+int dlsm_get_counters(dlsm_handle *h, dlsm_counters *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLSM_H */
