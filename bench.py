@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the MH-within-Gibbs hot path on B200 (see DESIGN.md, section Measurement).
+
+A *step* is one pass of the hot path over every chain resident on the GPU: latent-position sweep
+(T*n MH node-updates per chain) -> centring -> intercept MH (full-network likelihood)
+[-> radii MH] [-> label FFBS].  The metric is latent-position node-updates/s (whole job);
+sweeps/s (chain-sweeps per second) is reported beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg4|cfg3|cfg1]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference      # the reference's CPU implementation on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: T, n, d, K, directed, case_control, default chains per GPU, description
+    "cfg1": dict(T=3, n=18, d=2, K=0, directed=False, chains=1184,
+                 desc="DynamicNetworkLSM, Sampson-monks shape (T=3, n=18, d=2)"),
+    "cfg2": dict(T=9, n=120, d=2, K=10, directed=False, chains=1184,
+                 desc="DynamicNetworkHDPLPCM, community-splitting network (n=120, T=9, d=2, K=10)"),
+    "cfg3": dict(T=20, n=2000, d=2, K=0, directed=True, chains=1,
+                 desc="directed DynamicNetworkLSM with radii (n=2000, T=20, d=2), single chain"),
+    "cfg4": dict(T=10, n=500, d=2, K=10, directed=False, chains=296,
+                 desc="DynamicNetworkHDPLPCM multi-chain (n=500, T=10, d=2, K=10)"),
+}
+
+
+def expit(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def make_workload(name, seed=42):
+    """Synthetic community-structured dynamic network of the named shape plus a start state."""
+    w = dict(WORKLOADS[name])
+    T, n, d, K = w["T"], w["n"], w["d"], max(w["K"], 4)
+    rng = np.random.RandomState(seed)
+    directed = w["directed"]
+    scale = (1.0 / n) if directed else 1.0            # latent_space.py:92-93
+    centers = rng.randn(K, d) * 2.0 * scale
+    z0 = rng.randint(0, K, n)
+    X = np.empty((T, n, d))
+    X[0] = centers[z0] + 0.5 * scale * rng.randn(n, d)
+    z = np.empty((T, n), np.int64)
+    z[0] = z0
+    for t in range(1, T):
+        move = rng.rand(n) < 0.05
+        z[t] = np.where(move, rng.randint(0, K, n), z[t - 1])
+        X[t] = 0.8 * centers[z[t]] + 0.2 * X[t - 1] + 0.3 * scale * rng.randn(n, d)
+    X -= X.mean(axis=(0, 1))
+    Y = np.zeros((T, n, n))
+    if directed:
+        radii = rng.dirichlet(np.ones(n) * 20.0)
+        b_in, b_out = 0.3, 0.7
+        for t in range(T):
+            dist = np.sqrt(((X[t][:, None, :] - X[t][None, :, :]) ** 2).sum(-1))
+            eta = b_in * (1 - dist / radii[None, :]) + b_out * (1 - dist / radii[:, None])
+            Y[t] = (rng.rand(n, n) < expit(eta)).astype(np.float64)
+            np.fill_diagonal(Y[t], 0)
+        w.update(radii=radii, intercept=np.array([b_in, b_out]), step_X=0.0075 / 8,
+                 sigma_sq=0.001 * 1e-2, tau_sq=float(np.mean(X[0] * X[0])))
+    else:
+        beta = 1.0
+        for t in range(T):
+            dist = np.sqrt(((X[t][:, None, :] - X[t][None, :, :]) ** 2).sum(-1))
+            U = np.triu((rng.rand(n, n) < expit(beta - dist)).astype(np.float64), 1)
+            Y[t] = U + U.T
+        w.update(radii=None, intercept=np.array([beta]), step_X=0.1, sigma_sq=0.1, tau_sq=2.0)
+    Kc = w["K"]
+    if Kc:
+        mu = np.zeros((Kc, d)); mu[:K] = centers[:Kc] if Kc <= K else 0
+        mu[:min(K, Kc)] = centers[:min(K, Kc)]
+        sigma = np.full(Kc, 0.5)
+        zz = np.minimum(z, Kc - 1)
+        wts = np.full((T, Kc, Kc), 0.2 / (Kc - 1)) + np.eye(Kc) * (0.8 - 0.2 / (Kc - 1))
+        w.update(mu=mu, sigma=sigma, lmbda=0.8, z=zz, w=wts)
+    w.update(name=name, X=X, Y=Y, density=float(Y.mean()))
+    return w
+
+
+def bytes_per_node_update(w):
+    """Algorithmic bytes of one node-update, model M1 (SURVEY.md 8d / BASELINE.md section 4)."""
+    n, d = w["n"], w["d"]
+    if w["directed"]:
+        return 2 * n / 8.0 + 8.0 * d * n + 8.0 * n
+    return n / 8.0 + 8.0 * d * n
+
+
+def build_engine(w, chains, device, chain_offset, seed=42):
+    from dynetlsm_b200 import _lib as L
+    e = L.Engine(T=w["T"], n=w["n"], d=w["d"], n_chains=chains, K=w["K"], is_directed=w["directed"],
+                 mixture=bool(w["K"]), device=device, tune=2500, tune_interval=100,
+                 radii_tune=None)
+    e.set_network(w["Y"])
+    rng = np.random.RandomState(1000 + chain_offset)
+    disp = 0.1 * (1.0 / w["n"] if w["directed"] else 1.0)
+    X = w["X"][None] + disp * rng.randn(chains, w["T"], w["n"], w["d"])   # dispersed starts
+    e.set(L.F_X, X)
+    ic = np.zeros((chains, 2)); ic[:, :w["intercept"].size] = w["intercept"]
+    e.set(L.F_INTERCEPT, ic)
+    e.set_hyper(tau_sq=w["tau_sq"], sigma_sq=w["sigma_sq"], intercept_prior=w["intercept"],
+                intercept_variance_prior=2.0)
+    if w["directed"]:
+        e.set(L.F_RADII, np.tile(w["radii"][None], (chains, 1)))
+    if w["K"]:
+        e.set(L.F_MU, np.tile(w["mu"][None], (chains, 1, 1)))
+        e.set(L.F_SIGMA, np.tile(w["sigma"][None], (chains, 1)))
+        e.set(L.F_LAMBDA, np.full(chains, w["lmbda"]))
+        e.set(L.F_WEIGHTS, np.tile(w["w"][None], (chains, 1, 1, 1)))
+        e.set(L.F_Z, np.tile(w["z"][None], (chains, 1, 1)))
+    e.set_tuner(w["step_X"])
+    e.set_rng(seed, chain_offset=chain_offset)
+    return e
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU legs: the reference's implementation on the host cores, one chain per core
+# ---------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    name, sweeps, seed, kind = args
+    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = "1"
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    w = make_workload(name)
+    rng = np.random.RandomState(seed)
+    T, n = w["T"], w["n"]
+    X0 = w["X"] + 0.1 * (1.0 / n if w["directed"] else 1.0) * rng.randn(*w["X"].shape)
+    if kind == "reference":
+        import ref_driver as R
+        mix = (w["mu"], w["sigma"], np.array([w["lmbda"]]), w["z"].copy(), w["w"]) if w["K"] else None
+        st = R.make_state(w["Y"], X0, w["intercept"], is_directed=w["directed"], radii=w["radii"],
+                          mixture=mix, step_X=w["step_X"], tune=2500, tau_sq=w["tau_sq"],
+                          sigma_sq=w["sigma_sq"])
+        R.hot_path_sweep(st, rng)  # warm-up (imports, first-call overheads)
+        t0 = time.perf_counter()
+        for _ in range(sweeps):
+            R.hot_path_sweep(st, rng)
+        return time.perf_counter() - t0
+    import pyoracle as O
+    X = np.ascontiguousarray(X0)
+    tun = O.TunerState((T, n), w["step_X"], tune=2500, tune_interval=100)
+    itun = O.TunerState((w["intercept"].size,), 0.1, tune=2500, tune_interval=100)
+    ic = w["intercept"].copy()
+    mix = dict(mu=w["mu"], sigma=w["sigma"], lmbda=w["lmbda"], z=w["z"]) if w["K"] else None
+
+    def one():
+        O.sweep_latent(X, ic, tun, rng.randn(T, n, w["d"]), np.log(rng.rand(T, n)), Y=w["Y"],
+                       radii=w["radii"], is_directed=w["directed"], tau_sq=w["tau_sq"],
+                       sigma_sq=w["sigma_sq"], mixture=mix)
+        O.center(X)
+        dist = O.calculate_distances(X)
+        O.sample_intercepts(X, ic, itun, rng.randn(ic.size), np.log(rng.rand(ic.size)), ic, 2.0,
+                            Y=w["Y"], dist=dist, radii=w["radii"], is_directed=w["directed"])
+        if mix:
+            mix["z"], _, _, _ = O.sample_labels_block(X, w["mu"], w["sigma"], w["lmbda"], w["w"],
+                                                      rng.rand(n, T))
+    one()
+    t0 = time.perf_counter()
+    for _ in range(sweeps):
+        one()
+    return time.perf_counter() - t0
+
+
+def cpu_kind():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_driver
+    return "reference" if ref_driver.have_ref() else "port"
+
+
+def cpu_hot_path(name, sweeps_per_core, cores=None):
+    """Run `sweeps_per_core` hot-path sweeps on each of `cores` processes (one chain per core)."""
+    import multiprocessing as mp
+    kind = cpu_kind()
+    if kind == "port":
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    cores = cores or os.cpu_count() or 1
+    w = WORKLOADS[name]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        per = pool.map(_cpu_worker, [(name, sweeps_per_core, 7 + c, kind) for c in range(cores)])
+    wall = time.perf_counter() - t0
+    loop = max(per)
+    updates = cores * sweeps_per_core * w["T"] * w["n"]
+    return dict(value=updates / loop, unit="node-updates/s", cores=cores, kind=kind,
+                sweeps_per_s=cores * sweeps_per_core / loop, loop_s=loop, wall_s=wall,
+                sample="%d hot-path sweeps on each of %d cores (one chain per core), %s" % (
+                    sweeps_per_core, cores, WORKLOADS[name]["desc"]))
+
+
+def cpu_sweeps_for(name, target_s=12.0):
+    # rough per-sweep cost of the reference loop (survey-time measurements), to bound the sample
+    est = {"cfg1": 0.006, "cfg2": 0.12, "cfg3": 25.0, "cfg4": 0.9}[name]
+    if cpu_kind() == "port":
+        est *= 0.2
+    return max(1, int(target_s / est))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload
+    w = WORKLOADS[name]
+    per_step = max(1, cpu_sweeps_for(name, 60.0) // max(1, args.steps + args.warmup))
+    kind = cpu_kind()
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_hot_path(name, 1, cores)
+    t_loop, upd, sw = 0.0, 0, 0
+    for _ in range(args.steps):
+        r = cpu_hot_path(name, per_step, cores)
+        t_loop += r["loop_s"]; upd += cores * per_step * w["T"] * w["n"]; sw += cores * per_step
+    val = upd / t_loop
+    line = {"impl": "reference", "metric": "latent-position node-updates/sec", "value": val,
+            "unit": "node-updates/s", "sweeps_per_s": sw / t_loop, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_loop / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "%s: %s" % (name, w["desc"]),
+                       "chains": cores, "note": "one chain per host core; a step = %d sweeps per core" % per_step},
+            "cpu_baseline": {"value": val, "unit": "node-updates/s", "cores": cores, "kind": kind,
+                             "sample": "%d steps x %d sweeps on each of %d cores" % (args.steps, per_step, cores)},
+            "e2e": {"value": val, "unit": "node-updates/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--chains-per-gpu", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from dynetlsm_b200 import _lib as L
+
+    w = make_workload(args.workload)
+    chains = args.chains_per_gpu or w["chains"]
+    e = build_engine(w, chains, local, chain_offset=rank * chains)
+    stream = torch.cuda.current_stream()
+    e.set_stream(stream.cuda_stream)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        e.run_sweeps(1)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    c0 = e.counters()
+    e.enable_timing(True)
+    clocks = ClockSampler(local)
+    clocks.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    barrier()
+    for a, b in evs:
+        flush.zero_()                      # L2 flush between timed iterations (outside the events)
+        a.record(stream)
+        step()
+        b.record(stream)
+    barrier()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    clk = clocks.stop()
+    c1 = e.counters()
+    e.enable_timing(False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    upd_per_step = chains * w["T"] * w["n"]
+    total_updates = world * upd_per_step * args.steps
+    value = total_updates / (ms_max * 1e-3)
+    launches = c1["kernel_launches"] - c0["kernel_launches"]
+    latent_ms = c1["latent_ms"] - c0["latent_ms"]
+    other_ms = c1["other_ms"] - c0["other_ms"]
+
+    # roofline of the dominant kernel (k_sweep): algorithmic bytes per launch / mean launch time
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bpl = bytes_per_node_update(w) * upd_per_step
+    lat_per_launch_ms = latent_ms / args.steps
+    achieved = bpl / (lat_per_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_sweep", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "bytes_per_node_update": bytes_per_node_update(w),
+                "kernel_ms_per_launch": lat_per_launch_ms,
+                "kernel_share_of_step": latent_ms / ms if ms > 0 else None,
+                "kernel_node_updates_per_s": upd_per_step / (lat_per_launch_ms * 1e-3)}
+
+    # end-to-end through the public C-ABI with HOST buffers: what one iteration of the estimator's
+    # fit loop exchanges with the device when the conjugate HDP updates run on the host
+    e2e = None
+    if not args.no_e2e:
+        def pinned(a):
+            tt = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            return tt.numpy()
+        hX = pinned(e.get(L.F_X))
+        ins = [(L.F_X, hX)]
+        if w["K"]:
+            ins += [(L.F_MU, pinned(e.get(L.F_MU))), (L.F_SIGMA, pinned(e.get(L.F_SIGMA))),
+                    (L.F_LAMBDA, pinned(e.get(L.F_LAMBDA))), (L.F_WEIGHTS, pinned(e.get(L.F_WEIGHTS)))]
+        outs = [L.F_X, L.F_INTERCEPT] + ([L.F_Z, L.F_NCOUNT, L.F_NK] if w["K"] else []) + \
+               ([L.F_RADII] if w["directed"] else [])
+        h2d = sum(a.nbytes for _, a in ins)
+        d2h = 0
+        nst = max(3, min(args.steps, 10))
+        for it in range(2 + nst):
+            if it == 2:
+                barrier()
+                t0 = time.perf_counter()
+            for f, a in ins:
+                e.set(f, a)
+            e.run_sweeps(1)
+            got = [e.get(f) for f in outs]
+            ins[0] = (L.F_X, got[0])
+        barrier()
+        dt = time.perf_counter() - t0
+        d2h = sum(a.nbytes for a in got)
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * upd_per_step * nst / float(tt.item()), "unit": "node-updates/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": nst,
+               "api": "Engine.set(state) -> run_sweeps(1) -> Engine.get(state) over the dlsm C-ABI"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_hot_path(args.workload, cpu_sweeps_for(args.workload))
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "sweeps_per_s")}
+
+    if rank == 0:
+        line = {"metric": "latent-position node-updates/sec", "value": value,
+                "unit": "node-updates/s", "sweeps_per_s": world * chains * args.steps / (ms_max * 1e-3),
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "%s: %s" % (args.workload, w["desc"]),
+                           "chains_per_gpu": chains, "chains_total": chains * world,
+                           "density": w["density"], "rng": "device Philox4x32-10",
+                           "step": "latent sweep + centre + intercept MH" +
+                                   (" + radii MH" if w["directed"] else "") +
+                                   (" + label FFBS" if w["K"] else ""),
+                           "l2": "flushed between timed iterations (256 MiB write)"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk,
+                "gpu_launches": int(launches),
+                "phase_ms_per_step": {"latent": latent_ms / args.steps, "other": other_ms / args.steps}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -212,10 +212,10 @@ def test_lsm_intercepts_radii_replay(name, directed, cc):
     assert np.allclose(ratio, g["i_ratio"].reshape(S, m), rtol=1e-8, atol=1e-7)
     assert np.array_equal(e.get(L.F_B_STEP)[:-1, :m], g["itun_step"][1:].reshape(S - 1, m))
     if directed:
-        e.set(L.F_R_STEP, g["rtun_step"])
-        e.set(L.F_R_NACC, g["rtun_n_accepted"])
-        e.set(L.F_R_NSTEPS, g["rtun_n_steps"])
-        e.set(L.F_R_UNTIL, g["rtun_until"])
+        e.set(L.F_R_STEP, g["rtun_step"].reshape(S))
+        e.set(L.F_R_NACC, g["rtun_n_accepted"].reshape(S))
+        e.set(L.F_R_NSTEPS, g["rtun_n_steps"].reshape(S))
+        e.set(L.F_R_UNTIL, g["rtun_until"].reshape(S))
         acc, ratio = e.sample_radii(g["r_proposal"], g["r_logu"], want_stats=True)
         assert np.array_equal(acc, g["r_accepted"])
         assert np.array_equal(e.get(L.F_RADII), g["radii_out"])
