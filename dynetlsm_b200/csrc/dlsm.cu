@@ -199,24 +199,32 @@ size_t sweep_smem(const dlsm_handle *h, bool xs)
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
-template <int LK, int D, bool XS>
-int launch_sweep_t(dlsm_handle *h, const SweepParams &p)
+template <int LK, int D, bool XS, int MAXT, int MINB>
+int launch_sweep_t(dlsm_handle *h, const SweepParams &p, int warps)
 {
     const size_t smem = sweep_smem(h, XS);
-    auto kern = k_sweep<LK, D, XS>;
+    auto kern = k_sweep<LK, D, XS, MAXT, MINB>;
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int warps = h->cfg.T < 16 ? h->cfg.T : 16;
     kern<<<h->cfg.n_chains, warps * 32, smem, h->stream>>>(p);
     CHECK_LAUNCH(h);
     return DLSM_OK;
+}
+
+// Register budget follows the block size: chains with few time slices run 3 CTAs per SM.
+template <int LK, int D, bool XS>
+int launch_sweep_x(dlsm_handle *h, const SweepParams &p)
+{
+    const int warps = h->cfg.T < 16 ? h->cfg.T : 16;
+    if (warps <= 10) return launch_sweep_t<LK, D, XS, 320, 3>(h, p, warps);
+    return launch_sweep_t<LK, D, XS, 512, 2>(h, p, warps);
 }
 
 template <int LK>
 int launch_sweep_lk(dlsm_handle *h, const SweepParams &p)
 {
     const bool xs = sweep_smem(h, true) <= kMaxSmem;
-    if (h->cfg.d == 2) return xs ? launch_sweep_t<LK, 2, true>(h, p) : launch_sweep_t<LK, 2, false>(h, p);
-    return xs ? launch_sweep_t<LK, 0, true>(h, p) : launch_sweep_t<LK, 0, false>(h, p);
+    if (h->cfg.d == 2) return xs ? launch_sweep_x<LK, 2, true>(h, p) : launch_sweep_x<LK, 2, false>(h, p);
+    return xs ? launch_sweep_x<LK, 0, true>(h, p) : launch_sweep_x<LK, 0, false>(h, p);
 }
 
 int launch_sweep(dlsm_handle *h, const SweepParams &p)

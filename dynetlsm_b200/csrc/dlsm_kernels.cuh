@@ -74,24 +74,34 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
 {
     const int n = net.n, d = net.d;
     if (LK == kUndirected) {
-        // K1 static_network_fast.pyx:17-44
+        // K1 static_network_fast.pyx:17-44.  Two 32-node chunks per trip: four independent
+        // sqrt/softplus chains per lane keep the fp64 pipe busy.
         const uint32_t *row = net.rowbits + ((size_t)t * n + j) * net.W;
-        double an = 0.0, ao = 0.0;
-        for (int base = 0; base < n; base += 32) {
-            const int i = base + lane;
-            const uint32_t w = __ldg(row + (base >> 5));
-            if (i < n && i != j) {
+        double an = 0.0, ao = 0.0, an2 = 0.0, ao2 = 0.0;
+        for (int base = 0; base < n; base += 64) {
+            const int i0 = base + lane, i1 = i0 + 32;
+            const uint2 w = __ldg(reinterpret_cast<const uint2 *>(row + (base >> 5)));
+            if (i0 < n && i0 != j) {
                 double xi[DM];
-                load_pos<DM>(Xt + (size_t)i * d, d, xi);
+                load_pos<DM>(Xt + (size_t)i0 * d, d, xi);
                 const double en = b0 - sqrt(sqdist<DM>(xi, xn, d));
                 const double eo = b0 - sqrt(sqdist<DM>(xi, xo, d));
-                if ((w >> lane) & 1u) { an += en; ao += eo; }
+                if ((w.x >> lane) & 1u) { an += en; ao += eo; }
                 an -= log1pexp(en);
                 ao -= log1pexp(eo);
             }
+            if (i1 < n && i1 != j) {
+                double xi[DM];
+                load_pos<DM>(Xt + (size_t)i1 * d, d, xi);
+                const double en = b0 - sqrt(sqdist<DM>(xi, xn, d));
+                const double eo = b0 - sqrt(sqdist<DM>(xi, xo, d));
+                if ((w.y >> lane) & 1u) { an2 += en; ao2 += eo; }
+                an2 -= log1pexp(en);
+                ao2 -= log1pexp(eo);
+            }
         }
-        ll_new = warp_sum(an);
-        ll_old = warp_sum(ao);
+        ll_new = warp_sum(an + an2);
+        ll_old = warp_sum(ao + ao2);
     } else if (LK == kDirected) {
         // K2 directed_likelihoods_fast.pyx:46-80
         const uint32_t *row = net.rowbits + ((size_t)t * n + j) * net.W;
@@ -199,64 +209,84 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
     }
 }
 
-// closure `logp` = loglik minus the prior terms, subtracted one after the other
-// (sample_latent_positions.py:131-140 LSM, :187-199 mixture).  xprev/xnext may be null at the ends.
+// ---------------------------------------------------------------------------------------------
+// Prior terms of the closure `logp` (sample_latent_positions.py:131-140 LSM, :187-199 mixture).
+// The reference subtracts them from loglik one after the other:
+//     loglik -= term_prev(x | X[t-1,j])   (or the t == 0 term)
+//     loglik -= term_next(X[t+1,j] | x)   (if t < T-1)
+// term_next only needs the OLD X[t+1,j], so it is evaluated lane-parallel for 32 nodes at a time;
+// term_prev needs this sweep's X[t-1,j] and is evaluated when the wavefront flag allows.
+// ---------------------------------------------------------------------------------------------
 template <int DM>
-__device__ __forceinline__ double apply_prior(const SweepParams &p, int c, int t, int j,
-                                              double loglik, const double (&x)[DM],
-                                              const double (&xprev)[DM], const double (&xnext)[DM])
+__device__ __forceinline__ double prior_next(const SweepParams &p, int c, int t, int j,
+                                             const double (&x)[DM], const double (&xnext)[DM])
 {
     const int d = p.net.d, T = p.net.T, n = p.net.n;
     double diff[DM];
     if (p.prior == 0) {
-        if (t == 0) {
-            loglik = __dsub_rn(loglik, half_sumsq_over<DM>(x, d, p.tau_sq));
-        } else {
 #pragma unroll
-            for (int k = 0; k < DM; k++) diff[k] = (k < d) ? __dsub_rn(x[k], xprev[k]) : 0.0;
-            loglik = __dsub_rn(loglik, half_sumsq_over<DM>(diff, d, p.sigma_sq));
-        }
-        if (t < T - 1) {
+        for (int k = 0; k < DM; k++) diff[k] = (k < d) ? __dsub_rn(xnext[k], x[k]) : 0.0;
+        return half_sumsq_over<DM>(diff, d, p.sigma_sq);
+    }
+    const double lm = p.lambda[c], oml = __dsub_rn(1.0, lm);
+    const int zn = p.z[((size_t)c * T + (t + 1)) * n + j];
+    const double *mu = p.mu + ((size_t)c * p.K + zn) * d;
 #pragma unroll
-            for (int k = 0; k < DM; k++) diff[k] = (k < d) ? __dsub_rn(xnext[k], x[k]) : 0.0;
-            loglik = __dsub_rn(loglik, half_sumsq_over<DM>(diff, d, p.sigma_sq));
-        }
+    for (int k = 0; k < DM; k++)
+        diff[k] = (k < d) ? __dsub_rn(__dsub_rn(xnext[k], __dmul_rn(oml, x[k])), __dmul_rn(lm, mu[k]))
+                          : 0.0;
+    return half_sumsq_over<DM>(diff, d, p.sigma[(size_t)c * p.K + zn]);
+}
+
+template <int DM>
+__device__ __forceinline__ double prior_prev(const SweepParams &p, int c, int t, int zc,
+                                             const double (&x)[DM], const double (&xprev)[DM])
+{
+    const int d = p.net.d;
+    double diff[DM];
+    if (p.prior == 0) {
+        if (t == 0) return half_sumsq_over<DM>(x, d, p.tau_sq);
+#pragma unroll
+        for (int k = 0; k < DM; k++) diff[k] = (k < d) ? __dsub_rn(x[k], xprev[k]) : 0.0;
+        return half_sumsq_over<DM>(diff, d, p.sigma_sq);
+    }
+    const double *mu = p.mu + ((size_t)c * p.K + zc) * d;
+    if (t == 0) {
+#pragma unroll
+        for (int k = 0; k < DM; k++) diff[k] = (k < d) ? __dsub_rn(x[k], mu[k]) : 0.0;
     } else {
         const double lm = p.lambda[c], oml = __dsub_rn(1.0, lm);
-        const int32_t *z = p.z + (size_t)c * T * n;
-        const double *mu = p.mu + (size_t)c * p.K * d;
-        const double *sg = p.sigma + (size_t)c * p.K;
-        const int zc = z[(size_t)t * n + j];
-        if (t == 0) {
 #pragma unroll
-            for (int k = 0; k < DM; k++) diff[k] = (k < d) ? __dsub_rn(x[k], mu[zc * d + k]) : 0.0;
-        } else {
-#pragma unroll
-            for (int k = 0; k < DM; k++)
-                diff[k] = (k < d) ? __dsub_rn(__dsub_rn(x[k], __dmul_rn(oml, xprev[k])),
-                                              __dmul_rn(lm, mu[zc * d + k]))
-                                  : 0.0;
-        }
-        loglik = __dsub_rn(loglik, half_sumsq_over<DM>(diff, d, sg[zc]));
-        if (t < T - 1) {
-            const int zn = z[(size_t)(t + 1) * n + j];
-#pragma unroll
-            for (int k = 0; k < DM; k++)
-                diff[k] = (k < d) ? __dsub_rn(__dsub_rn(xnext[k], __dmul_rn(oml, x[k])),
-                                              __dmul_rn(lm, mu[zn * d + k]))
-                                  : 0.0;
-            loglik = __dsub_rn(loglik, half_sumsq_over<DM>(diff, d, sg[zn]));
-        }
+        for (int k = 0; k < DM; k++)
+            diff[k] = (k < d) ? __dsub_rn(__dsub_rn(x[k], __dmul_rn(oml, xprev[k])), __dmul_rn(lm, mu[k]))
+                              : 0.0;
     }
-    return loglik;
+    return half_sumsq_over<DM>(diff, d, p.sigma[(size_t)c * p.K + zc]);
+}
+
+template <int DM>
+__device__ __forceinline__ void shfl_vec(double (&dst)[DM], const double (&src)[DM], int d, int from)
+{
+#pragma unroll
+    for (int k = 0; k < DM; k++)
+        if (k < d) dst[k] = __shfl_sync(kFull, src[k], from);
+        else dst[k] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------
 // k_sweep: one latent-position sweep of every chain.
 // grid = C chains, block = 32 * min(T, 16) threads, dynamic smem = [T*n*d doubles if XS] + T ints
+//
+// Each warp owns a time slice and walks its nodes in blocks of 32.  At the head of a block lane l
+// prepares everything that does not depend on the in-flight wavefront for node jb+l -- the
+// sampler state, the random draws (replay buffer or Philox + Box-Muller), the proposal
+// x0 + step*eps and the "next" prior terms -- so that work is done once per 32 nodes with all lanes
+// busy, with coalesced loads/stores.  The serial part of a node-update is then: broadcast by
+// shuffle, the 32-lane pairwise reduction, the wavefront flag, the "prev" prior term and the
+// accept/reject, which lane (j mod 32) commits.
 // ---------------------------------------------------------------------------------------------
-template <int LK, int D, bool XS>
-__global__ void __launch_bounds__(512) k_sweep(const SweepParams p)
+template <int LK, int D, bool XS, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
 {
     constexpr int DM = (D == 0) ? kMaxD : D;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -281,73 +311,109 @@ __global__ void __launch_bounds__(512) k_sweep(const SweepParams p)
     const double b0 = p.intercept[c * 2 + 0], b1 = p.intercept[c * 2 + 1];
     const double *rinv = (LK == kUndirected) ? nullptr : p.rinv + (size_t)c * n;
     const uint32_t chain_id = (uint32_t)c + p.chain_offset;
+    bool nonfinite = false;
 
     for (int t = warp; t < T; t += nwarps) {
         double *Xt = Xc + (size_t)t * n * d;
-        for (int j = 0; j < n; j++) {
-            const size_t site = (size_t)t * n + j;
-            const size_t gs = (size_t)c * T * n + site;
-            // ---- proposal (metropolis.py:44): x = x0 + step * randn(d), separate roundings
-            double x0[DM], x[DM], eps[DM], logu;
-            load_pos<DM>(Xt + (size_t)j * d, d, x0);
-            const double step = p.step[gs];
-            if (p.eps) {
+        for (int jb = 0; jb < n; jb += 32) {
+            // ---------------- lane-parallel preparation for node jl = jb + lane ----------------
+            const int jl = jb + lane;
+            const bool mine = jl < n;
+            const size_t gs = ((size_t)c * T + t) * n + (mine ? jl : 0);
+            double my_x0[DM], my_x[DM], my_step = 0.0, my_logu = 0.0, my_next_new = 0.0,
+                                         my_next_old = 0.0;
+            int my_nacc = 0, my_nsteps = 0, my_until = 0, my_zc = 0;
 #pragma unroll
-                for (int k = 0; k < DM; k++) eps[k] = (k < d) ? p.eps[gs * d + k] : 0.0;
-                logu = p.logu[gs];
-            } else {
-                latent_draws<DM>(p.seed, (uint32_t)site, p.sweep, chain_id, d, eps, logu);
+            for (int k = 0; k < DM; k++) { my_x0[k] = 0.0; my_x[k] = 0.0; }
+            if (mine) {
+                double eps[DM];
+                load_pos<DM>(Xt + (size_t)jl * d, d, my_x0);
+                my_step = p.step[gs]; my_nacc = p.nacc[gs]; my_nsteps = p.nsteps[gs]; my_until = p.until[gs];
+                if (p.eps) {
+#pragma unroll
+                    for (int k = 0; k < DM; k++) eps[k] = (k < d) ? p.eps[gs * d + k] : 0.0;
+                    my_logu = p.logu[gs];
+                } else {
+                    latent_draws<DM>(p.seed, (uint32_t)(t * n + jl), p.sweep, chain_id, d, eps, my_logu);
+                }
+                // metropolis.py:44  x = x0 + step_size * randn(d): separately rounded mul and add
+#pragma unroll
+                for (int k = 0; k < DM; k++)
+                    my_x[k] = (k < d) ? __dadd_rn(my_x0[k], __dmul_rn(my_step, eps[k])) : 0.0;
+                if (p.prior != 0) my_zc = p.z[((size_t)c * T + t) * n + jl];
+                if (t < T - 1) { // X[t+1, jl] is still last sweep's value: slice t+1 trails this one
+                    double xnx[DM];
+                    const volatile double *q = Xc + ((size_t)(t + 1) * n + jl) * d;
+#pragma unroll
+                    for (int k = 0; k < DM; k++) xnx[k] = (k < d) ? q[k] : 0.0;
+                    my_next_new = prior_next<DM>(p, c, t, jl, my_x, xnx);
+                    my_next_old = prior_next<DM>(p, c, t, jl, my_x0, xnx);
+                }
             }
+            const int jend = (n - jb) < 32 ? (n - jb) : 32;
+            // ---------------- serial node-updates of this block ----------------
+            for (int jj = 0; jj < jend; jj++) {
+                const int j = jb + jj;
+                double x[DM], x0[DM];
+                shfl_vec<DM>(x, my_x, d, jj);
+                shfl_vec<DM>(x0, my_x0, d, jj);
+                const double logu = __shfl_sync(kFull, my_logu, jj);
+                const double nx_new = __shfl_sync(kFull, my_next_new, jj);
+                const double nx_old = __shfl_sync(kFull, my_next_old, jj);
+                const int zc = __shfl_sync(kFull, my_zc, jj);
+
+                if (LK != kCaseControl && j + 1 < n && lane * 32 < p.net.W) { // next row -> L1
+                    const size_t o = ((size_t)t * n + j + 1) * p.net.W + lane * 32;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(p.net.rowbits + o));
+                    if (LK == kDirected) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.net.colbits + o));
+                }
+                double ll_new, ll_old;
+                node_loglik2<LK, DM>(p.net, Xt, rinv, c, t, j, x, x0, b0, b1, lane, ll_new, ll_old,
+                                     p.flags);
+
+                double xp[DM];
 #pragma unroll
-            for (int k = 0; k < DM; k++) x[k] = (k < d) ? __dadd_rn(x0[k], __dmul_rn(step, eps[k])) : 0.0;
-
-            // ---- likelihood at x and x0: one pass over the row
-            double ll_new, ll_old;
-            node_loglik2<LK, DM>(p.net, Xt, rinv, c, t, j, x, x0, b0, b1, lane, ll_new, ll_old,
-                                 p.flags);
-
-            // ---- wavefront: X[t-1, j] must be this sweep's value
-            if (t > 0) {
-                if (lane == 0)
-                    while (progress[t - 1] <= j) { /* spin on shared memory */ }
-                __threadfence_block();
+                for (int k = 0; k < DM; k++) xp[k] = 0.0;
+                if (t > 0) { // wavefront: X[t-1, j] must be this sweep's value
+                    if (lane == 0)
+                        while (progress[t - 1] <= j) { /* spin on shared memory */ }
+                    __threadfence_block();
+                    __syncwarp();
+                    const volatile double *q = Xc + ((size_t)(t - 1) * n + j) * d;
+#pragma unroll
+                    for (int k = 0; k < DM; k++) if (k < d) xp[k] = q[k];
+                }
+                double lp_new = __dsub_rn(ll_new, prior_prev<DM>(p, c, t, zc, x, xp));
+                double lp_old = __dsub_rn(ll_old, prior_prev<DM>(p, c, t, zc, x0, xp));
+                if (t < T - 1) {
+                    lp_new = __dsub_rn(lp_new, nx_new);
+                    lp_old = __dsub_rn(lp_old, nx_old);
+                }
+                const double ratio = __dsub_rn(lp_new, lp_old);
+                const int acc = (logu >= ratio) ? 0 : 1; // metropolis.py:50 (a NaN ratio accepts)
+                if (lane == jj) {
+                    if (acc) {
+#pragma unroll
+                        for (int k = 0; k < DM; k++) if (k < d) Xt[(size_t)j * d + k] = x[k];
+                    }
+                    metropolis_bookkeep(my_step, my_nacc, my_nsteps, my_until, p.tune,
+                                        p.tune_interval, acc, false);
+                    const size_t gsj = ((size_t)c * T + t) * n + j;
+                    if (p.accepted) p.accepted[gsj] = acc;
+                    if (p.ratio) p.ratio[gsj] = ratio;
+                    if (!(ratio == ratio) || ratio - ratio != 0.0) nonfinite = true;
+                    __threadfence_block();
+                    progress[t] = j + 1;
+                }
                 __syncwarp();
             }
-            double xp[DM], xnx[DM];
-#pragma unroll
-            for (int k = 0; k < DM; k++) { xp[k] = 0.0; xnx[k] = 0.0; }
-            if (t > 0) {
-                const volatile double *q = Xc + ((size_t)(t - 1) * n + j) * d;
-#pragma unroll
-                for (int k = 0; k < DM; k++) if (k < d) xp[k] = q[k];
+            // ---------------- coalesced write-back of the sampler state ----------------
+            if (mine) {
+                p.step[gs] = my_step; p.nacc[gs] = my_nacc; p.nsteps[gs] = my_nsteps; p.until[gs] = my_until;
             }
-            if (t < T - 1) {
-                const volatile double *q = Xc + ((size_t)(t + 1) * n + j) * d;
-#pragma unroll
-                for (int k = 0; k < DM; k++) if (k < d) xnx[k] = q[k];
-            }
-            const double lp_new = apply_prior<DM>(p, c, t, j, ll_new, x, xp, xnx);
-            const double lp_old = apply_prior<DM>(p, c, t, j, ll_old, x0, xp, xnx);
-            const double ratio = __dsub_rn(lp_new, lp_old);
-            const int acc = (logu >= ratio) ? 0 : 1; // metropolis.py:50 (NaN ratio accepts)
-            if (lane == 0) {
-                if (acc) {
-#pragma unroll
-                    for (int k = 0; k < DM; k++) if (k < d) Xt[(size_t)j * d + k] = x[k];
-                }
-                double st = step;
-                int na = p.nacc[gs], ns = p.nsteps[gs], un = p.until[gs];
-                metropolis_bookkeep(st, na, ns, un, p.tune, p.tune_interval, acc, false);
-                p.step[gs] = st; p.nacc[gs] = na; p.nsteps[gs] = ns; p.until[gs] = un;
-                if (p.accepted) p.accepted[gs] = acc;
-                if (p.ratio) p.ratio[gs] = ratio;
-                if (!(ratio == ratio) || ratio - ratio != 0.0) atomicOr(p.flags, 1u);
-                __threadfence_block();
-                progress[t] = j + 1;
-            }
-            __syncwarp();
         }
     }
+    if (nonfinite) atomicOr(p.flags, 1u);
     if (XS) {
         __syncthreads();
         for (size_t e = threadIdx.x; e < chain_elems; e += blockDim.x) Xg[e] = Xc[e];

@@ -1,0 +1,35 @@
+// Host-side accuracy harness for dlsm::fast_log1pexp (the same __host__ __device__ source the
+// kernels inline).  Prints the max abs / rel error against long double log1pl(expl(x)).
+#include "../../dynetlsm_b200/csrc/dlsm_device.cuh"
+#include <cmath>
+#include <cstdio>
+#include <random>
+
+static long double ref(long double x)
+{
+    return (x > 0 ? x : 0.0L) + log1pl(expl(-fabsl(x)));
+}
+
+int main()
+{
+    double max_abs = 0, max_rel = 0, worst = 0;
+    std::mt19937_64 g(1);
+    std::uniform_real_distribution<double> U(-40.0, 40.0);
+    auto probe = [&](double x) {
+        const double got = dlsm::fast_log1pexp(x);
+        const long double want = ref((long double)x);
+        const double ae = (double)fabsl((long double)got - want);
+        const double re = (double)(ae / fabsl(want));
+        if (ae > max_abs) { max_abs = ae; worst = x; }
+        if (re > max_rel) max_rel = re;
+    };
+    for (int k = 0; k < 4000000; k++) probe(U(g));
+    for (int k = -4000; k <= 4000; k++) probe(k * 0.01);             // grid incl. 0 and the +-36 seam
+    for (int k = 0; k < 2000; k++) { probe(std::ldexp(1.0, -k % 60)); probe(-std::ldexp(1.0, -k % 60)); }
+    probe(36.0); probe(-36.0); probe(36.0000001); probe(-36.0000001); probe(700.0); probe(-700.0);
+    const double inf = INFINITY;
+    const int special_ok = std::isnan(dlsm::fast_log1pexp(NAN)) && dlsm::fast_log1pexp(inf) == inf &&
+                           dlsm::fast_log1pexp(-inf) == 0.0 && dlsm::fast_log1pexp(0.0) == std::log(2.0);
+    printf("%.3e %.3e %.6f %d\n", max_abs, max_rel, worst, special_ok);
+    return 0;
+}
