@@ -194,7 +194,9 @@ SweepParams sweep_params(dlsm_handle *h)
 size_t sweep_smem(const dlsm_handle *h, bool xs)
 {
     const size_t x = (size_t)h->cfg.T * h->cfg.n * h->cfg.d * sizeof(double);
-    return (xs ? x : 0) + (size_t)h->cfg.T * sizeof(int) + 16;
+    const int warps = h->cfg.T < 16 ? h->cfg.T : 16;
+    return (xs ? x : 0) + warps * sweep_stage_doubles(h->cfg.d) * sizeof(double) +
+           (size_t)h->cfg.T * sizeof(int) + 16;
 }
 
 constexpr size_t kMaxSmem = 227 * 1024;
@@ -210,12 +212,15 @@ int launch_sweep_t(dlsm_handle *h, const SweepParams &p, int warps)
     return DLSM_OK;
 }
 
+#ifndef DLSM_SWEEP_MINB
+#define DLSM_SWEEP_MINB 3
+#endif
 // Register budget follows the block size: chains with few time slices run 3 CTAs per SM.
 template <int LK, int D, bool XS>
 int launch_sweep_x(dlsm_handle *h, const SweepParams &p)
 {
     const int warps = h->cfg.T < 16 ? h->cfg.T : 16;
-    if (warps <= 10) return launch_sweep_t<LK, D, XS, 320, 3>(h, p, warps);
+    if (warps <= 10) return launch_sweep_t<LK, D, XS, 320, DLSM_SWEEP_MINB>(h, p, warps);
     return launch_sweep_t<LK, D, XS, 512, 2>(h, p, warps);
 }
 

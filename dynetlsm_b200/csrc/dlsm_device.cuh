@@ -99,60 +99,104 @@ __device__ __forceinline__ double log1pexp_naive(double eta) { return log(1.0 + 
 // ---------------------------------------------------------------------------------------------
 #define DLSM_X(v) v,
 __device__ const double d_exp_tab[32] = {DLSM_EXP_TAB(DLSM_X)};
-__device__ const double d_rcp_tab[64] = {DLSM_RCP_TAB(DLSM_X)};
-__device__ const double d_log_tab[64] = {DLSM_LOG_TAB(DLSM_X)};
+__device__ const double d_rcp_tab[65] = {DLSM_RCP_TAB(DLSM_X)};
+__device__ const double d_log_tab[65] = {DLSM_LOG_TAB(DLSM_X)};
 static const double h_exp_tab[32] = {DLSM_EXP_TAB(DLSM_X)};
-static const double h_rcp_tab[64] = {DLSM_RCP_TAB(DLSM_X)};
-static const double h_log_tab[64] = {DLSM_LOG_TAB(DLSM_X)};
+static const double h_rcp_tab[65] = {DLSM_RCP_TAB(DLSM_X)};
+static const double h_log_tab[65] = {DLSM_LOG_TAB(DLSM_X)};
 #undef DLSM_X
 
-__host__ __device__ __forceinline__ double fast_log1pexp(double eta)
+// scalar constants live in the constant bank so that DFMA takes them as c[][] operands instead of
+// burning registers / UMOV+IMAD pairs on 64-bit immediates
+#define DLSM_SP_CONSTS                                                                          \
+    {DLSM_32_OVER_LN2, 6755399441055744.0 /* 1.5*2^52 */, DLSM_LN2_32_HI, DLSM_LN2_32_LO,        \
+     1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0,                                  \
+     1.0 / 7.0, -1.0 / 6.0, 0.2, -0.25, 1.0 / 3.0, -0.5}
+__constant__ double d_spc[16] = DLSM_SP_CONSTS;
+static const double h_spc[16] = DLSM_SP_CONSTS;
+
+// log1p(exp(-|eta|)): the part of softplus that is left after splitting off max(eta, 0).
+// Branch-free and select-free on purpose (the sweep kernel is issue-bound, ncu profiles/r1):
+// independent evaluations in one thread interleave freely.
+//   t = e^{-a}:  a = n ln2/32 - r, |r| <= ln2/64;  t = 2^{-(n>>5)} 2^{-(n&31)/32} e^r   (deg 6)
+//   log1p(t):    y = 1 + t (rounding error c recovered); i = round(64 (y-1)), R = 1/(1 + i/64);
+//                z = y R - 1, |z| <= 1/128;  log y = -log R + (z - z^2/2 + ... + z^7/7);  + c R
+// n is clamped (unsigned) so that a > ~690 -- where t < 1e-300 -- cannot wrap the exponent.
+__host__ __device__ __forceinline__ double fast_log1pexp_neg(double a /* = |eta| */)
 {
 #ifdef __CUDA_ARCH__
-    const double *ET = d_exp_tab, *RT = d_rcp_tab, *LT = d_log_tab;
+    const double *ET = d_exp_tab, *RT = d_rcp_tab, *LT = d_log_tab, *K = d_spc;
 #else
-    const double *ET = h_exp_tab, *RT = h_rcp_tab, *LT = h_log_tab;
+    const double *ET = h_exp_tab, *RT = h_rcp_tab, *LT = h_log_tab, *K = h_spc;
 #endif
-    const double a = fabs(eta);
-    if (!(a <= 36.0)) { // rare tails (and NaN): e^{-a} < 2.4e-16, log1p(t) = t to double precision
-        if (a != a) return eta;
-        return (eta > 0.0 ? eta : 0.0) + exp(-a);
-    }
-    const double kMagic = 6755399441055744.0; // 1.5 * 2^52: round-to-nearest-integer by addition
-    const double kf = fma(a, DLSM_32_OVER_LN2, kMagic);
-    union { double f; long long i; } cv;
+    const double kf = fma(a, K[0], K[1]); // round(a * 32/ln2) lands in the low mantissa bits
+    union { double f; long long i; unsigned u[2]; } cv;
     cv.f = kf;
-    const int n = (int)(unsigned)(cv.i & 0xffffffffLL);
-    const double nf = kf - kMagic;
-    double r = fma(nf, DLSM_LN2_32_HI, -a);
-    r = fma(nf, DLSM_LN2_32_LO, r);
-    double p = fma(r, 1.0 / 720.0, 1.0 / 120.0);
-    p = fma(r, p, 1.0 / 24.0);
-    p = fma(r, p, 1.0 / 6.0);
-    p = fma(r, p, 0.5);
-    p = fma(r, p, 1.0);
-    p = fma(r, p, 1.0);
-    cv.f = p * ET[n & 31];
-    cv.i -= (long long)(n >> 5) << 52; // * 2^-(n>>5); stays normal (n>>5 <= 51)
+    const unsigned n = cv.u[0];
+    const double nf = kf - K[1];
+    double r = fma(nf, K[2], -a);
+    r = fma(nf, K[3], r);
+    double p = fma(r, K[4], K[5]);
+    p = fma(r, p, K[6]);
+    p = fma(r, p, K[7]);
+    p = fma(r, p, K[8]);
+    p = fma(r, p, K[9]);
+    p = fma(r, p, K[9]);
+    cv.f = p * ET[n & 31u];
+    const unsigned sh = n >> 5;
+    cv.u[1] -= (sh < 1000u ? sh : 1000u) << 20; // * 2^-(n>>5)
     const double t = cv.f;
-    const double y = 1.0 + t;
-    const double c = t - (y - 1.0);
+    const double y = K[9] + t;
+    const double c = t - (y - K[9]);
     cv.f = y;
-    const int hi = (int)(cv.i >> 32);
-    int i = (hi >> 14) & 63;
-    if (hi >= 0x40000000) i = 63; // y == 2 exactly (eta == 0)
+    unsigned i = (cv.u[1] - 0x3ff00000u + 0x2000u) >> 14; // 0..64
+    i = i < 64u ? i : 64u; // NaN / garbage never indexes out of the table
     const double R = RT[i];
-    const double z = fma(y, R, -1.0);
-    double q = fma(z, 1.0 / 7.0, -1.0 / 6.0);
-    q = fma(z, q, 0.2);
-    q = fma(z, q, -0.25);
-    q = fma(z, q, 1.0 / 3.0);
-    q = fma(z, q, -0.5);
-    q = fma(z, q, 1.0);
+    const double z = fma(y, R, -K[9]);
+    double q = fma(z, K[10], K[11]);
+    q = fma(z, q, K[12]);
+    q = fma(z, q, K[13]);
+    q = fma(z, q, K[14]);
+    q = fma(z, q, K[15]);
+    q = fma(z, q, K[9]);
     q = z * q;
-    double lg = fma(c, R, q) + LT[i];
-    if (t < 0x1p-20) lg = fma(-0.5 * t, t, t); // keep RELATIVE accuracy in the far-negative tail
-    return (eta > 0.0 ? eta : 0.0) + lg;
+    return fma(c, R, q) + LT[i];
+}
+
+// log(1 + e^eta) = max(eta, 0) + log1p(e^{-|eta|}); max(eta,0) = (eta + |eta|)/2 keeps NaN alive.
+// |abs error| < 1e-15 everywhere, relative error < 1e-15 in the negative tail
+// (tests/test_host_numerics.py).
+__host__ __device__ __forceinline__ double fast_log1pexp(double eta)
+{
+    const double a = fabs(eta);
+    return fma(0.5, a, 0.5 * eta) + fast_log1pexp_neg(a);
+}
+
+// One Bernoulli-logit term  y*eta - log(1 + e^eta)  with y in {0,1} passed as ym = y - 1/2:
+//     y eta - max(eta,0) - L = (y - 1/2) eta - |eta|/2 - L,   L = log1p(e^{-|eta|})
+// three fp64 instructions around L and no selects.
+__host__ __device__ __forceinline__ double logit_term(double ym, double eta)
+{
+    const double a = fabs(eta);
+    return fma(ym, eta, fma(-0.5, a, -fast_log1pexp_neg(a)));
+}
+
+// Branch-free fp64 sqrt: MUFU.RSQ64H seed (~22 bits) + two Goldschmidt steps + one correction;
+// within 1 ulp of IEEE sqrt.  1e-300 is added so that coincident points (s == 0) give 1e-150
+// instead of 0 * inf; it is absorbed exactly for every s > 1e-284.  NaN propagates.
+__device__ __forceinline__ double fast_sqrt(double s)
+{
+    s += 1e-300;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+    double g = s * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    return fma(fma(-g, g, s), h, g);
 }
 
 #ifndef DLSM_NAIVE_SOFTPLUS
@@ -166,6 +210,21 @@ __device__ __forceinline__ double warp_sum(double v)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
     return v;
+}
+
+// Reduce two per-lane partial sums over the warp with 6 double shuffles instead of 10: the first
+// exchange folds (a, b) so that lanes 0-15 carry a and lanes 16-31 carry b, four butterfly steps
+// finish both, one more exchange hands every lane both totals.
+__device__ __forceinline__ void warp_sum2(double &a, double &b, int lane)
+{
+    const bool up = lane & 16;
+    double keep = up ? b : a, give = up ? a : b;
+    keep += __shfl_xor_sync(kFull, give, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(kFull, keep, o);
+    const double other = __shfl_xor_sync(kFull, keep, 16);
+    a = up ? other : keep;
+    b = up ? keep : other;
 }
 
 // numpy pairwise_sum for n <= 8 (d <= 8 reductions in the priors): serial below 8, the

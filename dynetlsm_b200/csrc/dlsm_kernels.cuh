@@ -61,6 +61,15 @@ __device__ __forceinline__ double eta_directed(double b_in, double b_out, double
     return b_in * (1.0 - dist * rinv_recv) + b_out * (1.0 - dist * rinv_send);
 }
 
+// y in {0,1} -> y - 1/2 as a double, built from the adjacency bit with integer ops only
+__device__ __forceinline__ double ymask(uint32_t word, int lane)
+{
+    const uint32_t sign = ((~word >> lane) & 1u) << 31; // bit clear -> -0.5
+    return __hiloint2double((int)(0x3fe00000u | sign), 0);
+}
+
+__device__ __forceinline__ double vmask(bool v) { return __hiloint2double(v ? 0x3ff00000 : 0, 0); }
+
 // ---------------------------------------------------------------------------------------------
 // Per-node pairwise sums for the proposal (xn) and the current position (xo) of node j in slice
 // t, executed by one warp.  Returns the two log-likelihoods (warp-uniform).
@@ -74,63 +83,58 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
 {
     const int n = net.n, d = net.d;
     if (LK == kUndirected) {
-        // K1 static_network_fast.pyx:17-44.  Two 32-node chunks per trip: four independent
-        // sqrt/softplus chains per lane keep the fp64 pipe busy.
+        // K1 static_network_fast.pyx:17-44.  Two 32-node chunks per trip, branch- and select-free
+        // (out-of-range lanes and the self pair are evaluated on a clamped index and multiplied
+        // by a 0/1 mask): four independent sqrt/softplus chains per lane keep the fp64 pipe busy.
         const uint32_t *row = net.rowbits + ((size_t)t * n + j) * net.W;
         double an = 0.0, ao = 0.0, an2 = 0.0, ao2 = 0.0;
         for (int base = 0; base < n; base += 64) {
             const int i0 = base + lane, i1 = i0 + 32;
             const uint2 w = __ldg(reinterpret_cast<const uint2 *>(row + (base >> 5)));
-            if (i0 < n && i0 != j) {
-                double xi[DM];
-                load_pos<DM>(Xt + (size_t)i0 * d, d, xi);
-                const double en = b0 - sqrt(sqdist<DM>(xi, xn, d));
-                const double eo = b0 - sqrt(sqdist<DM>(xi, xo, d));
-                if ((w.x >> lane) & 1u) { an += en; ao += eo; }
-                an -= log1pexp(en);
-                ao -= log1pexp(eo);
-            }
-            if (i1 < n && i1 != j) {
-                double xi[DM];
-                load_pos<DM>(Xt + (size_t)i1 * d, d, xi);
-                const double en = b0 - sqrt(sqdist<DM>(xi, xn, d));
-                const double eo = b0 - sqrt(sqdist<DM>(xi, xo, d));
-                if ((w.y >> lane) & 1u) { an2 += en; ao2 += eo; }
-                an2 -= log1pexp(en);
-                ao2 -= log1pexp(eo);
-            }
+            const double v0 = vmask((i0 < n) && (i0 != j)), v1 = vmask((i1 < n) && (i1 != j));
+            const double y0 = ymask(w.x, lane), y1 = ymask(w.y, lane);
+            double xa[DM], xb[DM];
+            load_pos<DM>(Xt + (size_t)(i0 < n ? i0 : n - 1) * d, d, xa);
+            load_pos<DM>(Xt + (size_t)(i1 < n ? i1 : n - 1) * d, d, xb);
+            const double en0 = b0 - fast_sqrt(sqdist<DM>(xa, xn, d));
+            const double eo0 = b0 - fast_sqrt(sqdist<DM>(xa, xo, d));
+            const double en1 = b0 - fast_sqrt(sqdist<DM>(xb, xn, d));
+            const double eo1 = b0 - fast_sqrt(sqdist<DM>(xb, xo, d));
+            an = fma(v0, logit_term(y0, en0), an);
+            ao = fma(v0, logit_term(y0, eo0), ao);
+            an2 = fma(v1, logit_term(y1, en1), an2);
+            ao2 = fma(v1, logit_term(y1, eo1), ao2);
         }
-        ll_new = warp_sum(an + an2);
-        ll_old = warp_sum(ao + ao2);
+        ll_new = an + an2;
+        ll_old = ao + ao2;
+        warp_sum2(ll_new, ll_old, lane);
     } else if (LK == kDirected) {
-        // K2 directed_likelihoods_fast.pyx:46-80
+        // K2 directed_likelihoods_fast.pyx:46-80 (branch- and select-free, four chains per lane)
         const uint32_t *row = net.rowbits + ((size_t)t * n + j) * net.W;
         const uint32_t *col = net.colbits + ((size_t)t * n + j) * net.W;
         const double rj = rinv[j];
         double an = 0.0, ao = 0.0;
         for (int base = 0; base < n; base += 32) {
             const int i = base + lane;
-            const uint32_t wr = __ldg(row + (base >> 5));
-            const uint32_t wc = __ldg(col + (base >> 5));
-            if (i < n && i != j) {
-                double xi[DM];
-                load_pos<DM>(Xt + (size_t)i * d, d, xi);
-                const double ri = rinv[i];
-                const bool y_ji = (wr >> lane) & 1u; // Y[node, i]: node sends, i receives
-                const bool y_ij = (wc >> lane) & 1u; // Y[i, node]: i sends, node receives
-#pragma unroll
-                for (int v = 0; v < 2; v++) {
-                    const double dist = sqrt(sqdist<DM>(xi, v == 0 ? xn : xo, d));
-                    const double e1 = eta_directed(b0, b1, dist, ri, rj);
-                    const double e2 = eta_directed(b0, b1, dist, rj, ri);
-                    double acc = (y_ji ? e1 : 0.0) - log1pexp(e1);
-                    acc += (y_ij ? e2 : 0.0) - log1pexp(e2);
-                    if (v == 0) an += acc; else ao += acc;
-                }
-            }
+            const double y_ji = ymask(__ldg(row + (base >> 5)), lane); // Y[node, i]: node sends
+            const double y_ij = ymask(__ldg(col + (base >> 5)), lane); // Y[i, node]: i sends
+            const double v = vmask((i < n) && (i != j));
+            const int ic = i < n ? i : n - 1;
+            double xi[DM];
+            load_pos<DM>(Xt + (size_t)ic * d, d, xi);
+            const double ri = rinv[ic];
+            const double dn = fast_sqrt(sqdist<DM>(xi, xn, d));
+            const double dd = fast_sqrt(sqdist<DM>(xi, xo, d));
+            const double tn = logit_term(y_ji, eta_directed(b0, b1, dn, ri, rj)) +
+                              logit_term(y_ij, eta_directed(b0, b1, dn, rj, ri));
+            const double to = logit_term(y_ji, eta_directed(b0, b1, dd, ri, rj)) +
+                              logit_term(y_ij, eta_directed(b0, b1, dd, rj, ri));
+            an = fma(v, tn, an);
+            ao = fma(v, to, ao);
         }
-        ll_new = warp_sum(an);
-        ll_old = warp_sum(ao);
+        ll_new = an;
+        ll_old = ao;
+        warp_sum2(ll_new, ll_old, lane);
     } else {
         // K3 directed_likelihoods_fast.pyx:83-182 (case-control estimator)
         const size_t r = (size_t)t * n + j;
@@ -149,8 +153,8 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
             double xk[DM];
             load_pos<DM>(Xt + (size_t)k * d, d, xk);
             const double rk = rinv[k];
-            const double dn = sqrt(sqdist<DM>(xk, xn, d));
-            const double dd = sqrt(sqdist<DM>(xk, xo, d));
+            const double dn = fast_sqrt(sqdist<DM>(xk, xn, d));
+            const double dd = fast_sqrt(sqdist<DM>(xk, xo, d));
             const double r_recv = k_sends ? rj : rk, r_send = k_sends ? rk : rj;
             vn = eta_directed(b0, b1, dn, r_recv, r_send);
             vo = eta_directed(b0, b1, dd, r_recv, r_send);
@@ -158,14 +162,14 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
         for (int q = lane; q < indeg; q += 32) { // :108-119
             double vn, vo;
             eta_pair(ie[q], true, vn, vo);
-            e_n += vn - log1pexp(vn);
-            e_o += vo - log1pexp(vo);
+            e_n += logit_term(0.5, vn);
+            e_o += logit_term(0.5, vo);
         }
         for (int q = lane; q < outdeg; q += 32) { // :122-133
             double vn, vo;
             eta_pair(oe[q], false, vn, vo);
-            e_n += vn - log1pexp(vn);
-            e_o += vo - log1pexp(vo);
+            e_n += logit_term(0.5, vn);
+            e_o += logit_term(0.5, vo);
         }
         // usable controls = prefix of ctrl_in before its first -1 (:137; and :161, which tests the
         // IN list while walking the OUT list)
@@ -238,17 +242,28 @@ __device__ __forceinline__ double prior_next(const SweepParams &p, int c, int t,
     return half_sumsq_over<DM>(diff, d, p.sigma[(size_t)c * p.K + zn]);
 }
 
+// 0.5 * np.sum(v*v) * (1/s): the serial part of a node-update multiplies by a reciprocal prepared
+// once per 32-node block (1 ulp from the reference's division; decisions are unaffected)
 template <int DM>
-__device__ __forceinline__ double prior_prev(const SweepParams &p, int c, int t, int zc,
+__device__ __forceinline__ double half_sumsq_times(const double (&v)[DM], int d, double inv)
+{
+    double sq[DM];
+#pragma unroll
+    for (int k = 0; k < DM; k++) sq[k] = (k < d) ? __dmul_rn(v[k], v[k]) : 0.0;
+    return __dmul_rn(__dmul_rn(0.5, np_sum_small<DM>(sq, d)), inv);
+}
+
+template <int DM>
+__device__ __forceinline__ double prior_prev(const SweepParams &p, int c, int t, int zc, double inv,
                                              const double (&x)[DM], const double (&xprev)[DM])
 {
     const int d = p.net.d;
     double diff[DM];
     if (p.prior == 0) {
-        if (t == 0) return half_sumsq_over<DM>(x, d, p.tau_sq);
+        if (t == 0) return half_sumsq_times<DM>(x, d, inv);
 #pragma unroll
         for (int k = 0; k < DM; k++) diff[k] = (k < d) ? __dsub_rn(x[k], xprev[k]) : 0.0;
-        return half_sumsq_over<DM>(diff, d, p.sigma_sq);
+        return half_sumsq_times<DM>(diff, d, inv);
     }
     const double *mu = p.mu + ((size_t)c * p.K + zc) * d;
     if (t == 0) {
@@ -261,29 +276,25 @@ __device__ __forceinline__ double prior_prev(const SweepParams &p, int c, int t,
             diff[k] = (k < d) ? __dsub_rn(__dsub_rn(x[k], __dmul_rn(oml, xprev[k])), __dmul_rn(lm, mu[k]))
                               : 0.0;
     }
-    return half_sumsq_over<DM>(diff, d, p.sigma[(size_t)c * p.K + zc]);
+    return half_sumsq_times<DM>(diff, d, inv);
 }
 
-template <int DM>
-__device__ __forceinline__ void shfl_vec(double (&dst)[DM], const double (&src)[DM], int d, int from)
-{
-#pragma unroll
-    for (int k = 0; k < DM; k++)
-        if (k < d) dst[k] = __shfl_sync(kFull, src[k], from);
-        else dst[k] = 0.0;
-}
+// per-warp staging area of one 32-node block (shared memory)
+__host__ __device__ inline size_t sweep_stage_doubles(int d) { return (size_t)32 * (d + 5); }
 
 // ---------------------------------------------------------------------------------------------
 // k_sweep: one latent-position sweep of every chain.
-// grid = C chains, block = 32 * min(T, 16) threads, dynamic smem = [T*n*d doubles if XS] + T ints
+// grid = C chains, block = 32 * min(T, 16) threads,
+// dynamic smem = [T*n*d doubles if XS] + nwarps * 32*(d+5) doubles + T ints
 //
 // Each warp owns a time slice and walks its nodes in blocks of 32.  At the head of a block lane l
 // prepares everything that does not depend on the in-flight wavefront for node jb+l -- the
 // sampler state, the random draws (replay buffer or Philox + Box-Muller), the proposal
-// x0 + step*eps and the "next" prior terms -- so that work is done once per 32 nodes with all lanes
-// busy, with coalesced loads/stores.  The serial part of a node-update is then: broadcast by
-// shuffle, the 32-lane pairwise reduction, the wavefront flag, the "prev" prior term and the
-// accept/reject, which lane (j mod 32) commits.
+// x0 + step*eps, the "next" prior terms -- once per 32 nodes with all lanes busy and coalesced
+// loads, and parks it in a per-warp shared-memory stage.  The serial part of a node-update is then:
+// broadcast loads from the stage, the 32-lane pairwise reduction, the wavefront flag, the "prev"
+// prior term and the accept/reject, which lane (j mod 32) commits.  The Metropolis bookkeeping of
+// the 32 samplers runs lane-parallel at the end of the block.
 // ---------------------------------------------------------------------------------------------
 template <int LK, int D, bool XS, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
@@ -296,17 +307,24 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
     const size_t chain_elems = (size_t)T * n * d;
     double *Xg = p.X + (size_t)c * chain_elems;
     double *Xc;
-    volatile int *progress;
+    double *stage_base;
     if (XS) {
         Xc = reinterpret_cast<double *>(smem_raw);
-        progress = reinterpret_cast<volatile int *>(smem_raw + chain_elems * sizeof(double));
+        stage_base = Xc + chain_elems;
         for (size_t e = threadIdx.x; e < chain_elems; e += blockDim.x) Xc[e] = Xg[e];
     } else {
         Xc = Xg;
-        progress = reinterpret_cast<volatile int *>(smem_raw);
+        stage_base = reinterpret_cast<double *>(smem_raw);
     }
+    volatile int *progress =
+        reinterpret_cast<volatile int *>(stage_base + (size_t)nwarps * sweep_stage_doubles(d));
     for (int t = threadIdx.x; t < T; t += blockDim.x) progress[t] = 0;
     __syncthreads();
+
+    // stage layout: prop[32][d] | logu[32] | next_new[32] | next_old[32] | inv[32] | zc[32] (int)
+    double *st_prop = stage_base + (size_t)warp * sweep_stage_doubles(d);
+    double *st_logu = st_prop + 32 * d, *st_nn = st_logu + 32, *st_no = st_nn + 32, *st_inv = st_no + 32;
+    int *st_zc = reinterpret_cast<int *>(st_inv + 32);
 
     const double b0 = p.intercept[c * 2 + 0], b1 = p.intercept[c * 2 + 1];
     const double *rinv = (LK == kUndirected) ? nullptr : p.rinv + (size_t)c * n;
@@ -320,48 +338,54 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
             const int jl = jb + lane;
             const bool mine = jl < n;
             const size_t gs = ((size_t)c * T + t) * n + (mine ? jl : 0);
-            double my_x0[DM], my_x[DM], my_step = 0.0, my_logu = 0.0, my_next_new = 0.0,
-                                         my_next_old = 0.0;
-            int my_nacc = 0, my_nsteps = 0, my_until = 0, my_zc = 0;
-#pragma unroll
-            for (int k = 0; k < DM; k++) { my_x0[k] = 0.0; my_x[k] = 0.0; }
+            double my_step = 0.0;
+            int my_nacc = 0, my_nsteps = 0, my_until = 0, my_acc = 0;
             if (mine) {
-                double eps[DM];
-                load_pos<DM>(Xt + (size_t)jl * d, d, my_x0);
+                double eps[DM], x0[DM], x[DM], logu;
+                load_pos<DM>(Xt + (size_t)jl * d, d, x0);
                 my_step = p.step[gs]; my_nacc = p.nacc[gs]; my_nsteps = p.nsteps[gs]; my_until = p.until[gs];
                 if (p.eps) {
 #pragma unroll
                     for (int k = 0; k < DM; k++) eps[k] = (k < d) ? p.eps[gs * d + k] : 0.0;
-                    my_logu = p.logu[gs];
+                    logu = p.logu[gs];
                 } else {
-                    latent_draws<DM>(p.seed, (uint32_t)(t * n + jl), p.sweep, chain_id, d, eps, my_logu);
+                    latent_draws<DM>(p.seed, (uint32_t)(t * n + jl), p.sweep, chain_id, d, eps, logu);
                 }
                 // metropolis.py:44  x = x0 + step_size * randn(d): separately rounded mul and add
 #pragma unroll
-                for (int k = 0; k < DM; k++)
-                    my_x[k] = (k < d) ? __dadd_rn(my_x0[k], __dmul_rn(my_step, eps[k])) : 0.0;
-                if (p.prior != 0) my_zc = p.z[((size_t)c * T + t) * n + jl];
+                for (int k = 0; k < DM; k++) {
+                    x[k] = (k < d) ? __dadd_rn(x0[k], __dmul_rn(my_step, eps[k])) : 0.0;
+                    if (k < d) st_prop[lane * d + k] = x[k];
+                }
+                st_logu[lane] = logu;
+                double inv = (t == 0) ? 1.0 / p.tau_sq : 1.0 / p.sigma_sq; // LSM prior scales
+                int zc = 0;
+                if (p.prior != 0) {
+                    zc = p.z[((size_t)c * T + t) * n + jl];
+                    inv = 1.0 / p.sigma[(size_t)c * p.K + zc];
+                }
+                st_inv[lane] = inv;
+                st_zc[lane] = zc;
+                double nn = 0.0, no = 0.0;
                 if (t < T - 1) { // X[t+1, jl] is still last sweep's value: slice t+1 trails this one
                     double xnx[DM];
                     const volatile double *q = Xc + ((size_t)(t + 1) * n + jl) * d;
 #pragma unroll
                     for (int k = 0; k < DM; k++) xnx[k] = (k < d) ? q[k] : 0.0;
-                    my_next_new = prior_next<DM>(p, c, t, jl, my_x, xnx);
-                    my_next_old = prior_next<DM>(p, c, t, jl, my_x0, xnx);
+                    nn = prior_next<DM>(p, c, t, jl, x, xnx);
+                    no = prior_next<DM>(p, c, t, jl, x0, xnx);
                 }
+                st_nn[lane] = nn;
+                st_no[lane] = no;
             }
+            __syncwarp();
             const int jend = (n - jb) < 32 ? (n - jb) : 32;
             // ---------------- serial node-updates of this block ----------------
             for (int jj = 0; jj < jend; jj++) {
                 const int j = jb + jj;
                 double x[DM], x0[DM];
-                shfl_vec<DM>(x, my_x, d, jj);
-                shfl_vec<DM>(x0, my_x0, d, jj);
-                const double logu = __shfl_sync(kFull, my_logu, jj);
-                const double nx_new = __shfl_sync(kFull, my_next_new, jj);
-                const double nx_old = __shfl_sync(kFull, my_next_old, jj);
-                const int zc = __shfl_sync(kFull, my_zc, jj);
-
+                load_pos<DM>(st_prop + jj * d, d, x);
+                load_pos<DM>(Xt + (size_t)j * d, d, x0);
                 if (LK != kCaseControl && j + 1 < n && lane * 32 < p.net.W) { // next row -> L1
                     const size_t o = ((size_t)t * n + j + 1) * p.net.W + lane * 32;
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(p.net.rowbits + o));
@@ -374,43 +398,45 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
                 double xp[DM];
 #pragma unroll
                 for (int k = 0; k < DM; k++) xp[k] = 0.0;
-                if (t > 0) { // wavefront: X[t-1, j] must be this sweep's value
-                    if (lane == 0)
-                        while (progress[t - 1] <= j) { /* spin on shared memory */ }
+                if (t > 0) { // wavefront: X[t-1, j] must be this sweep's value (uniform poll)
+                    while (progress[t - 1] <= j) { /* spin on shared memory */ }
                     __threadfence_block();
-                    __syncwarp();
                     const volatile double *q = Xc + ((size_t)(t - 1) * n + j) * d;
 #pragma unroll
                     for (int k = 0; k < DM; k++) if (k < d) xp[k] = q[k];
                 }
-                double lp_new = __dsub_rn(ll_new, prior_prev<DM>(p, c, t, zc, x, xp));
-                double lp_old = __dsub_rn(ll_old, prior_prev<DM>(p, c, t, zc, x0, xp));
+                const double inv = st_inv[jj];
+                const int zc = st_zc[jj];
+                double lp_new = __dsub_rn(ll_new, prior_prev<DM>(p, c, t, zc, inv, x, xp));
+                double lp_old = __dsub_rn(ll_old, prior_prev<DM>(p, c, t, zc, inv, x0, xp));
                 if (t < T - 1) {
-                    lp_new = __dsub_rn(lp_new, nx_new);
-                    lp_old = __dsub_rn(lp_old, nx_old);
+                    lp_new = __dsub_rn(lp_new, st_nn[jj]);
+                    lp_old = __dsub_rn(lp_old, st_no[jj]);
                 }
                 const double ratio = __dsub_rn(lp_new, lp_old);
-                const int acc = (logu >= ratio) ? 0 : 1; // metropolis.py:50 (a NaN ratio accepts)
-                if (lane == jj) {
+                const int acc = (st_logu[jj] >= ratio) ? 0 : 1; // metropolis.py:50 (NaN accepts)
+                const bool me = lane == jj;
+                my_acc = me ? acc : my_acc;
+                nonfinite |= me && (!(ratio == ratio) || ratio - ratio != 0.0);
+                if (me) {
                     if (acc) {
 #pragma unroll
                         for (int k = 0; k < DM; k++) if (k < d) Xt[(size_t)j * d + k] = x[k];
                     }
-                    metropolis_bookkeep(my_step, my_nacc, my_nsteps, my_until, p.tune,
-                                        p.tune_interval, acc, false);
-                    const size_t gsj = ((size_t)c * T + t) * n + j;
-                    if (p.accepted) p.accepted[gsj] = acc;
-                    if (p.ratio) p.ratio[gsj] = ratio;
-                    if (!(ratio == ratio) || ratio - ratio != 0.0) nonfinite = true;
+                    if (p.ratio) p.ratio[((size_t)c * T + t) * n + j] = ratio;
                     __threadfence_block();
                     progress[t] = j + 1;
                 }
                 __syncwarp();
             }
-            // ---------------- coalesced write-back of the sampler state ----------------
+            // ---------------- lane-parallel Metropolis bookkeeping + coalesced write-back --------
             if (mine) {
+                metropolis_bookkeep(my_step, my_nacc, my_nsteps, my_until, p.tune, p.tune_interval,
+                                    my_acc, false);
                 p.step[gs] = my_step; p.nacc[gs] = my_nacc; p.nsteps[gs] = my_nsteps; p.until[gs] = my_until;
+                if (p.accepted) p.accepted[gs] = my_acc;
             }
+            __syncwarp();
         }
     }
     if (nonfinite) atomicOr(p.flags, 1u);
@@ -568,14 +594,13 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
             for (int base = ((i + 1) >> 5) << 5; base < n; base += 32) {
                 const int j = base + lane;
                 const uint32_t w = __ldg(row + (base >> 5));
-                if (j < n && j > i) {
+                {
+                    const double v = vmask(j < n && j > i), y = ymask(w, lane);
                     double xj[DM];
-                    load_pos<DM>(Xt + (size_t)j * d, d, xj);
-                    const double dist = sqrt(sqdist<DM>(xj, xi, d));
-                    const double e0 = b00 - dist, e1 = b10 - dist;
-                    if ((w >> lane) & 1u) { a0 += e0; a1 += e1; }
-                    a0 -= log1pexp(e0);
-                    a1 -= log1pexp(e1);
+                    load_pos<DM>(Xt + (size_t)(j < n ? j : n - 1) * d, d, xj);
+                    const double dist = fast_sqrt(sqdist<DM>(xj, xi, d));
+                    a0 = fma(v, logit_term(y, b00 - dist), a0);
+                    a1 = fma(v, logit_term(y, b10 - dist), a1);
                 }
             }
         } else if (LK == kDirected) {
@@ -588,25 +613,18 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
                 const int j = base + lane;
                 const uint32_t wr = __ldg(row + (base >> 5));
                 const uint32_t wc = __ldg(col + (base >> 5));
-                if (j < n && j > i) {
+                {
+                    const double v = vmask(j < n && j > i);
+                    const double y_ij = ymask(wr, lane), y_ji = ymask(wc, lane);
+                    const int jc = j < n ? j : n - 1;
                     double xj[DM];
-                    load_pos<DM>(Xt + (size_t)j * d, d, xj);
-                    const double dist = sqrt(sqdist<DM>(xj, xi, d));
-                    const bool y_ij = (wr >> lane) & 1u, y_ji = (wc >> lane) & 1u;
-                    {
-                        const double rj = r0[j];
-                        const double e_ij = eta_directed(b00, b01, dist, rj, ri0);
-                        const double e_ji = eta_directed(b00, b01, dist, ri0, rj);
-                        a0 += (y_ij ? e_ij : 0.0) - log1pexp(e_ij);
-                        a0 += (y_ji ? e_ji : 0.0) - log1pexp(e_ji);
-                    }
-                    {
-                        const double rj = r1[j];
-                        const double e_ij = eta_directed(b10, b11, dist, rj, ri1);
-                        const double e_ji = eta_directed(b10, b11, dist, ri1, rj);
-                        a1 += (y_ij ? e_ij : 0.0) - log1pexp(e_ij);
-                        a1 += (y_ji ? e_ji : 0.0) - log1pexp(e_ji);
-                    }
+                    load_pos<DM>(Xt + (size_t)jc * d, d, xj);
+                    const double dist = fast_sqrt(sqdist<DM>(xj, xi, d));
+                    const double rj0 = r0[jc], rj1 = r1[jc];
+                    a0 = fma(v, logit_term(y_ij, eta_directed(b00, b01, dist, rj0, ri0)) +
+                                    logit_term(y_ji, eta_directed(b00, b01, dist, ri0, rj0)), a0);
+                    a1 = fma(v, logit_term(y_ij, eta_directed(b10, b11, dist, rj1, ri1)) +
+                                    logit_term(y_ji, eta_directed(b10, b11, dist, ri1, rj1)), a1);
                 }
             }
         } else {
@@ -622,11 +640,11 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
                 const int k = oe[q];
                 double xk[DM];
                 load_pos<DM>(Xt + (size_t)k * d, d, xk);
-                const double dist = sqrt(sqdist<DM>(xk, xi, d));
+                const double dist = fast_sqrt(sqdist<DM>(xk, xi, d));
                 const double v0 = eta_directed(b00, b01, dist, r0[k], ri0);
                 const double v1 = eta_directed(b10, b11, dist, r1[k], ri1);
-                e0 += v0 - log1pexp(v0);
-                e1 += v1 - log1pexp(v1);
+                e0 += logit_term(0.5, v0);
+                e1 += logit_term(0.5, v1);
             }
             int m = p.net.n_control;
             for (int base = 0; base < p.net.n_control; base += 32) {
@@ -639,7 +657,7 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
                 const int k = co[q];
                 double xk[DM];
                 load_pos<DM>(Xt + (size_t)k * d, d, xk);
-                const double dist = sqrt(sqdist<DM>(xk, xi, d));
+                const double dist = fast_sqrt(sqdist<DM>(xk, xi, d));
                 c0 += log1pexp(eta_directed(b00, b01, dist, r0[k], ri0));
                 c1 += log1pexp(eta_directed(b10, b11, dist, r1[k], ri1));
             }
