@@ -752,18 +752,32 @@ static int labels_async(dlsm_handle *h, const double *d_U, double *lik_out, int 
     p.z = F<int32_t>(h, DLSM_F_Z);
     p.ncount = F<double>(h, DLSM_F_NCOUNT); p.nk = F<int32_t>(h, DLSM_F_NK);
     p.lik_out = lik_out; p.sample = sample;
-    const int wpb = 4;
-    const size_t per_warp = ((size_t)c.T * c.K + 3 * c.K) * sizeof(double);
-    const size_t smem = per_warp * wpb;
-    if (smem > kMaxSmem) FAIL(h, DLSM_ERR_UNSUPPORTED, "T*K too large for the label kernel");
-    CU(h, cudaFuncSetAttribute(k_ffbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (sample) {
         CU(h, cudaMemsetAsync(p.ncount, 0, h->field_bytes[DLSM_F_NCOUNT], h->stream));
         CU(h, cudaMemsetAsync(p.nk, 0, h->field_bytes[DLSM_F_NK], h->stream));
     }
-    const size_t warps = (size_t)c.n_chains * c.n;
+    // thread-per-node kernel when its [T*K + 2K][TPB] shared-memory stage fits, else warp-per-node
+    const size_t per_thread = ((size_t)c.T * c.K + 2 * c.K) * sizeof(double);
+    const size_t extra = (size_t)c.K * (c.d + 2) * sizeof(double);
+    int rc;
     begin_phase(h, 1);
-    int rc = launch_simple(h, k_ffbs, dim3((unsigned)((warps + wpb - 1) / wpb)), dim3(wpb * 32), smem, p);
+    if (per_thread * 64 + extra <= kMaxSmem / 2) {
+        const size_t smem = per_thread * 64 + extra;
+        CU(h, cudaFuncSetAttribute(k_ffbs_t<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rc = launch_simple(h, k_ffbs_t<64>, dim3((c.n + 63) / 64, c.n_chains), dim3(64), smem, p);
+    } else if (per_thread * 32 + extra <= kMaxSmem) {
+        const size_t smem = per_thread * 32 + extra;
+        CU(h, cudaFuncSetAttribute(k_ffbs_t<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rc = launch_simple(h, k_ffbs_t<32>, dim3((c.n + 31) / 32, c.n_chains), dim3(32), smem, p);
+    } else {
+        const int wpb = 4;
+        const size_t per_warp = ((size_t)c.T * c.K + 3 * c.K) * sizeof(double);
+        const size_t smem = per_warp * wpb;
+        if (smem > kMaxSmem) FAIL(h, DLSM_ERR_UNSUPPORTED, "T*K too large for the label kernel");
+        CU(h, cudaFuncSetAttribute(k_ffbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t warps = (size_t)c.n_chains * c.n;
+        rc = launch_simple(h, k_ffbs, dim3((unsigned)((warps + wpb - 1) / wpb)), dim3(wpb * 32), smem, p);
+    }
     end_phase(h);
     if (sample && !d_U) h->sweep_idx[kRngLabels] += 1;
     return rc;

@@ -5,6 +5,7 @@
 // contract them into FMAs: the reference (Cython built for baseline x86-64, numpy elementwise
 // ops) rounds every multiply and add separately, and accepted states must be bit-identical.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "dlsm_tables.cuh"
@@ -99,9 +100,11 @@ __device__ __forceinline__ double log1pexp_naive(double eta) { return log(1.0 + 
 // ---------------------------------------------------------------------------------------------
 #define DLSM_X(v) v,
 __device__ const double d_exp_tab[32] = {DLSM_EXP_TAB(DLSM_X)};
+__device__ const double d_expp_tab[32] = {DLSM_EXPP_TAB(DLSM_X)};
 __device__ const double d_rcp_tab[65] = {DLSM_RCP_TAB(DLSM_X)};
 __device__ const double d_log_tab[65] = {DLSM_LOG_TAB(DLSM_X)};
 static const double h_exp_tab[32] = {DLSM_EXP_TAB(DLSM_X)};
+static const double h_expp_tab[32] = {DLSM_EXPP_TAB(DLSM_X)};
 static const double h_rcp_tab[65] = {DLSM_RCP_TAB(DLSM_X)};
 static const double h_log_tab[65] = {DLSM_LOG_TAB(DLSM_X)};
 #undef DLSM_X
@@ -179,6 +182,39 @@ __host__ __device__ __forceinline__ double logit_term(double ym, double eta)
 {
     const double a = fabs(eta);
     return fma(ym, eta, fma(-0.5, a, -fast_log1pexp_neg(a)));
+}
+
+// Branch-free fp64 exp(x) on the same tables (relative error < 1e-15 for |x| < 700; flushes to 0
+// below x = -708 where the reference's libm returns denormals, +inf above 709.7).
+__host__ __device__ __forceinline__ double fast_exp(double x)
+{
+#ifdef __CUDA_ARCH__
+    const double *PT = d_expp_tab, *K = d_spc;
+#else
+    const double *PT = h_expp_tab, *K = h_spc;
+#endif
+    const double xc = fmin(fmax(x, -1000.0), 1000.0); // keeps the integer part in range; NaN -> handled below
+    const double kf = fma(xc, K[0], K[1]);
+    union { double f; long long i; unsigned u[2]; int s[2]; } cv;
+    cv.f = kf;
+    const int n = cv.s[0];
+    const double nf = kf - K[1];
+    double r = fma(nf, -K[2], xc);
+    r = fma(nf, -K[3], r);
+    double p = fma(r, K[4], K[5]);
+    p = fma(r, p, K[6]);
+    p = fma(r, p, K[7]);
+    p = fma(r, p, K[8]);
+    p = fma(r, p, K[9]);
+    p = fma(r, p, K[9]);
+    cv.f = p * PT[n & 31];
+    int e = n >> 5;
+    e = e < -1022 ? -1022 : (e > 1023 ? 1023 : e);
+    cv.s[1] += e << 20;
+    double v = cv.f;
+    v = (x < -708.0) ? 0.0 : v;
+    v = (x > 709.7) ? (double)INFINITY : v;
+    return (x != x) ? x : v;
 }
 
 // Branch-free fp64 sqrt: MUFU.RSQ64H seed (~22 bits) + two Goldschmidt steps + one correction;

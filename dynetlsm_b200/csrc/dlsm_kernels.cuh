@@ -1044,4 +1044,132 @@ __global__ void __launch_bounds__(128) k_ffbs(const LabelParams p)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_ffbs_t: HDP-HMM label block sampler, one THREAD per (chain, node) -- the production mapping.
+// The per-node recursion is strictly sequential in t and only K wide, so a warp per node leaves
+// two thirds of the lanes idle and pays a shuffle/sync per step (k_ffbs above, kept as the
+// fallback for very large T*K).  Here every lane runs its own node; the T*K partial marginals and
+// the two K-vectors of backward messages live in shared memory, laid out [entry][thread] so that a
+// warp's accesses are conflict-free.  grid = (ceil(n/TPB), C), block = TPB (32 or 64).
+// dynamic smem = (T*K + 2K) * TPB doubles + K*(d+2) doubles.
+// ---------------------------------------------------------------------------------------------
+template <int TPB>
+__global__ void __launch_bounds__(TPB) k_ffbs_t(const LabelParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = p.T, n = p.n, d = p.d, K = p.K;
+    const int c = blockIdx.y, tid = threadIdx.x;
+    const int i = blockIdx.x * TPB + tid;
+    const bool valid = i < n;
+    const int ic = valid ? i : n - 1;
+    double *pm = reinterpret_cast<double *>(smem_raw);  // [T*K][TPB]
+    double *bwA = pm + (size_t)T * K * TPB;             // [K][TPB]
+    double *bwB = bwA + (size_t)K * TPB;                // [K][TPB]
+    double *s_mu = bwB + (size_t)K * TPB;               // [K][d]
+    double *s_ln = s_mu + (size_t)K * d;                // [K]  -(d/2) log(2 pi var)
+    double *s_hv = s_ln + K;                            // [K]  0.5 * (1 / var)
+    const double *X = p.X + (size_t)c * T * n * d;
+    const double *w = p.w + (size_t)c * T * K * K;
+    const double lm = p.lambda[c], oml = __dsub_rn(1.0, lm);
+    for (int k = tid; k < K; k += TPB) {
+        const double var = p.sigma[(size_t)c * K + k];
+        s_ln[k] = __dmul_rn(__dmul_rn(-0.5, (double)d), log(__dmul_rn(6.283185307179586, var)));
+        s_hv[k] = __dmul_rn(0.5, __ddiv_rn(1.0, var));
+    }
+    for (int e = tid; e < K * d; e += TPB) s_mu[e] = p.mu[(size_t)c * K * d + e];
+    __syncthreads();
+
+    // K7 emission densities (gaussian_likelihood_fast.pyx:17-54), normalize=False
+    double xprev[kMaxD], xt[kMaxD];
+#pragma unroll
+    for (int q = 0; q < kMaxD; q++) xprev[q] = 0.0;
+    for (int t = 0; t < T; t++) {
+        const double *xg = X + ((size_t)t * n + ic) * d;
+#pragma unroll
+        for (int q = 0; q < kMaxD; q++) xt[q] = (q < d) ? xg[q] : 0.0;
+        for (int k = 0; k < K; k++) {
+            double sum_sq = 0.0;
+#pragma unroll
+            for (int q = 0; q < kMaxD; q++)
+                if (q < d) {
+                    const double m = s_mu[k * d + q];
+                    const double mean = (t == 0) ? m : __dadd_rn(__dmul_rn(lm, m), __dmul_rn(oml, xprev[q]));
+                    const double df = __dsub_rn(xt[q], mean);
+                    sum_sq = __dadd_rn(sum_sq, __dmul_rn(df, df));
+                }
+            const double L = fast_exp(__dsub_rn(s_ln[k], __dmul_rn(sum_sq, s_hv[k])));
+            pm[(size_t)(t * K + k) * TPB + tid] = L;
+            if (p.lik_out && valid) p.lik_out[(((size_t)c * n + i) * T + t) * K + k] = L;
+        }
+#pragma unroll
+        for (int q = 0; q < kMaxD; q++) xprev[q] = xt[q];
+    }
+    if (!p.sample) return;
+
+    // backward messages (sample_labels.py:164-169); bwds_msg[T-1] stays all ones
+    double *bcur = bwA, *bprev = bwB;
+    for (int k = 0; k < K; k++) bcur[k * TPB + tid] = 1.0;
+    for (int t = T - 1; t > 0; t--) {
+        for (int k = 0; k < K; k++) {
+            const size_t o = (size_t)(t * K + k) * TPB + tid;
+            pm[o] = __dmul_rn(pm[o], bcur[k * TPB + tid]);
+        }
+        for (int j = 0; j < K; j++) {
+            const double *wr = w + ((size_t)t * K + j) * K;
+            double sacc = 0.0;
+            for (int k = 0; k < K; k++)
+                sacc = __dadd_rn(sacc, __dmul_rn(__ldg(wr + k), pm[(size_t)(t * K + k) * TPB + tid]));
+            bprev[j * TPB + tid] = sacc;
+        }
+        // np.sum over K entries: numpy's pairwise order (serial below 8, 8 accumulators above)
+        double tot;
+        if (K < 8) {
+            tot = -0.0;
+            for (int k = 0; k < K; k++) tot = __dadd_rn(tot, bprev[k * TPB + tid]);
+        } else {
+            double r8[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) r8[q] = bprev[q * TPB + tid];
+            int k = 8;
+            for (; k < K - (K % 8); k += 8)
+#pragma unroll
+                for (int q = 0; q < 8; q++) r8[q] = __dadd_rn(r8[q], bprev[(k + q) * TPB + tid]);
+            tot = __dadd_rn(__dadd_rn(__dadd_rn(r8[0], r8[1]), __dadd_rn(r8[2], r8[3])),
+                            __dadd_rn(__dadd_rn(r8[4], r8[5]), __dadd_rn(r8[6], r8[7])));
+            for (; k < K; k++) tot = __dadd_rn(tot, bprev[k * TPB + tid]);
+        }
+        for (int j = 0; j < K; j++) bprev[j * TPB + tid] = __ddiv_rn(bprev[j * TPB + tid], tot);
+        double *tmp = bcur; bcur = bprev; bprev = tmp;
+    }
+    for (int k = 0; k < K; k++) pm[(size_t)k * TPB + tid] = __dmul_rn(pm[(size_t)k * TPB + tid], bcur[k * TPB + tid]);
+
+    // forward sampling (:173-188): cumsum, u = cdf[-1] * U, z = #{k : u > cdf[k]}
+    double *cdf = bprev; // reuse
+    int zp = 0;
+    for (int t = 0; t < T; t++) {
+        const double *wr = (t == 0) ? w : w + ((size_t)t * K + zp) * K;
+        double cs = 0.0;
+        for (int k = 0; k < K; k++) {
+            const double pr = __dmul_rn(wr[k], pm[(size_t)(t * K + k) * TPB + tid]);
+            cs = (k == 0) ? pr : __dadd_rn(cs, pr);
+            cdf[k * TPB + tid] = cs;
+        }
+        double U;
+        if (p.U) U = p.U[((size_t)c * n + ic) * T + t];
+        else U = philox_u2(p.seed, (uint32_t)(ic * T + t), p.sweep, (uint32_t)c + p.chain_offset,
+                           kRngLabels, 0).a;
+        const double u = __dmul_rn(cs, U);
+        int zz = 0;
+        for (int k = 0; k < K; k++) zz += (u > cdf[k * TPB + tid]) ? 1 : 0;
+        if (zz >= K) zz = K - 1;
+        if (valid) {
+            p.z[((size_t)c * T + t) * n + i] = zz;
+            if (t == 0) atomicAdd(&p.ncount[(size_t)c * T * K * K + zz], 1.0);
+            else atomicAdd(&p.ncount[(((size_t)c * T + t) * K + zp) * K + zz], 1.0);
+            atomicAdd(&p.nk[((size_t)c * T + t) * K + zz], 1);
+        }
+        zp = zz;
+    }
+}
+
 } // namespace dlsm

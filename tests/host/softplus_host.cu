@@ -40,6 +40,18 @@ int main()
             if (ae > max_term) max_term = ae;
         }
     }
-    printf("%.3e %.3e %.6f %d %.3e\n", max_abs, max_rel, worst, special_ok, max_term);
+    // fast_exp against expl
+    double max_exp_rel = 0;
+    std::uniform_real_distribution<double> V(-700.0, 700.0);
+    for (int k = 0; k < 2000000; k++) {
+        const double x = (k & 1) ? V(g) : U(g);
+        const long double want = expl((long double)x);
+        const double re = (double)(fabsl((long double)dlsm::fast_exp(x) - want) / want);
+        if (re > max_exp_rel) max_exp_rel = re;
+    }
+    const int exp_special = dlsm::fast_exp(-800.0) == 0.0 && std::isinf(dlsm::fast_exp(720.0)) &&
+                            std::isnan(dlsm::fast_exp(NAN)) && dlsm::fast_exp(0.0) == 1.0;
+    printf("%.3e %.3e %.6f %d %.3e %.3e %d\n", max_abs, max_rel, worst, special_ok, max_term,
+           max_exp_rel, exp_special);
     return 0;
 }

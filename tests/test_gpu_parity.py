@@ -383,10 +383,12 @@ def test_full_device_sweeps_are_deterministic_and_chain_independent():
     assert np.allclose(Xa.mean(axis=(1, 2)), 0, atol=1e-12)  # centred
 
 
-def test_labels_native_vs_oracle_with_device_uniforms_property():
-    """FFBS with recorded uniforms on a larger random problem vs the oracle (exact labels)."""
+@pytest.mark.parametrize("T,n,d,K", [(10, 200, 2, 12),   # thread-per-node, 64 threads per CTA
+                                     (12, 70, 3, 40),    # thread-per-node, 32 threads per CTA
+                                     (20, 40, 2, 60)])   # warp-per-node fallback (T*K too large)
+def test_labels_vs_oracle_all_kernel_variants(T, n, d, K):
+    """FFBS with recorded uniforms on larger random problems vs the oracle (exact labels)."""
     L = _F()
-    T, n, d, K = 10, 200, 2, 12
     rng = np.random.RandomState(8)
     X = rng.randn(T, n, d)
     mu = rng.randn(K, d) * 1.5

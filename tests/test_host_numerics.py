@@ -14,5 +14,6 @@ def test_fast_log1pexp_accuracy(tmp_path):
     max_abs, max_rel, special_ok = float(out[0]), float(out[1]), int(out[3])
     assert max_abs < 4e-15      # half an ulp of the largest results (|x| ~ 40)
     assert max_rel < 2e-15      # relative accuracy holds in the far-negative tail too
+    assert float(out[5]) < 1e-15 and int(out[6]) == 1   # fast_exp: relative error, special values
     assert float(out[4]) < 4e-15  # y*eta - log(1+e^eta) fused term, |eta| <= 20
     assert special_ok == 1      # NaN propagates, huge |x| and 0 are exact
