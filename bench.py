@@ -370,8 +370,16 @@ def main():
     bpl = bytes_per_node_update(w) * upd_per_step
     lat_per_launch_ms = latent_ms / args.steps
     achieved = bpl / (lat_per_launch_ms * 1e-3) / 1e9
+    traffic = None
+    try:  # measured DRAM bytes of one k_sweep launch from the committed ncu --set full capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        if tr and tr["chains"] == chains:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "k_sweep", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "algorithmic_bytes_per_launch": bpl,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "bytes_per_node_update": bytes_per_node_update(w),
                 "kernel_ms_per_launch": lat_per_launch_ms,
