@@ -1,0 +1,247 @@
+"""``DynamicNetworkHDPLPCM`` -- the reference estimator's API (hdp_lpcm.py:144-1330) over the
+device sampler.
+
+Per sweep the device runs the hot path -- mixture-prior latent-position sweep, centring,
+intercept / radii MH on the full-network likelihood, HDP-HMM label forward-filter /
+backward-sample -- and hands the label counts to the host, which performs the reference's
+conjugate and auxiliary-variable updates in numpy (``hdp_updates.py``; SURVEY.md 8f-1 marks a
+device version of that block as the next step).  ``sampler='replay'`` draws every random number
+from the numpy ``RandomState`` in the reference's order, so the chain reproduces the reference's.
+
+Post-processing that the reference delegates to its ``model_selection`` package (approximate BIC,
+posterior-expected VI) is outside the accelerated path: ``selection_type`` is accepted, and the
+reported point estimate is the maximum-a-posteriori draw after burn-in; co-clustering
+probabilities, posterior means and the Procrustes alignment of the traces are computed as in the
+reference (hdp_lpcm.py:1141-1153, label_utils.py:40-62).
+"""
+import numpy as np
+from sklearn.utils import check_array, check_random_state
+
+from . import _lib as L
+from .case_control_likelihood import DirectedCaseControlSampler
+from .hdp_updates import HDPHyper, conjugate_updates, hdp_log_prior
+from .host_init import longitudinal_kmeans, longitudinal_procrustes_rotation
+from .lsm import DynamicNetworkLSM, _Driver
+
+__all__ = ["DynamicNetworkHDPLPCM"]
+
+
+class DynamicNetworkHDPLPCM(object):
+    def __init__(self, n_features=2, n_components=10, is_directed=False, selection_type="vi",
+                 n_iter=5000, tune=2500, tune_interval=100, burn=2500, thin=None, gamma=1.0,
+                 gamma_prior_shape=1.0, gamma_prior_rate=0.1, alpha_init=1.0, alpha_init_shape=1.,
+                 alpha_init_rate=1., alpha=1.0, kappa=4.0, alpha_kappa_shape=5,
+                 alpha_kappa_rate=0.1, intercept_prior="auto", intercept_variance_prior=2,
+                 mean_variance_prior="auto", a=2.0, b="auto", lambda_prior=0.9,
+                 lambda_variance_prior=0.01, sigma_prior_std=4.0, mean_variance_prior_std=4.0,
+                 step_size_X="auto", step_size_intercept=0.1, step_size_radii=175000,
+                 n_control=None, n_resample_control=100, copy=True, random_state=None,
+                 sampler="device", device=0):
+        for k, v in list(locals().items()):
+            if k != "self":
+                setattr(self, k, v)
+
+    @property
+    def n_burn_(self):
+        return (self.burn or 0) + (self.tune or 0)
+
+    def fit(self, Y):
+        replay = self.sampler == "replay"
+        if self.sampler not in ("device", "replay"):
+            raise ValueError("`sampler` must be 'device' or 'replay', got {}".format(self.sampler))
+        T, n, _ = Y.shape
+        K, d = self.n_components, self.n_features
+        rng = check_random_state(self.random_state)
+        Y = check_array(Y, dtype=np.float64, ensure_all_finite="allow-nan", ensure_2d=False,
+                        allow_nd=True, copy=self.copy)
+        if np.any(Y == -1) or np.any(np.isnan(Y)):
+            raise NotImplementedError("missing dyads (-1 / NaN) are not supported by the device sampler")
+        self.Y_fit_ = Y
+        if self.burn is not None:
+            self.n_iter += self.burn
+        if self.tune is not None:
+            self.n_iter += self.tune
+        S, m = self.n_iter, (2 if self.is_directed else 1)
+
+        # ---- init_sampler (hdp_lpcm.py:48-141): a short LSM run, then k-means on its MAP ----
+        lsm_kw = dict(n_iter=500, n_features=d, tune=250, burn=250, is_directed=self.is_directed,
+                      random_state=rng, sampler=self.sampler, device=self.device)
+        if self.is_directed:
+            lsm_kw.update(sigma_sq=0.001, tau_sq="auto", step_size_X=0.0075,
+                          n_control=self.n_control, n_resample_control=self.n_resample_control)
+        else:
+            lsm_kw.update(sigma_sq=0.1, tau_sq=2.0, step_size_X=0.1)
+        emb = DynamicNetworkLSM(**lsm_kw).fit(Y)
+        self.lsm_init_ = emb
+        Xs = np.zeros((S, T, n, d)); Xs[0] = emb.X_
+        ics = np.zeros((S, m)); ics[0] = emb.intercept_
+        rads = None
+        if self.is_directed:
+            rads = np.zeros((S, n)); rads[0] = emb.radii_
+        zs = np.zeros((S, T, n), dtype=np.int64)
+        mus = np.zeros((S, K, d)); sigmas = np.zeros((S, K))
+        mus[0], sigmas[0], zs[0] = longitudinal_kmeans(Xs[0], n_clusters=K, random_state=rng)
+        weights = np.zeros((S, T, K, K))
+        weights[0, 0, 0] = np.bincount(zs[0, 0], minlength=K) / n
+        lambdas = np.zeros((S, 1)); lambdas[0] = self.lambda_prior
+        betas = np.zeros((S, K))
+        betas[0] = rng.dirichlet(np.repeat(self.gamma / K, K))
+        for t in range(1, T):
+            for k in range(K):
+                weights[0, t, k] = rng.dirichlet(self.alpha * betas[0] + 4.0 * np.eye(K)[k])  # init_sampler default kappa=4.0 (hdp_lpcm.py:50)
+
+        if self.step_size_X == "auto":
+            self.step_size_X = 0.01 if self.is_directed else 0.1
+        self.case_control_sampler_ = None
+        if self.n_control is not None:
+            if not self.is_directed:
+                raise ValueError("The case-control likelihood currently only "
+                                 "supported for directed networks.")
+            self.case_control_sampler_ = DirectedCaseControlSampler(
+                n_control=self.n_control, n_resample=self.n_resample_control, random_state=rng)
+            self.case_control_sampler_.init(Y)
+        if isinstance(self.intercept_prior, str) and self.intercept_prior == "auto":
+            self.intercept_prior = ics[0]   # (sic) a view of the trace's first row, as in the reference
+
+        # ---- hyper-priors (hdp_lpcm.py:750-793) ----
+        if self.mean_variance_prior == "auto":
+            mvp = (2 * (1. / n) ** (2. / d)) if self.is_directed else ((n ** (2. / d)) / 50.)
+        else:
+            mvp = self.mean_variance_prior
+        a0 = b0 = c0 = d0 = None
+        if self.mean_variance_prior_std is not None:
+            a0 = (self.mean_variance_prior_std ** 2 + 2) * 2
+            b0 = (a0 - 2) * mvp * 2
+        b_ = (self.a + 2) * mvp if self.b == "auto" else self.b
+        if self.sigma_prior_std is not None:
+            d0 = (self.sigma_prior_std ** 2 / b_) * 2
+            c0 = b_ * d0
+        hp = HDPHyper(self.gamma, self.alpha_init, self.alpha, self.kappa, mvp, b_, self.a, a0, b0,
+                      c0, d0, self.lambda_prior, self.lambda_variance_prior, self.gamma_prior_shape,
+                      self.gamma_prior_rate, self.alpha_init_shape, self.alpha_init_rate,
+                      self.alpha_kappa_shape, self.alpha_kappa_rate,
+                      self.mean_variance_prior_std is not None, self.sigma_prior_std is not None)
+        self.hyper_ = hp
+
+        # ---- device state ----
+        drv = _Driver(Y, d, 1, self.is_directed, self.case_control_sampler_, K, self.tune,
+                      self.tune_interval, (100, 100),   # hdp_lpcm.py:735-742: default interval
+                      self.tune, self.device, replay, rng)   # hdp_lpcm.py:745-747: radii sampler tunes
+        e = drv.engine
+        self._engine = e
+        e.set(L.F_X, Xs[0][None])
+        ic = np.zeros((1, 2)); ic[0, :m] = ics[0]
+        e.set(L.F_INTERCEPT, ic)
+        if self.is_directed:
+            e.set(L.F_RADII, rads[0][None])
+        e.set_hyper(intercept_prior=np.array(self.intercept_prior, dtype=np.float64),
+                    intercept_variance_prior=self.intercept_variance_prior)
+        e.set_tuner(self.step_size_X, self.step_size_intercept, self.step_size_radii)
+
+        def push_mixture(it):
+            e.set(L.F_MU, mus[it][None]); e.set(L.F_SIGMA, sigmas[it][None])
+            e.set(L.F_LAMBDA, lambdas[it]); e.set(L.F_WEIGHTS, weights[it][None])
+            e.set(L.F_Z, zs[it][None])
+
+        def logp(it):
+            r = rads[it] if self.is_directed else None
+            lp = hdp_log_prior(hp, K, Xs[it], ics[it], self.intercept_prior,
+                               self.intercept_variance_prior, mus[it], sigmas[it], zs[it],
+                               weights[it], betas[it], lambdas[it], radii=r)
+            return float(np.ravel(e.loglik_full()[0] + lp)[0])
+
+        logps = np.zeros(S)
+        push_mixture(0)
+        logps[0] = logp(0)
+
+        for it in range(1, S):
+            if self.case_control_sampler_ is not None:
+                self.case_control_sampler_.resample()
+                if self.case_control_sampler_.resampled_:
+                    drv.push_controls()
+            drv.sweep_latent()
+            e.center()
+            drv.sample_intercepts()
+            if self.is_directed:
+                drv.sample_radii()
+            drv.sample_labels()
+            X = e.get(L.F_X)[0]
+            z = e.get(L.F_Z)[0].astype(np.int64)
+            cnt = e.get(L.F_NCOUNT)[0]
+            nk = e.get(L.F_NK)[0].astype(np.int64)
+            mu, sigma, w = mus[it - 1].copy(), sigmas[it - 1].copy(), weights[it - 1].copy()
+            beta, lmbda = conjugate_updates(rng, hp, X, z, cnt, nk, mu, sigma, lambdas[it - 1].copy(),
+                                            betas[it - 1].copy(), w)
+            Xs[it], zs[it], mus[it], sigmas[it] = X, z, mu, sigma
+            betas[it], weights[it], lambdas[it] = beta, w, lmbda
+            ics[it] = e.get(L.F_INTERCEPT)[0, :m]
+            if self.is_directed:
+                rads[it] = e.get(L.F_RADII)[0]
+            push_mixture(it)
+            logps[it] = logp(it)
+
+        # mirror the reference's mutable hyper-parameter attributes
+        self.gamma, self.alpha_init, self.alpha, self.kappa = hp.gamma, hp.alpha_init, hp.alpha, hp.kappa
+        self.mean_variance_prior_, self.b_ = hp.mean_variance_prior, hp.b
+
+        if self.thin is not None:
+            sl = slice(None, None, self.thin)
+            Xs, ics, mus, sigmas, zs = Xs[sl], ics[sl], mus[sl], sigmas[sl], zs[sl]
+            betas, weights, lambdas, logps = betas[sl], weights[sl], lambdas[sl], logps[sl]
+            if self.is_directed:
+                rads = rads[sl]
+        self.Xs_, self.intercepts_, self.mus_, self.sigmas_, self.zs_ = Xs, ics, mus, sigmas, zs
+        self.betas_, self.weights_, self.lambdas_, self.logps_ = betas, weights, lambdas, logps
+        self.radiis_ = rads
+        self._post_process()
+        self.sampler_counters_ = e.counters()
+        return self
+
+    # ---- point estimate, alignment, posterior summaries -------------------------------------
+    def _post_process(self):
+        nb = min(self.n_burn_, self.Xs_.shape[0] - 1)
+        T, n = self.Y_fit_.shape[:2]
+        K = self.n_components
+        best = nb + int(np.argmax(self.logps_[nb:]))
+        self.selected_id_ = best
+        self.logp_ = self.logps_[best]
+        self.X_ = self.Xs_[best].copy()
+        self.intercept_ = self.intercepts_[best]
+        self.lambda_ = self.lambdas_[best]
+        if self.is_directed:
+            self.radii_ = self.radiis_[best]
+        # relabel to the active components and renormalise their weights (label_utils.py:10-37)
+        active, z = np.unique(self.zs_[best].ravel(), return_inverse=True)
+        self.z_ = z.reshape(T, n)
+        self.beta_ = self.betas_[best, active] / self.betas_[best, active].sum()
+        w = self.weights_[best]
+        self.init_weights_ = w[0, 0, active] / w[0, 0, active].sum()
+        self.trans_weights_ = np.zeros((T, active.size, active.size))
+        for t in range(1, T):
+            sub = w[t, active][:, active]
+            self.trans_weights_[t] = sub / np.sum(sub, axis=1).reshape(-1, 1)
+        self.mu_, self.sigma_ = self.mus_[best, active], self.sigmas_[best, active]
+        # co-clustering probabilities over the post-burn-in draws (label_utils.py:40-62)
+        self.cooccurrence_probas_ = np.zeros((T, n, n))
+        eye = np.eye(K)
+        for t in range(T):
+            ind = eye[self.zs_[nb:, t]]                      # (S', n, K)
+            self.cooccurrence_probas_[t] = np.einsum("sik,sjk->ij", ind, ind) / ind.shape[0]
+        self.counts_ = np.array([np.unique(zz).size for zz in self.zs_[nb:]])
+        # rotate every stored sample onto the point estimate (hdp_lpcm.py:1141-1146)
+        for idx in range(self.Xs_.shape[0]):
+            self.Xs_[idx], R = longitudinal_procrustes_rotation(self.X_, self.Xs_[idx])
+            self.mus_[idx] = np.dot(self.mus_[idx], R)
+        self.X_mean_ = self.Xs_[nb:].mean(axis=0)
+        self.lambda_mean_ = self.lambdas_[nb:].mean(axis=0)
+        self.intercepts_mean_ = self.intercepts_[nb:].mean(axis=0)
+        if self.is_directed:
+            self.radii_mean_ = self.radiis_[nb:].mean(axis=0)
+        from .diagnostics import geweke_z
+        self.logp_geweke_ = geweke_z(self.logps_, nb)
+        self.lambda_geweke_ = geweke_z(self.lambdas_[:, 0], nb)
+        if self.is_directed:
+            self.intercept_in_geweke_ = geweke_z(self.intercepts_[:, 0], nb)
+            self.intercept_out_geweke_ = geweke_z(self.intercepts_[:, 1], nb)
+        else:
+            self.intercept_geweke_ = geweke_z(self.intercepts_[:, 0], nb)

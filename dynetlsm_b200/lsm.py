@@ -1,0 +1,324 @@
+"""``DynamicNetworkLSM`` -- the reference estimator's API (lsm.py:100-625) over the device sampler.
+
+Constructor keywords, ``fit(Y) -> self`` and the fitted attributes (``Xs_``, ``intercepts_``,
+``radiis_``, ``logps_``, ``X_``, ``intercept_``, ``radii_``, ``logp_``, ``Y_fit_``,
+``case_control_sampler_``, ``n_burn_``, ``distances_``, ``probas_``, ``auc_``) follow the
+reference.  Three extra keywords select how the chain is driven:
+
+    sampler='device'   device Philox streams, nothing but traces crosses PCIe (default)
+    sampler='replay'   every random draw comes from the numpy ``RandomState`` in the reference's
+                       order and is shipped to the device, which then reproduces the reference's
+                       chain (accept/reject decisions bit-for-bit)
+    n_chains=C         C independent chains on one GPU (``sampler='device'``); the drop-in
+                       attributes describe chain 0, ``chains_`` holds the per-chain traces
+    device=k           CUDA device ordinal
+
+The hot path (latent-position sweep, full-network likelihood MH steps) runs in libdlsm.so; the
+host keeps what the reference also does once per sweep in numpy: Procrustes, MAP bookkeeping,
+prior terms of ``logp``.  There is no CPU fallback.
+"""
+import numpy as np
+from scipy.special import expit
+from sklearn.utils import check_array, check_random_state
+
+from . import _lib as L
+from .case_control_likelihood import DirectedCaseControlSampler
+from .host_init import (calculate_distances, directed_intercept_mle, generalized_mds,
+                        initialize_radii, longitudinal_procrustes_rotation, scale_intercept_mle)
+
+__all__ = ["DynamicNetworkLSM"]
+
+
+def _philox_seed(rng):
+    return int(rng.randint(0, 2 ** 31 - 1)) | (int(rng.randint(0, 2 ** 31 - 1)) << 31)
+
+
+class _Driver(object):
+    """Shared device plumbing of the two estimators: one Engine, draws in either mode."""
+
+    def __init__(self, Y, n_features, n_chains, is_directed, case_control_sampler, mixture_K, tune,
+                 tune_interval, intercept_tune_interval, radii_tune, device, replay, rng):
+        T, n, _ = Y.shape
+        self.T, self.n, self.d, self.C = T, n, n_features, n_chains
+        self.replay, self.rng = replay, rng
+        self.is_directed, self.cc = is_directed, case_control_sampler
+        self.engine = L.Engine(T=T, n=n, d=n_features, n_chains=n_chains, K=mixture_K,
+                               is_directed=is_directed, case_control=self.cc is not None,
+                               mixture=mixture_K > 0, device=device, tune=tune,
+                               tune_interval=tune_interval,
+                               intercept_tune_interval=intercept_tune_interval,
+                               radii_tune=radii_tune, radii_tune_interval=100)
+        if self.cc is None:
+            self.engine.set_network(Y)
+        else:
+            self.engine.set_edge_lists(self.cc.degrees_, self.cc.in_edges_, self.cc.out_edges_)
+            self.push_controls()
+        if not replay:
+            self.engine.set_rng(_philox_seed(rng))
+
+    def push_controls(self):
+        self.engine.set_controls(self.cc.control_nodes_in_, self.cc.control_nodes_out_)
+
+    # one latent sweep for every chain -------------------------------------------------
+    def sweep_latent(self):
+        e = self.engine
+        if not self.replay:
+            return e.sweep_latent()
+        T, n, d, rng = self.T, self.n, self.d, self.rng
+        eps = np.empty((1, T, n, d))
+        u = np.empty((1, T, n))
+        for t in range(T):           # metropolis.py:44,49: randn(d) then rand(), node by node
+            for j in range(n):
+                eps[0, t, j] = rng.randn(d)
+                u[0, t, j] = rng.rand()
+        return e.sweep_latent(eps, np.log(u))
+
+    def sample_intercepts(self):
+        e = self.engine
+        if not self.replay:
+            return e.sample_intercepts()
+        m = e.m
+        # sample_coefficients.py:20-88: randn(1) when the proposal is made, rand() after both
+        # log-posterior evaluations; the second intercept's draws follow the first's
+        eps, u = np.empty((1, m)), np.empty((1, m))
+        for i in range(m):
+            eps[0, i] = self.rng.randn(1)[0]
+            u[0, i] = self.rng.rand()
+        return e.sample_intercepts(eps, np.log(u))
+
+    def sample_radii(self):
+        e = self.engine
+        if not self.replay:
+            return e.sample_radii()
+        radii = e.get(L.F_RADII)[0]
+        step = e.get(L.F_R_STEP)[0]
+        prop = self.rng.dirichlet(step * radii)      # metropolis.py:61-67
+        if np.any(prop == 0.):
+            prop += 1e-5
+            prop /= np.sum(prop)
+        u = self.rng.rand()
+        return e.sample_radii(prop[None], np.array([np.log(u)]))
+
+    def sample_labels(self):
+        e = self.engine
+        if not self.replay:
+            return e.sample_labels()
+        # sample_labels.py:16-19: one uniform per (node, time), node-major; uniform(0, c) = c * U
+        U = self.rng.random_sample((1, self.n, self.T))
+        return e.sample_labels(U)
+
+
+class DynamicNetworkLSM(object):
+    """Latent space model for dynamic networks (Sewell & Chen 2015), sampled on a B200.
+
+    Parameters follow the reference estimator (lsm.py:103-213); see the module docstring for the
+    extra keywords ``sampler``, ``n_chains`` and ``device``.
+    """
+
+    def __init__(self, n_features=2, is_directed=False, n_iter=5000, tune=2500, tune_interval=100,
+                 burn=2500, intercept_prior="auto", intercept_variance_prior=2.0, tau_sq=2.0,
+                 sigma_sq=0.1, step_size_X=0.1, step_size_intercept=0.1, step_size_radii=175000,
+                 n_control=None, n_resample_control=100, copy=True, random_state=None,
+                 sampler="device", n_chains=1, device=0):
+        self.n_iter = n_iter
+        self.is_directed = is_directed
+        self.n_features = n_features
+        self.tau_sq = tau_sq
+        self.sigma_sq = sigma_sq
+        self.step_size_X = step_size_X
+        self.intercept_prior = intercept_prior
+        self.intercept_variance_prior = intercept_variance_prior
+        self.step_size_intercept = step_size_intercept
+        self.step_size_radii = step_size_radii
+        self.tune = tune
+        self.tune_interval = tune_interval
+        self.burn = burn
+        self.n_control = n_control
+        self.n_resample_control = n_resample_control
+        self.copy = copy
+        self.random_state = random_state
+        self.sampler = sampler
+        self.n_chains = n_chains
+        self.device = device
+
+    # -- reference properties (lsm.py:270-317) -----------------------------------------------
+    @property
+    def n_burn_(self):
+        return (self.burn or 0) + (self.tune or 0)
+
+    @property
+    def distances_(self):
+        if not hasattr(self, "X_"):
+            raise ValueError("Model not fit.")
+        return calculate_distances(self.X_)
+
+    @property
+    def probas_(self):
+        if not hasattr(self, "X_"):
+            raise ValueError("Model not fit.")
+        dist = self.distances_
+        if self.is_directed:
+            r = self.radii_
+            eta = (self.intercept_[0] * (1 - dist / r[None, None, :]) +
+                   self.intercept_[1] * (1 - dist / r[None, :, None]))
+            probas = expit(eta)
+        else:
+            probas = expit(self.intercept_ - dist)
+        idx = np.arange(dist.shape[1])
+        probas[:, idx, idx] = 0.0
+        return probas
+
+    @property
+    def auc_(self):
+        from sklearn.metrics import roc_auc_score
+        if not hasattr(self, "X_"):
+            raise ValueError("Model not fit.")
+        n = self.Y_fit_.shape[1]
+        mask = ~np.eye(n, dtype=bool) if self.is_directed else np.triu(np.ones((n, n), bool), 1)
+        return roc_auc_score(self.Y_fit_[:, mask].ravel(), self.probas_[:, mask].ravel())
+
+    # -- joint log-posterior (lsm.py:576-625), network term from the device -------------------
+    def _log_prior(self, X, intercept):
+        lp = 0.0
+        for t in range(X.shape[0]):
+            if t == 0:
+                lp -= np.sum(0.5 * np.sum(X[t] * X[t], axis=1) / self.tau_sq)
+            else:
+                diff = X[t] - X[t - 1]
+                lp -= np.sum(0.5 * np.sum(diff * diff, axis=1) / self.sigma_sq)
+        if self.is_directed:
+            diff = intercept - self.intercept_prior
+            lp -= np.sum(0.5 * (diff * diff) / self.intercept_variance_prior)
+        else:
+            diff = intercept[0] - np.ravel(self.intercept_prior)[0]
+            lp -= 0.5 * (diff * diff) / self.intercept_variance_prior
+        return lp
+
+    def fit(self, Y):
+        """Sample from the posterior given the dynamic network ``Y`` (T, n, n), entries 0/1."""
+        if self.sampler not in ("device", "replay"):
+            raise ValueError("`sampler` must be 'device' or 'replay', got {}".format(self.sampler))
+        replay = self.sampler == "replay"
+        if replay and self.n_chains != 1:
+            raise ValueError("sampler='replay' reproduces one reference chain; use n_chains=1")
+        n_time_steps, n_nodes, _ = Y.shape
+        rng = check_random_state(self.random_state)
+        Y = check_array(Y, dtype=np.float64, ensure_all_finite="allow-nan", ensure_2d=False,
+                        allow_nd=True, copy=self.copy)
+        if np.any(Y == -1) or np.any(np.isnan(Y)):
+            raise NotImplementedError("missing dyads (-1 / NaN) are not supported by the device "
+                                      "sampler; impute them first (the reference's "
+                                      "SimpleNetworkImputer is outside the accelerated path)")
+        self.Y_fit_ = Y
+        n_iter_procrustes = 0
+        if self.tune is not None:
+            self.n_iter += self.tune
+            n_iter_procrustes += self.tune
+        if self.burn is not None:
+            self.n_iter += self.burn
+            n_iter_procrustes += self.burn
+        S, C, m = self.n_iter, self.n_chains, (2 if self.is_directed else 1)
+
+        # ---- initial values on the host (lsm.py:385-413) ----
+        X = generalized_mds(Y, n_features=self.n_features, is_directed=self.is_directed,
+                            random_state=rng)
+        radii = None
+        if self.is_directed:
+            radii = initialize_radii(Y)
+            intercept = np.array(directed_intercept_mle(Y, X, radii))
+        else:
+            scale, b = scale_intercept_mle(Y, X)
+            intercept = np.array([b])
+            X *= np.exp(scale)
+        X -= np.mean(X, axis=(0, 1))
+        if isinstance(self.tau_sq, str) and self.tau_sq == "auto":
+            self.tau_sq = np.mean(X[0] * X[0])
+        if isinstance(self.intercept_prior, str) and self.intercept_prior == "auto":
+            self.intercept_prior = intercept.copy()
+
+        self.case_control_sampler_ = None
+        if self.n_control is not None:
+            if not self.is_directed:
+                raise ValueError("The case-control likelihood currently only "
+                                 "supported for directed networks.")
+            self.case_control_sampler_ = DirectedCaseControlSampler(
+                n_control=self.n_control, n_resample=self.n_resample_control, random_state=rng)
+            self.case_control_sampler_.init(Y)
+
+        # ---- device state ----
+        drv = _Driver(Y, self.n_features, C, self.is_directed, self.case_control_sampler_, 0,
+                      self.tune, self.tune_interval,
+                      # lsm.py:459-467: only the directed intercept samplers get tune_interval
+                      (self.tune_interval,) * 2 if self.is_directed else (100, 100),
+                      None, self.device, replay, rng)   # lsm.py:470-472: radii sampler never tunes
+        e = drv.engine
+        self._engine = e
+        disp = np.zeros((C, 1, 1, 1))
+        Xc = np.tile(X[None], (C, 1, 1, 1))
+        if C > 1:  # dispersed starts for the extra chains
+            Xc[1:] += 0.1 * np.std(X) * rng.randn(C - 1, *X.shape)
+        e.set(L.F_X, Xc + disp)
+        ic = np.zeros((C, 2))
+        ic[:, :m] = intercept
+        e.set(L.F_INTERCEPT, ic)
+        if self.is_directed:
+            e.set(L.F_RADII, np.tile(radii[None], (C, 1)))
+        e.set_hyper(tau_sq=self.tau_sq, sigma_sq=self.sigma_sq, intercept_prior=self.intercept_prior,
+                    intercept_variance_prior=self.intercept_variance_prior)
+        e.set_tuner(self.step_size_X, self.step_size_intercept, self.step_size_radii)
+
+        # ---- traces ----
+        Xs = np.zeros((C, S, n_time_steps, n_nodes, self.n_features))
+        ics = np.zeros((C, S, m))
+        rads = np.zeros((C, S, n_nodes)) if self.is_directed else None
+        logps = np.zeros((C, S))
+        Xs[:, 0] = e.get(L.F_X)
+        ics[:, 0] = intercept
+        if self.is_directed:
+            rads[:, 0] = radii
+        ll = e.loglik_full()
+        for c in range(C):
+            logps[c, 0] = ll[c] + self._log_prior(Xs[c, 0], ics[c, 0])
+        best = [dict(logp=logps[c, 0], it=0) for c in range(C)]
+
+        for it in range(1, S):
+            if self.case_control_sampler_ is not None:
+                self.case_control_sampler_.resample()
+                if self.case_control_sampler_.resampled_:
+                    drv.push_controls()
+            drv.sweep_latent()
+            if it > n_iter_procrustes:   # lsm.py:495-498: align with the best pre-burn-in sample
+                Xh = e.get(L.F_X)
+                for c in range(C):
+                    ref = Xs[c, np.argmax(logps[c, :(n_iter_procrustes + 1)])]
+                    Xh[c], _ = longitudinal_procrustes_rotation(ref, Xh[c])
+                e.set(L.F_X, Xh)
+            e.center()
+            drv.sample_intercepts()
+            if self.is_directed:
+                drv.sample_radii()
+            Xs[:, it] = e.get(L.F_X)
+            ics[:, it] = e.get(L.F_INTERCEPT)[:, :m]
+            if self.is_directed:
+                rads[:, it] = e.get(L.F_RADII)
+            ll = e.loglik_full()
+            for c in range(C):
+                logps[c, it] = ll[c] + self._log_prior(Xs[c, it], ics[c, it])
+                # MAP bookkeeping (lsm.py:554-566): restart at the end of burn-in, then track the max
+                if (self.tune and it == (self.tune + self.burn)) or logps[c, it] > best[c]["logp"]:
+                    best[c] = dict(logp=logps[c, it], it=it)
+
+        # ---- drop-in attributes (chain 0) + per-chain traces ----
+        self.Xs_, self.intercepts_, self.logps_ = Xs[0], ics[0], logps[0]
+        if self.is_directed:
+            self.radiis_ = rads[0]
+        b0 = best[0]["it"]
+        self.logp_ = logps[0, b0]
+        self.X_ = Xs[0, b0]
+        self.intercept_ = ics[0, b0]
+        if self.is_directed:
+            self.radii_ = rads[0, b0]
+        self.chains_ = dict(Xs=Xs, intercepts=ics, logps=logps, radiis=rads,
+                            map_iteration=[b["it"] for b in best])
+        self.sampler_counters_ = e.counters()
+        return self

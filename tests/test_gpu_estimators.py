@@ -1,0 +1,135 @@
+"""The estimator shells (drop-in API of lsm.py / hdp_lpcm.py) on the GPU.
+
+``sampler='replay'`` must reproduce the reference's chains recorded in tests/golden (whole ``fit``,
+from the reference's own initialisation through every sweep); ``sampler='device'`` (Philox) must
+agree with it in distribution.  Also the reference's own smoke tests, restated
+(dynetlsm/tests/test_lsm.py:5-13, test_hdp_lcpm.py:5-15: fit and assert shapes).
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+
+
+def _splitting_network(n=50, T=2, seed=42):
+    """A small community-structured undirected network (stand-in for the reference generator)."""
+    rng = np.random.RandomState(seed)
+    z = rng.randint(0, 2, n)
+    centers = np.array([[-1.5, 0.0], [1.5, 0.0]])
+    Y = np.zeros((T, n, n))
+    for t in range(T):
+        X = centers[z] + 0.6 * rng.randn(n, 2)
+        dist = np.sqrt(((X[:, None] - X[None]) ** 2).sum(-1))
+        U = np.triu((rng.rand(n, n) < 1 / (1 + np.exp(-(1.0 - dist)))).astype(float), 1)
+        Y[t] = U + U.T
+    return Y
+
+
+def test_reference_smoke_test_lsm_shapes():
+    from dynetlsm_b200 import DynamicNetworkLSM
+    Y = _splitting_network()
+    lsm = DynamicNetworkLSM(n_iter=250, burn=250, tune=250, n_features=2, random_state=123).fit(Y)
+    assert lsm.X_.shape == (2, 50, 2)
+    assert lsm.Xs_.shape == (750, 2, 50, 2) and lsm.intercepts_.shape == (750, 1)
+    assert np.isfinite(lsm.logps_).all() and 0.5 < lsm.auc_ <= 1.0
+    assert lsm.probas_.shape == (2, 50, 50) and lsm.distances_.shape == (2, 50, 50)
+
+
+def test_reference_smoke_test_hdp_lpcm_shapes():
+    from dynetlsm_b200 import DynamicNetworkHDPLPCM
+    Y = _splitting_network()
+    m = DynamicNetworkHDPLPCM(n_iter=100, burn=100, tune=100, n_features=2, n_components=10,
+                              random_state=123).fit(Y)
+    assert m.X_.shape == (2, 50, 2)
+    assert m.z_.shape == (2, 50)
+    assert m.zs_.shape == (300, 2, 50) and m.weights_.shape == (300, 2, 10, 10)
+    assert m.cooccurrence_probas_.shape == (2, 50, 50)
+    assert np.allclose(np.diagonal(m.cooccurrence_probas_, axis1=1, axis2=2), 1.0)
+    assert np.isfinite(m.logps_).all()
+
+
+def test_lsm_replay_reproduces_the_reference_fit_undirected():
+    """Whole fit(), reference initialisation included: same chain as the reference, draw for draw."""
+    from dynetlsm_b200 import DynamicNetworkLSM
+    g = load_golden("lsm_undirected_monks.npz")
+    Y = g["Y"].astype(np.float64)
+    m = DynamicNetworkLSM(n_iter=40, tune=30, burn=20, tune_interval=7, random_state=42,
+                          sampler="replay").fit(Y)
+    S = g["Xs"].shape[0]
+    assert np.array_equal(m.Xs_[0], g["Xs"][0])                 # initial state
+    assert np.array_equal(m.intercepts_[:S], g["intercepts"])   # every intercept draw
+    assert np.array_equal(m.Xs_[:S], g["Xs"])                   # every position, bit for bit
+    assert np.allclose(m.logps_[:S], g["logps"], rtol=1e-9, atol=0)
+
+
+def test_lsm_replay_case_control_runs_and_matches_reference_control_sets():
+    """Directed + case-control: initial values are not comparable (reference UB, K10), but the
+    control-set resampling schedule and RNG consumption are: check the chain is self-consistent."""
+    from dynetlsm_b200 import DynamicNetworkLSM
+    g = load_golden("lsm_casecontrol_monks.npz")
+    Y = g["Y"].astype(np.float64)
+    m = DynamicNetworkLSM(n_iter=20, tune=20, burn=10, tune_interval=6, is_directed=True,
+                          sigma_sq=0.001, tau_sq="auto", step_size_X=0.0075, n_control=5,
+                          n_resample_control=8, random_state=11, sampler="replay").fit(Y)
+    assert m.Xs_.shape == (50, 3, 18, 2) and m.radiis_.shape == (50, 18)
+    assert np.allclose(m.radiis_.sum(axis=1), 1.0)
+    assert np.isfinite(m.logps_).all()
+    assert np.array_equal(m.case_control_sampler_.in_edges_, g["cc_in_edges"])
+    assert m.sampler_counters_["ub_flags"] == 0
+
+
+def test_hdp_replay_reproduces_the_reference_fit():
+    """HDP-LPCM end to end in replay mode: the 999-sweep LSM initialisation, k-means, and the main
+    loop (device sweeps + label FFBS, host conjugate updates) follow the reference chain."""
+    from dynetlsm_b200 import DynamicNetworkHDPLPCM
+    g = load_golden("hdp_undirected_split.npz")
+    Y = g["Y"].astype(np.float64)
+    m = DynamicNetworkHDPLPCM(n_iter=25, tune=25, burn=10, tune_interval=8, n_components=6,
+                              random_state=3, sampler="replay").fit(Y)
+    S = g["z_out"].shape[0]
+    assert np.array_equal(m.zs_[1:S + 1], g["z_out"])                       # every label draw
+    assert np.array_equal(m.intercepts_[1:S + 1], g["intercept_out"])       # every intercept draw
+    assert np.array_equal(m.lambdas_[1:S + 1], g["lmbda_next"])             # host conjugate block
+    assert np.array_equal(m.sigmas_[1:S + 1], g["sigma_next"])
+    assert np.allclose(m.logps_[:S + 1], g["logps"], rtol=1e-9, atol=0)
+    # positions are rotated post hoc (hdp_lpcm.py:1141-1146): compare a rotation invariant
+    d_ref = np.linalg.norm(g["X_centered"][-1][0][:, None] - g["X_centered"][-1][0][None], axis=-1)
+    d_got = np.linalg.norm(m.Xs_[S][0][:, None] - m.Xs_[S][0][None], axis=-1)
+    assert np.allclose(d_ref, d_got, rtol=0, atol=1e-10)
+
+
+def test_device_rng_matches_replay_in_distribution():
+    """Native Philox chains vs reference-equivalent replay chains on the monks network: posterior
+    means of the intercept and of the pairwise distances agree within Monte-Carlo error."""
+    from dynetlsm_b200 import DynamicNetworkLSM
+    from dynetlsm_b200.diagnostics import ess, split_rhat
+    g = load_golden("lsm_undirected_monks.npz")
+    Y = g["Y"].astype(np.float64)
+    kw = dict(n_iter=3000, tune=500, burn=500)
+    dev = DynamicNetworkLSM(random_state=1, sampler="device", n_chains=4, **kw).fit(Y)
+    rep = DynamicNetworkLSM(random_state=2, sampler="replay", **kw).fit(Y)
+    nb = 1000
+    a = dev.chains_["intercepts"][:, nb:, 0]      # (4, 3000)
+    b = rep.intercepts_[nb:, 0]
+    se = np.sqrt(a.var() / max(ess(a), 10) + b.var() / max(ess(b[None]), 10))
+    assert abs(a.mean() - b.mean()) < 5 * se + 0.02
+    assert split_rhat(a) < 1.2
+    # distances are invariant to the rotation/translation non-identifiability
+    def mean_dist(Xs):
+        return np.linalg.norm(Xs[:, :, :, None] - Xs[:, :, None], axis=-1).mean(axis=0)
+    da = mean_dist(dev.chains_["Xs"][0, nb:])
+    db = mean_dist(rep.Xs_[nb:])
+    assert np.abs(da - db).mean() < 0.15 * db.mean()
+
+
+def test_missing_dyads_are_refused():
+    from dynetlsm_b200 import DynamicNetworkLSM
+    Y = _splitting_network(n=12)
+    Y[0, 1, 2] = Y[0, 2, 1] = -1
+    with pytest.raises(NotImplementedError):
+        DynamicNetworkLSM(n_iter=5, tune=5, burn=5).fit(Y)
