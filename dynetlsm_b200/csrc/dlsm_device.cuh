@@ -217,19 +217,17 @@ __host__ __device__ __forceinline__ double fast_exp(double x)
     return (x != x) ? x : v;
 }
 
-// Branch-free fp64 sqrt: MUFU.RSQ64H seed (~22 bits) + two Goldschmidt steps + one correction;
-// within 1 ulp of IEEE sqrt.  1e-300 is added so that coincident points (s == 0) give 1e-150
-// instead of 0 * inf; it is absorbed exactly for every s > 1e-284.  NaN propagates.
+// Branch-free fp64 sqrt: MUFU.RSQ64H seed (~22 bits), one Goldschmidt step (~44 bits) and a final
+// fused correction g += (s - g*g) * h, which squares the error again: within 1 ulp of IEEE sqrt.
+// 1e-300 is added so that coincident points (s == 0) give 1e-150 instead of 0 * inf; it is
+// absorbed exactly for every s > 1e-284.  NaN propagates.
 __device__ __forceinline__ double fast_sqrt(double s)
 {
     s += 1e-300;
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
     double g = s * y, h = 0.5 * y;
-    double r = fma(-h, g, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-h, g, 0.5);
+    const double r = fma(-h, g, 0.5);
     g = fma(g, r, g);
     h = fma(h, r, h);
     return fma(fma(-g, g, s), h, g);

@@ -53,6 +53,10 @@ struct SweepParams {
     unsigned int *flags;       // bit0 non-finite ratio, bit1 case-control out-of-bounds quirk
 };
 
+// latent dimension: a compile-time constant in the specialised (D == 2) instantiations
+template <int DM>
+__device__ __forceinline__ int latent_dim(const NetView &net) { return DM == kMaxD ? net.d : DM; }
+
 // eta of a directed dyad given dist and the two reciprocal radii
 //   sender s -> receiver r :  b_in * (1 - dist / r_r) + b_out * (1 - dist / r_s)
 __device__ __forceinline__ double eta_directed(double b_in, double b_out, double dist,
@@ -81,7 +85,7 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
                                              double b0, double b1, int lane, double &ll_new,
                                              double &ll_old, unsigned int *flags)
 {
-    const int n = net.n, d = net.d;
+    const int n = net.n, d = latent_dim<DM>(net);
     if (LK == kUndirected) {
         // K1 static_network_fast.pyx:17-44.  Two 32-node chunks per trip, branch- and select-free
         // (out-of-range lanes and the self pair are evaluated on a clamped index and multiplied
@@ -225,7 +229,7 @@ template <int DM>
 __device__ __forceinline__ double prior_next(const SweepParams &p, int c, int t, int j,
                                              const double (&x)[DM], const double (&xnext)[DM])
 {
-    const int d = p.net.d, T = p.net.T, n = p.net.n;
+    const int d = latent_dim<DM>(p.net), T = p.net.T, n = p.net.n;
     double diff[DM];
     if (p.prior == 0) {
 #pragma unroll
@@ -257,7 +261,7 @@ template <int DM>
 __device__ __forceinline__ double prior_prev(const SweepParams &p, int c, int t, int zc, double inv,
                                              const double (&x)[DM], const double (&xprev)[DM])
 {
-    const int d = p.net.d;
+    const int d = latent_dim<DM>(p.net);
     double diff[DM];
     if (p.prior == 0) {
         if (t == 0) return half_sumsq_times<DM>(x, d, inv);
