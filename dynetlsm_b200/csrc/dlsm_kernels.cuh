@@ -498,8 +498,17 @@ __global__ void k_center(double *X, int T, int n, int d)
     double *Xc = X + (size_t)blockIdx.x * T * n * d;
     const size_t rows = (size_t)T * n;
     if ((int)threadIdx.x < d) {
+        // eight loads in flight per step keep the serial DADD chain (8 cycles each) fed
         double s = 0.0;
-        for (size_t r = 0; r < rows; r++) s = __dadd_rn(s, Xc[r * d + threadIdx.x]);
+        size_t r = 0;
+        for (; r + 8 <= rows; r += 8) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = Xc[(r + q) * d + threadIdx.x];
+#pragma unroll
+            for (int q = 0; q < 8; q++) s = __dadd_rn(s, v[q]);
+        }
+        for (; r < rows; r++) s = __dadd_rn(s, Xc[r * d + threadIdx.x]);
         mean[threadIdx.x] = __ddiv_rn(s, (double)rows);
     }
     __syncthreads();
@@ -589,49 +598,58 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
     const double *r1 = p.rinv1 ? p.rinv1 + (size_t)c * n : nullptr;
     double a0 = 0.0, a1 = 0.0;
 
-    for (int i = tile + warp * p.tiles; i < n; i += nwarps * p.tiles) {
-        double xi[DM];
-        load_pos<DM>(Xt + (size_t)i * d, d, xi);
-        if (LK == kUndirected) {
-            // K5 network_likelihoods.py:26-33: pairs j > i, eta = beta - dist
-            const uint32_t *row = p.net.rowbits + ((size_t)t * n + i) * W;
-            for (int base = ((i + 1) >> 5) << 5; base < n; base += 32) {
-                const int j = base + lane;
-                const uint32_t w = __ldg(row + (base >> 5));
-                {
-                    const double v = vmask(j < n && j > i), y = ymask(w, lane);
-                    double xj[DM];
-                    load_pos<DM>(Xt + (size_t)(j < n ? j : n - 1) * d, d, xj);
-                    const double dist = fast_sqrt(sqdist<DM>(xj, xi, d));
-                    a0 = fma(v, logit_term(y, b00 - dist), a0);
-                    a1 = fma(v, logit_term(y, b10 - dist), a1);
+    if (LK != kCaseControl) {
+        // K5 network_likelihoods.py:26-33 / K4 directed_likelihoods_fast.pyx:185-205.
+        // Unordered pairs a < b of one slice, visited as FOLDED rows: row i (n-1-i pairs) is glued
+        // to row n-1-i (i pairs), so every folded row has n-1 pair slots and the lanes stay full
+        // (a plain triangular sweep leaves ~30 % of the lane slots empty).  Two 32-slot chunks
+        // per trip and two parameter variants per pair = four independent softplus chains.
+        const int half = (n + 1) >> 1;
+        for (int i = tile + warp * p.tiles; i < half; i += nwarps * p.tiles) {
+            const int i2 = n - 1 - i;
+            const int len1 = n - 1 - i;                       // pairs (i, i+1+m)
+            const int slots = (i2 == i) ? len1 : n - 1;       // + pairs (i2, i2+1+k), k < i
+            double xi[DM], xi2[DM];
+            load_pos<DM>(Xt + (size_t)i * d, d, xi);
+            load_pos<DM>(Xt + (size_t)i2 * d, d, xi2);
+            double ra0 = 0, ra1 = 0, rb0 = 0, rb1 = 0;
+            if (LK == kDirected) { ra0 = r0[i]; ra1 = r1[i]; rb0 = r0[i2]; rb1 = r1[i2]; }
+            for (int base = 0; base < slots; base += 64) {
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int m = base + u * 32 + lane;
+                    const bool first = m < len1;
+                    const int arow = first ? i : i2;
+                    int bcol = first ? (i + 1 + m) : (i2 + 1 + (m - len1));
+                    const double v = vmask(m < slots);
+                    bcol = bcol < n ? bcol : n - 1;
+                    double xb[DM], xa[DM];
+                    load_pos<DM>(Xt + (size_t)bcol * d, d, xb);
+#pragma unroll
+                    for (int k = 0; k < DM; k++) xa[k] = first ? xi[k] : xi2[k];
+                    const double dist = fast_sqrt(sqdist<DM>(xb, xa, d));
+                    const size_t wo = ((size_t)t * n + arow) * W + (bcol >> 5);
+                    if (LK == kUndirected) {
+                        const double y = ymask(__ldg(p.net.rowbits + wo), bcol & 31);
+                        a0 = fma(v, logit_term(y, b00 - dist), a0);
+                        a1 = fma(v, logit_term(y, b10 - dist), a1);
+                    } else {
+                        const double y_ab = ymask(__ldg(p.net.rowbits + wo), bcol & 31);
+                        const double y_ba = ymask(__ldg(p.net.colbits + wo), bcol & 31);
+                        const double q0 = first ? ra0 : rb0, q1 = first ? ra1 : rb1;
+                        const double s0 = r0[bcol], s1 = r1[bcol];
+                        a0 = fma(v, logit_term(y_ab, eta_directed(b00, b01, dist, s0, q0)) +
+                                        logit_term(y_ba, eta_directed(b00, b01, dist, q0, s0)), a0);
+                        a1 = fma(v, logit_term(y_ab, eta_directed(b10, b11, dist, s1, q1)) +
+                                        logit_term(y_ba, eta_directed(b10, b11, dist, q1, s1)), a1);
+                    }
                 }
             }
-        } else if (LK == kDirected) {
-            // K4 directed_likelihoods_fast.pyx:185-205: ordered pairs, visited as unordered pairs
-            // j > i with both directions sharing one distance
-            const uint32_t *row = p.net.rowbits + ((size_t)t * n + i) * W;
-            const uint32_t *col = p.net.colbits + ((size_t)t * n + i) * W;
-            const double ri0 = r0[i], ri1 = r1[i];
-            for (int base = ((i + 1) >> 5) << 5; base < n; base += 32) {
-                const int j = base + lane;
-                const uint32_t wr = __ldg(row + (base >> 5));
-                const uint32_t wc = __ldg(col + (base >> 5));
-                {
-                    const double v = vmask(j < n && j > i);
-                    const double y_ij = ymask(wr, lane), y_ji = ymask(wc, lane);
-                    const int jc = j < n ? j : n - 1;
-                    double xj[DM];
-                    load_pos<DM>(Xt + (size_t)jc * d, d, xj);
-                    const double dist = fast_sqrt(sqdist<DM>(xj, xi, d));
-                    const double rj0 = r0[jc], rj1 = r1[jc];
-                    a0 = fma(v, logit_term(y_ij, eta_directed(b00, b01, dist, rj0, ri0)) +
-                                    logit_term(y_ji, eta_directed(b00, b01, dist, ri0, rj0)), a0);
-                    a1 = fma(v, logit_term(y_ij, eta_directed(b10, b11, dist, rj1, ri1)) +
-                                    logit_term(y_ji, eta_directed(b10, b11, dist, ri1, rj1)), a1);
-                }
-            }
-        } else {
+        }
+    } else {
+        for (int i = tile + warp * p.tiles; i < n; i += nwarps * p.tiles) {
+            double xi[DM];
+            load_pos<DM>(Xt + (size_t)i * d, d, xi);
             // K6 directed_likelihoods_fast.pyx:208-270: out-edges and out-controls only
             const size_t r = (size_t)t * n + i;
             const int outdeg = p.net.deg[r * 2 + 1];
@@ -1142,7 +1160,8 @@ __global__ void __launch_bounds__(TPB) k_ffbs_t(const LabelParams p)
                             __dadd_rn(__dadd_rn(r8[4], r8[5]), __dadd_rn(r8[6], r8[7])));
             for (; k < K; k++) tot = __dadd_rn(tot, bprev[k * TPB + tid]);
         }
-        for (int j = 0; j < K; j++) bprev[j * TPB + tid] = __ddiv_rn(bprev[j * TPB + tid], tot);
+        const double itot = __ddiv_rn(1.0, tot); // one division per step (1 ulp from x / tot)
+        for (int j = 0; j < K; j++) bprev[j * TPB + tid] = __dmul_rn(bprev[j * TPB + tid], itot);
         double *tmp = bcur; bcur = bprev; bprev = tmp;
     }
     for (int k = 0; k < K; k++) pm[(size_t)k * TPB + tid] = __dmul_rn(pm[(size_t)k * TPB + tid], bcur[k * TPB + tid]);
