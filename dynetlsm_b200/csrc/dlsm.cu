@@ -4,6 +4,7 @@
 #include "dlsm_kernels.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -45,6 +46,9 @@ struct dlsm_handle {
     unsigned int *d_flags = nullptr;
     int *d_bad = nullptr;
     int full_tiles = 1, full_nblk = 1;
+    int *d_progress = nullptr;      // [C][T] wavefront flags of the CTA-per-slice sweep
+    unsigned int *d_ticket = nullptr;
+    int sweep_mode = 0;             // 0 auto, 1 CTA per chain, 2 CTA per (chain, slice)
     // rng
     uint64_t seed = 0, chain_offset = 0;
     uint32_t sweep_idx[4] = {0, 0, 0, 0};
@@ -232,13 +236,67 @@ int launch_sweep_lk(dlsm_handle *h, const SweepParams &p)
     return xs ? launch_sweep_x<LK, 0, true>(h, p) : launch_sweep_x<LK, 0, false>(h, p);
 }
 
+// ---- CTA-per-(chain, slice) variant ---------------------------------------------------------
+int slice_warps(const dlsm_handle *h)
+{
+    int work = h->cfg.n;
+    if (h->lk == kCaseControl) work = h->max_in + h->max_out + 2 * h->n_control;
+    int nw = (work + 63) / 64;
+    return nw < 1 ? 1 : (nw > 16 ? 16 : nw);
+}
+
+size_t slice_smem(const dlsm_handle *h, bool xs, int nw)
+{
+    const size_t x = (size_t)h->cfg.n * h->cfg.d * sizeof(double);
+    return (xs ? x : 0) + (sweep_stage_doubles(h->cfg.d) + 2 * (size_t)nw) * sizeof(double) + 16;
+}
+
+template <int LK, int D, bool XS>
+int launch_slice_t(dlsm_handle *h, const SweepParams &p, int nw)
+{
+    const size_t smem = slice_smem(h, XS, nw);
+    auto kern = k_sweep_slice<LK, D, XS>;
+    CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t CT = (size_t)h->cfg.n_chains * h->cfg.T;
+    CU(h, cudaMemsetAsync(h->d_progress, 0, CT * sizeof(int), h->stream));
+    CU(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
+    kern<<<(unsigned)CT, nw * 32, smem, h->stream>>>(p, h->d_progress, h->d_ticket);
+    CHECK_LAUNCH(h);
+    return DLSM_OK;
+}
+
+template <int LK>
+int launch_slice_lk(dlsm_handle *h, const SweepParams &p)
+{
+    const int nw = slice_warps(h);
+    const bool xs = slice_smem(h, true, nw) <= kMaxSmem / 2;
+    if (h->cfg.d == 2) return xs ? launch_slice_t<LK, 2, true>(h, p, nw) : launch_slice_t<LK, 2, false>(h, p, nw);
+    return xs ? launch_slice_t<LK, 0, true>(h, p, nw) : launch_slice_t<LK, 0, false>(h, p, nw);
+}
+
+// A warp per slice fills the GPU once there are a few chains per SM; below that (or when rows are
+// long) the CTA-per-slice kernel spreads one chain over T SMs and a row over up to 16 warps.
+bool use_slice_kernel(const dlsm_handle *h)
+{
+    if (h->sweep_mode == 1) return false;
+    if (h->sweep_mode == 2) return true;
+    const size_t warps_chain_mode = (size_t)h->cfg.n_chains * (h->cfg.T < 16 ? h->cfg.T : 16);
+    return h->cfg.n >= 256 && warps_chain_mode < 148 * 16;
+}
+
 int launch_sweep(dlsm_handle *h, const SweepParams &p)
 {
     begin_phase(h, 0);
     int rc;
-    if (h->lk == kUndirected) rc = launch_sweep_lk<kUndirected>(h, p);
-    else if (h->lk == kDirected) rc = launch_sweep_lk<kDirected>(h, p);
-    else rc = launch_sweep_lk<kCaseControl>(h, p);
+    if (use_slice_kernel(h)) {
+        if (h->lk == kUndirected) rc = launch_slice_lk<kUndirected>(h, p);
+        else if (h->lk == kDirected) rc = launch_slice_lk<kDirected>(h, p);
+        else rc = launch_slice_lk<kCaseControl>(h, p);
+    } else {
+        if (h->lk == kUndirected) rc = launch_sweep_lk<kUndirected>(h, p);
+        else if (h->lk == kDirected) rc = launch_sweep_lk<kDirected>(h, p);
+        else rc = launch_sweep_lk<kCaseControl>(h, p);
+    }
     end_phase(h);
     if (rc == DLSM_OK) {
         h->ctr.kernel_launches += 1;
@@ -368,6 +426,8 @@ int dlsm_create(const dlsm_config *cfg, dlsm_handle **out)
     h->lk = cfg->likelihood == DLSM_LIK_CASE_CONTROL ? kCaseControl
                                                       : (cfg->is_directed ? kDirected : kUndirected);
     h->W = ((cfg->n + 31) / 32 + 3) / 4 * 4;
+    if (const char *m = getenv("DLSM_SWEEP_MODE")) // chain | slice: override the heuristic (tests, tuning)
+        h->sweep_mode = !strcmp(m, "chain") ? 1 : (!strcmp(m, "slice") ? 2 : 0);
     auto fail = [&](const char *what, cudaError_t e) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
         dlsm_destroy(h);
@@ -398,6 +458,8 @@ int dlsm_create(const dlsm_config *cfg, dlsm_handle **out)
     ALLOC(h->d_small, C * 4 * 8);
     ALLOC(h->d_small_i, C * 4 * 4);
     ALLOC(h->d_flags, 4);
+    ALLOC(h->d_progress, C * T * sizeof(int));
+    ALLOC(h->d_ticket, 4);
     ALLOC(h->d_bad, 4);
     if (cfg->is_directed) {
         ALLOC(h->d_rprop, C * n * 8);
@@ -406,7 +468,6 @@ int dlsm_create(const dlsm_config *cfg, dlsm_handle **out)
 #undef ALLOC
     cudaMemsetAsync(h->d_flags, 0, 4, h->stream);
     cudaMemsetAsync(h->rinv, 0, C * n * 8, h->stream);
-    (void)T;
     if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return fail("init", e);
     *out = h;
     return DLSM_OK;
@@ -422,7 +483,7 @@ void dlsm_destroy(dlsm_handle *h)
     void *ptrs[] = {h->rowbits, h->colbits, h->deg, h->in_edges, h->out_edges, h->ctrl_in,
                     h->ctrl_out, h->rinv, h->d_eps, h->d_logu, h->d_ratio, h->d_out, h->d_acc,
                     h->d_partial, h->d_bvar, h->d_prop, h->d_ll2, h->d_rprop, h->d_rprop_inv,
-                    h->d_small, h->d_small_i, h->d_flags, h->d_bad};
+                    h->d_small, h->d_small_i, h->d_flags, h->d_bad, h->d_progress, h->d_ticket};
     for (void *p : ptrs) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;

@@ -83,8 +83,12 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
                                              const double *rinv /* [n] */, int chain, int t, int j,
                                              const double (&xn)[DM], const double (&xo)[DM],
                                              double b0, double b1, int lane, double &ll_new,
-                                             double &ll_old, unsigned int *flags)
+                                             double &ll_old, unsigned int *flags, int wteam = 0,
+                                             int nteam = 1)
 {
+    // wteam / nteam: this warp's rank in, and the size of, the team of warps that shares the row.
+    // The outputs are this warp's PARTIAL sums (the whole sums when nteam == 1); they are linear in
+    // the per-pair terms, so the caller adds the partials of the team in a fixed order.
     const int n = net.n, d = latent_dim<DM>(net);
     if (LK == kUndirected) {
         // K1 static_network_fast.pyx:17-44.  Two 32-node chunks per trip, branch- and select-free
@@ -92,7 +96,7 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
         // by a 0/1 mask): four independent sqrt/softplus chains per lane keep the fp64 pipe busy.
         const uint32_t *row = net.rowbits + ((size_t)t * n + j) * net.W;
         double an = 0.0, ao = 0.0, an2 = 0.0, ao2 = 0.0;
-        for (int base = 0; base < n; base += 64) {
+        for (int base = wteam * 64; base < n; base += 64 * nteam) {
             const int i0 = base + lane, i1 = i0 + 32;
             const uint2 w = __ldg(reinterpret_cast<const uint2 *>(row + (base >> 5)));
             const double v0 = vmask((i0 < n) && (i0 != j)), v1 = vmask((i1 < n) && (i1 != j));
@@ -118,7 +122,7 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
         const uint32_t *col = net.colbits + ((size_t)t * n + j) * net.W;
         const double rj = rinv[j];
         double an = 0.0, ao = 0.0;
-        for (int base = 0; base < n; base += 32) {
+        for (int base = wteam * 32; base < n; base += 32 * nteam) {
             const int i = base + lane;
             const double y_ji = ymask(__ldg(row + (base >> 5)), lane); // Y[node, i]: node sends
             const double y_ij = ymask(__ldg(col + (base >> 5)), lane); // Y[i, node]: i sends
@@ -163,13 +167,14 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
             vn = eta_directed(b0, b1, dn, r_recv, r_send);
             vo = eta_directed(b0, b1, dd, r_recv, r_send);
         };
-        for (int q = lane; q < indeg; q += 32) { // :108-119
+        const int q0 = wteam * 32 + lane, qs = 32 * nteam;
+        for (int q = q0; q < indeg; q += qs) { // :108-119
             double vn, vo;
             eta_pair(ie[q], true, vn, vo);
             e_n += logit_term(0.5, vn);
             e_o += logit_term(0.5, vo);
         }
-        for (int q = lane; q < outdeg; q += 32) { // :122-133
+        for (int q = q0; q < outdeg; q += qs) { // :122-133
             double vn, vo;
             eta_pair(oe[q], false, vn, vo);
             e_n += logit_term(0.5, vn);
@@ -191,17 +196,17 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
             const unsigned bal = __ballot_sync(kFull, bad);
             if (bal) {
                 m_out = base + __ffs(bal) - 1;
-                if (lane == 0) atomicOr(flags, 2u);
+                if (lane == 0 && wteam == 0) atomicOr(flags, 2u);
                 break;
             }
         }
-        for (int q = lane; q < m; q += 32) { // :136-152
+        for (int q = q0; q < m; q += qs) { // :136-152
             double vn, vo;
             eta_pair(ci[q], true, vn, vo);
             ci_n += log1pexp(vn);
             ci_o += log1pexp(vo);
         }
-        for (int q = lane; q < m_out; q += 32) { // :160-176
+        for (int q = q0; q < m_out; q += qs) { // :160-176
             double vn, vo;
             eta_pair(co[q], false, vn, vo);
             co_n += log1pexp(vn);
@@ -448,6 +453,161 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
         __syncthreads();
         for (size_t e = threadIdx.x; e < chain_elems; e += blockDim.x) Xg[e] = Xc[e];
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_sweep_slice: the same sweep with one CTA per (chain, time slice) -- for long rows and few
+// chains (cfg 3: one chain, n = 2000, T = 20), where a warp per slice would leave the GPU idle.
+// The team that shares a node's row is the whole CTA (NW warps): each warp reduces its chunks of
+// the row, warp 0 adds the NW partials in a fixed order and finishes the node.  The wavefront
+// crosses CTAs: progress flags and the neighbouring slices' positions travel through global
+// memory (st + __threadfence + flag; volatile loads on the other side).  CTAs take their (chain,
+// slice) from an atomic ticket, so a CTA only ever waits on a CTA that has already started:
+// no co-residency assumption, no deadlock.
+// grid = C*T, block = 32*NW, dynamic smem = [n*d doubles if XS] + 32*(d+5) doubles + 2*NW doubles
+// ---------------------------------------------------------------------------------------------
+template <int LK, int D, bool XS>
+__global__ void __launch_bounds__(512) k_sweep_slice(const SweepParams p, int *progress_g,
+                                                     unsigned int *ticket)
+{
+    constexpr int DM = (D == 0) ? kMaxD : D;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_ticket;
+    const int T = p.net.T, n = p.net.n, d = (D == 0) ? p.net.d : D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (threadIdx.x == 0) s_ticket = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int c = s_ticket / T, t = s_ticket % T;
+    double *Xchain = p.X + (size_t)c * T * n * d;
+    double *Xg = Xchain + (size_t)t * n * d;   // this slice in global memory
+    double *Xt, *stage_base;
+    if (XS) {
+        Xt = reinterpret_cast<double *>(smem_raw);
+        stage_base = Xt + (size_t)n * d;
+        for (int e = threadIdx.x; e < n * d; e += blockDim.x) Xt[e] = Xg[e];
+    } else {
+        Xt = Xg;
+        stage_base = reinterpret_cast<double *>(smem_raw);
+    }
+    double *st_prop = stage_base;
+    double *st_logu = st_prop + 32 * d, *st_nn = st_logu + 32, *st_no = st_nn + 32, *st_inv = st_no + 32;
+    int *st_zc = reinterpret_cast<int *>(st_inv + 32);
+    double *part = stage_base + sweep_stage_doubles(d);     // [nwarps][2]
+    volatile int *prog = progress_g + (size_t)c * T;
+    __syncthreads();
+
+    const double b0 = p.intercept[c * 2 + 0], b1 = p.intercept[c * 2 + 1];
+    const double *rinv = (LK == kUndirected) ? nullptr : p.rinv + (size_t)c * n;
+    const uint32_t chain_id = (uint32_t)c + p.chain_offset;
+    bool nonfinite = false;
+
+    for (int jb = 0; jb < n; jb += 32) {
+        // ---- lane-parallel preparation (warp 0) ----
+        const int jl = jb + lane;
+        const bool mine = (warp == 0) && (jl < n);
+        const size_t gs = ((size_t)c * T + t) * n + (jl < n ? jl : 0);
+        double my_step = 0.0;
+        int my_nacc = 0, my_nsteps = 0, my_until = 0, my_acc = 0;
+        if (mine) {
+            double eps[DM], x0[DM], x[DM], logu;
+            load_pos<DM>(Xt + (size_t)jl * d, d, x0);
+            my_step = p.step[gs]; my_nacc = p.nacc[gs]; my_nsteps = p.nsteps[gs]; my_until = p.until[gs];
+            if (p.eps) {
+#pragma unroll
+                for (int k = 0; k < DM; k++) eps[k] = (k < d) ? p.eps[gs * d + k] : 0.0;
+                logu = p.logu[gs];
+            } else {
+                latent_draws<DM>(p.seed, (uint32_t)(t * n + jl), p.sweep, chain_id, d, eps, logu);
+            }
+#pragma unroll
+            for (int k = 0; k < DM; k++) {
+                x[k] = (k < d) ? __dadd_rn(x0[k], __dmul_rn(my_step, eps[k])) : 0.0;
+                if (k < d) st_prop[lane * d + k] = x[k];
+            }
+            st_logu[lane] = logu;
+            double inv = (t == 0) ? 1.0 / p.tau_sq : 1.0 / p.sigma_sq;
+            int zc = 0;
+            if (p.prior != 0) {
+                zc = p.z[((size_t)c * T + t) * n + jl];
+                inv = 1.0 / p.sigma[(size_t)c * p.K + zc];
+            }
+            st_inv[lane] = inv;
+            st_zc[lane] = zc;
+            double nn = 0.0, no = 0.0;
+            if (t < T - 1) { // slice t+1 (another CTA) cannot have touched nodes >= jb yet
+                double xnx[DM];
+                const volatile double *q = Xchain + ((size_t)(t + 1) * n + jl) * d;
+#pragma unroll
+                for (int k = 0; k < DM; k++) xnx[k] = (k < d) ? q[k] : 0.0;
+                nn = prior_next<DM>(p, c, t, jl, x, xnx);
+                no = prior_next<DM>(p, c, t, jl, x0, xnx);
+            }
+            st_nn[lane] = nn;
+            st_no[lane] = no;
+        }
+        __syncthreads();
+        const int jend = (n - jb) < 32 ? (n - jb) : 32;
+        for (int jj = 0; jj < jend; jj++) {
+            const int j = jb + jj;
+            double x[DM], x0[DM];
+            load_pos<DM>(st_prop + jj * d, d, x);
+            load_pos<DM>(Xt + (size_t)j * d, d, x0);
+            double ll_new, ll_old;
+            node_loglik2<LK, DM>(p.net, Xt, rinv, c, t, j, x, x0, b0, b1, lane, ll_new, ll_old,
+                                 p.flags, warp, nwarps);
+            if (lane == 0) { part[warp * 2] = ll_new; part[warp * 2 + 1] = ll_old; }
+            __syncthreads();
+            if (warp == 0) {
+                ll_new = 0.0; ll_old = 0.0;
+                for (int w = 0; w < nwarps; w++) { ll_new += part[w * 2]; ll_old += part[w * 2 + 1]; }
+                double xp[DM];
+#pragma unroll
+                for (int k = 0; k < DM; k++) xp[k] = 0.0;
+                if (t > 0) {
+                    while (prog[t - 1] <= j) { /* spin on the L2-resident flag of slice t-1 */ }
+                    __threadfence();
+                    const volatile double *q = Xchain + ((size_t)(t - 1) * n + j) * d;
+#pragma unroll
+                    for (int k = 0; k < DM; k++) if (k < d) xp[k] = q[k];
+                }
+                const double inv = st_inv[jj];
+                const int zc = st_zc[jj];
+                double lp_new = __dsub_rn(ll_new, prior_prev<DM>(p, c, t, zc, inv, x, xp));
+                double lp_old = __dsub_rn(ll_old, prior_prev<DM>(p, c, t, zc, inv, x0, xp));
+                if (t < T - 1) {
+                    lp_new = __dsub_rn(lp_new, st_nn[jj]);
+                    lp_old = __dsub_rn(lp_old, st_no[jj]);
+                }
+                const double ratio = __dsub_rn(lp_new, lp_old);
+                const int acc = (st_logu[jj] >= ratio) ? 0 : 1;
+                const bool me = lane == jj;
+                my_acc = me ? acc : my_acc;
+                nonfinite |= me && (!(ratio == ratio) || ratio - ratio != 0.0);
+                if (me) {
+                    if (acc) {
+#pragma unroll
+                        for (int k = 0; k < DM; k++)
+                            if (k < d) {
+                                Xt[(size_t)j * d + k] = x[k];
+                                if (XS) Xg[(size_t)j * d + k] = x[k];
+                            }
+                    }
+                    if (p.ratio) p.ratio[((size_t)c * T + t) * n + j] = ratio;
+                    __threadfence();
+                    prog[t] = j + 1;
+                }
+            }
+            __syncthreads();
+        }
+        if (mine) {
+            metropolis_bookkeep(my_step, my_nacc, my_nsteps, my_until, p.tune, p.tune_interval,
+                                my_acc, false);
+            p.step[gs] = my_step; p.nacc[gs] = my_nacc; p.nsteps[gs] = my_nsteps; p.until[gs] = my_until;
+            if (p.accepted) p.accepted[gs] = my_acc;
+        }
+        __syncthreads();
+    }
+    if (nonfinite) atomicOr(p.flags, 1u);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -171,8 +171,11 @@ LSM_CASES = [("lsm_undirected_monks.npz", False, False), ("lsm_directed_monks.np
              ("lsm_casecontrol_monks.npz", True, True)]
 
 
+@pytest.mark.parametrize("mode", ["chain", "slice"])
 @pytest.mark.parametrize("name,directed,cc", LSM_CASES)
-def test_lsm_latent_sweep_replay(name, directed, cc):
+def test_lsm_latent_sweep_replay(name, directed, cc, mode, monkeypatch):
+    # both sweep kernels: one CTA per chain (warp per slice) and one CTA per (chain, slice)
+    monkeypatch.setenv("DLSM_SWEEP_MODE", mode)
     g, L = load_golden(name), _F()
     S = g["X_in"].shape[0]
     e = _lsm_engine(g, directed, cc)
@@ -234,8 +237,10 @@ def test_lsm_center_replay():
 HDP_CASES = [("hdp_undirected_split.npz", False), ("hdp_directed_monks.npz", True)]
 
 
+@pytest.mark.parametrize("mode", ["chain", "slice"])
 @pytest.mark.parametrize("name,directed", HDP_CASES)
-def test_hdp_sweep_center_labels_replay(name, directed):
+def test_hdp_sweep_center_labels_replay(name, directed, mode, monkeypatch):
+    monkeypatch.setenv("DLSM_SWEEP_MODE", mode)
     g, L = load_golden(name), _F()
     S, T, n, d = g["X_in"].shape
     K = g["sigma"].shape[1]
@@ -278,9 +283,17 @@ def _synthetic(T, n, d, directed, seed, density=0.15):
     return rng, X, Y
 
 
-@pytest.mark.parametrize("T,n,d,directed", [(9, 120, 2, False), (4, 70, 3, False),
-                                            (5, 90, 2, True), (10, 500, 2, False)])
-def test_free_running_replay_vs_oracle(T, n, d, directed):
+@pytest.mark.parametrize("T,n,d,directed,mode", [
+    (9, 120, 2, False, "auto"), (4, 70, 3, False, "auto"), (5, 90, 2, True, "auto"),
+    (10, 500, 2, False, "chain"),     # positions in shared memory, 16 chunks per row
+    (10, 500, 2, False, "slice"),     # CTA per slice, 8 warps per row
+    (6, 700, 2, True, "slice"),       # directed, CTA per slice
+    (10, 1500, 2, False, "chain"),    # chain too big for shared memory: positions stay in global/L2
+    (2, 1900, 8, False, "slice"),     # slice too big for half the shared memory: global positions, d = 8
+])
+def test_free_running_replay_vs_oracle(T, n, d, directed, mode, monkeypatch):
+    if mode != "auto":
+        monkeypatch.setenv("DLSM_SWEEP_MODE", mode)
     L = _F()
     rng, X, Y = _synthetic(T, n, d, directed, seed=T * 1000 + n)
     radii = rng.dirichlet(np.ones(n) * 5) if directed else None
@@ -288,7 +301,7 @@ def test_free_running_replay_vs_oracle(T, n, d, directed):
     step0 = 0.0075 / 4 if directed else 0.08
     sig = 0.001 if directed else 0.1
     tau = float(np.mean(X[0] * X[0])) if directed else 2.0
-    n_sweeps = 3 if n >= 500 else 6
+    n_sweeps = 2 if n >= 1500 else (3 if n >= 500 else 6)
     tun = O.TunerState((T, n), step0, tune=4, tune_interval=2)
     e = _engine(T=T, n=n, d=d, is_directed=directed, tune=4, tune_interval=2)
     e.set_network(Y)
