@@ -33,6 +33,9 @@ WORKLOADS = {
                  desc="directed DynamicNetworkLSM with radii (n=2000, T=20, d=2), single chain"),
     "cfg4": dict(T=10, n=500, d=2, K=10, directed=False, chains=296,
                  desc="DynamicNetworkHDPLPCM multi-chain (n=500, T=10, d=2, K=10)"),
+    "cfg5": dict(T=10, n=50000, d=2, K=0, directed=True, chains=8, case_control=True, n_control=100,
+                 desc="directed LSM, case-control likelihood, sparse network (n=50000, T=10, d=2, "
+                      "out-degree ~ Poisson(10), 100 controls)"),
 }
 
 
@@ -40,8 +43,65 @@ def expit(x):
     return 1.0 / (1.0 + np.exp(-x))
 
 
+def make_sparse_workload(name, seed=42):
+    """cfg 5: a sparse directed network that cannot exist as a dense tensor (200 GB): latent random
+    walk, out-neighbours drawn among the nearest nodes in the latent space, stored as the padded
+    edge lists + control sets of the case-control likelihood."""
+    from scipy.spatial import cKDTree
+    w = dict(WORKLOADS[name])
+    T, n, d, nc = w["T"], w["n"], w["d"], w["n_control"]
+    rng = np.random.RandomState(seed)
+    X = np.empty((T, n, d))
+    X[0] = 0.01 * rng.randn(n, d)
+    for t in range(1, T):
+        X[t] = X[t - 1] + 0.001 * rng.randn(n, d)
+    out_lists = []
+    for t in range(T):
+        deg = np.minimum(rng.poisson(10, n), 30)
+        _, nb = cKDTree(X[t]).query(X[t], k=41)
+        pick = np.argsort(rng.rand(n, 40), axis=1)          # random subset of the 40 nearest
+        out_lists.append((deg, np.take_along_axis(nb[:, 1:], pick, axis=1)))
+    max_out = 30
+    out_e = np.zeros((T, n, max_out), np.int32)
+    degs = np.zeros((T, n, 2), np.int32)
+    in_lists = []
+    for t, (deg, cand) in enumerate(out_lists):
+        keep = np.arange(max_out)[None, :] < deg[:, None]
+        out_e[t] = np.where(keep, cand[:, :max_out], 0)
+        degs[t, :, 1] = deg
+        src = np.repeat(np.arange(n), deg)
+        dst = cand[:, :max_out][keep]
+        order = np.lexsort((src, dst))
+        in_lists.append((dst[order], src[order]))
+        degs[t, :, 0] = np.bincount(dst, minlength=n)
+    max_in = int(degs[:, :, 0].max())
+    in_e = np.zeros((T, n, max_in), np.int32)
+    for t, (dst, src) in enumerate(in_lists):
+        start = np.searchsorted(dst, dst, side="left")
+        in_e[t, dst, np.arange(dst.size) - start] = src
+    # control sets: uniform non-neighbours (collisions with neighbours/self are rare at this
+    # sparsity and are redrawn once; a residual collision only perturbs the estimator's weights)
+    def controls(edges, deg_col):
+        c = rng.randint(0, n, size=(T, n, nc)).astype(np.int32)
+        for _ in range(2):
+            bad = c == np.arange(n, dtype=np.int32)[None, :, None]
+            for q in range(edges.shape[2]):
+                bad |= (c == edges[:, :, q:q + 1]) & (q < degs[:, :, deg_col])[:, :, None]
+            c[bad] = rng.randint(0, n, size=int(bad.sum()))
+        return c
+    radii = rng.dirichlet(np.ones(n) * 20.0)
+    w.update(name=name, X=X, Y=None, radii=radii, intercept=np.array([0.3, 0.7]),
+             step_X=0.0075 / n * 40, sigma_sq=1e-6, tau_sq=float(np.mean(X[0] * X[0])),
+             degrees=degs, in_edges=in_e, out_edges=out_e, ctrl_in=controls(in_e, 0),
+             ctrl_out=controls(out_e, 1), density=float(degs[:, :, 1].mean() / n),
+             mean_deg=float(degs[:, :, 0].mean() + degs[:, :, 1].mean()))
+    return w
+
+
 def make_workload(name, seed=42):
     """Synthetic community-structured dynamic network of the named shape plus a start state."""
+    if WORKLOADS[name].get("case_control"):
+        return make_sparse_workload(name, seed)
     w = dict(WORKLOADS[name])
     T, n, d, K = w["T"], w["n"], w["d"], max(w["K"], 4)
     rng = np.random.RandomState(seed)
@@ -91,6 +151,8 @@ def make_workload(name, seed=42):
 def bytes_per_node_update(w):
     """Algorithmic bytes of one node-update, model M1 (SURVEY.md 8d / BASELINE.md section 4)."""
     n, d = w["n"], w["d"]
+    if w.get("case_control"):
+        return (w["mean_deg"] + 2 * w["n_control"]) * (4 + 8.0 * d + 8)
     if w["directed"]:
         return 2 * n / 8.0 + 8.0 * d * n + 8.0 * n
     return n / 8.0 + 8.0 * d * n
@@ -100,8 +162,12 @@ def build_engine(w, chains, device, chain_offset, seed=42):
     from dynetlsm_b200 import _lib as L
     e = L.Engine(T=w["T"], n=w["n"], d=w["d"], n_chains=chains, K=w["K"], is_directed=w["directed"],
                  mixture=bool(w["K"]), device=device, tune=2500, tune_interval=100,
-                 radii_tune=None)
-    e.set_network(w["Y"])
+                 radii_tune=None, case_control=bool(w.get("case_control")))
+    if w.get("case_control"):
+        e.set_edge_lists(w["degrees"], w["in_edges"], w["out_edges"])
+        e.set_controls(w["ctrl_in"], w["ctrl_out"])
+    else:
+        e.set_network(w["Y"])
     rng = np.random.RandomState(1000 + chain_offset)
     disp = 0.1 * (1.0 / w["n"] if w["directed"] else 1.0)
     X = w["X"][None] + disp * rng.randn(chains, w["T"], w["n"], w["d"])   # dispersed starts
@@ -185,8 +251,11 @@ def _cpu_worker(args):
     if kind == "reference":
         import ref_driver as R
         mix = (w["mu"], w["sigma"], np.array([w["lmbda"]]), w["z"].copy(), w["w"]) if w["K"] else None
+        cc = None
+        if w.get("case_control"):
+            cc = {k: w[k].astype(np.int64) for k in ("in_edges", "out_edges", "degrees", "ctrl_in", "ctrl_out")}
         st = R.make_state(w["Y"], X0, w["intercept"], is_directed=w["directed"], radii=w["radii"],
-                          mixture=mix, step_X=w["step_X"], tune=2500, tau_sq=w["tau_sq"],
+                          mixture=mix, cc=cc, step_X=w["step_X"], tune=2500, tau_sq=w["tau_sq"],
                           sigma_sq=w["sigma_sq"])
         R.hot_path_sweep(st, rng)  # warm-up (imports, first-call overheads)
         t0 = time.perf_counter()
@@ -194,6 +263,8 @@ def _cpu_worker(args):
             R.hot_path_sweep(st, rng)
         return time.perf_counter() - t0
     import pyoracle as O
+    if w.get("case_control"):
+        raise SystemExit("the C-oracle CPU leg does not cover cfg5; build oracle/_ref")
     X = np.ascontiguousarray(X0)
     tun = O.TunerState((T, n), w["step_X"], tune=2500, tune_interval=100)
     itun = O.TunerState((w["intercept"].size,), 0.1, tune=2500, tune_interval=100)
@@ -247,7 +318,7 @@ def cpu_hot_path(name, sweeps_per_core, cores=None):
 
 def cpu_sweeps_for(name, target_s=12.0):
     # rough per-sweep cost of the reference loop (survey-time measurements), to bound the sample
-    est = {"cfg1": 0.006, "cfg2": 0.12, "cfg3": 25.0, "cfg4": 0.9}[name]
+    est = {"cfg1": 0.006, "cfg2": 0.12, "cfg3": 25.0, "cfg4": 0.9, "cfg5": 60.0}[name]
     if cpu_kind() == "port":
         est *= 0.2
     return max(1, int(target_s / est))
@@ -291,7 +362,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))  # cfg5: GPU arm only
     ap.add_argument("--chains-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -393,15 +464,19 @@ def main():
         def pinned(a):
             tt = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
             return tt.numpy()
-        hX = pinned(e.get(L.F_X))
-        ins = [(L.F_X, hX)]
+        # inputs of one HDP-LPCM fit iteration: the mixture parameters the host just resampled
+        # (positions stay resident; the LSM loop, which rotates X on the host after burn-in,
+        # uploads X as well); results: positions, labels, label counts, intercepts
+        ins = []
         if w["K"]:
             ins += [(L.F_MU, pinned(e.get(L.F_MU))), (L.F_SIGMA, pinned(e.get(L.F_SIGMA))),
                     (L.F_LAMBDA, pinned(e.get(L.F_LAMBDA))), (L.F_WEIGHTS, pinned(e.get(L.F_WEIGHTS)))]
+        else:
+            ins += [(L.F_X, pinned(e.get(L.F_X)))]
         outs = [L.F_X, L.F_INTERCEPT] + ([L.F_Z, L.F_NCOUNT, L.F_NK] if w["K"] else []) + \
                ([L.F_RADII] if w["directed"] else [])
+        bufs = {f: pinned(e.get(f)) for f in outs}
         h2d = sum(a.nbytes for _, a in ins)
-        d2h = 0
         nst = max(3, min(args.steps, 10))
         for it in range(2 + nst):
             if it == 2:
@@ -410,8 +485,9 @@ def main():
             for f, a in ins:
                 e.set(f, a)
             e.run_sweeps(1)
-            got = [e.get(f) for f in outs]
-            ins[0] = (L.F_X, got[0])
+            got = [e.get(f, out=bufs[f]) for f in outs]
+            if not w["K"]:
+                ins[0] = (L.F_X, got[0])
         barrier()
         dt = time.perf_counter() - t0
         d2h = sum(a.nbytes for a in got)

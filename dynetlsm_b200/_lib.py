@@ -198,8 +198,15 @@ class Engine(object):
         a = (_i32 if f in _INT_FIELDS else _f64)(a, self.shape_of(f))
         self._ck(self.L.dlsm_set_state(self.h, f, a.ctypes.data_as(C.c_void_p), a.nbytes))
 
-    def get(self, f):
-        a = np.empty(self.shape_of(f), dtype=np.int32 if f in _INT_FIELDS else np.float64)
+    def get(self, f, out=None):
+        """Copy a state field to the host; ``out`` (e.g. a pinned buffer) is filled in place."""
+        dt = np.int32 if f in _INT_FIELDS else np.float64
+        if out is None:
+            a = np.empty(self.shape_of(f), dtype=dt)
+        else:
+            a = out
+            if a.dtype != dt or a.shape != self.shape_of(f) or not a.flags.c_contiguous:
+                raise ValueError("out must be C-contiguous %s of shape %s" % (dt.__name__, self.shape_of(f)))
         self._ck(self.L.dlsm_get_state(self.h, f, a.ctypes.data_as(C.c_void_p), a.nbytes))
         return a
 
