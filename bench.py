@@ -184,6 +184,15 @@ def build_engine(w, chains, device, chain_offset, seed=42):
         e.set(L.F_LAMBDA, np.full(chains, w["lmbda"]))
         e.set(L.F_WEIGHTS, np.tile(w["w"][None], (chains, 1, 1, 1)))
         e.set(L.F_Z, np.tile(w["z"][None], (chains, 1, 1)))
+        # sticky HDP-HMM hyper state and priors (hdp_lpcm.py defaults, n-dependent 'auto' values)
+        K, n, d = w["K"], w["n"], w["d"]
+        mvp = (n ** (2.0 / d)) / 50.0
+        a, a0 = 2.0, (4.0 ** 2 + 2) * 2
+        b0, b_ = (a0 - 2) * mvp * 2, (a + 2) * mvp
+        d0 = (4.0 ** 2 / b_) * 2
+        e.set(L.F_BETA, np.full((chains, K), 1.0 / K))
+        e.set(L.F_HYPER, np.tile(np.array([[1.0, 1.0, 1.0, 4.0, mvp, b_, 0, 0]]), (chains, 1)))
+        e.set_hdp_prior(a, a0, b0, b_ * d0, d0, 0.9, 0.01, 1.0, 0.1, 1.0, 1.0, 5, 0.1, True, True)
     e.set_tuner(w["step_X"])
     e.set_rng(seed, chain_offset=chain_offset)
     return e
@@ -464,17 +473,12 @@ def main():
         def pinned(a):
             tt = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
             return tt.numpy()
-        # inputs of one HDP-LPCM fit iteration: the mixture parameters the host just resampled
-        # (positions stay resident; the LSM loop, which rotates X on the host after burn-in,
-        # uploads X as well); results: positions, labels, label counts, intercepts
-        ins = []
-        if w["K"]:
-            ins += [(L.F_MU, pinned(e.get(L.F_MU))), (L.F_SIGMA, pinned(e.get(L.F_SIGMA))),
-                    (L.F_LAMBDA, pinned(e.get(L.F_LAMBDA))), (L.F_WEIGHTS, pinned(e.get(L.F_WEIGHTS)))]
-        else:
-            ins += [(L.F_X, pinned(e.get(L.F_X)))]
-        outs = [L.F_X, L.F_INTERCEPT] + ([L.F_Z, L.F_NCOUNT, L.F_NK] if w["K"] else []) + \
-               ([L.F_RADII] if w["directed"] else [])
+        # the function-level contract of the reference (sample_latent_positions(Y, X, ...) -> X, then
+        # the other blocks): every step takes the positions from (pinned) host memory and returns
+        # the new state -- positions, labels, intercepts and the mixture parameters fit() records
+        ins = [(L.F_X, pinned(e.get(L.F_X)))]
+        outs = [L.F_X, L.F_INTERCEPT] + ([L.F_RADII] if w["directed"] else []) + \
+               ([L.F_Z, L.F_MU, L.F_SIGMA, L.F_LAMBDA, L.F_BETA, L.F_WEIGHTS, L.F_HYPER] if w["K"] else [])
         bufs = {f: pinned(e.get(f)) for f in outs}
         h2d = sum(a.nbytes for _, a in ins)
         nst = max(3, min(args.steps, 10))
@@ -486,8 +490,7 @@ def main():
                 e.set(f, a)
             e.run_sweeps(1)
             got = [e.get(f, out=bufs[f]) for f in outs]
-            if not w["K"]:
-                ins[0] = (L.F_X, got[0])
+            ins[0] = (L.F_X, got[0])
         barrier()
         dt = time.perf_counter() - t0
         d2h = sum(a.nbytes for a in got)
@@ -514,7 +517,7 @@ def main():
                            "density": w["density"], "rng": "device Philox4x32-10",
                            "step": "latent sweep + centre + intercept MH" +
                                    (" + radii MH" if w["directed"] else "") +
-                                   (" + label FFBS" if w["K"] else ""),
+                                   (" + label FFBS + HDP conjugate updates" if w["K"] else ""),
                            "l2": "flushed between timed iterations (256 MiB write)"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk,
                 "gpu_launches": int(launches),

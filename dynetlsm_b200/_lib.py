@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libdlsm.so")
 SRC = [os.path.join(HERE, "csrc", f) for f in ("dlsm.cu", "dlsm_kernels.cuh", "dlsm_device.cuh",
-                                              "dlsm_tables.cuh")]
+                                              "dlsm_tables.cuh", "dlsm_hdp.cuh")]
 SRC.append(os.path.join(ROOT, "include", "dlsm.h"))
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -51,6 +51,15 @@ class Hyper(C.Structure):
                 ("intercept_prior", C.c_double * 2), ("intercept_variance_prior", C.c_double)]
 
 
+class HdpPrior(C.Structure):
+    _fields_ = [("a", C.c_double), ("a0", C.c_double), ("b0", C.c_double), ("c0", C.c_double),
+                ("d0", C.c_double), ("lambda_prior", C.c_double), ("lambda_variance_prior", C.c_double),
+                ("gamma_prior_shape", C.c_double), ("gamma_prior_rate", C.c_double),
+                ("alpha_init_shape", C.c_double), ("alpha_init_rate", C.c_double),
+                ("alpha_kappa_shape", C.c_double), ("alpha_kappa_rate", C.c_double),
+                ("resample_mvp", C.c_int32), ("resample_b", C.c_int32)]
+
+
 class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("node_updates", C.c_uint64),
                 ("sweeps", C.c_uint64), ("latent_ms", C.c_double), ("other_ms", C.c_double),
@@ -63,15 +72,15 @@ EXPORTS = [
     "dlsm_set_stream", "dlsm_synchronize", "dlsm_set_network_dense", "dlsm_set_edge_lists",
     "dlsm_set_controls", "dlsm_set_state", "dlsm_get_state", "dlsm_set_hyper", "dlsm_set_rng",
     "dlsm_sweep_latent", "dlsm_center", "dlsm_sample_intercepts", "dlsm_sample_radii",
-    "dlsm_sample_labels", "dlsm_run_sweeps", "dlsm_loglik_partial", "dlsm_loglik_full",
-    "dlsm_gaussian_likelihood", "dlsm_debug_draws", "dlsm_enable_timing", "dlsm_get_counters",
+    "dlsm_sample_labels", "dlsm_set_hdp_prior", "dlsm_hdp_update", "dlsm_run_sweeps", "dlsm_loglik_partial", "dlsm_loglik_full",
+    "dlsm_gaussian_likelihood", "dlsm_debug_set_counts", "dlsm_debug_draws", "dlsm_enable_timing", "dlsm_get_counters",
 ]
 
 F_X, F_INTERCEPT, F_RADII, F_Z, F_MU, F_SIGMA, F_LAMBDA, F_WEIGHTS = range(8)
 F_X_STEP, F_X_NACC, F_X_NSTEPS, F_X_UNTIL = 8, 9, 10, 11
 F_B_STEP, F_B_NACC, F_B_NSTEPS, F_B_UNTIL = 12, 13, 14, 15
 F_R_STEP, F_R_NACC, F_R_NSTEPS, F_R_UNTIL = 16, 17, 18, 19
-F_NCOUNT, F_NK = 20, 21
+F_NCOUNT, F_NK, F_BETA, F_HYPER = 20, 21, 22, 23
 _INT_FIELDS = {F_Z, F_X_NACC, F_X_NSTEPS, F_X_UNTIL, F_B_NACC, F_B_NSTEPS, F_B_UNTIL, F_R_NACC,
                F_R_NSTEPS, F_R_UNTIL, F_NK}
 
@@ -107,10 +116,13 @@ def load():
     L.dlsm_sample_intercepts.argtypes = [vp, dp, dp, ip, dp]
     L.dlsm_sample_radii.argtypes = [vp, dp, dp, ip, dp]
     L.dlsm_sample_labels.argtypes = [vp, dp]
+    L.dlsm_set_hdp_prior.argtypes = [vp, C.POINTER(HdpPrior)]
+    L.dlsm_hdp_update.argtypes = [vp]
     L.dlsm_run_sweeps.argtypes = [vp, C.c_int32, C.c_uint32]
     L.dlsm_loglik_partial.argtypes = [vp, dp]
     L.dlsm_loglik_full.argtypes = [vp, dp]
     L.dlsm_gaussian_likelihood.argtypes = [vp, dp]
+    L.dlsm_debug_set_counts.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.dlsm_debug_draws.argtypes = [vp, dp, dp]
     L.dlsm_enable_timing.argtypes = [vp, C.c_int]
     L.dlsm_get_counters.argtypes = [vp, C.POINTER(Counters)]
@@ -192,7 +204,8 @@ class Engine(object):
                 F_X_STEP: (C_, T, n), F_X_NACC: (C_, T, n), F_X_NSTEPS: (C_, T, n),
                 F_X_UNTIL: (C_, T, n), F_B_STEP: (C_, 2), F_B_NACC: (C_, 2), F_B_NSTEPS: (C_, 2),
                 F_B_UNTIL: (C_, 2), F_R_STEP: (C_,), F_R_NACC: (C_,), F_R_NSTEPS: (C_,),
-                F_R_UNTIL: (C_,), F_NCOUNT: (C_, T, K, K), F_NK: (C_, T, K)}[f]
+                F_R_UNTIL: (C_,), F_NCOUNT: (C_, T, K, K), F_NK: (C_, T, K), F_BETA: (C_, K),
+                F_HYPER: (C_, 8)}[f]
 
     def set(self, f, a):
         a = (_i32 if f in _INT_FIELDS else _f64)(a, self.shape_of(f))
@@ -295,10 +308,26 @@ class Engine(object):
             U = _f64(U, (self.C, self.n, self.T))
         self._ck(self.L.dlsm_sample_labels(self.h, _dp(U)))
 
+    def set_hdp_prior(self, a, a0, b0, c0, d0, lambda_prior, lambda_variance_prior,
+                      gamma_prior_shape, gamma_prior_rate, alpha_init_shape, alpha_init_rate,
+                      alpha_kappa_shape, alpha_kappa_rate, resample_mvp=True, resample_b=True):
+        pr = HdpPrior()
+        pr.a, pr.a0, pr.b0 = float(a), float(a0 or 0.0), float(b0 or 0.0)
+        pr.c0, pr.d0 = float(c0 or 0.0), float(d0 or 0.0)
+        pr.lambda_prior, pr.lambda_variance_prior = float(lambda_prior), float(lambda_variance_prior)
+        pr.gamma_prior_shape, pr.gamma_prior_rate = float(gamma_prior_shape), float(gamma_prior_rate)
+        pr.alpha_init_shape, pr.alpha_init_rate = float(alpha_init_shape), float(alpha_init_rate)
+        pr.alpha_kappa_shape, pr.alpha_kappa_rate = float(alpha_kappa_shape), float(alpha_kappa_rate)
+        pr.resample_mvp, pr.resample_b = int(bool(resample_mvp)), int(bool(resample_b))
+        self._ck(self.L.dlsm_set_hdp_prior(self.h, C.byref(pr)))
+
+    def hdp_update(self):
+        self._ck(self.L.dlsm_hdp_update(self.h))
+
     def run_sweeps(self, n_sweeps, skip_center=False, skip_intercepts=False, skip_radii=False,
-                   skip_labels=False):
+                   skip_labels=False, skip_hdp=False):
         flags = (1 if skip_center else 0) | (2 if skip_intercepts else 0) | \
-                (4 if skip_radii else 0) | (8 if skip_labels else 0)
+                (4 if skip_radii else 0) | (8 if skip_labels else 0) | (16 if skip_hdp else 0)
         self._ck(self.L.dlsm_run_sweeps(self.h, int(n_sweeps), flags))
 
     # -- probes --------------------------------------------------------------------------

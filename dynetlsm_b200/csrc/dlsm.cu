@@ -2,6 +2,7 @@
 // No CPU fallback: every compute entry point needs a CUDA device.
 #include "../../include/dlsm.h"
 #include "dlsm_kernels.cuh"
+#include "dlsm_hdp.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -51,7 +52,9 @@ struct dlsm_handle {
     int sweep_mode = 0;             // 0 auto, 1 CTA per chain, 2 CTA per (chain, slice)
     // rng
     uint64_t seed = 0, chain_offset = 0;
-    uint32_t sweep_idx[4] = {0, 0, 0, 0};
+    uint32_t sweep_idx[5] = {0, 0, 0, 0, 0};
+    dlsm_hdp_prior hdp_prior;
+    bool have_hdp_prior = false;
     // counters
     dlsm_counters ctr;
     bool timing = false;
@@ -107,6 +110,8 @@ size_t field_elems(const dlsm_config &c, int f)
         return C * T * n;
     case DLSM_F_R_STEP: case DLSM_F_R_NACC: case DLSM_F_R_NSTEPS: case DLSM_F_R_UNTIL: return C;
     case DLSM_F_NK: return C * T * K;
+    case DLSM_F_BETA: return C * K;
+    case DLSM_F_HYPER: return K > 0 ? C * 8 : 0;
     default: return 0;
     }
 }
@@ -617,7 +622,7 @@ int dlsm_set_rng(dlsm_handle *h, uint64_t seed, uint64_t chain_offset, uint64_t 
     if (!h) return DLSM_ERR_INVALID;
     h->seed = seed;
     h->chain_offset = chain_offset;
-    for (int k = 0; k < 4; k++) h->sweep_idx[k] = (uint32_t)sweep_index;
+    for (int k = 0; k < 5; k++) h->sweep_idx[k] = (uint32_t)sweep_index;
     return DLSM_OK;
 }
 
@@ -863,6 +868,49 @@ int dlsm_sample_labels(dlsm_handle *h, const double *U)
     return DLSM_OK;
 }
 
+static int hdp_update_async(dlsm_handle *h)
+{
+    const dlsm_config &c = h->cfg;
+    HdpParams p;
+    memset(&p, 0, sizeof(p));
+    p.C = c.n_chains; p.T = c.T; p.n = c.n; p.d = c.d; p.K = c.K;
+    p.X = F<double>(h, DLSM_F_X); p.z = F<int32_t>(h, DLSM_F_Z);
+    p.ncount = F<double>(h, DLSM_F_NCOUNT); p.nk = F<int32_t>(h, DLSM_F_NK);
+    p.mu = F<double>(h, DLSM_F_MU); p.sigma = F<double>(h, DLSM_F_SIGMA);
+    p.lambda = F<double>(h, DLSM_F_LAMBDA); p.beta = F<double>(h, DLSM_F_BETA);
+    p.weights = F<double>(h, DLSM_F_WEIGHTS); p.hyper = F<double>(h, DLSM_F_HYPER);
+    p.pr = h->hdp_prior;
+    p.seed = h->seed; p.sweep = h->sweep_idx[4]; p.chain_offset = (uint32_t)h->chain_offset;
+    const size_t smem = hdp_smem_bytes(c.T, c.K, c.d);
+    if (smem > kMaxSmem) FAIL(h, DLSM_ERR_UNSUPPORTED, "T*K*K too large for the HDP update kernel");
+    CU(h, cudaFuncSetAttribute(k_hdp_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    begin_phase(h, 1);
+    int rc = launch_simple(h, k_hdp_update, dim3(c.n_chains), dim3(128), smem, p);
+    end_phase(h);
+    h->sweep_idx[4] += 1;
+    return rc;
+}
+
+int dlsm_set_hdp_prior(dlsm_handle *h, const dlsm_hdp_prior *pr)
+{
+    if (!h || !pr) return DLSM_ERR_INVALID;
+    if (h->cfg.prior != DLSM_PRIOR_MIXTURE) FAIL(h, DLSM_ERR_INVALID, "needs the mixture prior");
+    h->hdp_prior = *pr;
+    h->have_hdp_prior = true;
+    return DLSM_OK;
+}
+
+int dlsm_hdp_update(dlsm_handle *h)
+{
+    if (!h) return DLSM_ERR_INVALID;
+    if (!h->have_hdp_prior) FAIL(h, DLSM_ERR_NOTSET, "dlsm_set_hdp_prior has not been called");
+    CU(h, cudaSetDevice(h->cfg.device));
+    int rc = hdp_update_async(h);
+    if (rc != DLSM_OK) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return DLSM_OK;
+}
+
 int dlsm_run_sweeps(dlsm_handle *h, int32_t n_sweeps, uint32_t flags)
 {
     if (!h || n_sweeps < 0) return DLSM_ERR_INVALID;
@@ -878,9 +926,10 @@ int dlsm_run_sweeps(dlsm_handle *h, int32_t n_sweeps, uint32_t flags)
         if (h->cfg.is_directed && !(flags & 4u) &&
             (rc = radii_async(h, true, nullptr, nullptr, nullptr)) != DLSM_OK)
             return rc;
-        if (h->cfg.prior == DLSM_PRIOR_MIXTURE && !(flags & 8u) &&
-            (rc = labels_async(h, nullptr, nullptr, 1)) != DLSM_OK)
-            return rc;
+        if (h->cfg.prior == DLSM_PRIOR_MIXTURE && !(flags & 8u)) {
+            if ((rc = labels_async(h, nullptr, nullptr, 1)) != DLSM_OK) return rc;
+            if (h->have_hdp_prior && !(flags & 16u) && (rc = hdp_update_async(h)) != DLSM_OK) return rc;
+        }
     }
     return check_flags(h);
 }
@@ -935,6 +984,17 @@ int dlsm_gaussian_likelihood(dlsm_handle *h, double *out)
     if (rc == DLSM_OK) rc = download(h, out, d, N * 8);
     cudaFree(d);
     return rc;
+}
+
+int dlsm_debug_set_counts(dlsm_handle *h, int field, const void *host, size_t bytes)
+{
+    if (!h || !host || (field != DLSM_F_NCOUNT && field != DLSM_F_NK)) return DLSM_ERR_INVALID;
+    if (bytes != h->field_bytes[field] || bytes == 0) FAIL(h, DLSM_ERR_INVALID, "bad size");
+    CU(h, cudaSetDevice(h->cfg.device));
+    int rc = upload(h, h->field[field], host, bytes);
+    if (rc != DLSM_OK) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return DLSM_OK;
 }
 
 int dlsm_debug_draws(dlsm_handle *h, double *eps, double *logu)

@@ -1,0 +1,308 @@
+// dlsm_hdp.cuh -- the conjugate / auxiliary-variable block of one HDP-LPCM sweep on the device
+// (reference: hdp_lpcm.py:881-1023, sample_auxillary.py:6-50,
+// sample_concentration.py:6-21, distributions.py:72-102).  One CTA per chain, everything small
+// lives in shared memory; all draws come from per-(chain, sweep, site) Philox streams, so the
+// block is only distributionally -- not draw-for-draw -- equal to the host version
+// (dynetlsm_b200/hdp_updates.py), which stays the path of the bit-exact replay mode.
+#pragma once
+#include "dlsm_device.cuh"
+#include "../../include/dlsm.h"
+
+namespace dlsm {
+
+constexpr uint32_t kRngHdp = 4;
+
+// sequential stream of uniforms / normals / gammas / betas on one Philox (site) lane
+struct Stream {
+    uint64_t seed;
+    uint32_t site, sweep, chain, blk;
+    double spare;
+    bool has_spare;
+    __device__ Stream(uint64_t s, uint32_t site_, uint32_t sweep_, uint32_t chain_)
+        : seed(s), site(site_), sweep(sweep_), chain(chain_), blk(0), spare(0.0), has_spare(false) {}
+    __device__ double uniform()
+    {
+        if (has_spare) { has_spare = false; return spare; }
+        const U2 u = philox_u2(seed, site, sweep, chain, kRngHdp, blk++);
+        spare = u.b;
+        has_spare = true;
+        return u.a;
+    }
+    __device__ double normal()
+    {
+        double z0, z1;
+        box_muller(philox_u2(seed, site, sweep, chain, kRngHdp, blk++), z0, z1);
+        return z0;
+    }
+    // Marsaglia & Tsang (2000); shape < 1 boosted by U^(1/shape)
+    __device__ double gamma(double shape)
+    {
+        if (!(shape > 0.0)) return 0.0;
+        double boost = 1.0;
+        if (shape < 1.0) {
+            boost = pow(uniform(), 1.0 / shape);
+            shape += 1.0;
+        }
+        const double dd = shape - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * dd);
+        for (int it = 0; it < 256; it++) {
+            const double z = normal();
+            double v = 1.0 + cc * z;
+            if (v <= 0.0) continue;
+            v = v * v * v;
+            if (log(uniform()) < 0.5 * z * z + dd - dd * v + dd * log(v)) return boost * dd * v;
+        }
+        return boost * dd;
+    }
+    __device__ double beta(double a, double b)
+    {
+        const double x = gamma(a), y = gamma(b);
+        return x / (x + y);
+    }
+    __device__ int bernoulli(double p) { return uniform() < p ? 1 : 0; }
+    __device__ int binomial(int n, double p)
+    {
+        int s = 0;
+        for (int i = 0; i < n; i++) s += bernoulli(p);
+        return s;
+    }
+};
+
+struct HdpParams {
+    int C, T, n, d, K;
+    const double *X;        // [C][T][n][d]
+    const int32_t *z;       // [C][T][n]
+    const double *ncount;   // [C][T][K][K]
+    const int32_t *nk;      // [C][T][K]
+    double *mu, *sigma, *lambda, *beta, *weights, *hyper;
+    dlsm_hdp_prior pr;
+    uint64_t seed;
+    uint32_t sweep, chain_offset;
+};
+
+// Escobar & West (1995) auxiliary-variable update of a DP concentration parameter
+__device__ inline double concentration(Stream &g, double alpha, double n_clusters, double n_samples,
+                                       double shape, double rate)
+{
+    const double eta = g.beta(alpha + 1.0, n_samples);
+    double m_shape = shape + n_clusters - 1.0;
+    const double m_scale = rate - log(eta);
+    const double odds = (m_shape / m_scale) * (1.0 / n_samples);
+    if (g.bernoulli(odds / (1.0 + odds))) m_shape += 1.0;
+    return g.gamma(m_shape) / m_scale;
+}
+
+// dynamic smem: ints m[T*K*K], wover[T*K]; doubles S0[K*d], S1[K*d], R[K], mbar[K], newbeta[K],
+//               scal[16]
+__global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = p.T, n = p.n, d = p.d, K = p.K, KK = K * K;
+    const int c = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    int *m = reinterpret_cast<int *>(smem_raw);          // [T][K][K]
+    int *wov = m + T * KK;                               // [T][K] override counts (t >= 1)
+    double *S0 = reinterpret_cast<double *>(wov + T * K + ((T * KK + T * K) & 1));
+    double *S1 = S0 + K * d, *R = S1 + K * d, *mbar = R + K, *nbeta = mbar + K, *scal = nbeta + K;
+    const double *X = p.X + (size_t)c * T * n * d;
+    const int32_t *z = p.z + (size_t)c * T * n;
+    const double *cnt = p.ncount + (size_t)c * T * KK;
+    const int32_t *nk = p.nk + (size_t)c * T * K;
+    double *mu = p.mu + (size_t)c * K * d, *sigma = p.sigma + (size_t)c * K;
+    double *beta = p.beta + (size_t)c * K, *w = p.weights + (size_t)c * T * KK;
+    double *hy = p.hyper + (size_t)c * 8;
+    const uint32_t chain = (uint32_t)c + p.chain_offset;
+    const double gamma0 = hy[0], alpha_init = hy[1], alpha = hy[2], kappa = hy[3];
+    double mvp = hy[4], bpar = hy[5];
+    const double lm = p.lambda[c];
+    uint32_t site = 0; // families of streams get disjoint site ranges
+
+    // ---- 1. table counts m (sample_auxillary.py:6-28) ----
+    for (int cell = tid; cell < T * KK; cell += nt) {
+        const int t = cell / KK, j = (cell / K) % K, k = cell % K;
+        int mm = 0;
+        if (t > 0 || j == 0) {
+            const double pr = (t == 0) ? alpha_init * beta[k] : alpha * beta[k] + (j == k ? kappa : 0.0);
+            const int count = (int)cnt[cell];
+            Stream g(p.seed, site + cell, p.sweep, chain);
+            for (int i = 0; i < count; i++) mm += g.bernoulli(pr / (pr + i));
+        }
+        m[cell] = mm;
+    }
+    site += T * KK;
+    __syncthreads();
+    // ---- 2. override variables and m_bar (sample_auxillary.py:31-50) ----
+    const double rho0 = kappa / (alpha + kappa);
+    for (int e = tid; e < T * K; e += nt) {
+        const int t = e / K, j = e % K;
+        int wv = 0;
+        if (t > 0) {
+            Stream g(p.seed, site + e, p.sweep, chain);
+            wv = g.binomial(m[t * KK + j * K + j], rho0 / (rho0 + beta[j] * (1.0 - rho0)));
+        }
+        wov[e] = wv;
+    }
+    site += T * K;
+    __syncthreads();
+    for (int k = tid; k < K; k += nt) {
+        double s = m[k]; // m[0,0,k]
+        for (int t = 1; t < T; t++)
+            for (int j = 0; j < K; j++) s += m[t * KK + j * K + k] - (j == k ? wov[t * K + j] : 0);
+        mbar[k] = s;
+    }
+    __syncthreads();
+    // ---- 3. beta ~ Dir(gamma/K + m_bar) (hdp_lpcm.py:887) ----
+    for (int k = tid; k < K; k += nt) {
+        Stream g(p.seed, site + k, p.sweep, chain);
+        nbeta[k] = g.gamma(gamma0 / K + mbar[k]);
+    }
+    site += K;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int k = 0; k < K; k++) s += nbeta[k];
+        for (int k = 0; k < K; k++) nbeta[k] /= s;
+    }
+    __syncthreads();
+    // ---- 4. w0 and w[t,k] rows (hdp_lpcm.py:890-898), clipped Dirichlet parameters ----
+    for (int cell = tid; cell < T * KK; cell += nt) {
+        const int t = cell / KK, j = (cell / K) % K, k = cell % K;
+        if (t == 0 && j != 0) continue;
+        double a = (t == 0) ? alpha_init * nbeta[k] + nk[k]
+                            : alpha * nbeta[k] + (j == k ? kappa : 0.0) + cnt[cell];
+        if (a <= 0.0) a = 2.2250738585072014e-308;
+        Stream g(p.seed, site + cell, p.sweep, chain);
+        w[cell] = g.gamma(a);
+    }
+    site += T * KK;
+    __syncthreads();
+    for (int row = tid; row < T * K; row += nt) {
+        const int t = row / K, j = row % K;
+        if (t == 0 && j != 0) continue;
+        double s = 0.0;
+        for (int k = 0; k < K; k++) s += w[row * K + k];
+        for (int k = 0; k < K; k++) w[row * K + k] /= s;
+    }
+    // ---- 5. cluster means (hdp_lpcm.py:901-919) ----
+    for (int e = tid; e < 2 * K * d + K; e += nt) S0[e] = 0.0; // S0, S1, R are contiguous
+    __syncthreads();
+    for (int e = tid; e < T * n; e += nt) {
+        const int t = e / n, i = e % n, k = z[e];
+        const double *x = X + (size_t)e * d;
+        if (t == 0) {
+            for (int q = 0; q < d; q++) atomicAdd(&S0[k * d + q], x[q]);
+        } else {
+            const double *xp = X + ((size_t)(t - 1) * n + i) * d;
+            for (int q = 0; q < d; q++) atomicAdd(&S1[k * d + q], x[q] - (1.0 - lm) * xp[q]);
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += nt) {
+        double prec = 1.0 / mvp + nk[k] / sigma[k];
+        double nrest = 0.0;
+        for (int t = 1; t < T; t++) nrest += nk[t * K + k];
+        prec += (lm * lm / sigma[k]) * nrest;
+        const double var = 1.0 / prec, sd = sqrt(var);
+        Stream g(p.seed, site + k, p.sweep, chain);
+        for (int q = 0; q < d; q++) {
+            const double mean = ((1.0 / sigma[k]) * S0[k * d + q] + (lm / sigma[k]) * S1[k * d + q]) * var;
+            mu[k * d + q] = mean + sd * g.normal();
+        }
+    }
+    site += K;
+    __syncthreads();
+    // ---- 6. cluster variances (hdp_lpcm.py:922-937) ----
+    for (int e = tid; e < T * n; e += nt) {
+        const int t = e / n, i = e % n, k = z[e];
+        const double *x = X + (size_t)e * d;
+        double r2 = 0.0;
+        for (int q = 0; q < d; q++) {
+            double df = x[q] - ((t == 0) ? mu[k * d + q]
+                                         : (1.0 - lm) * X[((size_t)(t - 1) * n + i) * d + q] + lm * mu[k * d + q]);
+            r2 += df * df;
+        }
+        atomicAdd(&R[k], r2);
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += nt) {
+        double tot = 0.0;
+        for (int t = 0; t < T; t++) tot += nk[t * K + k];
+        const double shape = 0.5 * (tot * d + p.pr.a), rate = 0.5 * bpar + 0.5 * R[k];
+        Stream g(p.seed, site + k, p.sweep, chain);
+        sigma[k] = rate / g.gamma(shape);
+    }
+    site += K;
+    __syncthreads();
+    // ---- 7. lambda ~ truncated normal on (0,1) (hdp_lpcm.py:940-954) ----
+    if (tid < 2) scal[tid] = 0.0;
+    __syncthreads();
+    {
+        double ml = 0.0, sl = 0.0;
+        for (int e = n + tid; e < T * n; e += nt) { // t >= 1
+            const int t = e / n, i = e % n, k = z[e];
+            const double *x = X + (size_t)e * d, *xp = X + ((size_t)(t - 1) * n + i) * d;
+            for (int q = 0; q < d; q++) {
+                const double dm = mu[k * d + q] - xp[q];
+                ml += (dm / sigma[k]) * (x[q] - xp[q]);
+                sl += dm * dm / sigma[k];
+            }
+        }
+        ml = warp_sum(ml);
+        sl = warp_sum(sl);
+        if ((tid & 31) == 0) { atomicAdd(&scal[0], ml); atomicAdd(&scal[1], sl); }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        Stream g(p.seed, site, p.sweep, chain);
+        const double var = 1.0 / (1.0 / p.pr.lambda_variance_prior + scal[1]);
+        const double mean = (scal[0] + p.pr.lambda_prior / p.pr.lambda_variance_prior) * var;
+        const double sd = sqrt(var);
+        const double lo = normcdf((0.0 - mean) / sd), hi = normcdf((1.0 - mean) / sd);
+        double u = lo + (hi - lo) * g.uniform();
+        u = fmin(fmax(u, 1e-300), 1.0 - 1e-16);
+        double x = mean + sd * normcdfinv(u);
+        p.lambda[c] = fmin(fmax(x, 0.0), 1.0);
+        // ---- 8. hyper-priors (hdp_lpcm.py:957-972) ----
+        if (p.pr.resample_mvp) {
+            double bb = 0.5 * p.pr.b0;
+            for (int e = 0; e < K * d; e++) bb += 0.5 * mu[e] * mu[e];
+            mvp = bb / g.gamma(0.5 * (p.pr.a0 + K));
+        }
+        if (p.pr.resample_b) {
+            double sc = 0.5 * p.pr.d0;
+            for (int k = 0; k < K; k++) sc += 0.5 * (1.0 / sigma[k]);
+            bpar = g.gamma(0.5 * (p.pr.c0 + K * p.pr.a)) / sc;
+        }
+        // ---- 9. concentration parameters (hdp_lpcm.py:977-1023) ----
+        double ncl = 0.0, nsm = 0.0, m00 = 0.0;
+        for (int k = 0; k < K; k++) { ncl += mbar[k] > 0.0; nsm += mbar[k]; m00 += m[k]; }
+        const double new_gamma = concentration(g, gamma0, ncl, nsm, p.pr.gamma_prior_shape, p.pr.gamma_prior_rate);
+        const double new_ainit = concentration(g, alpha_init, m00, (double)n, p.pr.alpha_init_shape,
+                                               p.pr.alpha_init_rate);
+        double ak = alpha + kappa, s_sum = 0.0, logr = 0.0, m_valid = 0.0, m_all = 0.0, n_succ = 0.0;
+        for (int t = 1; t < T; t++)
+            for (int j = 0; j < K; j++) {
+                double nd = 0.0, mrow = 0.0;
+                for (int k = 0; k < K; k++) { nd += cnt[t * KK + j * K + k]; mrow += m[t * KK + j * K + k]; }
+                m_all += mrow;
+                n_succ += wov[t * K + j];
+                if (nd > 0.0) {
+                    s_sum += g.bernoulli(nd / (nd + ak));
+                    logr += log(g.beta(ak + 1.0, nd));
+                    m_valid += mrow;
+                }
+            }
+        ak = g.gamma(p.pr.alpha_kappa_shape + m_valid - s_sum) / (p.pr.alpha_kappa_rate - logr);
+        const double rho = g.beta(8.0 + n_succ, m_all - n_succ + 2.0);
+        hy[0] = new_gamma; hy[1] = new_ainit;
+        hy[3] = ak * rho; hy[2] = ak - ak * rho;
+        hy[4] = mvp; hy[5] = bpar;
+    }
+    for (int k = tid; k < K; k += nt) beta[k] = nbeta[k];
+}
+
+inline size_t hdp_smem_bytes(int T, int K, int d)
+{
+    const size_t ints = (size_t)T * K * K + (size_t)T * K;
+    return (ints + (ints & 1)) * sizeof(int) + ((size_t)2 * K * d + 3 * K + 16) * sizeof(double) + 16;
+}
+
+} // namespace dlsm

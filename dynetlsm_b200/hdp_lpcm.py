@@ -36,7 +36,7 @@ class DynamicNetworkHDPLPCM(object):
                  lambda_variance_prior=0.01, sigma_prior_std=4.0, mean_variance_prior_std=4.0,
                  step_size_X="auto", step_size_intercept=0.1, step_size_radii=175000,
                  n_control=None, n_resample_control=100, copy=True, random_state=None,
-                 sampler="device", device=0):
+                 sampler="device", n_chains=1, device=0):
         for k, v in list(locals().items()):
             if k != "self":
                 setattr(self, k, v)
@@ -124,16 +124,20 @@ class DynamicNetworkHDPLPCM(object):
         self.hyper_ = hp
 
         # ---- device state ----
-        drv = _Driver(Y, d, 1, self.is_directed, self.case_control_sampler_, K, self.tune,
+        C = 1 if replay else int(self.n_chains)
+        if replay and self.n_chains != 1:
+            raise ValueError("sampler='replay' reproduces one reference chain; use n_chains=1")
+        drv = _Driver(Y, d, C, self.is_directed, self.case_control_sampler_, K, self.tune,
                       self.tune_interval, (100, 100),   # hdp_lpcm.py:735-742: default interval
                       self.tune, self.device, replay, rng)   # hdp_lpcm.py:745-747: radii sampler tunes
         e = drv.engine
         self._engine = e
-        e.set(L.F_X, Xs[0][None])
-        ic = np.zeros((1, 2)); ic[0, :m] = ics[0]
+        tile = lambda a: np.tile(np.asarray(a)[None], (C,) + (1,) * np.ndim(a))
+        e.set(L.F_X, tile(Xs[0]))
+        ic = np.zeros((C, 2)); ic[:, :m] = ics[0]
         e.set(L.F_INTERCEPT, ic)
         if self.is_directed:
-            e.set(L.F_RADII, rads[0][None])
+            e.set(L.F_RADII, tile(rads[0]))
         e.set_hyper(intercept_prior=np.array(self.intercept_prior, dtype=np.float64),
                     intercept_variance_prior=self.intercept_variance_prior)
         e.set_tuner(self.step_size_X, self.step_size_intercept, self.step_size_radii)
@@ -143,42 +147,96 @@ class DynamicNetworkHDPLPCM(object):
             e.set(L.F_LAMBDA, lambdas[it]); e.set(L.F_WEIGHTS, weights[it][None])
             e.set(L.F_Z, zs[it][None])
 
-        def logp(it):
-            r = rads[it] if self.is_directed else None
-            lp = hdp_log_prior(hp, K, Xs[it], ics[it], self.intercept_prior,
-                               self.intercept_variance_prior, mus[it], sigmas[it], zs[it],
-                               weights[it], betas[it], lambdas[it], radii=r)
-            return float(np.ravel(e.loglik_full()[0] + lp)[0])
+        def log_post(ll, hpc, X, b, mu, sigma, z, w, beta, lmbda, r):
+            lp = hdp_log_prior(hpc, K, X, b, self.intercept_prior, self.intercept_variance_prior,
+                               mu, sigma, z, w, beta, lmbda, radii=r)
+            return float(np.ravel(ll + lp)[0])
 
         logps = np.zeros(S)
-        push_mixture(0)
-        logps[0] = logp(0)
+        if replay:
+            push_mixture(0)
+            logps[0] = log_post(e.loglik_full()[0], hp, Xs[0], ics[0], mus[0], sigmas[0], zs[0],
+                                weights[0], betas[0], lambdas[0], rads[0] if self.is_directed else None)
+            for it in range(1, S):
+                if self.case_control_sampler_ is not None:
+                    self.case_control_sampler_.resample()
+                    if self.case_control_sampler_.resampled_:
+                        drv.push_controls()
+                drv.sweep_latent()
+                e.center()
+                drv.sample_intercepts()
+                if self.is_directed:
+                    drv.sample_radii()
+                drv.sample_labels()
+                X = e.get(L.F_X)[0]
+                z = e.get(L.F_Z)[0].astype(np.int64)
+                cnt = e.get(L.F_NCOUNT)[0]
+                nk = e.get(L.F_NK)[0].astype(np.int64)
+                mu, sigma, w = mus[it - 1].copy(), sigmas[it - 1].copy(), weights[it - 1].copy()
+                beta, lmbda = conjugate_updates(rng, hp, X, z, cnt, nk, mu, sigma,
+                                                lambdas[it - 1].copy(), betas[it - 1].copy(), w)
+                Xs[it], zs[it], mus[it], sigmas[it] = X, z, mu, sigma
+                betas[it], weights[it], lambdas[it] = beta, w, lmbda
+                ics[it] = e.get(L.F_INTERCEPT)[0, :m]
+                if self.is_directed:
+                    rads[it] = e.get(L.F_RADII)[0]
+                push_mixture(it)
+                logps[it] = log_post(e.loglik_full()[0], hp, X, ics[it], mu, sigma, z, w, beta, lmbda,
+                                     rads[it] if self.is_directed else None)
+            chains = None
+        else:
+            # ---- device-resident chains: the conjugate block runs in k_hdp_update ----
+            import copy as _copy
+            e.set(L.F_MU, tile(mus[0])); e.set(L.F_SIGMA, tile(sigmas[0]))
+            e.set(L.F_LAMBDA, np.full(C, float(self.lambda_prior))); e.set(L.F_WEIGHTS, tile(weights[0]))
+            e.set(L.F_Z, tile(zs[0])); e.set(L.F_BETA, tile(betas[0]))
+            hy0 = np.array([hp.gamma, hp.alpha_init, hp.alpha, hp.kappa, hp.mean_variance_prior, hp.b, 0, 0],
+                           dtype=np.float64)
+            e.set(L.F_HYPER, tile(hy0))
+            e.set_hdp_prior(hp.a, hp.a0, hp.b0, hp.c0, hp.d0, hp.lambda_prior, hp.lambda_variance_prior,
+                            hp.gamma_prior_shape, hp.gamma_prior_rate, hp.alpha_init_shape,
+                            hp.alpha_init_rate, hp.alpha_kappa_shape, hp.alpha_kappa_rate,
+                            hp.resample_mean_variance, hp.resample_b)
+            chains = dict(intercepts=np.zeros((C, S, m)), lambdas=np.zeros((C, S)), logps=np.zeros((C, S)),
+                          n_clusters=np.zeros((C, S), dtype=np.int64), zs=np.zeros((C, S, T, n), np.int16))
+            chains["intercepts"][:, 0] = ics[0]; chains["lambdas"][:, 0] = self.lambda_prior
+            chains["zs"][:, 0] = zs[0]
 
-        for it in range(1, S):
-            if self.case_control_sampler_ is not None:
-                self.case_control_sampler_.resample()
-                if self.case_control_sampler_.resampled_:
-                    drv.push_controls()
-            drv.sweep_latent()
-            e.center()
-            drv.sample_intercepts()
-            if self.is_directed:
-                drv.sample_radii()
-            drv.sample_labels()
-            X = e.get(L.F_X)[0]
-            z = e.get(L.F_Z)[0].astype(np.int64)
-            cnt = e.get(L.F_NCOUNT)[0]
-            nk = e.get(L.F_NK)[0].astype(np.int64)
-            mu, sigma, w = mus[it - 1].copy(), sigmas[it - 1].copy(), weights[it - 1].copy()
-            beta, lmbda = conjugate_updates(rng, hp, X, z, cnt, nk, mu, sigma, lambdas[it - 1].copy(),
-                                            betas[it - 1].copy(), w)
-            Xs[it], zs[it], mus[it], sigmas[it] = X, z, mu, sigma
-            betas[it], weights[it], lambdas[it] = beta, w, lmbda
-            ics[it] = e.get(L.F_INTERCEPT)[0, :m]
-            if self.is_directed:
-                rads[it] = e.get(L.F_RADII)[0]
-            push_mixture(it)
-            logps[it] = logp(it)
+            def record(it):
+                Xa, za = e.get(L.F_X), e.get(L.F_Z)
+                mua, sga, lma = e.get(L.F_MU), e.get(L.F_SIGMA), e.get(L.F_LAMBDA)
+                bea, wa, hya = e.get(L.F_BETA), e.get(L.F_WEIGHTS), e.get(L.F_HYPER)
+                ica = e.get(L.F_INTERCEPT)[:, :m]
+                ra = e.get(L.F_RADII) if self.is_directed else None
+                ll = e.loglik_full()
+                for c in range(C):
+                    hpc = _copy.copy(hp)
+                    (hpc.gamma, hpc.alpha_init, hpc.alpha, hpc.kappa, hpc.mean_variance_prior,
+                     hpc.b) = hya[c, :6]
+                    lpc = log_post(ll[c], hpc, Xa[c], ica[c], mua[c], sga[c], za[c].astype(np.int64),
+                                   wa[c], bea[c], np.array([lma[c]]), None if ra is None else ra[c])
+                    chains["logps"][c, it] = lpc
+                    if c == 0:
+                        hp.__dict__.update(hpc.__dict__)
+                chains["intercepts"][:, it] = ica
+                chains["lambdas"][:, it] = lma
+                chains["zs"][:, it] = za
+                chains["n_clusters"][:, it] = [np.unique(za[c]).size for c in range(C)]
+                Xs[it], zs[it], mus[it], sigmas[it] = Xa[0], za[0], mua[0], sga[0]
+                betas[it], weights[it], lambdas[it], ics[it] = bea[0], wa[0], lma[0], ica[0]
+                if self.is_directed:
+                    rads[it] = ra[0]
+                logps[it] = chains["logps"][0, it]
+
+            record(0)
+            for it in range(1, S):
+                if self.case_control_sampler_ is not None:
+                    self.case_control_sampler_.resample()
+                    if self.case_control_sampler_.resampled_:
+                        drv.push_controls()
+                e.run_sweeps(1)   # latent -> centre -> intercepts -> [radii] -> labels -> HDP update
+                record(it)
+        self.chains_ = chains
 
         # mirror the reference's mutable hyper-parameter attributes
         self.gamma, self.alpha_init, self.alpha, self.kappa = hp.gamma, hp.alpha_init, hp.alpha, hp.kappa

@@ -185,10 +185,10 @@ def hdp_log_prior(hp, K, X, intercept, intercept_prior, intercept_variance_prior
     for t in range(1, T):
         for k in range(K):
             lp += _dirichlet_logpdf(weights[t, k], hp.alpha * beta + deltas[k])
-    for i in range(n_nodes):
-        lp += np.log(weights[0, 0, z[0, i]])
-        for t in range(1, T):
-            lp += np.log(weights[t, z[t - 1, i], z[t, i]])
+    # label Markov chains (hdp_lpcm.py:1208-1212), vectorised over nodes
+    lp += np.sum(np.log(weights[0, 0, z[0]]))
+    for t in range(1, T):
+        lp += np.sum(np.log(weights[t, z[t - 1], z[t]]))
     diff = intercept - intercept_prior
     if radii is not None:
         lp -= np.sum(0.5 * (diff * diff) / intercept_variance_prior)

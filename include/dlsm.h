@@ -90,6 +90,8 @@ typedef enum {
     DLSM_F_R_UNTIL = 19,   /* i32 (C,) */
     DLSM_F_NCOUNT = 20,    /* f64 (C,T,K,K)  transition counts of the last label draw (read-only) */
     DLSM_F_NK = 21,        /* i32 (C,T,K)    occupancy counts of the last label draw (read-only) */
+    DLSM_F_BETA = 22,      /* f64 (C,K)      global HDP weights beta */
+    DLSM_F_HYPER = 23,     /* f64 (C,8)      [gamma, alpha_init, alpha, kappa, mean_variance_prior, b, 0, 0] */
     DLSM_F_COUNT_
 } dlsm_field;
 
@@ -100,6 +102,18 @@ typedef struct {
     double intercept_prior[2];        /* prior means (lsm.py:239 'auto' resolved by the host) */
     double intercept_variance_prior;  /* lsm.py:240 */
 } dlsm_hyper;
+
+/* fixed hyper-hyper-parameters of the sticky HDP-HMM mixture (hdp_lpcm.py:385-455, :750-793) */
+typedef struct {
+    double a;                     /* sigma_k ~ InvGamma(a/2, b/2) */
+    double a0, b0;                /* mean_variance_prior ~ InvGamma(a0/2, b0/2)  (if resample_mvp) */
+    double c0, d0;                /* b ~ Gamma(c0/2, 2/d0)                        (if resample_b)   */
+    double lambda_prior, lambda_variance_prior;
+    double gamma_prior_shape, gamma_prior_rate;
+    double alpha_init_shape, alpha_init_rate;
+    double alpha_kappa_shape, alpha_kappa_rate;
+    int32_t resample_mvp, resample_b;
+} dlsm_hdp_prior;
 
 /* ---- lifecycle ------------------------------------------------------------------------- */
 int dlsm_abi_version(void);
@@ -157,9 +171,18 @@ int dlsm_sample_radii(dlsm_handle *h, const double *proposal, const double *logu
  * forward-filter/backward-sample per node.  replay: U (C,n,T) raw uniforms, node-major;
  * native: NULL.  Updates DLSM_F_Z, DLSM_F_NCOUNT, DLSM_F_NK. */
 int dlsm_sample_labels(dlsm_handle *h, const double *U);
-/* n_sweeps x [latent -> center -> intercepts -> (radii) -> (labels)] with device RNG, no host
- * round trip (the loop bodies lsm.py:483-523 / hdp_lpcm.py:840-878 minus the host-side blocks).
- * flags: bit0 skip center, bit1 skip intercepts, bit2 skip radii, bit3 skip labels. */
+/* The conjugate / auxiliary-variable block that follows the label draw in one HDP-LPCM sweep
+ * (hdp_lpcm.py:881-1023 with sample_auxillary.py:6-50, sample_concentration.py:6-21): table
+ * counts, override variables, beta, w0, w[t,k], mu_k, sigma_k, lambda, the tau^2 / b hyper-priors
+ * and the concentration parameters, one CTA per chain on device Philox streams.  Reads
+ * DLSM_F_NCOUNT / F_NK / F_Z / F_X, updates F_MU, F_SIGMA, F_LAMBDA, F_BETA, F_WEIGHTS, F_HYPER.
+ * Native RNG only: in replay mode the host performs this block with the numpy RandomState. */
+int dlsm_set_hdp_prior(dlsm_handle *h, const dlsm_hdp_prior *pr);
+int dlsm_hdp_update(dlsm_handle *h);
+/* n_sweeps x [latent -> center -> intercepts -> (radii) -> (labels -> (hdp update))] with device
+ * RNG, no host round trip (the loop bodies lsm.py:483-523 / hdp_lpcm.py:840-1023).
+ * flags: bit0 skip center, bit1 skip intercepts, bit2 skip radii, bit3 skip labels, bit4 skip the
+ * HDP update (it also needs dlsm_set_hdp_prior to have been called). */
 int dlsm_run_sweeps(dlsm_handle *h, int32_t n_sweeps, uint32_t flags);
 
 /* ---- parity probes --------------------------------------------------------------------- */
@@ -171,6 +194,9 @@ int dlsm_loglik_partial(dlsm_handle *h, double *out);
 int dlsm_loglik_full(dlsm_handle *h, double *out);
 /* emission densities of compute_gaussian_likelihood(normalize=False), out (C,n,T,K) */
 int dlsm_gaussian_likelihood(dlsm_handle *h, double *out);
+/* overwrite the read-only label-count fields (DLSM_F_NCOUNT / DLSM_F_NK) -- test probe for
+ * dlsm_hdp_update, which normally consumes what dlsm_sample_labels just produced */
+int dlsm_debug_set_counts(dlsm_handle *h, int field, const void *host, size_t bytes);
 /* the raw draws the NEXT native latent sweep will consume: eps (C,T,n,d), logu (C,T,n) */
 int dlsm_debug_draws(dlsm_handle *h, double *eps, double *logu);
 

@@ -1,0 +1,148 @@
+"""The device conjugate / auxiliary-variable block (k_hdp_update; reference hdp_lpcm.py:881-1023)
+against the host restatement that the bit-exact replay mode uses (dynetlsm_b200/hdp_updates.py,
+itself pinned on the reference chain by test_gpu_estimators.py).  The two use different random
+number generators, so the comparison is distributional: thousands of independent device chains
+from one state vs thousands of host replicates, every output within Monte-Carlo error."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _state(seed=0, T=4, n=60, d=2, K=5):
+    rng = np.random.RandomState(seed)
+    mu = rng.randn(K, d) * 1.5
+    z = np.empty((T, n), np.int64)
+    z[0] = rng.randint(0, K - 1, n)          # leave one component empty
+    for t in range(1, T):
+        z[t] = np.where(rng.rand(n) < 0.2, rng.randint(0, K - 1, n), z[t - 1])
+    X = np.empty((T, n, d))
+    X[0] = mu[z[0]] + 0.5 * rng.randn(n, d)
+    for t in range(1, T):
+        X[t] = 0.8 * mu[z[t]] + 0.2 * X[t - 1] + 0.4 * rng.randn(n, d)
+    cnt = np.zeros((T, K, K))
+    nk = np.zeros((T, K), np.int64)
+    for i in range(n):
+        cnt[0, 0, z[0, i]] += 1
+        nk[0, z[0, i]] += 1
+        for t in range(1, T):
+            cnt[t, z[t - 1, i], z[t, i]] += 1
+            nk[t, z[t, i]] += 1
+    sigma = rng.gamma(3, 0.2, K)
+    beta = rng.dirichlet(np.ones(K) * 2)
+    w = rng.dirichlet(np.ones(K), size=(T, K))
+    return X, z, cnt, nk, mu, sigma, 0.75, beta, w
+
+
+def _hyper():
+    from dynetlsm_b200.hdp_updates import HDPHyper
+    mvp, a = 2.0, 2.0
+    a0 = (4.0 ** 2 + 2) * 2
+    b0 = (a0 - 2) * mvp * 2
+    b_ = (a + 2) * mvp
+    d0 = (4.0 ** 2 / b_) * 2
+    c0 = b_ * d0
+    return HDPHyper(1.0, 1.0, 1.0, 4.0, mvp, b_, a, a0, b0, c0, d0, 0.9, 0.01, 1.0, 0.1, 1.0, 1.0,
+                    5, 0.1, True, True)
+
+
+def test_device_hdp_update_matches_host_in_distribution():
+    import copy
+    from dynetlsm_b200 import _lib as L
+    from dynetlsm_b200.hdp_updates import conjugate_updates
+    X, z, cnt, nk, mu, sigma, lm, beta, w = _state()
+    T, n, d = X.shape
+    K = sigma.size
+    hp0 = _hyper()
+    C_ = 4096
+    e = L.Engine(T=T, n=n, d=d, n_chains=C_, K=K, mixture=True)
+    tile = lambda a: np.tile(np.asarray(a)[None], (C_,) + (1,) * np.ndim(a))
+    e.set(L.F_X, tile(X)); e.set(L.F_Z, tile(z)); e.set(L.F_MU, tile(mu)); e.set(L.F_SIGMA, tile(sigma))
+    e.set(L.F_LAMBDA, np.full(C_, lm)); e.set(L.F_BETA, tile(beta)); e.set(L.F_WEIGHTS, tile(w))
+    hy = np.array([hp0.gamma, hp0.alpha_init, hp0.alpha, hp0.kappa, hp0.mean_variance_prior, hp0.b, 0, 0])
+    e.set(L.F_HYPER, tile(hy))
+    e.set_hdp_prior(hp0.a, hp0.a0, hp0.b0, hp0.c0, hp0.d0, hp0.lambda_prior, hp0.lambda_variance_prior,
+                    hp0.gamma_prior_shape, hp0.gamma_prior_rate, hp0.alpha_init_shape, hp0.alpha_init_rate,
+                    hp0.alpha_kappa_shape, hp0.alpha_kappa_rate, True, True)
+    # the label counts normally come from the label kernel: put them there by sampling labels with
+    # degenerate weights?  simpler: the probe path -- the fields are device buffers the kernel reads
+    e.L.dlsm_set_state  # (counts are read-only through the API; fill them through a label draw)
+    # run the label kernel with weights/emissions that reproduce z exactly: w rows = one-hot of z is
+    # not expressible per node, so instead overwrite via the private test hook below
+    _force_counts(e, L, cnt, nk)
+    e.set_rng(7)
+    e.hdp_update()
+    dev = dict(beta=e.get(L.F_BETA), w=e.get(L.F_WEIGHTS), mu=e.get(L.F_MU), sigma=e.get(L.F_SIGMA),
+               lam=e.get(L.F_LAMBDA)[:, None], hyper=e.get(L.F_HYPER)[:, :6])
+    R = 1500
+    host = dict(beta=[], w=[], mu=[], sigma=[], lam=[], hyper=[])
+    for r in range(R):
+        rng = np.random.RandomState(1000 + r)
+        hp = copy.copy(hp0)
+        mu_r, sg_r, w_r = mu.copy(), sigma.copy(), w.copy()
+        b_r, l_r = conjugate_updates(rng, hp, X, z, cnt, nk, mu_r, sg_r, np.array([lm]), beta.copy(), w_r)
+        host["beta"].append(b_r); host["w"].append(w_r); host["mu"].append(mu_r); host["sigma"].append(sg_r)
+        host["lam"].append(l_r)
+        host["hyper"].append([hp.gamma, hp.alpha_init, hp.alpha, hp.kappa,
+                              float(np.ravel(hp.mean_variance_prior)[0]), hp.b])
+    worst = 0.0
+    for key in dev:
+        a = dev[key].reshape(C_, -1)
+        b = np.asarray(host[key], dtype=np.float64).reshape(R, -1)
+        keep = np.ones(a.shape[1], bool)
+        if key == "w":                      # rows (t = 0, j != 0) are not part of the model
+            keep = np.ones((T, K, K), bool); keep[0, 1:] = False; keep = keep.ravel()
+        a, b = a[:, keep], b[:, keep]
+        se = np.sqrt(a.var(axis=0) / C_ + b.var(axis=0) / R) + 1e-12
+        zscore = np.abs(a.mean(axis=0) - b.mean(axis=0)) / se
+        worst = max(worst, float(zscore.max()))
+        assert zscore.max() < 5.5, (key, zscore.max(), a.mean(axis=0)[:4], b.mean(axis=0)[:4])
+        # shape of the distribution: split at the pooled median (robust for the very skewed
+        # Dirichlet entries with tiny parameters), and the spread where the skewness is moderate
+        med = np.median(np.concatenate([a, b]), axis=0)
+        fa, fb = (a < med).mean(axis=0), (b < med).mean(axis=0)
+        assert np.all(np.abs(fa - fb) < 5.5 * np.sqrt(0.25 / C_ + 0.25 / R)), (key, np.abs(fa - fb).max())
+        sd = b.std(axis=0)
+        skew = np.abs(((b - b.mean(axis=0)) ** 3).mean(axis=0)) / np.maximum(sd, 1e-300) ** 3
+        ok = (sd > 1e-6) & (skew < 1.5)
+        ratio = a.std(axis=0)[ok] / sd[ok]
+        assert ok.sum() > 0 and np.all((ratio > 0.85) & (ratio < 1.18)), (key, ratio.min(), ratio.max())
+    assert np.allclose(dev["beta"].sum(axis=1), 1.0) and np.all(dev["sigma"] > 0)
+    assert np.all((dev["lam"] >= 0) & (dev["lam"] <= 1))
+
+
+def _force_counts(e, L, cnt, nk):
+    """Drive the label kernel so that it produces exactly the wanted labels: emissions that put all
+    mass on the wanted component need per-node parameters, which the model does not have; the
+    counts are therefore produced by sampling labels from a degenerate chain built per time step."""
+    # Build the counts by an actual label draw: set mu far apart and X on the component means so
+    # the emission is effectively one-hot at the wanted label, with uniform weights.
+    T, K = nk.shape
+    C_, n, d = e.C, e.n, e.d
+    z = np.zeros((T, n), np.int64)
+    # reconstruct a label path with these counts is unnecessary: use the test-only state setter
+    import ctypes as C
+    for field, arr in ((L.F_NCOUNT, np.ascontiguousarray(np.tile(cnt[None], (C_, 1, 1, 1)))),
+                       (L.F_NK, np.ascontiguousarray(np.tile(nk[None].astype(np.int32), (C_, 1, 1))))):
+        rc = e.L.dlsm_debug_set_counts(e.h, field, arr.ctypes.data_as(C.c_void_p), arr.nbytes)
+        assert rc == 0
+
+
+def test_hdp_estimator_device_mode_multichain():
+    from dynetlsm_b200 import DynamicNetworkHDPLPCM
+    from test_gpu_estimators import _splitting_network
+    Y = _splitting_network(n=40, T=3)
+    m = DynamicNetworkHDPLPCM(n_iter=150, burn=100, tune=100, n_components=6, random_state=5,
+                              n_chains=4).fit(Y)
+    assert m.X_.shape == (3, 40, 2) and m.zs_.shape == (350, 3, 40)
+    ch = m.chains_
+    assert ch["logps"].shape == (4, 350) and np.isfinite(ch["logps"]).all()
+    assert not np.array_equal(ch["lambdas"][0], ch["lambdas"][1])      # chains are independent
+    assert np.all((ch["lambdas"][:, 1:] > 0) & (ch["lambdas"][:, 1:] < 1))
+    assert np.all(m.sigmas_[1:] > 0) and np.allclose(m.betas_[1:].sum(axis=1), 1.0)
+    assert np.allclose(m.weights_[5:, 1:].sum(axis=-1), 1.0)
+    # the two planted communities are recovered by the co-clustering matrix at t = 0
+    truth = np.random.RandomState(42).randint(0, 2, 40)
+    same = truth[:, None] == truth[None, :]
+    co = m.cooccurrence_probas_[0]
+    assert co[same].mean() > co[~same].mean() + 0.2
