@@ -27,7 +27,8 @@ WORKLOADS = {
     # name: T, n, d, K, directed, case_control, default chains per GPU, description
     "cfg1": dict(T=3, n=18, d=2, K=0, directed=False, chains=1184,
                  desc="DynamicNetworkLSM, Sampson-monks shape (T=3, n=18, d=2)"),
-    "cfg2": dict(T=9, n=120, d=2, K=10, directed=False, chains=1184,
+    # 1332 = 148 SMs x 3 resident CTAs x 3 waves of the sweep kernel
+    "cfg2": dict(T=9, n=120, d=2, K=10, directed=False, chains=1332,
                  desc="DynamicNetworkHDPLPCM, community-splitting network (n=120, T=9, d=2, K=10)"),
     "cfg3": dict(T=20, n=2000, d=2, K=0, directed=True, chains=1,
                  desc="directed DynamicNetworkLSM with radii (n=2000, T=20, d=2), single chain"),

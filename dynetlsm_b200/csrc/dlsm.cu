@@ -26,6 +26,8 @@ struct dlsm_handle {
     int lk;                 // Lik
     int W;                  // words per adjacency row
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t side_stream = nullptr;          // label FFBS + HDP update overlap the intercept MH
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     // network
     uint32_t *rowbits = nullptr, *colbits = nullptr;
@@ -49,6 +51,7 @@ struct dlsm_handle {
     int full_tiles = 1, full_nblk = 1;
     int *d_progress = nullptr;      // [C][T] wavefront flags of the CTA-per-slice sweep
     unsigned int *d_ticket = nullptr;
+    double *d_hdp_scratch = nullptr; // [C][2*K*d + K]
     int sweep_mode = 0;             // 0 auto, 1 CTA per chain, 2 CTA per (chain, slice)
     // rng
     uint64_t seed = 0, chain_offset = 0;
@@ -443,6 +446,14 @@ int dlsm_create(const dlsm_config *cfg, dlsm_handle **out)
     if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return fail("cudaStreamCreate", e);
     h->stream = h->own_stream;
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if ((e = cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, hi)) != cudaSuccess)
+            return fail("cudaStreamCreate(side)", e);
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    }
     for (int f = 0; f < DLSM_F_COUNT_; f++) {
         const size_t bytes = field_elems(*cfg, f) * elem_size(f);
         h->field_bytes[f] = bytes;
@@ -488,8 +499,11 @@ void dlsm_destroy(dlsm_handle *h)
     void *ptrs[] = {h->rowbits, h->colbits, h->deg, h->in_edges, h->out_edges, h->ctrl_in,
                     h->ctrl_out, h->rinv, h->d_eps, h->d_logu, h->d_ratio, h->d_out, h->d_acc,
                     h->d_partial, h->d_bvar, h->d_prop, h->d_ll2, h->d_rprop, h->d_rprop_inv,
-                    h->d_small, h->d_small_i, h->d_flags, h->d_bad, h->d_progress, h->d_ticket};
+                    h->d_small, h->d_small_i, h->d_flags, h->d_bad, h->d_progress, h->d_ticket, h->d_hdp_scratch};
     for (void *p : ptrs) cudaFree(p);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -824,7 +838,7 @@ static int labels_async(dlsm_handle *h, const double *d_U, double *lik_out, int 
     }
     // thread-per-node kernel when its [T*K + 2K][TPB] shared-memory stage fits, else warp-per-node
     const size_t per_thread = ((size_t)c.T * c.K + 2 * c.K) * sizeof(double);
-    const size_t extra = (size_t)c.K * (c.d + 2) * sizeof(double);
+    const size_t extra = ((size_t)c.K * (c.d + 2) + (size_t)c.K * c.K) * sizeof(double);
     int rc;
     begin_phase(h, 1);
     if (per_thread * 64 + extra <= kMaxSmem / 2) {
@@ -880,6 +894,10 @@ static int hdp_update_async(dlsm_handle *h)
     p.lambda = F<double>(h, DLSM_F_LAMBDA); p.beta = F<double>(h, DLSM_F_BETA);
     p.weights = F<double>(h, DLSM_F_WEIGHTS); p.hyper = F<double>(h, DLSM_F_HYPER);
     p.pr = h->hdp_prior;
+    const size_t sbytes = (size_t)c.n_chains * (2 * c.K * c.d + c.K) * sizeof(double);
+    if (!h->d_hdp_scratch) CU(h, cudaMalloc((void **)&h->d_hdp_scratch, sbytes));
+    CU(h, cudaMemsetAsync(h->d_hdp_scratch, 0, sbytes, h->stream));
+    p.scratch = h->d_hdp_scratch;
     p.seed = h->seed; p.sweep = h->sweep_idx[4]; p.chain_offset = (uint32_t)h->chain_offset;
     const size_t smem = hdp_smem_bytes(c.T, c.K, c.d);
     if (smem > kMaxSmem) FAIL(h, DLSM_ERR_UNSUPPORTED, "T*K*K too large for the HDP update kernel");
@@ -922,14 +940,29 @@ int dlsm_run_sweeps(dlsm_handle *h, int32_t n_sweeps, uint32_t flags)
         if ((rc = launch_sweep(h, p)) != DLSM_OK) return rc;
         h->sweep_idx[kRngLatent] += 1;
         if (!(flags & 1u) && (rc = center_async(h)) != DLSM_OK) return rc;
+        // After centring, the label block (FFBS -> HDP update; latency-bound, few warps per SM)
+        // and the intercept / radii MH (full-network kernel; issue-bound) are independent: run
+        // the label block on a high-priority side stream so the two overlap.
+        const bool labels = h->cfg.prior == DLSM_PRIOR_MIXTURE && !(flags & 8u);
+        cudaStream_t main_stream = h->stream;
+        if (labels) {
+            CU(h, cudaEventRecord(h->ev_fork, main_stream));
+            CU(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+            h->stream = h->side_stream;
+            const bool timing = h->timing;
+            h->timing = false; // phase events belong to the main stream
+            rc = labels_async(h, nullptr, nullptr, 1);
+            if (rc == DLSM_OK && h->have_hdp_prior && !(flags & 16u)) rc = hdp_update_async(h);
+            h->timing = timing;
+            h->stream = main_stream;
+            if (rc != DLSM_OK) return rc;
+            CU(h, cudaEventRecord(h->ev_join, h->side_stream));
+        }
         if (!(flags & 2u) && (rc = intercepts_async(h, nullptr, nullptr, nullptr, nullptr)) != DLSM_OK) return rc;
         if (h->cfg.is_directed && !(flags & 4u) &&
             (rc = radii_async(h, true, nullptr, nullptr, nullptr)) != DLSM_OK)
             return rc;
-        if (h->cfg.prior == DLSM_PRIOR_MIXTURE && !(flags & 8u)) {
-            if ((rc = labels_async(h, nullptr, nullptr, 1)) != DLSM_OK) return rc;
-            if (h->have_hdp_prior && !(flags & 16u) && (rc = hdp_update_async(h)) != DLSM_OK) return rc;
-        }
+        if (labels) CU(h, cudaStreamWaitEvent(main_stream, h->ev_join, 0));
     }
     return check_flags(h);
 }

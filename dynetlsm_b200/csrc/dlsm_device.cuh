@@ -34,6 +34,7 @@ __host__ __device__ inline void philox_round(uint32_t &c0, uint32_t &c1, uint32_
 }
 
 struct U2 { double a, b; };
+struct W4 { uint32_t x, y, z, w; };
 
 __host__ __device__ inline U2 philox_u2(uint64_t seed, uint32_t site, uint32_t sweep,
                                         uint32_t chain, uint32_t kind, uint32_t block)
@@ -51,6 +52,23 @@ __host__ __device__ inline U2 philox_u2(uint64_t seed, uint32_t site, uint32_t s
     u.a = ((double)(((uint64_t)c0 << 20) | (c1 >> 12)) + 0.5) * s;
     u.b = ((double)(((uint64_t)c2 << 20) | (c3 >> 12)) + 0.5) * s;
     return u;
+}
+
+// raw 4 x 32 bits of one Philox block (cheap Bernoulli trials: 32-bit resolution is plenty)
+__host__ __device__ inline W4 philox_w4(uint64_t seed, uint32_t site, uint32_t sweep, uint32_t chain,
+                                        uint32_t kind, uint32_t block)
+{
+    uint32_t c0 = site, c1 = sweep, c2 = chain, c3 = (kind << 24) | (block & 0xffffffu);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    W4 o;
+    o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
 }
 
 // Box-Muller pair from two uniforms in (0,1)

@@ -58,7 +58,21 @@ struct Stream {
         const double x = gamma(a), y = gamma(b);
         return x / (x + y);
     }
-    __device__ int bernoulli(double p) { return uniform() < p ? 1 : 0; }
+    // Bernoulli trials draw 32-bit uniforms, four per Philox block (blocks tagged in the high
+    // half of the counter range so they never collide with the 52-bit draws of this stream)
+    uint32_t w4[4];
+    int nw = 0;
+    uint32_t blk32 = 0;
+    __device__ int bernoulli(double p)
+    {
+        if (nw == 0) {
+            const W4 o = philox_w4(seed, site, sweep, chain, kRngHdp, 0x800000u | blk32++);
+            w4[0] = o.x; w4[1] = o.y; w4[2] = o.z; w4[3] = o.w;
+            nw = 4;
+        }
+        const uint32_t r = w4[--nw];
+        return ((double)r + 0.5) * 2.3283064365386963e-10 < p ? 1 : 0;
+    }
     __device__ int binomial(int n, double p)
     {
         int s = 0;
@@ -74,6 +88,7 @@ struct HdpParams {
     const double *ncount;   // [C][T][K][K]
     const int32_t *nk;      // [C][T][K]
     double *mu, *sigma, *lambda, *beta, *weights, *hyper;
+    double *scratch;        // [C][2*K*d + K] zeroed before the launch: S0 | S1 | R (global fp64 RED)
     dlsm_hdp_prior pr;
     uint64_t seed;
     uint32_t sweep, chain_offset;
@@ -91,8 +106,7 @@ __device__ inline double concentration(Stream &g, double alpha, double n_cluster
     return g.gamma(m_shape) / m_scale;
 }
 
-// dynamic smem: ints m[T*K*K], wover[T*K]; doubles S0[K*d], S1[K*d], R[K], mbar[K], newbeta[K],
-//               scal[16]
+// dynamic smem: ints m[T*K*K], wover[T*K]; doubles mbar[K], newbeta[K], scal[16]
 __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -100,8 +114,9 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
     const int c = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     int *m = reinterpret_cast<int *>(smem_raw);          // [T][K][K]
     int *wov = m + T * KK;                               // [T][K] override counts (t >= 1)
-    double *S0 = reinterpret_cast<double *>(wov + T * K + ((T * KK + T * K) & 1));
-    double *S1 = S0 + K * d, *R = S1 + K * d, *mbar = R + K, *nbeta = mbar + K, *scal = nbeta + K;
+    double *mbar = reinterpret_cast<double *>(wov + T * K + ((T * KK + T * K) & 1));
+    double *nbeta = mbar + K, *scal = nbeta + K;
+    double *S0 = p.scratch + (size_t)c * (2 * K * d + K), *S1 = S0 + K * d, *R = S1 + K * d;
     const double *X = p.X + (size_t)c * T * n * d;
     const int32_t *z = p.z + (size_t)c * T * n;
     const double *cnt = p.ncount + (size_t)c * T * KK;
@@ -111,7 +126,7 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
     double *hy = p.hyper + (size_t)c * 8;
     const uint32_t chain = (uint32_t)c + p.chain_offset;
     const double gamma0 = hy[0], alpha_init = hy[1], alpha = hy[2], kappa = hy[3];
-    double mvp = hy[4], bpar = hy[5];
+    const double mvp = hy[4], bpar = hy[5];
     const double lm = p.lambda[c];
     uint32_t site = 0; // families of streams get disjoint site ranges
 
@@ -182,8 +197,8 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
         for (int k = 0; k < K; k++) w[row * K + k] /= s;
     }
     // ---- 5. cluster means (hdp_lpcm.py:901-919) ----
-    for (int e = tid; e < 2 * K * d + K; e += nt) S0[e] = 0.0; // S0, S1, R are contiguous
-    __syncthreads();
+    // per-cluster sums: one pass, native fp64 RED.ADD into a zeroed global scratch (shared-memory
+    // fp64 atomics are CAS loops and K hot addresses under 128 threads is a CAS storm)
     for (int e = tid; e < T * n; e += nt) {
         const int t = e / n, i = e % n, k = z[e];
         const double *x = X + (size_t)e * d;
@@ -194,6 +209,7 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
             for (int q = 0; q < d; q++) atomicAdd(&S1[k * d + q], x[q] - (1.0 - lm) * xp[q]);
         }
     }
+    __threadfence();
     __syncthreads();
     for (int k = tid; k < K; k += nt) {
         double prec = 1.0 / mvp + nk[k] / sigma[k];
@@ -203,7 +219,8 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
         const double var = 1.0 / prec, sd = sqrt(var);
         Stream g(p.seed, site + k, p.sweep, chain);
         for (int q = 0; q < d; q++) {
-            const double mean = ((1.0 / sigma[k]) * S0[k * d + q] + (lm / sigma[k]) * S1[k * d + q]) * var;
+            const double mean = ((1.0 / sigma[k]) * __ldcg(&S0[k * d + q]) +
+                                 (lm / sigma[k]) * __ldcg(&S1[k * d + q])) * var;
             mu[k * d + q] = mean + sd * g.normal();
         }
     }
@@ -215,24 +232,28 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
         const double *x = X + (size_t)e * d;
         double r2 = 0.0;
         for (int q = 0; q < d; q++) {
-            double df = x[q] - ((t == 0) ? mu[k * d + q]
-                                         : (1.0 - lm) * X[((size_t)(t - 1) * n + i) * d + q] + lm * mu[k * d + q]);
+            const double df = x[q] - ((t == 0) ? mu[k * d + q]
+                                               : (1.0 - lm) * X[((size_t)(t - 1) * n + i) * d + q] +
+                                                     lm * mu[k * d + q]);
             r2 += df * df;
         }
         atomicAdd(&R[k], r2);
     }
+    __threadfence();
     __syncthreads();
     for (int k = tid; k < K; k += nt) {
         double tot = 0.0;
         for (int t = 0; t < T; t++) tot += nk[t * K + k];
-        const double shape = 0.5 * (tot * d + p.pr.a), rate = 0.5 * bpar + 0.5 * R[k];
+        const double shape = 0.5 * (tot * d + p.pr.a), rate = 0.5 * bpar + 0.5 * __ldcg(&R[k]);
         Stream g(p.seed, site + k, p.sweep, chain);
         sigma[k] = rate / g.gamma(shape);
     }
     site += K;
     __syncthreads();
-    // ---- 7. lambda ~ truncated normal on (0,1) (hdp_lpcm.py:940-954) ----
-    if (tid < 2) scal[tid] = 0.0;
+    // ---- 7-9. lambda, hyper-priors, concentration parameters: sums in parallel, then one scalar
+    //           task per thread (each on its own Philox stream) so no thread runs a long serial
+    //           chain of gamma rejection loops ----
+    if (tid < 16) scal[tid] = 0.0;
     __syncthreads();
     {
         double ml = 0.0, sl = 0.0;
@@ -249,52 +270,62 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
         sl = warp_sum(sl);
         if ((tid & 31) == 0) { atomicAdd(&scal[0], ml); atomicAdd(&scal[1], sl); }
     }
+    // alpha + kappa auxiliary variables, one (t >= 1, j) row per thread (hdp_lpcm.py:998-1012)
+    const double ak_old = alpha + kappa;
+    for (int row = K + tid; row < T * K; row += nt) {
+        double nd = 0.0, mrow = 0.0;
+        for (int k = 0; k < K; k++) { nd += cnt[row * K + k]; mrow += m[row * K + k]; }
+        atomicAdd(&scal[5], mrow);                  // sum of m[1:]
+        atomicAdd(&scal[6], (double)wov[row]);      // override successes
+        if (nd > 0.0) {
+            Stream g(p.seed, site + row, p.sweep, chain);
+            atomicAdd(&scal[2], (double)g.bernoulli(nd / (nd + ak_old)));
+            atomicAdd(&scal[3], log(g.beta(ak_old + 1.0, nd)));
+            atomicAdd(&scal[4], mrow);
+        }
+    }
+    site += T * K;
     __syncthreads();
-    if (tid == 0) {
-        Stream g(p.seed, site, p.sweep, chain);
+    if (tid == 0) { // lambda ~ truncated normal on (0, 1) (hdp_lpcm.py:940-954), inverse-cdf draw
+        Stream g(p.seed, site + 0, p.sweep, chain);
         const double var = 1.0 / (1.0 / p.pr.lambda_variance_prior + scal[1]);
         const double mean = (scal[0] + p.pr.lambda_prior / p.pr.lambda_variance_prior) * var;
         const double sd = sqrt(var);
         const double lo = normcdf((0.0 - mean) / sd), hi = normcdf((1.0 - mean) / sd);
         double u = lo + (hi - lo) * g.uniform();
         u = fmin(fmax(u, 1e-300), 1.0 - 1e-16);
-        double x = mean + sd * normcdfinv(u);
-        p.lambda[c] = fmin(fmax(x, 0.0), 1.0);
-        // ---- 8. hyper-priors (hdp_lpcm.py:957-972) ----
+        p.lambda[c] = fmin(fmax(mean + sd * normcdfinv(u), 0.0), 1.0);
+    } else if (tid == 1) { // tau^2 hyper-prior (hdp_lpcm.py:957-962)
         if (p.pr.resample_mvp) {
+            Stream g(p.seed, site + 1, p.sweep, chain);
             double bb = 0.5 * p.pr.b0;
             for (int e = 0; e < K * d; e++) bb += 0.5 * mu[e] * mu[e];
-            mvp = bb / g.gamma(0.5 * (p.pr.a0 + K));
+            hy[4] = bb / g.gamma(0.5 * (p.pr.a0 + K));
         }
+    } else if (tid == 2) { // b hyper-prior (:965-972)
         if (p.pr.resample_b) {
+            Stream g(p.seed, site + 2, p.sweep, chain);
             double sc = 0.5 * p.pr.d0;
             for (int k = 0; k < K; k++) sc += 0.5 * (1.0 / sigma[k]);
-            bpar = g.gamma(0.5 * (p.pr.c0 + K * p.pr.a)) / sc;
+            hy[5] = g.gamma(0.5 * (p.pr.c0 + K * p.pr.a)) / sc;
         }
-        // ---- 9. concentration parameters (hdp_lpcm.py:977-1023) ----
-        double ncl = 0.0, nsm = 0.0, m00 = 0.0;
-        for (int k = 0; k < K; k++) { ncl += mbar[k] > 0.0; nsm += mbar[k]; m00 += m[k]; }
-        const double new_gamma = concentration(g, gamma0, ncl, nsm, p.pr.gamma_prior_shape, p.pr.gamma_prior_rate);
-        const double new_ainit = concentration(g, alpha_init, m00, (double)n, p.pr.alpha_init_shape,
-                                               p.pr.alpha_init_rate);
-        double ak = alpha + kappa, s_sum = 0.0, logr = 0.0, m_valid = 0.0, m_all = 0.0, n_succ = 0.0;
-        for (int t = 1; t < T; t++)
-            for (int j = 0; j < K; j++) {
-                double nd = 0.0, mrow = 0.0;
-                for (int k = 0; k < K; k++) { nd += cnt[t * KK + j * K + k]; mrow += m[t * KK + j * K + k]; }
-                m_all += mrow;
-                n_succ += wov[t * K + j];
-                if (nd > 0.0) {
-                    s_sum += g.bernoulli(nd / (nd + ak));
-                    logr += log(g.beta(ak + 1.0, nd));
-                    m_valid += mrow;
-                }
-            }
-        ak = g.gamma(p.pr.alpha_kappa_shape + m_valid - s_sum) / (p.pr.alpha_kappa_rate - logr);
-        const double rho = g.beta(8.0 + n_succ, m_all - n_succ + 2.0);
-        hy[0] = new_gamma; hy[1] = new_ainit;
-        hy[3] = ak * rho; hy[2] = ak - ak * rho;
-        hy[4] = mvp; hy[5] = bpar;
+    } else if (tid == 3) { // gamma (:977-983)
+        Stream g(p.seed, site + 3, p.sweep, chain);
+        double ncl = 0.0, nsm = 0.0;
+        for (int k = 0; k < K; k++) { ncl += mbar[k] > 0.0; nsm += mbar[k]; }
+        hy[0] = concentration(g, gamma0, ncl, nsm, p.pr.gamma_prior_shape, p.pr.gamma_prior_rate);
+    } else if (tid == 4) { // alpha_init (:989-995)
+        Stream g(p.seed, site + 4, p.sweep, chain);
+        double m00 = 0.0;
+        for (int k = 0; k < K; k++) m00 += m[k];
+        hy[1] = concentration(g, alpha_init, m00, (double)n, p.pr.alpha_init_shape, p.pr.alpha_init_rate);
+    } else if (tid == 5) { // alpha + kappa and rho (:1010-1023)
+        Stream g(p.seed, site + 5, p.sweep, chain);
+        const double ak = g.gamma(p.pr.alpha_kappa_shape + scal[4] - scal[2]) /
+                          (p.pr.alpha_kappa_rate - scal[3]);
+        const double rho = g.beta(8.0 + scal[6], scal[5] - scal[6] + 2.0);
+        hy[3] = ak * rho;
+        hy[2] = ak - ak * rho;
     }
     for (int k = tid; k < K; k += nt) beta[k] = nbeta[k];
 }
@@ -302,7 +333,8 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
 inline size_t hdp_smem_bytes(int T, int K, int d)
 {
     const size_t ints = (size_t)T * K * K + (size_t)T * K;
-    return (ints + (ints & 1)) * sizeof(int) + ((size_t)2 * K * d + 3 * K + 16) * sizeof(double) + 16;
+    (void)d;
+    return (ints + (ints & 1)) * sizeof(int) + ((size_t)2 * K + 16) * sizeof(double) + 16;
 }
 
 } // namespace dlsm

@@ -1233,7 +1233,7 @@ __global__ void __launch_bounds__(128) k_ffbs(const LabelParams p)
 // fallback for very large T*K).  Here every lane runs its own node; the T*K partial marginals and
 // the two K-vectors of backward messages live in shared memory, laid out [entry][thread] so that a
 // warp's accesses are conflict-free.  grid = (ceil(n/TPB), C), block = TPB (32 or 64).
-// dynamic smem = (T*K + 2K) * TPB doubles + K*(d+2) doubles.
+// dynamic smem = (T*K + 2K) * TPB doubles + K*(d+2) doubles + K*K doubles (w[t] stage).
 // ---------------------------------------------------------------------------------------------
 template <int TPB>
 __global__ void __launch_bounds__(TPB) k_ffbs_t(const LabelParams p)
@@ -1250,6 +1250,7 @@ __global__ void __launch_bounds__(TPB) k_ffbs_t(const LabelParams p)
     double *s_mu = bwB + (size_t)K * TPB;               // [K][d]
     double *s_ln = s_mu + (size_t)K * d;                // [K]  -(d/2) log(2 pi var)
     double *s_hv = s_ln + K;                            // [K]  0.5 * (1 / var)
+    double *s_w = s_hv + K;                             // [K][K] transition weights of one step
     const double *X = p.X + (size_t)c * T * n * d;
     const double *w = p.w + (size_t)c * T * K * K;
     const double lm = p.lambda[c], oml = __dsub_rn(1.0, lm);
@@ -1292,15 +1293,34 @@ __global__ void __launch_bounds__(TPB) k_ffbs_t(const LabelParams p)
     double *bcur = bwA, *bprev = bwB;
     for (int k = 0; k < K; k++) bcur[k * TPB + tid] = 1.0;
     for (int t = T - 1; t > 0; t--) {
+        __syncthreads();
+        for (int e = tid; e < K * K; e += TPB) s_w[e] = w[(size_t)t * K * K + e]; // w[t] -> smem
         for (int k = 0; k < K; k++) {
             const size_t o = (size_t)(t * K + k) * TPB + tid;
             pm[o] = __dmul_rn(pm[o], bcur[k * TPB + tid]);
         }
-        for (int j = 0; j < K; j++) {
-            const double *wr = w + ((size_t)t * K + j) * K;
+        __syncthreads();
+        // bwd[t-1][j] = sum_k w[t][j][k] pm[t][k]: serial in k per j (the oracle's order), four
+        // rows j at a time so four dependent add chains are in flight per thread
+        int j = 0;
+        for (; j + 4 <= K; j += 4) {
+            const double *wr = s_w + j * K;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int k = 0; k < K; k++) {
+                const double v = pm[(size_t)(t * K + k) * TPB + tid];
+                s0 = __dadd_rn(s0, __dmul_rn(wr[k], v));
+                s1 = __dadd_rn(s1, __dmul_rn(wr[K + k], v));
+                s2 = __dadd_rn(s2, __dmul_rn(wr[2 * K + k], v));
+                s3 = __dadd_rn(s3, __dmul_rn(wr[3 * K + k], v));
+            }
+            bprev[j * TPB + tid] = s0; bprev[(j + 1) * TPB + tid] = s1;
+            bprev[(j + 2) * TPB + tid] = s2; bprev[(j + 3) * TPB + tid] = s3;
+        }
+        for (; j < K; j++) {
+            const double *wr = s_w + j * K;
             double sacc = 0.0;
             for (int k = 0; k < K; k++)
-                sacc = __dadd_rn(sacc, __dmul_rn(__ldg(wr + k), pm[(size_t)(t * K + k) * TPB + tid]));
+                sacc = __dadd_rn(sacc, __dmul_rn(wr[k], pm[(size_t)(t * K + k) * TPB + tid]));
             bprev[j * TPB + tid] = sacc;
         }
         // np.sum over K entries: numpy's pairwise order (serial below 8, 8 accumulators above)
@@ -1330,7 +1350,10 @@ __global__ void __launch_bounds__(TPB) k_ffbs_t(const LabelParams p)
     double *cdf = bprev; // reuse
     int zp = 0;
     for (int t = 0; t < T; t++) {
-        const double *wr = (t == 0) ? w : w + ((size_t)t * K + zp) * K;
+        __syncthreads();
+        for (int e = tid; e < K * K; e += TPB) s_w[e] = w[(size_t)t * K * K + e];
+        __syncthreads();
+        const double *wr = (t == 0) ? s_w : s_w + zp * K;
         double cs = 0.0;
         for (int k = 0; k < K; k++) {
             const double pr = __dmul_rn(wr[k], pm[(size_t)(t * K + k) * TPB + tid]);
