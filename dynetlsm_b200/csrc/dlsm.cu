@@ -232,7 +232,8 @@ template <int LK, int D, bool XS>
 int launch_sweep_x(dlsm_handle *h, const SweepParams &p)
 {
     const int warps = h->cfg.T < 16 ? h->cfg.T : 16;
-    if (warps <= 10) return launch_sweep_t<LK, D, XS, 320, DLSM_SWEEP_MINB>(h, p, warps);
+    if (warps <= 9) return launch_sweep_t<LK, D, XS, 288, DLSM_SWEEP_MINB>(h, p, warps);
+    if (warps <= 10) return launch_sweep_t<LK, D, XS, 320, 3>(h, p, warps);
     return launch_sweep_t<LK, D, XS, 512, 2>(h, p, warps);
 }
 
