@@ -40,7 +40,7 @@ struct Stream {
         if (!(shape > 0.0)) return 0.0;
         double boost = 1.0;
         if (shape < 1.0) {
-            boost = pow(uniform(), 1.0 / shape);
+            boost = exp(log(uniform()) / shape); // U^(1/shape) without the cost of pow()
             shape += 1.0;
         }
         const double dd = shape - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * dd);
