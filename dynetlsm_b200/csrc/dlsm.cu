@@ -938,9 +938,12 @@ int dlsm_run_sweeps(dlsm_handle *h, int32_t n_sweeps, uint32_t flags)
     if (rc != DLSM_OK) return rc;
     for (int s = 0; s < n_sweeps; s++) {
         SweepParams p = sweep_params(h);
+        // the chain kernel with positions in shared memory centres them on the way out
+        const bool fuse = !(flags & 1u) && !use_slice_kernel(h) && sweep_smem(h, true) <= kMaxSmem;
+        p.fuse_center = fuse ? 1 : 0;
         if ((rc = launch_sweep(h, p)) != DLSM_OK) return rc;
         h->sweep_idx[kRngLatent] += 1;
-        if (!(flags & 1u) && (rc = center_async(h)) != DLSM_OK) return rc;
+        if (!(flags & 1u) && !fuse && (rc = center_async(h)) != DLSM_OK) return rc;
         // After centring, the label block (FFBS -> HDP update; latency-bound, few warps per SM)
         // and the intercept / radii MH (full-network kernel; issue-bound) are independent: run
         // the label block on a high-priority side stream so the two overlap.

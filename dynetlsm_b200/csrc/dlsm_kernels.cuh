@@ -51,6 +51,7 @@ struct SweepParams {
     int32_t *accepted;         // optional [C][T][n]
     double *ratio;             // optional [C][T][n]
     unsigned int *flags;       // bit0 non-finite ratio, bit1 case-control out-of-bounds quirk
+    int fuse_center;           // k_sweep (positions in shared memory): centre before the write-back
 };
 
 // latent dimension: a compile-time constant in the specialised (D == 2) instantiations
@@ -451,7 +452,22 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
     if (nonfinite) atomicOr(p.flags, 1u);
     if (XS) {
         __syncthreads();
-        for (size_t e = threadIdx.x; e < chain_elems; e += blockDim.x) Xg[e] = Xc[e];
+        if (p.fuse_center) {
+            // X -= np.mean(X, axis=(0,1)) (lsm.py:501) while the chain is still in shared memory:
+            // serial per-column accumulation = numpy's order, bit-identical to k_center
+            double *mean = stage_base; // the staging area is free now
+            if ((int)threadIdx.x < d) {
+                const size_t rows = (size_t)T * n;
+                double sacc = 0.0;
+                for (size_t r = 0; r < rows; r++) sacc = __dadd_rn(sacc, Xc[r * d + threadIdx.x]);
+                mean[threadIdx.x] = __ddiv_rn(sacc, (double)rows);
+            }
+            __syncthreads();
+            for (size_t e = threadIdx.x; e < chain_elems; e += blockDim.x)
+                Xg[e] = __dsub_rn(Xc[e], mean[e % d]);
+        } else {
+            for (size_t e = threadIdx.x; e < chain_elems; e += blockDim.x) Xg[e] = Xc[e];
+        }
     }
 }
 

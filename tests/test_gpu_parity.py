@@ -416,3 +416,25 @@ def test_labels_vs_oracle_all_kernel_variants(T, n, d, K):
     assert np.array_equal(e.get(L.F_Z)[0], z)
     assert np.array_equal(e.get(L.F_NCOUNT)[0], nc)
     assert np.array_equal(e.get(L.F_NK)[0], nk)
+
+
+def test_fused_centring_equals_sweep_then_center():
+    """dlsm_run_sweeps centres inside the sweep kernel when the chain lives in shared memory; the
+    result must be bit-identical to sweep -> k_center (numpy summation order)."""
+    L = _F()
+    T, n, d = 7, 90, 2
+    rng, X, Y = _synthetic(T, n, d, False, seed=21)
+
+    def make():
+        e = _engine(T=T, n=n, d=d, n_chains=3)
+        e.set_network(Y)
+        e.set(L.F_X, np.stack([X, X + 0.01, X - 0.02]))
+        e.set(L.F_INTERCEPT, np.tile([[0.6, 0.0]], (3, 1)))
+        e.set_tuner(0.1)
+        e.set_rng(5)
+        return e
+    a, b = make(), make()
+    a.run_sweeps(1, skip_intercepts=True)          # fused
+    b.sweep_latent()                               # same Philox draws
+    b.center()
+    assert np.array_equal(a.get(L.F_X), b.get(L.F_X))
