@@ -117,14 +117,14 @@ __device__ __forceinline__ double log1pexp_naive(double eta) { return log(1.0 + 
 // relative parity bound on the summed log-likelihoods.
 // ---------------------------------------------------------------------------------------------
 #define DLSM_X(v) v,
-__device__ const double d_exp_tab[32] = {DLSM_EXP_TAB(DLSM_X)};
-__device__ const double d_expp_tab[32] = {DLSM_EXPP_TAB(DLSM_X)};
-__device__ const double d_rcp_tab[65] = {DLSM_RCP_TAB(DLSM_X)};
-__device__ const double d_log_tab[65] = {DLSM_LOG_TAB(DLSM_X)};
-static const double h_exp_tab[32] = {DLSM_EXP_TAB(DLSM_X)};
-static const double h_expp_tab[32] = {DLSM_EXPP_TAB(DLSM_X)};
-static const double h_rcp_tab[65] = {DLSM_RCP_TAB(DLSM_X)};
-static const double h_log_tab[65] = {DLSM_LOG_TAB(DLSM_X)};
+__device__ const double d_exp_tab[64] = {DLSM_EXP_TAB(DLSM_X)};
+__device__ const double d_expp_tab[64] = {DLSM_EXPP_TAB(DLSM_X)};
+__device__ const double d_rcp_tab[129] = {DLSM_RCP_TAB(DLSM_X)};
+__device__ const double d_log_tab[129] = {DLSM_LOG_TAB(DLSM_X)};
+static const double h_exp_tab[64] = {DLSM_EXP_TAB(DLSM_X)};
+static const double h_expp_tab[64] = {DLSM_EXPP_TAB(DLSM_X)};
+static const double h_rcp_tab[129] = {DLSM_RCP_TAB(DLSM_X)};
+static const double h_log_tab[129] = {DLSM_LOG_TAB(DLSM_X)};
 #undef DLSM_X
 
 // scalar constants live in the constant bank so that DFMA takes them as c[][] operands instead of
@@ -138,10 +138,13 @@ static const double h_spc[16] = DLSM_SP_CONSTS;
 
 // log1p(exp(-|eta|)): the part of softplus that is left after splitting off max(eta, 0).
 // Branch-free and select-free on purpose (the sweep kernel is issue-bound, ncu profiles/r1):
-// independent evaluations in one thread interleave freely.
-//   t = e^{-a}:  a = n ln2/32 - r, |r| <= ln2/64;  t = 2^{-(n>>5)} 2^{-(n&31)/32} e^r   (deg 6)
-//   log1p(t):    y = 1 + t (rounding error c recovered); i = round(64 (y-1)), R = 1/(1 + i/64);
-//                z = y R - 1, |z| <= 1/128;  log y = -log R + (z - z^2/2 + ... + z^7/7);  + c R
+// independent evaluations in one thread interleave freely.  21 fp64 instructions, 2 table loads.
+//   t = e^{-a}:  a = n ln2/64 - r, |r| <= ln2/128;  t = 2^{-(n>>6)} 2^{-(n&63)/64} e^r   (deg 5)
+//   log1p(t):    y = 1 + t;  i = round(128 (y-1)), R = 1/(1 + i/128);  z = y R - 1, |z| <= 1/256;
+//                log y = -log R + (z - z^2/2 + ... + z^6/6)
+// The rounding of y = 1 + t (<= 1.1e-16 absolute) is NOT compensated: the result is accurate to
+// ~2e-16 ABSOLUTE, which is what sums of O(1) terms need (relative accuracy in the far tail,
+// where the term is < 1e-9, is ~1e-7); tests/test_host_numerics.py.
 // n is clamped (unsigned) so that a > ~690 -- where t < 1e-300 -- cannot wrap the exponent.
 __host__ __device__ __forceinline__ double fast_log1pexp_neg(double a /* = |eta| */)
 {
@@ -150,38 +153,32 @@ __host__ __device__ __forceinline__ double fast_log1pexp_neg(double a /* = |eta|
 #else
     const double *ET = h_exp_tab, *RT = h_rcp_tab, *LT = h_log_tab, *K = h_spc;
 #endif
-    const double kf = fma(a, K[0], K[1]); // round(a * 32/ln2) lands in the low mantissa bits
+    const double kf = fma(a, K[0], K[1]); // round(a * 64/ln2) lands in the low mantissa bits
     union { double f; long long i; unsigned u[2]; } cv;
     cv.f = kf;
     const unsigned n = cv.u[0];
     const double nf = kf - K[1];
     double r = fma(nf, K[2], -a);
     r = fma(nf, K[3], r);
-    double p = fma(r, K[4], K[5]);
-    p = fma(r, p, K[6]);
+    double p = fma(r, K[5], K[6]);
     p = fma(r, p, K[7]);
     p = fma(r, p, K[8]);
     p = fma(r, p, K[9]);
     p = fma(r, p, K[9]);
-    cv.f = p * ET[n & 31u];
-    const unsigned sh = n >> 5;
-    cv.u[1] -= (sh < 1000u ? sh : 1000u) << 20; // * 2^-(n>>5)
-    const double t = cv.f;
-    const double y = K[9] + t;
-    const double c = t - (y - K[9]);
+    cv.f = p * ET[n & 63u];
+    const unsigned sh = n >> 6;
+    cv.u[1] -= (sh < 1000u ? sh : 1000u) << 20; // * 2^-(n>>6)
+    const double y = K[9] + cv.f;
     cv.f = y;
-    unsigned i = (cv.u[1] - 0x3ff00000u + 0x2000u) >> 14; // 0..64
-    i = i < 64u ? i : 64u; // NaN / garbage never indexes out of the table
-    const double R = RT[i];
-    const double z = fma(y, R, -K[9]);
-    double q = fma(z, K[10], K[11]);
-    q = fma(z, q, K[12]);
+    unsigned i = (cv.u[1] - 0x3ff00000u + 0x1000u) >> 13; // 0..128
+    i = i < 128u ? i : 128u; // NaN / garbage never indexes out of the table
+    const double z = fma(y, RT[i], -K[9]);
+    double q = fma(z, K[11], K[12]);
     q = fma(z, q, K[13]);
     q = fma(z, q, K[14]);
     q = fma(z, q, K[15]);
     q = fma(z, q, K[9]);
-    q = z * q;
-    return fma(c, R, q) + LT[i];
+    return fma(z, q, LT[i]);
 }
 
 // log(1 + e^eta) = max(eta, 0) + log1p(e^{-|eta|}); max(eta,0) = (eta + |eta|)/2 keeps NaN alive.
@@ -219,14 +216,13 @@ __host__ __device__ __forceinline__ double fast_exp(double x)
     const double nf = kf - K[1];
     double r = fma(nf, -K[2], xc);
     r = fma(nf, -K[3], r);
-    double p = fma(r, K[4], K[5]);
-    p = fma(r, p, K[6]);
+    double p = fma(r, K[5], K[6]);
     p = fma(r, p, K[7]);
     p = fma(r, p, K[8]);
     p = fma(r, p, K[9]);
     p = fma(r, p, K[9]);
-    cv.f = p * PT[n & 31];
-    int e = n >> 5;
+    cv.f = p * PT[n & 63];
+    int e = n >> 6;
     e = e < -1022 ? -1022 : (e > 1023 ? 1023 : e);
     cv.s[1] += e << 20;
     double v = cv.f;
@@ -236,19 +232,37 @@ __host__ __device__ __forceinline__ double fast_exp(double x)
 }
 
 // Branch-free fp64 sqrt: MUFU.RSQ64H seed (~22 bits), one Goldschmidt step (~44 bits) and a final
-// fused correction g += (s - g*g) * h, which squares the error again: within 1 ulp of IEEE sqrt.
-// 1e-300 is added so that coincident points (s == 0) give 1e-150 instead of 0 * inf; it is
-// absorbed exactly for every s > 1e-284.  NaN propagates.
-__device__ __forceinline__ double fast_sqrt(double s)
+// fused correction g += (s - g*g) * h (h only needs the seed's accuracy there), which squares the
+// error again: exactly rounded on 4M random inputs (tools/ubench/sqrt_check.cu).  The argument
+// must be > 0 and normal: callers add 1e-300 so that coincident points give 1e-150 instead of
+// 0 * inf (absorbed exactly for every s > 1e-284).  NaN propagates.
+__device__ __forceinline__ double fast_sqrt_pos(double s)
 {
-    s += 1e-300;
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
-    double g = s * y, h = 0.5 * y;
-    const double r = fma(-h, g, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
+    double g = s * y;
+    const double h = 0.5 * y;
+    g = fma(g, fma(-h, g, 0.5), g);
     return fma(fma(-g, g, s), h, g);
+}
+
+__device__ __forceinline__ double fast_sqrt(double s) { return fast_sqrt_pos(s + 1e-300); }
+
+// Euclidean distance for the likelihood terms: squared differences accumulated by FMA on top of
+// the 1e-300 guard (one rounding fewer than the reference's separate multiply and add -- inside
+// the 1e-10 parity bound of the log-likelihoods, and irrelevant to the bit-exactness of the
+// states, which only depends on decisions)
+template <int DM>
+__device__ __forceinline__ double fast_dist(const double (&a)[DM], const double (&b)[DM], int d)
+{
+    double s = 1e-300;
+#pragma unroll
+    for (int k = 0; k < DM; k++)
+        if (k < d) {
+            const double df = a[k] - b[k];
+            s = fma(df, df, s);
+        }
+    return fast_sqrt_pos(s);
 }
 
 #ifndef DLSM_NAIVE_SOFTPLUS

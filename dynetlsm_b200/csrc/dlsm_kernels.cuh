@@ -105,10 +105,10 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
             double xa[DM], xb[DM];
             load_pos<DM>(Xt + (size_t)(i0 < n ? i0 : n - 1) * d, d, xa);
             load_pos<DM>(Xt + (size_t)(i1 < n ? i1 : n - 1) * d, d, xb);
-            const double en0 = b0 - fast_sqrt(sqdist<DM>(xa, xn, d));
-            const double eo0 = b0 - fast_sqrt(sqdist<DM>(xa, xo, d));
-            const double en1 = b0 - fast_sqrt(sqdist<DM>(xb, xn, d));
-            const double eo1 = b0 - fast_sqrt(sqdist<DM>(xb, xo, d));
+            const double en0 = b0 - fast_dist<DM>(xa, xn, d);
+            const double eo0 = b0 - fast_dist<DM>(xa, xo, d);
+            const double en1 = b0 - fast_dist<DM>(xb, xn, d);
+            const double eo1 = b0 - fast_dist<DM>(xb, xo, d);
             an = fma(v0, logit_term(y0, en0), an);
             ao = fma(v0, logit_term(y0, eo0), ao);
             an2 = fma(v1, logit_term(y1, en1), an2);
@@ -132,8 +132,8 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
             double xi[DM];
             load_pos<DM>(Xt + (size_t)ic * d, d, xi);
             const double ri = rinv[ic];
-            const double dn = fast_sqrt(sqdist<DM>(xi, xn, d));
-            const double dd = fast_sqrt(sqdist<DM>(xi, xo, d));
+            const double dn = fast_dist<DM>(xi, xn, d);
+            const double dd = fast_dist<DM>(xi, xo, d);
             const double tn = logit_term(y_ji, eta_directed(b0, b1, dn, ri, rj)) +
                               logit_term(y_ij, eta_directed(b0, b1, dn, rj, ri));
             const double to = logit_term(y_ji, eta_directed(b0, b1, dd, ri, rj)) +
@@ -162,8 +162,8 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
             double xk[DM];
             load_pos<DM>(Xt + (size_t)k * d, d, xk);
             const double rk = rinv[k];
-            const double dn = fast_sqrt(sqdist<DM>(xk, xn, d));
-            const double dd = fast_sqrt(sqdist<DM>(xk, xo, d));
+            const double dn = fast_dist<DM>(xk, xn, d);
+            const double dd = fast_dist<DM>(xk, xo, d);
             const double r_recv = k_sends ? rj : rk, r_send = k_sends ? rk : rj;
             vn = eta_directed(b0, b1, dn, r_recv, r_send);
             vo = eta_directed(b0, b1, dd, r_recv, r_send);
@@ -803,7 +803,7 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
                     load_pos<DM>(Xt + (size_t)bcol * d, d, xb);
 #pragma unroll
                     for (int k = 0; k < DM; k++) xa[k] = first ? xi[k] : xi2[k];
-                    const double dist = fast_sqrt(sqdist<DM>(xb, xa, d));
+                    const double dist = fast_dist<DM>(xb, xa, d);
                     const size_t wo = ((size_t)t * n + arow) * W + (bcol >> 5);
                     if (LK == kUndirected) {
                         const double y = ymask(__ldg(p.net.rowbits + wo), bcol & 31);
@@ -838,7 +838,7 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
                 const int k = oe[q];
                 double xk[DM];
                 load_pos<DM>(Xt + (size_t)k * d, d, xk);
-                const double dist = fast_sqrt(sqdist<DM>(xk, xi, d));
+                const double dist = fast_dist<DM>(xk, xi, d);
                 const double v0 = eta_directed(b00, b01, dist, r0[k], ri0);
                 const double v1 = eta_directed(b10, b11, dist, r1[k], ri1);
                 e0 += logit_term(0.5, v0);
@@ -855,7 +855,7 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
                 const int k = co[q];
                 double xk[DM];
                 load_pos<DM>(Xt + (size_t)k * d, d, xk);
-                const double dist = fast_sqrt(sqdist<DM>(xk, xi, d));
+                const double dist = fast_dist<DM>(xk, xi, d);
                 c0 += log1pexp(eta_directed(b00, b01, dist, r0[k], ri0));
                 c1 += log1pexp(eta_directed(b10, b11, dist, r1[k], ri1));
             }
