@@ -1,0 +1,179 @@
+"""Edge cases of the hot path against the CPU oracle: degenerate shapes, row lengths around the
+32/64-lane chunking, every latent dimension up to 8 (numpy's 8-accumulator sum kicks in at d = 8),
+empty / complete graphs, coincident positions (distance exactly 0), far-apart positions (softplus
+tails), single-component mixtures, ragged case-control lists with sentinels."""
+import numpy as np
+import pytest
+
+import pyoracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _L():
+    from dynetlsm_b200 import _lib
+    return _lib
+
+
+def _net(rng, T, n, directed, density):
+    Y = (rng.rand(T, n, n) < density).astype(np.float64)
+    for t in range(T):
+        np.fill_diagonal(Y[t], 0)
+    if not directed:
+        Y = np.triu(Y, 1)
+        Y = Y + Y.transpose(0, 2, 1)
+    return Y
+
+
+def _run_both(T, n, d, directed, Y, X, mode=None, monkeypatch=None, n_sweeps=2, mixture=None,
+              tau=2.0, sig=0.1, step=0.1, seed=0):
+    L = _L()
+    if mode:
+        monkeypatch.setenv("DLSM_SWEEP_MODE", mode)
+    rng = np.random.RandomState(seed)
+    radii = rng.dirichlet(np.ones(n) * 5) if directed else None
+    ic = np.array([0.4, 0.7]) if directed else np.array([0.9])
+    K = 0 if mixture is None else mixture["sigma"].size
+    e = L.Engine(T=T, n=n, d=d, is_directed=directed, K=K, mixture=mixture is not None, tune=3,
+                 tune_interval=1)
+    e.set_network(Y)
+    e.set_hyper(tau_sq=tau, sigma_sq=sig)
+    icd = np.zeros((1, 2)); icd[0, :ic.size] = ic
+    e.set(L.F_INTERCEPT, icd)
+    if directed:
+        e.set(L.F_RADII, radii[None])
+    if mixture is not None:
+        e.set(L.F_MU, mixture["mu"][None]); e.set(L.F_SIGMA, mixture["sigma"][None])
+        e.set(L.F_LAMBDA, np.array([mixture["lmbda"]])); e.set(L.F_Z, mixture["z"][None])
+    e.set(L.F_X, X[None])
+    e.set_tuner(step)
+    tun = O.TunerState((T, n), step, tune=3, tune_interval=1)
+    Xo = X.copy()
+    # per-node and full-network log-likelihoods at the start state
+    part = e.loglik_partial()[0]
+    for t in range(T):
+        for i in range(0, n, max(1, n // 7)):
+            ref = (O.directed_partial_loglikelihood(Y[t], Xo[t], radii, ic[0], ic[1], i) if directed
+                   else O.partial_loglikelihood(Y[t], Xo[t], ic[0], i))
+            assert abs(part[t, i] - ref) <= 1e-10 * max(abs(ref), 1e-300) + 1e-13, (t, i, part[t, i], ref)
+    for s in range(n_sweeps):
+        eps = rng.randn(T, n, d)
+        logu = np.log(rng.rand(T, n))
+        out = O.sweep_latent(Xo, ic, tun, eps, logu, Y=Y, radii=radii, is_directed=directed,
+                             tau_sq=tau, sigma_sq=sig, mixture=mixture)
+        acc, ratio = e.sweep_latent(eps[None], logu[None], want_stats=True)
+        assert np.array_equal(acc[0], out["accepted"])
+        assert np.array_equal(e.get(L.F_X)[0], Xo)
+        O.center(Xo)
+        e.center()
+        assert np.array_equal(e.get(L.F_X)[0], Xo)
+    assert np.array_equal(e.get(L.F_X_STEP)[0], tun.step)
+    return e
+
+
+@pytest.mark.parametrize("mode", ["chain", "slice"])
+@pytest.mark.parametrize("T,n,d", [(1, 2, 1), (1, 5, 2), (2, 31, 2), (2, 32, 2), (2, 33, 3), (3, 63, 2),
+                                   (2, 64, 4), (2, 65, 5), (2, 97, 6), (2, 128, 7), (2, 129, 8), (40, 6, 2)])
+def test_shapes_around_the_chunking(T, n, d, mode, monkeypatch):
+    rng = np.random.RandomState(T * 100 + n)
+    _run_both(T, n, d, False, _net(rng, T, n, False, 0.3), rng.randn(T, n, d), mode, monkeypatch)
+
+
+@pytest.mark.parametrize("mode", ["chain", "slice"])
+@pytest.mark.parametrize("T,n,d", [(1, 3, 2), (3, 40, 2), (2, 70, 3)])
+def test_directed_shapes(T, n, d, mode, monkeypatch):
+    rng = np.random.RandomState(T * 10 + n)
+    _run_both(T, n, d, True, _net(rng, T, n, True, 0.2), rng.randn(T, n, d) / n, mode, monkeypatch,
+              tau=1.0 / n ** 2, sig=1e-3 / n, step=0.02 / n)
+
+
+@pytest.mark.parametrize("density", [0.0, 1.0])
+def test_empty_and_complete_graphs(density):
+    rng = np.random.RandomState(3)
+    T, n, d = 2, 40, 2
+    _run_both(T, n, d, False, _net(rng, T, n, False, density), rng.randn(T, n, d))
+    _run_both(T, n, d, True, _net(rng, T, n, True, density), rng.randn(T, n, d) / n, tau=1e-3, sig=1e-4,
+              step=0.01 / n)
+
+
+def test_coincident_and_far_apart_positions():
+    """dist == 0 exactly (several nodes on one point) and |eta| up to ~2000 (softplus tails)."""
+    rng = np.random.RandomState(4)
+    T, n, d = 2, 50, 2
+    X = rng.randn(T, n, d)
+    X[:, 5:9] = X[:, 4:5]            # four nodes on top of a fifth
+    X[:, 20:25] *= 400.0             # far away: eta ~ -1000
+    _run_both(T, n, d, False, _net(rng, T, n, False, 0.2), X)
+
+
+def test_single_component_mixture_and_labels():
+    L = _L()
+    rng = np.random.RandomState(5)
+    T, n, d, K = 3, 20, 2, 1
+    mix = dict(mu=rng.randn(K, d), sigma=np.array([0.7]), lmbda=0.6, z=np.zeros((T, n), np.int64))
+    e = _run_both(T, n, d, False, _net(rng, T, n, False, 0.3), rng.randn(T, n, d), mixture=mix)
+    w = np.ones((T, K, K))
+    e.set(L.F_WEIGHTS, w[None])
+    U = rng.rand(n, T)
+    e.sample_labels(U[None])
+    assert np.all(e.get(L.F_Z) == 0) and np.all(e.get(L.F_NK)[0] == n)
+
+
+def test_ragged_case_control_lists():
+    """Nodes with no edges, with fewer non-neighbours than n_control (sentinel-terminated lists)
+    and the reference's out-of-bounds configuration (flagged, never read)."""
+    L = _L()
+    from dynetlsm_b200 import DirectedCaseControlSampler
+    rng = np.random.RandomState(6)
+    T, n, d = 2, 30, 2
+    Y = _net(rng, T, n, True, 0.15)
+    Y[0, 3, :] = 0; Y[0, :, 3] = 0                      # isolated node
+    Y[1, 7, :] = 1; Y[1, 7, 7] = 0; Y[1, 7, 10:14] = 0  # out-degree n-5: only 4 out-controls exist
+    Y[1, :, 8] = 1; Y[1, 8, 8] = 0; Y[1, 0:3, 8] = 0    # in-degree n-4: only 3 in-controls exist
+    cc = DirectedCaseControlSampler(n_control=6, n_resample=None, random_state=np.random.RandomState(1)).init(Y)
+    n_in = (cc.control_nodes_in_ != -1).sum(axis=2)
+    n_out = (cc.control_nodes_out_ != -1).sum(axis=2)
+    assert (n_in < 6).any() and (n_out < n_in).any()    # ragged, and the UB pattern is present
+    X = rng.randn(T, n, d) / n
+    radii = rng.dirichlet(np.ones(n) * 5)
+    e = L.Engine(T=T, n=n, d=d, is_directed=True, case_control=True)
+    e.set_edge_lists(cc.degrees_, cc.in_edges_, cc.out_edges_)
+    e.set_controls(cc.control_nodes_in_, cc.control_nodes_out_)
+    e.set(L.F_X, X[None]); e.set(L.F_RADII, radii[None]); e.set(L.F_INTERCEPT, np.array([[0.3, 0.6]]))
+    got = e.loglik_partial()[0]
+    n_ub = 0
+    for t in range(T):
+        for i in range(n):
+            ref, ub = O.approx_directed_partial_loglikelihood(
+                X[t], radii, cc.in_edges_[t], cc.out_edges_[t], cc.degrees_[t], cc.control_nodes_in_[t],
+                cc.control_nodes_out_[t], 0.3, 0.6, i, return_ub=True)
+            n_ub += ub
+            if np.isnan(ref):
+                assert np.isnan(got[t, i])
+            else:
+                assert abs(got[t, i] - ref) <= 1e-10 * abs(ref) + 1e-13
+    full = e.loglik_full()[0]
+    ref = O.approx_directed_network_loglikelihood(X, radii, cc.out_edges_, cc.degrees_,
+                                                  cc.control_nodes_out_, 0.3, 0.6)
+    assert abs(full - ref) <= 1e-10 * abs(ref)
+    assert n_ub > 0
+    e.set_tuner(0.001)
+    try:
+        e.sweep_latent(rng.randn(1, T, n, d), np.log(rng.rand(1, T, n)))
+    except L.DlsmError as err:       # a node with no non-neighbours gives 0/0 = NaN, as in the reference
+        assert err.code == -5
+    assert e.counters()["ub_flags"] >= 1
+
+
+def test_shape_and_argument_errors():
+    L = _L()
+    e = L.Engine(T=2, n=5, d=2)
+    with pytest.raises(ValueError):
+        e.set(L.F_X, np.zeros((1, 2, 5, 3)))
+    with pytest.raises(L.DlsmError) as ei:
+        e.sweep_latent()                      # network not set
+    assert ei.value.code == -4
+    with pytest.raises(L.DlsmError):
+        e.sample_radii()                      # undirected model has no radii
+    with pytest.raises(L.DlsmError):
+        e.sample_labels()                     # no mixture prior
