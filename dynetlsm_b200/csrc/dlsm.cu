@@ -256,7 +256,7 @@ int slice_warps(const dlsm_handle *h)
 
 size_t slice_smem(const dlsm_handle *h, bool xs, int nw)
 {
-    const size_t x = (size_t)h->cfg.n * h->cfg.d * sizeof(double);
+    const size_t x = (size_t)h->cfg.n * (h->cfg.d + (h->lk == kUndirected ? 0 : 1)) * sizeof(double);
     return (xs ? x : 0) + (sweep_stage_doubles(h->cfg.d) + 2 * (size_t)nw) * sizeof(double) + 16;
 }
 

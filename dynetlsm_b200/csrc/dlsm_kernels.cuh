@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
 // memory (st + __threadfence + flag; volatile loads on the other side).  CTAs take their (chain,
 // slice) from an atomic ticket, so a CTA only ever waits on a CTA that has already started:
 // no co-residency assumption, no deadlock.
-// grid = C*T, block = 32*NW, dynamic smem = [n*d doubles if XS] + 32*(d+5) doubles + 2*NW doubles
+// grid = C*T, block = 32*NW, dynamic smem = [n*d (+ n) doubles if XS] + 32*(d+5) doubles + 2*NW doubles
 // ---------------------------------------------------------------------------------------------
 template <int LK, int D, bool XS>
 __global__ void __launch_bounds__(512) k_sweep_slice(const SweepParams p, int *progress_g,
@@ -510,10 +510,15 @@ __global__ void __launch_bounds__(512) k_sweep_slice(const SweepParams p, int *p
     int *st_zc = reinterpret_cast<int *>(st_inv + 32);
     double *part = stage_base + sweep_stage_doubles(d);     // [nwarps][2]
     volatile int *prog = progress_g + (size_t)c * T;
+    const double *rinv = (LK == kUndirected) ? nullptr : p.rinv + (size_t)c * n;
+    if (XS && LK != kUndirected) { // reciprocal radii next to the positions (read once per pair)
+        double *s_rinv = part + 2 * nwarps;
+        for (int e = threadIdx.x; e < n; e += blockDim.x) s_rinv[e] = rinv[e];
+        rinv = s_rinv;
+    }
     __syncthreads();
 
     const double b0 = p.intercept[c * 2 + 0], b1 = p.intercept[c * 2 + 1];
-    const double *rinv = (LK == kUndirected) ? nullptr : p.rinv + (size_t)c * n;
     const uint32_t chain_id = (uint32_t)c + p.chain_offset;
     bool nonfinite = false;
 
@@ -568,6 +573,11 @@ __global__ void __launch_bounds__(512) k_sweep_slice(const SweepParams p, int *p
             double x[DM], x0[DM];
             load_pos<DM>(st_prop + jj * d, d, x);
             load_pos<DM>(Xt + (size_t)j * d, d, x0);
+            if (LK != kCaseControl && j + 1 < n && (int)threadIdx.x * 32 < p.net.W) { // next row -> L1
+                const size_t o = ((size_t)t * n + j + 1) * p.net.W + threadIdx.x * 32;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.net.rowbits + o));
+                if (LK == kDirected) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.net.colbits + o));
+            }
             double ll_new, ll_old;
             node_loglik2<LK, DM>(p.net, Xt, rinv, c, t, j, x, x0, b0, b1, lane, ll_new, ll_old,
                                  p.flags, warp, nwarps);
