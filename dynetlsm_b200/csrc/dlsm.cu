@@ -53,6 +53,7 @@ struct dlsm_handle {
     unsigned int *d_ticket = nullptr;
     double *d_hdp_scratch = nullptr; // [C][2*K*d + K]
     int sweep_mode = 0;             // 0 auto, 1 CTA per chain, 2 CTA per (chain, slice)
+    bool no_pipeline = false;       // DLSM_SWEEP_MODE=slice-plain: the unpipelined slice kernel
     // rng
     uint64_t seed = 0, chain_offset = 0;
     uint32_t sweep_idx[5] = {0, 0, 0, 0, 0};
@@ -263,13 +264,22 @@ size_t slice_smem(const dlsm_handle *h, bool xs, int nw)
 template <int LK, int D, bool XS>
 int launch_slice_t(dlsm_handle *h, const SweepParams &p, int nw)
 {
-    const size_t smem = slice_smem(h, XS, nw);
-    auto kern = k_sweep_slice<LK, D, XS>;
-    CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t CT = (size_t)h->cfg.n_chains * h->cfg.T;
     CU(h, cudaMemsetAsync(h->d_progress, 0, CT * sizeof(int), h->stream));
     CU(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
-    kern<<<(unsigned)CT, nw * 32, smem, h->stream>>>(p, h->d_progress, h->d_ticket);
+    if (LK != kCaseControl && nw >= 3 && !h->no_pipeline) {
+        // warp-specialised, pipelined variant: one control warp + nw compute warps
+        const int warps = nw + 1;
+        const size_t smem = slice_smem(h, XS, warps) + (2 * warps) * sizeof(double) + warps * sizeof(int);
+        auto kern = k_sweep_slice_ws<LK == kCaseControl ? kDirected : LK, D, XS>;
+        CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)CT, warps * 32, smem, h->stream>>>(p, h->d_progress, h->d_ticket);
+    } else {
+        const size_t smem = slice_smem(h, XS, nw);
+        auto kern = k_sweep_slice<LK, D, XS>;
+        CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)CT, nw * 32, smem, h->stream>>>(p, h->d_progress, h->d_ticket);
+    }
     CHECK_LAUNCH(h);
     return DLSM_OK;
 }
@@ -278,7 +288,7 @@ template <int LK>
 int launch_slice_lk(dlsm_handle *h, const SweepParams &p)
 {
     const int nw = slice_warps(h);
-    const bool xs = slice_smem(h, true, nw) <= kMaxSmem / 2;
+    const bool xs = slice_smem(h, true, nw + 1) + 4096 <= kMaxSmem / 2;
     if (h->cfg.d == 2) return xs ? launch_slice_t<LK, 2, true>(h, p, nw) : launch_slice_t<LK, 2, false>(h, p, nw);
     return xs ? launch_slice_t<LK, 0, true>(h, p, nw) : launch_slice_t<LK, 0, false>(h, p, nw);
 }
@@ -436,7 +446,10 @@ int dlsm_create(const dlsm_config *cfg, dlsm_handle **out)
                                                       : (cfg->is_directed ? kDirected : kUndirected);
     h->W = ((cfg->n + 31) / 32 + 3) / 4 * 4;
     if (const char *m = getenv("DLSM_SWEEP_MODE")) // chain | slice: override the heuristic (tests, tuning)
-        h->sweep_mode = !strcmp(m, "chain") ? 1 : (!strcmp(m, "slice") ? 2 : 0);
+    {
+        h->sweep_mode = !strcmp(m, "chain") ? 1 : ((!strcmp(m, "slice") || !strcmp(m, "slice-plain")) ? 2 : 0);
+        h->no_pipeline = !strcmp(m, "slice-plain");
+    }
     auto fail = [&](const char *what, cudaError_t e) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
         dlsm_destroy(h);

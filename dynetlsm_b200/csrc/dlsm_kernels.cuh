@@ -85,8 +85,9 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
                                              const double (&xn)[DM], const double (&xo)[DM],
                                              double b0, double b1, int lane, double &ll_new,
                                              double &ll_old, unsigned int *flags, int wteam = 0,
-                                             int nteam = 1)
+                                             int nteam = 1, int skip = -1)
 {
+    // skip: a second index left out of the sums (the pipelined slice kernel adds that pair later)
     // wteam / nteam: this warp's rank in, and the size of, the team of warps that shares the row.
     // The outputs are this warp's PARTIAL sums (the whole sums when nteam == 1); they are linear in
     // the per-pair terms, so the caller adds the partials of the team in a fixed order.
@@ -100,7 +101,8 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
         for (int base = wteam * 64; base < n; base += 64 * nteam) {
             const int i0 = base + lane, i1 = i0 + 32;
             const uint2 w = __ldg(reinterpret_cast<const uint2 *>(row + (base >> 5)));
-            const double v0 = vmask((i0 < n) && (i0 != j)), v1 = vmask((i1 < n) && (i1 != j));
+            const double v0 = vmask((i0 < n) && (i0 != j) && (i0 != skip));
+            const double v1 = vmask((i1 < n) && (i1 != j) && (i1 != skip));
             const double y0 = ymask(w.x, lane), y1 = ymask(w.y, lane);
             double xa[DM], xb[DM];
             load_pos<DM>(Xt + (size_t)(i0 < n ? i0 : n - 1) * d, d, xa);
@@ -127,7 +129,7 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
             const int i = base + lane;
             const double y_ji = ymask(__ldg(row + (base >> 5)), lane); // Y[node, i]: node sends
             const double y_ij = ymask(__ldg(col + (base >> 5)), lane); // Y[i, node]: i sends
-            const double v = vmask((i < n) && (i != j));
+            const double v = vmask((i < n) && (i != j) && (i != skip));
             const int ic = i < n ? i : n - 1;
             double xi[DM];
             load_pos<DM>(Xt + (size_t)ic * d, d, xi);
@@ -625,6 +627,230 @@ __global__ void __launch_bounds__(512) k_sweep_slice(const SweepParams p, int *p
             }
             __syncthreads();
         }
+        if (mine) {
+            metropolis_bookkeep(my_step, my_nacc, my_nsteps, my_until, p.tune, p.tune_interval,
+                                my_acc, false);
+            p.step[gs] = my_step; p.nacc[gs] = my_nacc; p.nsteps[gs] = my_nsteps; p.until[gs] = my_until;
+            if (p.accepted) p.accepted[gs] = my_acc;
+        }
+        __syncthreads();
+    }
+    if (nonfinite) atomicOr(p.flags, 1u);
+}
+
+// the (j, i) dyad's contribution to node j's two log-likelihoods (proposal xn, current xo)
+template <int LK, int DM>
+__device__ __forceinline__ void pair_term2(const NetView &net, const double *Xt, const double *rinv,
+                                           int t, int j, int i, const double (&xn)[DM],
+                                           const double (&xo)[DM], double b0, double b1, double &tn,
+                                           double &to)
+{
+    const int n = net.n, d = latent_dim<DM>(net);
+    double xi[DM];
+    load_pos<DM>(Xt + (size_t)i * d, d, xi);
+    const size_t wo = ((size_t)t * n + j) * net.W + (i >> 5);
+    const double dn = fast_dist<DM>(xi, xn, d), dd = fast_dist<DM>(xi, xo, d);
+    if (LK == kUndirected) {
+        const double y = ymask(__ldg(net.rowbits + wo), i & 31);
+        tn = logit_term(y, b0 - dn);
+        to = logit_term(y, b0 - dd);
+    } else {
+        const double y_ji = ymask(__ldg(net.rowbits + wo), i & 31);
+        const double y_ij = ymask(__ldg(net.colbits + wo), i & 31);
+        const double ri = rinv[i], rj = rinv[j];
+        tn = logit_term(y_ji, eta_directed(b0, b1, dn, ri, rj)) + logit_term(y_ij, eta_directed(b0, b1, dn, rj, ri));
+        to = logit_term(y_ji, eta_directed(b0, b1, dd, ri, rj)) + logit_term(y_ij, eta_directed(b0, b1, dd, rj, ri));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_sweep_slice_ws: the CTA-per-(chain, slice) sweep, warp-specialised and software-pipelined.
+// Warp 0 is the CONTROL warp (wavefront flag, priors, accept/reject, commit); warps 1..NW-1 are
+// COMPUTE warps (the pairwise reduction).  Node j+1's row depends on node j's decision through ONE
+// dyad only, (j+1, j): the compute warps therefore start node j+1 as soon as node j-1 is decided,
+// always leaving out i = j, and the control warp adds that single dyad once it has decided node j.
+// The serial tail of a node (L2 round trips for the flag and the neighbour slice, fences, prior)
+// then overlaps the next node's reduction instead of adding to it.  Exact (undirected / directed)
+// likelihoods only; the case-control lists use k_sweep_slice.
+// dynamic smem = [n*(d [+1]) doubles if XS] + 32*(d+5) doubles + 4*NW doubles + 2*NW ints
+// ---------------------------------------------------------------------------------------------
+template <int LK, int D, bool XS>
+__global__ void __launch_bounds__(576) k_sweep_slice_ws(const SweepParams p, int *progress_g,
+                                                        unsigned int *ticket)
+{
+    constexpr int DM = (D == 0) ? kMaxD : D;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_ticket;
+    __shared__ volatile int s_decided; // nodes 0 .. s_decided-1 of this slice are final in Xt
+    const int T = p.net.T, n = p.net.n, d = (D == 0) ? p.net.d : D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int ncomp = nwarps - 1;
+    if (threadIdx.x == 0) { s_ticket = (int)atomicAdd(ticket, 1u); s_decided = 0; }
+    __syncthreads();
+    const int c = s_ticket / T, t = s_ticket % T;
+    double *Xchain = p.X + (size_t)c * T * n * d;
+    double *Xg = Xchain + (size_t)t * n * d;
+    double *Xt, *stage_base;
+    const double *rinv = (LK == kUndirected) ? nullptr : p.rinv + (size_t)c * n;
+    if (XS) {
+        Xt = reinterpret_cast<double *>(smem_raw);
+        stage_base = Xt + (size_t)n * d;
+        for (int e = threadIdx.x; e < n * d; e += blockDim.x) Xt[e] = Xg[e];
+        if (LK != kUndirected) {
+            double *s_rinv = stage_base;
+            stage_base += n;
+            for (int e = threadIdx.x; e < n; e += blockDim.x) s_rinv[e] = rinv[e];
+            rinv = s_rinv;
+        }
+    } else {
+        Xt = Xg;
+        stage_base = reinterpret_cast<double *>(smem_raw);
+    }
+    double *st_prop = stage_base;
+    double *st_logu = st_prop + 32 * d, *st_nn = st_logu + 32, *st_no = st_nn + 32, *st_inv = st_no + 32;
+    int *st_zc = reinterpret_cast<int *>(st_inv + 32);
+    double *part = stage_base + sweep_stage_doubles(d);          // [2][nwarps][2]
+    volatile int *done = reinterpret_cast<volatile int *>(part + 4 * nwarps); // [nwarps] nodes summed
+    volatile int *prog = progress_g + (size_t)c * T;
+    for (int w = threadIdx.x; w < nwarps; w += blockDim.x) done[w] = 0;
+    __syncthreads();
+
+    const double b0 = p.intercept[c * 2 + 0], b1 = p.intercept[c * 2 + 1];
+    const uint32_t chain_id = (uint32_t)c + p.chain_offset;
+    bool nonfinite = false;
+
+    for (int jb = 0; jb < n; jb += 32) {
+        // ---- lane-parallel preparation of the block (control warp) ----
+        const int jl = jb + lane;
+        const bool mine = (warp == 0) && (jl < n);
+        const size_t gs = ((size_t)c * T + t) * n + (jl < n ? jl : 0);
+        double my_step = 0.0;
+        int my_nacc = 0, my_nsteps = 0, my_until = 0, my_acc = 0;
+        if (mine) {
+            double eps[DM], x0[DM], x[DM], logu;
+            load_pos<DM>(Xt + (size_t)jl * d, d, x0);
+            my_step = p.step[gs]; my_nacc = p.nacc[gs]; my_nsteps = p.nsteps[gs]; my_until = p.until[gs];
+            if (p.eps) {
+#pragma unroll
+                for (int k = 0; k < DM; k++) eps[k] = (k < d) ? p.eps[gs * d + k] : 0.0;
+                logu = p.logu[gs];
+            } else {
+                latent_draws<DM>(p.seed, (uint32_t)(t * n + jl), p.sweep, chain_id, d, eps, logu);
+            }
+#pragma unroll
+            for (int k = 0; k < DM; k++) {
+                x[k] = (k < d) ? __dadd_rn(x0[k], __dmul_rn(my_step, eps[k])) : 0.0;
+                if (k < d) st_prop[lane * d + k] = x[k];
+            }
+            st_logu[lane] = logu;
+            double inv = (t == 0) ? 1.0 / p.tau_sq : 1.0 / p.sigma_sq;
+            int zc = 0;
+            if (p.prior != 0) {
+                zc = p.z[((size_t)c * T + t) * n + jl];
+                inv = 1.0 / p.sigma[(size_t)c * p.K + zc];
+            }
+            st_inv[lane] = inv;
+            st_zc[lane] = zc;
+            double nn = 0.0, no = 0.0;
+            if (t < T - 1) {
+                double xnx[DM];
+                const volatile double *q = Xchain + ((size_t)(t + 1) * n + jl) * d;
+#pragma unroll
+                for (int k = 0; k < DM; k++) xnx[k] = (k < d) ? q[k] : 0.0;
+                nn = prior_next<DM>(p, c, t, jl, x, xnx);
+                no = prior_next<DM>(p, c, t, jl, x0, xnx);
+            }
+            st_nn[lane] = nn;
+            st_no[lane] = no;
+        }
+        __syncthreads();
+        const int jend = (n - jb) < 32 ? (n - jb) : 32;
+        if (warp > 0) {
+            // ---------------- compute warps: pairwise sums, one node ahead of the decisions ------
+            for (int jj = 0; jj < jend; jj++) {
+                const int j = jb + jj;
+                while (s_decided < j - 1) { /* nodes < j-1 must be final; node j-1 is left out */ }
+                __threadfence_block();
+                double x[DM], x0[DM];
+                load_pos<DM>(st_prop + jj * d, d, x);
+                load_pos<DM>(Xt + (size_t)j * d, d, x0);
+                if (j + 1 < n && (warp - 1) == 0 && lane * 32 < p.net.W) {
+                    const size_t o = ((size_t)t * n + j + 1) * p.net.W + lane * 32;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(p.net.rowbits + o));
+                    if (LK == kDirected) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.net.colbits + o));
+                }
+                double ll_new, ll_old;
+                node_loglik2<LK, DM>(p.net, Xt, rinv, c, t, j, x, x0, b0, b1, lane, ll_new, ll_old,
+                                     p.flags, warp - 1, ncomp, j - 1);
+                if (lane == 0) {
+                    double *pp = part + ((j & 1) * nwarps + warp) * 2;
+                    pp[0] = ll_new; pp[1] = ll_old;
+                    __threadfence_block();
+                    done[warp] = j + 1;
+                }
+                __syncwarp();
+            }
+        } else {
+            // ---------------- control warp: finish node j while node j+1 is being summed --------
+            for (int jj = 0; jj < jend; jj++) {
+                const int j = jb + jj;
+                double x[DM], x0[DM];
+                load_pos<DM>(st_prop + jj * d, d, x);
+                load_pos<DM>(Xt + (size_t)j * d, d, x0);
+                double tn = 0.0, to = 0.0;
+                if (j > 0) pair_term2<LK, DM>(p.net, Xt, rinv, t, j, j - 1, x, x0, b0, b1, tn, to);
+                double xp[DM];
+#pragma unroll
+                for (int k = 0; k < DM; k++) xp[k] = 0.0;
+                if (t > 0) {
+                    while (prog[t - 1] <= j) { /* spin on the L2-resident flag of slice t-1 */ }
+                    __threadfence();
+                    const volatile double *q = Xchain + ((size_t)(t - 1) * n + j) * d;
+#pragma unroll
+                    for (int k = 0; k < DM; k++) if (k < d) xp[k] = q[k];
+                }
+                const double inv = st_inv[jj];
+                const int zc = st_zc[jj];
+                const double pr_new = prior_prev<DM>(p, c, t, zc, inv, x, xp);
+                const double pr_old = prior_prev<DM>(p, c, t, zc, inv, x0, xp);
+                // the row sums of the compute warps, in warp order, then the deferred dyad
+                for (int w = 1; w < nwarps; w++)
+                    while (done[w] <= j) { /* spin */ }
+                __threadfence_block();
+                double ll_new = 0.0, ll_old = 0.0;
+                const double *pp = part + (j & 1) * nwarps * 2;
+                for (int w = 1; w < nwarps; w++) { ll_new += pp[w * 2]; ll_old += pp[w * 2 + 1]; }
+                ll_new += tn;
+                ll_old += to;
+                double lp_new = __dsub_rn(ll_new, pr_new), lp_old = __dsub_rn(ll_old, pr_old);
+                if (t < T - 1) {
+                    lp_new = __dsub_rn(lp_new, st_nn[jj]);
+                    lp_old = __dsub_rn(lp_old, st_no[jj]);
+                }
+                const double ratio = __dsub_rn(lp_new, lp_old);
+                const int acc = (st_logu[jj] >= ratio) ? 0 : 1;
+                const bool me = lane == jj;
+                my_acc = me ? acc : my_acc;
+                nonfinite |= me && (!(ratio == ratio) || ratio - ratio != 0.0);
+                if (me) {
+                    if (acc) {
+#pragma unroll
+                        for (int k = 0; k < DM; k++)
+                            if (k < d) {
+                                Xt[(size_t)j * d + k] = x[k];
+                                if (XS) Xg[(size_t)j * d + k] = x[k];
+                            }
+                    }
+                    if (p.ratio) p.ratio[((size_t)c * T + t) * n + j] = ratio;
+                    __threadfence_block();
+                    s_decided = j + 1;       // releases the compute warps' node j+2
+                    __threadfence();
+                    prog[t] = j + 1;         // releases slice t+1's node j
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
         if (mine) {
             metropolis_bookkeep(my_step, my_nacc, my_nsteps, my_until, p.tune, p.tune_interval,
                                 my_acc, false);
