@@ -322,7 +322,9 @@ def cpu_hot_path(name, sweeps_per_core, cores=None):
     updates = cores * sweeps_per_core * w["T"] * w["n"]
     return dict(value=updates / loop, unit="node-updates/s", cores=cores, kind=kind,
                 sweeps_per_s=cores * sweeps_per_core / loop, loop_s=loop, wall_s=wall,
-                sample="%d hot-path sweeps on each of %d cores (one chain per core), %s" % (
+                sample="%d hot-path sweeps (latent + centre + distance cache + intercept MH [+ radii MH] "
+                       "[+ label FFBS]; the reference's host-side conjugate block is NOT included, which "
+                       "favours the CPU side) on each of %d cores, one chain per core, %s" % (
                     sweeps_per_core, cores, WORKLOADS[name]["desc"]))
 
 
