@@ -396,9 +396,15 @@ def test_full_device_sweeps_are_deterministic_and_chain_independent():
     assert np.allclose(Xa.mean(axis=(1, 2)), 0, atol=1e-12)  # centred
 
 
-@pytest.mark.parametrize("T,n,d,K", [(10, 200, 2, 12),   # thread-per-node, 64 threads per CTA
-                                     (12, 70, 3, 40),    # thread-per-node, 32 threads per CTA
-                                     (20, 40, 2, 60)])   # warp-per-node fallback (T*K too large)
+@pytest.mark.parametrize("T,n,d,K", [
+    (10, 200, 2, 12),   # thread-per-node, 64 threads per CTA
+    (16, 45, 3, 7),     # K < 8 (numpy's serial sum)
+    (5, 33, 2, 8),      # K = 8 (numpy's 8-accumulator sum)
+    (9, 64, 2, 17),
+    (4, 50, 1, 32),
+    (3, 70, 2, 1),      # single component
+    (12, 70, 3, 40),    # thread-per-node, 32 threads per CTA
+    (20, 40, 2, 60)])   # warp-per-node fallback (T*K too large for the thread kernel's stage)
 def test_labels_vs_oracle_all_kernel_variants(T, n, d, K):
     """FFBS with recorded uniforms on larger random problems vs the oracle (exact labels)."""
     L = _F()
