@@ -896,7 +896,8 @@ int dlsm_sample_labels(dlsm_handle *h, const double *U)
     return DLSM_OK;
 }
 
-static int hdp_update_async(dlsm_handle *h)
+// part: 0 = whole block, 1 = emission side (mu, sigma, lambda, tau^2, b), 2 = transition side
+static int hdp_update_async(dlsm_handle *h, int part)
 {
     const dlsm_config &c = h->cfg;
     HdpParams p;
@@ -910,16 +911,25 @@ static int hdp_update_async(dlsm_handle *h)
     p.pr = h->hdp_prior;
     const size_t sbytes = (size_t)c.n_chains * (2 * c.K * c.d + c.K) * sizeof(double);
     if (!h->d_hdp_scratch) CU(h, cudaMalloc((void **)&h->d_hdp_scratch, sbytes));
-    CU(h, cudaMemsetAsync(h->d_hdp_scratch, 0, sbytes, h->stream));
+    if (part != 2) CU(h, cudaMemsetAsync(h->d_hdp_scratch, 0, sbytes, h->stream));
     p.scratch = h->d_hdp_scratch;
     p.seed = h->seed; p.sweep = h->sweep_idx[4]; p.chain_offset = (uint32_t)h->chain_offset;
     const size_t smem = hdp_smem_bytes(c.T, c.K, c.d);
     if (smem > kMaxSmem) FAIL(h, DLSM_ERR_UNSUPPORTED, "T*K*K too large for the HDP update kernel");
-    CU(h, cudaFuncSetAttribute(k_hdp_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     begin_phase(h, 1);
-    int rc = launch_simple(h, k_hdp_update, dim3(c.n_chains), dim3(128), smem, p);
+    int rc;
+    if (part == 1) {
+        CU(h, cudaFuncSetAttribute(k_hdp_update<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rc = launch_simple(h, k_hdp_update<1>, dim3(c.n_chains), dim3(128), smem, p);
+    } else if (part == 2) {
+        CU(h, cudaFuncSetAttribute(k_hdp_update<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rc = launch_simple(h, k_hdp_update<2>, dim3(c.n_chains), dim3(128), smem, p);
+    } else {
+        CU(h, cudaFuncSetAttribute(k_hdp_update<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rc = launch_simple(h, k_hdp_update<0>, dim3(c.n_chains), dim3(128), smem, p);
+    }
     end_phase(h);
-    h->sweep_idx[4] += 1;
+    if (part != 1) h->sweep_idx[4] += 1; // the emission side runs first when the block is split
     return rc;
 }
 
@@ -937,7 +947,7 @@ int dlsm_hdp_update(dlsm_handle *h)
     if (!h) return DLSM_ERR_INVALID;
     if (!h->have_hdp_prior) FAIL(h, DLSM_ERR_NOTSET, "dlsm_set_hdp_prior has not been called");
     CU(h, cudaSetDevice(h->cfg.device));
-    int rc = hdp_update_async(h);
+    int rc = hdp_update_async(h, 0);
     if (rc != DLSM_OK) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     return DLSM_OK;
@@ -961,25 +971,38 @@ int dlsm_run_sweeps(dlsm_handle *h, int32_t n_sweeps, uint32_t flags)
         // and the intercept / radii MH (full-network kernel; issue-bound) are independent: run
         // the label block on a high-priority side stream so the two overlap.
         const bool labels = h->cfg.prior == DLSM_PRIOR_MIXTURE && !(flags & 8u);
+        const bool hdp = labels && h->have_hdp_prior && !(flags & 16u);
         cudaStream_t main_stream = h->stream;
         if (labels) {
+            // side stream: FFBS -> emission side of the HDP block (what the next latent sweep
+            // needs) -> [event] -> transition side, which only the next label draw needs and which
+            // therefore overlaps the next latent sweep as well
             CU(h, cudaEventRecord(h->ev_fork, main_stream));
             CU(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
             h->stream = h->side_stream;
             const bool timing = h->timing;
             h->timing = false; // phase events belong to the main stream
             rc = labels_async(h, nullptr, nullptr, 1);
-            if (rc == DLSM_OK && h->have_hdp_prior && !(flags & 16u)) rc = hdp_update_async(h);
+            if (rc == DLSM_OK && hdp) rc = hdp_update_async(h, 1);
+            if (rc == DLSM_OK) {
+                cudaError_t ce = cudaEventRecord(h->ev_join, h->side_stream);
+                if (ce != cudaSuccess) rc = DLSM_ERR_CUDA;
+            }
+            if (rc == DLSM_OK && hdp) rc = hdp_update_async(h, 2);
             h->timing = timing;
             h->stream = main_stream;
             if (rc != DLSM_OK) return rc;
-            CU(h, cudaEventRecord(h->ev_join, h->side_stream));
         }
         if (!(flags & 2u) && (rc = intercepts_async(h, nullptr, nullptr, nullptr, nullptr)) != DLSM_OK) return rc;
         if (h->cfg.is_directed && !(flags & 4u) &&
             (rc = radii_async(h, true, nullptr, nullptr, nullptr)) != DLSM_OK)
             return rc;
         if (labels) CU(h, cudaStreamWaitEvent(main_stream, h->ev_join, 0));
+    }
+    if (h->cfg.prior == DLSM_PRIOR_MIXTURE && !(flags & 8u)) {
+        // the last transition-side update is still in flight on the side stream
+        CU(h, cudaEventRecord(h->ev_fork, h->side_stream));
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_fork, 0));
     }
     return check_flags(h);
 }

@@ -106,9 +106,18 @@ __device__ inline double concentration(Stream &g, double alpha, double n_cluster
     return g.gamma(m_shape) / m_scale;
 }
 
+// The block factorises into two groups that are conditionally independent given the labels and
+// the positions, so they are separate launches (PART) that may run in either order or concurrently:
+//   PART 1 "emission side":  mu_k, sigma_k, lambda, tau^2 (mvp), b        -- what the NEXT latent
+//                            sweep needs; reads X, z, nk
+//   PART 2 "transition side": tables m, overrides, beta, w0, w[t,k], gamma, alpha_init, alpha, kappa
+//                            -- only the next label draw needs them; reads the counts
+//   PART 0 = both.
 // dynamic smem: ints m[T*K*K], wover[T*K]; doubles mbar[K], newbeta[K], scal[16]
+template <int PART>
 __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
 {
+    constexpr bool kEmis = PART != 2, kTrans = PART != 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = p.T, n = p.n, d = p.d, K = p.K, KK = K * K;
     const int c = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
@@ -130,6 +139,7 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
     const double lm = p.lambda[c];
     uint32_t site = 0; // families of streams get disjoint site ranges
 
+    if (kTrans) {
     // ---- 1. table counts m (sample_auxillary.py:6-28) ----
     for (int cell = tid; cell < T * KK; cell += nt) {
         const int t = cell / KK, j = (cell / K) % K, k = cell % K;
@@ -196,6 +206,47 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
         for (int k = 0; k < K; k++) s += w[row * K + k];
         for (int k = 0; k < K; k++) w[row * K + k] /= s;
     }
+    // alpha + kappa auxiliary variables, one (t >= 1, j) row per thread (hdp_lpcm.py:998-1012)
+    if (tid < 16) scal[tid] = 0.0;
+    __syncthreads();
+    const double ak_old = alpha + kappa;
+    for (int row = K + tid; row < T * K; row += nt) {
+        double nd = 0.0, mrow = 0.0;
+        for (int k = 0; k < K; k++) { nd += cnt[row * K + k]; mrow += m[row * K + k]; }
+        atomicAdd(&scal[5], mrow);                  // sum of m[1:]
+        atomicAdd(&scal[6], (double)wov[row]);      // override successes
+        if (nd > 0.0) {
+            Stream g(p.seed, site + row, p.sweep, chain);
+            atomicAdd(&scal[2], (double)g.bernoulli(nd / (nd + ak_old)));
+            atomicAdd(&scal[3], log(g.beta(ak_old + 1.0, nd)));
+            atomicAdd(&scal[4], mrow);
+        }
+    }
+    site += T * K;
+    __syncthreads();
+    // one scalar task per thread, each on its own Philox stream (no long serial gamma chains)
+    if (tid == 3) { // gamma (:977-983)
+        Stream g(p.seed, site + 3, p.sweep, chain);
+        double ncl = 0.0, nsm = 0.0;
+        for (int k = 0; k < K; k++) { ncl += mbar[k] > 0.0; nsm += mbar[k]; }
+        hy[0] = concentration(g, gamma0, ncl, nsm, p.pr.gamma_prior_shape, p.pr.gamma_prior_rate);
+    } else if (tid == 4) { // alpha_init (:989-995)
+        Stream g(p.seed, site + 4, p.sweep, chain);
+        double m00 = 0.0;
+        for (int k = 0; k < K; k++) m00 += m[k];
+        hy[1] = concentration(g, alpha_init, m00, (double)n, p.pr.alpha_init_shape, p.pr.alpha_init_rate);
+    } else if (tid == 5) { // alpha + kappa and rho (:1010-1023)
+        Stream g(p.seed, site + 5, p.sweep, chain);
+        const double ak = g.gamma(p.pr.alpha_kappa_shape + scal[4] - scal[2]) /
+                          (p.pr.alpha_kappa_rate - scal[3]);
+        const double rho = g.beta(8.0 + scal[6], scal[5] - scal[6] + 2.0);
+        hy[3] = ak * rho;
+        hy[2] = ak - ak * rho;
+    }
+    for (int k = tid; k < K; k += nt) beta[k] = nbeta[k];
+    } // kTrans
+    site = 2 * T * KK + 2 * T * K + K + 8; // fixed layout of the Philox site ranges, whatever PART runs
+    if (kEmis) {
     // ---- 5. cluster means (hdp_lpcm.py:901-919) ----
     // per-cluster sums: one pass, native fp64 RED.ADD into a zeroed global scratch (shared-memory
     // fp64 atomics are CAS loops and K hot addresses under 128 threads is a CAS storm)
@@ -250,10 +301,9 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
     }
     site += K;
     __syncthreads();
-    // ---- 7-9. lambda, hyper-priors, concentration parameters: sums in parallel, then one scalar
-    //           task per thread (each on its own Philox stream) so no thread runs a long serial
-    //           chain of gamma rejection loops ----
-    if (tid < 16) scal[tid] = 0.0;
+    // ---- 7. lambda ~ truncated normal on (0,1); 8. the tau^2 and b hyper-priors ----
+    __syncthreads();
+    if (tid < 2) scal[tid] = 0.0;
     __syncthreads();
     {
         double ml = 0.0, sl = 0.0;
@@ -270,23 +320,8 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
         sl = warp_sum(sl);
         if ((tid & 31) == 0) { atomicAdd(&scal[0], ml); atomicAdd(&scal[1], sl); }
     }
-    // alpha + kappa auxiliary variables, one (t >= 1, j) row per thread (hdp_lpcm.py:998-1012)
-    const double ak_old = alpha + kappa;
-    for (int row = K + tid; row < T * K; row += nt) {
-        double nd = 0.0, mrow = 0.0;
-        for (int k = 0; k < K; k++) { nd += cnt[row * K + k]; mrow += m[row * K + k]; }
-        atomicAdd(&scal[5], mrow);                  // sum of m[1:]
-        atomicAdd(&scal[6], (double)wov[row]);      // override successes
-        if (nd > 0.0) {
-            Stream g(p.seed, site + row, p.sweep, chain);
-            atomicAdd(&scal[2], (double)g.bernoulli(nd / (nd + ak_old)));
-            atomicAdd(&scal[3], log(g.beta(ak_old + 1.0, nd)));
-            atomicAdd(&scal[4], mrow);
-        }
-    }
-    site += T * K;
     __syncthreads();
-    if (tid == 0) { // lambda ~ truncated normal on (0, 1) (hdp_lpcm.py:940-954), inverse-cdf draw
+    if (tid == 0) { // (hdp_lpcm.py:940-954), inverse-cdf draw
         Stream g(p.seed, site + 0, p.sweep, chain);
         const double var = 1.0 / (1.0 / p.pr.lambda_variance_prior + scal[1]);
         const double mean = (scal[0] + p.pr.lambda_prior / p.pr.lambda_variance_prior) * var;
@@ -309,25 +344,8 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
             for (int k = 0; k < K; k++) sc += 0.5 * (1.0 / sigma[k]);
             hy[5] = g.gamma(0.5 * (p.pr.c0 + K * p.pr.a)) / sc;
         }
-    } else if (tid == 3) { // gamma (:977-983)
-        Stream g(p.seed, site + 3, p.sweep, chain);
-        double ncl = 0.0, nsm = 0.0;
-        for (int k = 0; k < K; k++) { ncl += mbar[k] > 0.0; nsm += mbar[k]; }
-        hy[0] = concentration(g, gamma0, ncl, nsm, p.pr.gamma_prior_shape, p.pr.gamma_prior_rate);
-    } else if (tid == 4) { // alpha_init (:989-995)
-        Stream g(p.seed, site + 4, p.sweep, chain);
-        double m00 = 0.0;
-        for (int k = 0; k < K; k++) m00 += m[k];
-        hy[1] = concentration(g, alpha_init, m00, (double)n, p.pr.alpha_init_shape, p.pr.alpha_init_rate);
-    } else if (tid == 5) { // alpha + kappa and rho (:1010-1023)
-        Stream g(p.seed, site + 5, p.sweep, chain);
-        const double ak = g.gamma(p.pr.alpha_kappa_shape + scal[4] - scal[2]) /
-                          (p.pr.alpha_kappa_rate - scal[3]);
-        const double rho = g.beta(8.0 + scal[6], scal[5] - scal[6] + 2.0);
-        hy[3] = ak * rho;
-        hy[2] = ak - ak * rho;
     }
-    for (int k = tid; k < K; k += nt) beta[k] = nbeta[k];
+    } // kEmis
 }
 
 inline size_t hdp_smem_bytes(int T, int K, int d)
