@@ -52,6 +52,8 @@ struct dlsm_handle {
     int *d_progress = nullptr;      // [C][T] wavefront flags of the CTA-per-slice sweep
     unsigned int *d_ticket = nullptr;
     double *d_hdp_scratch = nullptr; // [C][2*K*d + K]
+    double *d_ffbs_stage = nullptr;  // global (L2-resident) stage of the thread-per-node label kernel
+    size_t ffbs_stage_bytes = 0;
     int sweep_mode = 0;             // 0 auto, 1 CTA per chain, 2 CTA per (chain, slice)
     bool no_pipeline = false;       // DLSM_SWEEP_MODE=slice-plain: the unpipelined slice kernel
     // rng
@@ -513,7 +515,7 @@ void dlsm_destroy(dlsm_handle *h)
     void *ptrs[] = {h->rowbits, h->colbits, h->deg, h->in_edges, h->out_edges, h->ctrl_in,
                     h->ctrl_out, h->rinv, h->d_eps, h->d_logu, h->d_ratio, h->d_out, h->d_acc,
                     h->d_partial, h->d_bvar, h->d_prop, h->d_ll2, h->d_rprop, h->d_rprop_inv,
-                    h->d_small, h->d_small_i, h->d_flags, h->d_bad, h->d_progress, h->d_ticket, h->d_hdp_scratch};
+                    h->d_small, h->d_small_i, h->d_flags, h->d_bad, h->d_progress, h->d_ticket, h->d_hdp_scratch, h->d_ffbs_stage};
     for (void *p : ptrs) cudaFree(p);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -855,7 +857,24 @@ static int labels_async(dlsm_handle *h, const double *d_U, double *lik_out, int 
     const size_t extra = ((size_t)c.K * (c.d + 2) + (size_t)c.K * c.K) * sizeof(double);
     int rc;
     begin_phase(h, 1);
-    if (per_thread * 64 + extra <= kMaxSmem / 2) {
+    // The thread-per-node kernel keeps (T*K + 2K) doubles per thread.  In shared memory that caps
+    // the SM at 227 KB / footprint threads (8 warps at cfg 2) and blocks co-resident kernels; in an
+    // L2-resident global stage ([entry][thread] per CTA, coalesced) the cap is the register file.
+    // Measured at cfg 2: 408 us (shared) vs 277 us (global).  DLSM_FFBS_SMEM=1 forces the former.
+    const size_t ctas = (size_t)((c.n + 63) / 64) * c.n_chains;
+    const size_t need = ctas * per_thread * 64;
+    if (!getenv("DLSM_FFBS_SMEM") && per_thread * 64 > 16 * 1024 && need <= ((size_t)4 << 30) &&
+        extra <= kMaxSmem) {
+        if (need > h->ffbs_stage_bytes) {
+            cudaFree(h->d_ffbs_stage);
+            h->d_ffbs_stage = nullptr;
+            CU(h, cudaMalloc((void **)&h->d_ffbs_stage, need));
+            h->ffbs_stage_bytes = need;
+        }
+        p.gstage = h->d_ffbs_stage;
+        CU(h, cudaFuncSetAttribute(k_ffbs_t<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)extra));
+        rc = launch_simple(h, k_ffbs_t<64>, dim3((c.n + 63) / 64, c.n_chains), dim3(64), extra, p);
+    } else if (per_thread * 64 + extra <= kMaxSmem / 2) {
         const size_t smem = per_thread * 64 + extra;
         CU(h, cudaFuncSetAttribute(k_ffbs_t<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rc = launch_simple(h, k_ffbs_t<64>, dim3((c.n + 63) / 64, c.n_chains), dim3(64), smem, p);

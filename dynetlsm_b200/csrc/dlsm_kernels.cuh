@@ -1365,6 +1365,7 @@ struct LabelParams {
     double *ncount;         // [C][T][K][K] out (zeroed by the caller)
     int32_t *nk;            // [C][T][K]  out (zeroed by the caller)
     double *lik_out;        // optional probe [C][n][T][K]
+    double *gstage;         // optional global stage for k_ffbs_t: (T*K + 2K) * TPB doubles per CTA
     int sample;             // 0: emission densities only
 };
 
@@ -1496,10 +1497,19 @@ __global__ void __launch_bounds__(TPB) k_ffbs_t(const LabelParams p)
     const int i = blockIdx.x * TPB + tid;
     const bool valid = i < n;
     const int ic = valid ? i : n - 1;
-    double *pm = reinterpret_cast<double *>(smem_raw);  // [T*K][TPB]
+    // The per-thread stage (T*K partial marginals + two K-vectors) lives either in shared memory
+    // (8 warps per SM at cfg 2) or, when p.gstage is set, in an L2-resident global scratch laid out
+    // [entry][thread] per CTA (coalesced), which lifts the occupancy cap.
+    double *pm, *s_mu;
+    if (p.gstage) {
+        pm = p.gstage + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ((size_t)T * K + 2 * K) * TPB;
+        s_mu = reinterpret_cast<double *>(smem_raw);
+    } else {
+        pm = reinterpret_cast<double *>(smem_raw);      // [T*K][TPB]
+        s_mu = pm + ((size_t)T * K + 2 * K) * TPB;      // [K][d]
+    }
     double *bwA = pm + (size_t)T * K * TPB;             // [K][TPB]
     double *bwB = bwA + (size_t)K * TPB;                // [K][TPB]
-    double *s_mu = bwB + (size_t)K * TPB;               // [K][d]
     double *s_ln = s_mu + (size_t)K * d;                // [K]  -(d/2) log(2 pi var)
     double *s_hv = s_ln + K;                            // [K]  0.5 * (1 / var)
     double *s_w = s_hv + K;                             // [K][K] transition weights of one step

@@ -405,8 +405,12 @@ def test_full_device_sweeps_are_deterministic_and_chain_independent():
     (3, 70, 2, 1),      # single component
     (12, 70, 3, 40),    # thread-per-node, 32 threads per CTA
     (20, 40, 2, 60)])   # warp-per-node fallback (T*K too large for the thread kernel's stage)
-def test_labels_vs_oracle_all_kernel_variants(T, n, d, K):
-    """FFBS with recorded uniforms on larger random problems vs the oracle (exact labels)."""
+@pytest.mark.parametrize("stage", ["global", "shared"])
+def test_labels_vs_oracle_all_kernel_variants(T, n, d, K, stage, monkeypatch):
+    """FFBS with recorded uniforms on larger random problems vs the oracle (exact labels); the
+    thread-per-node kernel with its stage in L2-resident global memory and in shared memory."""
+    if stage == "shared":
+        monkeypatch.setenv("DLSM_FFBS_SMEM", "1")
     L = _F()
     rng = np.random.RandomState(8)
     X = rng.randn(T, n, d)
