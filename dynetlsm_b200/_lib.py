@@ -80,7 +80,7 @@ F_X, F_INTERCEPT, F_RADII, F_Z, F_MU, F_SIGMA, F_LAMBDA, F_WEIGHTS = range(8)
 F_X_STEP, F_X_NACC, F_X_NSTEPS, F_X_UNTIL = 8, 9, 10, 11
 F_B_STEP, F_B_NACC, F_B_NSTEPS, F_B_UNTIL = 12, 13, 14, 15
 F_R_STEP, F_R_NACC, F_R_NSTEPS, F_R_UNTIL = 16, 17, 18, 19
-F_NCOUNT, F_NK, F_BETA, F_HYPER = 20, 21, 22, 23
+F_NCOUNT, F_NK, F_BETA, F_HYPER, F_LOGLIK = 20, 21, 22, 23, 24
 _INT_FIELDS = {F_Z, F_X_NACC, F_X_NSTEPS, F_X_UNTIL, F_B_NACC, F_B_NSTEPS, F_B_UNTIL, F_R_NACC,
                F_R_NSTEPS, F_R_UNTIL, F_NK}
 
@@ -205,7 +205,7 @@ class Engine(object):
                 F_X_UNTIL: (C_, T, n), F_B_STEP: (C_, 2), F_B_NACC: (C_, 2), F_B_NSTEPS: (C_, 2),
                 F_B_UNTIL: (C_, 2), F_R_STEP: (C_,), F_R_NACC: (C_,), F_R_NSTEPS: (C_,),
                 F_R_UNTIL: (C_,), F_NCOUNT: (C_, T, K, K), F_NK: (C_, T, K), F_BETA: (C_, K),
-                F_HYPER: (C_, 8)}[f]
+                F_HYPER: (C_, 8), F_LOGLIK: (C_,)}[f]
 
     def set(self, f, a):
         a = (_i32 if f in _INT_FIELDS else _f64)(a, self.shape_of(f))

@@ -118,6 +118,7 @@ size_t field_elems(const dlsm_config &c, int f)
     case DLSM_F_NK: return C * T * K;
     case DLSM_F_BETA: return C * K;
     case DLSM_F_HYPER: return K > 0 ? C * 8 : 0;
+    case DLSM_F_LOGLIK: return C;
     default: return 0;
     }
 }
@@ -337,7 +338,7 @@ int launch_simple(dlsm_handle *h, K kern, dim3 grid, dim3 block, size_t smem, A.
 }
 
 // full-network log-likelihood for two variants -> h->d_partial
-int launch_full(dlsm_handle *h, const double *rinv0, const double *rinv1)
+int launch_full(dlsm_handle *h, const double *rinv0, const double *rinv1, int nv = 2)
 {
     FullParams p;
     memset(&p, 0, sizeof(p));
@@ -351,20 +352,23 @@ int launch_full(dlsm_handle *h, const double *rinv0, const double *rinv1)
     dim3 grid(h->cfg.T * h->full_tiles, h->cfg.n_chains);
     const size_t smem = (h->lk == kCaseControl) ? 0 : (size_t)h->cfg.n * h->cfg.d * sizeof(double);
     const bool d2 = h->cfg.d == 2;
+#define LAUNCH_FULL_NV(LK, D, NV)                                                                \
+    do {                                                                                         \
+        CU(h, cudaFuncSetAttribute(k_full<LK, D, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_full<LK, D, NV><<<grid, 256, smem, h->stream>>>(p);                                    \
+    } while (0)
 #define LAUNCH_FULL(LK)                                                                          \
     do {                                                                                         \
-        if (d2) {                                                                                \
-            CU(h, cudaFuncSetAttribute(k_full<LK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            k_full<LK, 2><<<grid, 256, smem, h->stream>>>(p);                                    \
-        } else {                                                                                 \
-            CU(h, cudaFuncSetAttribute(k_full<LK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            k_full<LK, 0><<<grid, 256, smem, h->stream>>>(p);                                    \
-        }                                                                                        \
+        if (d2 && nv == 1) LAUNCH_FULL_NV(LK, 2, 1);                                             \
+        else if (d2) LAUNCH_FULL_NV(LK, 2, 2);                                                   \
+        else if (nv == 1) LAUNCH_FULL_NV(LK, 0, 1);                                              \
+        else LAUNCH_FULL_NV(LK, 0, 2);                                                           \
     } while (0)
     if (smem > kMaxSmem) FAIL(h, DLSM_ERR_UNSUPPORTED, "n too large for the exact full-network kernel");
     if (h->lk == kUndirected) LAUNCH_FULL(kUndirected);
     else if (h->lk == kDirected) LAUNCH_FULL(kDirected);
-    else LAUNCH_FULL(kCaseControl);
+    else LAUNCH_FULL_NV(kCaseControl, 0, 2); // runtime d; always both variants
+#undef LAUNCH_FULL_NV
 #undef LAUNCH_FULL
     CHECK_LAUNCH(h);
     h->ctr.kernel_launches += 1;
@@ -619,7 +623,7 @@ int dlsm_set_controls(dlsm_handle *h, const int32_t *ctrl_in, const int32_t *ctr
 int dlsm_set_state(dlsm_handle *h, int field, const void *host, size_t bytes)
 {
     if (!h || !host || field < 0 || field >= DLSM_F_COUNT_) return DLSM_ERR_INVALID;
-    if (field == DLSM_F_NCOUNT || field == DLSM_F_NK) FAIL(h, DLSM_ERR_INVALID, "read-only field");
+    if (field == DLSM_F_NCOUNT || field == DLSM_F_NK || field == DLSM_F_LOGLIK) FAIL(h, DLSM_ERR_INVALID, "read-only field");
     if (bytes != h->field_bytes[field] || bytes == 0)
         FAIL(h, DLSM_ERR_INVALID, "field %d expects %zu bytes, got %zu", field, h->field_bytes[field], bytes);
     CU(h, cudaSetDevice(h->cfg.device));
@@ -715,7 +719,7 @@ int dlsm_center(dlsm_handle *h)
 
 // device-side part of sample_intercepts; d_eps/d_logu are device pointers or null (native)
 static int intercepts_async(dlsm_handle *h, const double *d_eps, const double *d_logu,
-                            int32_t *d_acc, double *d_ratio)
+                            int32_t *d_acc, double *d_ratio, bool use_cur = false)
 {
     const int C = h->cfg.n_chains, m = h->cfg.is_directed ? 2 : 1;
     const dim3 g1((C + 127) / 128), b1(128);
@@ -737,9 +741,10 @@ static int intercepts_async(dlsm_handle *h, const double *d_eps, const double *d
         p.chain_offset = (uint32_t)h->chain_offset;
         p.site = (uint32_t)((size_t)h->cfg.T * h->cfg.n);
         p.accepted = d_acc; p.ratio = d_ratio; p.flags = h->d_flags;
+        p.ll_cur = use_cur ? F<double>(h, DLSM_F_LOGLIK) : nullptr; p.use_cur = use_cur ? 1 : 0;
         int rc = launch_simple(h, k_intercept_propose, g1, b1, 0, p);
         if (rc != DLSM_OK) return rc;
-        if ((rc = launch_full(h, h->rinv, h->rinv)) != DLSM_OK) return rc;
+        if ((rc = launch_full(h, h->rinv, h->rinv, use_cur ? 1 : 2)) != DLSM_OK) return rc;
         if ((rc = launch_simple(h, k_intercept_finalize, g1, b1, 0, p)) != DLSM_OK) return rc;
     }
     end_phase(h);
@@ -771,7 +776,7 @@ int dlsm_sample_intercepts(dlsm_handle *h, const double *eps, const double *logu
 }
 
 static int radii_async(dlsm_handle *h, bool native, const double *d_logu, int32_t *d_acc,
-                       double *d_ratio)
+                       double *d_ratio, bool use_cur = false)
 {
     const int C = h->cfg.n_chains, n = h->cfg.n;
     begin_phase(h, 1);
@@ -791,7 +796,7 @@ static int radii_async(dlsm_handle *h, bool native, const double *d_logu, int32_
     rc = launch_simple(h, k_bvar_current, dim3((C + 127) / 128), dim3(128), 0, C,
                        (const double *)F<double>(h, DLSM_F_INTERCEPT), h->d_bvar);
     if (rc != DLSM_OK) return rc;
-    if ((rc = launch_full(h, h->d_rprop_inv, h->rinv)) != DLSM_OK) return rc;
+    if ((rc = launch_full(h, h->d_rprop_inv, h->rinv, use_cur ? 1 : 2)) != DLSM_OK) return rc;
     RadiiMH p;
     memset(&p, 0, sizeof(p));
     p.C = C; p.n = n; p.nblk = h->full_nblk;
@@ -806,6 +811,7 @@ static int radii_async(dlsm_handle *h, bool native, const double *d_logu, int32_
     p.seed = h->seed; p.sweep = h->sweep_idx[kRngRadii];
     p.chain_offset = (uint32_t)h->chain_offset; p.site = site0;
     p.accepted = d_acc; p.ratio = d_ratio; p.flags = h->d_flags;
+    p.ll_cur = use_cur ? F<double>(h, DLSM_F_LOGLIK) : nullptr; p.use_cur = use_cur ? 1 : 0;
     rc = launch_simple(h, k_radii_finalize, dim3(C), dim3(256), 0, p);
     end_phase(h);
     if (native) h->sweep_idx[kRngRadii] += 1;
@@ -983,6 +989,10 @@ int dlsm_run_sweeps(dlsm_handle *h, int32_t n_sweeps, uint32_t flags)
         // the chain kernel with positions in shared memory centres them on the way out
         const bool fuse = !(flags & 1u) && !use_slice_kernel(h) && sweep_smem(h, true) <= kMaxSmem;
         p.fuse_center = fuse ? 1 : 0;
+        // the chain kernel also hands over the full-network log-likelihood of the state it leaves
+        // behind, so the intercept / radii MH below evaluates only its proposals
+        const bool use_cur = !use_slice_kernel(h) && h->lk != kCaseControl && !getenv("DLSM_NO_LLCUR");
+        p.ll_cur = use_cur ? F<double>(h, DLSM_F_LOGLIK) : nullptr;
         if ((rc = launch_sweep(h, p)) != DLSM_OK) return rc;
         h->sweep_idx[kRngLatent] += 1;
         if (!(flags & 1u) && !fuse && (rc = center_async(h)) != DLSM_OK) return rc;
@@ -1012,9 +1022,9 @@ int dlsm_run_sweeps(dlsm_handle *h, int32_t n_sweeps, uint32_t flags)
             h->stream = main_stream;
             if (rc != DLSM_OK) return rc;
         }
-        if (!(flags & 2u) && (rc = intercepts_async(h, nullptr, nullptr, nullptr, nullptr)) != DLSM_OK) return rc;
+        if (!(flags & 2u) && (rc = intercepts_async(h, nullptr, nullptr, nullptr, nullptr, use_cur)) != DLSM_OK) return rc;
         if (h->cfg.is_directed && !(flags & 4u) &&
-            (rc = radii_async(h, true, nullptr, nullptr, nullptr)) != DLSM_OK)
+            (rc = radii_async(h, true, nullptr, nullptr, nullptr, use_cur)) != DLSM_OK)
             return rc;
         if (labels) CU(h, cudaStreamWaitEvent(main_stream, h->ev_join, 0));
     }

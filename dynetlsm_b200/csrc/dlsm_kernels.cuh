@@ -52,6 +52,7 @@ struct SweepParams {
     double *ratio;             // optional [C][T][n]
     unsigned int *flags;       // bit0 non-finite ratio, bit1 case-control out-of-bounds quirk
     int fuse_center;           // k_sweep (positions in shared memory): centre before the write-back
+    double *ll_cur;            // optional [C]: full-network log-likelihood of the post-sweep state
 };
 
 // latent dimension: a compile-time constant in the specialised (D == 2) instantiations
@@ -79,13 +80,18 @@ __device__ __forceinline__ double vmask(bool v) { return __hiloint2double(v ? 0x
 // Per-node pairwise sums for the proposal (xn) and the current position (xo) of node j in slice
 // t, executed by one warp.  Returns the two log-likelihoods (warp-uniform).
 // ---------------------------------------------------------------------------------------------
-template <int LK, int DM>
+// LO (needs nteam == 1, skip < 0): also return, per lane, the part of both sums that comes from
+// i < j (lo_new / lo_old, NOT reduced over the warp).  Summed over the nodes of a slice with the accepted variant picked each
+// time, these give the full-network log-likelihood of the post-sweep state for free: the dyad
+// {i, j}, i < j, is last evaluated when j is updated, with x_i already final.
+template <int LK, int DM, bool LO = false>
 __device__ __forceinline__ void node_loglik2(const NetView &net, const double *Xt /* [n][d] */,
                                              const double *rinv /* [n] */, int chain, int t, int j,
                                              const double (&xn)[DM], const double (&xo)[DM],
                                              double b0, double b1, int lane, double &ll_new,
                                              double &ll_old, unsigned int *flags, int wteam = 0,
-                                             int nteam = 1, int skip = -1)
+                                             int nteam = 1, int skip = -1, double *lo_new = nullptr,
+                                             double *lo_old = nullptr)
 {
     // skip: a second index left out of the sums (the pipelined slice kernel adds that pair later)
     // wteam / nteam: this warp's rank in, and the size of, the team of warps that shares the row.
@@ -111,10 +117,18 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
             const double eo0 = b0 - fast_dist<DM>(xa, xo, d);
             const double en1 = b0 - fast_dist<DM>(xb, xn, d);
             const double eo1 = b0 - fast_dist<DM>(xb, xo, d);
-            an = fma(v0, logit_term(y0, en0), an);
-            ao = fma(v0, logit_term(y0, eo0), ao);
-            an2 = fma(v1, logit_term(y1, en1), an2);
-            ao2 = fma(v1, logit_term(y1, eo1), ao2);
+            const double tn0 = logit_term(y0, en0), to0 = logit_term(y0, eo0);
+            const double tn1 = logit_term(y1, en1), to1 = logit_term(y1, eo1);
+            if (LO && (unsigned)(j - base) < 64u) {
+                // the one trip that straddles j: everything accumulated so far is i < j
+                const double l0 = vmask(i0 < j), l1 = vmask(i1 < j);
+                *lo_new = fma(l0, tn0, fma(l1, tn1, an + an2));
+                *lo_old = fma(l0, to0, fma(l1, to1, ao + ao2));
+            }
+            an = fma(v0, tn0, an);
+            ao = fma(v0, to0, ao);
+            an2 = fma(v1, tn1, an2);
+            ao2 = fma(v1, to1, ao2);
         }
         ll_new = an + an2;
         ll_old = ao + ao2;
@@ -140,6 +154,11 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
                               logit_term(y_ij, eta_directed(b0, b1, dn, rj, ri));
             const double to = logit_term(y_ji, eta_directed(b0, b1, dd, ri, rj)) +
                               logit_term(y_ij, eta_directed(b0, b1, dd, rj, ri));
+            if (LO && (unsigned)(j - base) < 32u) {
+                const double l = vmask(i < j);
+                *lo_new = fma(l, tn, an);
+                *lo_old = fma(l, to, ao);
+            }
             an = fma(v, tn, an);
             ao = fma(v, to, ao);
         }
@@ -343,6 +362,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
     const uint32_t chain_id = (uint32_t)c + p.chain_offset;
     bool nonfinite = false;
 
+    double full_acc = 0.0; // lower-triangle terms of this warp's slices at the kept states
     for (int t = warp; t < T; t += nwarps) {
         double *Xt = Xc + (size_t)t * n * d;
         for (int jb = 0; jb < n; jb += 32) {
@@ -403,9 +423,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(p.net.rowbits + o));
                     if (LK == kDirected) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.net.colbits + o));
                 }
-                double ll_new, ll_old;
-                node_loglik2<LK, DM>(p.net, Xt, rinv, c, t, j, x, x0, b0, b1, lane, ll_new, ll_old,
-                                     p.flags);
+                double ll_new, ll_old, lo_n = 0.0, lo_o = 0.0;
+                if (LK != kCaseControl)
+                    node_loglik2<LK, DM, true>(p.net, Xt, rinv, c, t, j, x, x0, b0, b1, lane, ll_new,
+                                               ll_old, p.flags, 0, 1, -1, &lo_n, &lo_o);
+                else
+                    node_loglik2<LK, DM>(p.net, Xt, rinv, c, t, j, x, x0, b0, b1, lane, ll_new, ll_old,
+                                         p.flags);
 
                 double xp[DM];
 #pragma unroll
@@ -429,6 +453,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
                 const int acc = (st_logu[jj] >= ratio) ? 0 : 1; // metropolis.py:50 (NaN accepts)
                 const bool me = lane == jj;
                 my_acc = me ? acc : my_acc;
+                full_acc += acc ? lo_n : lo_o; // this lane's share of the dyads {i < j} at the kept state
                 nonfinite |= me && (!(ratio == ratio) || ratio - ratio != 0.0);
                 if (me) {
                     if (acc) {
@@ -452,6 +477,18 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
         }
     }
     if (nonfinite) atomicOr(p.flags, 1u);
+    if (p.ll_cur) { // full-network log-likelihood of the post-sweep state, summed in warp order
+        full_acc = warp_sum(full_acc);
+        __syncthreads();
+        double *wsum = stage_base; // the staging area is free now
+        if (lane == 0) wsum[warp] = full_acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double sacc = 0.0;
+            for (int w = 0; w < nwarps; w++) sacc += wsum[w];
+            p.ll_cur[c] = sacc;
+        }
+    }
     if (XS) {
         __syncthreads();
         if (p.fuse_center) {
@@ -984,7 +1021,9 @@ struct FullParams {
     unsigned int *flags;
 };
 
-template <int LK, int D>
+// NV = 2: proposal and current variants; NV = 1: proposal only (the device loop tracks the current
+// state's log-likelihood itself, see SweepParams::ll_cur)
+template <int LK, int D, int NV>
 __global__ void __launch_bounds__(256) k_full(const FullParams p)
 {
     constexpr int DM = (D == 0) ? kMaxD : D;
@@ -1044,7 +1083,7 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
                     if (LK == kUndirected) {
                         const double y = ymask(__ldg(p.net.rowbits + wo), bcol & 31);
                         a0 = fma(v, logit_term(y, b00 - dist), a0);
-                        a1 = fma(v, logit_term(y, b10 - dist), a1);
+                        if (NV == 2) a1 = fma(v, logit_term(y, b10 - dist), a1);
                     } else {
                         const double y_ab = ymask(__ldg(p.net.rowbits + wo), bcol & 31);
                         const double y_ba = ymask(__ldg(p.net.colbits + wo), bcol & 31);
@@ -1052,8 +1091,9 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
                         const double s0 = r0[bcol], s1 = r1[bcol];
                         a0 = fma(v, logit_term(y_ab, eta_directed(b00, b01, dist, s0, q0)) +
                                         logit_term(y_ba, eta_directed(b00, b01, dist, q0, s0)), a0);
-                        a1 = fma(v, logit_term(y_ab, eta_directed(b10, b11, dist, s1, q1)) +
-                                        logit_term(y_ba, eta_directed(b10, b11, dist, q1, s1)), a1);
+                        if (NV == 2)
+                            a1 = fma(v, logit_term(y_ab, eta_directed(b10, b11, dist, s1, q1)) +
+                                            logit_term(y_ba, eta_directed(b10, b11, dist, q1, s1)), a1);
                     }
                 }
             }
@@ -1134,6 +1174,8 @@ struct ScalarMH {
     int32_t *accepted;       // optional [C][m]
     double *ratio;           // optional [C][m]
     double *ll_out;          // optional [C][2] (variant sums) for probes
+    double *ll_cur;          // optional [C]: log-likelihood of the current state, kept up to date
+    int use_cur;             // 1: partial[..][1] was not computed, take ll_cur instead
     unsigned int *flags;
 };
 
@@ -1166,6 +1208,7 @@ __global__ void k_intercept_finalize(const ScalarMH p)
     double s0 = 0.0, s1 = 0.0;
     const double *pp = p.partial + (size_t)c * p.nblk * 2;
     for (int b = 0; b < p.nblk; b++) { s0 += pp[b * 2]; s1 += pp[b * 2 + 1]; }
+    if (p.use_cur) s1 = p.ll_cur[c];
     const double x = p.prop[c], x0 = p.intercept[c * 2 + p.which];
     // sample_coefficients.py:39-41 / :84-85:  loglik -= (x - prior) ** 2 / (2 * variance)
     double df = __dsub_rn(x, p.prior_mean);
@@ -1179,6 +1222,7 @@ __global__ void k_intercept_finalize(const ScalarMH p)
                               kRngIntercept, 0).a);
     const int acc = (logu >= ratio) ? 0 : 1;
     if (acc) p.intercept[c * 2 + p.which] = x;
+    if (p.ll_cur) p.ll_cur[c] = acc ? s0 : s1;
     const int o = c * 2 + p.which;
     double st = p.step[o];
     int na = p.nacc[o], ns = p.nsteps[o], un = p.until[o];
@@ -1225,6 +1269,8 @@ struct RadiiMH {
     int32_t *accepted;
     double *ratio;
     unsigned int *flags;
+    double *ll_cur;                  // optional [C], see ScalarMH
+    int use_cur;
 };
 
 __device__ __forceinline__ double block_sum(double v, double *sh)
@@ -1262,6 +1308,7 @@ __global__ void __launch_bounds__(256) k_radii_finalize(const RadiiMH p)
         double s0 = 0.0, s1 = 0.0;
         const double *pp = p.partial + (size_t)c * p.nblk * 2;
         for (int b = 0; b < p.nblk; b++) { s0 += pp[b * 2]; s1 += pp[b * 2 + 1]; }
+        if (p.use_cur) s1 = p.ll_cur[c];
         const double lf = -(sl_f - lgamma(sa_f)) + sx_f;
         const double lb = -(sl_b - lgamma(sa_b)) + sx_b;
         const double ratio = (s0 - s1) + (lf - lb);
@@ -1270,6 +1317,7 @@ __global__ void __launch_bounds__(256) k_radii_finalize(const RadiiMH p)
         else logu = log(philox_u2(p.seed, p.site, p.sweep, (uint32_t)c + p.chain_offset, kRngRadii, 0).a);
         const int acc = (logu >= ratio) ? 0 : 1;
         s_acc = acc;
+        if (p.ll_cur) p.ll_cur[c] = acc ? s0 : s1;
         double st = s;
         int na = p.nacc[c], ns = p.nsteps[c], un = p.until[c];
         metropolis_bookkeep(st, na, ns, un, p.tune, p.tune_interval, acc, true);

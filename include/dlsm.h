@@ -92,6 +92,8 @@ typedef enum {
     DLSM_F_NK = 21,        /* i32 (C,T,K)    occupancy counts of the last label draw (read-only) */
     DLSM_F_BETA = 22,      /* f64 (C,K)      global HDP weights beta */
     DLSM_F_HYPER = 23,     /* f64 (C,8)      [gamma, alpha_init, alpha, kappa, mean_variance_prior, b, 0, 0] */
+    DLSM_F_LOGLIK = 24,    /* f64 (C,)       network log-likelihood of the state dlsm_run_sweeps left behind,
+                              tracked by the device loop (read-only; dense likelihoods, chain kernel) */
     DLSM_F_COUNT_
 } dlsm_field;
 

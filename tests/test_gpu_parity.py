@@ -448,3 +448,43 @@ def test_fused_centring_equals_sweep_then_center():
     b.sweep_latent()                               # same Philox draws
     b.center()
     assert np.array_equal(a.get(L.F_X), b.get(L.F_X))
+
+
+@pytest.mark.parametrize("directed", [False, True])
+@pytest.mark.parametrize("T,n,d", [(6, 90, 2), (3, 64, 3), (11, 33, 2), (2, 200, 2)])
+def test_tracked_loglik_matches_full_kernel(T, n, d, directed, monkeypatch):
+    """The chain kernel accumulates the full-network log-likelihood of the state it leaves behind
+    (dyad {i<j} taken from node j's update) and the intercept / radii MH keeps it current, so that
+    k_full only evaluates proposals inside dlsm_run_sweeps.  The tracked value must equal a fresh
+    full-network evaluation (network_likelihoods.py:26-33, directed_likelihoods_fast.pyx:185-205)
+    to summation-order accuracy, and the chain must be the one the two-variant path produces."""
+    L = _F()
+    monkeypatch.setenv("DLSM_SWEEP_MODE", "chain")
+    rng, X, Y = _synthetic(T, n, d, directed, seed=31)
+    C_ = 3
+
+    def make():
+        e = _engine(T=T, n=n, d=d, n_chains=C_, is_directed=directed)
+        e.set_network(Y)
+        e.set(L.F_X, np.stack([X, X * 1.1, X - 0.03]))
+        e.set(L.F_INTERCEPT, np.tile([[0.6, 0.3]], (C_, 1)))
+        if directed:
+            e.set(L.F_RADII, np.random.RandomState(2).dirichlet(np.ones(n) * 4, size=C_))
+        e.set_tuner(0.15)
+        e.set_rng(17)
+        return e
+    a = make()
+    for sweeps in (1, 3):
+        a.run_sweeps(sweeps)
+        tracked = a.get(L.F_LOGLIK)
+        fresh = a.loglik_full()
+        assert np.all(np.isfinite(tracked))
+        assert np.allclose(tracked, fresh, rtol=1e-11, atol=0)
+    monkeypatch.setenv("DLSM_NO_LLCUR", "1")
+    b = make()
+    b.run_sweeps(4)
+    # same Philox draws; acceptance tests differ only in the rounding of ll(current)
+    assert np.array_equal(a.get(L.F_X), b.get(L.F_X))
+    assert np.array_equal(a.get(L.F_INTERCEPT), b.get(L.F_INTERCEPT))
+    if directed:
+        assert np.array_equal(a.get(L.F_RADII), b.get(L.F_RADII))
