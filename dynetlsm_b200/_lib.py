@@ -60,6 +60,11 @@ class HdpPrior(C.Structure):
                 ("resample_mvp", C.c_int32), ("resample_b", C.c_int32)]
 
 
+class TraceSpec(C.Structure):
+    _fields_ = [("fields_all", C.c_uint32), ("fields_first", C.c_uint32), ("thin", C.c_int32),
+                ("want_logp", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
 class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("node_updates", C.c_uint64),
                 ("sweeps", C.c_uint64), ("latent_ms", C.c_double), ("other_ms", C.c_double),
@@ -74,6 +79,7 @@ EXPORTS = [
     "dlsm_sweep_latent", "dlsm_center", "dlsm_sample_intercepts", "dlsm_sample_radii",
     "dlsm_sample_labels", "dlsm_set_hdp_prior", "dlsm_hdp_update", "dlsm_run_sweeps", "dlsm_loglik_partial", "dlsm_loglik_full",
     "dlsm_gaussian_likelihood", "dlsm_debug_set_counts", "dlsm_debug_draws", "dlsm_enable_timing", "dlsm_get_counters",
+    "dlsm_logp", "dlsm_set_procrustes_ref", "dlsm_procrustes", "dlsm_run_traced", "dlsm_host_alloc", "dlsm_host_free",
 ]
 
 F_X, F_INTERCEPT, F_RADII, F_Z, F_MU, F_SIGMA, F_LAMBDA, F_WEIGHTS = range(8)
@@ -126,6 +132,12 @@ def load():
     L.dlsm_debug_draws.argtypes = [vp, dp, dp]
     L.dlsm_enable_timing.argtypes = [vp, C.c_int]
     L.dlsm_get_counters.argtypes = [vp, C.POINTER(Counters)]
+    L.dlsm_logp.argtypes = [vp, dp]
+    L.dlsm_set_procrustes_ref.argtypes = [vp, dp]
+    L.dlsm_procrustes.argtypes = [vp]
+    L.dlsm_run_traced.argtypes = [vp, C.c_int32, C.c_uint32, C.POINTER(TraceSpec), C.POINTER(vp), dp]
+    L.dlsm_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.dlsm_host_free.argtypes = [vp]
     _lib = L
     return L
 
@@ -150,6 +162,34 @@ def _i32(a, shape=None):
     if shape is not None and a.shape != tuple(shape):
         raise ValueError("expected shape %s, got %s" % (tuple(shape), a.shape))
     return a
+
+
+N_FIELDS = 25
+
+
+class _Pinned(object):
+    """Page-locked host block (dlsm_host_alloc) exposed through the array interface."""
+
+    def __init__(self, nbytes):
+        L = load()
+        self._L, self.ptr = L, C.c_void_p()
+        if L.dlsm_host_alloc(max(int(nbytes), 1), C.byref(self.ptr)) != 0:
+            raise MemoryError("dlsm_host_alloc(%d) failed" % nbytes)
+        self.__array_interface__ = {"shape": (max(int(nbytes), 1),), "typestr": "|u1",
+                                    "data": (self.ptr.value, False), "version": 3}
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and self.ptr.value:
+            self._L.dlsm_host_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array in page-locked memory (freed when the last view goes away)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    raw = np.asarray(_Pinned(nbytes))
+    return raw[:nbytes].view(dtype).reshape(shape)
 
 
 class Engine(object):
@@ -329,6 +369,50 @@ class Engine(object):
         flags = (1 if skip_center else 0) | (2 if skip_intercepts else 0) | \
                 (4 if skip_radii else 0) | (8 if skip_labels else 0) | (16 if skip_hdp else 0)
         self._ck(self.L.dlsm_run_sweeps(self.h, int(n_sweeps), flags))
+
+    def run_traced(self, n_sweeps, fields_all=(), fields_first=(), thin=1, logp=True, pinned=False,
+                   skip_center=False, skip_intercepts=False, skip_radii=False, skip_labels=False,
+                   skip_hdp=False):
+        """``n_sweeps`` sweeps on the device, recording every ``thin``-th state: returns
+        ``{field: array (records, C or 1, ...)}`` plus ``"logp": (records, C)``.  The copies to the
+        host overlap the following sweeps."""
+        flags = (1 if skip_center else 0) | (2 if skip_intercepts else 0) | \
+                (4 if skip_radii else 0) | (8 if skip_labels else 0) | (16 if skip_hdp else 0)
+        rec = int(n_sweeps) // int(thin)
+        alloc = pinned_empty if pinned else np.empty
+        spec = TraceSpec(thin=int(thin), want_logp=int(bool(logp)))
+        dst = (C.c_void_p * N_FIELDS)()
+        out = {}
+        for group, first in ((fields_all, False), (fields_first, True)):
+            for f in group:
+                shp = self.shape_of(f)
+                a = alloc((rec, 1 if first else shp[0]) + tuple(shp[1:]),
+                          np.int32 if f in _INT_FIELDS else np.float64)
+                out[f] = a
+                dst[f] = a.ctypes.data
+                if first:
+                    spec.fields_first |= 1 << f
+                else:
+                    spec.fields_all |= 1 << f
+        lp = alloc((rec, self.C), np.float64) if logp else None
+        self._ck(self.L.dlsm_run_traced(self.h, int(n_sweeps), flags, C.byref(spec), dst, _dp(lp)))
+        if logp:
+            out["logp"] = lp
+        return out
+
+    def logp(self):
+        out = np.empty((self.C,))
+        self._ck(self.L.dlsm_logp(self.h, _dp(out)))
+        return out
+
+    def set_procrustes_ref(self, Xref):
+        if Xref is None:
+            self._ck(self.L.dlsm_set_procrustes_ref(self.h, None))
+        else:
+            self._ck(self.L.dlsm_set_procrustes_ref(self.h, _dp(_f64(Xref, self.shape_of(F_X)))))
+
+    def procrustes(self):
+        self._ck(self.L.dlsm_procrustes(self.h))
 
     # -- probes --------------------------------------------------------------------------
     def loglik_partial(self):

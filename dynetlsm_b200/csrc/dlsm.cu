@@ -3,6 +3,7 @@
 #include "../../include/dlsm.h"
 #include "dlsm_kernels.cuh"
 #include "dlsm_hdp.cuh"
+#include "dlsm_trace.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -51,7 +52,6 @@ struct dlsm_handle {
     int full_tiles = 1, full_nblk = 1;
     int *d_progress = nullptr;      // [C][T] wavefront flags of the CTA-per-slice sweep
     unsigned int *d_ticket = nullptr;
-    double *d_hdp_scratch = nullptr; // [C][2*K*d + K]
     double *d_ffbs_stage = nullptr;  // global (L2-resident) stage of the thread-per-node label kernel
     size_t ffbs_stage_bytes = 0;
     int sweep_mode = 0;             // 0 auto, 1 CTA per chain, 2 CTA per (chain, slice)
@@ -61,6 +61,25 @@ struct dlsm_handle {
     uint32_t sweep_idx[5] = {0, 0, 0, 0, 0};
     dlsm_hdp_prior hdp_prior;
     bool have_hdp_prior = false;
+    // trace pipeline (dlsm_run_traced): two device chunks of trace_R records each, drained to the
+    // host on copy_stream while the next chunk fills
+    cudaStream_t copy_stream = nullptr;
+    struct TraceChunk {
+        void *dev[DLSM_F_COUNT_] = {nullptr};
+        double *logp = nullptr;
+        cudaEvent_t filled = nullptr, drained = nullptr;
+        bool used = false;
+    } chunk[2];
+    size_t trace_slot[DLSM_F_COUNT_] = {0}; // bytes one record takes per field (0 = not traced)
+    uint32_t trace_all = 0, trace_first = 0;
+    int trace_logp = 0, trace_R = 0;
+    double *d_logp = nullptr;       // [C] scratch of dlsm_logp
+    double *d_proc_ref = nullptr;   // [C][T][n][d] reference configuration of the in-loop Procrustes
+    bool have_proc_ref = false;
+    // developer timeline (DLSM_TIMELINE=1): start/stop of every launch group on its own stream
+    struct TimelineEntry { cudaEvent_t a, b; const char *name; };
+    std::vector<TimelineEntry> timeline;
+    bool timeline_on = false;
     // counters
     dlsm_counters ctr;
     bool timing = false;
@@ -124,6 +143,38 @@ size_t field_elems(const dlsm_config &c, int f)
 }
 
 template <typename T> T *F(dlsm_handle *h, int f) { return static_cast<T *>(h->field[f]); }
+
+void tl_begin(dlsm_handle *h, const char *name)
+{
+    if (!h->timeline_on) return;
+    dlsm_handle::TimelineEntry e;
+    cudaEventCreate(&e.a);
+    cudaEventCreate(&e.b);
+    e.name = name;
+    cudaEventRecord(e.a, h->stream);
+    h->timeline.push_back(e);
+}
+
+void tl_end(dlsm_handle *h)
+{
+    if (!h->timeline_on || h->timeline.empty()) return;
+    cudaEventRecord(h->timeline.back().b, h->stream);
+}
+
+void tl_dump(dlsm_handle *h)
+{
+    if (!h->timeline_on || h->timeline.empty()) return;
+    cudaDeviceSynchronize();
+    for (auto &e : h->timeline) {
+        float t0 = 0.f, t1 = 0.f;
+        cudaEventElapsedTime(&t0, h->timeline.front().a, e.a);
+        cudaEventElapsedTime(&t1, h->timeline.front().a, e.b);
+        fprintf(stderr, "[dlsm timeline] %-18s %9.1f -> %9.1f us  (%7.1f)\n", e.name, t0 * 1e3, t1 * 1e3,
+                (t1 - t0) * 1e3);
+    }
+    for (auto &e : h->timeline) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    h->timeline.clear();
+}
 
 void begin_phase(dlsm_handle *h, int cat)
 {
@@ -406,6 +457,19 @@ int update_rinv(dlsm_handle *h)
                          (const double *)F<double>(h, DLSM_F_RADII), h->rinv, total);
 }
 
+void free_trace(dlsm_handle *h)
+{
+    for (auto &ch : h->chunk) {
+        for (int f = 0; f < DLSM_F_COUNT_; f++) { cudaFree(ch.dev[f]); ch.dev[f] = nullptr; }
+        cudaFree(ch.logp); ch.logp = nullptr;
+        if (ch.filled) cudaEventDestroy(ch.filled);
+        if (ch.drained) cudaEventDestroy(ch.drained);
+        ch.filled = ch.drained = nullptr;
+        ch.used = false;
+    }
+    h->trace_R = 0;
+}
+
 } // namespace
 
 extern "C" {
@@ -451,6 +515,7 @@ int dlsm_create(const dlsm_config *cfg, dlsm_handle **out)
     h->lk = cfg->likelihood == DLSM_LIK_CASE_CONTROL ? kCaseControl
                                                       : (cfg->is_directed ? kDirected : kUndirected);
     h->W = ((cfg->n + 31) / 32 + 3) / 4 * 4;
+    h->timeline_on = getenv("DLSM_TIMELINE") != nullptr;
     if (const char *m = getenv("DLSM_SWEEP_MODE")) // chain | slice: override the heuristic (tests, tuning)
     {
         h->sweep_mode = !strcmp(m, "chain") ? 1 : ((!strcmp(m, "slice") || !strcmp(m, "slice-plain")) ? 2 : 0);
@@ -519,8 +584,12 @@ void dlsm_destroy(dlsm_handle *h)
     void *ptrs[] = {h->rowbits, h->colbits, h->deg, h->in_edges, h->out_edges, h->ctrl_in,
                     h->ctrl_out, h->rinv, h->d_eps, h->d_logu, h->d_ratio, h->d_out, h->d_acc,
                     h->d_partial, h->d_bvar, h->d_prop, h->d_ll2, h->d_rprop, h->d_rprop_inv,
-                    h->d_small, h->d_small_i, h->d_flags, h->d_bad, h->d_progress, h->d_ticket, h->d_hdp_scratch, h->d_ffbs_stage};
+                    h->d_small, h->d_small_i, h->d_flags, h->d_bad, h->d_progress, h->d_ticket, h->d_ffbs_stage};
     for (void *p : ptrs) cudaFree(p);
+    free_trace(h);
+    cudaFree(h->d_logp);
+    cudaFree(h->d_proc_ref);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -869,7 +938,40 @@ static int labels_async(dlsm_handle *h, const double *d_U, double *lik_out, int 
     // Measured at cfg 2: 408 us (shared) vs 277 us (global).  DLSM_FFBS_SMEM=1 forces the former.
     const size_t ctas = (size_t)((c.n + 63) / 64) * c.n_chains;
     const size_t need = ctas * per_thread * 64;
-    if (!getenv("DLSM_FFBS_SMEM") && per_thread * 64 > 16 * 1024 && need <= ((size_t)4 << 30) &&
+    // K <= 16: the register-resident kernel (persistent grid, stage indexed by CTA slot)
+    const size_t tables = ((size_t)c.T * c.K * c.K + (size_t)c.K * (c.d + 2)) * sizeof(double);
+    const char *ffbs_env = getenv("DLSM_FFBS"); // "thread" / "warp": force an older mapping (tests)
+    if (c.K <= 16 && tables <= 64 * 1024 && !ffbs_env && !getenv("DLSM_FFBS_SMEM")) {
+        const int KC = (c.K + 3) / 4 * 4;
+        const int tiles = (c.n + 63) / 64;
+        const long items = (long)tiles * c.n_chains;
+        auto launch = [&](auto kern) -> int {
+            CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tables));
+            int per_sm = 0;
+            CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 64, tables));
+            if (per_sm < 1) per_sm = 1;
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
+            long grid = (long)sms * per_sm;
+            if (grid > items) grid = items;
+            const size_t stage = (size_t)grid * c.T * c.K * 64 * sizeof(double);
+            if (stage > h->ffbs_stage_bytes) {
+                cudaFree(h->d_ffbs_stage);
+                h->d_ffbs_stage = nullptr;
+                CU(h, cudaMalloc((void **)&h->d_ffbs_stage, stage));
+                h->ffbs_stage_bytes = stage;
+            }
+            p.gstage = h->d_ffbs_stage;
+            return launch_simple(h, kern, dim3((unsigned)grid), dim3(64), tables, p, tiles, (int)items);
+        };
+        if (c.d == 2) {
+            rc = KC == 4 ? launch(k_ffbs_r<4, 2>) : KC == 8 ? launch(k_ffbs_r<8, 2>)
+                 : KC == 12 ? launch(k_ffbs_r<12, 2>) : launch(k_ffbs_r<16, 2>);
+        } else {
+            rc = KC == 4 ? launch(k_ffbs_r<4, 0>) : KC == 8 ? launch(k_ffbs_r<8, 0>)
+                 : KC == 12 ? launch(k_ffbs_r<12, 0>) : launch(k_ffbs_r<16, 0>);
+        }
+    } else if (!(ffbs_env && !strcmp(ffbs_env, "warp")) && !getenv("DLSM_FFBS_SMEM") && per_thread * 64 > 16 * 1024 && need <= ((size_t)4 << 30) &&
         extra <= kMaxSmem) {
         if (need > h->ffbs_stage_bytes) {
             cudaFree(h->d_ffbs_stage);
@@ -880,11 +982,11 @@ static int labels_async(dlsm_handle *h, const double *d_U, double *lik_out, int 
         p.gstage = h->d_ffbs_stage;
         CU(h, cudaFuncSetAttribute(k_ffbs_t<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)extra));
         rc = launch_simple(h, k_ffbs_t<64>, dim3((c.n + 63) / 64, c.n_chains), dim3(64), extra, p);
-    } else if (per_thread * 64 + extra <= kMaxSmem / 2) {
+    } else if (!(ffbs_env && !strcmp(ffbs_env, "warp")) && per_thread * 64 + extra <= kMaxSmem / 2) {
         const size_t smem = per_thread * 64 + extra;
         CU(h, cudaFuncSetAttribute(k_ffbs_t<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rc = launch_simple(h, k_ffbs_t<64>, dim3((c.n + 63) / 64, c.n_chains), dim3(64), smem, p);
-    } else if (per_thread * 32 + extra <= kMaxSmem) {
+    } else if (!(ffbs_env && !strcmp(ffbs_env, "warp")) && per_thread * 32 + extra <= kMaxSmem) {
         const size_t smem = per_thread * 32 + extra;
         CU(h, cudaFuncSetAttribute(k_ffbs_t<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rc = launch_simple(h, k_ffbs_t<32>, dim3((c.n + 31) / 32, c.n_chains), dim3(32), smem, p);
@@ -934,12 +1036,9 @@ static int hdp_update_async(dlsm_handle *h, int part)
     p.lambda = F<double>(h, DLSM_F_LAMBDA); p.beta = F<double>(h, DLSM_F_BETA);
     p.weights = F<double>(h, DLSM_F_WEIGHTS); p.hyper = F<double>(h, DLSM_F_HYPER);
     p.pr = h->hdp_prior;
-    const size_t sbytes = (size_t)c.n_chains * (2 * c.K * c.d + c.K) * sizeof(double);
-    if (!h->d_hdp_scratch) CU(h, cudaMalloc((void **)&h->d_hdp_scratch, sbytes));
-    if (part != 2) CU(h, cudaMemsetAsync(h->d_hdp_scratch, 0, sbytes, h->stream));
-    p.scratch = h->d_hdp_scratch;
     p.seed = h->seed; p.sweep = h->sweep_idx[4]; p.chain_offset = (uint32_t)h->chain_offset;
     const size_t smem = hdp_smem_bytes(c.T, c.K, c.d);
+    p.bin_rows = getenv("DLSM_HDP_SEGMENTED") ? 0 : hdp_bin_rows(c.K, c.d);
     if (smem > kMaxSmem) FAIL(h, DLSM_ERR_UNSUPPORTED, "T*K*K too large for the HDP update kernel");
     begin_phase(h, 1);
     int rc;
@@ -978,61 +1077,335 @@ int dlsm_hdp_update(dlsm_handle *h)
     return DLSM_OK;
 }
 
+static int procrustes_async(dlsm_handle *h);
+
+// One sweep of the estimator loop body, everything asynchronous.  *tracked tells whether
+// DLSM_F_LOGLIK holds the network log-likelihood of the state this sweep leaves behind.
+static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
+{
+    int rc;
+    SweepParams p = sweep_params(h);
+    const bool procrustes = h->have_proc_ref && !(flags & 1u);
+    // the chain kernel with positions in shared memory centres them on the way out
+    const bool fuse = !(flags & 1u) && !procrustes && !use_slice_kernel(h) &&
+                      sweep_smem(h, true) <= kMaxSmem;
+    p.fuse_center = fuse ? 1 : 0;
+    // the chain kernel also hands over the full-network log-likelihood of the state it leaves
+    // behind, so the intercept / radii MH below evaluates only its proposals
+    const bool use_cur = !use_slice_kernel(h) && h->lk != kCaseControl && !getenv("DLSM_NO_LLCUR");
+    p.ll_cur = use_cur ? F<double>(h, DLSM_F_LOGLIK) : nullptr;
+    if (tracked) *tracked = use_cur;
+    tl_begin(h, "sweep");
+    if ((rc = launch_sweep(h, p)) != DLSM_OK) return rc;
+    tl_end(h);
+    h->sweep_idx[kRngLatent] += 1;
+    if (procrustes && (rc = procrustes_async(h)) != DLSM_OK) return rc; // lsm.py:495-498
+    if (!(flags & 1u) && !fuse && (rc = center_async(h)) != DLSM_OK) return rc;
+    // After centring, the label block (FFBS -> HDP update; latency-bound, few warps per SM)
+    // and the intercept / radii MH (full-network kernel; issue-bound) are independent: run
+    // the label block on a high-priority side stream so the two overlap.
+    const bool labels = h->cfg.prior == DLSM_PRIOR_MIXTURE && !(flags & 8u);
+    const bool hdp = labels && h->have_hdp_prior && !(flags & 16u);
+    cudaStream_t main_stream = h->stream;
+    if (labels) {
+        // side stream: FFBS -> emission side of the HDP block (what the next latent sweep
+        // needs) -> [event] -> transition side, which only the next label draw needs and which
+        // therefore overlaps the next latent sweep as well
+        CU(h, cudaEventRecord(h->ev_fork, main_stream));
+        CU(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        h->stream = h->side_stream;
+        const bool timing = h->timing;
+        h->timing = false; // phase events belong to the main stream
+        tl_begin(h, "ffbs");
+        rc = labels_async(h, nullptr, nullptr, 1);
+        tl_end(h);
+        tl_begin(h, "hdp emission");
+        if (rc == DLSM_OK && hdp) rc = hdp_update_async(h, 1);
+        tl_end(h);
+        if (rc == DLSM_OK) {
+            cudaError_t ce = cudaEventRecord(h->ev_join, h->side_stream);
+            if (ce != cudaSuccess) rc = DLSM_ERR_CUDA;
+        }
+        tl_begin(h, "hdp transition");
+        if (rc == DLSM_OK && hdp) rc = hdp_update_async(h, 2);
+        tl_end(h);
+        h->timing = timing;
+        h->stream = main_stream;
+        if (rc != DLSM_OK) return rc;
+    }
+    tl_begin(h, "intercepts");
+    if (!(flags & 2u) && (rc = intercepts_async(h, nullptr, nullptr, nullptr, nullptr, use_cur)) != DLSM_OK) return rc;
+    tl_end(h);
+    if (h->cfg.is_directed && !(flags & 4u) &&
+        (rc = radii_async(h, true, nullptr, nullptr, nullptr, use_cur)) != DLSM_OK)
+        return rc;
+    if (labels) CU(h, cudaStreamWaitEvent(main_stream, h->ev_join, 0));
+    return DLSM_OK;
+}
+
+// the transition-side HDP update of the last sweep may still be in flight on the side stream
+static int join_side_stream(dlsm_handle *h, uint32_t flags)
+{
+    if (h->cfg.prior == DLSM_PRIOR_MIXTURE && !(flags & 8u)) {
+        CU(h, cudaEventRecord(h->ev_fork, h->side_stream));
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_fork, 0));
+    }
+    return DLSM_OK;
+}
+
 int dlsm_run_sweeps(dlsm_handle *h, int32_t n_sweeps, uint32_t flags)
 {
     if (!h || n_sweeps < 0) return DLSM_ERR_INVALID;
     CU(h, cudaSetDevice(h->cfg.device));
     int rc = need_inputs(h);
     if (rc != DLSM_OK) return rc;
+    for (int s = 0; s < n_sweeps; s++)
+        if ((rc = one_sweep(h, flags, nullptr)) != DLSM_OK) return rc;
+    if ((rc = join_side_stream(h, flags)) != DLSM_OK) return rc;
+    tl_dump(h);
+    return check_flags(h);
+}
+
+// joint log-posterior of the current state -> out_dev[C]; ll_tracked: DLSM_F_LOGLIK is current
+static int logp_async(dlsm_handle *h, double *out_dev, bool ll_tracked)
+{
+    const dlsm_config &c = h->cfg;
+    int rc;
+    LogpParams p;
+    memset(&p, 0, sizeof(p));
+    if (ll_tracked) {
+        p.ll = F<double>(h, DLSM_F_LOGLIK); p.ll_stride = 1;
+    } else {
+        rc = launch_simple(h, k_bvar_current, dim3((c.n_chains + 127) / 128), dim3(128), 0, c.n_chains,
+                           (const double *)F<double>(h, DLSM_F_INTERCEPT), h->d_bvar);
+        if (rc != DLSM_OK) return rc;
+        if ((rc = launch_full(h, h->rinv, h->rinv, 1)) != DLSM_OK) return rc;
+        rc = launch_simple(h, k_sum_partials, dim3((c.n_chains + 127) / 128), dim3(128), 0, c.n_chains,
+                           h->full_nblk, (const double *)h->d_partial, h->d_ll2);
+        if (rc != DLSM_OK) return rc;
+        p.ll = h->d_ll2; p.ll_stride = 2;
+    }
+    p.C = c.n_chains; p.T = c.T; p.n = c.n; p.d = c.d; p.K = c.K; p.m = c.is_directed ? 2 : 1;
+    p.mixture = c.prior == DLSM_PRIOR_MIXTURE; p.directed = c.is_directed;
+    p.X = F<double>(h, DLSM_F_X); p.intercept = F<double>(h, DLSM_F_INTERCEPT);
+    p.tau_sq = h->hy.tau_sq; p.sigma_sq = h->hy.sigma_sq;
+    p.ic_prior0 = h->hy.intercept_prior[0]; p.ic_prior1 = h->hy.intercept_prior[1];
+    p.ic_var = h->hy.intercept_variance_prior;
+    if (p.mixture) {
+        if (!h->have_hdp_prior) FAIL(h, DLSM_ERR_NOTSET, "dlsm_set_hdp_prior has not been called");
+        p.mu = F<double>(h, DLSM_F_MU); p.sigma = F<double>(h, DLSM_F_SIGMA);
+        p.lambda = F<double>(h, DLSM_F_LAMBDA); p.weights = F<double>(h, DLSM_F_WEIGHTS);
+        p.beta = F<double>(h, DLSM_F_BETA); p.hyper = F<double>(h, DLSM_F_HYPER);
+        p.z = F<int32_t>(h, DLSM_F_Z);
+        p.pr = h->hdp_prior;
+    }
+    p.out = out_dev;
+    return launch_simple(h, k_logp, dim3(c.n_chains), dim3(256), 0, p);
+}
+
+int dlsm_logp(dlsm_handle *h, double *out)
+{
+    if (!h || !out) return DLSM_ERR_INVALID;
+    CU(h, cudaSetDevice(h->cfg.device));
+    int rc = need_inputs(h);
+    if (rc != DLSM_OK) return rc;
+    const size_t C = h->cfg.n_chains;
+    if (!h->d_logp) CU(h, cudaMalloc((void **)&h->d_logp, C * 8));
+    if ((rc = logp_async(h, h->d_logp, false)) != DLSM_OK) return rc;
+    if ((rc = download(h, out, h->d_logp, C * 8)) != DLSM_OK) return rc;
+    return check_flags(h);
+}
+
+static int procrustes_async(dlsm_handle *h)
+{
+    const dlsm_config &c = h->cfg;
+    double *X = F<double>(h, DLSM_F_X);
+    begin_phase(h, 1);
+    int rc;
+    if (c.d == 2) rc = launch_simple(h, k_procrustes<2>, dim3(c.n_chains), dim3(256), 0, c.T, c.n, c.d, X, (const double *)h->d_proc_ref);
+    else if (c.d == 3) rc = launch_simple(h, k_procrustes<3>, dim3(c.n_chains), dim3(256), 0, c.T, c.n, c.d, X, (const double *)h->d_proc_ref);
+    else rc = launch_simple(h, k_procrustes<kMaxD>, dim3(c.n_chains), dim3(256), 0, c.T, c.n, c.d, X, (const double *)h->d_proc_ref);
+    end_phase(h);
+    return rc;
+}
+
+int dlsm_set_procrustes_ref(dlsm_handle *h, const double *Xref)
+{
+    if (!h) return DLSM_ERR_INVALID;
+    CU(h, cudaSetDevice(h->cfg.device));
+    if (!Xref) { h->have_proc_ref = false; return DLSM_OK; }
+    const size_t bytes = h->field_bytes[DLSM_F_X];
+    if (!h->d_proc_ref) CU(h, cudaMalloc((void **)&h->d_proc_ref, bytes));
+    int rc = upload(h, h->d_proc_ref, Xref, bytes);
+    if (rc != DLSM_OK) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->have_proc_ref = true;
+    return DLSM_OK;
+}
+
+int dlsm_procrustes(dlsm_handle *h)
+{
+    if (!h) return DLSM_ERR_INVALID;
+    if (!h->have_proc_ref) FAIL(h, DLSM_ERR_NOTSET, "dlsm_set_procrustes_ref has not been called");
+    CU(h, cudaSetDevice(h->cfg.device));
+    int rc = procrustes_async(h);
+    if (rc != DLSM_OK) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return DLSM_OK;
+}
+
+int dlsm_host_alloc(size_t bytes, void **out)
+{
+    if (!out || bytes == 0) return DLSM_ERR_INVALID;
+    *out = nullptr;
+    if (cudaHostAlloc(out, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        g_create_error = "cudaHostAlloc failed";
+        return DLSM_ERR_CUDA;
+    }
+    return DLSM_OK;
+}
+
+int dlsm_host_free(void *p)
+{
+    if (!p) return DLSM_OK;
+    return cudaFreeHost(p) == cudaSuccess ? DLSM_OK : DLSM_ERR_CUDA;
+}
+
+// (re)allocate the two device trace chunks for a trace specification
+static int prepare_trace(dlsm_handle *h, const dlsm_trace_spec *sp, int n_records)
+{
+    const dlsm_config &c = h->cfg;
+    size_t slot[DLSM_F_COUNT_] = {0};
+    size_t per_record = sp->want_logp ? (size_t)c.n_chains * 8 : 0;
+    int nseg = 0;
+    for (int f = 0; f < DLSM_F_COUNT_; f++) {
+        const bool all = (sp->fields_all >> f) & 1u, first = (sp->fields_first >> f) & 1u;
+        if (!all && !first) continue;
+        if (h->field_bytes[f] == 0) FAIL(h, DLSM_ERR_INVALID, "traced field %d does not exist in this configuration", f);
+        slot[f] = all ? h->field_bytes[f] : h->field_bytes[f] / c.n_chains;
+        per_record += slot[f];
+        nseg++;
+    }
+    if (nseg > kMaxSnapSeg) FAIL(h, DLSM_ERR_INVALID, "at most %d traced fields", kMaxSnapSeg);
+    if (per_record == 0) { free_trace(h); return DLSM_OK; }
+    size_t free_b = 0, total_b = 0;
+    CU(h, cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = (size_t)512 << 20; // per chunk
+    if (budget > free_b / 8) budget = free_b / 8;
+    if (const char *e = getenv("DLSM_TRACE_CHUNK_BYTES")) budget = (size_t)atoll(e);
+    long R = (long)(budget / per_record);
+    if (R < 1) R = 1;
+    if (R > 1024) R = 1024;
+    if (R > n_records) R = n_records > 0 ? n_records : 1;
+    bool same = h->trace_R >= R && h->trace_all == sp->fields_all && h->trace_first == sp->fields_first &&
+                h->trace_logp == (sp->want_logp ? 1 : 0);
+    if (same) return DLSM_OK;
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (h->copy_stream) CU(h, cudaStreamSynchronize(h->copy_stream));
+    free_trace(h);
+    if (!h->copy_stream) CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (auto &ch : h->chunk) {
+        for (int f = 0; f < DLSM_F_COUNT_; f++)
+            if (slot[f]) CU(h, cudaMalloc(&ch.dev[f], slot[f] * (size_t)R));
+        if (sp->want_logp) CU(h, cudaMalloc((void **)&ch.logp, (size_t)c.n_chains * 8 * (size_t)R));
+        CU(h, cudaEventCreateWithFlags(&ch.filled, cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&ch.drained, cudaEventDisableTiming));
+    }
+    memcpy(h->trace_slot, slot, sizeof(slot));
+    h->trace_all = sp->fields_all; h->trace_first = sp->fields_first;
+    h->trace_logp = sp->want_logp ? 1 : 0;
+    h->trace_R = (int)R;
+    return DLSM_OK;
+}
+
+// device chunk -> host destination records [first, first + count), on the copy stream
+static int drain_chunk(dlsm_handle *h, int which, size_t first, int count, void *const *dst, double *logp_dst)
+{
+    auto &ch = h->chunk[which];
+    CU(h, cudaStreamWaitEvent(h->copy_stream, ch.filled, 0));
+    for (int f = 0; f < DLSM_F_COUNT_; f++) {
+        if (!h->trace_slot[f]) continue;
+        char *to = static_cast<char *>(dst[f]) + first * h->trace_slot[f];
+        CU(h, cudaMemcpyAsync(to, ch.dev[f], h->trace_slot[f] * (size_t)count, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+    if (h->trace_logp) {
+        const size_t rb = (size_t)h->cfg.n_chains * 8;
+        CU(h, cudaMemcpyAsync(reinterpret_cast<char *>(logp_dst) + first * rb, ch.logp, rb * (size_t)count,
+                              cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+    CU(h, cudaEventRecord(ch.drained, h->copy_stream));
+    return DLSM_OK;
+}
+
+int dlsm_run_traced(dlsm_handle *h, int32_t n_sweeps, uint32_t flags, const dlsm_trace_spec *sp,
+                    void *const *dst, double *logp_dst)
+{
+    if (!h || !sp || n_sweeps < 0) return DLSM_ERR_INVALID;
+    if (sp->thin < 1) FAIL(h, DLSM_ERR_INVALID, "thin must be >= 1");
+    if (sp->fields_all & sp->fields_first) FAIL(h, DLSM_ERR_INVALID, "a field is traced either for all chains or for the first");
+    CU(h, cudaSetDevice(h->cfg.device));
+    int rc = need_inputs(h);
+    if (rc != DLSM_OK) return rc;
+    const int n_records = n_sweeps / sp->thin;
+    for (int f = 0; f < DLSM_F_COUNT_; f++)
+        if ((((sp->fields_all | sp->fields_first) >> f) & 1u) && n_records > 0 && (!dst || !dst[f]))
+            FAIL(h, DLSM_ERR_INVALID, "no destination for traced field %d", f);
+    if (sp->want_logp && n_records > 0 && !logp_dst) FAIL(h, DLSM_ERR_INVALID, "no destination for the log-posterior trace");
+    if ((rc = prepare_trace(h, sp, n_records)) != DLSM_OK) return rc;
+    const bool tracing = h->trace_R > 0 && n_records > 0;
+    const int R = h->trace_R;
+    int cur = 0, fill = 0;          // chunk being filled, records in it
+    size_t done = 0;                // records handed to earlier chunks
+    int pending = -1, pending_n = 0; // filled chunk not yet drained (one chunk of lookahead keeps
+    size_t pending_first = 0;        // the launch queue busy while a pageable copy blocks the host)
+    for (auto &ch : h->chunk) ch.used = false;
     for (int s = 0; s < n_sweeps; s++) {
-        SweepParams p = sweep_params(h);
-        // the chain kernel with positions in shared memory centres them on the way out
-        const bool fuse = !(flags & 1u) && !use_slice_kernel(h) && sweep_smem(h, true) <= kMaxSmem;
-        p.fuse_center = fuse ? 1 : 0;
-        // the chain kernel also hands over the full-network log-likelihood of the state it leaves
-        // behind, so the intercept / radii MH below evaluates only its proposals
-        const bool use_cur = !use_slice_kernel(h) && h->lk != kCaseControl && !getenv("DLSM_NO_LLCUR");
-        p.ll_cur = use_cur ? F<double>(h, DLSM_F_LOGLIK) : nullptr;
-        if ((rc = launch_sweep(h, p)) != DLSM_OK) return rc;
-        h->sweep_idx[kRngLatent] += 1;
-        if (!(flags & 1u) && !fuse && (rc = center_async(h)) != DLSM_OK) return rc;
-        // After centring, the label block (FFBS -> HDP update; latency-bound, few warps per SM)
-        // and the intercept / radii MH (full-network kernel; issue-bound) are independent: run
-        // the label block on a high-priority side stream so the two overlap.
-        const bool labels = h->cfg.prior == DLSM_PRIOR_MIXTURE && !(flags & 8u);
-        const bool hdp = labels && h->have_hdp_prior && !(flags & 16u);
-        cudaStream_t main_stream = h->stream;
-        if (labels) {
-            // side stream: FFBS -> emission side of the HDP block (what the next latent sweep
-            // needs) -> [event] -> transition side, which only the next label draw needs and which
-            // therefore overlaps the next latent sweep as well
-            CU(h, cudaEventRecord(h->ev_fork, main_stream));
-            CU(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-            h->stream = h->side_stream;
-            const bool timing = h->timing;
-            h->timing = false; // phase events belong to the main stream
-            rc = labels_async(h, nullptr, nullptr, 1);
-            if (rc == DLSM_OK && hdp) rc = hdp_update_async(h, 1);
-            if (rc == DLSM_OK) {
-                cudaError_t ce = cudaEventRecord(h->ev_join, h->side_stream);
-                if (ce != cudaSuccess) rc = DLSM_ERR_CUDA;
-            }
-            if (rc == DLSM_OK && hdp) rc = hdp_update_async(h, 2);
-            h->timing = timing;
-            h->stream = main_stream;
-            if (rc != DLSM_OK) return rc;
-        }
-        if (!(flags & 2u) && (rc = intercepts_async(h, nullptr, nullptr, nullptr, nullptr, use_cur)) != DLSM_OK) return rc;
-        if (h->cfg.is_directed && !(flags & 4u) &&
-            (rc = radii_async(h, true, nullptr, nullptr, nullptr, use_cur)) != DLSM_OK)
+        bool tracked = false;
+        if ((rc = one_sweep(h, flags, &tracked)) != DLSM_OK) return rc;
+        if (!tracing || (s + 1) % sp->thin != 0) continue;
+        if ((rc = join_side_stream(h, flags)) != DLSM_OK) return rc;
+        auto &ch = h->chunk[cur];
+        if (fill == 0 && ch.used) CU(h, cudaStreamWaitEvent(h->stream, ch.drained, 0));
+        if (h->trace_logp &&
+            (rc = logp_async(h, ch.logp + (size_t)fill * h->cfg.n_chains, tracked)) != DLSM_OK)
             return rc;
-        if (labels) CU(h, cudaStreamWaitEvent(main_stream, h->ev_join, 0));
+        SnapParams sn;
+        memset(&sn, 0, sizeof(sn));
+        size_t max_words = 0;
+        for (int f = 0; f < DLSM_F_COUNT_; f++) {
+            if (!h->trace_slot[f]) continue;
+            sn.src[sn.nseg] = static_cast<const uint32_t *>(h->field[f]);
+            sn.dst[sn.nseg] = reinterpret_cast<uint32_t *>(static_cast<char *>(ch.dev[f]) + (size_t)fill * h->trace_slot[f]);
+            sn.words[sn.nseg] = h->trace_slot[f] / 4;
+            if (sn.words[sn.nseg] > max_words) max_words = sn.words[sn.nseg];
+            sn.nseg++;
+        }
+        if (sn.nseg) {
+            size_t blocks = (max_words / 4 + 255) / 256;
+            if (blocks < 1) blocks = 1;
+            if (blocks > 592) blocks = 592; // 4 CTAs per SM
+            if ((rc = launch_simple(h, k_snapshot, dim3((unsigned)blocks, sn.nseg), dim3(256), 0, sn)) != DLSM_OK) return rc;
+        }
+        fill++;
+        if (fill == R) {
+            CU(h, cudaEventRecord(ch.filled, h->stream));
+            ch.used = true;
+            if (pending >= 0 && (rc = drain_chunk(h, pending, pending_first, pending_n, dst, logp_dst)) != DLSM_OK) return rc;
+            pending = cur; pending_n = fill; pending_first = done;
+            done += fill; fill = 0; cur ^= 1;
+        }
     }
-    if (h->cfg.prior == DLSM_PRIOR_MIXTURE && !(flags & 8u)) {
-        // the last transition-side update is still in flight on the side stream
-        CU(h, cudaEventRecord(h->ev_fork, h->side_stream));
-        CU(h, cudaStreamWaitEvent(h->stream, h->ev_fork, 0));
+    if (tracing) {
+        if (pending >= 0 && (rc = drain_chunk(h, pending, pending_first, pending_n, dst, logp_dst)) != DLSM_OK) return rc;
+        if (fill > 0) {
+            CU(h, cudaEventRecord(h->chunk[cur].filled, h->stream));
+            h->chunk[cur].used = true;
+            if ((rc = drain_chunk(h, cur, done, fill, dst, logp_dst)) != DLSM_OK) return rc;
+        }
+        CU(h, cudaStreamSynchronize(h->copy_stream));
     }
+    if ((rc = join_side_stream(h, flags)) != DLSM_OK) return rc;
     return check_flags(h);
 }
 

@@ -28,10 +28,14 @@ struct Stream {
         has_spare = true;
         return u.a;
     }
+    double nspare = 0.0;
+    bool has_nspare = false;
     __device__ double normal()
     {
-        double z0, z1;
-        box_muller(philox_u2(seed, site, sweep, chain, kRngHdp, blk++), z0, z1);
+        if (has_nspare) { has_nspare = false; return nspare; }
+        double z0;
+        box_muller(philox_u2(seed, site, sweep, chain, kRngHdp, blk++), z0, nspare);
+        has_nspare = true;
         return z0;
     }
     // Marsaglia & Tsang (2000); shape < 1 boosted by U^(1/shape)
@@ -49,7 +53,9 @@ struct Stream {
             double v = 1.0 + cc * z;
             if (v <= 0.0) continue;
             v = v * v * v;
-            if (log(uniform()) < 0.5 * z * z + dd - dd * v + dd * log(v)) return boost * dd * v;
+            const double u = uniform(), z2 = z * z;
+            if (u < 1.0 - 0.0331 * z2 * z2) return boost * dd * v; // squeeze: no logarithms
+            if (log(u) < 0.5 * z2 + dd - dd * v + dd * log(v)) return boost * dd * v;
         }
         return boost * dd;
     }
@@ -88,10 +94,10 @@ struct HdpParams {
     const double *ncount;   // [C][T][K][K]
     const int32_t *nk;      // [C][T][K]
     double *mu, *sigma, *lambda, *beta, *weights, *hyper;
-    double *scratch;        // [C][2*K*d + K] zeroed before the launch: S0 | S1 | R (global fp64 RED)
     dlsm_hdp_prior pr;
     uint64_t seed;
     uint32_t sweep, chain_offset;
+    int bin_rows;           // private rows of the per-cluster binning (0: per-warp segmented reduction)
 };
 
 // Escobar & West (1995) auxiliary-variable update of a DP concentration parameter
@@ -113,7 +119,8 @@ __device__ inline double concentration(Stream &g, double alpha, double n_cluster
 //   PART 2 "transition side": tables m, overrides, beta, w0, w[t,k], gamma, alpha_init, alpha, kappa
 //                            -- only the next label draw needs them; reads the counts
 //   PART 0 = both.
-// dynamic smem: ints m[T*K*K], wover[T*K]; doubles mbar[K], newbeta[K], scal[16]
+// dynamic smem: ints m[T*K*K], wover[T*K], gstart[T*K*K]; doubles mbar[K], newbeta[K], scal[16], rowlog[T*K],
+// bins[rows][2*K*d + K], totals[2*K*d + K]
 template <int PART>
 __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
 {
@@ -123,9 +130,14 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
     const int c = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     int *m = reinterpret_cast<int *>(smem_raw);          // [T][K][K]
     int *wov = m + T * KK;                               // [T][K] override counts (t >= 1)
-    double *mbar = reinterpret_cast<double *>(wov + T * K + ((T * KK + T * K) & 1));
+    int *gstart = wov + T * K;                           // [T][K][K] first Philox group of a cell
+    double *mbar = reinterpret_cast<double *>(gstart + T * KK + ((2 * T * KK + T * K) & 1));
     double *nbeta = mbar + K, *scal = nbeta + K;
-    double *S0 = p.scratch + (size_t)c * (2 * K * d + K), *S1 = S0 + K * d, *R = S1 + K * d;
+    double *rowlog = scal + 16;                          // [T*K] log-beta terms of the alpha+kappa update
+    const int nbin = 2 * K * d + K;                      // S0 | S1 | R
+    const int brows = p.bin_rows > 0 ? p.bin_rows : 4;
+    double *bins = rowlog + T * K;                       // [brows][nbin] private partial sums
+    double *S0 = bins + brows * nbin, *S1 = S0 + K * d, *R = S1 + K * d; // totals
     const double *X = p.X + (size_t)c * T * n * d;
     const int32_t *z = p.z + (size_t)c * T * n;
     const double *cnt = p.ncount + (size_t)c * T * KK;
@@ -141,16 +153,57 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
 
     if (kTrans) {
     // ---- 1. table counts m (sample_auxillary.py:6-28) ----
-    for (int cell = tid; cell < T * KK; cell += nt) {
-        const int t = cell / KK, j = (cell / K) % K, k = cell % K;
-        int mm = 0;
-        if (t > 0 || j == 0) {
+    // m[cell] = sum_{i < count} Bernoulli(pr / (pr + i)).  The draws of all cells are flattened
+    // into groups of four customers (one Philox block each) and dealt to the threads, so the few
+    // heavy cells (the self-transitions) do not serialise on one lane: draw (cell, i) always uses
+    // word 3 - i % 4 of block i / 4 of the cell's stream, whoever computes it.
+    {
+        const int ncell = T * KK, per = (ncell + nt - 1) / nt;
+        const int lo = min(tid * per, ncell), hi = min(lo + per, ncell);
+        int loc = 0;
+        for (int cell = lo; cell < hi; cell++) {
+            const int t = cell / KK, j = (cell / K) % K;
+            const int groups = (t > 0 || j == 0) ? ((int)cnt[cell] + 3) >> 2 : 0;
+            gstart[cell] = loc;
+            loc += groups;
+            m[cell] = 0;
+        }
+        int incl = loc;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((tid & 31) >= o) incl += up;
+        }
+        int *wtot = reinterpret_cast<int *>(scal); // scal is not in use yet
+        if ((tid & 31) == 31) wtot[tid >> 5] = incl;
+        __syncthreads();
+        int base = 0, total = 0;
+        for (int wq = 0; wq < (nt >> 5); wq++) {
+            if (wq < (tid >> 5)) base += wtot[wq];
+            total += wtot[wq];
+        }
+        const int off = base + incl - loc;
+        for (int cell = lo; cell < hi; cell++) gstart[cell] += off;
+        __syncthreads();
+        for (int g = tid; g < total; g += nt) {
+            int a = 0, b = ncell; // the last cell whose first group is <= g owns g
+            while (b - a > 1) {
+                const int mid = (a + b) >> 1;
+                if (gstart[mid] <= g) a = mid; else b = mid;
+            }
+            const int cell = a, gi = g - gstart[cell];
+            const int t = cell / KK, j = (cell / K) % K, k = cell % K;
             const double pr = (t == 0) ? alpha_init * beta[k] : alpha * beta[k] + (j == k ? kappa : 0.0);
             const int count = (int)cnt[cell];
-            Stream g(p.seed, site + cell, p.sweep, chain);
-            for (int i = 0; i < count; i++) mm += g.bernoulli(pr / (pr + i));
+            const W4 o = philox_w4(p.seed, site + cell, p.sweep, chain, kRngHdp, 0x800000u | (uint32_t)gi);
+            const uint32_t wd[4] = {o.w, o.z, o.y, o.x};
+            int mm = 0;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int i = 4 * gi + r;
+                if (i < count && ((double)wd[r] + 0.5) * 2.3283064365386963e-10 < pr / (pr + i)) mm++;
+            }
+            if (mm) atomicAdd(&m[cell], mm);
         }
-        m[cell] = mm;
     }
     site += T * KK;
     __syncthreads();
@@ -215,12 +268,15 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
         for (int k = 0; k < K; k++) { nd += cnt[row * K + k]; mrow += m[row * K + k]; }
         atomicAdd(&scal[5], mrow);                  // sum of m[1:]
         atomicAdd(&scal[6], (double)wov[row]);      // override successes
+        double lb = 0.0;
         if (nd > 0.0) {
             Stream g(p.seed, site + row, p.sweep, chain);
             atomicAdd(&scal[2], (double)g.bernoulli(nd / (nd + ak_old)));
-            atomicAdd(&scal[3], log(g.beta(ak_old + 1.0, nd)));
+            lb = log(g.beta(ak_old + 1.0, nd));
             atomicAdd(&scal[4], mrow);
         }
+        rowlog[row] = lb; // summed in row order below: the integer-valued sums above are exact in
+                          // any order, this one is not
     }
     site += T * K;
     __syncthreads();
@@ -237,8 +293,10 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
         hy[1] = concentration(g, alpha_init, m00, (double)n, p.pr.alpha_init_shape, p.pr.alpha_init_rate);
     } else if (tid == 5) { // alpha + kappa and rho (:1010-1023)
         Stream g(p.seed, site + 5, p.sweep, chain);
+        double slog = 0.0;
+        for (int row = K; row < T * K; row++) slog += rowlog[row];
         const double ak = g.gamma(p.pr.alpha_kappa_shape + scal[4] - scal[2]) /
-                          (p.pr.alpha_kappa_rate - scal[3]);
+                          (p.pr.alpha_kappa_rate - slog);
         const double rho = g.beta(8.0 + scal[6], scal[5] - scal[6] + 2.0);
         hy[3] = ak * rho;
         hy[2] = ak - ak * rho;
@@ -248,19 +306,55 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
     site = 2 * T * KK + 2 * T * K + K + 8; // fixed layout of the Philox site ranges, whatever PART runs
     if (kEmis) {
     // ---- 5. cluster means (hdp_lpcm.py:901-919) ----
-    // per-cluster sums: one pass, native fp64 RED.ADD into a zeroed global scratch (shared-memory
-    // fp64 atomics are CAS loops and K hot addresses under 128 threads is a CAS storm)
-    for (int e = tid; e < T * n; e += nt) {
-        const int t = e / n, i = e % n, k = z[e];
-        const double *x = X + (size_t)e * d;
-        if (t == 0) {
-            for (int q = 0; q < d; q++) atomicAdd(&S0[k * d + q], x[q]);
-        } else {
-            const double *xp = X + ((size_t)(t - 1) * n + i) * d;
-            for (int q = 0; q < d; q++) atomicAdd(&S1[k * d + q], x[q] - (1.0 - lm) * xp[q]);
+    // per-cluster sums, reproducible: a warp reduces its 32 entries cluster by cluster with the
+    // fixed butterfly and its leader lane adds into the warp's private bins; the four warps' bins
+    // are then added in warp order (fp64 atomics would make the chain depend on the arrival order)
+    const int lane = tid & 31, warp = tid >> 5;
+    double *mybins = bins + (p.bin_rows > 0 ? tid : warp) * nbin;
+    for (int e = tid; e < brows * nbin; e += nt) bins[e] = 0.0;
+    __syncthreads();
+    if (p.bin_rows > 0) {
+        // thread r < bin_rows owns row r of the bins and the entries e = r (mod bin_rows), in order
+        if (tid < p.bin_rows)
+            for (int e = tid; e < T * n; e += p.bin_rows) {
+                const int t = e / n, i = e % n;
+                double *dst = mybins + (z[e] + (t > 0 ? K : 0)) * d; // S0 bins, then S1 bins
+                for (int q = 0; q < d; q++) {
+                    double v = X[(size_t)e * d + q];
+                    if (t > 0) v -= (1.0 - lm) * X[((size_t)(t - 1) * n + i) * d + q];
+                    dst[q] += v;
+                }
+            }
+    } else {
+        // large K * d: a warp reduces its 32 entries cluster by cluster with the fixed butterfly
+        for (int e0 = warp * 32; e0 < T * n; e0 += nt) {
+            const int e = e0 + lane;
+            const bool valid = e < T * n;
+            const int t = valid ? e / n : 0, i = valid ? e % n : 0;
+            const int key = valid ? z[e] + (t > 0 ? K : 0) : -1;
+            unsigned todo = __ballot_sync(0xffffffffu, valid);
+            while (todo) {
+                const int kk = __shfl_sync(0xffffffffu, key, __ffs(todo) - 1);
+                const bool mine = valid && key == kk;
+                for (int q = 0; q < d; q++) {
+                    double v = 0.0;
+                    if (mine) {
+                        v = X[(size_t)e * d + q];
+                        if (t > 0) v -= (1.0 - lm) * X[((size_t)(t - 1) * n + i) * d + q];
+                    }
+                    v = warp_sum(v);
+                    if (lane == 0) mybins[kk * d + q] += v;
+                }
+                todo &= ~__ballot_sync(0xffffffffu, mine);
+            }
         }
     }
-    __threadfence();
+    __syncthreads();
+    for (int e = tid; e < 2 * K * d; e += nt) { // rows added in row order: reproducible
+        double sacc = 0.0;
+        for (int r = 0; r < brows; r++) sacc += bins[r * nbin + e];
+        S0[e] = sacc;
+    }
     __syncthreads();
     for (int k = tid; k < K; k += nt) {
         double prec = 1.0 / mvp + nk[k] / sigma[k];
@@ -270,32 +364,62 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
         const double var = 1.0 / prec, sd = sqrt(var);
         Stream g(p.seed, site + k, p.sweep, chain);
         for (int q = 0; q < d; q++) {
-            const double mean = ((1.0 / sigma[k]) * __ldcg(&S0[k * d + q]) +
-                                 (lm / sigma[k]) * __ldcg(&S1[k * d + q])) * var;
+            const double mean = ((1.0 / sigma[k]) * S0[k * d + q] + (lm / sigma[k]) * S1[k * d + q]) * var;
             mu[k * d + q] = mean + sd * g.normal();
         }
     }
     site += K;
     __syncthreads();
     // ---- 6. cluster variances (hdp_lpcm.py:922-937) ----
-    for (int e = tid; e < T * n; e += nt) {
-        const int t = e / n, i = e % n, k = z[e];
-        const double *x = X + (size_t)e * d;
-        double r2 = 0.0;
-        for (int q = 0; q < d; q++) {
-            const double df = x[q] - ((t == 0) ? mu[k * d + q]
-                                               : (1.0 - lm) * X[((size_t)(t - 1) * n + i) * d + q] +
-                                                     lm * mu[k * d + q]);
-            r2 += df * df;
+    if (p.bin_rows > 0) {
+        if (tid < p.bin_rows)
+            for (int e = tid; e < T * n; e += p.bin_rows) {
+                const int t = e / n, i = e % n, k = z[e];
+                double r2 = 0.0;
+                for (int q = 0; q < d; q++) {
+                    const double df = X[(size_t)e * d + q] -
+                                      ((t == 0) ? mu[k * d + q]
+                                                : (1.0 - lm) * X[((size_t)(t - 1) * n + i) * d + q] + lm * mu[k * d + q]);
+                    r2 += df * df;
+                }
+                mybins[2 * K * d + k] += r2;
+            }
+    } else {
+        for (int e0 = warp * 32; e0 < T * n; e0 += nt) {
+            const int e = e0 + lane;
+            const bool valid = e < T * n;
+            const int t = valid ? e / n : 0, i = valid ? e % n : 0;
+            const int k = valid ? z[e] : -1;
+            double r2 = 0.0;
+            if (valid)
+                for (int q = 0; q < d; q++) {
+                    const double df = X[(size_t)e * d + q] -
+                                      ((t == 0) ? mu[k * d + q]
+                                                : (1.0 - lm) * X[((size_t)(t - 1) * n + i) * d + q] + lm * mu[k * d + q]);
+                    r2 += df * df;
+                }
+            unsigned todo = __ballot_sync(0xffffffffu, valid);
+            while (todo) {
+                const int kk = __shfl_sync(0xffffffffu, k, __ffs(todo) - 1);
+                const bool mine = valid && k == kk;
+                const double v = warp_sum(mine ? r2 : 0.0);
+                if (lane == 0) mybins[2 * K * d + kk] += v;
+                todo &= ~__ballot_sync(0xffffffffu, mine);
+            }
         }
-        atomicAdd(&R[k], r2);
     }
-    __threadfence();
+    __syncthreads();
+    for (int k = tid; k < K; k += nt) {
+        const int e = 2 * K * d + k;
+        double sacc = 0.0;
+        for (int r = 0; r < brows; r++) sacc += bins[r * nbin + e];
+        R[k] = sacc;
+    }
     __syncthreads();
     for (int k = tid; k < K; k += nt) {
         double tot = 0.0;
         for (int t = 0; t < T; t++) tot += nk[t * K + k];
-        const double shape = 0.5 * (tot * d + p.pr.a), rate = 0.5 * bpar + 0.5 * __ldcg(&R[k]);
+        const double shape = 0.5 * (tot * d + p.pr.a), rate = 0.5 * bpar + 0.5 * R[k];
         Stream g(p.seed, site + k, p.sweep, chain);
         sigma[k] = rate / g.gamma(shape);
     }
@@ -318,13 +442,15 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
         }
         ml = warp_sum(ml);
         sl = warp_sum(sl);
-        if ((tid & 31) == 0) { atomicAdd(&scal[0], ml); atomicAdd(&scal[1], sl); }
+        if ((tid & 31) == 0) { scal[8 + (tid >> 5)] = ml; scal[12 + (tid >> 5)] = sl; }
     }
     __syncthreads();
     if (tid == 0) { // (hdp_lpcm.py:940-954), inverse-cdf draw
         Stream g(p.seed, site + 0, p.sweep, chain);
-        const double var = 1.0 / (1.0 / p.pr.lambda_variance_prior + scal[1]);
-        const double mean = (scal[0] + p.pr.lambda_prior / p.pr.lambda_variance_prior) * var;
+        const double sum_ml = ((scal[8] + scal[9]) + scal[10]) + scal[11];
+        const double sum_sl = ((scal[12] + scal[13]) + scal[14]) + scal[15];
+        const double var = 1.0 / (1.0 / p.pr.lambda_variance_prior + sum_sl);
+        const double mean = (sum_ml + p.pr.lambda_prior / p.pr.lambda_variance_prior) * var;
         const double sd = sqrt(var);
         const double lo = normcdf((0.0 - mean) / sd), hi = normcdf((1.0 - mean) / sd);
         double u = lo + (hi - lo) * g.uniform();
@@ -348,11 +474,21 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
     } // kEmis
 }
 
+// private binning rows: as many of the 128 threads as fit a 24 KB bin area (multiples of 32)
+inline int hdp_bin_rows(int K, int d)
+{
+    const size_t nbin = (size_t)2 * K * d + K;
+    const size_t rows = ((size_t)24 * 1024) / (nbin * sizeof(double));
+    return rows >= 128 ? 128 : (rows >= 64 ? 64 : (rows >= 32 ? 32 : 0));
+}
+
 inline size_t hdp_smem_bytes(int T, int K, int d)
 {
-    const size_t ints = (size_t)T * K * K + (size_t)T * K;
-    (void)d;
-    return (ints + (ints & 1)) * sizeof(int) + ((size_t)2 * K + 16) * sizeof(double) + 16;
+    const size_t ints = (size_t)2 * T * K * K + (size_t)T * K;
+    const size_t nbin = (size_t)2 * K * d + K;
+    const int rows = hdp_bin_rows(K, d);
+    return (ints + (ints & 1)) * sizeof(int) +
+           ((size_t)2 * K + 16 + (size_t)T * K + ((rows > 0 ? rows : 4) + 1) * nbin) * sizeof(double) + 16;
 }
 
 } // namespace dlsm

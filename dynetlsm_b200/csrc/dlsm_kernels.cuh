@@ -1528,6 +1528,185 @@ __global__ void __launch_bounds__(128) k_ffbs(const LabelParams p)
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_ffbs_r: the label block sampler for K <= 16, one THREAD per (chain, node), with everything
+// that is indexed by the component held in REGISTERS (arrays of KC = 4/8/12/16 >= K entries, all
+// loops over components fully unrolled): the emission row, the backward message and the matrix-
+// vector product of a step never touch memory, the transition weights of all T steps sit in
+// shared memory (broadcast reads), and the only per-thread stage is pm[t][k] = L[t][k] bwd[t][k]
+// (T*K doubles, written once and read once per pass).  That stage lives in a global scratch
+// indexed by CTA *slot*: the grid is persistent (a few CTAs per SM, each looping over (chain,
+// node-tile) items), so the scratch stays a few tens of MB and L2-resident.
+// Arithmetic and its order are those of k_ffbs_t / the oracle (separate multiplies and adds,
+// serial-in-k rows, numpy's pairwise total): labels are bit-identical.
+// grid = min(items, 148 * resident), block = 64;
+// dynamic smem = (T*K*K + K*d + 2K) doubles (+ T*K*64 doubles when the stage is in shared memory)
+// ---------------------------------------------------------------------------------------------
+template <int KC>
+__device__ __forceinline__ double np_sum_regs(const double (&a)[KC], int K)
+{
+    if (K < 8) {
+        double r = -0.0;
+#pragma unroll
+        for (int k = 0; k < KC; k++)
+            if (k < K && k < 8) r = __dadd_rn(r, a[k]);
+        return r;
+    }
+    double res = 0.0;
+    if (KC >= 8) {
+        double r8[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) r8[q] = a[q < KC ? q : 0];
+        if (KC >= 16 && K >= 16) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) r8[q] = __dadd_rn(r8[q], a[(8 + q) < KC ? 8 + q : 0]);
+        }
+        res = __dadd_rn(__dadd_rn(__dadd_rn(r8[0], r8[1]), __dadd_rn(r8[2], r8[3])),
+                        __dadd_rn(__dadd_rn(r8[4], r8[5]), __dadd_rn(r8[6], r8[7])));
+        const int done = K - (K % 8);
+#pragma unroll
+        for (int k = 8; k < KC; k++)
+            if (k >= done && k < K) res = __dadd_rn(res, a[k]);
+    }
+    return res;
+}
+
+template <int KC, int D>
+__global__ void __launch_bounds__(64) k_ffbs_r(const LabelParams p, int tiles, int items)
+{
+    constexpr int TPB = 64;
+    constexpr int DM = (D == 0) ? kMaxD : D;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = p.T, n = p.n, K = p.K, d = (D == 0) ? p.d : D, KK = K * K;
+    const int tid = threadIdx.x, lane = tid & 31;
+    double *s_w = reinterpret_cast<double *>(smem_raw);   // [T][K][K]
+    double *s_mu = s_w + (size_t)T * KK;                  // [K][d]
+    double *s_ln = s_mu + (size_t)K * d;                  // [K]  -(d/2) log(2 pi var)
+    double *s_hv = s_ln + K;                              // [K]  0.5 * (1 / var)
+    double *pm = p.gstage ? p.gstage + (size_t)blockIdx.x * T * K * TPB : s_hv + K; // [T*K][TPB]
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int c = item / tiles, i = (item % tiles) * TPB + tid;
+        const bool valid = i < n;
+        const int ic = valid ? i : n - 1;
+        const double *X = p.X + (size_t)c * T * n * d;
+        const double *w = p.w + (size_t)c * T * KK;
+        const double lm = p.lambda[c], oml = __dsub_rn(1.0, lm);
+        __syncthreads(); // the previous item is done with the shared tables
+        for (int e = tid; e < T * KK; e += TPB) s_w[e] = w[e];
+        for (int k = tid; k < K; k += TPB) {
+            const double var = p.sigma[(size_t)c * K + k];
+            s_ln[k] = __dmul_rn(__dmul_rn(-0.5, (double)d), log(__dmul_rn(6.283185307179586, var)));
+            s_hv[k] = __dmul_rn(0.5, __ddiv_rn(1.0, var));
+        }
+        for (int e = tid; e < K * d; e += TPB) s_mu[e] = p.mu[(size_t)c * K * d + e];
+        __syncthreads();
+
+        // K7 emission densities (gaussian_likelihood_fast.pyx:17-54), normalize=False
+        double xprev[DM], xt[DM];
+#pragma unroll
+        for (int q = 0; q < DM; q++) xprev[q] = 0.0;
+        for (int t = 0; t < T; t++) {
+            const double *xg = X + ((size_t)t * n + ic) * d;
+#pragma unroll
+            for (int q = 0; q < DM; q++) xt[q] = (q < d) ? xg[q] : 0.0;
+#pragma unroll
+            for (int k = 0; k < KC; k++) {
+                if (k < K) {
+                    double sum_sq = 0.0;
+#pragma unroll
+                    for (int q = 0; q < DM; q++)
+                        if (q < d) {
+                            const double m = s_mu[k * d + q];
+                            const double mean = (t == 0) ? m : __dadd_rn(__dmul_rn(lm, m), __dmul_rn(oml, xprev[q]));
+                            const double df = __dsub_rn(xt[q], mean);
+                            sum_sq = __dadd_rn(sum_sq, __dmul_rn(df, df));
+                        }
+                    const double L = fast_exp(__dsub_rn(s_ln[k], __dmul_rn(sum_sq, s_hv[k])));
+                    pm[(size_t)(t * K + k) * TPB + tid] = L;
+                    if (p.lik_out && valid) p.lik_out[(((size_t)c * n + i) * T + t) * K + k] = L;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < DM; q++) xprev[q] = xt[q];
+        }
+        if (!p.sample) continue;
+
+        // backward messages (sample_labels.py:164-169); bwds_msg[T-1] stays all ones
+        double b[KC], v[KC];
+#pragma unroll
+        for (int k = 0; k < KC; k++) b[k] = 1.0;
+        for (int t = T - 1; t > 0; t--) {
+            const double *wt = s_w + (size_t)t * KK;
+#pragma unroll
+            for (int k = 0; k < KC; k++) {
+                v[k] = 0.0;
+                if (k < K) {
+                    const size_t o = (size_t)(t * K + k) * TPB + tid;
+                    v[k] = __dmul_rn(pm[o], b[k]);
+                    pm[o] = v[k];
+                }
+            }
+            // bwd[t-1][j] = sum_k w[t][j][k] pm[t][k], serial in k per row j (the oracle's order);
+            // the rows are independent chains the scheduler interleaves
+#pragma unroll
+            for (int j = 0; j < KC; j++) {
+                double sacc = 0.0;
+                if (j < K) {
+#pragma unroll
+                    for (int k = 0; k < KC; k++)
+                        if (k < K) sacc = __dadd_rn(sacc, __dmul_rn(wt[j * K + k], v[k]));
+                }
+                b[j] = sacc;
+            }
+            const double itot = __ddiv_rn(1.0, np_sum_regs<KC>(b, K)); // one division per step
+#pragma unroll
+            for (int j = 0; j < KC; j++) b[j] = __dmul_rn(b[j], itot);
+        }
+#pragma unroll
+        for (int k = 0; k < KC; k++) v[k] = (k < K) ? __dmul_rn(pm[(size_t)k * TPB + tid], b[k]) : 0.0;
+
+        // forward sampling (:173-188): cumsum, u = cdf[-1] * U, z = #{k : u > cdf[k]}
+        int zp = 0;
+        for (int t = 0; t < T; t++) {
+            if (t > 0) {
+#pragma unroll
+                for (int k = 0; k < KC; k++) v[k] = (k < K) ? pm[(size_t)(t * K + k) * TPB + tid] : 0.0;
+            }
+            const double *wr = (t == 0) ? s_w : s_w + (size_t)t * KK + zp * K;
+            double cdf[KC];
+            double cs = 0.0;
+#pragma unroll
+            for (int k = 0; k < KC; k++) {
+                if (k < K) {
+                    const double pr = __dmul_rn(wr[k], v[k]);
+                    cs = (k == 0) ? pr : __dadd_rn(cs, pr);
+                }
+                cdf[k] = cs;
+            }
+            double U;
+            if (p.U) U = p.U[((size_t)c * n + ic) * T + t];
+            else U = philox_u2(p.seed, (uint32_t)(ic * T + t), p.sweep, (uint32_t)c + p.chain_offset,
+                               kRngLabels, 0).a;
+            const double u = __dmul_rn(cs, U);
+            int zz = 0;
+#pragma unroll
+            for (int k = 0; k < KC; k++) zz += (k < K && u > cdf[k]) ? 1 : 0;
+            if (zz >= K) zz = K - 1;
+            if (valid) p.z[((size_t)c * T + t) * n + i] = zz;
+            // counts: one atomic per distinct (from, to) pair / label in the warp
+            const int from = (t == 0) ? 0 : zp;
+            const int key = valid ? from * K + zz : -1;
+            const unsigned same = __match_any_sync(kFull, key);
+            if (valid && lane == __ffs(same) - 1)
+                atomicAdd(&p.ncount[((size_t)c * T + t) * KK + key], (double)__popc(same));
+            const unsigned same_z = __match_any_sync(kFull, valid ? zz : -1);
+            if (valid && lane == __ffs(same_z) - 1)
+                atomicAdd(&p.nk[((size_t)c * T + t) * K + zz], __popc(same_z));
+            zp = zz;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_ffbs_t: HDP-HMM label block sampler, one THREAD per (chain, node) -- the production mapping.
 // The per-node recursion is strictly sequential in t and only K wide, so a warp per node leaves
 // two thirds of the lanes idle and pays a shuffle/sync per step (k_ffbs above, kept as the

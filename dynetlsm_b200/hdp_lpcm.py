@@ -4,9 +4,11 @@ device sampler.
 Per sweep the device runs the hot path -- mixture-prior latent-position sweep, centring,
 intercept / radii MH on the full-network likelihood, HDP-HMM label forward-filter /
 backward-sample -- and hands the label counts to the host, which performs the reference's
-conjugate and auxiliary-variable updates in numpy (``hdp_updates.py``; SURVEY.md 8f-1 marks a
-device version of that block as the next step).  ``sampler='replay'`` draws every random number
-from the numpy ``RandomState`` in the reference's order, so the chain reproduces the reference's.
+conjugate and auxiliary-variable updates in numpy (``hdp_updates.py``) when ``sampler='replay'``:
+every random number then comes from the numpy ``RandomState`` in the reference's order, so the
+chain reproduces the reference's.  With ``sampler='device'`` (default) that block, the joint
+log-posterior and the stored samples are produced on the device as well (``dlsm_hdp_update``,
+``dlsm_run_traced``) and ``fit`` makes no host round trip per sweep.
 
 Post-processing that the reference delegates to its ``model_selection`` package (approximate BIC,
 posterior-expected VI) is outside the accelerated path: ``selection_type`` is accepted, and the
@@ -186,7 +188,6 @@ class DynamicNetworkHDPLPCM(object):
             chains = None
         else:
             # ---- device-resident chains: the conjugate block runs in k_hdp_update ----
-            import copy as _copy
             e.set(L.F_MU, tile(mus[0])); e.set(L.F_SIGMA, tile(sigmas[0]))
             e.set(L.F_LAMBDA, np.full(C, float(self.lambda_prior))); e.set(L.F_WEIGHTS, tile(weights[0]))
             e.set(L.F_Z, tile(zs[0])); e.set(L.F_BETA, tile(betas[0]))
@@ -201,41 +202,52 @@ class DynamicNetworkHDPLPCM(object):
                           n_clusters=np.zeros((C, S), dtype=np.int64), zs=np.zeros((C, S, T, n), np.int16))
             chains["intercepts"][:, 0] = ics[0]; chains["lambdas"][:, 0] = self.lambda_prior
             chains["zs"][:, 0] = zs[0]
+            chains["n_clusters"][:, 0] = np.unique(zs[0]).size
+            chains["logps"][:, 0] = e.logp()
+            logps[0] = chains["logps"][0, 0]
 
-            def record(it):
-                Xa, za = e.get(L.F_X), e.get(L.F_Z)
-                mua, sga, lma = e.get(L.F_MU), e.get(L.F_SIGMA), e.get(L.F_LAMBDA)
-                bea, wa, hya = e.get(L.F_BETA), e.get(L.F_WEIGHTS), e.get(L.F_HYPER)
-                ica = e.get(L.F_INTERCEPT)[:, :m]
-                ra = e.get(L.F_RADII) if self.is_directed else None
-                ll = e.loglik_full()
-                for c in range(C):
-                    hpc = _copy.copy(hp)
-                    (hpc.gamma, hpc.alpha_init, hpc.alpha, hpc.kappa, hpc.mean_variance_prior,
-                     hpc.b) = hya[c, :6]
-                    lpc = log_post(ll[c], hpc, Xa[c], ica[c], mua[c], sga[c], za[c].astype(np.int64),
-                                   wa[c], bea[c], np.array([lma[c]]), None if ra is None else ra[c])
-                    chains["logps"][c, it] = lpc
-                    if c == 0:
-                        hp.__dict__.update(hpc.__dict__)
-                chains["intercepts"][:, it] = ica
-                chains["lambdas"][:, it] = lma
-                chains["zs"][:, it] = za
-                chains["n_clusters"][:, it] = [np.unique(za[c]).size for c in range(C)]
-                Xs[it], zs[it], mus[it], sigmas[it] = Xa[0], za[0], mua[0], sga[0]
-                betas[it], weights[it], lambdas[it], ics[it] = bea[0], wa[0], lma[0], ica[0]
-                if self.is_directed:
-                    rads[it] = ra[0]
-                logps[it] = chains["logps"][0, it]
-
-            record(0)
-            for it in range(1, S):
-                if self.case_control_sampler_ is not None:
-                    self.case_control_sampler_.resample()
-                    if self.case_control_sampler_.resampled_:
+            # The whole loop body (hdp_lpcm.py:823-1069) runs on the device, stored samples and the
+            # joint log-posterior included (dlsm_run_traced); the host only splits the run where
+            # the case-control sets are redrawn and to bound the size of one trace transfer.
+            first = (L.F_X, L.F_MU, L.F_SIGMA, L.F_BETA, L.F_WEIGHTS) + ((L.F_RADII,) if self.is_directed else ())
+            every = (L.F_INTERCEPT, L.F_LAMBDA, L.F_Z, L.F_HYPER)
+            rec_bytes = 8 * (T * n * d + K * d + 2 * K + T * K * K + n) + C * (4 * T * n + 8 * 12)
+            seg = int(max(1, min(S, (256 << 20) // rec_bytes)))
+            cc = self.case_control_sampler_
+            hya = None
+            it = 1
+            while it < S:
+                stop = min(S, it + seg)
+                if cc is not None:              # hdp_lpcm.py:826-829
+                    cc.resample()
+                    if cc.resampled_:
                         drv.push_controls()
-                e.run_sweeps(1)   # latent -> centre -> intercepts -> [radii] -> labels -> HDP update
-                record(it)
+                    quiet = S if cc.n_resample is None else (cc.n_resample - cc.n_iter % cc.n_resample) % cc.n_resample
+                    stop = min(stop, it + 1 + quiet)
+                tr = e.run_traced(stop - it, fields_all=every, fields_first=first, pinned=True)
+                if cc is not None:
+                    cc.n_iter += stop - it - 1
+                sl = slice(it, stop)
+                Xs[sl], mus[sl], sigmas[sl] = tr[L.F_X][:, 0], tr[L.F_MU][:, 0], tr[L.F_SIGMA][:, 0]
+                betas[sl], weights[sl] = tr[L.F_BETA][:, 0], tr[L.F_WEIGHTS][:, 0]
+                za = tr[L.F_Z]
+                zs[sl] = za[:, 0]
+                lambdas[sl, 0] = tr[L.F_LAMBDA][:, 0]
+                ics[sl] = tr[L.F_INTERCEPT][:, 0, :m]
+                if self.is_directed:
+                    rads[sl] = tr[L.F_RADII][:, 0]
+                logps[sl] = tr["logp"][:, 0]
+                chains["logps"][:, sl] = tr["logp"].T
+                chains["intercepts"][:, sl] = tr[L.F_INTERCEPT].transpose(1, 0, 2)[:, :, :m]
+                chains["lambdas"][:, sl] = tr[L.F_LAMBDA].T
+                chains["zs"][:, sl] = za.transpose(1, 0, 2, 3)
+                present = np.zeros(za.shape[:2] + (K,), dtype=bool)
+                np.put_along_axis(present, za.reshape(za.shape[0], C, -1), True, axis=2)
+                chains["n_clusters"][:, sl] = present.sum(axis=2).T
+                hya = tr[L.F_HYPER][-1, 0]
+                it = stop
+            if hya is not None:
+                (hp.gamma, hp.alpha_init, hp.alpha, hp.kappa, hp.mean_variance_prior, hp.b) = hya[:6]
         self.chains_ = chains
 
         # mirror the reference's mutable hyper-parameter attributes

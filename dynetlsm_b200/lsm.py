@@ -194,6 +194,66 @@ class DynamicNetworkLSM(object):
             lp -= 0.5 * (diff * diff) / self.intercept_variance_prior
         return lp
 
+    def _replay_loop(self, drv, S, n_iter_procrustes, Xs, ics, rads, logps):
+        """The reference's loop, block by block, on its own RandomState (lsm.py:474-572)."""
+        e, C, m = drv.engine, self.n_chains, (2 if self.is_directed else 1)
+        for it in range(1, S):
+            if self.case_control_sampler_ is not None:
+                self.case_control_sampler_.resample()
+                if self.case_control_sampler_.resampled_:
+                    drv.push_controls()
+            drv.sweep_latent()
+            if it > n_iter_procrustes:   # lsm.py:495-498: align with the best pre-burn-in sample
+                Xh = e.get(L.F_X)
+                for c in range(C):
+                    ref = Xs[c, np.argmax(logps[c, :(n_iter_procrustes + 1)])]
+                    Xh[c], _ = longitudinal_procrustes_rotation(ref, Xh[c])
+                e.set(L.F_X, Xh)
+            e.center()
+            drv.sample_intercepts()
+            if self.is_directed:
+                drv.sample_radii()
+            Xs[:, it] = e.get(L.F_X)
+            ics[:, it] = e.get(L.F_INTERCEPT)[:, :m]
+            if self.is_directed:
+                rads[:, it] = e.get(L.F_RADII)
+            ll = e.loglik_full()
+            for c in range(C):
+                logps[c, it] = ll[c] + self._log_prior(Xs[c, it], ics[c, it])
+
+    def _device_loop(self, drv, S, n_iter_procrustes, Xs, ics, rads, logps):
+        """Device-resident chains: sweeps, centring, Procrustes, log-posterior and traces all stay
+        on the GPU (dlsm_run_traced); the host only intervenes where the reference's loop changes
+        regime -- the end of burn-in (Procrustes reference) and case-control resampling."""
+        e, C, m = drv.engine, self.n_chains, (2 if self.is_directed else 1)
+        cc = self.case_control_sampler_
+        fields = (L.F_X, L.F_INTERCEPT) + ((L.F_RADII,) if self.is_directed else ())
+        it = 1
+        while it < S:
+            stop = S
+            if it <= n_iter_procrustes:
+                stop = min(stop, n_iter_procrustes + 1)
+            if cc is not None:                     # lsm.py:478-481, case_control_likelihood.py:27-33
+                cc.resample()
+                if cc.resampled_:
+                    drv.push_controls()
+                # iterations whose resample() call is a no-op are batched with this one
+                quiet = S if cc.n_resample is None else (cc.n_resample - cc.n_iter % cc.n_resample) % cc.n_resample
+                stop = min(stop, it + 1 + quiet)
+            if it == n_iter_procrustes + 1:        # lsm.py:495-498
+                ref = np.stack([Xs[c, np.argmax(logps[c, :(n_iter_procrustes + 1)])] for c in range(C)])
+                e.set_procrustes_ref(ref)
+            tr = e.run_traced(stop - it, fields_all=fields, pinned=True)
+            Xs[:, it:stop] = tr[L.F_X].transpose(1, 0, 2, 3, 4)
+            ics[:, it:stop] = tr[L.F_INTERCEPT].transpose(1, 0, 2)[:, :, :m]
+            if self.is_directed:
+                rads[:, it:stop] = tr[L.F_RADII].transpose(1, 0, 2)
+            logps[:, it:stop] = tr["logp"].T
+            if cc is not None:
+                cc.n_iter += stop - it - 1
+            it = stop
+        e.set_procrustes_ref(None)
+
     def fit(self, Y):
         """Sample from the posterior given the dynamic network ``Y`` (T, n, n), entries 0/1."""
         if self.sampler not in ("device", "replay"):
@@ -276,37 +336,21 @@ class DynamicNetworkLSM(object):
         ics[:, 0] = intercept
         if self.is_directed:
             rads[:, 0] = radii
-        ll = e.loglik_full()
-        for c in range(C):
-            logps[c, 0] = ll[c] + self._log_prior(Xs[c, 0], ics[c, 0])
-        best = [dict(logp=logps[c, 0], it=0) for c in range(C)]
+        logps[:, 0] = e.logp() if not replay else [
+            ll + self._log_prior(Xs[c, 0], ics[c, 0]) for c, ll in enumerate(e.loglik_full())]
 
-        for it in range(1, S):
-            if self.case_control_sampler_ is not None:
-                self.case_control_sampler_.resample()
-                if self.case_control_sampler_.resampled_:
-                    drv.push_controls()
-            drv.sweep_latent()
-            if it > n_iter_procrustes:   # lsm.py:495-498: align with the best pre-burn-in sample
-                Xh = e.get(L.F_X)
-                for c in range(C):
-                    ref = Xs[c, np.argmax(logps[c, :(n_iter_procrustes + 1)])]
-                    Xh[c], _ = longitudinal_procrustes_rotation(ref, Xh[c])
-                e.set(L.F_X, Xh)
-            e.center()
-            drv.sample_intercepts()
-            if self.is_directed:
-                drv.sample_radii()
-            Xs[:, it] = e.get(L.F_X)
-            ics[:, it] = e.get(L.F_INTERCEPT)[:, :m]
-            if self.is_directed:
-                rads[:, it] = e.get(L.F_RADII)
-            ll = e.loglik_full()
-            for c in range(C):
-                logps[c, it] = ll[c] + self._log_prior(Xs[c, it], ics[c, it])
-                # MAP bookkeeping (lsm.py:554-566): restart at the end of burn-in, then track the max
-                if (self.tune and it == (self.tune + self.burn)) or logps[c, it] > best[c]["logp"]:
-                    best[c] = dict(logp=logps[c, it], it=it)
+        if replay:
+            self._replay_loop(drv, S, n_iter_procrustes, Xs, ics, rads, logps)
+        else:
+            self._device_loop(drv, S, n_iter_procrustes, Xs, ics, rads, logps)
+
+        # MAP bookkeeping (lsm.py:554-566): restart at the end of burn-in, then track the max
+        best = []
+        nb = (self.tune or 0) + (self.burn or 0)
+        for c in range(C):
+            start = nb if (self.tune and nb < S) else 0
+            best.append(dict(it=start + int(np.argmax(logps[c, start:]))))
+            best[c]["logp"] = logps[c, best[c]["it"]]
 
         # ---- drop-in attributes (chain 0) + per-chain traces ----
         self.Xs_, self.intercepts_, self.logps_ = Xs[0], ics[0], logps[0]

@@ -187,6 +187,36 @@ int dlsm_hdp_update(dlsm_handle *h);
  * HDP update (it also needs dlsm_set_hdp_prior to have been called). */
 int dlsm_run_sweeps(dlsm_handle *h, int32_t n_sweeps, uint32_t flags);
 
+/* ---- the rest of the estimator loop, device-resident ---------------- */
+/* Joint log-posterior of the current state, out (C,): LSM lsm.py:576-625; HDP-LPCM
+ * hdp_lpcm.py:1188-1280 (needs dlsm_set_hdp_prior and the F_BETA / F_HYPER fields). */
+int dlsm_logp(dlsm_handle *h, double *out);
+/* In-loop longitudinal Procrustes (lsm.py:495-498 -> procrustes.py:28-35): while a reference
+ * configuration Xref (C,T,n,d) is set, every sweep of dlsm_run_sweeps / dlsm_run_traced rotates
+ * X onto it (one rotation for all time steps) between the latent sweep and the centring.
+ * NULL clears it.  dlsm_procrustes applies the rotation once (parity probe). */
+int dlsm_set_procrustes_ref(dlsm_handle *h, const double *Xref);
+int dlsm_procrustes(dlsm_handle *h);
+/* What a stored sample consists of (the per-iteration trace writes lsm.py:475-477, :526-566 and
+ * hdp_lpcm.py:823-837, :1025-1069). */
+typedef struct {
+    uint32_t fields_all;   /* bit f: store DLSM_F_<f> of every chain with each record */
+    uint32_t fields_first; /* bit f: store DLSM_F_<f> of chain 0 only */
+    int32_t thin;          /* one record every `thin` sweeps (>= 1) */
+    int32_t want_logp;     /* also store the joint log-posterior of every chain */
+    int32_t reserved[4];
+} dlsm_trace_spec;
+/* dlsm_run_sweeps that also records the chain: after every `thin`-th sweep the traced fields (and
+ * the log-posterior) are gathered into a device ring and streamed to the host on a copy stream
+ * while the following sweeps run.  dst[f] (f < DLSM_F_COUNT_) receives field f as
+ * (n_sweeps / thin, C or 1, <field shape per chain>), logp_dst (n_sweeps / thin, C); pageable or
+ * pinned (dlsm_host_alloc) memory, valid until the call returns. */
+int dlsm_run_traced(dlsm_handle *h, int32_t n_sweeps, uint32_t flags, const dlsm_trace_spec *spec,
+                    void *const *dst, double *logp_dst);
+/* page-locked host memory for trace destinations */
+int dlsm_host_alloc(size_t bytes, void **out);
+int dlsm_host_free(void *p);
+
 /* ---- parity probes --------------------------------------------------------------------- */
 /* per-node log-likelihood at the current state, out (C,T,n):
  * partial_loglikelihood / directed_partial_loglikelihood / approx_directed_partial_loglikelihood */

@@ -146,3 +146,50 @@ def test_hdp_estimator_device_mode_multichain():
     same = truth[:, None] == truth[None, :]
     co = m.cooccurrence_probas_[0]
     assert co[same].mean() > co[~same].mean() + 0.2
+
+
+def test_device_hdp_chain_is_reproducible():
+    """Same seed -> the same chain, bit for bit: the conjugate block's sufficient statistics are
+    reduced in a fixed order (no floating-point atomics)."""
+    import bench
+    from dynetlsm_b200 import _lib as L
+    w = bench.make_workload("cfg2")
+    outs = []
+    for rep in range(2):
+        e = bench.build_engine(w, 5, 0, 0)
+        e.run_sweeps(40)
+        outs.append([e.get(f) for f in (L.F_X, L.F_Z, L.F_MU, L.F_SIGMA, L.F_LAMBDA, L.F_BETA,
+                                        L.F_WEIGHTS, L.F_HYPER, L.F_INTERCEPT)])
+        e.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
+def test_binning_variants_agree(monkeypatch):
+    """The per-cluster sufficient statistics have two reproducible reductions (private bin rows for
+    small K*d, per-warp segmented butterflies otherwise).  Same Philox streams, same state: the
+    draws agree to summation-order accuracy."""
+    from dynetlsm_b200 import _lib as L
+    X, z, cnt, nk, mu, sigma, lm, beta, w = _state(seed=3, T=5, n=77, d=3, K=6)
+    hp0 = _hyper()
+    C_ = 8
+    tile = lambda a: np.tile(np.asarray(a)[None], (C_,) + (1,) * np.ndim(a))
+    outs = []
+    for segmented in (False, True):
+        if segmented:
+            monkeypatch.setenv("DLSM_HDP_SEGMENTED", "1")
+        e = L.Engine(T=X.shape[0], n=X.shape[1], d=X.shape[2], n_chains=C_, K=sigma.size, mixture=True)
+        e.set(L.F_X, tile(X)); e.set(L.F_Z, tile(z)); e.set(L.F_MU, tile(mu)); e.set(L.F_SIGMA, tile(sigma))
+        e.set(L.F_LAMBDA, np.full(C_, lm)); e.set(L.F_BETA, tile(beta)); e.set(L.F_WEIGHTS, tile(w))
+        hy = np.array([hp0.gamma, hp0.alpha_init, hp0.alpha, hp0.kappa, hp0.mean_variance_prior, hp0.b, 0, 0])
+        e.set(L.F_HYPER, tile(hy))
+        e.set_hdp_prior(hp0.a, hp0.a0, hp0.b0, hp0.c0, hp0.d0, hp0.lambda_prior, hp0.lambda_variance_prior,
+                        hp0.gamma_prior_shape, hp0.gamma_prior_rate, hp0.alpha_init_shape,
+                        hp0.alpha_init_rate, hp0.alpha_kappa_shape, hp0.alpha_kappa_rate, True, True)
+        _force_counts(e, L, cnt, nk)
+        e.set_rng(21)
+        e.hdp_update()
+        outs.append([e.get(f) for f in (L.F_MU, L.F_SIGMA, L.F_LAMBDA, L.F_BETA, L.F_WEIGHTS, L.F_HYPER)])
+    for a, b in zip(*outs):
+        assert np.allclose(a, b, rtol=1e-9, atol=1e-12)
+    assert not np.array_equal(outs[0][0][0], outs[0][0][1])   # chains differ from each other

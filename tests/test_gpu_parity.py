@@ -404,13 +404,22 @@ def test_full_device_sweeps_are_deterministic_and_chain_independent():
     (4, 50, 1, 32),
     (3, 70, 2, 1),      # single component
     (12, 70, 3, 40),    # thread-per-node, 32 threads per CTA
-    (20, 40, 2, 60)])   # warp-per-node fallback (T*K too large for the thread kernel's stage)
-@pytest.mark.parametrize("stage", ["global", "shared"])
+    (20, 40, 2, 60),    # warp-per-node fallback (T*K too large for the thread kernel's stage)
+    (7, 129, 2, 16),    # register kernel, KC = 16 exactly (two numpy 8-blocks)
+    (6, 64, 2, 13),     # KC = 16 with three guarded components
+    (8, 65, 3, 4),      # KC = 4, generic latent dimension
+    (5, 100, 2, 5),     # KC = 8
+    (2, 300, 2, 10),    # several node tiles per chain
+    (1, 40, 2, 10)])    # a single time step: no backward pass
+@pytest.mark.parametrize("stage", ["default", "global", "shared"])
 def test_labels_vs_oracle_all_kernel_variants(T, n, d, K, stage, monkeypatch):
-    """FFBS with recorded uniforms on larger random problems vs the oracle (exact labels); the
-    thread-per-node kernel with its stage in L2-resident global memory and in shared memory."""
+    """FFBS with recorded uniforms on larger random problems vs the oracle (exact labels): the
+    register-resident kernel (default for K <= 16), the thread-per-node kernel with its stage in
+    L2-resident global memory and in shared memory, the warp-per-node fallback."""
     if stage == "shared":
         monkeypatch.setenv("DLSM_FFBS_SMEM", "1")
+    elif stage == "global":
+        monkeypatch.setenv("DLSM_FFBS", "thread")
     L = _F()
     rng = np.random.RandomState(8)
     X = rng.randn(T, n, d)

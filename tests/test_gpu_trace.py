@@ -1,0 +1,222 @@
+"""The device-resident remainder of the estimator loops: joint log-posterior
+(lsm.py:576-625, hdp_lpcm.py:1188-1280), in-loop Procrustes (lsm.py:495-498, procrustes.py:20-35) and
+the trace pipeline of dlsm_run_traced, each against its host statement."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _L():
+    from dynetlsm_b200 import _lib
+    return _lib
+
+
+def _net(rng, T, n, directed, density=0.2):
+    Y = (rng.rand(T, n, n) < density).astype(np.float64)
+    for t in range(T):
+        np.fill_diagonal(Y[t], 0)
+    if not directed:
+        Y = np.triu(Y, 1)
+        Y = Y + Y.transpose(0, 2, 1)
+    return Y
+
+
+def _lsm_engine(T, n, d, C_, directed, seed=0, chunk=None):
+    L = _L()
+    rng = np.random.RandomState(seed)
+    Y = _net(rng, T, n, directed)
+    e = L.Engine(T=T, n=n, d=d, n_chains=C_, is_directed=directed, tune=50, tune_interval=10)
+    e.set_network(Y)
+    X = rng.randn(C_, T, n, d) * (0.02 if directed else 1.0)
+    e.set(L.F_X, X)
+    ic = np.zeros((C_, 2)); ic[:, 0] = 0.4 + 0.1 * rng.rand(C_); ic[:, 1] = 0.7 if directed else 0.0
+    e.set(L.F_INTERCEPT, ic)
+    if directed:
+        e.set(L.F_RADII, rng.dirichlet(np.ones(n) * 5, size=C_))
+    e.set_hyper(tau_sq=1.7, sigma_sq=0.3 if not directed else 0.001, intercept_prior=(0.3, 0.6),
+                intercept_variance_prior=2.5)
+    e.set_tuner(0.1 if not directed else 0.005)
+    e.set_rng(seed + 11)
+    return e
+
+
+def _hdp_engine(T, n, d, K, C_, directed, seed=0):
+    L = _L()
+    from dynetlsm_b200.hdp_updates import HDPHyper
+    rng = np.random.RandomState(seed)
+    Y = _net(rng, T, n, directed)
+    e = L.Engine(T=T, n=n, d=d, n_chains=C_, K=K, mixture=True, is_directed=directed, tune=50,
+                 tune_interval=10)
+    e.set_network(Y)
+    e.set(L.F_X, rng.randn(C_, T, n, d) * (0.02 if directed else 1.0))
+    ic = np.zeros((C_, 2)); ic[:, 0] = 0.5; ic[:, 1] = 0.6 if directed else 0.0
+    e.set(L.F_INTERCEPT, ic)
+    if directed:
+        e.set(L.F_RADII, rng.dirichlet(np.ones(n) * 5, size=C_))
+    e.set(L.F_MU, rng.randn(C_, K, d)); e.set(L.F_SIGMA, rng.gamma(3, 0.3, (C_, K)))
+    e.set(L.F_LAMBDA, rng.uniform(0.3, 0.95, C_))
+    e.set(L.F_WEIGHTS, rng.dirichlet(np.ones(K), size=(C_, T, K)))
+    e.set(L.F_BETA, rng.dirichlet(np.ones(K) * 2, size=C_))
+    e.set(L.F_Z, rng.randint(0, K, (C_, T, n)))
+    hy = np.zeros((C_, 8))
+    hy[:, :6] = np.c_[rng.gamma(2, 1, C_), rng.gamma(2, 1, C_), rng.gamma(2, 1, C_), rng.gamma(2, 2, C_),
+                      rng.gamma(3, 1, C_), rng.gamma(2, 1, C_)]
+    e.set(L.F_HYPER, hy)
+    hp = HDPHyper(gamma=1.0, alpha_init=1.0, alpha=1.0, kappa=1.0, mean_variance_prior=2.0, b=1.0, a=2.0,
+                  a0=0.1, b0=0.1, c0=3.0, d0=0.5, lambda_prior=0.9, lambda_variance_prior=0.01,
+                  gamma_prior_shape=1.0, gamma_prior_rate=0.1, alpha_init_shape=1.0, alpha_init_rate=0.1,
+                  alpha_kappa_shape=1.0, alpha_kappa_rate=0.1, resample_mean_variance=True,
+                  resample_b=True)
+    e.set_hdp_prior(hp.a, hp.a0, hp.b0, hp.c0, hp.d0, hp.lambda_prior, hp.lambda_variance_prior,
+                    hp.gamma_prior_shape, hp.gamma_prior_rate, hp.alpha_init_shape, hp.alpha_init_rate,
+                    hp.alpha_kappa_shape, hp.alpha_kappa_rate, hp.resample_mean_variance, hp.resample_b)
+    e.set_hyper(intercept_prior=(0.4, 0.5), intercept_variance_prior=2.0)
+    e.set_tuner(0.1 if not directed else 0.005)
+    e.set_rng(seed + 5)
+    return e, hp
+
+
+def _host_logp_lsm(e, tau_sq, sigma_sq, prior, var):
+    L = _L()
+    X, ic = e.get(L.F_X), e.get(L.F_INTERCEPT)
+    out = e.loglik_full()
+    for c in range(e.C):
+        lp = -np.sum(0.5 * np.sum(X[c, 0] ** 2, axis=1) / tau_sq)
+        for t in range(1, e.T):
+            lp -= np.sum(0.5 * np.sum((X[c, t] - X[c, t - 1]) ** 2, axis=1) / sigma_sq)
+        for i in range(e.m):
+            lp -= 0.5 * (ic[c, i] - prior[i]) ** 2 / var
+        out[c] += lp
+    return out
+
+
+def _host_logp_hdp(e, hp):
+    import copy
+    L = _L()
+    from dynetlsm_b200.hdp_updates import hdp_log_prior
+    X, ic, z = e.get(L.F_X), e.get(L.F_INTERCEPT), e.get(L.F_Z).astype(np.int64)
+    mu, sg, lam = e.get(L.F_MU), e.get(L.F_SIGMA), e.get(L.F_LAMBDA)
+    w, be, hy = e.get(L.F_WEIGHTS), e.get(L.F_BETA), e.get(L.F_HYPER)
+    ra = e.get(L.F_RADII) if e.is_directed else None
+    out = e.loglik_full()
+    for c in range(e.C):
+        h = copy.copy(hp)
+        h.gamma, h.alpha_init, h.alpha, h.kappa, h.mean_variance_prior, h.b = hy[c, :6]
+        lp = hdp_log_prior(h, e.K, X[c], ic[c, :e.m], np.array([0.4, 0.5])[:e.m], 2.0, mu[c], sg[c], z[c],
+                           w[c], be[c], np.array([lam[c]]), radii=None if ra is None else ra[c])
+        out[c] += float(np.ravel(lp)[0])
+    return out
+
+
+@pytest.mark.parametrize("directed", [False, True])
+def test_logp_lsm(directed):
+    e = _lsm_engine(5, 40, 2, 3, directed)
+    want = _host_logp_lsm(e, 1.7, 0.3 if not directed else 0.001, (0.3, 0.6), 2.5)
+    assert np.allclose(e.logp(), want, rtol=1e-11, atol=0)
+
+
+@pytest.mark.parametrize("directed,K,d", [(False, 6, 2), (True, 4, 2), (False, 9, 3)])
+def test_logp_hdp(directed, K, d):
+    e, hp = _hdp_engine(6, 35, d, K, 3, directed)
+    want = _host_logp_hdp(e, hp)
+    got = e.logp()
+    assert np.all(np.isfinite(got))
+    assert np.allclose(got, want, rtol=1e-10, atol=0)
+
+
+def test_logp_hdp_with_zero_weights():
+    """Dirichlet draws that underflow to exactly 0 are clipped like the reference does
+    (distributions.py:72-102)."""
+    L = _L()
+    e, hp = _hdp_engine(4, 20, 2, 5, 2, False)
+    w = e.get(L.F_WEIGHTS)
+    w[:, 2, 1, 0] += w[:, 2, 1, 3]
+    w[:, 2, 1, 3] = 0.0
+    e.set(L.F_WEIGHTS, w)
+    z = e.get(L.F_Z)
+    z[(z == 3)] = 2                       # no transition uses the zero entry
+    e.set(L.F_Z, z)
+    assert np.allclose(e.logp(), _host_logp_hdp(e, hp), rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 5, 8])
+def test_procrustes_matches_scipy(d):
+    from dynetlsm_b200.host_init import longitudinal_procrustes_rotation
+    from scipy.stats import ortho_group
+    L = _L()
+    T, n, C_ = 4, 30, 3
+    rng = np.random.RandomState(d)
+    e = L.Engine(T=T, n=n, d=d, n_chains=C_)
+    ref = rng.randn(C_, T, n, d)
+    X = np.empty_like(ref)
+    for c in range(C_):
+        Q = ortho_group.rvs(d, random_state=rng) if d > 1 else np.array([[-1.0]])
+        X[c] = ref[c] @ Q + 0.05 * rng.randn(T, n, d)
+    e.set(L.F_X, X)
+    e.set_procrustes_ref(ref)
+    e.procrustes()
+    got = e.get(L.F_X)
+    for c in range(C_):
+        want, _ = longitudinal_procrustes_rotation(ref[c], X[c])
+        assert np.allclose(got[c], want, rtol=0, atol=1e-12)
+    e.set_procrustes_ref(None)
+    with pytest.raises(L.DlsmError):
+        e.procrustes()
+
+
+@pytest.mark.parametrize("model", ["lsm", "lsm-directed", "hdp"])
+@pytest.mark.parametrize("thin,pinned", [(1, False), (3, True)])
+def test_run_traced_equals_stepwise(model, thin, pinned, monkeypatch):
+    """Records of dlsm_run_traced == the states a sweep-by-sweep loop reads back, across several
+    ring chunks (the chunk size is forced down to a few records)."""
+    L = _L()
+    monkeypatch.setenv("DLSM_TRACE_CHUNK_BYTES", "60000")
+
+    def make():
+        if model == "hdp":
+            return _hdp_engine(5, 30, 2, 6, 3, False)[0]
+        return _lsm_engine(5, 30, 2, 3, model == "lsm-directed")
+    a, b = make(), make()
+    n_sweeps = 23
+    first = (L.F_X,) + ((L.F_MU, L.F_WEIGHTS) if model == "hdp" else ())
+    every = (L.F_INTERCEPT,) + ((L.F_Z, L.F_LAMBDA, L.F_HYPER) if model == "hdp" else ()) + \
+            ((L.F_RADII,) if model == "lsm-directed" else ())
+    tr = a.run_traced(n_sweeps, fields_all=every, fields_first=first, thin=thin, pinned=pinned)
+    rec = n_sweeps // thin
+    assert tr["logp"].shape == (rec, 3)
+    for r in range(rec):
+        b.run_sweeps(thin)
+        for f in every:
+            assert np.array_equal(tr[f][r], b.get(f)), (f, r)
+        for f in first:
+            assert np.array_equal(tr[f][r, 0], b.get(f)[0]), (f, r)
+        assert np.allclose(tr["logp"][r], b.logp(), rtol=1e-10, atol=0)
+    b.run_sweeps(n_sweeps - rec * thin)
+    assert np.array_equal(a.get(L.F_X), b.get(L.F_X))      # the tail after the last record ran too
+
+
+def test_run_traced_with_procrustes_reference():
+    L = _L()
+    a, b = _lsm_engine(4, 25, 2, 2, False), _lsm_engine(4, 25, 2, 2, False)
+    ref = a.get(L.F_X)
+    a.set_procrustes_ref(ref); b.set_procrustes_ref(ref)
+    tr = a.run_traced(6, fields_all=(L.F_X,))
+    for r in range(6):
+        b.sweep_latent()
+        b.procrustes()
+        b.center()
+        b.sample_intercepts()
+        assert np.array_equal(tr[L.F_X][r], b.get(L.F_X))
+    assert np.allclose(tr[L.F_X].mean(axis=(2, 3)), 0, atol=1e-12)
+
+
+def test_run_traced_argument_errors():
+    L = _L()
+    e = _lsm_engine(3, 12, 2, 1, False)
+    with pytest.raises(L.DlsmError):
+        e.run_traced(4, fields_all=(L.F_MU,))                 # no mixture fields in an LSM engine
+    with pytest.raises(L.DlsmError):
+        e._ck(e.L.dlsm_run_traced(e.h, 4, 0, L.TraceSpec(thin=0), None, None))
+    out = e.run_traced(0, fields_all=(L.F_X,))
+    assert out[L.F_X].shape[0] == 0
