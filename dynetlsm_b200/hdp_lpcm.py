@@ -293,10 +293,11 @@ class DynamicNetworkHDPLPCM(object):
         self.mu_, self.sigma_ = self.mus_[best, active], self.sigmas_[best, active]
         # co-clustering probabilities over the post-burn-in draws (label_utils.py:40-62)
         self.cooccurrence_probas_ = np.zeros((T, n, n))
-        eye = np.eye(K)
+        eye = np.eye(K, dtype=np.float32)                    # 0/1 indicators: exact in fp32 BLAS
         for t in range(T):
             ind = eye[self.zs_[nb:, t]]                      # (S', n, K)
-            self.cooccurrence_probas_[t] = np.einsum("sik,sjk->ij", ind, ind) / ind.shape[0]
+            flat = ind.transpose(1, 0, 2).reshape(n, -1)     # (n, S' K): one GEMM per time step
+            self.cooccurrence_probas_[t] = (flat @ flat.T).astype(np.float64) / ind.shape[0]
         self.counts_ = np.array([np.unique(zz).size for zz in self.zs_[nb:]])
         # rotate every stored sample onto the point estimate (hdp_lpcm.py:1141-1146)
         for idx in range(self.Xs_.shape[0]):
