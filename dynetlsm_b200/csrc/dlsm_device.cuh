@@ -121,6 +121,9 @@ __device__ const double d_exp_tab[64] = {DLSM_EXP_TAB(DLSM_X)};
 __device__ const double d_expp_tab[64] = {DLSM_EXPP_TAB(DLSM_X)};
 __device__ const double d_rcp_tab[129] = {DLSM_RCP_TAB(DLSM_X)};
 __device__ const double d_log_tab[129] = {DLSM_LOG_TAB(DLSM_X)};
+#define DLSM_X2(r, l) {r, l},
+__device__ __align__(16) const double2 d_rl_tab[129] = {DLSM_RL_TAB(DLSM_X2)}; // {R[i], -log R[i]}
+#undef DLSM_X2
 static const double h_exp_tab[64] = {DLSM_EXP_TAB(DLSM_X)};
 static const double h_expp_tab[64] = {DLSM_EXPP_TAB(DLSM_X)};
 static const double h_rcp_tab[129] = {DLSM_RCP_TAB(DLSM_X)};
@@ -172,13 +175,20 @@ __host__ __device__ __forceinline__ double fast_log1pexp_neg(double a /* = |eta|
     cv.f = y;
     unsigned i = (cv.u[1] - 0x3ff00000u + 0x1000u) >> 13; // 0..128
     i = i < 128u ? i : 128u; // NaN / garbage never indexes out of the table
-    const double z = fma(y, RT[i], -K[9]);
+#ifdef __CUDA_ARCH__
+    const double2 rl = __ldg(&d_rl_tab[i]); // reciprocal and log in one 128-bit load
+    const double Ri = rl.x, Li = rl.y;
+    (void)RT; (void)LT;
+#else
+    const double Ri = RT[i], Li = LT[i];
+#endif
+    const double z = fma(y, Ri, -K[9]);
     double q = fma(z, K[11], K[12]);
     q = fma(z, q, K[13]);
     q = fma(z, q, K[14]);
     q = fma(z, q, K[15]);
     q = fma(z, q, K[9]);
-    return fma(z, q, LT[i]);
+    return fma(z, q, Li);
 }
 
 // log(1 + e^eta) = max(eta, 0) + log1p(e^{-|eta|}); max(eta,0) = (eta + |eta|)/2 keeps NaN alive.
