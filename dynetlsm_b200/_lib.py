@@ -79,7 +79,7 @@ EXPORTS = [
     "dlsm_sweep_latent", "dlsm_center", "dlsm_sample_intercepts", "dlsm_sample_radii",
     "dlsm_sample_labels", "dlsm_set_hdp_prior", "dlsm_hdp_update", "dlsm_run_sweeps", "dlsm_loglik_partial", "dlsm_loglik_full",
     "dlsm_gaussian_likelihood", "dlsm_debug_set_counts", "dlsm_debug_draws", "dlsm_enable_timing", "dlsm_get_counters",
-    "dlsm_logp", "dlsm_set_procrustes_ref", "dlsm_procrustes", "dlsm_run_traced", "dlsm_host_alloc", "dlsm_host_free",
+    "dlsm_resample_controls", "dlsm_get_controls", "dlsm_logp", "dlsm_set_procrustes_ref", "dlsm_procrustes", "dlsm_run_traced", "dlsm_host_alloc", "dlsm_host_free",
 ]
 
 F_X, F_INTERCEPT, F_RADII, F_Z, F_MU, F_SIGMA, F_LAMBDA, F_WEIGHTS = range(8)
@@ -133,6 +133,8 @@ def load():
     L.dlsm_enable_timing.argtypes = [vp, C.c_int]
     L.dlsm_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.dlsm_logp.argtypes = [vp, dp]
+    L.dlsm_resample_controls.argtypes = [vp, C.c_int32, C.c_int32]
+    L.dlsm_get_controls.argtypes = [vp, ip, ip]
     L.dlsm_set_procrustes_ref.argtypes = [vp, dp]
     L.dlsm_procrustes.argtypes = [vp]
     L.dlsm_run_traced.argtypes = [vp, C.c_int32, C.c_uint32, C.POINTER(TraceSpec), C.POINTER(vp), dp]
@@ -284,6 +286,7 @@ class Engine(object):
         if ci.ndim == 3:
             ci, co = ci[None], co[None]
         self._ck(self.L.dlsm_set_controls(self.h, _ip(ci), _ip(co), ci.shape[3], ci.shape[0]))
+        self._n_control, self._ctrl_sets = int(ci.shape[3]), int(ci.shape[0])
 
     def set_hyper(self, tau_sq=2.0, sigma_sq=0.1, intercept_prior=(0.0, 0.0),
                   intercept_variance_prior=2.0):
@@ -399,6 +402,17 @@ class Engine(object):
         if logp:
             out["logp"] = lp
         return out
+
+    def resample_controls(self, n_control, per_chain=False):
+        """Redraw the case-control sets on the device (uniform without replacement)."""
+        self._n_control, self._ctrl_sets = int(n_control), (self.C if per_chain else 1)
+        self._ck(self.L.dlsm_resample_controls(self.h, self._n_control, self._ctrl_sets))
+
+    def get_controls(self):
+        shp = (self._ctrl_sets, self.T, self.n, self._n_control)
+        ci, co = np.empty(shp, np.int32), np.empty(shp, np.int32)
+        self._ck(self.L.dlsm_get_controls(self.h, _ip(ci), _ip(co)))
+        return ci, co
 
     def logp(self):
         out = np.empty((self.C,))

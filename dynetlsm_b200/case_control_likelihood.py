@@ -29,7 +29,7 @@ class DirectedCaseControlSampler(object):
         else:
             self.n_control_ = int(self.n_control * n_nodes)
 
-    def init(self, Y):
+    def init(self, Y, sample=True):
         T, n, _ = Y.shape
         self._resolve_n_control(n)
         deg = np.zeros((T, n, 2), dtype=np.int64)
@@ -42,15 +42,19 @@ class DirectedCaseControlSampler(object):
             order = np.lexsort((src, dst))             # sorted by dst, then src
             _fill_padded(out_e[t], src, dst)
             _fill_padded(in_e[t], dst[order], src[order])
-        return self.init_from_edges(deg, in_e, out_e)
+        return self.init_from_edges(deg, in_e, out_e, sample=sample)
 
-    def init_from_edges(self, degrees, in_edges, out_edges):
+    def init_from_edges(self, degrees, in_edges, out_edges, sample=True):
+        """``sample=False`` leaves the control sets to the device (``Engine.resample_controls``)."""
         self.degrees_ = np.asarray(degrees, dtype=np.int64)
         self.in_edges_ = np.asarray(in_edges, dtype=np.int64)
         self.out_edges_ = np.asarray(out_edges, dtype=np.int64)
         if not hasattr(self, "n_control_"):
             self._resolve_n_control(self.degrees_.shape[1])
-        self.control_nodes_in_, self.control_nodes_out_ = self.sample()
+        if sample:
+            self.control_nodes_in_, self.control_nodes_out_ = self.sample()
+        else:
+            self.control_nodes_in_ = self.control_nodes_out_ = None
         self.n_iter += 1
         return self
 

@@ -59,6 +59,7 @@ struct dlsm_handle {
     // rng
     uint64_t seed = 0, chain_offset = 0;
     uint32_t sweep_idx[5] = {0, 0, 0, 0, 0};
+    uint32_t control_draws = 0;     // Philox sweep index of dlsm_resample_controls
     dlsm_hdp_prior hdp_prior;
     bool have_hdp_prior = false;
     // trace pipeline (dlsm_run_traced): two device chunks of trace_R records each, drained to the
@@ -687,6 +688,48 @@ int dlsm_set_controls(dlsm_handle *h, const int32_t *ctrl_in, const int32_t *ctr
     h->n_control = n_control; h->ctrl_sets = n_sets;
     h->have_ctrl = true;
     return DLSM_OK;
+}
+
+int dlsm_resample_controls(dlsm_handle *h, int32_t n_control, int32_t n_sets)
+{
+    if (!h || n_control < 1) return DLSM_ERR_INVALID;
+    if (!h->have_edges) FAIL(h, DLSM_ERR_NOTSET, "dlsm_set_edge_lists has not been called");
+    if (n_sets != 1 && n_sets != h->cfg.n_chains) FAIL(h, DLSM_ERR_INVALID, "n_sets must be 1 or n_chains");
+    CU(h, cudaSetDevice(h->cfg.device));
+    const dlsm_config &c = h->cfg;
+    const size_t bytes = (size_t)n_sets * c.T * c.n * n_control * 4;
+    if (n_control != h->n_control || n_sets != h->ctrl_sets || !h->ctrl_in) {
+        CU(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->ctrl_in); cudaFree(h->ctrl_out);
+        h->ctrl_in = h->ctrl_out = nullptr;
+        CU(h, cudaMalloc((void **)&h->ctrl_in, bytes));
+        CU(h, cudaMalloc((void **)&h->ctrl_out, bytes));
+        h->n_control = n_control; h->ctrl_sets = n_sets;
+    }
+    ControlParams p;
+    memset(&p, 0, sizeof(p));
+    p.sets = n_sets; p.T = c.T; p.n = c.n; p.n_control = n_control;
+    p.max_in = h->max_in; p.max_out = h->max_out;
+    p.deg = h->deg; p.in_edges = h->in_edges; p.out_edges = h->out_edges;
+    p.ctrl_in = h->ctrl_in; p.ctrl_out = h->ctrl_out;
+    p.seed = h->seed; p.sweep = h->control_draws; p.chain_offset = (uint32_t)h->chain_offset;
+    const size_t warps = (size_t)n_sets * c.T * c.n * 2;
+    int rc = launch_simple(h, k_resample_controls, dim3((unsigned)((warps + 3) / 4)), dim3(128), 0, p);
+    if (rc != DLSM_OK) return rc;
+    h->control_draws += 1;
+    h->have_ctrl = true;
+    return DLSM_OK;
+}
+
+int dlsm_get_controls(dlsm_handle *h, int32_t *ctrl_in, int32_t *ctrl_out)
+{
+    if (!h || !ctrl_in || !ctrl_out) return DLSM_ERR_INVALID;
+    if (!h->have_ctrl) FAIL(h, DLSM_ERR_NOTSET, "no control sets on the device");
+    CU(h, cudaSetDevice(h->cfg.device));
+    const size_t bytes = (size_t)h->ctrl_sets * h->cfg.T * h->cfg.n * h->n_control * 4;
+    int rc = download(h, ctrl_in, h->ctrl_in, bytes);
+    if (rc == DLSM_OK) rc = download(h, ctrl_out, h->ctrl_out, bytes);
+    return rc;
 }
 
 int dlsm_set_state(dlsm_handle *h, int field, const void *host, size_t bytes)

@@ -119,8 +119,6 @@ __device__ __forceinline__ double log1pexp_naive(double eta) { return log(1.0 + 
 #define DLSM_X(v) v,
 __device__ const double d_exp_tab[64] = {DLSM_EXP_TAB(DLSM_X)};
 __device__ const double d_expp_tab[64] = {DLSM_EXPP_TAB(DLSM_X)};
-__device__ const double d_rcp_tab[129] = {DLSM_RCP_TAB(DLSM_X)};
-__device__ const double d_log_tab[129] = {DLSM_LOG_TAB(DLSM_X)};
 #define DLSM_X2(r, l) {r, l},
 __device__ __align__(16) const double2 d_rl_tab[129] = {DLSM_RL_TAB(DLSM_X2)}; // {R[i], -log R[i]}
 #undef DLSM_X2
@@ -152,7 +150,7 @@ static const double h_spc[16] = DLSM_SP_CONSTS;
 __host__ __device__ __forceinline__ double fast_log1pexp_neg(double a /* = |eta| */)
 {
 #ifdef __CUDA_ARCH__
-    const double *ET = d_exp_tab, *RT = d_rcp_tab, *LT = d_log_tab, *K = d_spc;
+    const double *ET = d_exp_tab, *K = d_spc;
 #else
     const double *ET = h_exp_tab, *RT = h_rcp_tab, *LT = h_log_tab, *K = h_spc;
 #endif
@@ -178,7 +176,6 @@ __host__ __device__ __forceinline__ double fast_log1pexp_neg(double a /* = |eta|
 #ifdef __CUDA_ARCH__
     const double2 rl = __ldg(&d_rl_tab[i]); // reciprocal and log in one 128-bit load
     const double Ri = rl.x, Li = rl.y;
-    (void)RT; (void)LT;
 #else
     const double Ri = RT[i], Li = LT[i];
 #endif

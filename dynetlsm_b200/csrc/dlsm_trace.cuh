@@ -276,4 +276,66 @@ __global__ void __launch_bounds__(256) k_snapshot(const SnapParams p)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Case-control sets on the device (DirectedCaseControlSampler.sample,
+// case_control_likelihood.py:75-112): for every (set, t, i) and both directions, min(n - deg - 1,
+// n_control) DISTINCT nodes drawn uniformly from the non-neighbours of i (i itself excluded), the
+// rest of the row padded with -1.  One warp per (set, t, i, direction): rounds of 32 Philox
+// candidates, each accepted in lane order unless it is i, a neighbour, already in the list or a
+// duplicate of a lower lane -- sequential rejection sampling, hence a uniform random subset in
+// uniform random order.  The reference consumes numpy's rng.choice; this is the device-RNG
+// counterpart (same distribution, not the same draws).
+// grid = ceil(sets * T * n * 2 / warps per CTA), block = 128
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kRngControls = 5;
+
+struct ControlParams {
+    int sets, T, n, n_control, max_in, max_out;
+    const int32_t *deg;        // [T][n][2] in, out
+    const int32_t *in_edges;   // [T][n][max_in]
+    const int32_t *out_edges;  // [T][n][max_out]
+    int32_t *ctrl_in, *ctrl_out; // [sets][T][n][n_control]
+    uint64_t seed;
+    uint32_t sweep, chain_offset;
+};
+
+__global__ void __launch_bounds__(128) k_resample_controls(const ControlParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t total = (size_t)p.sets * p.T * p.n * 2;
+    if (wid >= total) return;
+    const int dir = (int)(wid & 1);                 // 0: in-controls, 1: out-controls
+    const size_t row = wid >> 1;                    // (set, t, i)
+    const int i = (int)(row % p.n);
+    const size_t ti = row % ((size_t)p.T * p.n);
+    const int set = (int)(row / ((size_t)p.T * p.n));
+    const int deg = p.deg[ti * 2 + dir];
+    const int32_t *nb = dir == 0 ? p.in_edges + ti * p.max_in : p.out_edges + ti * p.max_out;
+    int32_t *out = (dir == 0 ? p.ctrl_in : p.ctrl_out) + row * p.n_control;
+    int want = p.n - deg - 1;
+    want = want < p.n_control ? want : p.n_control;
+    want = want > 0 ? want : 0;
+    int have = 0;
+    for (uint32_t round = 0; have < want && round < (1u << 20); round++) {
+        const U2 u = philox_u2(p.seed, (uint32_t)(ti * 2 + dir), p.sweep, (uint32_t)set + p.chain_offset,
+                               kRngControls, round * 16 + (lane >> 1));
+        int c = (int)(((lane & 1) ? u.b : u.a) * p.n);
+        c = c < p.n ? c : p.n - 1;
+        bool ok = c != i;
+        for (int q = 0; ok && q < deg; q++) ok = nb[q] != c;          // neighbour lists are short
+        for (int q = 0; ok && q < have; q++) ok = out[q] != c;        // already drawn
+        const unsigned same = __match_any_sync(kFull, ok ? c : -1 - lane); // duplicates in the batch
+        ok = ok && lane == __ffs(same) - 1;
+        const unsigned acc = __ballot_sync(kFull, ok);
+        const int pos = have + __popc(acc & ((1u << lane) - 1u));
+        if (ok && pos < want) out[pos] = c;
+        have += __popc(acc);
+        have = have < want ? have : want;
+        __syncwarp();
+    }
+    for (int q = want + lane; q < p.n_control; q += 32) out[q] = -1;
+}
+
 } // namespace dlsm

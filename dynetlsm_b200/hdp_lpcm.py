@@ -101,7 +101,7 @@ class DynamicNetworkHDPLPCM(object):
                                  "supported for directed networks.")
             self.case_control_sampler_ = DirectedCaseControlSampler(
                 n_control=self.n_control, n_resample=self.n_resample_control, random_state=rng)
-            self.case_control_sampler_.init(Y)
+            self.case_control_sampler_.init(Y, sample=replay)
         if isinstance(self.intercept_prior, str) and self.intercept_prior == "auto":
             self.intercept_prior = ics[0]   # (sic) a view of the trace's first row, as in the reference
 
@@ -219,9 +219,9 @@ class DynamicNetworkHDPLPCM(object):
             while it < S:
                 stop = min(S, it + seg)
                 if cc is not None:              # hdp_lpcm.py:826-829
-                    cc.resample()
-                    if cc.resampled_:
-                        drv.push_controls()
+                    if cc.n_resample is not None and cc.n_iter % cc.n_resample == 0:
+                        drv.draw_controls()
+                    cc.n_iter += 1
                     quiet = S if cc.n_resample is None else (cc.n_resample - cc.n_iter % cc.n_resample) % cc.n_resample
                     stop = min(stop, it + 1 + quiet)
                 tr = e.run_traced(stop - it, fields_all=every, fields_first=first, pinned=True)
@@ -248,6 +248,9 @@ class DynamicNetworkHDPLPCM(object):
                 it = stop
             if hya is not None:
                 (hp.gamma, hp.alpha_init, hp.alpha, hp.kappa, hp.mean_variance_prior, hp.b) = hya[:6]
+            if cc is not None:
+                ci, co = e.get_controls()
+                cc.control_nodes_in_, cc.control_nodes_out_ = ci[0].astype(np.int64), co[0].astype(np.int64)
         self.chains_ = chains
 
         # mirror the reference's mutable hyper-parameter attributes

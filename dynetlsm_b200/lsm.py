@@ -52,9 +52,16 @@ class _Driver(object):
             self.engine.set_network(Y)
         else:
             self.engine.set_edge_lists(self.cc.degrees_, self.cc.in_edges_, self.cc.out_edges_)
-            self.push_controls()
+            if self.cc.control_nodes_in_ is not None:
+                self.push_controls()
         if not replay:
             self.engine.set_rng(_philox_seed(rng))
+            if self.cc is not None and self.cc.control_nodes_in_ is None:
+                self.draw_controls()
+
+    def draw_controls(self):
+        """Device-side redraw of the control sets, one set per chain."""
+        self.engine.resample_controls(self.cc.n_control_, per_chain=self.C > 1)
 
     def push_controls(self):
         self.engine.set_controls(self.cc.control_nodes_in_, self.cc.control_nodes_out_)
@@ -234,9 +241,9 @@ class DynamicNetworkLSM(object):
             if it <= n_iter_procrustes:
                 stop = min(stop, n_iter_procrustes + 1)
             if cc is not None:                     # lsm.py:478-481, case_control_likelihood.py:27-33
-                cc.resample()
-                if cc.resampled_:
-                    drv.push_controls()
+                if cc.n_resample is not None and cc.n_iter % cc.n_resample == 0:
+                    drv.draw_controls()            # dlsm_resample_controls: no host sampling
+                cc.n_iter += 1
                 # iterations whose resample() call is a no-op are batched with this one
                 quiet = S if cc.n_resample is None else (cc.n_resample - cc.n_iter % cc.n_resample) % cc.n_resample
                 stop = min(stop, it + 1 + quiet)
@@ -253,6 +260,9 @@ class DynamicNetworkLSM(object):
                 cc.n_iter += stop - it - 1
             it = stop
         e.set_procrustes_ref(None)
+        if cc is not None:                         # expose the last sets under the reference's names
+            ci, co = e.get_controls()
+            cc.control_nodes_in_, cc.control_nodes_out_ = ci[0].astype(np.int64), co[0].astype(np.int64)
 
     def fit(self, Y):
         """Sample from the posterior given the dynamic network ``Y`` (T, n, n), entries 0/1."""
@@ -303,7 +313,7 @@ class DynamicNetworkLSM(object):
                                  "supported for directed networks.")
             self.case_control_sampler_ = DirectedCaseControlSampler(
                 n_control=self.n_control, n_resample=self.n_resample_control, random_state=rng)
-            self.case_control_sampler_.init(Y)
+            self.case_control_sampler_.init(Y, sample=replay)   # device mode draws them on the GPU
 
         # ---- device state ----
         drv = _Driver(Y, self.n_features, C, self.is_directed, self.case_control_sampler_, 0,

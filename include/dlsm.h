@@ -142,6 +142,14 @@ int dlsm_set_edge_lists(dlsm_handle *h, const int32_t *degrees, const int32_t *i
 int dlsm_set_controls(dlsm_handle *h, const int32_t *ctrl_in, const int32_t *ctrl_out,
                       int32_t n_control, int32_t n_sets);
 
+/* Device-side redraw of the control sets (DirectedCaseControlSampler.sample,
+ * case_control_likelihood.py:75-112) on the Philox streams: for every node and direction
+ * min(n - degree - 1, n_control) distinct non-neighbours, uniformly, -1 padded; n_sets = 1 (shared)
+ * or n_chains (one set per chain).  Needs dlsm_set_edge_lists.  dlsm_get_controls copies the
+ * current sets (n_sets,T,n,n_control) to the host. */
+int dlsm_resample_controls(dlsm_handle *h, int32_t n_control, int32_t n_sets);
+int dlsm_get_controls(dlsm_handle *h, int32_t *ctrl_in, int32_t *ctrl_out);
+
 /* ---- chain state ----------------------------------------------------------------------- */
 int dlsm_set_state(dlsm_handle *h, int field, const void *host, size_t bytes);
 int dlsm_get_state(dlsm_handle *h, int field, void *host, size_t bytes);

@@ -220,3 +220,74 @@ def test_run_traced_argument_errors():
         e._ck(e.L.dlsm_run_traced(e.h, 4, 0, L.TraceSpec(thin=0), None, None))
     out = e.run_traced(0, fields_all=(L.F_X,))
     assert out[L.F_X].shape[0] == 0
+
+
+def _edge_engine(T, n, C_, density, seed):
+    L = _L()
+    from dynetlsm_b200.case_control_likelihood import DirectedCaseControlSampler
+    rng = np.random.RandomState(seed)
+    Y = _net(rng, T, n, True, density)
+    cc = DirectedCaseControlSampler(n_control=5, n_resample=10, random_state=rng).init(Y, sample=False)
+    e = L.Engine(T=T, n=n, d=2, n_chains=C_, is_directed=True, case_control=True)
+    e.set_edge_lists(cc.degrees_, cc.in_edges_, cc.out_edges_)
+    return e, Y
+
+
+@pytest.mark.parametrize("n,m,density,per_chain", [(30, 7, 0.15, False), (12, 20, 0.3, True), (64, 33, 0.05, True)])
+def test_device_control_sets_are_valid(n, m, density, per_chain):
+    """dlsm_resample_controls (case_control_likelihood.py:75-112 on the device RNG): the right number
+    of distinct non-neighbours per node and direction, -1 padded, never the node itself."""
+    T, C_ = 3, 3
+    e, Y = _edge_engine(T, n, C_, density, seed=n)
+    e.set_rng(123)
+    e.resample_controls(m, per_chain=per_chain)
+    ci, co = e.get_controls()
+    assert ci.shape == ((C_ if per_chain else 1), T, n, m)
+    for s in range(ci.shape[0]):
+        for t in range(T):
+            for i in range(n):
+                for arr, nbrs in ((ci, np.nonzero(Y[t][:, i])[0]), (co, np.nonzero(Y[t][i])[0])):
+                    row = arr[s, t, i]
+                    want = min(n - nbrs.size - 1, m)
+                    got = row[:want]
+                    assert np.all(got >= 0) and np.all(row[want:] == -1)
+                    assert np.unique(got).size == want
+                    assert i not in got and not np.intersect1d(got, nbrs).size
+    first = ci.copy()
+    e.resample_controls(m, per_chain=per_chain)
+    assert not np.array_equal(first, e.get_controls()[0])          # a new draw
+    e2, _ = _edge_engine(T, n, C_, density, seed=n)
+    e2.set_rng(123)
+    e2.resample_controls(m, per_chain=per_chain)
+    assert np.array_equal(first, e2.get_controls()[0])             # same seed, same sets
+    if per_chain:
+        assert not np.array_equal(first[0], first[1])
+
+
+def test_device_control_sets_are_uniform():
+    """Every eligible node is equally likely to be a control (and equally likely in every slot)."""
+    T, n, m, C_ = 1, 10, 3, 4096
+    e, Y = _edge_engine(T, n, C_, 0.2, seed=1)
+    e.set_rng(9)
+    e.resample_controls(m, per_chain=True)
+    ci, co = e.get_controls()
+    for arr, nb_of in ((co, lambda i: np.nonzero(Y[0][i])[0]), (ci, lambda i: np.nonzero(Y[0][:, i])[0])):
+        for i in (0, 4, 9):
+            elig = np.setdiff1d(np.arange(n), np.r_[nb_of(i), i])
+            want = min(elig.size, m)
+            for slot in range(want):
+                cnt = np.bincount(arr[:, 0, i, slot], minlength=n)[elig]
+                exp = C_ / elig.size
+                chi2 = np.sum((cnt - exp) ** 2 / exp)
+                assert chi2 < 40.0, (i, slot, cnt)              # dof <= 8: p ~ 1e-6
+
+
+def test_device_mode_case_control_fit_runs():
+    from dynetlsm_b200 import DynamicNetworkLSM
+    rng = np.random.RandomState(0)
+    Y = _net(rng, 3, 25, True, 0.2)
+    m = DynamicNetworkLSM(is_directed=True, n_iter=40, tune=20, burn=20, n_control=6, n_resample_control=15,
+                          random_state=1, n_chains=2).fit(Y)
+    assert m.Xs_.shape == (80, 3, 25, 2) and np.all(np.isfinite(m.logps_))
+    cc = m.case_control_sampler_
+    assert cc.control_nodes_in_.shape == (3, 25, 6) and cc.control_nodes_out_.max() < 25
