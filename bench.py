@@ -503,6 +503,23 @@ def main():
         e2e = {"value": world * upd_per_step * nst / float(tt.item()), "unit": "node-updates/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": nst,
                "api": "Engine.set(state) -> run_sweeps(1) -> Engine.get(state) over the dlsm C-ABI"}
+        # the same state leaving the device every sweep through the streaming call fit() uses
+        # (dlsm_run_traced: device trace ring drained on a copy stream while the next sweeps run);
+        # no per-step host input exists in this mode, so it is reported beside e2e, not as e2e
+        ntr = 3 * nst
+        tr = e.run_traced(ntr, fields_all=outs, pinned=True)   # allocates the pinned destination
+        barrier()
+        t0 = time.perf_counter()
+        tr = e.run_traced(ntr, fields_all=outs, pinned=True, out=tr)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e["traced"] = {"value": world * upd_per_step * ntr / float(tt.item()), "unit": "node-updates/s",
+                         "steps": ntr, "d2h_bytes_per_step": int(sum(a.nbytes for a in tr.values()) // ntr),
+                         "api": "Engine.run_traced(n, every state field of every chain, pinned destination)"}
+        del tr
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -194,6 +194,11 @@ def pinned_empty(shape, dtype=np.float64):
     return raw[:nbytes].view(dtype).reshape(shape)
 
 
+class _TraceDict(dict):
+    """Result of Engine.run_traced; keeps the (possibly larger) destination buffers for reuse."""
+    _base = None
+
+
 class Engine(object):
     """Device-resident sampler state for ``n_chains`` chains sharing one dynamic network."""
 
@@ -375,33 +380,43 @@ class Engine(object):
 
     def run_traced(self, n_sweeps, fields_all=(), fields_first=(), thin=1, logp=True, pinned=False,
                    skip_center=False, skip_intercepts=False, skip_radii=False, skip_labels=False,
-                   skip_hdp=False):
+                   skip_hdp=False, out=None):
         """``n_sweeps`` sweeps on the device, recording every ``thin``-th state: returns
         ``{field: array (records, C or 1, ...)}`` plus ``"logp": (records, C)``.  The copies to the
-        host overlap the following sweeps."""
+        host overlap the following sweeps.  ``out``: a dict returned by an earlier call with at
+        least as many records, reused as the destination (page-locking memory is slow: allocate
+        once, then pass it back in); the returned arrays are views of its first ``records`` rows."""
         flags = (1 if skip_center else 0) | (2 if skip_intercepts else 0) | \
                 (4 if skip_radii else 0) | (8 if skip_labels else 0) | (16 if skip_hdp else 0)
         rec = int(n_sweeps) // int(thin)
         alloc = pinned_empty if pinned else np.empty
         spec = TraceSpec(thin=int(thin), want_logp=int(bool(logp)))
         dst = (C.c_void_p * N_FIELDS)()
-        out = {}
+        base = out._base if isinstance(out, _TraceDict) else (out or {})
+        res = _TraceDict()
+        res._base = base
+
+        def buffer(key, shape, dtype):
+            a = base.get(key)
+            if a is None or a.shape[0] < rec or a.shape[1:] != shape[1:] or a.dtype != dtype:
+                a = base[key] = alloc(shape, dtype)
+            return a
         for group, first in ((fields_all, False), (fields_first, True)):
             for f in group:
                 shp = self.shape_of(f)
-                a = alloc((rec, 1 if first else shp[0]) + tuple(shp[1:]),
-                          np.int32 if f in _INT_FIELDS else np.float64)
-                out[f] = a
+                a = buffer(f, (rec, 1 if first else shp[0]) + tuple(shp[1:]),
+                           np.dtype(np.int32 if f in _INT_FIELDS else np.float64))
+                res[f] = a[:rec]
                 dst[f] = a.ctypes.data
                 if first:
                     spec.fields_first |= 1 << f
                 else:
                     spec.fields_all |= 1 << f
-        lp = alloc((rec, self.C), np.float64) if logp else None
+        lp = buffer("logp", (rec, self.C), np.dtype(np.float64)) if logp else None
         self._ck(self.L.dlsm_run_traced(self.h, int(n_sweeps), flags, C.byref(spec), dst, _dp(lp)))
         if logp:
-            out["logp"] = lp
-        return out
+            res["logp"] = lp[:rec]
+        return res
 
     def resample_controls(self, n_control, per_chain=False):
         """Redraw the case-control sets on the device (uniform without replacement)."""

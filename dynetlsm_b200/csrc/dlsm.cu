@@ -1397,7 +1397,11 @@ int dlsm_run_traced(dlsm_handle *h, int32_t n_sweeps, uint32_t flags, const dlsm
     if (sp->want_logp && n_records > 0 && !logp_dst) FAIL(h, DLSM_ERR_INVALID, "no destination for the log-posterior trace");
     if ((rc = prepare_trace(h, sp, n_records)) != DLSM_OK) return rc;
     const bool tracing = h->trace_R > 0 && n_records > 0;
-    const int R = h->trace_R;
+    // records per chunk: the allocated capacity, but at least ~4 chunks per call so that the copy
+    // of one chunk overlaps the sweeps filling the next even in short, heavy runs
+    int R = h->trace_R;
+    if (R > (n_records + 3) / 4) R = (n_records + 3) / 4;
+    if (R < 1) R = 1;
     int cur = 0, fill = 0;          // chunk being filled, records in it
     size_t done = 0;                // records handed to earlier chunks
     int pending = -1, pending_n = 0; // filled chunk not yet drained (one chunk of lookahead keeps

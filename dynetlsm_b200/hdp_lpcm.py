@@ -212,7 +212,8 @@ class DynamicNetworkHDPLPCM(object):
             first = (L.F_X, L.F_MU, L.F_SIGMA, L.F_BETA, L.F_WEIGHTS) + ((L.F_RADII,) if self.is_directed else ())
             every = (L.F_INTERCEPT, L.F_LAMBDA, L.F_Z, L.F_HYPER)
             rec_bytes = 8 * (T * n * d + K * d + 2 * K + T * K * K + n) + C * (4 * T * n + 8 * 12)
-            seg = int(max(1, min(S, (256 << 20) // rec_bytes)))
+            seg = int(max(1, min(S, (128 << 20) // rec_bytes)))   # bounded, reused pinned destination
+            tr = None
             cc = self.case_control_sampler_
             hya = None
             it = 1
@@ -224,7 +225,7 @@ class DynamicNetworkHDPLPCM(object):
                     cc.n_iter += 1
                     quiet = S if cc.n_resample is None else (cc.n_resample - cc.n_iter % cc.n_resample) % cc.n_resample
                     stop = min(stop, it + 1 + quiet)
-                tr = e.run_traced(stop - it, fields_all=every, fields_first=first, pinned=True)
+                tr = e.run_traced(stop - it, fields_all=every, fields_first=first, pinned=True, out=tr)
                 if cc is not None:
                     cc.n_iter += stop - it - 1
                 sl = slice(it, stop)

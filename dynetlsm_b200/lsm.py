@@ -235,7 +235,9 @@ class DynamicNetworkLSM(object):
         e, C, m = drv.engine, self.n_chains, (2 if self.is_directed else 1)
         cc = self.case_control_sampler_
         fields = (L.F_X, L.F_INTERCEPT) + ((L.F_RADII,) if self.is_directed else ())
-        it = 1
+        rec_bytes = 8 * C * (self.Y_fit_.shape[0] * self.Y_fit_.shape[1] * (self.n_features + 1) + 4)
+        seg = int(max(1, min(S, (128 << 20) // rec_bytes)))   # bounded, reused pinned destination
+        it, tr = 1, None
         while it < S:
             stop = S
             if it <= n_iter_procrustes:
@@ -250,7 +252,8 @@ class DynamicNetworkLSM(object):
             if it == n_iter_procrustes + 1:        # lsm.py:495-498
                 ref = np.stack([Xs[c, np.argmax(logps[c, :(n_iter_procrustes + 1)])] for c in range(C)])
                 e.set_procrustes_ref(ref)
-            tr = e.run_traced(stop - it, fields_all=fields, pinned=True)
+            stop = min(stop, it + seg)
+            tr = e.run_traced(stop - it, fields_all=fields, pinned=True, out=tr)
             Xs[:, it:stop] = tr[L.F_X].transpose(1, 0, 2, 3, 4)
             ics[:, it:stop] = tr[L.F_INTERCEPT].transpose(1, 0, 2)[:, :, :m]
             if self.is_directed:
