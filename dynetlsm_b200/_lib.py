@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libdlsm.so")
 SRC = [os.path.join(HERE, "csrc", f) for f in ("dlsm.cu", "dlsm_kernels.cuh", "dlsm_device.cuh",
-                                              "dlsm_tables.cuh", "dlsm_hdp.cuh")]
+                                              "dlsm_tables.cuh", "dlsm_hdp.cuh", "dlsm_trace.cuh")]
 SRC.append(os.path.join(ROOT, "include", "dlsm.h"))
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
