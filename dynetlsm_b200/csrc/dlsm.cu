@@ -993,6 +993,7 @@ static int labels_async(dlsm_handle *h, const double *d_U, double *lik_out, int 
             int per_sm = 0;
             CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 64, tables));
             if (per_sm < 1) per_sm = 1;
+            if (const char *cap = getenv("DLSM_FFBS_PER_SM")) per_sm = atoi(cap) > 0 && atoi(cap) < per_sm ? atoi(cap) : per_sm;
             int sms = 148;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
             long grid = (long)sms * per_sm;
