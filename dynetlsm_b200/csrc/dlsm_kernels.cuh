@@ -1383,7 +1383,9 @@ __global__ void __launch_bounds__(256) k_radii_propose(int n, const double *radi
     tot = block_sum(tot, sh);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         q[i] = q[i] / tot;
-        if (q[i] == 0.0) any_zero = 1;
+        // metropolis.py:65 tests `== 0`; a subnormal component is treated the same way: its
+        // reciprocal is inf and the likelihood NaN (in the reference as well)
+        if (q[i] < 2.2250738585072014e-308) any_zero = 1;
     }
     __syncthreads();
     if (any_zero) {

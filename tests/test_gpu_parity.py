@@ -497,3 +497,34 @@ def test_tracked_loglik_matches_full_kernel(T, n, d, directed, monkeypatch):
     assert np.array_equal(a.get(L.F_INTERCEPT), b.get(L.F_INTERCEPT))
     if directed:
         assert np.array_equal(a.get(L.F_RADII), b.get(L.F_RADII))
+
+
+def test_native_radii_sampler_targets_the_flat_dirichlet_prior():
+    """With both intercepts at 0 the likelihood does not depend on the radii, so the device radii
+    MH (gamma-variate Dirichlet proposal on Philox, Hastings correction of metropolis.py:57-82) must
+    leave the flat Dirichlet prior invariant: checks proposal, correction and RNG together."""
+    L = _F()
+    T, n, d, C_ = 2, 5, 2, 4096
+    rng = np.random.RandomState(0)
+    e = _engine(T=T, n=n, d=d, n_chains=C_, is_directed=True, radii_tune=None)
+    e.set_network(np.zeros((T, n, n)))
+    e.set(L.F_X, rng.randn(C_, T, n, d))
+    e.set(L.F_INTERCEPT, np.zeros((C_, 2)))
+    e.set(L.F_RADII, rng.dirichlet(np.ones(n) * 30, size=C_))     # far from the target's spread
+    e.set_tuner(0.1, 0.1, 60.0)   # broad proposals Dir(60 r), yet no gamma variate can underflow
+    e.set_rng(3)
+    acc = 0.0
+    for _ in range(400):
+        a, _ = e.sample_radii(want_stats=True)
+        acc += a.mean()
+    assert 0.15 < acc / 400 < 0.95
+    r = e.get(L.F_RADII)
+    assert np.allclose(r.sum(axis=1), 1.0, atol=1e-12) and np.all(r > 0)
+    # Dirichlet(1,...,1): mean 1/n, variance (n-1)/(n^2 (n+1)), P(r_i < x) = 1 - (1-x)^(n-1)
+    assert np.all(np.abs(r.mean(axis=0) - 1.0 / n) < 5 * np.sqrt((n - 1) / (n * n * (n + 1.0)) / C_))
+    var = (n - 1) / (n * n * (n + 1.0))
+    assert np.all(np.abs(r.var(axis=0) / var - 1.0) < 0.12)
+    for x in (0.05, 0.2, 0.5):
+        want = 1 - (1 - x) ** (n - 1)
+        got = (r < x).mean(axis=0)
+        assert np.all(np.abs(got - want) < 5 * np.sqrt(want * (1 - want) / C_) + 0.01), (x, got, want)
