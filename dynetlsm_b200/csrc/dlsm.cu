@@ -35,6 +35,8 @@ struct dlsm_handle {
     int32_t *deg = nullptr, *in_edges = nullptr, *out_edges = nullptr;
     int32_t *ctrl_in = nullptr, *ctrl_out = nullptr;
     int max_in = 0, max_out = 0, n_control = 0, ctrl_sets = 0;
+    int32_t *d_cc_dep = nullptr;     // [ctrl_sets][T][n] batch schedule of the case-control sweep
+    bool cc_dep_valid = false;
     bool have_net = false, have_edges = false, have_ctrl = false;
     // state
     void *field[DLSM_F_COUNT_] = {nullptr};
@@ -339,9 +341,35 @@ int launch_slice_t(dlsm_handle *h, const SweepParams &p, int nw)
     return DLSM_OK;
 }
 
+// case-control sweep, batch-parallel: a warp per node of a run of mutually independent nodes
+int launch_cc_batch(dlsm_handle *h, const SweepParams &p)
+{
+    const dlsm_config &c = h->cfg;
+    const size_t CT = (size_t)c.n_chains * c.T;
+    if (!h->cc_dep_valid) {
+        const size_t cells = (size_t)h->ctrl_sets * c.T * c.n;
+        cudaFree(h->d_cc_dep);
+        h->d_cc_dep = nullptr;
+        CU(h, cudaMalloc((void **)&h->d_cc_dep, cells * sizeof(int32_t)));
+        k_cc_deps<<<(unsigned)((cells * 32 + 255) / 256), 256, 0, h->stream>>>(p.net, h->ctrl_sets, h->d_cc_dep);
+        CHECK_LAUNCH(h);
+        h->ctr.kernel_launches += 1;
+        h->cc_dep_valid = true;
+    }
+    CU(h, cudaMemsetAsync(h->d_progress, 0, CT * sizeof(int), h->stream));
+    CU(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
+    const int nw = 16;
+    const size_t smem = sweep_stage_doubles(c.d) * sizeof(double) + 64 * sizeof(int) + 16;
+    if (c.d == 2) k_sweep_cc<2><<<(unsigned)CT, nw * 32, smem, h->stream>>>(p, h->d_progress, h->d_ticket, h->d_cc_dep);
+    else k_sweep_cc<0><<<(unsigned)CT, nw * 32, smem, h->stream>>>(p, h->d_progress, h->d_ticket, h->d_cc_dep);
+    CHECK_LAUNCH(h);
+    return DLSM_OK;
+}
+
 template <int LK>
 int launch_slice_lk(dlsm_handle *h, const SweepParams &p)
 {
+    if (LK == kCaseControl && !h->no_pipeline) return launch_cc_batch(h, p);
     const int nw = slice_warps(h);
     const bool xs = slice_smem(h, true, nw + 1) + 4096 <= kMaxSmem / 2;
     if (h->cfg.d == 2) return xs ? launch_slice_t<LK, 2, true>(h, p, nw) : launch_slice_t<LK, 2, false>(h, p, nw);
@@ -419,7 +447,8 @@ int launch_full(dlsm_handle *h, const double *rinv0, const double *rinv1, int nv
     if (smem > kMaxSmem) FAIL(h, DLSM_ERR_UNSUPPORTED, "n too large for the exact full-network kernel");
     if (h->lk == kUndirected) LAUNCH_FULL(kUndirected);
     else if (h->lk == kDirected) LAUNCH_FULL(kDirected);
-    else LAUNCH_FULL_NV(kCaseControl, 0, 2); // runtime d; always both variants
+    else if (nv == 1) LAUNCH_FULL_NV(kCaseControl, 0, 1); // runtime d
+    else LAUNCH_FULL_NV(kCaseControl, 0, 2);
 #undef LAUNCH_FULL_NV
 #undef LAUNCH_FULL
     CHECK_LAUNCH(h);
@@ -585,7 +614,8 @@ void dlsm_destroy(dlsm_handle *h)
     void *ptrs[] = {h->rowbits, h->colbits, h->deg, h->in_edges, h->out_edges, h->ctrl_in,
                     h->ctrl_out, h->rinv, h->d_eps, h->d_logu, h->d_ratio, h->d_out, h->d_acc,
                     h->d_partial, h->d_bvar, h->d_prop, h->d_ll2, h->d_rprop, h->d_rprop_inv,
-                    h->d_small, h->d_small_i, h->d_flags, h->d_bad, h->d_progress, h->d_ticket, h->d_ffbs_stage};
+                    h->d_small, h->d_small_i, h->d_flags, h->d_bad, h->d_progress, h->d_ticket, h->d_ffbs_stage,
+                    h->d_cc_dep};
     for (void *p : ptrs) cudaFree(p);
     free_trace(h);
     cudaFree(h->d_logp);
@@ -664,6 +694,7 @@ int dlsm_set_edge_lists(dlsm_handle *h, const int32_t *degrees, const int32_t *i
     CU(h, cudaStreamSynchronize(h->stream));
     h->max_in = max_in; h->max_out = max_out;
     h->have_edges = true;
+    h->cc_dep_valid = false;
     return DLSM_OK;
 }
 
@@ -687,6 +718,7 @@ int dlsm_set_controls(dlsm_handle *h, const int32_t *ctrl_in, const int32_t *ctr
     CU(h, cudaStreamSynchronize(h->stream));
     h->n_control = n_control; h->ctrl_sets = n_sets;
     h->have_ctrl = true;
+    h->cc_dep_valid = false;
     return DLSM_OK;
 }
 
@@ -718,6 +750,7 @@ int dlsm_resample_controls(dlsm_handle *h, int32_t n_control, int32_t n_sets)
     if (rc != DLSM_OK) return rc;
     h->control_draws += 1;
     h->have_ctrl = true;
+    h->cc_dep_valid = false;
     return DLSM_OK;
 }
 
@@ -1136,9 +1169,8 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
     p.fuse_center = fuse ? 1 : 0;
     // the chain kernel also hands over the full-network log-likelihood of the state it leaves
     // behind, so the intercept / radii MH below evaluates only its proposals
-    const bool use_cur = !use_slice_kernel(h) && h->lk != kCaseControl && !getenv("DLSM_NO_LLCUR");
+    bool use_cur = !use_slice_kernel(h) && h->lk != kCaseControl && !getenv("DLSM_NO_LLCUR");
     p.ll_cur = use_cur ? F<double>(h, DLSM_F_LOGLIK) : nullptr;
-    if (tracked) *tracked = use_cur;
     tl_begin(h, "sweep");
     if ((rc = launch_sweep(h, p)) != DLSM_OK) return rc;
     tl_end(h);
@@ -1177,6 +1209,22 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
         h->stream = main_stream;
         if (rc != DLSM_OK) return rc;
     }
+    // Where the sweep kernel does not track the log-likelihood (case-control lists, CTA-per-slice
+    // kernels) one evaluation of the current state serves all the MH steps of this sweep: 1 + 3
+    // variant evaluations instead of 3 x 2.
+    const bool any_mh = !(flags & 2u) || (h->cfg.is_directed && !(flags & 4u));
+    if (!use_cur && any_mh && !getenv("DLSM_NO_LLCUR")) {
+        const int C = h->cfg.n_chains;
+        rc = launch_simple(h, k_bvar_current, dim3((C + 127) / 128), dim3(128), 0, C,
+                           (const double *)F<double>(h, DLSM_F_INTERCEPT), h->d_bvar);
+        if (rc == DLSM_OK) rc = launch_full(h, h->rinv, h->rinv, 1);
+        if (rc == DLSM_OK)
+            rc = launch_simple(h, k_sum_partials, dim3((C + 127) / 128), dim3(128), 0, C, h->full_nblk,
+                               (const double *)h->d_partial, h->d_ll2, F<double>(h, DLSM_F_LOGLIK));
+        if (rc != DLSM_OK) return rc;
+        use_cur = true;
+    }
+    if (tracked) *tracked = use_cur;
     tl_begin(h, "intercepts");
     if (!(flags & 2u) && (rc = intercepts_async(h, nullptr, nullptr, nullptr, nullptr, use_cur)) != DLSM_OK) return rc;
     tl_end(h);
@@ -1225,7 +1273,7 @@ static int logp_async(dlsm_handle *h, double *out_dev, bool ll_tracked)
         if (rc != DLSM_OK) return rc;
         if ((rc = launch_full(h, h->rinv, h->rinv, 1)) != DLSM_OK) return rc;
         rc = launch_simple(h, k_sum_partials, dim3((c.n_chains + 127) / 128), dim3(128), 0, c.n_chains,
-                           h->full_nblk, (const double *)h->d_partial, h->d_ll2);
+                           h->full_nblk, (const double *)h->d_partial, h->d_ll2, (double *)nullptr);
         if (rc != DLSM_OK) return rc;
         p.ll = h->d_ll2; p.ll_stride = 2;
     }
@@ -1487,7 +1535,7 @@ int dlsm_loglik_full(dlsm_handle *h, double *out)
     if (rc != DLSM_OK) return rc;
     if ((rc = launch_full(h, h->rinv, h->rinv)) != DLSM_OK) return rc;
     rc = launch_simple(h, k_sum_partials, dim3((C + 127) / 128), dim3(128), 0, C, h->full_nblk,
-                       (const double *)h->d_partial, h->d_ll2);
+                       (const double *)h->d_partial, h->d_ll2, (double *)nullptr);
     if (rc != DLSM_OK) return rc;
     std::vector<double> tmp((size_t)C * 2);
     if ((rc = download(h, tmp.data(), h->d_ll2, (size_t)C * 16)) != DLSM_OK) return rc;

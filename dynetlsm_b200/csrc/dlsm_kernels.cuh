@@ -190,49 +190,94 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
             vo = eta_directed(b0, b1, dd, r_recv, r_send);
         };
         const int q0 = wteam * 32 + lane, qs = 32 * nteam;
-        for (int q = q0; q < indeg; q += qs) { // :108-119
-            double vn, vo;
-            eta_pair(ie[q], true, vn, vo);
-            e_n += logit_term(0.5, vn);
-            e_o += logit_term(0.5, vo);
-        }
-        for (int q = q0; q < outdeg; q += qs) { // :122-133
-            double vn, vo;
-            eta_pair(oe[q], false, vn, vo);
-            e_n += logit_term(0.5, vn);
-            e_o += logit_term(0.5, vo);
-        }
-        // usable controls = prefix of ctrl_in before its first -1 (:137; and :161, which tests the
-        // IN list while walking the OUT list)
-        int m = net.n_control;
-        for (int base = 0; base < net.n_control; base += 32) {
-            const int q = base + lane;
-            const bool stop = (q < net.n_control) && (ci[q] == -1);
-            const unsigned bal = __ballot_sync(kFull, stop);
-            if (bal) { m = base + __ffs(bal) - 1; break; }
-        }
-        int m_out = m;
-        for (int base = 0; base < m; base += 32) { // the reference reads X[-1] here: flag + stop
-            const int q = base + lane;
-            const bool bad = (q < m) && (co[q] < 0);
-            const unsigned bal = __ballot_sync(kFull, bad);
-            if (bal) {
-                m_out = base + __ffs(bal) - 1;
-                if (lane == 0 && wteam == 0) atomicOr(flags, 2u);
-                break;
+        // Edge lists, two trips per pass: both index loads and then both position gathers are
+        // independent, so their L2 round trips overlap (a list walk is a chain of dependent loads).
+        // Per-lane accumulation order is unchanged (q, q + qs, q + 2 qs, ...).
+        auto edge_list = [&](const int32_t *lst, int len, bool k_sends) {
+            for (int q = q0; q < len; q += 2 * qs) {
+                const int qb = q + qs;
+                const bool two = qb < len;
+                const int ka = lst[q], kb = lst[two ? qb : q];
+                double an, ao, bn, bo;
+                eta_pair(ka, k_sends, an, ao);
+                eta_pair(kb, k_sends, bn, bo);
+                e_n += logit_term(0.5, an);
+                e_o += logit_term(0.5, ao);
+                if (two) {
+                    e_n += logit_term(0.5, bn);
+                    e_o += logit_term(0.5, bo);
+                }
             }
-        }
-        for (int q = q0; q < m; q += qs) { // :136-152
-            double vn, vo;
-            eta_pair(ci[q], true, vn, vo);
-            ci_n += log1pexp(vn);
-            ci_o += log1pexp(vo);
-        }
-        for (int q = q0; q < m_out; q += qs) { // :160-176
-            double vn, vo;
-            eta_pair(co[q], false, vn, vo);
-            co_n += log1pexp(vn);
-            co_o += log1pexp(vo);
+        };
+        edge_list(ie, indeg, true);  // :108-119
+        edge_list(oe, outdeg, false); // :122-133
+        int m = net.n_control, m_out;
+        if (nteam == 1 && net.n_control <= 128) {
+            // all control indices of the node in registers with one round trip (4 + 4 loads)
+            int cin[4], cout[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int q = u * 32 + lane;
+                cin[u] = q < net.n_control ? ci[q] : 0;
+                cout[u] = q < net.n_control ? co[q] : 0;
+            }
+            // usable controls = prefix of ctrl_in before its first -1 (:137; and :161, which tests
+            // the IN list while walking the OUT list)
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const unsigned bal = __ballot_sync(kFull, u * 32 + lane < net.n_control && cin[u] == -1);
+                if (bal && m == net.n_control) m = u * 32 + __ffs(bal) - 1;
+            }
+            m_out = m;
+#pragma unroll
+            for (int u = 0; u < 4; u++) { // the reference reads X[-1] here: flag + stop
+                const unsigned bal = __ballot_sync(kFull, u * 32 + lane < m && cout[u] < 0);
+                if (bal && m_out == m) {
+                    m_out = u * 32 + __ffs(bal) - 1;
+                    if (lane == 0) atomicOr(flags, 2u);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) { // :136-152 and :160-176; clamped gathers, masked sums
+                const int q = u * 32 + lane;
+                const bool vi = q < m, vo_ = q < m_out;
+                double an, ao, bn, bo;
+                eta_pair(vi ? cin[u] : j, true, an, ao);
+                eta_pair(vo_ ? cout[u] : j, false, bn, bo);
+                const double la = log1pexp(an), lb = log1pexp(ao), lc = log1pexp(bn), ld = log1pexp(bo);
+                if (vi) { ci_n += la; ci_o += lb; }
+                if (vo_) { co_n += lc; co_o += ld; }
+            }
+        } else {
+            for (int base = 0; base < net.n_control; base += 32) {
+                const int q = base + lane;
+                const bool stop = (q < net.n_control) && (ci[q] == -1);
+                const unsigned bal = __ballot_sync(kFull, stop);
+                if (bal) { m = base + __ffs(bal) - 1; break; }
+            }
+            m_out = m;
+            for (int base = 0; base < m; base += 32) { // the reference reads X[-1] here: flag + stop
+                const int q = base + lane;
+                const bool bad = (q < m) && (co[q] < 0);
+                const unsigned bal = __ballot_sync(kFull, bad);
+                if (bal) {
+                    m_out = base + __ffs(bal) - 1;
+                    if (lane == 0 && wteam == 0) atomicOr(flags, 2u);
+                    break;
+                }
+            }
+            for (int q = q0; q < m; q += qs) { // :136-152
+                double vn, vo;
+                eta_pair(ci[q], true, vn, vo);
+                ci_n += log1pexp(vn);
+                ci_o += log1pexp(vo);
+            }
+            for (int q = q0; q < m_out; q += qs) { // :160-176
+                double vn, vo;
+                eta_pair(co[q], false, vn, vo);
+                co_n += log1pexp(vn);
+                co_o += log1pexp(vo);
+            }
         }
         e_n = warp_sum(e_n); e_o = warp_sum(e_o);
         ci_n = warp_sum(ci_n); ci_o = warp_sum(ci_o);
@@ -675,6 +720,191 @@ __global__ void __launch_bounds__(512) k_sweep_slice(const SweepParams p, int *p
     if (nonfinite) atomicOr(p.flags, 1u);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Case-control sweeps of large sparse networks (cfg 5: n = 50 000, ~220 list entries per node).
+// Node j's conditional only reads the positions of the nodes in ITS lists (in/out edges, in/out
+// controls).  dep[j] = 1 + max{i in lists(j) : i < j} (0 if none) is precomputed by k_cc_deps; then
+// the consecutive nodes b, b+1, ..., e-1 can be updated CONCURRENTLY with the result of the
+// sequential sweep iff dep[j] <= b for all of them: none reads a batch-mate with a smaller index
+// (whose new value it would need), and batch-mates with a larger index are read at their old value
+// because commits wait for a CTA barrier.  With lists of ~220 out of 50 000 nodes batches are ~15-20
+// nodes long, so one CTA per (chain, slice) runs a warp per node of the batch instead of a team per
+// node: the sweep is the same Markov transition, ~10x faster.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cc_deps(NetView net, int sets, int32_t *dep)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t per_set = (size_t)net.T * net.n;
+    if (wid >= (size_t)sets * per_set) return;
+    const size_t r = wid % per_set;
+    const int j = (int)(r % net.n);
+    int best = -1;
+    auto scan = [&](const int32_t *lst, int len) {
+        for (int q = lane; q < len; q += 32) {
+            const int i = lst[q];
+            if (i >= 0 && i < j && i > best) best = i;
+        }
+    };
+    scan(net.in_edges + r * net.max_in, net.deg[r * 2 + 0]);
+    scan(net.out_edges + r * net.max_out, net.deg[r * 2 + 1]);
+    const size_t coff = ((wid / per_set) * per_set + r) * net.n_control;
+    scan(net.ctrl_in + coff, net.n_control);
+    scan(net.ctrl_out + coff, net.n_control);
+    for (int o = 16; o > 0; o >>= 1) {
+        const int other = __shfl_xor_sync(kFull, best, o);
+        best = other > best ? other : best;
+    }
+    if (lane == 0) dep[wid] = best + 1;
+}
+
+// grid = C*T (atomic ticket), block = 32*NW (NW = largest batch), positions in global memory;
+// dynamic smem = 32*(d+5) doubles (stage) + 32 ints (decisions)
+template <int D>
+__global__ void __launch_bounds__(512, 1) k_sweep_cc(const SweepParams p, int *progress_g,
+                                                     unsigned int *ticket, const int32_t *dep_all)
+{
+    constexpr int DM = (D == 0) ? kMaxD : D;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_ticket;
+    const int T = p.net.T, n = p.net.n, d = (D == 0) ? p.net.d : D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (threadIdx.x == 0) s_ticket = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int c = s_ticket / T, t = s_ticket % T;
+    double *Xchain = p.X + (size_t)c * T * n * d;
+    double *Xt = Xchain + (size_t)t * n * d;
+    double *st_prop = reinterpret_cast<double *>(smem_raw);
+    double *st_logu = st_prop + 32 * d, *st_nn = st_logu + 32, *st_no = st_nn + 32, *st_inv = st_no + 32;
+    int *st_zc = reinterpret_cast<int *>(st_inv + 32);
+    int *st_acc = reinterpret_cast<int *>(st_prop + sweep_stage_doubles(d));
+    int *st_dep = st_acc + 32;
+    volatile int *prog = progress_g + (size_t)c * T;
+    const double *rinv = p.rinv + (size_t)c * n;
+    const int32_t *dep = dep_all + ((size_t)(p.net.ctrl_per_chain ? c : 0) * T + t) * n;
+    const double b0 = p.intercept[c * 2 + 0], b1 = p.intercept[c * 2 + 1];
+    const uint32_t chain_id = (uint32_t)c + p.chain_offset;
+    bool nonfinite = false;
+
+    for (int jb = 0; jb < n; jb += 32) {
+        // ---- lane-parallel preparation of 32 nodes (warp 0), as in k_sweep_slice ----
+        const int jl = jb + lane;
+        const bool mine = (warp == 0) && (jl < n);
+        const size_t gs = ((size_t)c * T + t) * n + (jl < n ? jl : 0);
+        double my_step = 0.0;
+        int my_nacc = 0, my_nsteps = 0, my_until = 0;
+        if (mine) {
+            double eps[DM], x0[DM], x[DM], logu;
+            load_pos<DM>(Xt + (size_t)jl * d, d, x0);
+            my_step = p.step[gs]; my_nacc = p.nacc[gs]; my_nsteps = p.nsteps[gs]; my_until = p.until[gs];
+            if (p.eps) {
+#pragma unroll
+                for (int k = 0; k < DM; k++) eps[k] = (k < d) ? p.eps[gs * d + k] : 0.0;
+                logu = p.logu[gs];
+            } else {
+                latent_draws<DM>(p.seed, (uint32_t)(t * n + jl), p.sweep, chain_id, d, eps, logu);
+            }
+#pragma unroll
+            for (int k = 0; k < DM; k++) {
+                x[k] = (k < d) ? __dadd_rn(x0[k], __dmul_rn(my_step, eps[k])) : 0.0;
+                if (k < d) st_prop[lane * d + k] = x[k];
+            }
+            st_logu[lane] = logu;
+            double inv = (t == 0) ? 1.0 / p.tau_sq : 1.0 / p.sigma_sq;
+            int zc = 0;
+            if (p.prior != 0) {
+                zc = p.z[((size_t)c * T + t) * n + jl];
+                inv = 1.0 / p.sigma[(size_t)c * p.K + zc];
+            }
+            st_inv[lane] = inv;
+            st_zc[lane] = zc;
+            double nn = 0.0, no = 0.0;
+            if (t < T - 1) { // slice t+1 (another CTA) cannot have touched nodes >= jb yet
+                double xnx[DM];
+                const volatile double *q = Xchain + ((size_t)(t + 1) * n + jl) * d;
+#pragma unroll
+                for (int k = 0; k < DM; k++) xnx[k] = (k < d) ? q[k] : 0.0;
+                nn = prior_next<DM>(p, c, t, jl, x, xnx);
+                no = prior_next<DM>(p, c, t, jl, x0, xnx);
+            }
+            st_nn[lane] = nn;
+            st_no[lane] = no;
+            st_dep[lane] = dep[jl];
+        }
+        __syncthreads();
+        const int jend = (n - jb) < 32 ? (n - jb) : 32;
+        int b = 0;
+        while (b < jend) {
+            // batch [b, b+len): the longest run whose members do not read an earlier member
+            // (every warp derives the same length from the same dep entries)
+            const int cand = b + lane;
+            const bool fits = lane < nwarps && cand < jend && st_dep[cand] <= jb + b;
+            const unsigned run = __ballot_sync(kFull, fits);
+            const int len = (run == kFull) ? 32 : __ffs(~run) - 1; // >= 1: dep[j] <= j always
+            int acc = 0;
+            const int jj = b + warp, j = jb + jj;
+            if (warp < len) {
+                double x[DM], x0[DM];
+                load_pos<DM>(st_prop + jj * d, d, x);
+                load_pos<DM>(Xt + (size_t)j * d, d, x0);
+                // X[t-1, j]: look at the wavefront flag and fetch the neighbour slice's position
+                // BEFORE the list walk, so that their L2 round trips overlap it; in steady state
+                // slice t-1 is ahead and the early copy is the one that is used
+                double xp[DM];
+#pragma unroll
+                for (int k = 0; k < DM; k++) xp[k] = 0.0;
+                bool early = false;
+                if (t > 0) {
+                    early = prog[t - 1] > j;
+                    __threadfence();
+                    const volatile double *q = Xchain + ((size_t)(t - 1) * n + j) * d;
+#pragma unroll
+                    for (int k = 0; k < DM; k++) if (k < d) xp[k] = q[k];
+                }
+                double ll_new, ll_old;
+                node_loglik2<kCaseControl, DM>(p.net, Xt, rinv, c, t, j, x, x0, b0, b1, lane, ll_new,
+                                               ll_old, p.flags);
+                if (t > 0 && !early) {
+                    while (prog[t - 1] <= j) { /* spin on the L2-resident flag of slice t-1 */ }
+                    __threadfence();
+                    const volatile double *q = Xchain + ((size_t)(t - 1) * n + j) * d;
+#pragma unroll
+                    for (int k = 0; k < DM; k++) if (k < d) xp[k] = q[k];
+                }
+                const double inv = st_inv[jj];
+                const int zc = st_zc[jj];
+                double lp_new = __dsub_rn(ll_new, prior_prev<DM>(p, c, t, zc, inv, x, xp));
+                double lp_old = __dsub_rn(ll_old, prior_prev<DM>(p, c, t, zc, inv, x0, xp));
+                if (t < T - 1) {
+                    lp_new = __dsub_rn(lp_new, st_nn[jj]);
+                    lp_old = __dsub_rn(lp_old, st_no[jj]);
+                }
+                const double ratio = __dsub_rn(lp_new, lp_old);
+                acc = (st_logu[jj] >= ratio) ? 0 : 1;
+                if (lane == 0) {
+                    st_acc[jj] = acc;
+                    nonfinite |= !(ratio == ratio) || ratio - ratio != 0.0;
+                    if (p.ratio) p.ratio[((size_t)c * T + t) * n + j] = ratio;
+                }
+            }
+            __syncthreads(); // every member has read what it needs: commits may start
+            if (warp < len && acc && lane < d) Xt[(size_t)j * d + lane] = st_prop[jj * d + lane];
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) prog[t] = jb + b + len;
+            b += len;
+        }
+        if (mine) {
+            metropolis_bookkeep(my_step, my_nacc, my_nsteps, my_until, p.tune, p.tune_interval,
+                                st_acc[lane], false);
+            p.step[gs] = my_step; p.nacc[gs] = my_nacc; p.nsteps[gs] = my_nsteps; p.until[gs] = my_until;
+            if (p.accepted) p.accepted[gs] = st_acc[lane];
+        }
+        __syncthreads();
+    }
+    if (nonfinite) atomicOr(p.flags, 1u);
+}
+
 // the (j, i) dyad's contribution to node j's two log-likelihoods (proposal xn, current xo)
 template <int LK, int DM>
 __device__ __forceinline__ void pair_term2(const NetView &net, const double *Xt, const double *rinv,
@@ -1110,7 +1340,7 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
             const int32_t *oe = p.net.out_edges + r * p.net.max_out;
             const int32_t *co = p.net.ctrl_out +
                                 ((size_t)(p.net.ctrl_per_chain ? c : 0) * T * n + r) * p.net.n_control;
-            const double ri0 = r0[i], ri1 = r1[i];
+            const double ri0 = r0[i], ri1 = (NV == 2) ? r1[i] : 0.0;
             double e0 = 0.0, e1 = 0.0, c0 = 0.0, c1 = 0.0;
             for (int q = lane; q < outdeg; q += 32) {
                 const int k = oe[q];
@@ -1118,9 +1348,8 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
                 load_pos<DM>(Xt + (size_t)k * d, d, xk);
                 const double dist = fast_dist<DM>(xk, xi, d);
                 const double v0 = eta_directed(b00, b01, dist, r0[k], ri0);
-                const double v1 = eta_directed(b10, b11, dist, r1[k], ri1);
                 e0 += logit_term(0.5, v0);
-                e1 += logit_term(0.5, v1);
+                if (NV == 2) e1 += logit_term(0.5, eta_directed(b10, b11, dist, r1[k], ri1));
             }
             int m = p.net.n_control;
             for (int base = 0; base < p.net.n_control; base += 32) {
@@ -1135,7 +1364,7 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
                 load_pos<DM>(Xt + (size_t)k * d, d, xk);
                 const double dist = fast_dist<DM>(xk, xi, d);
                 c0 += log1pexp(eta_directed(b00, b01, dist, r0[k], ri0));
-                c1 += log1pexp(eta_directed(b10, b11, dist, r1[k], ri1));
+                if (NV == 2) c1 += log1pexp(eta_directed(b10, b11, dist, r1[k], ri1));
             }
             e0 = warp_sum(e0); e1 = warp_sum(e1);
             c0 = warp_sum(c0); c1 = warp_sum(c1);
@@ -1245,13 +1474,14 @@ __global__ void k_bvar_current(int C, const double *intercept, double *bvar)
     bvar[c * 4 + 1] = bvar[c * 4 + 3] = intercept[c * 2 + 1];
 }
 
-__global__ void k_sum_partials(int C, int nblk, const double *partial, double *out2)
+__global__ void k_sum_partials(int C, int nblk, const double *partial, double *out2, double *out_first = nullptr)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double s0 = 0.0, s1 = 0.0;
     for (int b = 0; b < nblk; b++) { s0 += partial[((size_t)c * nblk + b) * 2]; s1 += partial[((size_t)c * nblk + b) * 2 + 1]; }
     out2[c * 2] = s0; out2[c * 2 + 1] = s1;
+    if (out_first) out_first[c] = s0;
 }
 
 // ---------------------------------------------------------------------------------------------

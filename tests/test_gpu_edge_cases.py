@@ -177,3 +177,71 @@ def test_shape_and_argument_errors():
         e.sample_radii()                      # undirected model has no radii
     with pytest.raises(L.DlsmError):
         e.sample_labels()                     # no mixture prior
+
+
+def _sparse_directed(rng, T, n, out_deg):
+    """Sparse directed network as padded edge lists (what dlsm_set_edge_lists takes)."""
+    deg = np.zeros((T, n, 2), np.int64)
+    outs = [[np.sort(rng.choice(np.delete(np.arange(n), i), size=rng.poisson(out_deg) % (n - 1), replace=False))
+             for i in range(n)] for _ in range(T)]
+    ins = [[[] for _ in range(n)] for _ in range(T)]
+    for t in range(T):
+        for i in range(n):
+            deg[t, i, 1] = len(outs[t][i])
+            for k in outs[t][i]:
+                ins[t][k].append(i)
+        for i in range(n):
+            deg[t, i, 0] = len(ins[t][i])
+    in_e = np.zeros((T, n, max(1, deg[:, :, 0].max())), np.int64)
+    out_e = np.zeros((T, n, max(1, deg[:, :, 1].max())), np.int64)
+    for t in range(T):
+        for i in range(n):
+            in_e[t, i, :deg[t, i, 0]] = ins[t][i]
+            out_e[t, i, :deg[t, i, 1]] = outs[t][i]
+    return deg, in_e, out_e
+
+
+@pytest.mark.parametrize("mode", ["chain", "slice", "slice-plain"])
+@pytest.mark.parametrize("T,n,m,per_chain", [(3, 400, 8, False), (2, 150, 5, True), (4, 70, 20, False)])
+def test_case_control_sweep_all_mappings(T, n, m, per_chain, mode, monkeypatch):
+    """The case-control sweep (directed_likelihoods_fast.pyx:83-182 inside
+    sample_latent_positions.py:92-146) with recorded draws against the oracle: warp per slice
+    ("chain"), batch-parallel CTA per slice ("slice": runs of mutually independent nodes updated
+    concurrently, k_sweep_cc) and the serial CTA-per-slice kernel ("slice-plain") all make the
+    oracle's decisions and leave its positions."""
+    L = _L()
+    monkeypatch.setenv("DLSM_SWEEP_MODE", mode)
+    rng = np.random.RandomState(n + m)
+    d, C_ = 2, 2
+    deg, in_e, out_e = _sparse_directed(rng, T, n, 4.0)
+    e = L.Engine(T=T, n=n, d=d, n_chains=C_, is_directed=True, case_control=True, tune=2, tune_interval=1)
+    e.set_edge_lists(deg, in_e, out_e)
+    e.set_rng(77)
+    e.resample_controls(m, per_chain=per_chain)       # device-drawn control sets, read back for the oracle
+    ci, co = e.get_controls()
+    X = rng.randn(C_, T, n, d) * 0.02
+    radii = rng.dirichlet(np.ones(n) * 5, size=C_)
+    ic = np.tile([[0.4, 0.7]], (C_, 1))
+    e.set(L.F_X, X); e.set(L.F_RADII, radii); e.set(L.F_INTERCEPT, ic)
+    e.set_hyper(tau_sq=0.5, sigma_sq=0.002)
+    e.set_tuner(0.004)
+    Xo = X.copy()
+    tuners = [O.TunerState((T, n), 0.004, tune=2, tune_interval=1) for _ in range(C_)]
+    for s in range(3):
+        eps = rng.randn(C_, T, n, d)
+        logu = np.log(rng.rand(C_, T, n))
+        acc, _ = e.sweep_latent(eps, logu, want_stats=True)
+        got = e.get(L.F_X)
+        for c in range(C_):
+            k = c if per_chain else 0
+            cc = dict(in_edges=in_e, out_edges=out_e, degrees=deg, ctrl_in=ci[k].astype(np.int64),
+                      ctrl_out=co[k].astype(np.int64))
+            out = O.sweep_latent(Xo[c], ic[c], tuners[c], eps[c], logu[c], radii=radii[c], is_directed=True,
+                                 tau_sq=0.5, sigma_sq=0.002, case_control=cc)
+            assert np.array_equal(acc[c], out["accepted"]), (mode, s, c)
+            assert np.array_equal(got[c], Xo[c])
+        assert 0.05 < acc.mean() < 0.98
+    assert np.array_equal(e.get(L.F_X_STEP)[0], tuners[0].step)
+    # the device loop on top of it: sweeps + intercept / radii MH, log-likelihood kept current
+    e.run_sweeps(2)
+    assert np.allclose(e.get(L.F_LOGLIK), e.loglik_full(), rtol=1e-10, atol=0)

@@ -459,16 +459,17 @@ def test_fused_centring_equals_sweep_then_center():
     assert np.array_equal(a.get(L.F_X), b.get(L.F_X))
 
 
+@pytest.mark.parametrize("mode", ["chain", "slice"])
 @pytest.mark.parametrize("directed", [False, True])
 @pytest.mark.parametrize("T,n,d", [(6, 90, 2), (3, 64, 3), (11, 33, 2), (2, 200, 2)])
-def test_tracked_loglik_matches_full_kernel(T, n, d, directed, monkeypatch):
+def test_tracked_loglik_matches_full_kernel(T, n, d, directed, mode, monkeypatch):
     """The chain kernel accumulates the full-network log-likelihood of the state it leaves behind
     (dyad {i<j} taken from node j's update) and the intercept / radii MH keeps it current, so that
     k_full only evaluates proposals inside dlsm_run_sweeps.  The tracked value must equal a fresh
     full-network evaluation (network_likelihoods.py:26-33, directed_likelihoods_fast.pyx:185-205)
     to summation-order accuracy, and the chain must be the one the two-variant path produces."""
     L = _F()
-    monkeypatch.setenv("DLSM_SWEEP_MODE", "chain")
+    monkeypatch.setenv("DLSM_SWEEP_MODE", mode)   # "slice": one evaluation of the current state per sweep
     rng, X, Y = _synthetic(T, n, d, directed, seed=31)
     C_ = 3
 
