@@ -77,6 +77,7 @@ struct dlsm_handle {
     uint32_t trace_all = 0, trace_first = 0;
     int trace_logp = 0, trace_R = 0;
     double *d_logp = nullptr;       // [C] scratch of dlsm_logp
+    double *d_center = nullptr;     // means [C][8] + partial sums [C][128][8] of the long-chain centring
     double *d_proc_ref = nullptr;   // [C][T][n][d] reference configuration of the in-loop Procrustes
     bool have_proc_ref = false;
     // developer timeline (DLSM_TIMELINE=1): start/stop of every launch group on its own stream
@@ -447,8 +448,7 @@ int launch_full(dlsm_handle *h, const double *rinv0, const double *rinv1, int nv
     if (smem > kMaxSmem) FAIL(h, DLSM_ERR_UNSUPPORTED, "n too large for the exact full-network kernel");
     if (h->lk == kUndirected) LAUNCH_FULL(kUndirected);
     else if (h->lk == kDirected) LAUNCH_FULL(kDirected);
-    else if (nv == 1) LAUNCH_FULL_NV(kCaseControl, 0, 1); // runtime d
-    else LAUNCH_FULL_NV(kCaseControl, 0, 2);
+    else LAUNCH_FULL(kCaseControl);
 #undef LAUNCH_FULL_NV
 #undef LAUNCH_FULL
     CHECK_LAUNCH(h);
@@ -619,6 +619,7 @@ void dlsm_destroy(dlsm_handle *h)
     for (void *p : ptrs) cudaFree(p);
     free_trace(h);
     cudaFree(h->d_logp);
+    cudaFree(h->d_center);
     cudaFree(h->d_proc_ref);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -843,11 +844,34 @@ int dlsm_sweep_latent(dlsm_handle *h, const double *eps, const double *logu, int
     return check_flags(h);
 }
 
-static int center_async(dlsm_handle *h)
+// exact: numpy's summation order (dlsm_center, replay); otherwise a deterministic tree (device loop)
+static int center_async(dlsm_handle *h, bool exact = true)
 {
+    const dlsm_config &c = h->cfg;
+    const size_t rows = (size_t)c.T * c.n;
+    double *X = F<double>(h, DLSM_F_X);
     begin_phase(h, 1);
-    int rc = launch_simple(h, k_center, dim3(h->cfg.n_chains), dim3(256), 0, F<double>(h, DLSM_F_X),
-                           h->cfg.T, h->cfg.n, h->cfg.d);
+    int rc;
+    if (rows <= 16384) {
+        rc = launch_simple(h, k_center, dim3(c.n_chains), dim3(256), 0, X, c.T, c.n, c.d);
+    } else {
+        const int B = (int)((rows + 8191) / 8192 < 128 ? (rows + 8191) / 8192 : 128);
+        if (!h->d_center) CU(h, cudaMalloc((void **)&h->d_center, (size_t)c.n_chains * (128 + 1) * kMaxD * sizeof(double)));
+        double *means = h->d_center, *partial = h->d_center + (size_t)c.n_chains * kMaxD;
+        if (exact) {
+            rc = launch_simple(h, k_center_mean_exact, dim3(c.n_chains), dim3(256), 0, (const double *)X,
+                               c.T, c.n, c.d, means);
+        } else {
+            rc = launch_simple(h, k_center_partial, dim3(B, c.n_chains), dim3(256), 0, (const double *)X, c.T,
+                               c.n, c.d, partial);
+            if (rc == DLSM_OK)
+                rc = launch_simple(h, k_center_total, dim3(c.n_chains), dim3(32), 0, (const double *)partial, B,
+                                   c.d, (double)rows, means);
+        }
+        if (rc == DLSM_OK)
+            rc = launch_simple(h, k_center_apply, dim3(B, c.n_chains), dim3(256), 0, X, c.T, c.n, c.d,
+                               (const double *)means);
+    }
     end_phase(h);
     return rc;
 }
@@ -1176,7 +1200,7 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
     tl_end(h);
     h->sweep_idx[kRngLatent] += 1;
     if (procrustes && (rc = procrustes_async(h)) != DLSM_OK) return rc; // lsm.py:495-498
-    if (!(flags & 1u) && !fuse && (rc = center_async(h)) != DLSM_OK) return rc;
+    if (!(flags & 1u) && !fuse && (rc = center_async(h, getenv("DLSM_CENTER_EXACT") != nullptr)) != DLSM_OK) return rc;
     // After centring, the label block (FFBS -> HDP update; latency-bound, few warps per SM)
     // and the intercept / radii MH (full-network kernel; issue-bound) are independent: run
     // the label block on a high-priority side stream so the two overlap.
@@ -1215,6 +1239,7 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
     const bool any_mh = !(flags & 2u) || (h->cfg.is_directed && !(flags & 4u));
     if (!use_cur && any_mh && !getenv("DLSM_NO_LLCUR")) {
         const int C = h->cfg.n_chains;
+        tl_begin(h, "loglik(current)");
         rc = launch_simple(h, k_bvar_current, dim3((C + 127) / 128), dim3(128), 0, C,
                            (const double *)F<double>(h, DLSM_F_INTERCEPT), h->d_bvar);
         if (rc == DLSM_OK) rc = launch_full(h, h->rinv, h->rinv, 1);
@@ -1222,15 +1247,18 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
             rc = launch_simple(h, k_sum_partials, dim3((C + 127) / 128), dim3(128), 0, C, h->full_nblk,
                                (const double *)h->d_partial, h->d_ll2, F<double>(h, DLSM_F_LOGLIK));
         if (rc != DLSM_OK) return rc;
+        tl_end(h);
         use_cur = true;
     }
     if (tracked) *tracked = use_cur;
     tl_begin(h, "intercepts");
     if (!(flags & 2u) && (rc = intercepts_async(h, nullptr, nullptr, nullptr, nullptr, use_cur)) != DLSM_OK) return rc;
     tl_end(h);
+    tl_begin(h, "radii");
     if (h->cfg.is_directed && !(flags & 4u) &&
         (rc = radii_async(h, true, nullptr, nullptr, nullptr, use_cur)) != DLSM_OK)
         return rc;
+    tl_end(h);
     if (labels) CU(h, cudaStreamWaitEvent(main_stream, h->ev_join, 0));
     return DLSM_OK;
 }

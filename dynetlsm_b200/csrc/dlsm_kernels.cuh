@@ -1195,6 +1195,85 @@ __global__ void k_center(double *X, int T, int n, int d)
         Xc[e] = __dsub_rn(Xc[e], mean[e % d]);
 }
 
+// Long chains (cfg 5: T n = 500 000 rows): the column means in two shapes, the subtraction spread
+// over (B, C) CTAs.
+//   k_center_mean_exact  numpy's serial order, bit-identical to k_center: the CTA stages 2048-row
+//                        chunks in shared memory (coalesced), thread k < d adds them in order --
+//                        bounded by the serial DADD chain (~8 cycles per row), not by load latency
+//   k_center_mean_tree   device loop only: per-(chain, block) partial sums + a fixed-order total;
+//                        deterministic, but not numpy's rounding
+__global__ void __launch_bounds__(256) k_center_mean_exact(const double *X, int T, int n, int d, double *means)
+{
+    __shared__ double buf[2048 * kMaxD / 4]; // 2048 rows at d = 2, 512 rows at d = 8
+    const double *Xc = X + (size_t)blockIdx.x * T * n * d;
+    const size_t rows = (size_t)T * n;
+    const int chunk = (2048 * kMaxD / 4) / d;
+    double s = 0.0;
+    for (size_t r0 = 0; r0 < rows; r0 += chunk) {
+        const int cnt = (int)((rows - r0) < (size_t)chunk ? (rows - r0) : (size_t)chunk);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt * d; e += blockDim.x) buf[e] = Xc[r0 * d + e];
+        __syncthreads();
+        if ((int)threadIdx.x < d) {
+            int r = 0;
+            for (; r + 8 <= cnt; r += 8) {
+                double v[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[q] = buf[(r + q) * d + threadIdx.x];
+#pragma unroll
+                for (int q = 0; q < 8; q++) s = __dadd_rn(s, v[q]);
+            }
+            for (; r < cnt; r++) s = __dadd_rn(s, buf[r * d + threadIdx.x]);
+        }
+    }
+    if ((int)threadIdx.x < d) means[blockIdx.x * kMaxD + threadIdx.x] = __ddiv_rn(s, (double)rows);
+}
+
+__device__ __forceinline__ double block_sum(double v, double *sh);
+
+// grid (B, C): partial[c][b][k] = sum over the rows of block b
+__global__ void __launch_bounds__(256) k_center_partial(const double *X, int T, int n, int d, double *partial)
+{
+    __shared__ double sh[8];
+    const int B = gridDim.x, b = blockIdx.x, c = blockIdx.y;
+    const double *Xc = X + (size_t)c * T * n * d;
+    const size_t rows = (size_t)T * n, per = (rows + B - 1) / B;
+    const size_t lo = per * b, hi = (lo + per) < rows ? (lo + per) : rows;
+    double acc[kMaxD];
+#pragma unroll
+    for (int k = 0; k < kMaxD; k++) acc[k] = 0.0;
+    for (size_t r = lo + threadIdx.x; r < hi; r += blockDim.x)
+#pragma unroll
+        for (int k = 0; k < kMaxD; k++)
+            if (k < d) acc[k] += Xc[r * d + k];
+    for (int k = 0; k < d; k++) {
+        const double tot = block_sum(acc[k], sh);
+        if (threadIdx.x == 0) partial[((size_t)c * B + b) * kMaxD + k] = tot;
+    }
+}
+
+__global__ void k_center_total(const double *partial, int B, int d, double rows, double *means)
+{
+    const int c = blockIdx.x, k = threadIdx.x;
+    if (k >= d) return;
+    double s = 0.0;
+    for (int b = 0; b < B; b++) s += partial[((size_t)c * B + b) * kMaxD + k];
+    means[c * kMaxD + k] = s / rows;
+}
+
+// grid (B, C): X -= mean (exactly rounded subtraction, as numpy's in-place -=)
+__global__ void __launch_bounds__(256) k_center_apply(double *X, int T, int n, int d, const double *means)
+{
+    __shared__ double mean[kMaxD];
+    const int c = blockIdx.y;
+    if ((int)threadIdx.x < d) mean[threadIdx.x] = means[c * kMaxD + threadIdx.x];
+    __syncthreads();
+    double *Xc = X + (size_t)c * T * n * d;
+    const size_t total = (size_t)T * n * d;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x)
+        Xc[e] = __dsub_rn(Xc[e], mean[e % d]);
+}
+
 __global__ void k_rinv(const double *radii, double *rinv, size_t total)
 {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -245,3 +245,46 @@ def test_case_control_sweep_all_mappings(T, n, m, per_chain, mode, monkeypatch):
     # the device loop on top of it: sweeps + intercept / radii MH, log-likelihood kept current
     e.run_sweeps(2)
     assert np.allclose(e.get(L.F_LOGLIK), e.loglik_full(), rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("T,n,d", [(3, 9000, 2), (2, 12000, 3), (5, 5000, 8)])
+def test_centring_of_long_chains(T, n, d, monkeypatch):
+    """T n > 16384 rows: dlsm_center keeps numpy's summation order bit for bit (staged serial sum
+    + a subtraction spread over many CTAs)."""
+    L = _L()
+    rng = np.random.RandomState(T * n)
+    X = rng.randn(2, T, n, d) + rng.randn(2, 1, 1, d)
+    e = L.Engine(T=T, n=n, d=d, n_chains=2)
+    e.set(L.F_X, X)
+    e.center()
+    want = X.copy()
+    for c in range(2):
+        O.center(want[c])
+    assert np.array_equal(e.get(L.F_X), want)
+
+
+def test_device_loop_centring_tree_vs_exact(monkeypatch):
+    """Inside dlsm_run_sweeps long chains are centred with a deterministic tree sum; against the
+    numpy-ordered sum (DLSM_CENTER_EXACT=1) the chain differs by rounding only."""
+    L = _L()
+    rng = np.random.RandomState(3)
+    T, n, d, m = 2, 9000, 2, 6
+    deg, in_e, out_e = _sparse_directed(rng, T, n, 3.0)
+    X0 = rng.randn(1, T, n, d) * 0.01 + 0.5
+    radii = rng.dirichlet(np.ones(n) * 5, size=1)
+    outs = []
+    for exact in (False, True):
+        if exact:
+            monkeypatch.setenv("DLSM_CENTER_EXACT", "1")
+        e = L.Engine(T=T, n=n, d=d, is_directed=True, case_control=True)
+        e.set_edge_lists(deg, in_e, out_e)
+        e.set_rng(5)
+        e.resample_controls(m)
+        e.set(L.F_X, X0); e.set(L.F_RADII, radii); e.set(L.F_INTERCEPT, np.array([[0.4, 0.7]]))
+        e.set_hyper(tau_sq=0.5, sigma_sq=0.002)
+        e.set_tuner(0.002)
+        e.run_sweeps(2)
+        outs.append(e.get(L.F_X))
+    assert np.all(np.abs(outs[0].mean(axis=(1, 2))) < 1e-15)
+    assert np.allclose(outs[0], outs[1], rtol=0, atol=1e-14)
+    assert not np.allclose(outs[0], X0 - X0.mean(axis=(1, 2), keepdims=True), atol=1e-6)   # it moved
