@@ -77,6 +77,7 @@ struct dlsm_handle {
     uint32_t trace_all = 0, trace_first = 0;
     int trace_logp = 0, trace_R = 0;
     double *d_logp = nullptr;       // [C] scratch of dlsm_logp
+    double *d_gather = nullptr;     // [C][T][n][4] packed {x, y, 1/r, 0} records of the case-control kernels
     double *d_center = nullptr;     // means [C][8] + partial sums [C][128][8] of the long-chain centring
     double *d_proc_ref = nullptr;   // [C][T][n][d] reference configuration of the in-loop Procrustes
     bool have_proc_ref = false;
@@ -430,6 +431,16 @@ int launch_full(dlsm_handle *h, const double *rinv0, const double *rinv1, int nv
     p.rinv0 = rinv0; p.rinv1 = rinv1;
     p.partial = h->d_partial;
     p.flags = h->d_flags;
+    if (h->lk == kCaseControl && h->cfg.d == 2 && nv == 1 && !getenv("DLSM_NO_GATHER_PACK")) {
+        // positions and reciprocal radii of this evaluation as 32-byte records: one 256-bit load
+        // per gathered node instead of two loads (the kernel is bound by L1 gather wavefronts)
+        const size_t cells = (size_t)h->cfg.n_chains * h->cfg.T * h->cfg.n;
+        if (!h->d_gather) CU(h, cudaMalloc((void **)&h->d_gather, cells * 4 * sizeof(double)));
+        int rc = launch_simple(h, k_pack_gather, dim3((unsigned)((cells + 255) / 256)), dim3(256), 0,
+                               (const double *)p.X, rinv0, h->d_gather, h->cfg.n_chains, h->cfg.T, h->cfg.n);
+        if (rc != DLSM_OK) return rc;
+        p.gather = h->d_gather;
+    }
     dim3 grid(h->cfg.T * h->full_tiles, h->cfg.n_chains);
     const size_t smem = (h->lk == kCaseControl) ? 0 : (size_t)h->cfg.n * h->cfg.d * sizeof(double);
     const bool d2 = h->cfg.d == 2;
@@ -620,6 +631,7 @@ void dlsm_destroy(dlsm_handle *h)
     free_trace(h);
     cudaFree(h->d_logp);
     cudaFree(h->d_center);
+    cudaFree(h->d_gather);
     cudaFree(h->d_proc_ref);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);

@@ -1328,7 +1328,27 @@ struct FullParams {
     const double *rinv1;    // [C][n] variant 1
     double *partial;        // [C][T*tiles][2]
     unsigned int *flags;
+    const double *gather;   // optional [C][T][n][4] = {x0, x1, 1/r (variant 0), 0}: d = 2 case-control rows
 };
+
+// one 256-bit load (LDG.E.256 on sm_100a): a whole 32-byte gather record with a single L1 wavefront
+__device__ __forceinline__ void ld256(const double *p, double &a, double &b, double &c, double &d)
+{
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+// G[c][t][j] = {X[c,t,j,0], X[c,t,j,1], rinv[c,j], 0}
+__global__ void k_pack_gather(const double *X, const double *rinv, double *G, int C, int T, int n)
+{
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)C * T * n;
+    if (g >= total) return;
+    const size_t c = g / ((size_t)T * n);
+    const int j = (int)(g % n);
+    double2 x = reinterpret_cast<const double2 *>(X)[g];
+    double4 o = make_double4(x.x, x.y, rinv[c * n + j], 0.0);
+    reinterpret_cast<double4 *>(G)[g] = o;
+}
 
 // NV = 2: proposal and current variants; NV = 1: proposal only (the device loop tracks the current
 // state's log-likelihood itself, see SweepParams::ll_cur)
@@ -1421,29 +1441,72 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
                                 ((size_t)(p.net.ctrl_per_chain ? c : 0) * T * n + r) * p.net.n_control;
             const double ri0 = r0[i], ri1 = (NV == 2) ? r1[i] : 0.0;
             double e0 = 0.0, e1 = 0.0, c0 = 0.0, c1 = 0.0;
-            for (int q = lane; q < outdeg; q += 32) {
-                const int k = oe[q];
-                double xk[DM];
-                load_pos<DM>(Xt + (size_t)k * d, d, xk);
+            const double *Gt = (D == 2 && NV == 1 && p.gather)
+                                   ? p.gather + ((size_t)c * T + t) * n * 4 : nullptr;
+            auto terms = [&](int k, double &v0, double &v1) {
+                double xk[DM], rk0;
+                if (D == 2 && NV == 1 && Gt) {
+                    double pad;
+                    ld256(Gt + (size_t)k * 4, xk[0], xk[DM > 1 ? 1 : 0], rk0, pad);
+                } else {
+                    load_pos<DM>(Xt + (size_t)k * d, d, xk);
+                    rk0 = r0[k];
+                }
                 const double dist = fast_dist<DM>(xk, xi, d);
-                const double v0 = eta_directed(b00, b01, dist, r0[k], ri0);
-                e0 += logit_term(0.5, v0);
-                if (NV == 2) e1 += logit_term(0.5, eta_directed(b10, b11, dist, r1[k], ri1));
-            }
+                v0 = eta_directed(b00, b01, dist, rk0, ri0);
+                v1 = (NV == 2) ? eta_directed(b10, b11, dist, r1[k], ri1) : 0.0;
+            };
             int m = p.net.n_control;
-            for (int base = 0; base < p.net.n_control; base += 32) {
-                const int q = base + lane;
-                const bool stop = (q < p.net.n_control) && (co[q] == -1);
-                const unsigned bal = __ballot_sync(kFull, stop);
-                if (bal) { m = base + __ffs(bal) - 1; break; }
-            }
-            for (int q = lane; q < m; q += 32) {
-                const int k = co[q];
-                double xk[DM];
-                load_pos<DM>(Xt + (size_t)k * d, d, xk);
-                const double dist = fast_dist<DM>(xk, xi, d);
-                c0 += log1pexp(eta_directed(b00, b01, dist, r0[k], ri0));
-                if (NV == 2) c1 += log1pexp(eta_directed(b10, b11, dist, r1[k], ri1));
+            if (p.net.n_control <= 128 && outdeg <= 64) {
+                // every list index of the row in registers after ONE round trip (2 + 4 loads), then
+                // clamped, masked gathers: the L2 latencies of a row overlap instead of chaining
+                int eo[2], cq[4];
+#pragma unroll
+                for (int u = 0; u < 2; u++) eo[u] = (u * 32 + lane < outdeg) ? oe[u * 32 + lane] : i;
+#pragma unroll
+                for (int u = 0; u < 4; u++) cq[u] = (u * 32 + lane < p.net.n_control) ? co[u * 32 + lane] : 0;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const unsigned bal = __ballot_sync(kFull, u * 32 + lane < p.net.n_control && cq[u] == -1);
+                    if (bal && m == p.net.n_control) m = u * 32 + __ffs(bal) - 1;
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    double v0, v1;
+                    terms(eo[u], v0, v1);
+                    if (u * 32 + lane < outdeg) {
+                        e0 += logit_term(0.5, v0);
+                        if (NV == 2) e1 += logit_term(0.5, v1);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool ok = u * 32 + lane < m;
+                    double v0, v1;
+                    terms(ok ? cq[u] : i, v0, v1);
+                    const double l0 = log1pexp(v0);
+                    if (ok) c0 += l0;
+                    if (NV == 2) { const double l1 = log1pexp(v1); if (ok) c1 += l1; }
+                }
+            } else {
+                for (int q = lane; q < outdeg; q += 32) {
+                    double v0, v1;
+                    terms(oe[q], v0, v1);
+                    e0 += logit_term(0.5, v0);
+                    if (NV == 2) e1 += logit_term(0.5, v1);
+                }
+                for (int base = 0; base < p.net.n_control; base += 32) {
+                    const int q = base + lane;
+                    const bool stop = (q < p.net.n_control) && (co[q] == -1);
+                    const unsigned bal = __ballot_sync(kFull, stop);
+                    if (bal) { m = base + __ffs(bal) - 1; break; }
+                }
+                for (int q = lane; q < m; q += 32) {
+                    double v0, v1;
+                    terms(co[q], v0, v1);
+                    c0 += log1pexp(v0);
+                    if (NV == 2) c1 += log1pexp(v1);
+                }
             }
             e0 = warp_sum(e0); e1 = warp_sum(e1);
             c0 = warp_sum(c0); c1 = warp_sum(c1);
