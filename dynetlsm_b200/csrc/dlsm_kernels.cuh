@@ -555,6 +555,20 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
     }
 }
 
+// wavefront flags across CTAs with acquire / release instead of full fences: the producer's
+// st.release (after the CTA barrier that follows the commits) orders every member's stores before
+// the flag, the consumer's ld.acquire orders the flag before its reads of the neighbour slice
+__device__ __forceinline__ int ld_acquire_gpu(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_sweep_slice: the same sweep with one CTA per (chain, time slice) -- for long rows and few
 // chains (cfg 3: one chain, n = 2000, T = 20), where a warp per slice would leave the GPU idle.
@@ -593,7 +607,7 @@ __global__ void __launch_bounds__(512) k_sweep_slice(const SweepParams p, int *p
     double *st_logu = st_prop + 32 * d, *st_nn = st_logu + 32, *st_no = st_nn + 32, *st_inv = st_no + 32;
     int *st_zc = reinterpret_cast<int *>(st_inv + 32);
     double *part = stage_base + sweep_stage_doubles(d);     // [nwarps][2]
-    volatile int *prog = progress_g + (size_t)c * T;
+    int *prog = progress_g + (size_t)c * T;
     const double *rinv = (LK == kUndirected) ? nullptr : p.rinv + (size_t)c * n;
     if (XS && LK != kUndirected) { // reciprocal radii next to the positions (read once per pair)
         double *s_rinv = part + 2 * nwarps;
@@ -674,8 +688,7 @@ __global__ void __launch_bounds__(512) k_sweep_slice(const SweepParams p, int *p
 #pragma unroll
                 for (int k = 0; k < DM; k++) xp[k] = 0.0;
                 if (t > 0) {
-                    while (prog[t - 1] <= j) { /* spin on the L2-resident flag of slice t-1 */ }
-                    __threadfence();
+                    while (ld_acquire_gpu(prog + t - 1) <= j) { /* spin on the L2-resident flag of slice t-1 */ }
                     const volatile double *q = Xchain + ((size_t)(t - 1) * n + j) * d;
 #pragma unroll
                     for (int k = 0; k < DM; k++) if (k < d) xp[k] = q[k];
@@ -703,8 +716,7 @@ __global__ void __launch_bounds__(512) k_sweep_slice(const SweepParams p, int *p
                             }
                     }
                     if (p.ratio) p.ratio[((size_t)c * T + t) * n + j] = ratio;
-                    __threadfence();
-                    prog[t] = j + 1;
+                    st_release_gpu(prog + t, j + 1); // this lane's stores above are ordered before the flag
                 }
             }
             __syncthreads();
@@ -779,7 +791,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_cc(const SweepParams p, int *p
     int *st_zc = reinterpret_cast<int *>(st_inv + 32);
     int *st_acc = reinterpret_cast<int *>(st_prop + sweep_stage_doubles(d));
     int *st_dep = st_acc + 32;
-    volatile int *prog = progress_g + (size_t)c * T;
+    int *prog = progress_g + (size_t)c * T;
     const double *rinv = p.rinv + (size_t)c * n;
     const int32_t *dep = dep_all + ((size_t)(p.net.ctrl_per_chain ? c : 0) * T + t) * n;
     const double b0 = p.intercept[c * 2 + 0], b1 = p.intercept[c * 2 + 1];
@@ -855,8 +867,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_cc(const SweepParams p, int *p
                 for (int k = 0; k < DM; k++) xp[k] = 0.0;
                 bool early = false;
                 if (t > 0) {
-                    early = prog[t - 1] > j;
-                    __threadfence();
+                    early = ld_acquire_gpu(prog + t - 1) > j;
                     const volatile double *q = Xchain + ((size_t)(t - 1) * n + j) * d;
 #pragma unroll
                     for (int k = 0; k < DM; k++) if (k < d) xp[k] = q[k];
@@ -865,8 +876,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_cc(const SweepParams p, int *p
                 node_loglik2<kCaseControl, DM>(p.net, Xt, rinv, c, t, j, x, x0, b0, b1, lane, ll_new,
                                                ll_old, p.flags);
                 if (t > 0 && !early) {
-                    while (prog[t - 1] <= j) { /* spin on the L2-resident flag of slice t-1 */ }
-                    __threadfence();
+                    while (ld_acquire_gpu(prog + t - 1) <= j) { /* spin on the L2-resident flag of slice t-1 */ }
                     const volatile double *q = Xchain + ((size_t)(t - 1) * n + j) * d;
 #pragma unroll
                     for (int k = 0; k < DM; k++) if (k < d) xp[k] = q[k];
@@ -889,9 +899,8 @@ __global__ void __launch_bounds__(512, 1) k_sweep_cc(const SweepParams p, int *p
             }
             __syncthreads(); // every member has read what it needs: commits may start
             if (warp < len && acc && lane < d) Xt[(size_t)j * d + lane] = st_prop[jj * d + lane];
-            __threadfence();
             __syncthreads();
-            if (threadIdx.x == 0) prog[t] = jb + b + len;
+            if (threadIdx.x == 0) st_release_gpu(prog + t, jb + b + len);
             b += len;
         }
         if (mine) {
@@ -978,7 +987,7 @@ __global__ void __launch_bounds__(576) k_sweep_slice_ws(const SweepParams p, int
     int *st_zc = reinterpret_cast<int *>(st_inv + 32);
     double *part = stage_base + sweep_stage_doubles(d);          // [2][nwarps][2]
     volatile int *done = reinterpret_cast<volatile int *>(part + 4 * nwarps); // [nwarps] nodes summed
-    volatile int *prog = progress_g + (size_t)c * T;
+    int *prog = progress_g + (size_t)c * T;
     for (int w = threadIdx.x; w < nwarps; w += blockDim.x) done[w] = 0;
     __syncthreads();
 
@@ -1070,8 +1079,7 @@ __global__ void __launch_bounds__(576) k_sweep_slice_ws(const SweepParams p, int
 #pragma unroll
                 for (int k = 0; k < DM; k++) xp[k] = 0.0;
                 if (t > 0) {
-                    while (prog[t - 1] <= j) { /* spin on the L2-resident flag of slice t-1 */ }
-                    __threadfence();
+                    while (ld_acquire_gpu(prog + t - 1) <= j) { /* spin on the L2-resident flag of slice t-1 */ }
                     const volatile double *q = Xchain + ((size_t)(t - 1) * n + j) * d;
 #pragma unroll
                     for (int k = 0; k < DM; k++) if (k < d) xp[k] = q[k];
@@ -1111,8 +1119,7 @@ __global__ void __launch_bounds__(576) k_sweep_slice_ws(const SweepParams p, int
                     if (p.ratio) p.ratio[((size_t)c * T + t) * n + j] = ratio;
                     __threadfence_block();
                     s_decided = j + 1;       // releases the compute warps' node j+2
-                    __threadfence();
-                    prog[t] = j + 1;         // releases slice t+1's node j
+                    st_release_gpu(prog + t, j + 1); // releases slice t+1's node j
                 }
                 __syncwarp();
             }
