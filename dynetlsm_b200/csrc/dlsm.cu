@@ -57,6 +57,8 @@ struct dlsm_handle {
     double *d_ffbs_stage = nullptr;  // global (L2-resident) stage of the thread-per-node label kernel
     size_t ffbs_stage_bytes = 0;
     int sweep_mode = 0;             // 0 auto, 1 CTA per chain, 2 CTA per (chain, slice)
+    int sm_count = 148;
+    bool dense_build = false;
     bool no_pipeline = false;       // DLSM_SWEEP_MODE=slice-plain: the unpipelined slice kernel
     // rng
     uint64_t seed = 0, chain_offset = 0;
@@ -292,6 +294,14 @@ template <int LK, int D, bool XS>
 int launch_sweep_x(dlsm_handle *h, const SweepParams &p)
 {
     const int warps = h->cfg.T < 16 ? h->cfg.T : 16;
+    // At most one chain per SM (the reference's own single-chain use): nothing to share the
+    // register file with, so the compiler may keep all four softplus chains of a trip in flight
+    // (156 registers; 15 % lower sweep latency than the 72-register build, which serialises them
+    // and relies on 27 resident warps to fill the gaps).
+    if (h->cfg.n_chains <= h->sm_count && !h->dense_build) {
+        if (warps <= 9) return launch_sweep_t<LK, D, XS, 288, 1>(h, p, warps);
+        return launch_sweep_t<LK, D, XS, 512, 1>(h, p, warps);
+    }
     if (warps <= 9) return launch_sweep_t<LK, D, XS, 288, DLSM_SWEEP_MINB>(h, p, warps);
     if (warps <= 10) return launch_sweep_t<LK, D, XS, 320, 3>(h, p, warps);
     return launch_sweep_t<LK, D, XS, 512, 2>(h, p, warps);
@@ -559,7 +569,9 @@ int dlsm_create(const dlsm_config *cfg, dlsm_handle **out)
     h->timeline_on = getenv("DLSM_TIMELINE") != nullptr;
     if (const char *m = getenv("DLSM_SWEEP_MODE")) // chain | slice: override the heuristic (tests, tuning)
     {
-        h->sweep_mode = !strcmp(m, "chain") ? 1 : ((!strcmp(m, "slice") || !strcmp(m, "slice-plain")) ? 2 : 0);
+        h->sweep_mode = (!strcmp(m, "chain") || !strcmp(m, "chain-dense")) ? 1
+                        : ((!strcmp(m, "slice") || !strcmp(m, "slice-plain")) ? 2 : 0);
+        h->dense_build = !strcmp(m, "chain-dense"); // the many-chains register budget, whatever C is
         h->no_pipeline = !strcmp(m, "slice-plain");
     }
     auto fail = [&](const char *what, cudaError_t e) {
@@ -569,6 +581,7 @@ int dlsm_create(const dlsm_config *cfg, dlsm_handle **out)
     };
     cudaError_t e;
     if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
     if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return fail("cudaStreamCreate", e);
     h->stream = h->own_stream;

@@ -14,6 +14,10 @@
 #pragma once
 #include "dlsm_device.cuh"
 
+#ifndef DLSM_SPIN_NS
+#define DLSM_SPIN_NS 20
+#endif
+
 namespace dlsm {
 
 enum Lik : int { kUndirected = 0, kDirected = 1, kCaseControl = 2 };
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
 #pragma unroll
                 for (int k = 0; k < DM; k++) xp[k] = 0.0;
                 if (t > 0) { // wavefront: X[t-1, j] must be this sweep's value (uniform poll)
-                    while (progress[t - 1] <= j) { /* spin on shared memory */ }
+                    while (progress[t - 1] <= j) { __nanosleep(DLSM_SPIN_NS); } /* poll shared memory, yielding issue slots */
                     __threadfence_block();
                     const volatile double *q = Xc + ((size_t)(t - 1) * n + j) * d;
 #pragma unroll

@@ -71,7 +71,7 @@ def _run_both(T, n, d, directed, Y, X, mode=None, monkeypatch=None, n_sweeps=2, 
     return e
 
 
-@pytest.mark.parametrize("mode", ["chain", "slice"])
+@pytest.mark.parametrize("mode", ["chain", "chain-dense", "slice"])
 @pytest.mark.parametrize("T,n,d", [(1, 2, 1), (1, 5, 2), (2, 31, 2), (2, 32, 2), (2, 33, 3), (3, 63, 2),
                                    (2, 64, 4), (2, 65, 5), (2, 97, 6), (2, 128, 7), (2, 129, 8), (40, 6, 2)])
 def test_shapes_around_the_chunking(T, n, d, mode, monkeypatch):

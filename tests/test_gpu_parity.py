@@ -171,10 +171,12 @@ LSM_CASES = [("lsm_undirected_monks.npz", False, False), ("lsm_directed_monks.np
              ("lsm_casecontrol_monks.npz", True, True)]
 
 
-@pytest.mark.parametrize("mode", ["chain", "slice"])
+@pytest.mark.parametrize("mode", ["chain", "chain-dense", "slice"])
 @pytest.mark.parametrize("name,directed,cc", LSM_CASES)
 def test_lsm_latent_sweep_replay(name, directed, cc, mode, monkeypatch):
-    # both sweep kernels: one CTA per chain (warp per slice) and one CTA per (chain, slice)
+    # the sweep kernels: one CTA per chain (warp per slice) in its few-chains build ("chain": all
+    # registers) and in its many-chains build ("chain-dense": 72 registers, 3 CTAs per SM), and one
+    # CTA per (chain, slice)
     monkeypatch.setenv("DLSM_SWEEP_MODE", mode)
     g, L = load_golden(name), _F()
     S = g["X_in"].shape[0]
@@ -237,7 +239,7 @@ def test_lsm_center_replay():
 HDP_CASES = [("hdp_undirected_split.npz", False), ("hdp_directed_monks.npz", True)]
 
 
-@pytest.mark.parametrize("mode", ["chain", "slice"])
+@pytest.mark.parametrize("mode", ["chain", "chain-dense", "slice"])
 @pytest.mark.parametrize("name,directed", HDP_CASES)
 def test_hdp_sweep_center_labels_replay(name, directed, mode, monkeypatch):
     monkeypatch.setenv("DLSM_SWEEP_MODE", mode)
@@ -286,6 +288,8 @@ def _synthetic(T, n, d, directed, seed, density=0.15):
 @pytest.mark.parametrize("T,n,d,directed,mode", [
     (9, 120, 2, False, "auto"), (4, 70, 3, False, "auto"), (5, 90, 2, True, "auto"),
     (10, 500, 2, False, "chain"),     # positions in shared memory, 16 chunks per row
+    (10, 500, 2, False, "chain-dense"),  # the same with the many-chains register budget
+    (9, 120, 2, False, "chain-dense"), (5, 90, 2, True, "chain-dense"),
     (10, 500, 2, False, "slice"),     # CTA per slice, 8 warps per row
     (6, 700, 2, True, "slice"),       # directed, CTA per slice
     (10, 1500, 2, False, "chain"),    # chain too big for shared memory: positions stay in global/L2
