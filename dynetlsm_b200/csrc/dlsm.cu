@@ -302,6 +302,9 @@ int launch_sweep_x(dlsm_handle *h, const SweepParams &p)
         if (warps <= 9) return launch_sweep_t<LK, D, XS, 288, 1>(h, p, warps);
         return launch_sweep_t<LK, D, XS, 512, 1>(h, p, warps);
     }
+    // shared memory admits only two CTAs per SM (cfg 4: 98 KB per chain): give them the registers
+    if (warps <= 10 && 3 * sweep_smem(h, XS) > kMaxSmem && !h->dense_build)
+        return launch_sweep_t<LK, D, XS, 320, 2>(h, p, warps);
     if (warps <= 9) return launch_sweep_t<LK, D, XS, 288, DLSM_SWEEP_MINB>(h, p, warps);
     if (warps <= 10) return launch_sweep_t<LK, D, XS, 320, 3>(h, p, warps);
     return launch_sweep_t<LK, D, XS, 512, 2>(h, p, warps);
