@@ -482,31 +482,35 @@ def main():
         ins = [(L.F_X, pinned(e.get(L.F_X)))]
         outs = [L.F_X, L.F_INTERCEPT] + ([L.F_RADII] if w["directed"] else []) + \
                ([L.F_Z, L.F_MU, L.F_SIGMA, L.F_LAMBDA, L.F_BETA, L.F_WEIGHTS, L.F_HYPER] if w["K"] else [])
-        bufs = {f: pinned(e.get(f)) for f in outs}
         h2d = sum(a.nbytes for _, a in ins)
         nst = max(3, min(args.steps, 10))
+        # one call per step returns the whole new state: dlsm_run_traced(1) copies the positions out
+        # as soon as they are centred (while the intercept MH / label block still run) and the rest
+        # of the state at the end of the sweep
+        tr = None
         for it in range(2 + nst):
             if it == 2:
                 barrier()
                 t0 = time.perf_counter()
             for f, a in ins:
                 e.set(f, a)
-            e.run_sweeps(1)
-            got = [e.get(f, out=bufs[f]) for f in outs]
-            ins[0] = (L.F_X, got[0])
+            tr = e.run_traced(1, fields_all=outs, logp=True, pinned=True, out=tr)
+            ins[0] = (L.F_X, tr[L.F_X][0])
         barrier()
         dt = time.perf_counter() - t0
-        d2h = sum(a.nbytes for a in got)
+        d2h = sum(a.nbytes for a in tr.values())
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * upd_per_step * nst / float(tt.item()), "unit": "node-updates/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": nst,
-               "api": "Engine.set(state) -> run_sweeps(1) -> Engine.get(state) over the dlsm C-ABI"}
+               "api": "Engine.set(positions) -> Engine.run_traced(1 sweep, whole state + log-posterior to pinned host "
+                      "buffers) over the dlsm C-ABI"}
         # the same state leaving the device every sweep through the streaming call fit() uses
         # (dlsm_run_traced: device trace ring drained on a copy stream while the next sweeps run);
         # no per-step host input exists in this mode, so it is reported beside e2e, not as e2e
         ntr = 3 * nst
+        tr = None
         tr = e.run_traced(ntr, fields_all=outs, pinned=True)   # allocates the pinned destination
         barrier()
         t0 = time.perf_counter()

@@ -78,6 +78,13 @@ struct dlsm_handle {
     size_t trace_slot[DLSM_F_COUNT_] = {0}; // bytes one record takes per field (0 = not traced)
     uint32_t trace_all = 0, trace_first = 0;
     int trace_logp = 0, trace_R = 0;
+    // early copy of the positions: X is final once it is centred, so its record can leave for the host
+    // while the rest of the sweep (intercept / radii MH, labels, HDP block) still runs
+    char *early_x_dst = nullptr;     // host address of this sweep's X record, or null
+    cudaEvent_t ev_x_ready = nullptr, ev_x_copied = nullptr;
+    cudaStream_t x_stream = nullptr; // its own stream: never queued behind a ring drain
+    bool x_copy_pending = false;
+    bool early_x_active = false;     // this dlsm_run_traced call bypasses the ring for X
     double *d_logp = nullptr;       // [C] scratch of dlsm_logp
     double *d_gather = nullptr;     // [C][T][n][4] packed {x, y, 1/r, 0} records of the case-control kernels
     double *d_center = nullptr;     // means [C][8] + partial sums [C][128][8] of the long-chain centring
@@ -644,6 +651,9 @@ void dlsm_destroy(dlsm_handle *h)
                     h->d_small, h->d_small_i, h->d_flags, h->d_bad, h->d_progress, h->d_ticket, h->d_ffbs_stage,
                     h->d_cc_dep};
     for (void *p : ptrs) cudaFree(p);
+    if (h->x_stream) cudaStreamDestroy(h->x_stream);
+    if (h->ev_x_ready) cudaEventDestroy(h->ev_x_ready);
+    if (h->ev_x_copied) cudaEventDestroy(h->ev_x_copied);
     free_trace(h);
     cudaFree(h->d_logp);
     cudaFree(h->d_center);
@@ -1223,12 +1233,25 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
     // behind, so the intercept / radii MH below evaluates only its proposals
     bool use_cur = !use_slice_kernel(h) && h->lk != kCaseControl && !getenv("DLSM_NO_LLCUR");
     p.ll_cur = use_cur ? F<double>(h, DLSM_F_LOGLIK) : nullptr;
+    if (h->x_copy_pending) { // the previous record of X is still on its way to the host
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_x_copied, 0));
+        h->x_copy_pending = false;
+    }
     tl_begin(h, "sweep");
     if ((rc = launch_sweep(h, p)) != DLSM_OK) return rc;
     tl_end(h);
     h->sweep_idx[kRngLatent] += 1;
     if (procrustes && (rc = procrustes_async(h)) != DLSM_OK) return rc; // lsm.py:495-498
     if (!(flags & 1u) && !fuse && (rc = center_async(h, getenv("DLSM_CENTER_EXACT") != nullptr)) != DLSM_OK) return rc;
+    if (h->early_x_dst) { // X is final for this sweep: stream its record out now
+        CU(h, cudaEventRecord(h->ev_x_ready, h->stream));
+        CU(h, cudaStreamWaitEvent(h->x_stream, h->ev_x_ready, 0));
+        CU(h, cudaMemcpyAsync(h->early_x_dst, h->field[DLSM_F_X], h->field_bytes[DLSM_F_X],
+                              cudaMemcpyDeviceToHost, h->x_stream));
+        CU(h, cudaEventRecord(h->ev_x_copied, h->x_stream));
+        h->x_copy_pending = true;
+        h->early_x_dst = nullptr;
+    }
     // After centring, the label block (FFBS -> HDP update; latency-bound, few warps per SM)
     // and the intercept / radii MH (full-network kernel; issue-bound) are independent: run
     // the label block on a high-priority side stream so the two overlap.
@@ -1437,6 +1460,9 @@ static int prepare_trace(dlsm_handle *h, const dlsm_trace_spec *sp, int n_record
     }
     if (nseg > kMaxSnapSeg) FAIL(h, DLSM_ERR_INVALID, "at most %d traced fields", kMaxSnapSeg);
     if (per_record == 0) { free_trace(h); return DLSM_OK; }
+    const bool same_spec = h->trace_R > 0 && h->trace_all == sp->fields_all &&
+                           h->trace_first == sp->fields_first && h->trace_logp == (sp->want_logp ? 1 : 0);
+    if (same_spec && h->trace_R >= n_records) return DLSM_OK; // the common case: no driver query
     size_t free_b = 0, total_b = 0;
     CU(h, cudaMemGetInfo(&free_b, &total_b));
     size_t budget = (size_t)512 << 20; // per chunk
@@ -1446,9 +1472,7 @@ static int prepare_trace(dlsm_handle *h, const dlsm_trace_spec *sp, int n_record
     if (R < 1) R = 1;
     if (R > 1024) R = 1024;
     if (R > n_records) R = n_records > 0 ? n_records : 1;
-    bool same = h->trace_R >= R && h->trace_all == sp->fields_all && h->trace_first == sp->fields_first &&
-                h->trace_logp == (sp->want_logp ? 1 : 0);
-    if (same) return DLSM_OK;
+    if (same_spec && h->trace_R >= R) return DLSM_OK;
     CU(h, cudaStreamSynchronize(h->stream));
     if (h->copy_stream) CU(h, cudaStreamSynchronize(h->copy_stream));
     free_trace(h);
@@ -1473,7 +1497,7 @@ static int drain_chunk(dlsm_handle *h, int which, size_t first, int count, void 
     auto &ch = h->chunk[which];
     CU(h, cudaStreamWaitEvent(h->copy_stream, ch.filled, 0));
     for (int f = 0; f < DLSM_F_COUNT_; f++) {
-        if (!h->trace_slot[f]) continue;
+        if (!h->trace_slot[f] || (h->early_x_active && f == DLSM_F_X)) continue;
         char *to = static_cast<char *>(dst[f]) + first * h->trace_slot[f];
         CU(h, cudaMemcpyAsync(to, ch.dev[f], h->trace_slot[f] * (size_t)count, cudaMemcpyDeviceToHost, h->copy_stream));
     }
@@ -1507,6 +1531,21 @@ int dlsm_run_traced(dlsm_handle *h, int32_t n_sweeps, uint32_t flags, const dlsm
     int R = h->trace_R;
     if (R > (n_records + 3) / 4) R = (n_records + 3) / 4;
     if (R < 1) R = 1;
+    // Positions traced for every chain into page-locked memory leave early (see one_sweep); a
+    // pageable destination would block the host inside the sweep, so it goes through the ring.
+    bool early_x = false;
+    if (tracing && !(flags & 1u) && h->trace_slot[DLSM_F_X] == h->field_bytes[DLSM_F_X] &&
+        h->trace_slot[DLSM_F_X] >= ((size_t)1 << 20) && !getenv("DLSM_NO_EARLY_X")) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, dst[DLSM_F_X]) == cudaSuccess && at.type == cudaMemoryTypeHost) early_x = true;
+        cudaGetLastError();
+        if (early_x && !h->ev_x_ready) {
+            CU(h, cudaEventCreateWithFlags(&h->ev_x_ready, cudaEventDisableTiming));
+            CU(h, cudaEventCreateWithFlags(&h->ev_x_copied, cudaEventDisableTiming));
+            CU(h, cudaStreamCreateWithFlags(&h->x_stream, cudaStreamNonBlocking));
+        }
+    }
+    h->early_x_active = early_x;
     int cur = 0, fill = 0;          // chunk being filled, records in it
     size_t done = 0;                // records handed to earlier chunks
     int pending = -1, pending_n = 0; // filled chunk not yet drained (one chunk of lookahead keeps
@@ -1514,8 +1553,12 @@ int dlsm_run_traced(dlsm_handle *h, int32_t n_sweeps, uint32_t flags, const dlsm
     for (auto &ch : h->chunk) ch.used = false;
     for (int s = 0; s < n_sweeps; s++) {
         bool tracked = false;
+        const bool record = tracing && (s + 1) % sp->thin == 0;
+        h->early_x_dst = (early_x && record)
+                             ? static_cast<char *>(dst[DLSM_F_X]) + (done + fill) * h->trace_slot[DLSM_F_X]
+                             : nullptr;
         if ((rc = one_sweep(h, flags, &tracked)) != DLSM_OK) return rc;
-        if (!tracing || (s + 1) % sp->thin != 0) continue;
+        if (!record) continue;
         if ((rc = join_side_stream(h, flags)) != DLSM_OK) return rc;
         auto &ch = h->chunk[cur];
         if (fill == 0 && ch.used) CU(h, cudaStreamWaitEvent(h->stream, ch.drained, 0));
@@ -1526,7 +1569,7 @@ int dlsm_run_traced(dlsm_handle *h, int32_t n_sweeps, uint32_t flags, const dlsm
         memset(&sn, 0, sizeof(sn));
         size_t max_words = 0;
         for (int f = 0; f < DLSM_F_COUNT_; f++) {
-            if (!h->trace_slot[f]) continue;
+            if (!h->trace_slot[f] || (early_x && f == DLSM_F_X)) continue;
             sn.src[sn.nseg] = static_cast<const uint32_t *>(h->field[f]);
             sn.dst[sn.nseg] = reinterpret_cast<uint32_t *>(static_cast<char *>(ch.dev[f]) + (size_t)fill * h->trace_slot[f]);
             sn.words[sn.nseg] = h->trace_slot[f] / 4;
@@ -1556,7 +1599,10 @@ int dlsm_run_traced(dlsm_handle *h, int32_t n_sweeps, uint32_t flags, const dlsm
             if ((rc = drain_chunk(h, cur, done, fill, dst, logp_dst)) != DLSM_OK) return rc;
         }
         CU(h, cudaStreamSynchronize(h->copy_stream));
+        if (early_x) CU(h, cudaStreamSynchronize(h->x_stream));
     }
+    h->early_x_active = false;
+    h->x_copy_pending = false; // the copy stream has been drained
     if ((rc = join_side_stream(h, flags)) != DLSM_OK) return rc;
     return check_flags(h);
 }

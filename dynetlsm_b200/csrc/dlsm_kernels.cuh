@@ -1405,11 +1405,9 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
             load_pos<DM>(Xt + (size_t)i2 * d, d, xi2);
             double ra0 = 0, ra1 = 0, rb0 = 0, rb1 = 0;
             if (LK == kDirected) { ra0 = r0[i]; ra1 = r1[i]; rb0 = r0[i2]; rb1 = r1[i2]; }
-            // chunks of 32 pair slots per trip: four softplus chains in flight per lane either way
-            constexpr int UC = (NV == 1) ? 4 : 2;
-            for (int base = 0; base < slots; base += 32 * UC) {
+            for (int base = 0; base < slots; base += 64) {
 #pragma unroll
-                for (int u = 0; u < UC; u++) {
+                for (int u = 0; u < 2; u++) {
                     const int m = base + u * 32 + lane;
                     const bool first = m < len1;
                     const int arow = first ? i : i2;

@@ -291,3 +291,35 @@ def test_device_mode_case_control_fit_runs():
     assert m.Xs_.shape == (80, 3, 25, 2) and np.all(np.isfinite(m.logps_))
     cc = m.case_control_sampler_
     assert cc.control_nodes_in_.shape == (3, 25, 6) and cc.control_nodes_out_.max() < 25
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_run_traced_large_positions_leave_early(pinned):
+    """Position records of at least 1 MB into page-locked memory are copied out right after the
+    centring, concurrently with the rest of the sweep (pageable destinations go through the ring):
+    same records either way, and the same as a sweep-by-sweep loop."""
+    L = _L()
+    T, n, d, C_ = 4, 1100, 2, 16                    # X = 1.1 MB per record
+    rng = np.random.RandomState(4)
+    Y = _net(rng, T, n, False, 0.02)
+
+    def make():
+        e = L.Engine(T=T, n=n, d=d, n_chains=C_, tune=50, tune_interval=10)
+        e.set_network(Y)
+        r2 = np.random.RandomState(5)
+        e.set(L.F_X, r2.randn(C_, T, n, d))
+        e.set(L.F_INTERCEPT, np.tile([[0.5, 0.0]], (C_, 1)))
+        e.set_hyper(tau_sq=2.0, sigma_sq=0.2)
+        e.set_tuner(0.05)
+        e.set_rng(8)
+        return e
+    a, b = make(), make()
+    tr = a.run_traced(7, fields_all=(L.F_X, L.F_INTERCEPT), thin=2, pinned=pinned)
+    assert tr[L.F_X].shape == (3, C_, T, n, d)
+    for r in range(3):
+        b.run_sweeps(2)
+        assert np.array_equal(tr[L.F_X][r], b.get(L.F_X)), r
+        assert np.array_equal(tr[L.F_INTERCEPT][r], b.get(L.F_INTERCEPT)), r
+        assert np.allclose(tr["logp"][r], b.logp(), rtol=1e-10, atol=0)
+    b.run_sweeps(1)
+    assert np.array_equal(a.get(L.F_X), b.get(L.F_X))
