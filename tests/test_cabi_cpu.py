@@ -62,3 +62,16 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "pyoracle" not in src and "liboracle" not in src and "oracle/" not in src, f
+
+
+def test_field_ids_match_the_header():
+    """The Python field constants mirror include/dlsm.h's dlsm_field enum one to one."""
+    import re
+    from dynetlsm_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "dlsm.h")).read()
+    enum = src[src.index("DLSM_F_X = 0"):src.index("DLSM_F_COUNT_")]
+    ids = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"DLSM_F_(\w+)\s*=\s*(\d+)", enum))
+    assert sorted(ids.values()) == list(range(len(ids)))
+    assert _lib.N_FIELDS == len(ids)
+    for name, val in ids.items():
+        assert getattr(_lib, "F_" + name) == val, name
