@@ -85,6 +85,7 @@ struct dlsm_handle {
     cudaStream_t x_stream = nullptr; // its own stream: never queued behind a ring drain
     bool x_copy_pending = false;
     bool early_x_active = false;     // this dlsm_run_traced call bypasses the ring for X
+    bool trace_early_x = false;      // ... and the ring was allocated without an X slot
     double *d_logp = nullptr;       // [C] scratch of dlsm_logp
     double *d_gather = nullptr;     // [C][T][n][4] packed {x, y, 1/r, 0} records of the case-control kernels
     double *d_center = nullptr;     // means [C][8] + partial sums [C][128][8] of the long-chain centring
@@ -1444,7 +1445,7 @@ int dlsm_host_free(void *p)
 }
 
 // (re)allocate the two device trace chunks for a trace specification
-static int prepare_trace(dlsm_handle *h, const dlsm_trace_spec *sp, int n_records)
+static int prepare_trace(dlsm_handle *h, const dlsm_trace_spec *sp, int n_records, bool early_x)
 {
     const dlsm_config &c = h->cfg;
     size_t slot[DLSM_F_COUNT_] = {0};
@@ -1455,13 +1456,16 @@ static int prepare_trace(dlsm_handle *h, const dlsm_trace_spec *sp, int n_record
         if (!all && !first) continue;
         if (h->field_bytes[f] == 0) FAIL(h, DLSM_ERR_INVALID, "traced field %d does not exist in this configuration", f);
         slot[f] = all ? h->field_bytes[f] : h->field_bytes[f] / c.n_chains;
+        if (early_x && f == DLSM_F_X) continue; // copied straight from the live state, no ring slot
         per_record += slot[f];
         nseg++;
     }
     if (nseg > kMaxSnapSeg) FAIL(h, DLSM_ERR_INVALID, "at most %d traced fields", kMaxSnapSeg);
-    if (per_record == 0) { free_trace(h); return DLSM_OK; }
+    if (per_record == 0 && !early_x) { free_trace(h); return DLSM_OK; }
+    if (per_record == 0) per_record = 1; // only the early-copied positions: events, no ring buffers
     const bool same_spec = h->trace_R > 0 && h->trace_all == sp->fields_all &&
-                           h->trace_first == sp->fields_first && h->trace_logp == (sp->want_logp ? 1 : 0);
+                           h->trace_first == sp->fields_first && h->trace_logp == (sp->want_logp ? 1 : 0) &&
+                           h->trace_early_x == early_x;
     if (same_spec && h->trace_R >= n_records) return DLSM_OK; // the common case: no driver query
     size_t free_b = 0, total_b = 0;
     CU(h, cudaMemGetInfo(&free_b, &total_b));
@@ -1479,7 +1483,7 @@ static int prepare_trace(dlsm_handle *h, const dlsm_trace_spec *sp, int n_record
     if (!h->copy_stream) CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (auto &ch : h->chunk) {
         for (int f = 0; f < DLSM_F_COUNT_; f++)
-            if (slot[f]) CU(h, cudaMalloc(&ch.dev[f], slot[f] * (size_t)R));
+            if (slot[f] && !(early_x && f == DLSM_F_X)) CU(h, cudaMalloc(&ch.dev[f], slot[f] * (size_t)R));
         if (sp->want_logp) CU(h, cudaMalloc((void **)&ch.logp, (size_t)c.n_chains * 8 * (size_t)R));
         CU(h, cudaEventCreateWithFlags(&ch.filled, cudaEventDisableTiming));
         CU(h, cudaEventCreateWithFlags(&ch.drained, cudaEventDisableTiming));
@@ -1487,6 +1491,7 @@ static int prepare_trace(dlsm_handle *h, const dlsm_trace_spec *sp, int n_record
     memcpy(h->trace_slot, slot, sizeof(slot));
     h->trace_all = sp->fields_all; h->trace_first = sp->fields_first;
     h->trace_logp = sp->want_logp ? 1 : 0;
+    h->trace_early_x = early_x;
     h->trace_R = (int)R;
     return DLSM_OK;
 }
@@ -1524,26 +1529,26 @@ int dlsm_run_traced(dlsm_handle *h, int32_t n_sweeps, uint32_t flags, const dlsm
         if ((((sp->fields_all | sp->fields_first) >> f) & 1u) && n_records > 0 && (!dst || !dst[f]))
             FAIL(h, DLSM_ERR_INVALID, "no destination for traced field %d", f);
     if (sp->want_logp && n_records > 0 && !logp_dst) FAIL(h, DLSM_ERR_INVALID, "no destination for the log-posterior trace");
-    if ((rc = prepare_trace(h, sp, n_records)) != DLSM_OK) return rc;
-    const bool tracing = h->trace_R > 0 && n_records > 0;
+    // Positions traced for every chain into page-locked memory leave early (see one_sweep); a
+    // pageable destination would block the host inside the sweep, so it goes through the ring.
+    bool early_x = false;
+    if (n_records > 0 && !(flags & 1u) && ((sp->fields_all >> DLSM_F_X) & 1u) &&
+        h->field_bytes[DLSM_F_X] >= ((size_t)1 << 20) && !getenv("DLSM_NO_EARLY_X")) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, dst[DLSM_F_X]) == cudaSuccess && at.type == cudaMemoryTypeHost) early_x = true;
+        cudaGetLastError();
+    }
+    if ((rc = prepare_trace(h, sp, n_records, early_x)) != DLSM_OK) return rc;
+    const bool tracing = (h->trace_R > 0 || early_x) && n_records > 0;
     // records per chunk: the allocated capacity, but at least ~4 chunks per call so that the copy
     // of one chunk overlaps the sweeps filling the next even in short, heavy runs
     int R = h->trace_R;
     if (R > (n_records + 3) / 4) R = (n_records + 3) / 4;
     if (R < 1) R = 1;
-    // Positions traced for every chain into page-locked memory leave early (see one_sweep); a
-    // pageable destination would block the host inside the sweep, so it goes through the ring.
-    bool early_x = false;
-    if (tracing && !(flags & 1u) && h->trace_slot[DLSM_F_X] == h->field_bytes[DLSM_F_X] &&
-        h->trace_slot[DLSM_F_X] >= ((size_t)1 << 20) && !getenv("DLSM_NO_EARLY_X")) {
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, dst[DLSM_F_X]) == cudaSuccess && at.type == cudaMemoryTypeHost) early_x = true;
-        cudaGetLastError();
-        if (early_x && !h->ev_x_ready) {
-            CU(h, cudaEventCreateWithFlags(&h->ev_x_ready, cudaEventDisableTiming));
-            CU(h, cudaEventCreateWithFlags(&h->ev_x_copied, cudaEventDisableTiming));
-            CU(h, cudaStreamCreateWithFlags(&h->x_stream, cudaStreamNonBlocking));
-        }
+    if (early_x && !h->ev_x_ready) {
+        CU(h, cudaEventCreateWithFlags(&h->ev_x_ready, cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&h->ev_x_copied, cudaEventDisableTiming));
+        CU(h, cudaStreamCreateWithFlags(&h->x_stream, cudaStreamNonBlocking));
     }
     h->early_x_active = early_x;
     int cur = 0, fill = 0;          // chunk being filled, records in it

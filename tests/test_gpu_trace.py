@@ -323,3 +323,7 @@ def test_run_traced_large_positions_leave_early(pinned):
         assert np.allclose(tr["logp"][r], b.logp(), rtol=1e-10, atol=0)
     b.run_sweeps(1)
     assert np.array_equal(a.get(L.F_X), b.get(L.F_X))
+    # positions only, no log-posterior: nothing goes through the ring on the early path
+    tr = a.run_traced(3, fields_all=(L.F_X,), logp=False, pinned=pinned)
+    b.run_sweeps(3)
+    assert np.array_equal(tr[L.F_X][2], b.get(L.F_X))
