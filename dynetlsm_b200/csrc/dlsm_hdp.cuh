@@ -8,6 +8,10 @@
 #include "dlsm_device.cuh"
 #include "../../include/dlsm.h"
 
+#ifndef DLSM_HDP_BIN_BYTES
+#define DLSM_HDP_BIN_BYTES (24 * 1024)
+#endif
+
 namespace dlsm {
 
 constexpr uint32_t kRngHdp = 4;
@@ -478,7 +482,7 @@ __global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
 inline int hdp_bin_rows(int K, int d)
 {
     const size_t nbin = (size_t)2 * K * d + K;
-    const size_t rows = ((size_t)24 * 1024) / (nbin * sizeof(double));
+    const size_t rows = ((size_t)DLSM_HDP_BIN_BYTES) / (nbin * sizeof(double));
     return rows >= 128 ? 128 : (rows >= 64 ? 64 : (rows >= 32 ? 32 : 0));
 }
 
