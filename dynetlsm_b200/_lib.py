@@ -79,7 +79,7 @@ EXPORTS = [
     "dlsm_sweep_latent", "dlsm_center", "dlsm_sample_intercepts", "dlsm_sample_radii",
     "dlsm_sample_labels", "dlsm_set_hdp_prior", "dlsm_hdp_update", "dlsm_run_sweeps", "dlsm_loglik_partial", "dlsm_loglik_full",
     "dlsm_gaussian_likelihood", "dlsm_debug_set_counts", "dlsm_debug_draws", "dlsm_enable_timing", "dlsm_get_counters",
-    "dlsm_resample_controls", "dlsm_get_controls", "dlsm_logp", "dlsm_set_procrustes_ref", "dlsm_procrustes", "dlsm_run_traced", "dlsm_host_alloc", "dlsm_host_free",
+    "dlsm_resample_controls", "dlsm_get_controls", "dlsm_edge_probas", "dlsm_logp", "dlsm_set_procrustes_ref", "dlsm_procrustes", "dlsm_run_traced", "dlsm_host_alloc", "dlsm_host_free",
 ]
 
 F_X, F_INTERCEPT, F_RADII, F_Z, F_MU, F_SIGMA, F_LAMBDA, F_WEIGHTS = range(8)
@@ -133,6 +133,7 @@ def load():
     L.dlsm_enable_timing.argtypes = [vp, C.c_int]
     L.dlsm_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.dlsm_logp.argtypes = [vp, dp]
+    L.dlsm_edge_probas.argtypes = [vp, C.c_int32, dp]
     L.dlsm_resample_controls.argtypes = [vp, C.c_int32, C.c_int32]
     L.dlsm_get_controls.argtypes = [vp, ip, ip]
     L.dlsm_set_procrustes_ref.argtypes = [vp, dp]
@@ -428,6 +429,12 @@ class Engine(object):
         ci, co = np.empty(shp, np.int32), np.empty(shp, np.int32)
         self._ck(self.L.dlsm_get_controls(self.h, _ip(ci), _ip(co)))
         return ci, co
+
+    def edge_probas(self, chain=0):
+        """(T, n, n) edge probabilities of one chain at its current state (zero diagonal)."""
+        out = np.empty((self.T, self.n, self.n))
+        self._ck(self.L.dlsm_edge_probas(self.h, int(chain), _dp(out)))
+        return out
 
     def logp(self):
         out = np.empty((self.C,))

@@ -1401,6 +1401,25 @@ static int procrustes_async(dlsm_handle *h)
     return rc;
 }
 
+int dlsm_edge_probas(dlsm_handle *h, int32_t chain, double *out)
+{
+    if (!h || !out) return DLSM_ERR_INVALID;
+    const dlsm_config &c = h->cfg;
+    if (chain < 0 || chain >= c.n_chains) FAIL(h, DLSM_ERR_INVALID, "chain out of range");
+    CU(h, cudaSetDevice(c.device));
+    const size_t cells = (size_t)c.T * c.n * c.n;
+    double *d_out = nullptr;
+    CU(h, cudaMalloc((void **)&d_out, cells * sizeof(double)));
+    const double *X = F<double>(h, DLSM_F_X) + (size_t)chain * c.T * c.n * c.d;
+    const double *ic = F<double>(h, DLSM_F_INTERCEPT) + (size_t)chain * 2;
+    const double *ri = c.is_directed ? h->rinv + (size_t)chain * c.n : nullptr;
+    int rc = launch_simple(h, k_edge_probas, dim3((unsigned)(((size_t)c.n * c.n + 255) / 256), c.T), dim3(256), 0,
+                           X, ic, ri, c.n, c.d, (int)c.is_directed, d_out);
+    if (rc == DLSM_OK) rc = download(h, out, d_out, cells * sizeof(double));
+    cudaFree(d_out);
+    return rc;
+}
+
 int dlsm_set_procrustes_ref(dlsm_handle *h, const double *Xref)
 {
     if (!h) return DLSM_ERR_INVALID;

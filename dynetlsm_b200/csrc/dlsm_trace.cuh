@@ -278,6 +278,32 @@ __global__ void __launch_bounds__(256) k_snapshot(const SnapParams p)
 
 
 // ---------------------------------------------------------------------------------------------
+// Edge probabilities at a chain's current state (K9 directed_network_probas,
+// directed_likelihoods_fast.pyx:273-294; undirected: expit(beta - dist), lsm.py:296-305), zero diagonal.
+// out (T, n, n);  grid = (ceil(n*n/256), T), block = 256
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_edge_probas(const double *X /* [T][n][d] */, const double *intercept,
+                                                     const double *rinv /* [n] or null */, int n, int d,
+                                                     int directed, double *out)
+{
+    const int t = blockIdx.y;
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)n * n) return;
+    const int i = (int)(e / n), j = (int)(e % n);
+    double pr = 0.0;
+    if (i != j) {
+        const double *xi = X + ((size_t)t * n + i) * d, *xj = X + ((size_t)t * n + j) * d;
+        double s = 0.0;
+        for (int k = 0; k < d; k++) { const double df = xi[k] - xj[k]; s += df * df; }
+        const double dist = sqrt(s);
+        const double eta = directed ? intercept[0] * (1.0 - dist * rinv[j]) + intercept[1] * (1.0 - dist * rinv[i])
+                                    : intercept[0] - dist;
+        pr = 1.0 / (1.0 + exp(-eta));
+    }
+    out[(size_t)t * n * n + e] = pr;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Case-control sets on the device (DirectedCaseControlSampler.sample,
 // case_control_likelihood.py:75-112): for every (set, t, i) and both directions, min(n - deg - 1,
 // n_control) DISTINCT nodes drawn uniformly from the non-neighbours of i (i itself excluded), the

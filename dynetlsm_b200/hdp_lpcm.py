@@ -23,12 +23,12 @@ from . import _lib as L
 from .case_control_likelihood import DirectedCaseControlSampler
 from .hdp_updates import HDPHyper, conjugate_updates, hdp_log_prior
 from .host_init import longitudinal_kmeans, longitudinal_procrustes_rotation
-from .lsm import DynamicNetworkLSM, _Driver
+from .lsm import DynamicNetworkLSM, _Driver, _FittedNetworkMixin
 
 __all__ = ["DynamicNetworkHDPLPCM"]
 
 
-class DynamicNetworkHDPLPCM(object):
+class DynamicNetworkHDPLPCM(_FittedNetworkMixin):
     def __init__(self, n_features=2, n_components=10, is_directed=False, selection_type="vi",
                  n_iter=5000, tune=2500, tune_interval=100, burn=2500, thin=None, gamma=1.0,
                  gamma_prior_shape=1.0, gamma_prior_rate=0.1, alpha_init=1.0, alpha_init_shape=1.,
@@ -42,10 +42,6 @@ class DynamicNetworkHDPLPCM(object):
         for k, v in list(locals().items()):
             if k != "self":
                 setattr(self, k, v)
-
-    @property
-    def n_burn_(self):
-        return (self.burn or 0) + (self.tune or 0)
 
     def fit(self, Y):
         replay = self.sampler == "replay"

@@ -115,7 +115,50 @@ class _Driver(object):
         return e.sample_labels(U)
 
 
-class DynamicNetworkLSM(object):
+class _FittedNetworkMixin(object):
+    """Derived quantities of a fitted estimator (lsm.py:270-317, hdp_lpcm.py:462-495)."""
+
+    @property
+    def n_burn_(self):
+        return (self.burn or 0) + (self.tune or 0)
+
+    @property
+    def distances_(self):
+        if not hasattr(self, "X_"):
+            raise ValueError("Model not fit.")
+        return calculate_distances(self.X_)
+
+    @property
+    def probas_(self):
+        """Edge probabilities at the point estimate, (T, n, n), zero diagonal: directed
+        directed_network_probas (directed_likelihoods_fast.pyx:273-294), undirected
+        expit(intercept - dist); evaluated by dlsm_edge_probas on the device."""
+        if not hasattr(self, "X_"):
+            raise ValueError("Model not fit.")
+        T, n, d = self.X_.shape
+        e = L.Engine(T=T, n=n, d=d, n_chains=1, is_directed=self.is_directed, device=self.device)
+        try:
+            e.set(L.F_X, self.X_[None])
+            ic = np.zeros((1, 2))
+            ic[0, :np.size(self.intercept_)] = np.ravel(self.intercept_)
+            e.set(L.F_INTERCEPT, ic)
+            if self.is_directed:
+                e.set(L.F_RADII, np.asarray(self.radii_)[None])
+            return e.edge_probas(0)
+        finally:
+            e.close()
+
+    @property
+    def auc_(self):
+        from sklearn.metrics import roc_auc_score
+        if not hasattr(self, "X_"):
+            raise ValueError("Model not fit.")
+        n = self.Y_fit_.shape[1]
+        mask = ~np.eye(n, dtype=bool) if self.is_directed else np.triu(np.ones((n, n), bool), 1)
+        return roc_auc_score(self.Y_fit_[:, mask].ravel(), self.probas_[:, mask].ravel())
+
+
+class DynamicNetworkLSM(_FittedNetworkMixin):
     """Latent space model for dynamic networks (Sewell & Chen 2015), sampled on a B200.
 
     Parameters follow the reference estimator (lsm.py:103-213); see the module docstring for the
@@ -148,41 +191,7 @@ class DynamicNetworkLSM(object):
         self.n_chains = n_chains
         self.device = device
 
-    # -- reference properties (lsm.py:270-317) -----------------------------------------------
-    @property
-    def n_burn_(self):
-        return (self.burn or 0) + (self.tune or 0)
-
-    @property
-    def distances_(self):
-        if not hasattr(self, "X_"):
-            raise ValueError("Model not fit.")
-        return calculate_distances(self.X_)
-
-    @property
-    def probas_(self):
-        if not hasattr(self, "X_"):
-            raise ValueError("Model not fit.")
-        dist = self.distances_
-        if self.is_directed:
-            r = self.radii_
-            eta = (self.intercept_[0] * (1 - dist / r[None, None, :]) +
-                   self.intercept_[1] * (1 - dist / r[None, :, None]))
-            probas = expit(eta)
-        else:
-            probas = expit(self.intercept_ - dist)
-        idx = np.arange(dist.shape[1])
-        probas[:, idx, idx] = 0.0
-        return probas
-
-    @property
-    def auc_(self):
-        from sklearn.metrics import roc_auc_score
-        if not hasattr(self, "X_"):
-            raise ValueError("Model not fit.")
-        n = self.Y_fit_.shape[1]
-        mask = ~np.eye(n, dtype=bool) if self.is_directed else np.triu(np.ones((n, n), bool), 1)
-        return roc_auc_score(self.Y_fit_[:, mask].ravel(), self.probas_[:, mask].ravel())
+    # -- reference properties (lsm.py:270-317) live in _FittedNetworkMixin ----------------------
 
     # -- joint log-posterior (lsm.py:576-625), network term from the device -------------------
     def _log_prior(self, X, intercept):

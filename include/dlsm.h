@@ -225,6 +225,11 @@ int dlsm_run_traced(dlsm_handle *h, int32_t n_sweeps, uint32_t flags, const dlsm
 int dlsm_host_alloc(size_t bytes, void **out);
 int dlsm_host_free(void *p);
 
+/* Edge probabilities of one chain at its current state, out (T,n,n), zero diagonal: directed
+ * directed_network_probas (directed_likelihoods_fast.pyx:273-294, the estimators' probas_,
+ * hdp_lpcm.py:480-492), undirected expit(beta - dist) (lsm.py:296-305). */
+int dlsm_edge_probas(dlsm_handle *h, int32_t chain, double *out);
+
 /* ---- parity probes --------------------------------------------------------------------- */
 /* per-node log-likelihood at the current state, out (C,T,n):
  * partial_loglikelihood / directed_partial_loglikelihood / approx_directed_partial_loglikelihood */

@@ -327,3 +327,36 @@ def test_run_traced_large_positions_leave_early(pinned):
     tr = a.run_traced(3, fields_all=(L.F_X,), logp=False, pinned=pinned)
     b.run_sweeps(3)
     assert np.array_equal(tr[L.F_X][2], b.get(L.F_X))
+
+
+@pytest.mark.parametrize("directed,d", [(False, 2), (True, 2), (True, 3)])
+def test_edge_probas_vs_reference_kernel(directed, d):
+    """dlsm_edge_probas against the reference's compiled directed_network_probas (K9,
+    directed_likelihoods_fast.pyx:273-294) / expit(beta - dist) for the undirected model."""
+    import ref_driver as R
+    from scipy.special import expit
+    L = _L()
+    T, n, C_ = 3, 37, 2
+    rng = np.random.RandomState(d)
+    X = rng.randn(C_, T, n, d) * (0.02 if directed else 1.0)
+    e = L.Engine(T=T, n=n, d=d, n_chains=C_, is_directed=directed)
+    e.set(L.F_X, X)
+    ic = np.array([[0.4, 0.7], [0.1, 0.9]]) if directed else np.array([[0.8, 0.0], [1.3, 0.0]])
+    e.set(L.F_INTERCEPT, ic)
+    radii = rng.dirichlet(np.ones(n) * 5, size=C_)
+    if directed:
+        e.set(L.F_RADII, radii)
+    for c in range(C_):
+        got = e.edge_probas(c)
+        dist = np.linalg.norm(X[c][:, :, None, :] - X[c][:, None, :, :], axis=-1)
+        if directed:
+            if not R.have_ref():
+                pytest.skip("oracle/_ref not built")
+            want = R.ref_kernels()["directed_likelihoods_fast"].directed_network_probas(
+                np.ascontiguousarray(dist), radii[c], ic[c, 0], ic[c, 1])
+        else:
+            want = expit(ic[c, 0] - dist)
+            idx = np.arange(n)
+            want[:, idx, idx] = 0.0
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-15)
+        assert np.all(np.diagonal(got, axis1=1, axis2=2) == 0.0)
