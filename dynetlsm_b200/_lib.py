@@ -62,7 +62,8 @@ class HdpPrior(C.Structure):
 
 class TraceSpec(C.Structure):
     _fields_ = [("fields_all", C.c_uint32), ("fields_first", C.c_uint32), ("thin", C.c_int32),
-                ("want_logp", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("want_logp", C.c_int32), ("cooc_mode", C.c_int32), ("cooc_from", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
 
 
 class Counters(C.Structure):
@@ -79,7 +80,7 @@ EXPORTS = [
     "dlsm_sweep_latent", "dlsm_center", "dlsm_sample_intercepts", "dlsm_sample_radii",
     "dlsm_sample_labels", "dlsm_set_hdp_prior", "dlsm_hdp_update", "dlsm_run_sweeps", "dlsm_loglik_partial", "dlsm_loglik_full",
     "dlsm_gaussian_likelihood", "dlsm_debug_set_counts", "dlsm_debug_draws", "dlsm_enable_timing", "dlsm_get_counters",
-    "dlsm_resample_controls", "dlsm_get_controls", "dlsm_edge_probas", "dlsm_logp", "dlsm_set_procrustes_ref", "dlsm_procrustes", "dlsm_run_traced", "dlsm_host_alloc", "dlsm_host_free",
+    "dlsm_resample_controls", "dlsm_get_controls", "dlsm_edge_probas", "dlsm_cooccurrence", "dlsm_logp", "dlsm_set_procrustes_ref", "dlsm_procrustes", "dlsm_run_traced", "dlsm_host_alloc", "dlsm_host_free",
 ]
 
 F_X, F_INTERCEPT, F_RADII, F_Z, F_MU, F_SIGMA, F_LAMBDA, F_WEIGHTS = range(8)
@@ -134,6 +135,7 @@ def load():
     L.dlsm_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.dlsm_logp.argtypes = [vp, dp]
     L.dlsm_edge_probas.argtypes = [vp, C.c_int32, dp]
+    L.dlsm_cooccurrence.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_int32]
     L.dlsm_resample_controls.argtypes = [vp, C.c_int32, C.c_int32]
     L.dlsm_get_controls.argtypes = [vp, ip, ip]
     L.dlsm_set_procrustes_ref.argtypes = [vp, dp]
@@ -381,7 +383,7 @@ class Engine(object):
 
     def run_traced(self, n_sweeps, fields_all=(), fields_first=(), thin=1, logp=True, pinned=False,
                    skip_center=False, skip_intercepts=False, skip_radii=False, skip_labels=False,
-                   skip_hdp=False, out=None):
+                   skip_hdp=False, out=None, cooc=0, cooc_from=0):
         """``n_sweeps`` sweeps on the device, recording every ``thin``-th state: returns
         ``{field: array (records, C or 1, ...)}`` plus ``"logp": (records, C)``.  The copies to the
         host overlap the following sweeps.  ``out``: a dict returned by an earlier call with at
@@ -391,7 +393,8 @@ class Engine(object):
                 (4 if skip_radii else 0) | (8 if skip_labels else 0) | (16 if skip_hdp else 0)
         rec = int(n_sweeps) // int(thin)
         alloc = pinned_empty if pinned else np.empty
-        spec = TraceSpec(thin=int(thin), want_logp=int(bool(logp)))
+        spec = TraceSpec(thin=int(thin), want_logp=int(bool(logp)), cooc_mode=int(cooc),
+                         cooc_from=int(cooc_from))
         dst = (C.c_void_p * N_FIELDS)()
         base = out._base if isinstance(out, _TraceDict) else (out or {})
         res = _TraceDict()
@@ -429,6 +432,14 @@ class Engine(object):
         ci, co = np.empty(shp, np.int32), np.empty(shp, np.int32)
         self._ck(self.L.dlsm_get_controls(self.h, _ip(ci), _ip(co)))
         return ci, co
+
+    def cooccurrence(self, reset=False):
+        """(counts (T, n, n) uint32, n_samples) accumulated by run_traced(cooc=1|2)."""
+        out = np.zeros((self.T, self.n, self.n), np.uint32)
+        ns = C.c_uint64(0)
+        self._ck(self.L.dlsm_cooccurrence(self.h, out.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(ns),
+                                          int(bool(reset))))
+        return out, int(ns.value)
 
     def edge_probas(self, chain=0):
         """(T, n, n) edge probabilities of one chain at its current state (zero diagonal)."""

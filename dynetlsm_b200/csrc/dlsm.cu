@@ -87,6 +87,8 @@ struct dlsm_handle {
     bool early_x_active = false;     // this dlsm_run_traced call bypasses the ring for X
     bool trace_early_x = false;      // ... and the ring was allocated without an X slot
     double *d_logp = nullptr;       // [C] scratch of dlsm_logp
+    uint32_t *d_cooc = nullptr;     // [T][n][n] co-clustering counts accumulated by dlsm_run_traced
+    uint64_t cooc_samples = 0;
     double *d_gather = nullptr;     // [C][T][n][4] packed {x, y, 1/r, 0} records of the case-control kernels
     double *d_center = nullptr;     // means [C][8] + partial sums [C][128][8] of the long-chain centring
     double *d_proc_ref = nullptr;   // [C][T][n][d] reference configuration of the in-loop Procrustes
@@ -658,6 +660,7 @@ void dlsm_destroy(dlsm_handle *h)
     free_trace(h);
     cudaFree(h->d_logp);
     cudaFree(h->d_center);
+    cudaFree(h->d_cooc);
     cudaFree(h->d_gather);
     cudaFree(h->d_proc_ref);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -1401,6 +1404,28 @@ static int procrustes_async(dlsm_handle *h)
     return rc;
 }
 
+int dlsm_cooccurrence(dlsm_handle *h, uint32_t *out, uint64_t *n_samples, int32_t reset)
+{
+    if (!h || !n_samples) return DLSM_ERR_INVALID;
+    CU(h, cudaSetDevice(h->cfg.device));
+    const size_t cells = (size_t)h->cfg.T * h->cfg.n * h->cfg.n;
+    *n_samples = h->d_cooc ? h->cooc_samples : 0;
+    if (out) {
+        if (h->d_cooc) {
+            int rc = download(h, out, h->d_cooc, cells * sizeof(uint32_t));
+            if (rc != DLSM_OK) return rc;
+        } else {
+            memset(out, 0, cells * sizeof(uint32_t));
+        }
+    }
+    if (reset && h->d_cooc) {
+        CU(h, cudaMemsetAsync(h->d_cooc, 0, cells * sizeof(uint32_t), h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->cooc_samples = 0;
+    }
+    return DLSM_OK;
+}
+
 int dlsm_edge_probas(dlsm_handle *h, int32_t chain, double *out)
 {
     if (!h || !out) return DLSM_ERR_INVALID;
@@ -1584,6 +1609,20 @@ int dlsm_run_traced(dlsm_handle *h, int32_t n_sweeps, uint32_t flags, const dlsm
         if ((rc = one_sweep(h, flags, &tracked)) != DLSM_OK) return rc;
         if (!record) continue;
         if ((rc = join_side_stream(h, flags)) != DLSM_OK) return rc;
+        if (sp->cooc_mode && h->cfg.prior == DLSM_PRIOR_MIXTURE && (int64_t)(done + fill) >= sp->cooc_from) {
+            const dlsm_config &c = h->cfg;
+            const size_t cells = (size_t)c.T * c.n * c.n;
+            if (!h->d_cooc) {
+                CU(h, cudaMalloc((void **)&h->d_cooc, cells * sizeof(uint32_t)));
+                CU(h, cudaMemsetAsync(h->d_cooc, 0, cells * sizeof(uint32_t), h->stream));
+                h->cooc_samples = 0;
+            }
+            const int C_use = sp->cooc_mode == 2 ? c.n_chains : 1;
+            rc = launch_simple(h, k_cooc_accumulate, dim3((unsigned)(((size_t)c.n * c.n + 255) / 256), c.T), dim3(256),
+                               0, (const int32_t *)F<int32_t>(h, DLSM_F_Z), C_use, c.T, c.n, h->d_cooc);
+            if (rc != DLSM_OK) return rc;
+            h->cooc_samples += (uint64_t)C_use;
+        }
         auto &ch = h->chunk[cur];
         if (fill == 0 && ch.used) CU(h, cudaStreamWaitEvent(h->stream, ch.drained, 0));
         if (h->trace_logp &&

@@ -278,6 +278,26 @@ __global__ void __launch_bounds__(256) k_snapshot(const SnapParams p)
 
 
 // ---------------------------------------------------------------------------------------------
+// Posterior co-clustering counts (label_utils.py:40-62 calculate_posterior_cooccurrence):
+// cooc[t][i][j] += #{chains c < C_use : z[c,t,i] == z[c,t,j]} for the current labels.
+// grid = (ceil(n*n/256), T), block = 256
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cooc_accumulate(const int32_t *z /* [C][T][n] */, int C_use, int T,
+                                                         int n, uint32_t *cooc /* [T][n][n] */)
+{
+    const int t = blockIdx.y;
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)n * n) return;
+    const int i = (int)(e / n), j = (int)(e % n);
+    uint32_t cnt = 0;
+    for (int c = 0; c < C_use; c++) {
+        const int32_t *zc = z + ((size_t)c * T + t) * n;
+        cnt += (zc[i] == zc[j]) ? 1u : 0u;
+    }
+    cooc[(size_t)t * n * n + e] += cnt;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Edge probabilities at a chain's current state (K9 directed_network_probas,
 // directed_likelihoods_fast.pyx:273-294; undirected: expit(beta - dist), lsm.py:296-305), zero diagonal.
 // out (T, n, n);  grid = (ceil(n*n/256), T), block = 256

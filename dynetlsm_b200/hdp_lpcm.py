@@ -221,7 +221,9 @@ class DynamicNetworkHDPLPCM(_FittedNetworkMixin):
                     cc.n_iter += 1
                     quiet = S if cc.n_resample is None else (cc.n_resample - cc.n_iter % cc.n_resample) % cc.n_resample
                     stop = min(stop, it + 1 + quiet)
-                tr = e.run_traced(stop - it, fields_all=every, fields_first=first, pinned=True, out=tr)
+                nb_ = min(self.n_burn_, S - 1)
+                tr = e.run_traced(stop - it, fields_all=every, fields_first=first, pinned=True, out=tr,
+                                  cooc=1, cooc_from=max(0, nb_ - it))   # co-clustering counts of chain 0
                 if cc is not None:
                     cc.n_iter += stop - it - 1
                 sl = slice(it, stop)
@@ -245,6 +247,8 @@ class DynamicNetworkHDPLPCM(_FittedNetworkMixin):
                 it = stop
             if hya is not None:
                 (hp.gamma, hp.alpha_init, hp.alpha, hp.kappa, hp.mean_variance_prior, hp.b) = hya[:6]
+            if self.thin is None and min(self.n_burn_, S - 1) >= 1:
+                self._device_cooc = e.cooccurrence(reset=True)   # (counts, samples) from the device
             if cc is not None:
                 ci, co = e.get_controls()
                 cc.control_nodes_in_, cc.control_nodes_out_ = ci[0].astype(np.int64), co[0].astype(np.int64)
@@ -293,11 +297,17 @@ class DynamicNetworkHDPLPCM(_FittedNetworkMixin):
         self.mu_, self.sigma_ = self.mus_[best, active], self.sigmas_[best, active]
         # co-clustering probabilities over the post-burn-in draws (label_utils.py:40-62)
         self.cooccurrence_probas_ = np.zeros((T, n, n))
-        eye = np.eye(K, dtype=np.float32)                    # 0/1 indicators: exact in fp32 BLAS
-        for t in range(T):
-            ind = eye[self.zs_[nb:, t]]                      # (S', n, K)
-            flat = ind.transpose(1, 0, 2).reshape(n, -1)     # (n, S' K): one GEMM per time step
-            self.cooccurrence_probas_[t] = (flat @ flat.T).astype(np.float64) / ind.shape[0]
+        dev = getattr(self, "_device_cooc", None)
+        if dev is not None and dev[1] == self.zs_.shape[0] - nb:
+            # accumulated on the device while sampling (dlsm_run_traced cooc_mode)
+            self.cooccurrence_probas_ = dev[0].astype(np.float64) / dev[1]
+        else:
+            eye = np.eye(K, dtype=np.float32)                    # 0/1 indicators: exact in fp32 BLAS
+            for t in range(T):
+                ind = eye[self.zs_[nb:, t]]                      # (S', n, K)
+                flat = ind.transpose(1, 0, 2).reshape(n, -1)     # (n, S' K): one GEMM per time step
+                self.cooccurrence_probas_[t] = (flat @ flat.T).astype(np.float64) / ind.shape[0]
+        self._device_cooc = None
         self.counts_ = np.array([np.unique(zz).size for zz in self.zs_[nb:]])
         # rotate every stored sample onto the point estimate (hdp_lpcm.py:1141-1146)
         for idx in range(self.Xs_.shape[0]):

@@ -212,7 +212,9 @@ typedef struct {
     uint32_t fields_first; /* bit f: store DLSM_F_<f> of chain 0 only */
     int32_t thin;          /* one record every `thin` sweeps (>= 1) */
     int32_t want_logp;     /* also store the joint log-posterior of every chain */
-    int32_t reserved[4];
+    int32_t cooc_mode;     /* co-clustering counts (label_utils.py:40-62): 0 off, 1 chain 0, 2 all chains pooled */
+    int32_t cooc_from;     /* first record of this call that is counted (burn-in) */
+    int32_t reserved[2];
 } dlsm_trace_spec;
 /* dlsm_run_sweeps that also records the chain: after every `thin`-th sweep the traced fields (and
  * the log-posterior) are gathered into a device ring and streamed to the host on a copy stream
@@ -221,6 +223,9 @@ typedef struct {
  * pinned (dlsm_host_alloc) memory, valid until the call returns. */
 int dlsm_run_traced(dlsm_handle *h, int32_t n_sweeps, uint32_t flags, const dlsm_trace_spec *spec,
                     void *const *dst, double *logp_dst);
+/* co-clustering counts accumulated on the device by dlsm_run_traced (cooc_mode): out (T,n,n) u32 (may
+ * be NULL), *n_samples = label configurations counted; reset != 0 clears the accumulator afterwards */
+int dlsm_cooccurrence(dlsm_handle *h, uint32_t *out, uint64_t *n_samples, int32_t reset);
 /* page-locked host memory for trace destinations */
 int dlsm_host_alloc(size_t bytes, void **out);
 int dlsm_host_free(void *p);

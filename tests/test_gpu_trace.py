@@ -360,3 +360,26 @@ def test_edge_probas_vs_reference_kernel(directed, d):
             want[:, idx, idx] = 0.0
         assert np.allclose(got, want, rtol=1e-12, atol=1e-15)
         assert np.all(np.diagonal(got, axis1=1, axis2=2) == 0.0)
+
+
+def test_device_cooccurrence_equals_host_counts():
+    """Co-clustering probabilities accumulated on the device while sampling (dlsm_run_traced
+    cooc_mode; label_utils.py:40-62) equal the host computation from the stored label draws."""
+    from dynetlsm_b200 import DynamicNetworkHDPLPCM
+    rng = np.random.RandomState(0)
+    Y = _net(rng, 3, 28, False, 0.25)
+    m = DynamicNetworkHDPLPCM(n_iter=60, tune=30, burn=30, n_components=5, random_state=3, n_chains=2).fit(Y)
+    nb = m.n_burn_
+    zs = m.zs_[nb:]
+    want = (zs[:, :, :, None] == zs[:, :, None, :]).mean(axis=0)
+    assert m.cooccurrence_probas_.shape == (3, 28, 28)
+    assert np.allclose(m.cooccurrence_probas_, want, rtol=0, atol=1e-15)
+    # the engine-level accumulator, pooled over chains
+    L = _L()
+    e, _ = _hdp_engine(4, 20, 2, 5, 3, False)
+    tr = e.run_traced(9, fields_all=(L.F_Z,), cooc=2, cooc_from=4)
+    counts, ns = e.cooccurrence(reset=True)
+    z = tr[L.F_Z][4:]                                     # (5 records, 3 chains, T, n)
+    assert ns == 15
+    assert np.array_equal(counts, (z[:, :, :, :, None] == z[:, :, :, None, :]).sum(axis=(0, 1)).astype(np.uint32))
+    assert e.cooccurrence()[1] == 0
