@@ -88,7 +88,10 @@ __device__ __forceinline__ double vmask(bool v) { return __hiloint2double(v ? 0x
 // i < j (lo_new / lo_old, NOT reduced over the warp).  Summed over the nodes of a slice with the accepted variant picked each
 // time, these give the full-network log-likelihood of the post-sweep state for free: the dyad
 // {i, j}, i < j, is last evaluated when j is updated, with x_i already final.
-template <int LK, int DM, bool LO = false>
+// INTR: give interior trips (64 existing pairs, none of them the self pair) their own unmasked body;
+// pays off for long rows (cfg 4: +2.7 %), costs 1.5 % at n = 120 where every trip is a boundary trip
+// or nearly, so only the long-row instantiation of k_sweep turns it on.
+template <int LK, int DM, bool LO = false, bool INTR = false>
 __device__ __forceinline__ void node_loglik2(const NetView &net, const double *Xt /* [n][d] */,
                                              const double *rinv /* [n] */, int chain, int t, int j,
                                              const double (&xn)[DM], const double (&xo)[DM],
@@ -111,6 +114,21 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
         for (int base = wteam * 64; base < n; base += 64 * nteam) {
             const int i0 = base + lane, i1 = i0 + 32;
             const uint2 w = __ldg(reinterpret_cast<const uint2 *>(row + (base >> 5)));
+            if (INTR && base + 64 <= n && (unsigned)(j - base) >= 64u &&
+                (skip < 0 || (unsigned)(skip - base) >= 64u)) {
+                // interior trip (warp-uniform): all 64 pairs exist and none is the self pair, so no
+                // masks, no clamped indices and -- the pairs being all below or all above j -- no
+                // lower-triangle bookkeeping either
+                const double y0 = ymask(w.x, lane), y1 = ymask(w.y, lane);
+                double xa[DM], xb[DM];
+                load_pos<DM>(Xt + (size_t)i0 * d, d, xa);
+                load_pos<DM>(Xt + (size_t)i1 * d, d, xb);
+                an += logit_term(y0, b0 - fast_dist<DM>(xa, xn, d));
+                ao += logit_term(y0, b0 - fast_dist<DM>(xa, xo, d));
+                an2 += logit_term(y1, b0 - fast_dist<DM>(xb, xn, d));
+                ao2 += logit_term(y1, b0 - fast_dist<DM>(xb, xo, d));
+                continue;
+            }
             const double v0 = vmask((i0 < n) && (i0 != j) && (i0 != skip));
             const double v1 = vmask((i1 < n) && (i1 != j) && (i1 != skip));
             const double y0 = ymask(w.x, lane), y1 = ymask(w.y, lane);
@@ -473,9 +491,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
                     if (LK == kDirected) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.net.colbits + o));
                 }
                 double ll_new, ll_old, lo_n = 0.0, lo_o = 0.0;
+                // the (320, 2) build is the one picked when shared memory admits two chains per SM,
+                // i.e. for long rows: it gets the unmasked interior trips
                 if (LK != kCaseControl)
-                    node_loglik2<LK, DM, true>(p.net, Xt, rinv, c, t, j, x, x0, b0, b1, lane, ll_new,
-                                               ll_old, p.flags, 0, 1, -1, &lo_n, &lo_o);
+                    node_loglik2<LK, DM, true, (MAXT == 320 && MINB == 2)>(p.net, Xt, rinv, c, t, j, x, x0, b0,
+                                                                          b1, lane, ll_new, ll_old, p.flags, 0,
+                                                                          1, -1, &lo_n, &lo_o);
                 else
                     node_loglik2<LK, DM>(p.net, Xt, rinv, c, t, j, x, x0, b0, b1, lane, ll_new, ll_old,
                                          p.flags);

@@ -533,3 +533,32 @@ def test_native_radii_sampler_targets_the_flat_dirichlet_prior():
         want = 1 - (1 - x) ** (n - 1)
         got = (r < x).mean(axis=0)
         assert np.all(np.abs(got - want) < 5 * np.sqrt(want * (1 - want) / C_) + 0.01), (x, got, want)
+
+
+def test_long_row_many_chains_build_vs_oracle():
+    """More chains than SMs with ~100 KB of positions each (cfg-4 shape): the (320, 2) instantiation
+    of k_sweep with its unmasked interior trips.  Recorded draws, three of the 150 chains replayed by
+    the oracle: identical decisions and positions."""
+    L = _F()
+    T, n, d, C_ = 10, 500, 2, 150
+    rng, X, Y = _synthetic(T, n, d, False, seed=41, density=0.05)
+    e = _engine(T=T, n=n, d=d, n_chains=C_, tune=2, tune_interval=1)
+    e.set_network(Y)
+    Xc = X[None] + 0.05 * rng.randn(C_, T, n, d)
+    e.set(L.F_X, Xc)
+    e.set(L.F_INTERCEPT, np.tile([[0.7, 0.0]], (C_, 1)))
+    e.set_hyper(tau_sq=2.0, sigma_sq=0.1)
+    e.set_tuner(0.03)
+    check = (0, 77, 149)
+    Xo = {c: Xc[c].copy() for c in check}
+    tun = {c: O.TunerState((T, n), 0.03, tune=2, tune_interval=1) for c in check}
+    for s in range(2):
+        eps = rng.randn(C_, T, n, d)
+        logu = np.log(rng.rand(C_, T, n))
+        acc, _ = e.sweep_latent(eps, logu, want_stats=True)
+        got = e.get(L.F_X)
+        for c in check:
+            out = O.sweep_latent(Xo[c], np.array([0.7]), tun[c], eps[c], logu[c], Y=Y, tau_sq=2.0, sigma_sq=0.1)
+            assert np.array_equal(acc[c], out["accepted"]), (s, c)
+            assert np.array_equal(got[c], Xo[c])
+    assert 0.05 < acc.mean() < 0.95
