@@ -220,7 +220,9 @@ typedef struct {
  * the log-posterior) are gathered into a device ring and streamed to the host on a copy stream
  * while the following sweeps run.  dst[f] (f < DLSM_F_COUNT_) receives field f as
  * (n_sweeps / thin, C or 1, <field shape per chain>), logp_dst (n_sweeps / thin, C); pageable or
- * pinned (dlsm_host_alloc) memory, valid until the call returns. */
+ * pinned (dlsm_host_alloc) memory, valid until the call returns.  Position records of >= 1 MB going
+ * to pinned memory skip the ring: they are copied from the live state right after the centring, on
+ * their own stream, while the rest of the sweep still runs. */
 int dlsm_run_traced(dlsm_handle *h, int32_t n_sweeps, uint32_t flags, const dlsm_trace_spec *spec,
                     void *const *dst, double *logp_dst);
 /* co-clustering counts accumulated on the device by dlsm_run_traced (cooc_mode): out (T,n,n) u32 (may
