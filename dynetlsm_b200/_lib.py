@@ -81,7 +81,14 @@ EXPORTS = [
     "dlsm_sample_labels", "dlsm_set_hdp_prior", "dlsm_hdp_update", "dlsm_run_sweeps", "dlsm_loglik_partial", "dlsm_loglik_full",
     "dlsm_gaussian_likelihood", "dlsm_debug_set_counts", "dlsm_debug_draws", "dlsm_enable_timing", "dlsm_get_counters",
     "dlsm_resample_controls", "dlsm_get_controls", "dlsm_edge_probas", "dlsm_cooccurrence", "dlsm_logp", "dlsm_set_procrustes_ref", "dlsm_procrustes", "dlsm_run_traced", "dlsm_host_alloc", "dlsm_host_free",
+    "dlsm_set_option",
 ]
+
+# dlsm_option / dlsm_sweep_mode / dlsm_ffbs_kernel (include/dlsm.h)
+(OPT_SWEEP_MODE, OPT_FFBS_KERNEL, OPT_FFBS_SMEM_STAGE, OPT_FFBS_CTAS_PER_SM, OPT_NO_GATHER_PACK,
+ OPT_NO_TRACKED_LOGLIK, OPT_CENTER_EXACT, OPT_HDP_SEGMENTED, OPT_NO_EARLY_X, OPT_TRACE_CHUNK_BYTES) = range(10)
+SWEEP_AUTO, SWEEP_CHAIN, SWEEP_CHAIN_DENSE, SWEEP_SLICE, SWEEP_SLICE_PLAIN = range(5)
+FFBS_AUTO, FFBS_THREAD, FFBS_WARP = range(3)
 
 F_X, F_INTERCEPT, F_RADII, F_Z, F_MU, F_SIGMA, F_LAMBDA, F_WEIGHTS = range(8)
 F_X_STEP, F_X_NACC, F_X_NSTEPS, F_X_UNTIL = 8, 9, 10, 11
@@ -111,6 +118,7 @@ def load():
     L.dlsm_destroy.restype = None
     L.dlsm_set_stream.argtypes = [vp, vp]
     L.dlsm_synchronize.argtypes = [vp]
+    L.dlsm_set_option.argtypes = [vp, C.c_int, C.c_int64]
     L.dlsm_set_network_dense.argtypes = [vp, dp]
     L.dlsm_set_edge_lists.argtypes = [vp, ip, ip, C.c_int32, ip, C.c_int32]
     L.dlsm_set_controls.argtypes = [vp, ip, ip, C.c_int32, C.c_int32]
@@ -272,6 +280,10 @@ class Engine(object):
                 raise ValueError("out must be C-contiguous %s of shape %s" % (dt.__name__, self.shape_of(f)))
         self._ck(self.L.dlsm_get_state(self.h, f, a.ctypes.data_as(C.c_void_p), a.nbytes))
         return a
+
+    def set_option(self, option, value):
+        """Typed developer option (dlsm_set_option): which kernel variant serves a step."""
+        self._ck(self.L.dlsm_set_option(self.h, int(option), int(value)))
 
     def set_stream(self, cuda_stream):
         self._ck(self.L.dlsm_set_stream(self.h, C.c_void_p(cuda_stream)))

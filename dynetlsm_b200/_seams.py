@@ -9,10 +9,21 @@ _CACHE = {}
 _MAX = 4
 
 
+def clear_cache():
+    """Drop the cached engines (device memory, adjacency bits) explicitly."""
+    for e, _ in _CACHE.values():
+        e.close()
+    _CACHE.clear()
+
+
 def engine_for(Y, X, is_directed, K=0, cc=None, tune=None, tune_interval=100,
                intercept_tune_interval=(100, 100), radii_tune=None, radii_tune_interval=100):
     T, n, d = X.shape
-    key = (id(Y), None if Y is None else Y.shape, T, n, d, bool(is_directed), int(K), id(cc),
+    # content fingerprint: a Y mutated in place between calls (imputed dyads) must not reuse the
+    # stale packed adjacency already on the device
+    finger = None if Y is None else float(np.dot(np.asarray(Y, dtype=np.float64).ravel()[::7], 1.0 + np.arange(
+        np.asarray(Y).size)[::7] % 1021))
+    key = (id(Y), finger, None if Y is None else Y.shape, T, n, d, bool(is_directed), int(K), id(cc),
            tune, tune_interval, tuple(intercept_tune_interval), radii_tune, radii_tune_interval)
     hit = _CACHE.get(key)
     if hit is not None and (Y is None or hit[1] is Y):
@@ -29,7 +40,7 @@ def engine_for(Y, X, is_directed, K=0, cc=None, tune=None, tune_interval=100,
         else:
             e.set_edge_lists(cc.degrees_, cc.in_edges_, cc.out_edges_)
         if len(_CACHE) >= _MAX:
-            _CACHE.pop(next(iter(_CACHE)))
+            _CACHE.pop(next(iter(_CACHE)))[0].close()
         _CACHE[key] = (e, Y)
     if cc is not None:
         e.set_controls(cc.control_nodes_in_, cc.control_nodes_out_)

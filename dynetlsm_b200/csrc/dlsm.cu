@@ -60,6 +60,8 @@ struct dlsm_handle {
     int sm_count = 148;
     bool dense_build = false;
     bool no_pipeline = false;       // DLSM_SWEEP_MODE=slice-plain: the unpipelined slice kernel
+    // developer options (dlsm_set_option; environment defaults are read ONCE, in dlsm_create)
+    int64_t opt[DLSM_OPT_COUNT_] = {0};
     // rng
     uint64_t seed = 0, chain_offset = 0;
     uint32_t sweep_idx[5] = {0, 0, 0, 0, 0};
@@ -224,6 +226,40 @@ void end_phase(dlsm_handle *h)
     if (!h->timing) return;
     cudaEventRecord(h->events.back().b, h->stream);
     if (h->events.size() > 2048) flush_events(h);
+}
+
+// Developer / test overrides.  Every one is a typed option of the handle (dlsm_set_option); the
+// environment only supplies DEFAULTS, read once here -- nothing on the per-sweep path calls getenv.
+void apply_sweep_mode(dlsm_handle *h)
+{
+    const int64_t m = h->opt[DLSM_OPT_SWEEP_MODE];
+    h->sweep_mode = (m == DLSM_SWEEP_CHAIN || m == DLSM_SWEEP_CHAIN_DENSE) ? 1
+                    : ((m == DLSM_SWEEP_SLICE || m == DLSM_SWEEP_SLICE_PLAIN) ? 2 : 0);
+    h->dense_build = m == DLSM_SWEEP_CHAIN_DENSE; // the many-chains register budget, whatever C is
+    h->no_pipeline = m == DLSM_SWEEP_SLICE_PLAIN;
+}
+
+void read_env_options(dlsm_handle *h)
+{
+    auto on = [](const char *name) { return getenv(name) != nullptr; };
+    h->timeline_on = on("DLSM_TIMELINE");
+    if (const char *m = getenv("DLSM_SWEEP_MODE")) {
+        h->opt[DLSM_OPT_SWEEP_MODE] = !strcmp(m, "chain") ? DLSM_SWEEP_CHAIN
+                                      : !strcmp(m, "chain-dense") ? DLSM_SWEEP_CHAIN_DENSE
+                                      : !strcmp(m, "slice") ? DLSM_SWEEP_SLICE
+                                      : !strcmp(m, "slice-plain") ? DLSM_SWEEP_SLICE_PLAIN : DLSM_SWEEP_AUTO;
+    }
+    if (const char *m = getenv("DLSM_FFBS"))
+        h->opt[DLSM_OPT_FFBS_KERNEL] = !strcmp(m, "warp") ? DLSM_FFBS_WARP : DLSM_FFBS_THREAD;
+    h->opt[DLSM_OPT_FFBS_SMEM_STAGE] = on("DLSM_FFBS_SMEM");
+    if (const char *m = getenv("DLSM_FFBS_PER_SM")) h->opt[DLSM_OPT_FFBS_CTAS_PER_SM] = atoll(m);
+    h->opt[DLSM_OPT_NO_GATHER_PACK] = on("DLSM_NO_GATHER_PACK");
+    h->opt[DLSM_OPT_NO_TRACKED_LOGLIK] = on("DLSM_NO_LLCUR");
+    h->opt[DLSM_OPT_CENTER_EXACT] = on("DLSM_CENTER_EXACT");
+    h->opt[DLSM_OPT_HDP_SEGMENTED] = on("DLSM_HDP_SEGMENTED");
+    h->opt[DLSM_OPT_NO_EARLY_X] = on("DLSM_NO_EARLY_X");
+    if (const char *m = getenv("DLSM_TRACE_CHUNK_BYTES")) h->opt[DLSM_OPT_TRACE_CHUNK_BYTES] = atoll(m);
+    apply_sweep_mode(h);
 }
 
 NetView net_view(const dlsm_handle *h)
@@ -408,7 +444,7 @@ bool use_slice_kernel(const dlsm_handle *h)
     if (h->sweep_mode == 1) return false;
     if (h->sweep_mode == 2) return true;
     const size_t warps_chain_mode = (size_t)h->cfg.n_chains * (h->cfg.T < 16 ? h->cfg.T : 16);
-    return h->cfg.n >= 256 && warps_chain_mode < 148 * 16;
+    return h->cfg.n >= 256 && warps_chain_mode < (size_t)h->sm_count * 16;
 }
 
 int launch_sweep(dlsm_handle *h, const SweepParams &p)
@@ -454,7 +490,7 @@ int launch_full(dlsm_handle *h, const double *rinv0, const double *rinv1, int nv
     p.rinv0 = rinv0; p.rinv1 = rinv1;
     p.partial = h->d_partial;
     p.flags = h->d_flags;
-    if (h->lk == kCaseControl && h->cfg.d == 2 && nv == 1 && !getenv("DLSM_NO_GATHER_PACK")) {
+    if (h->lk == kCaseControl && h->cfg.d == 2 && nv == 1 && !h->opt[DLSM_OPT_NO_GATHER_PACK]) {
         // positions and reciprocal radii of this evaluation as 32-byte records: one 256-bit load
         // per gathered node instead of two loads (the kernel is bound by L1 gather wavefronts)
         const size_t cells = (size_t)h->cfg.n_chains * h->cfg.T * h->cfg.n;
@@ -579,14 +615,7 @@ int dlsm_create(const dlsm_config *cfg, dlsm_handle **out)
     h->lk = cfg->likelihood == DLSM_LIK_CASE_CONTROL ? kCaseControl
                                                       : (cfg->is_directed ? kDirected : kUndirected);
     h->W = ((cfg->n + 31) / 32 + 3) / 4 * 4;
-    h->timeline_on = getenv("DLSM_TIMELINE") != nullptr;
-    if (const char *m = getenv("DLSM_SWEEP_MODE")) // chain | slice: override the heuristic (tests, tuning)
-    {
-        h->sweep_mode = (!strcmp(m, "chain") || !strcmp(m, "chain-dense")) ? 1
-                        : ((!strcmp(m, "slice") || !strcmp(m, "slice-plain")) ? 2 : 0);
-        h->dense_build = !strcmp(m, "chain-dense"); // the many-chains register budget, whatever C is
-        h->no_pipeline = !strcmp(m, "slice-plain");
-    }
+    read_env_options(h);
     auto fail = [&](const char *what, cudaError_t e) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
         dlsm_destroy(h);
@@ -669,6 +698,20 @@ void dlsm_destroy(dlsm_handle *h)
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
+}
+
+int dlsm_set_option(dlsm_handle *h, int option, int64_t value)
+{
+    if (!h) return DLSM_ERR_INVALID;
+    if (option < 0 || option >= DLSM_OPT_COUNT_) FAIL(h, DLSM_ERR_INVALID, "unknown option %d", option);
+    if (option == DLSM_OPT_SWEEP_MODE && (value < DLSM_SWEEP_AUTO || value > DLSM_SWEEP_SLICE_PLAIN))
+        FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_SWEEP_MODE takes a dlsm_sweep_mode value");
+    if (option == DLSM_OPT_FFBS_KERNEL && (value < DLSM_FFBS_AUTO || value > DLSM_FFBS_WARP))
+        FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_FFBS_KERNEL takes a dlsm_ffbs_kernel value");
+    if (value < 0) FAIL(h, DLSM_ERR_INVALID, "option values are non-negative");
+    h->opt[option] = value;
+    if (option == DLSM_OPT_SWEEP_MODE) apply_sweep_mode(h);
+    return DLSM_OK;
 }
 
 int dlsm_set_stream(dlsm_handle *h, void *s)
@@ -1082,8 +1125,9 @@ static int labels_async(dlsm_handle *h, const double *d_U, double *lik_out, int 
     const size_t need = ctas * per_thread * 64;
     // K <= 16: the register-resident kernel (persistent grid, stage indexed by CTA slot)
     const size_t tables = ((size_t)c.T * c.K * c.K + (size_t)c.K * (c.d + 2)) * sizeof(double);
-    const char *ffbs_env = getenv("DLSM_FFBS"); // "thread" / "warp": force an older mapping (tests)
-    if (c.K <= 16 && tables <= 64 * 1024 && !ffbs_env && !getenv("DLSM_FFBS_SMEM")) {
+    const int64_t ffbs_kernel = h->opt[DLSM_OPT_FFBS_KERNEL]; // thread / warp: force an older mapping (tests)
+    const bool ffbs_warp = ffbs_kernel == DLSM_FFBS_WARP, ffbs_smem = h->opt[DLSM_OPT_FFBS_SMEM_STAGE] != 0;
+    if (c.K <= 16 && tables <= 64 * 1024 && ffbs_kernel == DLSM_FFBS_AUTO && !ffbs_smem) {
         const int KC = (c.K + 3) / 4 * 4;
         const int tiles = (c.n + 63) / 64;
         const long items = (long)tiles * c.n_chains;
@@ -1092,10 +1136,9 @@ static int labels_async(dlsm_handle *h, const double *d_U, double *lik_out, int 
             int per_sm = 0;
             CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 64, tables));
             if (per_sm < 1) per_sm = 1;
-            if (const char *cap = getenv("DLSM_FFBS_PER_SM")) per_sm = atoi(cap) > 0 && atoi(cap) < per_sm ? atoi(cap) : per_sm;
-            int sms = 148;
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
-            long grid = (long)sms * per_sm;
+            const int64_t cap = h->opt[DLSM_OPT_FFBS_CTAS_PER_SM];
+            if (cap > 0 && cap < per_sm) per_sm = (int)cap;
+            long grid = (long)h->sm_count * per_sm;
             if (grid > items) grid = items;
             const size_t stage = (size_t)grid * c.T * c.K * 64 * sizeof(double);
             if (stage > h->ffbs_stage_bytes) {
@@ -1114,7 +1157,7 @@ static int labels_async(dlsm_handle *h, const double *d_U, double *lik_out, int 
             rc = KC == 4 ? launch(k_ffbs_r<4, 0>) : KC == 8 ? launch(k_ffbs_r<8, 0>)
                  : KC == 12 ? launch(k_ffbs_r<12, 0>) : launch(k_ffbs_r<16, 0>);
         }
-    } else if (!(ffbs_env && !strcmp(ffbs_env, "warp")) && !getenv("DLSM_FFBS_SMEM") && per_thread * 64 > 16 * 1024 && need <= ((size_t)4 << 30) &&
+    } else if (!ffbs_warp && !ffbs_smem && per_thread * 64 > 16 * 1024 && need <= ((size_t)4 << 30) &&
         extra <= kMaxSmem) {
         if (need > h->ffbs_stage_bytes) {
             cudaFree(h->d_ffbs_stage);
@@ -1125,11 +1168,11 @@ static int labels_async(dlsm_handle *h, const double *d_U, double *lik_out, int 
         p.gstage = h->d_ffbs_stage;
         CU(h, cudaFuncSetAttribute(k_ffbs_t<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)extra));
         rc = launch_simple(h, k_ffbs_t<64>, dim3((c.n + 63) / 64, c.n_chains), dim3(64), extra, p);
-    } else if (!(ffbs_env && !strcmp(ffbs_env, "warp")) && per_thread * 64 + extra <= kMaxSmem / 2) {
+    } else if (!ffbs_warp && per_thread * 64 + extra <= kMaxSmem / 2) {
         const size_t smem = per_thread * 64 + extra;
         CU(h, cudaFuncSetAttribute(k_ffbs_t<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rc = launch_simple(h, k_ffbs_t<64>, dim3((c.n + 63) / 64, c.n_chains), dim3(64), smem, p);
-    } else if (!(ffbs_env && !strcmp(ffbs_env, "warp")) && per_thread * 32 + extra <= kMaxSmem) {
+    } else if (!ffbs_warp && per_thread * 32 + extra <= kMaxSmem) {
         const size_t smem = per_thread * 32 + extra;
         CU(h, cudaFuncSetAttribute(k_ffbs_t<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rc = launch_simple(h, k_ffbs_t<32>, dim3((c.n + 31) / 32, c.n_chains), dim3(32), smem, p);
@@ -1181,7 +1224,7 @@ static int hdp_update_async(dlsm_handle *h, int part)
     p.pr = h->hdp_prior;
     p.seed = h->seed; p.sweep = h->sweep_idx[4]; p.chain_offset = (uint32_t)h->chain_offset;
     const size_t smem = hdp_smem_bytes(c.T, c.K, c.d);
-    p.bin_rows = getenv("DLSM_HDP_SEGMENTED") ? 0 : hdp_bin_rows(c.K, c.d);
+    p.bin_rows = h->opt[DLSM_OPT_HDP_SEGMENTED] ? 0 : hdp_bin_rows(c.K, c.d);
     if (smem > kMaxSmem) FAIL(h, DLSM_ERR_UNSUPPORTED, "T*K*K too large for the HDP update kernel");
     begin_phase(h, 1);
     int rc;
@@ -1235,7 +1278,7 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
     p.fuse_center = fuse ? 1 : 0;
     // the chain kernel also hands over the full-network log-likelihood of the state it leaves
     // behind, so the intercept / radii MH below evaluates only its proposals
-    bool use_cur = !use_slice_kernel(h) && h->lk != kCaseControl && !getenv("DLSM_NO_LLCUR");
+    bool use_cur = !use_slice_kernel(h) && h->lk != kCaseControl && !h->opt[DLSM_OPT_NO_TRACKED_LOGLIK];
     p.ll_cur = use_cur ? F<double>(h, DLSM_F_LOGLIK) : nullptr;
     if (h->x_copy_pending) { // the previous record of X is still on its way to the host
         CU(h, cudaStreamWaitEvent(h->stream, h->ev_x_copied, 0));
@@ -1246,7 +1289,7 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
     tl_end(h);
     h->sweep_idx[kRngLatent] += 1;
     if (procrustes && (rc = procrustes_async(h)) != DLSM_OK) return rc; // lsm.py:495-498
-    if (!(flags & 1u) && !fuse && (rc = center_async(h, getenv("DLSM_CENTER_EXACT") != nullptr)) != DLSM_OK) return rc;
+    if (!(flags & 1u) && !fuse && (rc = center_async(h, h->opt[DLSM_OPT_CENTER_EXACT] != 0)) != DLSM_OK) return rc;
     if (h->early_x_dst) { // X is final for this sweep: stream its record out now
         CU(h, cudaEventRecord(h->ev_x_ready, h->stream));
         CU(h, cudaStreamWaitEvent(h->x_stream, h->ev_x_ready, 0));
@@ -1292,7 +1335,7 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
     // kernels) one evaluation of the current state serves all the MH steps of this sweep: 1 + 3
     // variant evaluations instead of 3 x 2.
     const bool any_mh = !(flags & 2u) || (h->cfg.is_directed && !(flags & 4u));
-    if (!use_cur && any_mh && !getenv("DLSM_NO_LLCUR")) {
+    if (!use_cur && any_mh && !h->opt[DLSM_OPT_NO_TRACKED_LOGLIK]) {
         const int C = h->cfg.n_chains;
         tl_begin(h, "loglik(current)");
         rc = launch_simple(h, k_bvar_current, dim3((C + 127) / 128), dim3(128), 0, C,
@@ -1515,7 +1558,7 @@ static int prepare_trace(dlsm_handle *h, const dlsm_trace_spec *sp, int n_record
     CU(h, cudaMemGetInfo(&free_b, &total_b));
     size_t budget = (size_t)512 << 20; // per chunk
     if (budget > free_b / 8) budget = free_b / 8;
-    if (const char *e = getenv("DLSM_TRACE_CHUNK_BYTES")) budget = (size_t)atoll(e);
+    if (h->opt[DLSM_OPT_TRACE_CHUNK_BYTES] > 0) budget = (size_t)h->opt[DLSM_OPT_TRACE_CHUNK_BYTES];
     long R = (long)(budget / per_record);
     if (R < 1) R = 1;
     if (R > 1024) R = 1024;
@@ -1559,10 +1602,34 @@ static int drain_chunk(dlsm_handle *h, int which, size_t first, int count, void 
     return DLSM_OK;
 }
 
+static int run_traced_body(dlsm_handle *h, int32_t n_sweeps, uint32_t flags, const dlsm_trace_spec *sp,
+                           void *const *dst, double *logp_dst);
+
 int dlsm_run_traced(dlsm_handle *h, int32_t n_sweeps, uint32_t flags, const dlsm_trace_spec *sp,
                     void *const *dst, double *logp_dst)
 {
     if (!h || !sp || n_sweeps < 0) return DLSM_ERR_INVALID;
+    const int rc = run_traced_body(h, n_sweeps, flags, sp, dst, logp_dst);
+    if (rc != DLSM_OK) {
+        // common error exit: no copy into the caller's (possibly pinned, soon to be freed) buffers
+        // may still be in flight when the error is reported, and the early-copy state is cleared
+        const std::string keep = h->err;
+        if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+        if (h->x_stream) cudaStreamSynchronize(h->x_stream);
+        cudaStreamSynchronize(h->side_stream);
+        cudaStreamSynchronize(h->stream);
+        cudaGetLastError();
+        h->early_x_active = false;
+        h->early_x_dst = nullptr;
+        h->x_copy_pending = false;
+        h->err = keep;
+    }
+    return rc;
+}
+
+static int run_traced_body(dlsm_handle *h, int32_t n_sweeps, uint32_t flags, const dlsm_trace_spec *sp,
+                           void *const *dst, double *logp_dst)
+{
     if (sp->thin < 1) FAIL(h, DLSM_ERR_INVALID, "thin must be >= 1");
     if (sp->fields_all & sp->fields_first) FAIL(h, DLSM_ERR_INVALID, "a field is traced either for all chains or for the first");
     CU(h, cudaSetDevice(h->cfg.device));
@@ -1577,7 +1644,7 @@ int dlsm_run_traced(dlsm_handle *h, int32_t n_sweeps, uint32_t flags, const dlsm
     // pageable destination would block the host inside the sweep, so it goes through the ring.
     bool early_x = false;
     if (n_records > 0 && !(flags & 1u) && ((sp->fields_all >> DLSM_F_X) & 1u) &&
-        h->field_bytes[DLSM_F_X] >= ((size_t)1 << 20) && !getenv("DLSM_NO_EARLY_X")) {
+        h->field_bytes[DLSM_F_X] >= ((size_t)1 << 20) && !h->opt[DLSM_OPT_NO_EARLY_X]) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, dst[DLSM_F_X]) == cudaSuccess && at.type == cudaMemoryTypeHost) early_x = true;
         cudaGetLastError();

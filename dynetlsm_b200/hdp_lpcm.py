@@ -43,6 +43,12 @@ class DynamicNetworkHDPLPCM(_FittedNetworkMixin):
             if k != "self":
                 setattr(self, k, v)
 
+    @property
+    def n_burn_(self):
+        # hdp_lpcm.py:458-465: burn-in counted in STORED samples when the trace is thinned
+        nb = (self.burn or 0) + (self.tune or 0)
+        return int(np.ceil(nb / self.thin)) if self.thin else nb
+
     def fit(self, Y):
         replay = self.sampler == "replay"
         if self.sampler not in ("device", "replay"):
@@ -221,7 +227,7 @@ class DynamicNetworkHDPLPCM(_FittedNetworkMixin):
                     cc.n_iter += 1
                     quiet = S if cc.n_resample is None else (cc.n_resample - cc.n_iter % cc.n_resample) % cc.n_resample
                     stop = min(stop, it + 1 + quiet)
-                nb_ = min(self.n_burn_, S - 1)
+                nb_ = min((self.burn or 0) + (self.tune or 0), S - 1)
                 tr = e.run_traced(stop - it, fields_all=every, fields_first=first, pinned=True, out=tr,
                                   cooc=1, cooc_from=max(0, nb_ - it))   # co-clustering counts of chain 0
                 if cc is not None:
@@ -269,6 +275,8 @@ class DynamicNetworkHDPLPCM(_FittedNetworkMixin):
         self.radiis_ = rads
         self._post_process()
         self.sampler_counters_ = e.counters()
+        e.close()            # chain state, trace rings and pinned buffers are not kept after fit
+        self._engine = None
         return self
 
     # ---- point estimate, alignment, posterior summaries -------------------------------------

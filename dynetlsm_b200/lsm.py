@@ -135,6 +135,11 @@ class _FittedNetworkMixin(object):
         expit(intercept - dist); evaluated by dlsm_edge_probas on the device."""
         if not hasattr(self, "X_"):
             raise ValueError("Model not fit.")
+        # cached per fitted point estimate: auc_ and repeated accesses do not rebuild an engine
+        key = (id(self.X_), float(np.sum(self.X_)), tuple(np.ravel(self.intercept_)))
+        hit = getattr(self, "_probas_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
         T, n, d = self.X_.shape
         e = L.Engine(T=T, n=n, d=d, n_chains=1, is_directed=self.is_directed, device=self.device)
         try:
@@ -144,9 +149,11 @@ class _FittedNetworkMixin(object):
             e.set(L.F_INTERCEPT, ic)
             if self.is_directed:
                 e.set(L.F_RADII, np.asarray(self.radii_)[None])
-            return e.edge_probas(0)
+            out = e.edge_probas(0)
         finally:
             e.close()
+        self._probas_cache = (key, out)
+        return out
 
     @property
     def auc_(self):
@@ -387,4 +394,6 @@ class DynamicNetworkLSM(_FittedNetworkMixin):
         self.chains_ = dict(Xs=Xs, intercepts=ics, logps=logps, radiis=rads,
                             map_iteration=[b["it"] for b in best])
         self.sampler_counters_ = e.counters()
+        e.close()            # chain state, trace rings and pinned buffers are not kept after fit
+        self._engine = None
         return self

@@ -128,6 +128,32 @@ const char *dlsm_last_error(const dlsm_handle *h); /* h may be NULL: last creati
 int dlsm_set_stream(dlsm_handle *h, void *cuda_stream);
 int dlsm_synchronize(dlsm_handle *h);
 
+/* Developer / test options: which kernel variant serves a step.  None changes results beyond the
+ * documented rounding (the parity tests run every variant).  Each option also has an environment
+ * variable that only supplies its DEFAULT, read once by dlsm_create (never on the sweep path):
+ * DLSM_SWEEP_MODE=chain|chain-dense|slice|slice-plain, DLSM_FFBS=thread|warp, DLSM_FFBS_SMEM,
+ * DLSM_FFBS_PER_SM=<n>, DLSM_NO_GATHER_PACK, DLSM_NO_LLCUR, DLSM_CENTER_EXACT, DLSM_HDP_SEGMENTED,
+ * DLSM_NO_EARLY_X, DLSM_TRACE_CHUNK_BYTES=<bytes>. */
+typedef enum {
+    DLSM_OPT_SWEEP_MODE = 0,        /* dlsm_sweep_mode: which latent-sweep kernel (default: heuristic) */
+    DLSM_OPT_FFBS_KERNEL = 1,       /* dlsm_ffbs_kernel: label kernel mapping */
+    DLSM_OPT_FFBS_SMEM_STAGE = 2,   /* 1: thread-per-node label kernel keeps its stage in shared memory */
+    DLSM_OPT_FFBS_CTAS_PER_SM = 3,  /* cap of the persistent label grid (0 = occupancy) */
+    DLSM_OPT_NO_GATHER_PACK = 4,    /* 1: case-control full-network kernel gathers X and 1/r separately */
+    DLSM_OPT_NO_TRACKED_LOGLIK = 5, /* 1: intercept / radii MH evaluate current AND proposal every time */
+    DLSM_OPT_CENTER_EXACT = 6,      /* 1: long-chain centring inside the device loop uses numpy's serial order */
+    DLSM_OPT_HDP_SEGMENTED = 7,     /* 1: segmented-butterfly sufficient statistics in the HDP update */
+    DLSM_OPT_NO_EARLY_X = 8,        /* 1: position records always go through the trace ring */
+    DLSM_OPT_TRACE_CHUNK_BYTES = 9, /* device bytes of one trace-ring chunk (0 = 512 MB or free/8) */
+    DLSM_OPT_COUNT_
+} dlsm_option;
+typedef enum {
+    DLSM_SWEEP_AUTO = 0, DLSM_SWEEP_CHAIN = 1, DLSM_SWEEP_CHAIN_DENSE = 2, DLSM_SWEEP_SLICE = 3,
+    DLSM_SWEEP_SLICE_PLAIN = 4
+} dlsm_sweep_mode;
+typedef enum { DLSM_FFBS_AUTO = 0, DLSM_FFBS_THREAD = 1, DLSM_FFBS_WARP = 2 } dlsm_ffbs_kernel;
+int dlsm_set_option(dlsm_handle *h, int option, int64_t value);
+
 /* ---- network -------------------------------------------------------------------------- */
 /* Y (T,n,n) fp64 0/1 as passed to DynamicNetworkLSM.fit (lsm.py:319-343).  Bit-packed on the
  * device: row-major always, transposed too when is_directed. */

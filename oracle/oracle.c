@@ -11,7 +11,7 @@
  * this restatement is pinned against outputs of the reference itself, run in the build container
  * from /root/reference with fixed seeds (oracle/make_golden.py -> tests/golden/ *.npz; checked by
  * tests/test_oracle_golden.py) and, where oracle/_ref holds the compiled reference Cython kernels,
- * directly against those (tests/test_oracle_vs_ref.py).
+ * directly against those (tests/test_oracle_golden.py, tests/test_oracle_golden_big.py, tests/test_ref_driver.py).
  *
  * Every function cites the reference file:line it follows (paths relative to the reference root).
  * Arithmetic is IEEE fp64 with NO fused multiply-add contraction (build with -ffp-contract=off):

@@ -64,11 +64,8 @@ def test_device_hdp_update_matches_host_in_distribution():
     e.set_hdp_prior(hp0.a, hp0.a0, hp0.b0, hp0.c0, hp0.d0, hp0.lambda_prior, hp0.lambda_variance_prior,
                     hp0.gamma_prior_shape, hp0.gamma_prior_rate, hp0.alpha_init_shape, hp0.alpha_init_rate,
                     hp0.alpha_kappa_shape, hp0.alpha_kappa_rate, True, True)
-    # the label counts normally come from the label kernel: put them there by sampling labels with
-    # degenerate weights?  simpler: the probe path -- the fields are device buffers the kernel reads
-    e.L.dlsm_set_state  # (counts are read-only through the API; fill them through a label draw)
-    # run the label kernel with weights/emissions that reproduce z exactly: w rows = one-hot of z is
-    # not expressible per node, so instead overwrite via the private test hook below
+    # the label counts normally come from the label kernel; the test probe dlsm_debug_set_counts
+    # writes the counts that belong to z
     _force_counts(e, L, cnt, nk)
     e.set_rng(7)
     e.hdp_update()
