@@ -351,7 +351,7 @@ def measure(ctx, name, steps, warmup, chains_override=0, e2e=True, cpu=True, par
                    "api": "Engine.set(positions) -> Engine.run_traced(1 sweep, whole state + log-posterior to "
                           "pinned host buffers) over the dlsm C-ABI"}
         # the same state leaving the device every sweep through the streaming call fit() uses
-        ntr = 3 * nst
+        ntr = int(max(4, min(3 * nst, (1 << 30) // max(1, d2h))))   # at most ~1 GB of pinned destination
         tr = e.run_traced(ntr, fields_all=outs, pinned=True)   # allocates the pinned destination
         barrier()
         t0 = time.perf_counter()
