@@ -81,12 +81,13 @@ EXPORTS = [
     "dlsm_sample_labels", "dlsm_set_hdp_prior", "dlsm_hdp_update", "dlsm_run_sweeps", "dlsm_loglik_partial", "dlsm_loglik_full",
     "dlsm_gaussian_likelihood", "dlsm_debug_set_counts", "dlsm_debug_draws", "dlsm_enable_timing", "dlsm_get_counters",
     "dlsm_resample_controls", "dlsm_get_controls", "dlsm_edge_probas", "dlsm_cooccurrence", "dlsm_logp", "dlsm_set_procrustes_ref", "dlsm_procrustes", "dlsm_run_traced", "dlsm_host_alloc", "dlsm_host_free",
-    "dlsm_set_option",
+    "dlsm_set_option", "dlsm_debug_rowsums",
 ]
 
 # dlsm_option / dlsm_sweep_mode / dlsm_ffbs_kernel (include/dlsm.h)
 (OPT_SWEEP_MODE, OPT_FFBS_KERNEL, OPT_FFBS_SMEM_STAGE, OPT_FFBS_CTAS_PER_SM, OPT_NO_GATHER_PACK,
- OPT_NO_TRACKED_LOGLIK, OPT_CENTER_EXACT, OPT_HDP_SEGMENTED, OPT_NO_EARLY_X, OPT_TRACE_CHUNK_BYTES) = range(10)
+ OPT_NO_TRACKED_LOGLIK, OPT_CENTER_EXACT, OPT_HDP_SEGMENTED, OPT_NO_EARLY_X, OPT_TRACE_CHUNK_BYTES,
+ OPT_NO_ROWSUM_CACHE) = range(11)
 SWEEP_AUTO, SWEEP_CHAIN, SWEEP_CHAIN_DENSE, SWEEP_SLICE, SWEEP_SLICE_PLAIN = range(5)
 FFBS_AUTO, FFBS_THREAD, FFBS_WARP = range(3)
 
@@ -139,6 +140,7 @@ def load():
     L.dlsm_gaussian_likelihood.argtypes = [vp, dp]
     L.dlsm_debug_set_counts.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.dlsm_debug_draws.argtypes = [vp, dp, dp]
+    L.dlsm_debug_rowsums.argtypes = [vp, dp]
     L.dlsm_enable_timing.argtypes = [vp, C.c_int]
     L.dlsm_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.dlsm_logp.argtypes = [vp, dp]
@@ -487,6 +489,12 @@ class Engine(object):
     def gaussian_likelihood(self):
         out = np.empty((self.C, self.n, self.T, self.K))
         self._ck(self.L.dlsm_gaussian_likelihood(self.h, _dp(out)))
+        return out
+
+    def rowsums(self):
+        """The device loop's cached per-node log-likelihoods (C, T, n) (dlsm_debug_rowsums)."""
+        out = np.empty((self.C, self.T, self.n))
+        self._ck(self.L.dlsm_debug_rowsums(self.h, _dp(out)))
         return out
 
     def debug_draws(self):

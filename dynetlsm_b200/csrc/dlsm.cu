@@ -60,6 +60,12 @@ struct dlsm_handle {
     int sm_count = 148;
     bool dense_build = false;
     bool no_pipeline = false;       // DLSM_SWEEP_MODE=slice-plain: the unpipelined slice kernel
+    // row-sum cache of the exact likelihoods (see node_loglik1 / k_rows): rows[c][t][j], scratch of the
+    // proposal's pair terms, and the tile vectors k_rows leaves for k_rows_commit
+    double *d_rows = nullptr, *d_scr = nullptr, *d_rows_own = nullptr, *d_rows_part = nullptr;
+    int32_t *d_accflag = nullptr;
+    bool rows_valid = false;
+    int rows_nb = 0, rows_JS = 16, rows_G = 1, rows_ni = 0, rows_chunks = 1;
     // developer options (dlsm_set_option; environment defaults are read ONCE, in dlsm_create)
     int64_t opt[DLSM_OPT_COUNT_] = {0};
     // rng
@@ -258,6 +264,7 @@ void read_env_options(dlsm_handle *h)
     h->opt[DLSM_OPT_CENTER_EXACT] = on("DLSM_CENTER_EXACT");
     h->opt[DLSM_OPT_HDP_SEGMENTED] = on("DLSM_HDP_SEGMENTED");
     h->opt[DLSM_OPT_NO_EARLY_X] = on("DLSM_NO_EARLY_X");
+    h->opt[DLSM_OPT_NO_ROWSUM_CACHE] = on("DLSM_NO_ROWSUM");
     if (const char *m = getenv("DLSM_TRACE_CHUNK_BYTES")) h->opt[DLSM_OPT_TRACE_CHUNK_BYTES] = atoll(m);
     apply_sweep_mode(h);
 }
@@ -325,9 +332,15 @@ template <int LK, int D, bool XS, int MAXT, int MINB>
 int launch_sweep_t(dlsm_handle *h, const SweepParams &p, int warps)
 {
     const size_t smem = sweep_smem(h, XS);
-    auto kern = k_sweep<LK, D, XS, MAXT, MINB>;
-    CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<h->cfg.n_chains, warps * 32, smem, h->stream>>>(p);
+    if (LK != kCaseControl && p.rows) { // proposal-only evaluation on the row-sum cache
+        auto kern = k_sweep<LK == kCaseControl ? kDirected : LK, D, XS, MAXT, MINB, true>;
+        CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<h->cfg.n_chains, warps * 32, smem, h->stream>>>(p);
+    } else {
+        auto kern = k_sweep<LK, D, XS, MAXT, MINB>;
+        CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<h->cfg.n_chains, warps * 32, smem, h->stream>>>(p);
+    }
     CHECK_LAUNCH(h);
     return DLSM_OK;
 }
@@ -526,6 +539,95 @@ int launch_full(dlsm_handle *h, const double *rinv0, const double *rinv1, int nv
     return DLSM_OK;
 }
 
+// ---- row-sum cache ---------------------------------------------------------------------------
+// used by the device loop (dlsm_run_sweeps / dlsm_run_traced) with the exact likelihoods and the
+// chain kernel; the function-level entry points keep the two-variant evaluation
+bool rows_enabled(const dlsm_handle *h)
+{
+    return h->lk != kCaseControl && !use_slice_kernel(h) && !h->opt[DLSM_OPT_NO_ROWSUM_CACHE] &&
+           !h->opt[DLSM_OPT_NO_TRACKED_LOGLIK] &&
+           (size_t)h->cfg.n * (h->cfg.d + 1) * sizeof(double) <= kMaxSmem;
+}
+
+int ensure_rows(dlsm_handle *h)
+{
+    if (h->d_rows) return DLSM_OK;
+    const dlsm_config &c = h->cfg;
+    const size_t cells = (size_t)c.n_chains * c.T * c.n, slices = (size_t)c.n_chains * c.T;
+    h->rows_nb = (c.n + 31) / 32;
+    h->rows_G = (h->rows_nb + h->rows_JS - 1) / h->rows_JS;
+    h->rows_ni = 0;
+    for (int I = 0; I < h->rows_nb; I++) h->rows_ni += rows_runs(h->rows_nb, h->rows_JS, I);
+    h->rows_chunks = (h->rows_ni + 7) / 8;
+    const size_t nb = h->rows_nb;
+    CU(h, cudaMalloc((void **)&h->d_rows, cells * 8));
+    CU(h, cudaMalloc((void **)&h->d_scr, cells * 8));
+    CU(h, cudaMalloc((void **)&h->d_rows_own, slices * nb * h->rows_G * 32 * 8));
+    CU(h, cudaMalloc((void **)&h->d_rows_part, (slices * (nb * (nb - 1) / 2) * 32 + 32) * 8));
+    CU(h, cudaMalloc((void **)&h->d_accflag, (size_t)c.n_chains * 4));
+    const size_t need = (size_t)c.n_chains * c.T * h->rows_chunks * 2 * 8;
+    if (need > (size_t)c.n_chains * h->full_nblk * 2 * 8) { // k_rows has its own partial-sum layout
+        CU(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_partial);
+        h->d_partial = nullptr;
+        CU(h, cudaMalloc((void **)&h->d_partial, need));
+    }
+    h->rows_valid = false;
+    return DLSM_OK;
+}
+
+// full-network log-likelihood of variant 0 (bvar, rinv0) -> d_partial, its row sums -> (own, part)
+int launch_rows(dlsm_handle *h, const double *rinv0)
+{
+    const dlsm_config &c = h->cfg;
+    RowsParams p;
+    memset(&p, 0, sizeof(p));
+    p.net = net_view(h);
+    p.C = c.n_chains; p.nb = h->rows_nb; p.JS = h->rows_JS; p.G = h->rows_G; p.ni = h->rows_ni;
+    p.chunks = h->rows_chunks;
+    p.X = F<double>(h, DLSM_F_X); p.bvar = h->d_bvar; p.rinv0 = rinv0;
+    p.partial = h->d_partial; p.own = h->d_rows_own; p.part = h->d_rows_part;
+    const dim3 grid(c.T * h->rows_chunks, c.n_chains);
+    const size_t smem = (size_t)c.n * (c.d + (h->lk == kDirected ? 1 : 0)) * sizeof(double);
+#define LAUNCH_ROWS(LK, D)                                                                                \
+    do {                                                                                                  \
+        CU(h, cudaFuncSetAttribute(k_rows<LK, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_rows<LK, D><<<grid, 256, smem, h->stream>>>(p);                                                 \
+    } while (0)
+    if (h->lk == kUndirected) { if (c.d == 2) LAUNCH_ROWS(kUndirected, 2); else LAUNCH_ROWS(kUndirected, 0); }
+    else { if (c.d == 2) LAUNCH_ROWS(kDirected, 2); else LAUNCH_ROWS(kDirected, 0); }
+#undef LAUNCH_ROWS
+    CHECK_LAUNCH(h);
+    h->ctr.kernel_launches += 1;
+    return DLSM_OK;
+}
+
+int rows_nblk(const dlsm_handle *h) { return h->cfg.T * h->rows_chunks; }
+
+int commit_rows(dlsm_handle *h, const int32_t *flag)
+{
+    const dlsm_config &c = h->cfg;
+    const int warps = c.T * h->rows_nb;
+    return launch_simple(h, k_rows_commit, dim3((warps + 7) / 8, c.n_chains), dim3(256), 0, flag, c.T, c.n,
+                         h->rows_nb, h->rows_JS, h->rows_G, (const double *)h->d_rows_own,
+                         (const double *)h->d_rows_part, h->d_rows);
+}
+
+// rows <- the current state's row sums, DLSM_F_LOGLIK <- its log-likelihood
+int refresh_rows(dlsm_handle *h)
+{
+    const int C = h->cfg.n_chains;
+    int rc = launch_simple(h, k_bvar_current, dim3((C + 127) / 128), dim3(128), 0, C,
+                           (const double *)F<double>(h, DLSM_F_INTERCEPT), h->d_bvar);
+    if (rc == DLSM_OK) rc = launch_rows(h, h->rinv);
+    if (rc == DLSM_OK)
+        rc = launch_simple(h, k_sum_partials, dim3((C + 127) / 128), dim3(128), 0, C, rows_nblk(h),
+                           (const double *)h->d_partial, h->d_ll2, F<double>(h, DLSM_F_LOGLIK));
+    if (rc == DLSM_OK) rc = commit_rows(h, nullptr);
+    if (rc == DLSM_OK) h->rows_valid = true;
+    return rc;
+}
+
 int check_flags(dlsm_handle *h)
 {
     unsigned int f = 0;
@@ -681,7 +783,7 @@ void dlsm_destroy(dlsm_handle *h)
                     h->ctrl_out, h->rinv, h->d_eps, h->d_logu, h->d_ratio, h->d_out, h->d_acc,
                     h->d_partial, h->d_bvar, h->d_prop, h->d_ll2, h->d_rprop, h->d_rprop_inv,
                     h->d_small, h->d_small_i, h->d_flags, h->d_bad, h->d_progress, h->d_ticket, h->d_ffbs_stage,
-                    h->d_cc_dep};
+                    h->d_cc_dep, h->d_rows, h->d_scr, h->d_rows_own, h->d_rows_part, h->d_accflag};
     for (void *p : ptrs) cudaFree(p);
     if (h->x_stream) cudaStreamDestroy(h->x_stream);
     if (h->ev_x_ready) cudaEventDestroy(h->ev_x_ready);
@@ -710,6 +812,7 @@ int dlsm_set_option(dlsm_handle *h, int option, int64_t value)
         FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_FFBS_KERNEL takes a dlsm_ffbs_kernel value");
     if (value < 0) FAIL(h, DLSM_ERR_INVALID, "option values are non-negative");
     h->opt[option] = value;
+    h->rows_valid = false;
     if (option == DLSM_OPT_SWEEP_MODE) apply_sweep_mode(h);
     return DLSM_OK;
 }
@@ -758,6 +861,7 @@ int dlsm_set_network_dense(dlsm_handle *h, const double *Y)
     CHECK_LAUNCH(h);
     if (bad) FAIL(h, DLSM_ERR_NONBINARY, "adjacency must be 0/1 (weighted or missing (-1) dyads are not supported on the device path)");
     h->have_net = true;
+    h->rows_valid = false;
     return DLSM_OK;
 }
 
@@ -860,6 +964,7 @@ int dlsm_set_state(dlsm_handle *h, int field, const void *host, size_t bytes)
     CU(h, cudaSetDevice(h->cfg.device));
     int rc = upload(h, h->field[field], host, bytes);
     if (rc != DLSM_OK) return rc;
+    if (field == DLSM_F_X || field == DLSM_F_INTERCEPT || field == DLSM_F_RADII) h->rows_valid = false;
     if (field == DLSM_F_RADII) rc = update_rinv(h);
     if (rc != DLSM_OK) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
@@ -911,6 +1016,7 @@ int dlsm_sweep_latent(dlsm_handle *h, const double *eps, const double *logu, int
     if (rc != DLSM_OK) return rc;
     const size_t N = (size_t)h->cfg.n_chains * h->cfg.T * h->cfg.n;
     SweepParams p = sweep_params(h);
+    h->rows_valid = false; // the function-level sweep evaluates both variants and keeps no row sums
     if (eps || accepted || ratio) {
         rc = ensure_replay_buffers(h);
         if (rc != DLSM_OK) return rc;
@@ -973,7 +1079,7 @@ int dlsm_center(dlsm_handle *h)
 
 // device-side part of sample_intercepts; d_eps/d_logu are device pointers or null (native)
 static int intercepts_async(dlsm_handle *h, const double *d_eps, const double *d_logu,
-                            int32_t *d_acc, double *d_ratio, bool use_cur = false)
+                            int32_t *d_acc, double *d_ratio, bool use_cur = false, bool rows = false)
 {
     const int C = h->cfg.n_chains, m = h->cfg.is_directed ? 2 : 1;
     const dim3 g1((C + 127) / 128), b1(128);
@@ -981,7 +1087,8 @@ static int intercepts_async(dlsm_handle *h, const double *d_eps, const double *d
     for (int i = 0; i < m; i++) {
         ScalarMH p;
         memset(&p, 0, sizeof(p));
-        p.C = C; p.which = i; p.nblk = h->full_nblk;
+        p.C = C; p.which = i; p.nblk = rows ? rows_nblk(h) : h->full_nblk;
+        p.accflag = rows ? h->d_accflag : nullptr;
         p.tune = h->cfg.tune; p.tune_interval = h->cfg.intercept_tune_interval[i];
         p.intercept = F<double>(h, DLSM_F_INTERCEPT);
         p.bvar = h->d_bvar; p.prop = h->d_prop; p.partial = h->d_partial;
@@ -998,8 +1105,11 @@ static int intercepts_async(dlsm_handle *h, const double *d_eps, const double *d
         p.ll_cur = use_cur ? F<double>(h, DLSM_F_LOGLIK) : nullptr; p.use_cur = use_cur ? 1 : 0;
         int rc = launch_simple(h, k_intercept_propose, g1, b1, 0, p);
         if (rc != DLSM_OK) return rc;
-        if ((rc = launch_full(h, h->rinv, h->rinv, use_cur ? 1 : 2)) != DLSM_OK) return rc;
+        if (rows) rc = launch_rows(h, h->rinv); // the proposal's log-likelihood AND its row sums
+        else rc = launch_full(h, h->rinv, h->rinv, use_cur ? 1 : 2);
+        if (rc != DLSM_OK) return rc;
         if ((rc = launch_simple(h, k_intercept_finalize, g1, b1, 0, p)) != DLSM_OK) return rc;
+        if (rows && (rc = commit_rows(h, h->d_accflag)) != DLSM_OK) return rc; // accepted chains adopt them
     }
     end_phase(h);
     if (!d_eps) h->sweep_idx[kRngIntercept] += 1;
@@ -1016,6 +1126,7 @@ int dlsm_sample_intercepts(dlsm_handle *h, const double *eps, const double *logu
     if (rc != DLSM_OK) return rc;
     const size_t C = h->cfg.n_chains, m = h->cfg.is_directed ? 2 : 1;
     double *d_eps = nullptr, *d_logu = nullptr;
+    h->rows_valid = false;
     if (eps) {
         d_eps = h->d_small; d_logu = h->d_small + C * 2;
         if ((rc = upload(h, d_eps, eps, C * m * 8)) != DLSM_OK) return rc;
@@ -1030,7 +1141,7 @@ int dlsm_sample_intercepts(dlsm_handle *h, const double *eps, const double *logu
 }
 
 static int radii_async(dlsm_handle *h, bool native, const double *d_logu, int32_t *d_acc,
-                       double *d_ratio, bool use_cur = false)
+                       double *d_ratio, bool use_cur = false, bool rows = false)
 {
     const int C = h->cfg.n_chains, n = h->cfg.n;
     begin_phase(h, 1);
@@ -1050,10 +1161,13 @@ static int radii_async(dlsm_handle *h, bool native, const double *d_logu, int32_
     rc = launch_simple(h, k_bvar_current, dim3((C + 127) / 128), dim3(128), 0, C,
                        (const double *)F<double>(h, DLSM_F_INTERCEPT), h->d_bvar);
     if (rc != DLSM_OK) return rc;
-    if ((rc = launch_full(h, h->d_rprop_inv, h->rinv, use_cur ? 1 : 2)) != DLSM_OK) return rc;
+    if (rows) rc = launch_rows(h, h->d_rprop_inv);
+    else rc = launch_full(h, h->d_rprop_inv, h->rinv, use_cur ? 1 : 2);
+    if (rc != DLSM_OK) return rc;
     RadiiMH p;
     memset(&p, 0, sizeof(p));
-    p.C = C; p.n = n; p.nblk = h->full_nblk;
+    p.C = C; p.n = n; p.nblk = rows ? rows_nblk(h) : h->full_nblk;
+    p.accflag = rows ? h->d_accflag : nullptr;
     p.tune = h->cfg.radii_tune; p.tune_interval = h->cfg.radii_tune_interval;
     p.radii = F<double>(h, DLSM_F_RADII); p.rinv = h->rinv;
     p.prop = h->d_rprop; p.prop_rinv = h->d_rprop_inv; p.partial = h->d_partial;
@@ -1067,6 +1181,7 @@ static int radii_async(dlsm_handle *h, bool native, const double *d_logu, int32_
     p.accepted = d_acc; p.ratio = d_ratio; p.flags = h->d_flags;
     p.ll_cur = use_cur ? F<double>(h, DLSM_F_LOGLIK) : nullptr; p.use_cur = use_cur ? 1 : 0;
     rc = launch_simple(h, k_radii_finalize, dim3(C), dim3(256), 0, p);
+    if (rc == DLSM_OK && rows) rc = commit_rows(h, h->d_accflag);
     end_phase(h);
     if (native) h->sweep_idx[kRngRadii] += 1;
     return rc;
@@ -1082,6 +1197,7 @@ int dlsm_sample_radii(dlsm_handle *h, const double *proposal, const double *logu
     int rc = need_inputs(h);
     if (rc != DLSM_OK) return rc;
     const size_t C = h->cfg.n_chains, n = h->cfg.n;
+    h->rows_valid = false;
     if (proposal) {
         if ((rc = upload(h, h->d_rprop, proposal, C * n * 8)) != DLSM_OK) return rc;
         if ((rc = upload(h, h->d_small, logu, C * 8)) != DLSM_OK) return rc;
@@ -1280,6 +1396,20 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
     // behind, so the intercept / radii MH below evaluates only its proposals
     bool use_cur = !use_slice_kernel(h) && h->lk != kCaseControl && !h->opt[DLSM_OPT_NO_TRACKED_LOGLIK];
     p.ll_cur = use_cur ? F<double>(h, DLSM_F_LOGLIK) : nullptr;
+    // ... and keeps the per-node row sums, so that a node-update evaluates its proposal only
+    const bool rows = use_cur && rows_enabled(h);
+    if (rows) {
+        if ((rc = ensure_rows(h)) != DLSM_OK) return rc;
+        if (!h->rows_valid) {
+            tl_begin(h, "row sums");
+            begin_phase(h, 1);
+            rc = refresh_rows(h);
+            end_phase(h);
+            tl_end(h);
+            if (rc != DLSM_OK) return rc;
+        }
+        p.rows = h->d_rows; p.scr = h->d_scr;
+    }
     if (h->x_copy_pending) { // the previous record of X is still on its way to the host
         CU(h, cudaStreamWaitEvent(h->stream, h->ev_x_copied, 0));
         h->x_copy_pending = false;
@@ -1350,11 +1480,11 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
     }
     if (tracked) *tracked = use_cur;
     tl_begin(h, "intercepts");
-    if (!(flags & 2u) && (rc = intercepts_async(h, nullptr, nullptr, nullptr, nullptr, use_cur)) != DLSM_OK) return rc;
+    if (!(flags & 2u) && (rc = intercepts_async(h, nullptr, nullptr, nullptr, nullptr, use_cur, rows)) != DLSM_OK) return rc;
     tl_end(h);
     tl_begin(h, "radii");
     if (h->cfg.is_directed && !(flags & 4u) &&
-        (rc = radii_async(h, true, nullptr, nullptr, nullptr, use_cur)) != DLSM_OK)
+        (rc = radii_async(h, true, nullptr, nullptr, nullptr, use_cur, rows)) != DLSM_OK)
         return rc;
     tl_end(h);
     if (labels) CU(h, cudaStreamWaitEvent(main_stream, h->ev_join, 0));
@@ -1798,6 +1928,18 @@ int dlsm_debug_set_counts(dlsm_handle *h, int field, const void *host, size_t by
     if (rc != DLSM_OK) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     return DLSM_OK;
+}
+
+int dlsm_debug_rowsums(dlsm_handle *h, double *out)
+{
+    if (!h || !out) return DLSM_ERR_INVALID;
+    CU(h, cudaSetDevice(h->cfg.device));
+    int rc = need_inputs(h);
+    if (rc != DLSM_OK) return rc;
+    if (!rows_enabled(h)) FAIL(h, DLSM_ERR_UNSUPPORTED, "no row-sum cache in this configuration");
+    if ((rc = ensure_rows(h)) != DLSM_OK) return rc;
+    if (!h->rows_valid && (rc = refresh_rows(h)) != DLSM_OK) return rc;
+    return download(h, out, h->d_rows, (size_t)h->cfg.n_chains * h->cfg.T * h->cfg.n * 8);
 }
 
 int dlsm_debug_draws(dlsm_handle *h, double *eps, double *logu)

@@ -57,6 +57,11 @@ struct SweepParams {
     unsigned int *flags;       // bit0 non-finite ratio, bit1 case-control out-of-bounds quirk
     int fuse_center;           // k_sweep (positions in shared memory): centre before the write-back
     double *ll_cur;            // optional [C]: full-network log-likelihood of the post-sweep state
+    // row-sum cache (exact likelihoods, device loop): rows[c][t][j] = sum_i term(i, j) at the current
+    // state, so that a node-update evaluates its PROPOSAL only; scr[c][t][i] parks the proposal's
+    // per-pair terms until the decision (see node_loglik1 / rows_apply)
+    double *rows;              // [C][T][n] or nullptr (two-variant evaluation)
+    double *scr;               // [C][T][n]
 };
 
 // latent dimension: a compile-time constant in the specialised (D == 2) instantiations
@@ -312,6 +317,159 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row-sum cache.  The MH ratio of node j needs l_j(x') - l_j(x) with l_j(.) = sum_i term(x_i, .).
+// The reference evaluates both sums afresh (2 (n-1) pair terms per node-update).  Here the device
+// loop keeps rows[j] = l_j(x_j) for every node of the slice: a node-update evaluates the
+// PROPOSAL's terms only (node_loglik1, parking them in scr[]), takes l_j(x) from the cache, and
+// only an ACCEPTED move pays the second pass (rows_apply): rows[i] += term(x_i, x') - term(x_i, x)
+// for every other node and rows[j] = l_j(x').  (1 + p_accept)(n-1) pair terms instead of 2 (n-1).
+// The cached sums differ from fresh ones by summation order only (<= ~1e-13 relative); whatever
+// moves the whole network at once (an accepted intercept / radii proposal) replaces the rows by
+// the ones k_rows computed for that proposal.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ld_cg(const double *p) { return __ldcg(p); }
+__device__ __forceinline__ void st_cg(double *p, double v) { __stcg(p, v); }
+
+// proposal-only pass: returns l_j(xn) (warp-uniform); scr[i] = term(x_i, xn) for every i != j
+template <int LK, int DM, bool INTR>
+__device__ __forceinline__ double node_loglik1(const NetView &net, const double *Xt, const double *rinv,
+                                               int t, int j, const double (&xn)[DM], double b0, double b1,
+                                               int lane, double *scr)
+{
+    const int n = net.n, d = latent_dim<DM>(net);
+    if (LK == kUndirected) {
+        // four 32-node chunks per trip = four independent sqrt/softplus chains per lane; the 128
+        // adjacency bits of a trip arrive with one 128-bit load (rows are 16-byte aligned)
+        const uint32_t *row = net.rowbits + ((size_t)t * n + j) * net.W;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (int base = 0; base < n; base += 128) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4 *>(row + (base >> 5)));
+            const int i0 = base + lane, i1 = i0 + 32, i2 = i0 + 64, i3 = i0 + 96;
+            const double y0 = ymask(w.x, lane), y1 = ymask(w.y, lane), y2 = ymask(w.z, lane), y3 = ymask(w.w, lane);
+            double xa[DM], xb[DM], xc[DM], xd[DM];
+            if (INTR && base + 128 <= n && (unsigned)(j - base) >= 128u) { // interior trip: no masks
+                load_pos<DM>(Xt + (size_t)i0 * d, d, xa);
+                load_pos<DM>(Xt + (size_t)i1 * d, d, xb);
+                load_pos<DM>(Xt + (size_t)i2 * d, d, xc);
+                load_pos<DM>(Xt + (size_t)i3 * d, d, xd);
+                const double t0 = logit_term(y0, b0 - fast_dist<DM>(xa, xn, d));
+                const double t1 = logit_term(y1, b0 - fast_dist<DM>(xb, xn, d));
+                const double t2 = logit_term(y2, b0 - fast_dist<DM>(xc, xn, d));
+                const double t3 = logit_term(y3, b0 - fast_dist<DM>(xd, xn, d));
+                st_cg(scr + i0, t0); st_cg(scr + i1, t1); st_cg(scr + i2, t2); st_cg(scr + i3, t3);
+                a0 += t0; a1 += t1; a2 += t2; a3 += t3;
+                continue;
+            }
+            load_pos<DM>(Xt + (size_t)(i0 < n ? i0 : n - 1) * d, d, xa);
+            load_pos<DM>(Xt + (size_t)(i1 < n ? i1 : n - 1) * d, d, xb);
+            load_pos<DM>(Xt + (size_t)(i2 < n ? i2 : n - 1) * d, d, xc);
+            load_pos<DM>(Xt + (size_t)(i3 < n ? i3 : n - 1) * d, d, xd);
+            const double t0 = logit_term(y0, b0 - fast_dist<DM>(xa, xn, d));
+            const double t1 = logit_term(y1, b0 - fast_dist<DM>(xb, xn, d));
+            const double t2 = logit_term(y2, b0 - fast_dist<DM>(xc, xn, d));
+            const double t3 = logit_term(y3, b0 - fast_dist<DM>(xd, xn, d));
+            if (i0 < n) st_cg(scr + i0, t0);
+            if (i1 < n) st_cg(scr + i1, t1);
+            if (i2 < n) st_cg(scr + i2, t2);
+            if (i3 < n) st_cg(scr + i3, t3);
+            a0 = fma(vmask((i0 < n) && (i0 != j)), t0, a0);
+            a1 = fma(vmask((i1 < n) && (i1 != j)), t1, a1);
+            a2 = fma(vmask((i2 < n) && (i2 != j)), t2, a2);
+            a3 = fma(vmask((i3 < n) && (i3 != j)), t3, a3);
+        }
+        return warp_sum((a0 + a1) + (a2 + a3));
+    } else {
+        // K2: two chunks per trip x two directions = four softplus chains per lane
+        const uint32_t *row = net.rowbits + ((size_t)t * n + j) * net.W;
+        const uint32_t *col = net.colbits + ((size_t)t * n + j) * net.W;
+        const double rj = rinv[j];
+        double a0 = 0.0, a1 = 0.0;
+        for (int base = 0; base < n; base += 64) {
+            const uint2 wr = __ldg(reinterpret_cast<const uint2 *>(row + (base >> 5)));
+            const uint2 wc = __ldg(reinterpret_cast<const uint2 *>(col + (base >> 5)));
+            const int i0 = base + lane, i1 = i0 + 32;
+            const int c0 = i0 < n ? i0 : n - 1, c1 = i1 < n ? i1 : n - 1;
+            double xa[DM], xb[DM];
+            load_pos<DM>(Xt + (size_t)c0 * d, d, xa);
+            load_pos<DM>(Xt + (size_t)c1 * d, d, xb);
+            const double r0 = rinv[c0], r1 = rinv[c1];
+            const double d0 = fast_dist<DM>(xa, xn, d), d1 = fast_dist<DM>(xb, xn, d);
+            const double t0 = logit_term(ymask(wr.x, lane), eta_directed(b0, b1, d0, r0, rj)) +
+                              logit_term(ymask(wc.x, lane), eta_directed(b0, b1, d0, rj, r0));
+            const double t1 = logit_term(ymask(wr.y, lane), eta_directed(b0, b1, d1, r1, rj)) +
+                              logit_term(ymask(wc.y, lane), eta_directed(b0, b1, d1, rj, r1));
+            if (i0 < n) st_cg(scr + i0, t0);
+            if (i1 < n) st_cg(scr + i1, t1);
+            a0 = fma(vmask((i0 < n) && (i0 != j)), t0, a0);
+            a1 = fma(vmask((i1 < n) && (i1 != j)), t1, a1);
+        }
+        return warp_sum(a0 + a1);
+    }
+}
+
+// accepted move of node j (old position xo): every other row trades its old pair term for the
+// parked new one, row j becomes the proposal's sum.  One warp; rows / scr point at slice t.
+template <int LK, int DM>
+__device__ __forceinline__ void rows_apply(const NetView &net, const double *Xt, const double *rinv, int t,
+                                           int j, const double (&xo)[DM], double b0, double b1, int lane,
+                                           const double *scr, double *rows, double ll_new)
+{
+    const int n = net.n, d = latent_dim<DM>(net);
+    if (LK == kUndirected) {
+        const uint32_t *row = net.rowbits + ((size_t)t * n + j) * net.W;
+        for (int base = 0; base < n; base += 128) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4 *>(row + (base >> 5)));
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            double told[4], tnew[4], cur[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + lane + 32 * u;
+                ok[u] = (i < n) && (i != j);
+                const int ic = i < n ? i : n - 1;
+                double xi[DM];
+                load_pos<DM>(Xt + (size_t)ic * d, d, xi);
+                tnew[u] = ld_cg(scr + ic);
+                cur[u] = ld_cg(rows + ic);
+                told[u] = logit_term(ymask(ww[u], lane), b0 - fast_dist<DM>(xi, xo, d));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (ok[u]) st_cg(rows + base + lane + 32 * u, cur[u] + (tnew[u] - told[u]));
+        }
+    } else {
+        const uint32_t *row = net.rowbits + ((size_t)t * n + j) * net.W;
+        const uint32_t *col = net.colbits + ((size_t)t * n + j) * net.W;
+        const double rj = rinv[j];
+        for (int base = 0; base < n; base += 64) {
+            const uint2 wr = __ldg(reinterpret_cast<const uint2 *>(row + (base >> 5)));
+            const uint2 wc = __ldg(reinterpret_cast<const uint2 *>(col + (base >> 5)));
+            const uint32_t wrr[2] = {wr.x, wr.y}, wcc[2] = {wc.x, wc.y};
+            double told[2], tnew[2], cur[2];
+            bool ok[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int i = base + lane + 32 * u;
+                ok[u] = (i < n) && (i != j);
+                const int ic = i < n ? i : n - 1;
+                double xi[DM];
+                load_pos<DM>(Xt + (size_t)ic * d, d, xi);
+                const double ri = rinv[ic];
+                tnew[u] = ld_cg(scr + ic);
+                cur[u] = ld_cg(rows + ic);
+                const double dd = fast_dist<DM>(xi, xo, d);
+                told[u] = logit_term(ymask(wrr[u], lane), eta_directed(b0, b1, dd, ri, rj)) +
+                          logit_term(ymask(wcc[u], lane), eta_directed(b0, b1, dd, rj, ri));
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (ok[u]) st_cg(rows + base + lane + 32 * u, cur[u] + (tnew[u] - told[u]));
+        }
+    }
+    if (lane == 0) st_cg(rows + j, ll_new);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Prior terms of the closure `logp` (sample_latent_positions.py:131-140 LSM, :187-199 mixture).
 // The reference subtracts them from loglik one after the other:
 //     loglik -= term_prev(x | X[t-1,j])   (or the t == 0 term)
@@ -394,7 +552,7 @@ __host__ __device__ inline size_t sweep_stage_doubles(int d) { return (size_t)32
 // prior term and the accept/reject, which lane (j mod 32) commits.  The Metropolis bookkeeping of
 // the 32 samplers runs lane-parallel at the end of the block.
 // ---------------------------------------------------------------------------------------------
-template <int LK, int D, bool XS, int MAXT, int MINB>
+template <int LK, int D, bool XS, int MAXT, int MINB, bool RS = false>
 __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
 {
     constexpr int DM = (D == 0) ? kMaxD : D;
@@ -432,6 +590,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
     double full_acc = 0.0; // lower-triangle terms of this warp's slices at the kept states
     for (int t = warp; t < T; t += nwarps) {
         double *Xt = Xc + (size_t)t * n * d;
+        double *rows_t = RS ? p.rows + ((size_t)c * T + t) * n : nullptr; // row-sum cache of this slice
+        double *scr_t = RS ? p.scr + ((size_t)c * T + t) * n : nullptr;
         for (int jb = 0; jb < n; jb += 32) {
             // ---------------- lane-parallel preparation for node jl = jb + lane ----------------
             const int jl = jb + lane;
@@ -493,7 +653,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
                 double ll_new, ll_old, lo_n = 0.0, lo_o = 0.0;
                 // the (320, 2) build is the one picked when shared memory admits two chains per SM,
                 // i.e. for long rows: it gets the unmasked interior trips
-                if (LK != kCaseControl)
+                if (RS && LK != kCaseControl) {
+                    // proposal only; the current position's sum comes from the row-sum cache
+                    ll_old = ld_cg(rows_t + j);
+                    ll_new = node_loglik1<LK == kCaseControl ? kDirected : LK, DM, (MAXT == 320 && MINB == 2)>(
+                        p.net, Xt, rinv, t, j, x, b0, b1, lane, scr_t);
+                } else if (LK != kCaseControl)
                     node_loglik2<LK, DM, true, (MAXT == 320 && MINB == 2)>(p.net, Xt, rinv, c, t, j, x, x0, b0,
                                                                           b1, lane, ll_new, ll_old, p.flags, 0,
                                                                           1, -1, &lo_n, &lo_o);
@@ -534,6 +699,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
                     __threadfence_block();
                     progress[t] = j + 1;
                 }
+                if (RS && LK != kCaseControl && acc) // accepted: the other rows trade their pair terms
+                    rows_apply<LK == kCaseControl ? kDirected : LK, DM>(p.net, Xt, rinv, t, j, x0, b0, b1, lane,
+                                                                        scr_t, rows_t, ll_new);
                 __syncwarp();
             }
             // ---------------- lane-parallel Metropolis bookkeeping + coalesced write-back --------
@@ -548,6 +716,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
     }
     if (nonfinite) atomicOr(p.flags, 1u);
     if (p.ll_cur) { // full-network log-likelihood of the post-sweep state, summed in warp order
+        if (RS && LK != kCaseControl) { // every dyad sits in the row sums of both its nodes
+            full_acc = 0.0;
+            for (int t = warp; t < T; t += nwarps) {
+                const double *rows_t = p.rows + ((size_t)c * T + t) * n;
+                for (int i = lane; i < n; i += 32) full_acc += 0.5 * ld_cg(rows_t + i);
+            }
+        }
         full_acc = warp_sum(full_acc);
         __syncthreads();
         double *wsum = stage_base; // the staging area is free now
@@ -1559,6 +1734,153 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_rows: the full-network log-likelihood of ONE parameter variant (an intercept / radii proposal,
+// or the current state) together with its ROW SUMS rows'[j] = sum_i term(i, j), every unordered
+// pair evaluated once (exact likelihoods; feeds the row-sum cache of the sweep kernels).
+// Pairs are visited as 32 x 32 tiles (row block I, column block J >= I).  A warp owns a row block
+// and a run of JS column blocks: lane l keeps node a = 32 I + l and its row accumulator for the
+// whole run; at step s it meets node b = 32 J + (l + s) mod 32, whose column accumulator ROTATES
+// through the lanes (one 64-bit shuffle per step), so both nodes of a pair are credited from one
+// evaluation and nothing is reduced through memory or atomics: the column vector of every tile is
+// written once (part[J][I][32]), the row vector once per run (own[I][g][32]), and k_rows_commit
+// adds them in a fixed order -> the result is reproducible bit for bit.
+// grid = (T * chunks, C), block = 256 (8 items per CTA, all of one slice);
+// dynamic smem = n * (d [+ 1]) doubles
+// ---------------------------------------------------------------------------------------------
+struct RowsParams {
+    NetView net;
+    int C, nb, JS, G, ni, chunks;  // row blocks, tiles per run, runs per row block (max), items per slice
+    const double *X;        // [C][T][n][d]
+    const double *bvar;     // [C][2][2]: variant 0 is evaluated
+    const double *rinv0;    // [C][n]
+    double *partial;        // [C][T*chunks][2] (slot 0)
+    double *own;            // [C][T][nb][G][32]
+    double *part;           // [C][T][nb (nb-1) / 2][32]
+};
+
+__host__ __device__ inline int rows_runs(int nb, int JS, int I) { return (nb - I + JS - 1) / JS; }
+// row blocks are dealt in folded order 0, nb-1, 1, nb-2, ... so that consecutive items pair a long
+// row of tiles with a short one
+__host__ __device__ inline int rows_fold(int nb, int q) { return (q & 1) ? nb - 1 - (q >> 1) : (q >> 1); }
+
+template <int LK, int D>
+__global__ void __launch_bounds__(256) k_rows(const RowsParams p)
+{
+    constexpr int DM = (D == 0) ? kMaxD : D;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[8];
+    const int T = p.net.T, n = p.net.n, d = (D == 0) ? p.net.d : D, W = p.net.W, nb = p.nb;
+    const int c = blockIdx.y, t = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *Xs = reinterpret_cast<double *>(smem_raw);
+    const double *Xg = p.X + ((size_t)c * T + t) * n * d;
+    for (int e = threadIdx.x; e < n * d; e += blockDim.x) Xs[e] = Xg[e];
+    const double *rv = nullptr;
+    if (LK == kDirected) {
+        double *rs = Xs + (size_t)n * d;
+        for (int e = threadIdx.x; e < n; e += blockDim.x) rs[e] = p.rinv0[(size_t)c * n + e];
+        rv = rs;
+    }
+    __syncthreads();
+    const double b0 = p.bvar[(size_t)c * 4], b1 = p.bvar[(size_t)c * 4 + 1];
+    double once = 0.0; // every pair of this warp's tiles counted once
+    int item = chunk * 8 + warp, I = -1, g = 0;
+    if (item < p.ni) {
+        for (int q = 0; q < nb; q++) { // decode (row block, run) from the folded item order
+            const int Iq = rows_fold(nb, q), r = rows_runs(nb, p.JS, Iq);
+            if (item < r) { I = Iq; g = item; break; }
+            item -= r;
+        }
+    }
+    if (I >= 0) {
+        const int a = 32 * I + lane;
+        const bool va = a < n;
+        const int ac = va ? a : n - 1;
+        double xa[DM];
+        load_pos<DM>(Xs + (size_t)ac * d, d, xa);
+        const double ra = (LK == kDirected) ? rv[ac] : 0.0;
+        const uint32_t *rowa = p.net.rowbits + ((size_t)t * n + ac) * W;
+        const uint32_t *cola = (LK == kDirected) ? p.net.colbits + ((size_t)t * n + ac) * W : nullptr;
+        const size_t slice = (size_t)c * T + t;
+        double *part_t = p.part + slice * ((size_t)nb * (nb - 1) / 2) * 32;
+        double rowacc = 0.0;
+        const int J0 = I + g * p.JS, J1 = (J0 + p.JS < nb) ? J0 + p.JS : nb;
+        auto pair_term = [&](int J, int bl, uint32_t wr, uint32_t wc) {
+            const int b = 32 * J + bl;
+            const int bc = b < n ? b : n - 1;
+            double xb[DM];
+            load_pos<DM>(Xs + (size_t)bc * d, d, xb);
+            const double dist = fast_dist<DM>(xb, xa, d);
+            if (LK == kUndirected) return logit_term(ymask(wr, bl), b0 - dist);
+            const double rb = rv[bc];
+            return logit_term(ymask(wr, bl), eta_directed(b0, b1, dist, rb, ra)) +  // a sends to b
+                   logit_term(ymask(wc, bl), eta_directed(b0, b1, dist, ra, rb));   // b sends to a
+        };
+        for (int J = J0; J < J1; J++) {
+            const uint32_t wr = __ldg(rowa + J);
+            const uint32_t wc = (LK == kDirected) ? __ldg(cola + J) : 0u;
+            double R = 0.0, tile = 0.0;
+            if (J == I) {
+                // diagonal tile: pairs at cyclic distance 1..16 (distance 16 is met from both ends)
+#pragma unroll 4
+                for (int s = 1; s <= 16; s++) {
+                    const int bl = (lane + s) & 31;
+                    const double v = vmask(va && (32 * J + bl < n) && (s < 16 || lane < 16));
+                    const double term = pair_term(J, bl, wr, wc);
+                    R = __shfl_sync(kFull, R, (lane + 1) & 31);
+                    R = fma(v, term, R);
+                    tile = fma(v, term, tile);
+                }
+                R = __shfl_sync(kFull, R, (lane + 16) & 31); // column accumulators back to their nodes
+                rowacc += tile + R;
+            } else {
+#pragma unroll 4
+                for (int s = 0; s < 32; s++) {
+                    const int bl = (lane + s) & 31;
+                    const double v = vmask(va && (32 * J + bl < n));
+                    const double term = pair_term(J, bl, wr, wc);
+                    if (s) R = __shfl_sync(kFull, R, (lane + 1) & 31);
+                    R = fma(v, term, R);
+                    tile = fma(v, term, tile);
+                }
+                R = __shfl_sync(kFull, R, (lane + 1) & 31);
+                part_t[((size_t)J * (J - 1) / 2 + I) * 32 + lane] = R;
+                rowacc += tile;
+            }
+            once += tile;
+        }
+        p.own[((slice * nb + I) * p.G + g) * 32 + lane] = rowacc;
+    }
+    once = warp_sum(once);
+    if (lane == 0) red[warp] = once;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sacc = 0.0;
+        for (int w = 0; w < 8; w++) sacc += red[w];
+        p.partial[((size_t)c * gridDim.x + blockIdx.x) * 2] = sacc;
+    }
+}
+
+// rows[c][t][j] <- the row sums k_rows left in (own, part), for every chain whose flag is set
+// (flag == nullptr: all chains); one warp per (slice, row block), fixed summation order
+__global__ void __launch_bounds__(256) k_rows_commit(const int32_t *flag, int T, int n, int nb, int JS, int G,
+                                                     const double *own, const double *part, double *rows)
+{
+    const int c = blockIdx.y, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= T * nb || (flag && !flag[c])) return;
+    const int t = w / nb, Q = w % nb;
+    const size_t slice = (size_t)c * T + t;
+    double s = 0.0;
+    const int runs = rows_runs(nb, JS, Q);
+    for (int g = 0; g < runs; g++) s += own[((slice * nb + Q) * G + g) * 32 + lane];
+    const double *pt = part + slice * ((size_t)nb * (nb - 1) / 2) * 32 + ((size_t)Q * (Q - 1) / 2) * 32;
+    for (int I = 0; I < Q; I++) s += pt[(size_t)I * 32 + lane];
+    const int i = 32 * Q + lane;
+    if (i < n) rows[slice * n + i] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
 // scalar MH on the full-network likelihood: propose / finalize (one thread per chain)
 // ---------------------------------------------------------------------------------------------
 struct ScalarMH {
@@ -1580,6 +1902,7 @@ struct ScalarMH {
     double *ll_cur;          // optional [C]: log-likelihood of the current state, kept up to date
     int use_cur;             // 1: partial[..][1] was not computed, take ll_cur instead
     unsigned int *flags;
+    int32_t *accflag;        // optional [C]: this step's decision (k_rows_commit reads it)
 };
 
 __global__ void k_intercept_propose(const ScalarMH p)
@@ -1625,6 +1948,7 @@ __global__ void k_intercept_finalize(const ScalarMH p)
                               kRngIntercept, 0).a);
     const int acc = (logu >= ratio) ? 0 : 1;
     if (acc) p.intercept[c * 2 + p.which] = x;
+    if (p.accflag) p.accflag[c] = acc;
     if (p.ll_cur) p.ll_cur[c] = acc ? s0 : s1;
     const int o = c * 2 + p.which;
     double st = p.step[o];
@@ -1675,6 +1999,7 @@ struct RadiiMH {
     unsigned int *flags;
     double *ll_cur;                  // optional [C], see ScalarMH
     int use_cur;
+    int32_t *accflag;                // optional [C], see ScalarMH
 };
 
 __device__ __forceinline__ double block_sum(double v, double *sh)
@@ -1721,6 +2046,7 @@ __global__ void __launch_bounds__(256) k_radii_finalize(const RadiiMH p)
         else logu = log(philox_u2(p.seed, p.site, p.sweep, (uint32_t)c + p.chain_offset, kRngRadii, 0).a);
         const int acc = (logu >= ratio) ? 0 : 1;
         s_acc = acc;
+        if (p.accflag) p.accflag[c] = acc;
         if (p.ll_cur) p.ll_cur[c] = acc ? s0 : s1;
         double st = s;
         int na = p.nacc[c], ns = p.nsteps[c], un = p.until[c];

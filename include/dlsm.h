@@ -133,7 +133,7 @@ int dlsm_synchronize(dlsm_handle *h);
  * variable that only supplies its DEFAULT, read once by dlsm_create (never on the sweep path):
  * DLSM_SWEEP_MODE=chain|chain-dense|slice|slice-plain, DLSM_FFBS=thread|warp, DLSM_FFBS_SMEM,
  * DLSM_FFBS_PER_SM=<n>, DLSM_NO_GATHER_PACK, DLSM_NO_LLCUR, DLSM_CENTER_EXACT, DLSM_HDP_SEGMENTED,
- * DLSM_NO_EARLY_X, DLSM_TRACE_CHUNK_BYTES=<bytes>. */
+ * DLSM_NO_EARLY_X, DLSM_TRACE_CHUNK_BYTES=<bytes>, DLSM_NO_ROWSUM. */
 typedef enum {
     DLSM_OPT_SWEEP_MODE = 0,        /* dlsm_sweep_mode: which latent-sweep kernel (default: heuristic) */
     DLSM_OPT_FFBS_KERNEL = 1,       /* dlsm_ffbs_kernel: label kernel mapping */
@@ -145,6 +145,8 @@ typedef enum {
     DLSM_OPT_HDP_SEGMENTED = 7,     /* 1: segmented-butterfly sufficient statistics in the HDP update */
     DLSM_OPT_NO_EARLY_X = 8,        /* 1: position records always go through the trace ring */
     DLSM_OPT_TRACE_CHUNK_BYTES = 9, /* device bytes of one trace-ring chunk (0 = 512 MB or free/8) */
+    DLSM_OPT_NO_ROWSUM_CACHE = 10,  /* 1: the device loop evaluates proposal AND current position of every
+                                       node-update afresh instead of keeping per-node row sums */
     DLSM_OPT_COUNT_
 } dlsm_option;
 typedef enum {
@@ -275,6 +277,10 @@ int dlsm_gaussian_likelihood(dlsm_handle *h, double *out);
 /* overwrite the read-only label-count fields (DLSM_F_NCOUNT / DLSM_F_NK) -- test probe for
  * dlsm_hdp_update, which normally consumes what dlsm_sample_labels just produced */
 int dlsm_debug_set_counts(dlsm_handle *h, int field, const void *host, size_t bytes);
+/* the device loop's row-sum cache, out (C,T,n): rows[c,t,j] = per-node log-likelihood of node j at the
+ * current state as the loop tracks it (computed by k_rows if the cache is not current);
+ * DLSM_ERR_UNSUPPORTED where the loop keeps no cache (case-control lists, CTA-per-slice kernels) */
+int dlsm_debug_rowsums(dlsm_handle *h, double *out);
 /* the raw draws the NEXT native latent sweep will consume: eps (C,T,n,d), logu (C,T,n) */
 int dlsm_debug_draws(dlsm_handle *h, double *eps, double *logu);
 
