@@ -263,6 +263,7 @@ def measure(ctx, name, steps, warmup, chains_override=0, e2e=True, cpu=True, par
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    step_tuned, tune_log = pretune(e, w)
     for _ in range(warmup):
         e.run_sweeps(1)
     torch.cuda.synchronize()
@@ -396,11 +397,34 @@ def measure(ctx, name, steps, warmup, chains_override=0, e2e=True, cpu=True, par
                        "step": "latent sweep + centre + intercept MH" +
                                (" + radii MH" if w["directed"] else "") +
                                (" + label FFBS + HDP conjugate updates" if w["K"] else ""),
-                       "accept_rate": acc_rate,
+                       "accept_rate": acc_rate, "step_size_X": step_tuned,
+                       "step_tuning": "before the warm-up the reference's tuning table (metropolis.py:5-37) is "
+                                      "applied to the chain-averaged acceptance rate, one sweep per adjustment, from "
+                                      "step_size_X = %g until the rate is in its dead band [0.25, 0.4] (%d sweeps): "
+                                      "the state every tuned sampler of a long run sits in" % (w["step_X"], len(tune_log)),
                        "l2": "flushed between timed iterations (256 MiB write)"},
             "roofline": roofline, "cpu_baseline": cpu_res, "e2e": e2e_res, "clocks": clk,
             "gpu_launches": int(launches), "pool_traces": pooled,
             "phase_ms_per_step": {"latent": latent_ms / steps, "other": other_ms / steps}}
+
+
+def pretune(e, w, max_sweeps=60):
+    """Bring the latent samplers to the acceptance band the reference's tuner converges to."""
+    from dynetlsm_b200 import _lib as L
+    step, log = float(w["step_X"]), []
+    for _ in range(max_sweeps):
+        acc, _ = e.sweep_latent(want_stats=True)
+        rate = float(acc.mean())
+        log.append((step, rate))
+        if 0.25 <= rate <= 0.4:
+            break
+        # metropolis.py:5-37
+        f = (0.1 if rate < 0.001 else 0.5 if rate < 0.05 else 0.9 if rate < 0.25 else
+             10.0 if rate > 0.95 else 2.0 if rate > 0.75 else 1.1)
+        step *= f
+        e.set(L.F_X_STEP, np.full(e.shape_of(L.F_X_STEP), step))
+    e.set_tuner(step)
+    return step, log
 
 
 def cpu_leg(name, e, w, parity):

@@ -69,7 +69,7 @@ class TraceSpec(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("node_updates", C.c_uint64),
                 ("sweeps", C.c_uint64), ("latent_ms", C.c_double), ("other_ms", C.c_double),
-                ("ub_flags", C.c_uint64)]
+                ("ub_flags", C.c_uint64), ("cluster_sweeps", C.c_uint64), ("rowsum_sweeps", C.c_uint64)]
 
 
 # every symbol include/dlsm.h declares
@@ -87,7 +87,7 @@ EXPORTS = [
 # dlsm_option / dlsm_sweep_mode / dlsm_ffbs_kernel (include/dlsm.h)
 (OPT_SWEEP_MODE, OPT_FFBS_KERNEL, OPT_FFBS_SMEM_STAGE, OPT_FFBS_CTAS_PER_SM, OPT_NO_GATHER_PACK,
  OPT_NO_TRACKED_LOGLIK, OPT_CENTER_EXACT, OPT_HDP_SEGMENTED, OPT_NO_EARLY_X, OPT_TRACE_CHUNK_BYTES,
- OPT_NO_ROWSUM_CACHE) = range(11)
+ OPT_NO_ROWSUM_CACHE, OPT_NO_CLUSTER) = range(12)
 SWEEP_AUTO, SWEEP_CHAIN, SWEEP_CHAIN_DENSE, SWEEP_SLICE, SWEEP_SLICE_PLAIN = range(5)
 FFBS_AUTO, FFBS_THREAD, FFBS_WARP = range(3)
 
@@ -510,7 +510,8 @@ class Engine(object):
         c = Counters()
         self._ck(self.L.dlsm_get_counters(self.h, C.byref(c)))
         return dict(kernel_launches=c.kernel_launches, node_updates=c.node_updates, sweeps=c.sweeps,
-                    latent_ms=c.latent_ms, other_ms=c.other_ms, ub_flags=c.ub_flags)
+                    latent_ms=c.latent_ms, other_ms=c.other_ms, ub_flags=c.ub_flags,
+                    cluster_sweeps=c.cluster_sweeps, rowsum_sweeps=c.rowsum_sweeps)
 
 
 def device_count():

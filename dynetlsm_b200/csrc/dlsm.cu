@@ -65,7 +65,9 @@ struct dlsm_handle {
     double *d_rows = nullptr, *d_scr = nullptr, *d_rows_own = nullptr, *d_rows_part = nullptr;
     int32_t *d_accflag = nullptr;
     bool rows_valid = false;
-    int rows_nb = 0, rows_JS = 16, rows_G = 1, rows_ni = 0, rows_chunks = 1;
+    int rows_nb = 0, rows_half = 0, rows_R = 1, rows_L = 0, rows_ipc = 0, rows_ns = 1, rows_grid = 1;
+    int cluster_cs = -1;            // CTAs per (chain, slice) cluster of k_sweep_slice_cl (-1: not probed, 0: none)
+    int cluster_ncomp = 0;
     // developer options (dlsm_set_option; environment defaults are read ONCE, in dlsm_create)
     int64_t opt[DLSM_OPT_COUNT_] = {0};
     // rng
@@ -265,6 +267,7 @@ void read_env_options(dlsm_handle *h)
     h->opt[DLSM_OPT_HDP_SEGMENTED] = on("DLSM_HDP_SEGMENTED");
     h->opt[DLSM_OPT_NO_EARLY_X] = on("DLSM_NO_EARLY_X");
     h->opt[DLSM_OPT_NO_ROWSUM_CACHE] = on("DLSM_NO_ROWSUM");
+    h->opt[DLSM_OPT_NO_CLUSTER] = on("DLSM_NO_CLUSTER");
     if (const char *m = getenv("DLSM_TRACE_CHUNK_BYTES")) h->opt[DLSM_OPT_TRACE_CHUNK_BYTES] = atoll(m);
     apply_sweep_mode(h);
 }
@@ -415,6 +418,79 @@ int launch_slice_t(dlsm_handle *h, const SweepParams &p, int nw)
     return DLSM_OK;
 }
 
+// ---- cluster-per-(chain, slice) variant: few slices, long rows (cfg 3) ---------------------------
+size_t cluster_smem(const dlsm_handle *h)
+{
+    const dlsm_config &c = h->cfg;
+    return (size_t)c.n * (c.d + (h->lk == kUndirected ? 0 : 1)) * sizeof(double) +
+           (sweep_stage_doubles(c.d) + 2 * (size_t)kMaxTeam * 2) * sizeof(double) + 16;
+}
+
+template <int LK, int D>
+int cluster_launch_t(dlsm_handle *h, const SweepParams *p, int CS, int ncomp, int *max_active)
+{
+    const size_t CT = (size_t)h->cfg.n_chains * h->cfg.T;
+    const size_t smem = cluster_smem(h);
+    auto kern = k_sweep_slice_cl<LK, D>;
+    CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(CT * CS));
+    cfg.blockDim = dim3(32 * (1 + ncomp));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (max_active) { // probe only: how many such clusters can be resident at once
+        CU(h, cudaOccupancyMaxActiveClusters(max_active, kern, &cfg));
+        return DLSM_OK;
+    }
+    CU(h, cudaMemsetAsync(h->d_progress, 0, CT * sizeof(int), h->stream));
+    CU(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
+    CU(h, cudaLaunchKernelEx(&cfg, kern, *p, h->d_progress, h->d_ticket));
+    CHECK_LAUNCH(h);
+    return DLSM_OK;
+}
+
+int cluster_dispatch(dlsm_handle *h, const SweepParams *p, int CS, int ncomp, int *max_active)
+{
+    const bool d2 = h->cfg.d == 2;
+    if (h->lk == kUndirected)
+        return d2 ? cluster_launch_t<kUndirected, 2>(h, p, CS, ncomp, max_active)
+                  : cluster_launch_t<kUndirected, 0>(h, p, CS, ncomp, max_active);
+    return d2 ? cluster_launch_t<kDirected, 2>(h, p, CS, ncomp, max_active)
+              : cluster_launch_t<kDirected, 0>(h, p, CS, ncomp, max_active);
+}
+
+// CTAs per cluster: the largest size whose C*T clusters can all be resident (they form a wavefront
+// over the slices), so that one chain spreads over as many SMs as the part has; 0 = not applicable
+int cluster_size(dlsm_handle *h)
+{
+    if (h->cluster_cs >= 0) return h->cluster_cs;
+    h->cluster_cs = 0;
+    const dlsm_config &c = h->cfg;
+    const int CT = c.n_chains * c.T;
+    if (h->lk == kCaseControl || h->no_pipeline || h->opt[DLSM_OPT_NO_CLUSTER] || CT * 2 > h->sm_count ||
+        cluster_smem(h) > kMaxSmem)
+        return 0;
+    const int chunks = (c.n + (h->lk == kUndirected ? 63 : 31)) / (h->lk == kUndirected ? 64 : 32);
+    for (int CS = h->sm_count / CT < 8 ? h->sm_count / CT : 8; CS >= 2; CS--) {
+        int ncomp = (chunks + CS - 1) / CS;
+        ncomp = ncomp < 1 ? 1 : (ncomp > 15 ? 15 : ncomp);
+        int active = 0;
+        if (cluster_dispatch(h, nullptr, CS, ncomp, &active) != DLSM_OK) { cudaGetLastError(); continue; }
+        if (active >= CT) {
+            h->cluster_cs = CS;
+            h->cluster_ncomp = ncomp;
+            break;
+        }
+    }
+    return h->cluster_cs;
+}
+
 // case-control sweep, batch-parallel: a warp per node of a run of mutually independent nodes
 int launch_cc_batch(dlsm_handle *h, const SweepParams &p)
 {
@@ -444,6 +520,10 @@ template <int LK>
 int launch_slice_lk(dlsm_handle *h, const SweepParams &p)
 {
     if (LK == kCaseControl && !h->no_pipeline) return launch_cc_batch(h, p);
+    if (LK != kCaseControl && cluster_size(h) >= 2) {
+        h->ctr.cluster_sweeps += 1;
+        return cluster_dispatch(h, &p, h->cluster_cs, h->cluster_ncomp, nullptr);
+    }
     const int nw = slice_warps(h);
     const bool xs = slice_smem(h, true, nw + 1) + 4096 <= kMaxSmem / 2;
     if (h->cfg.d == 2) return xs ? launch_slice_t<LK, 2, true>(h, p, nw) : launch_slice_t<LK, 2, false>(h, p, nw);
@@ -542,11 +622,17 @@ int launch_full(dlsm_handle *h, const double *rinv0, const double *rinv1, int nv
 // ---- row-sum cache ---------------------------------------------------------------------------
 // used by the device loop (dlsm_run_sweeps / dlsm_run_traced) with the exact likelihoods and the
 // chain kernel; the function-level entry points keep the two-variant evaluation
+size_t rows_smem(const dlsm_handle *h)
+{
+    const dlsm_config &c = h->cfg;
+    const int ns = 7 / (((c.n + 31) / 32 + 1) / 2 * (((c.n + 31) / 32 + 1 + 16) / 17)) + 2;
+    return (size_t)(ns < c.T ? ns : c.T) * c.n * (c.d + (h->lk == kDirected ? 1 : 0)) * sizeof(double);
+}
+
 bool rows_enabled(const dlsm_handle *h)
 {
     return h->lk != kCaseControl && !use_slice_kernel(h) && !h->opt[DLSM_OPT_NO_ROWSUM_CACHE] &&
-           !h->opt[DLSM_OPT_NO_TRACKED_LOGLIK] &&
-           (size_t)h->cfg.n * (h->cfg.d + 1) * sizeof(double) <= kMaxSmem;
+           !h->opt[DLSM_OPT_NO_TRACKED_LOGLIK] && rows_smem(h) <= kMaxSmem;
 }
 
 int ensure_rows(dlsm_handle *h)
@@ -554,18 +640,21 @@ int ensure_rows(dlsm_handle *h)
     if (h->d_rows) return DLSM_OK;
     const dlsm_config &c = h->cfg;
     const size_t cells = (size_t)c.n_chains * c.T * c.n, slices = (size_t)c.n_chains * c.T;
-    h->rows_nb = (c.n + 31) / 32;
-    h->rows_G = (h->rows_nb + h->rows_JS - 1) / h->rows_JS;
-    h->rows_ni = 0;
-    for (int I = 0; I < h->rows_nb; I++) h->rows_ni += rows_runs(h->rows_nb, h->rows_JS, I);
-    h->rows_chunks = (h->rows_ni + 7) / 8;
-    const size_t nb = h->rows_nb;
+    const int nb = (c.n + 31) / 32;
+    h->rows_nb = nb;
+    h->rows_half = (nb + 1) / 2;
+    h->rows_R = (nb + 1 + 16) / 17;                    // runs of <= ~17 tiles
+    h->rows_L = (nb + 1 + h->rows_R - 1) / h->rows_R;
+    h->rows_ipc = h->rows_half * h->rows_R;
+    h->rows_grid = (c.T * h->rows_ipc + 7) / 8;
+    h->rows_ns = 7 / h->rows_ipc + 2;
+    if (h->rows_ns > c.T) h->rows_ns = c.T;
     CU(h, cudaMalloc((void **)&h->d_rows, cells * 8));
     CU(h, cudaMalloc((void **)&h->d_scr, cells * 8));
-    CU(h, cudaMalloc((void **)&h->d_rows_own, slices * nb * h->rows_G * 32 * 8));
-    CU(h, cudaMalloc((void **)&h->d_rows_part, (slices * (nb * (nb - 1) / 2) * 32 + 32) * 8));
+    CU(h, cudaMalloc((void **)&h->d_rows_own, slices * h->rows_half * h->rows_R * 2 * 32 * 8));
+    CU(h, cudaMalloc((void **)&h->d_rows_part, (slices * ((size_t)nb * (nb - 1) / 2) * 32 + 32) * 8));
     CU(h, cudaMalloc((void **)&h->d_accflag, (size_t)c.n_chains * 4));
-    const size_t need = (size_t)c.n_chains * c.T * h->rows_chunks * 2 * 8;
+    const size_t need = (size_t)c.n_chains * h->rows_grid * 2 * 8;
     if (need > (size_t)c.n_chains * h->full_nblk * 2 * 8) { // k_rows has its own partial-sum layout
         CU(h, cudaStreamSynchronize(h->stream));
         cudaFree(h->d_partial);
@@ -583,12 +672,12 @@ int launch_rows(dlsm_handle *h, const double *rinv0)
     RowsParams p;
     memset(&p, 0, sizeof(p));
     p.net = net_view(h);
-    p.C = c.n_chains; p.nb = h->rows_nb; p.JS = h->rows_JS; p.G = h->rows_G; p.ni = h->rows_ni;
-    p.chunks = h->rows_chunks;
+    p.C = c.n_chains; p.nb = h->rows_nb; p.half = h->rows_half; p.R = h->rows_R; p.L = h->rows_L;
+    p.ipc = h->rows_ipc; p.ns = h->rows_ns;
     p.X = F<double>(h, DLSM_F_X); p.bvar = h->d_bvar; p.rinv0 = rinv0;
     p.partial = h->d_partial; p.own = h->d_rows_own; p.part = h->d_rows_part;
-    const dim3 grid(c.T * h->rows_chunks, c.n_chains);
-    const size_t smem = (size_t)c.n * (c.d + (h->lk == kDirected ? 1 : 0)) * sizeof(double);
+    const dim3 grid(h->rows_grid, c.n_chains);
+    const size_t smem = rows_smem(h);
 #define LAUNCH_ROWS(LK, D)                                                                                \
     do {                                                                                                  \
         CU(h, cudaFuncSetAttribute(k_rows<LK, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -602,14 +691,14 @@ int launch_rows(dlsm_handle *h, const double *rinv0)
     return DLSM_OK;
 }
 
-int rows_nblk(const dlsm_handle *h) { return h->cfg.T * h->rows_chunks; }
+int rows_nblk(const dlsm_handle *h) { return h->rows_grid; }
 
 int commit_rows(dlsm_handle *h, const int32_t *flag)
 {
     const dlsm_config &c = h->cfg;
     const int warps = c.T * h->rows_nb;
     return launch_simple(h, k_rows_commit, dim3((warps + 7) / 8, c.n_chains), dim3(256), 0, flag, c.T, c.n,
-                         h->rows_nb, h->rows_JS, h->rows_G, (const double *)h->d_rows_own,
+                         h->rows_nb, h->rows_half, h->rows_R, (const double *)h->d_rows_own,
                          (const double *)h->d_rows_part, h->d_rows);
 }
 
@@ -813,6 +902,7 @@ int dlsm_set_option(dlsm_handle *h, int option, int64_t value)
     if (value < 0) FAIL(h, DLSM_ERR_INVALID, "option values are non-negative");
     h->opt[option] = value;
     h->rows_valid = false;
+    h->cluster_cs = -1;
     if (option == DLSM_OPT_SWEEP_MODE) apply_sweep_mode(h);
     return DLSM_OK;
 }
@@ -1409,6 +1499,7 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
             if (rc != DLSM_OK) return rc;
         }
         p.rows = h->d_rows; p.scr = h->d_scr;
+        h->ctr.rowsum_sweeps += 1;
     }
     if (h->x_copy_pending) { // the previous record of X is still on its way to the host
         CU(h, cudaStreamWaitEvent(h->stream, h->ev_x_copied, 0));

@@ -1337,6 +1337,287 @@ __global__ void __launch_bounds__(576) k_sweep_slice_ws(const SweepParams p, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_sweep_slice_cl: a thread-block CLUSTER per (chain, slice) -- the single-chain mapping (cfg 3:
+// one chain, n = 2 000, T = 20, where CTA-per-slice leaves 128 of the 148 SMs idle).
+// The CS CTAs of a cluster each hold a copy of the slice's positions (+ reciprocal radii) in their
+// own shared memory and reduce 1/CS of every node's row: compute warp w of CTA r is member
+// r * NCOMP + w of a team of CS * NCOMP warps (node_loglik2's wteam / nteam).  Partial sums travel
+// through DISTRIBUTED SHARED MEMORY: lane 0 of a compute warp stores its pair into the leader
+// CTA's slot (st.shared::cluster) and arrives on the leader's mbarrier
+// (mbarrier.arrive.release.cluster); the leader's control warp waits for the phase, adds the
+// partials in team order, adds the deferred (j, j-1) dyad, decides, and broadcasts the decision:
+// the accepted position into every CTA's copy of the slice, then st.release.cluster of that CTA's
+// `decided` counter, which its compute warps poll locally (ld.acquire.cluster).  As in
+// k_sweep_slice_ws the compute warps run one node ahead of the decisions, so the DSMEM round trip
+// (~2 x 215 cycles) overlaps the next node's reduction.  The wavefront across slices still goes
+// through the L2 flags (prog[], st.release.gpu / ld.acquire.gpu), and clusters take their (chain,
+// slice) from an atomic ticket: a cluster only waits on clusters that have started.
+// Every CTA's warp 0 stages the proposals of a 32-node block redundantly (same inputs, same
+// arithmetic), so nothing but partial sums and decisions crosses the cluster.
+// grid = C*T*CS, cluster = (CS,1,1), block = 32 * (1 + NCOMP);
+// dynamic smem = n*(d [+1]) doubles + 32*(d+5) doubles + 2 * kMaxTeam * 2 doubles
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxTeam = 128; // CS * NCOMP <= 8 * 16
+
+__device__ __forceinline__ uint32_t cl_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cl_size()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cl_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t cl_map(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cl_st_f64(uint32_t addr, double v)
+{
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ int cl_ld_s32(uint32_t addr)
+{
+    int v;
+    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cl_st_release_s32(uint32_t addr, int v)
+{
+    asm volatile("st.release.cluster.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int cl_ld_acquire_local_s32(uint32_t addr)
+{
+    int v;
+    asm volatile("ld.acquire.cluster.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t}" ::"r"(addr), "r"(parity) : "memory");
+}
+
+template <int LK, int D>
+__global__ void __launch_bounds__(512, 1) k_sweep_slice_cl(const SweepParams p, int *progress_g,
+                                                           unsigned int *ticket)
+{
+    constexpr int DM = (D == 0) ? kMaxD : D;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_bar[2]; // leader: partials of node j arrive on s_bar[j & 1]
+    __shared__ int s_ticket;
+    __shared__ int s_decided; // nodes 0 .. s_decided-1 of this slice are final in THIS CTA's copy
+    const int T = p.net.T, n = p.net.n, d = (D == 0) ? p.net.d : D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int ncomp = nwarps - 1;
+    const int rank = (int)cl_rank(), CS = (int)cl_size();
+    const int nteam = CS * ncomp;
+    const bool leader = rank == 0;
+    if (threadIdx.x == 0) {
+        s_decided = 0;
+        if (leader) {
+            s_ticket = (int)atomicAdd(ticket, 1u);
+            mbar_init(smem_addr(&s_bar[0]), (uint32_t)nteam);
+            mbar_init(smem_addr(&s_bar[1]), (uint32_t)nteam);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    cl_sync();
+    const int tk = cl_ld_s32(cl_map(smem_addr(&s_ticket), 0));
+    const int c = tk / T, t = tk % T;
+    double *Xchain = p.X + (size_t)c * T * n * d;
+    double *Xg = Xchain + (size_t)t * n * d;
+    double *Xt = reinterpret_cast<double *>(smem_raw);
+    double *stage_base = Xt + (size_t)n * d;
+    const double *rinv = nullptr;
+    for (int e = threadIdx.x; e < n * d; e += blockDim.x) Xt[e] = Xg[e];
+    if (LK != kUndirected) {
+        double *s_rinv = stage_base;
+        stage_base += n;
+        const double *rg = p.rinv + (size_t)c * n;
+        for (int e = threadIdx.x; e < n; e += blockDim.x) s_rinv[e] = rg[e];
+        rinv = s_rinv;
+    }
+    double *st_prop = stage_base;
+    double *st_logu = st_prop + 32 * d, *st_nn = st_logu + 32, *st_no = st_nn + 32, *st_inv = st_no + 32;
+    int *st_zc = reinterpret_cast<int *>(st_inv + 32);
+    double *part = stage_base + sweep_stage_doubles(d); // leader: [2][kMaxTeam][2]
+    int *prog = progress_g + (size_t)c * T;
+    __syncthreads();
+
+    const double b0 = p.intercept[c * 2 + 0], b1 = p.intercept[c * 2 + 1];
+    const uint32_t chain_id = (uint32_t)c + p.chain_offset;
+    const uint32_t a_decided = smem_addr(&s_decided);
+    const uint32_t a_part0 = cl_map(smem_addr(part), 0);          // the leader's slots and barriers
+    const uint32_t a_bar0 = cl_map(smem_addr(&s_bar[0]), 0), a_bar1 = cl_map(smem_addr(&s_bar[1]), 0);
+    bool nonfinite = false;
+
+    for (int jb = 0; jb < n; jb += 32) {
+        // ---- lane-parallel preparation of the block: every CTA stages the proposals, the leader
+        //      also the sampler state, the uniforms and the "next" prior terms ----
+        const int jl = jb + lane;
+        const bool mine = (warp == 0) && (jl < n);
+        const size_t gs = ((size_t)c * T + t) * n + (jl < n ? jl : 0);
+        double my_step = 0.0;
+        int my_nacc = 0, my_nsteps = 0, my_until = 0, my_acc = 0;
+        if (mine) {
+            double eps[DM], x0[DM], x[DM], logu;
+            load_pos<DM>(Xt + (size_t)jl * d, d, x0);
+            my_step = p.step[gs];
+            if (p.eps) {
+#pragma unroll
+                for (int k = 0; k < DM; k++) eps[k] = (k < d) ? p.eps[gs * d + k] : 0.0;
+                logu = p.logu[gs];
+            } else {
+                latent_draws<DM>(p.seed, (uint32_t)(t * n + jl), p.sweep, chain_id, d, eps, logu);
+            }
+#pragma unroll
+            for (int k = 0; k < DM; k++) {
+                x[k] = (k < d) ? __dadd_rn(x0[k], __dmul_rn(my_step, eps[k])) : 0.0;
+                if (k < d) st_prop[lane * d + k] = x[k];
+            }
+            if (leader) {
+                my_nacc = p.nacc[gs]; my_nsteps = p.nsteps[gs]; my_until = p.until[gs];
+                st_logu[lane] = logu;
+                double inv = (t == 0) ? 1.0 / p.tau_sq : 1.0 / p.sigma_sq;
+                int zc = 0;
+                if (p.prior != 0) {
+                    zc = p.z[((size_t)c * T + t) * n + jl];
+                    inv = 1.0 / p.sigma[(size_t)c * p.K + zc];
+                }
+                st_inv[lane] = inv;
+                st_zc[lane] = zc;
+                double nn = 0.0, no = 0.0;
+                if (t < T - 1) {
+                    double xnx[DM];
+                    const volatile double *q = Xchain + ((size_t)(t + 1) * n + jl) * d;
+#pragma unroll
+                    for (int k = 0; k < DM; k++) xnx[k] = (k < d) ? q[k] : 0.0;
+                    nn = prior_next<DM>(p, c, t, jl, x, xnx);
+                    no = prior_next<DM>(p, c, t, jl, x0, xnx);
+                }
+                st_nn[lane] = nn;
+                st_no[lane] = no;
+            }
+        }
+        __syncthreads();
+        const int jend = (n - jb) < 32 ? (n - jb) : 32;
+        if (warp > 0) {
+            // ---------------- compute warps of every CTA: 1 / (CS * NCOMP) of each row ----------
+            const int wteam = rank * ncomp + (warp - 1);
+            for (int jj = 0; jj < jend; jj++) {
+                const int j = jb + jj;
+                while (cl_ld_acquire_local_s32(a_decided) < j - 1) { /* node j-1 is left out */ }
+                double x[DM], x0[DM];
+                load_pos<DM>(st_prop + jj * d, d, x);
+                load_pos<DM>(Xt + (size_t)j * d, d, x0);
+                double ll_new, ll_old;
+                node_loglik2<LK, DM>(p.net, Xt, rinv, c, t, j, x, x0, b0, b1, lane, ll_new, ll_old, p.flags,
+                                     wteam, nteam, j - 1);
+                if (lane == 0) {
+                    const uint32_t slot = a_part0 + (uint32_t)(((j & 1) * kMaxTeam + wteam) * 2 * sizeof(double));
+                    cl_st_f64(slot, ll_new);
+                    cl_st_f64(slot + 8, ll_old);
+                    mbar_arrive_remote((j & 1) ? a_bar1 : a_bar0); // release: the two stores come first
+                }
+                __syncwarp();
+            }
+        } else if (leader) {
+            // ---------------- control warp of the leader CTA ------------------------------------
+            for (int jj = 0; jj < jend; jj++) {
+                const int j = jb + jj;
+                double x[DM], x0[DM];
+                load_pos<DM>(st_prop + jj * d, d, x);
+                load_pos<DM>(Xt + (size_t)j * d, d, x0);
+                double tn = 0.0, to = 0.0;
+                if (j > 0) pair_term2<LK, DM>(p.net, Xt, rinv, t, j, j - 1, x, x0, b0, b1, tn, to);
+                double xp[DM];
+#pragma unroll
+                for (int k = 0; k < DM; k++) xp[k] = 0.0;
+                if (t > 0) {
+                    while (ld_acquire_gpu(prog + t - 1) <= j) { /* spin on the L2-resident flag of slice t-1 */ }
+                    const volatile double *q = Xchain + ((size_t)(t - 1) * n + j) * d;
+#pragma unroll
+                    for (int k = 0; k < DM; k++) if (k < d) xp[k] = q[k];
+                }
+                const double inv = st_inv[jj];
+                const int zc = st_zc[jj];
+                const double pr_new = prior_prev<DM>(p, c, t, zc, inv, x, xp);
+                const double pr_old = prior_prev<DM>(p, c, t, zc, inv, x0, xp);
+                mbar_wait(smem_addr(&s_bar[j & 1]), (uint32_t)((j >> 1) & 1)); // all partials of node j are in
+                double ll_new = 0.0, ll_old = 0.0;
+                const volatile double *pp = part + (size_t)(j & 1) * kMaxTeam * 2;
+                for (int w = 0; w < nteam; w++) { ll_new += pp[w * 2]; ll_old += pp[w * 2 + 1]; }
+                ll_new += tn;
+                ll_old += to;
+                double lp_new = __dsub_rn(ll_new, pr_new), lp_old = __dsub_rn(ll_old, pr_old);
+                if (t < T - 1) {
+                    lp_new = __dsub_rn(lp_new, st_nn[jj]);
+                    lp_old = __dsub_rn(lp_old, st_no[jj]);
+                }
+                const double ratio = __dsub_rn(lp_new, lp_old);
+                const int acc = (st_logu[jj] >= ratio) ? 0 : 1;
+                my_acc = (lane == jj) ? acc : my_acc;
+                nonfinite |= (lane == jj) && (!(ratio == ratio) || ratio - ratio != 0.0);
+                if (lane < CS) { // lane r publishes the decision to CTA r (lane 0: this CTA and global)
+                    if (acc) {
+                        const uint32_t xr = cl_map(smem_addr(Xt + (size_t)j * d), (uint32_t)lane);
+#pragma unroll
+                        for (int k = 0; k < DM; k++)
+                            if (k < d) cl_st_f64(xr + 8 * k, x[k]);
+                    }
+                    cl_st_release_s32(cl_map(a_decided, (uint32_t)lane), j + 1);
+                } else if (lane == CS) {
+                    if (acc) {
+#pragma unroll
+                        for (int k = 0; k < DM; k++)
+                            if (k < d) Xg[(size_t)j * d + k] = x[k];
+                    }
+                    if (p.ratio) p.ratio[((size_t)c * T + t) * n + j] = ratio;
+                    st_release_gpu(prog + t, j + 1); // releases slice t+1's node j
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (mine && leader) {
+            metropolis_bookkeep(my_step, my_nacc, my_nsteps, my_until, p.tune, p.tune_interval,
+                                my_acc, false);
+            p.step[gs] = my_step; p.nacc[gs] = my_nacc; p.nsteps[gs] = my_nsteps; p.until[gs] = my_until;
+            if (p.accepted) p.accepted[gs] = my_acc;
+        }
+        // (no cluster barrier per block: a block's step sizes are read by every CTA before any of its
+        //  partial sums can reach the leader, and written back by the leader only after all of them)
+    }
+    if (nonfinite) atomicOr(p.flags, 1u);
+    cl_sync(); // no CTA may exit while a peer can still write into its shared memory
+}
+
+// ---------------------------------------------------------------------------------------------
 // parity probe: per-node log-likelihood at the current state, one warp per (c, t, j)
 // ---------------------------------------------------------------------------------------------
 template <int LK, int D>
@@ -1737,31 +2018,28 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
 // k_rows: the full-network log-likelihood of ONE parameter variant (an intercept / radii proposal,
 // or the current state) together with its ROW SUMS rows'[j] = sum_i term(i, j), every unordered
 // pair evaluated once (exact likelihoods; feeds the row-sum cache of the sweep kernels).
-// Pairs are visited as 32 x 32 tiles (row block I, column block J >= I).  A warp owns a row block
-// and a run of JS column blocks: lane l keeps node a = 32 I + l and its row accumulator for the
-// whole run; at step s it meets node b = 32 J + (l + s) mod 32, whose column accumulator ROTATES
-// through the lanes (one 64-bit shuffle per step), so both nodes of a pair are credited from one
-// evaluation and nothing is reduced through memory or atomics: the column vector of every tile is
-// written once (part[J][I][32]), the row vector once per run (own[I][g][32]), and k_rows_commit
-// adds them in a fixed order -> the result is reproducible bit for bit.
-// grid = (T * chunks, C), block = 256 (8 items per CTA, all of one slice);
-// dynamic smem = n * (d [+ 1]) doubles
+// Pairs are visited as 32 x 32 tiles (row block I, column block J >= I).  Within a tile lane l
+// keeps node a = 32 I + l and its row accumulator; at step s it meets node b = 32 J + (l + s) mod 32,
+// whose column accumulator ROTATES through the lanes (one 64-bit shuffle per step), so both nodes
+// of a pair are credited from one evaluation and nothing is reduced through atomics: the column
+// vector of every tile is written once (part[J][I][32]), the row vectors once per run
+// (own[f][r][h][32]), and k_rows_commit adds them in a fixed order -> reproducible bit for bit.
+// Work is dealt in equal pieces: row block I is glued to row block nb-1-I (together nb + 1 tiles)
+// and the glued row is cut into R runs of <= ~17 tiles; a warp takes one run, a CTA eight
+// consecutive runs of one chain (they may span several short slices, all staged in shared memory).
+// grid = (ceil(T * ipc / 8), C), block = 256; dynamic smem = ns * n * (d [+ 1]) doubles
 // ---------------------------------------------------------------------------------------------
 struct RowsParams {
     NetView net;
-    int C, nb, JS, G, ni, chunks;  // row blocks, tiles per run, runs per row block (max), items per slice
+    int C, nb, half, R, L, ipc, ns;  // row blocks, glued rows, runs per glued row, tiles per run,
+                                     // items per slice, slices staged per CTA (max)
     const double *X;        // [C][T][n][d]
     const double *bvar;     // [C][2][2]: variant 0 is evaluated
     const double *rinv0;    // [C][n]
-    double *partial;        // [C][T*chunks][2] (slot 0)
-    double *own;            // [C][T][nb][G][32]
+    double *partial;        // [C][gridDim.x][2] (slot 0)
+    double *own;            // [C][T][half][R][2][32]
     double *part;           // [C][T][nb (nb-1) / 2][32]
 };
-
-__host__ __device__ inline int rows_runs(int nb, int JS, int I) { return (nb - I + JS - 1) / JS; }
-// row blocks are dealt in folded order 0, nb-1, 1, nb-2, ... so that consecutive items pair a long
-// row of tiles with a short one
-__host__ __device__ inline int rows_fold(int nb, int q) { return (q & 1) ? nb - 1 - (q >> 1) : (q >> 1); }
 
 template <int LK, int D>
 __global__ void __launch_bounds__(256) k_rows(const RowsParams p)
@@ -1770,53 +2048,65 @@ __global__ void __launch_bounds__(256) k_rows(const RowsParams p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[8];
     const int T = p.net.T, n = p.net.n, d = (D == 0) ? p.net.d : D, W = p.net.W, nb = p.nb;
-    const int c = blockIdx.y, t = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
+    const int c = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int items = T * p.ipc;
+    const int first = blockIdx.x * 8, last = (first + 7 < items ? first + 7 : items - 1);
+    const int t0 = first / p.ipc, t1 = last / p.ipc;
+    const int per = n * (d + (LK == kDirected ? 1 : 0)); // doubles staged per slice
     double *Xs = reinterpret_cast<double *>(smem_raw);
-    const double *Xg = p.X + ((size_t)c * T + t) * n * d;
-    for (int e = threadIdx.x; e < n * d; e += blockDim.x) Xs[e] = Xg[e];
-    const double *rv = nullptr;
-    if (LK == kDirected) {
-        double *rs = Xs + (size_t)n * d;
-        for (int e = threadIdx.x; e < n; e += blockDim.x) rs[e] = p.rinv0[(size_t)c * n + e];
-        rv = rs;
+    for (int sl = 0; sl <= t1 - t0; sl++) {
+        const double *Xg = p.X + ((size_t)c * T + t0 + sl) * n * d;
+        double *dst = Xs + (size_t)sl * per;
+        for (int e = threadIdx.x; e < n * d; e += blockDim.x) dst[e] = Xg[e];
+        if (LK == kDirected)
+            for (int e = threadIdx.x; e < n; e += blockDim.x) dst[n * d + e] = p.rinv0[(size_t)c * n + e];
     }
     __syncthreads();
     const double b0 = p.bvar[(size_t)c * 4], b1 = p.bvar[(size_t)c * 4 + 1];
     double once = 0.0; // every pair of this warp's tiles counted once
-    int item = chunk * 8 + warp, I = -1, g = 0;
-    if (item < p.ni) {
-        for (int q = 0; q < nb; q++) { // decode (row block, run) from the folded item order
-            const int Iq = rows_fold(nb, q), r = rows_runs(nb, p.JS, Iq);
-            if (item < r) { I = Iq; g = item; break; }
-            item -= r;
-        }
-    }
-    if (I >= 0) {
-        const int a = 32 * I + lane;
-        const bool va = a < n;
-        const int ac = va ? a : n - 1;
-        double xa[DM];
-        load_pos<DM>(Xs + (size_t)ac * d, d, xa);
-        const double ra = (LK == kDirected) ? rv[ac] : 0.0;
-        const uint32_t *rowa = p.net.rowbits + ((size_t)t * n + ac) * W;
-        const uint32_t *cola = (LK == kDirected) ? p.net.colbits + ((size_t)t * n + ac) * W : nullptr;
+    const int item = first + warp;
+    if (item < items) {
+        const int t = item / p.ipc, rem = item % p.ipc, f = rem / p.R, r = rem % p.R;
+        const int I1 = f, I2 = nb - 1 - f;
+        const int len1 = nb - I1;                         // tiles of row block I1: J = I1 .. nb-1
+        const int tp = (I2 == I1) ? len1 : nb + 1;        // + those of row block I2: J = I2 .. nb-1
+        const int u0 = r * p.L, u1 = (u0 + p.L < tp) ? u0 + p.L : tp;
+        const double *Xt = Xs + (size_t)(t - t0) * per;
+        const double *rv = Xt + (size_t)n * d;
         const size_t slice = (size_t)c * T + t;
         double *part_t = p.part + slice * ((size_t)nb * (nb - 1) / 2) * 32;
-        double rowacc = 0.0;
-        const int J0 = I + g * p.JS, J1 = (J0 + p.JS < nb) ? J0 + p.JS : nb;
+        double acc[2] = {0.0, 0.0};
+        int cur = -1, a = 0, ac = 0;
+        bool va = false;
+        double xa[DM], ra = 0.0;
+        const uint32_t *rowa = nullptr, *cola = nullptr;
+#pragma unroll
+        for (int k = 0; k < DM; k++) xa[k] = 0.0;
         auto pair_term = [&](int J, int bl, uint32_t wr, uint32_t wc) {
             const int b = 32 * J + bl;
             const int bc = b < n ? b : n - 1;
             double xb[DM];
-            load_pos<DM>(Xs + (size_t)bc * d, d, xb);
+            load_pos<DM>(Xt + (size_t)bc * d, d, xb);
             const double dist = fast_dist<DM>(xb, xa, d);
             if (LK == kUndirected) return logit_term(ymask(wr, bl), b0 - dist);
             const double rb = rv[bc];
             return logit_term(ymask(wr, bl), eta_directed(b0, b1, dist, rb, ra)) +  // a sends to b
                    logit_term(ymask(wc, bl), eta_directed(b0, b1, dist, ra, rb));   // b sends to a
         };
-        for (int J = J0; J < J1; J++) {
+        for (int u = u0; u < u1; u++) {
+            const int h = u >= len1 ? 1 : 0;
+            const int I = h ? I2 : I1, J = h ? I2 + (u - len1) : I1 + u;
+            if (I != cur) { // (re)load this lane's row node
+                cur = I;
+                a = 32 * I + lane;
+                va = a < n;
+                ac = va ? a : n - 1;
+                load_pos<DM>(Xt + (size_t)ac * d, d, xa);
+                if (LK == kDirected) ra = rv[ac];
+                rowa = p.net.rowbits + ((size_t)t * n + ac) * W;
+                if (LK == kDirected) cola = p.net.colbits + ((size_t)t * n + ac) * W;
+            }
             const uint32_t wr = __ldg(rowa + J);
             const uint32_t wc = (LK == kDirected) ? __ldg(cola + J) : 0u;
             double R = 0.0, tile = 0.0;
@@ -1832,7 +2122,7 @@ __global__ void __launch_bounds__(256) k_rows(const RowsParams p)
                     tile = fma(v, term, tile);
                 }
                 R = __shfl_sync(kFull, R, (lane + 16) & 31); // column accumulators back to their nodes
-                rowacc += tile + R;
+                acc[h] += tile + R;
             } else {
 #pragma unroll 4
                 for (int s = 0; s < 32; s++) {
@@ -1845,11 +2135,13 @@ __global__ void __launch_bounds__(256) k_rows(const RowsParams p)
                 }
                 R = __shfl_sync(kFull, R, (lane + 1) & 31);
                 part_t[((size_t)J * (J - 1) / 2 + I) * 32 + lane] = R;
-                rowacc += tile;
+                acc[h] += tile;
             }
             once += tile;
         }
-        p.own[((slice * nb + I) * p.G + g) * 32 + lane] = rowacc;
+        double *own = p.own + (((slice * p.half + f) * p.R + r) * 2) * 32;
+        own[lane] = acc[0];
+        own[32 + lane] = acc[1];
     }
     once = warp_sum(once);
     if (lane == 0) red[warp] = once;
@@ -1863,7 +2155,7 @@ __global__ void __launch_bounds__(256) k_rows(const RowsParams p)
 
 // rows[c][t][j] <- the row sums k_rows left in (own, part), for every chain whose flag is set
 // (flag == nullptr: all chains); one warp per (slice, row block), fixed summation order
-__global__ void __launch_bounds__(256) k_rows_commit(const int32_t *flag, int T, int n, int nb, int JS, int G,
+__global__ void __launch_bounds__(256) k_rows_commit(const int32_t *flag, int T, int n, int nb, int half, int R,
                                                      const double *own, const double *part, double *rows)
 {
     const int c = blockIdx.y, lane = threadIdx.x & 31;
@@ -1871,9 +2163,9 @@ __global__ void __launch_bounds__(256) k_rows_commit(const int32_t *flag, int T,
     if (w >= T * nb || (flag && !flag[c])) return;
     const int t = w / nb, Q = w % nb;
     const size_t slice = (size_t)c * T + t;
+    const int f = Q < nb - 1 - Q ? Q : nb - 1 - Q, h = (Q == f) ? 0 : 1;
     double s = 0.0;
-    const int runs = rows_runs(nb, JS, Q);
-    for (int g = 0; g < runs; g++) s += own[((slice * nb + Q) * G + g) * 32 + lane];
+    for (int r = 0; r < R; r++) s += own[(((slice * half + f) * R + r) * 2 + h) * 32 + lane];
     const double *pt = part + slice * ((size_t)nb * (nb - 1) / 2) * 32 + ((size_t)Q * (Q - 1) / 2) * 32;
     for (int I = 0; I < Q; I++) s += pt[(size_t)I * 32 + lane];
     const int i = 32 * Q + lane;

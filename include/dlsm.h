@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DLSM_ABI_VERSION 1
+#define DLSM_ABI_VERSION 2
 
 typedef struct dlsm_handle dlsm_handle;
 
@@ -133,7 +133,7 @@ int dlsm_synchronize(dlsm_handle *h);
  * variable that only supplies its DEFAULT, read once by dlsm_create (never on the sweep path):
  * DLSM_SWEEP_MODE=chain|chain-dense|slice|slice-plain, DLSM_FFBS=thread|warp, DLSM_FFBS_SMEM,
  * DLSM_FFBS_PER_SM=<n>, DLSM_NO_GATHER_PACK, DLSM_NO_LLCUR, DLSM_CENTER_EXACT, DLSM_HDP_SEGMENTED,
- * DLSM_NO_EARLY_X, DLSM_TRACE_CHUNK_BYTES=<bytes>, DLSM_NO_ROWSUM. */
+ * DLSM_NO_EARLY_X, DLSM_TRACE_CHUNK_BYTES=<bytes>, DLSM_NO_ROWSUM, DLSM_NO_CLUSTER. */
 typedef enum {
     DLSM_OPT_SWEEP_MODE = 0,        /* dlsm_sweep_mode: which latent-sweep kernel (default: heuristic) */
     DLSM_OPT_FFBS_KERNEL = 1,       /* dlsm_ffbs_kernel: label kernel mapping */
@@ -147,6 +147,7 @@ typedef enum {
     DLSM_OPT_TRACE_CHUNK_BYTES = 9, /* device bytes of one trace-ring chunk (0 = 512 MB or free/8) */
     DLSM_OPT_NO_ROWSUM_CACHE = 10,  /* 1: the device loop evaluates proposal AND current position of every
                                        node-update afresh instead of keeping per-node row sums */
+    DLSM_OPT_NO_CLUSTER = 11,       /* 1: never spread a (chain, slice) over a thread-block cluster */
     DLSM_OPT_COUNT_
 } dlsm_option;
 typedef enum {
@@ -292,6 +293,8 @@ typedef struct {
     double latent_ms;          /* device time in the latent sweep kernel (when timing enabled) */
     double other_ms;           /* device time in the other hot-path kernels */
     uint64_t ub_flags;         /* case-control lists that hit the reference's out-of-bounds quirk */
+    uint64_t cluster_sweeps;   /* latent sweeps served by the thread-block-cluster kernel */
+    uint64_t rowsum_sweeps;    /* latent sweeps served from the row-sum cache (proposal-only evaluation) */
 } dlsm_counters;
 int dlsm_enable_timing(dlsm_handle *h, int on); /* CUDA events around every phase */
 int dlsm_get_counters(dlsm_handle *h, dlsm_counters *out);

@@ -22,7 +22,7 @@ def test_header_and_exports_agree(lib):
     assert declared == set(_lib.EXPORTS)
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.dlsm_abi_version() == 1
+    assert lib.dlsm_abi_version() == 2
 
 
 def test_every_entry_point_cites_the_reference():

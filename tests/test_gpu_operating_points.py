@@ -86,6 +86,7 @@ def test_cfg3_full_sweep_replay_vs_oracle():
     T, n, d = w["T"], w["n"], w["d"]
     rng = np.random.RandomState(303)
     X0 = W.chain_starts(w, 1, 0)[0]
+    step = w["step_X"] / 40.0      # ~25 % acceptance at this state (the bench tunes its step the same way)
     e = L.Engine(T=T, n=n, d=d, is_directed=True, tune=4, tune_interval=2, intercept_tune_interval=(2, 2))
     e.set_network(w["Y"])
     e.set_hyper(tau_sq=w["tau_sq"], sigma_sq=w["sigma_sq"], intercept_prior=w["intercept"],
@@ -93,9 +94,9 @@ def test_cfg3_full_sweep_replay_vs_oracle():
     e.set(L.F_X, X0[None])
     e.set(L.F_INTERCEPT, w["intercept"][None])
     e.set(L.F_RADII, w["radii"][None])
-    e.set_tuner(w["step_X"])
+    e.set_tuner(step)
     Xo, ic, radii = X0.copy(), w["intercept"].copy(), w["radii"].copy()
-    tun = O.TunerState((T, n), w["step_X"], tune=4, tune_interval=2)
+    tun = O.TunerState((T, n), step, tune=4, tune_interval=2)
     itun = O.TunerState((2,), 0.1, tune=4, tune_interval=2)
     rtun = O.TunerState((1,), 175000.0, tune=None, tune_interval=100)
     for s in range(2):
@@ -123,8 +124,9 @@ def test_cfg3_full_sweep_replay_vs_oracle():
         racc, _ = e.sample_radii(prop[None], np.array([rlogu]), want_stats=True)
         assert int(racc[0]) == ro["accepted"]
         assert np.array_equal(e.get(L.F_RADII)[0], radii)
-    assert 0.02 < out["accepted"].mean() < 0.98
+    assert 0.01 < out["accepted"].mean() < 0.99
     assert np.array_equal(e.get(L.F_X_STEP)[0], tun.step)
+    assert e.counters()["cluster_sweeps"] == 2     # the thread-block-cluster kernel served this chain
 
 
 # ------------------------------------------------------------------------------------------

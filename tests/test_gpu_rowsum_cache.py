@@ -128,3 +128,53 @@ def test_device_loop_chain_is_the_two_variant_chain(T, n, d, directed, K):
             assert np.allclose(a, b, rtol=1e-11, atol=0)
         else:
             assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------
+# thread-block-cluster sweep kernel (k_sweep_slice_cl): a (chain, slice) spread over CS CTAs with
+# partial sums through distributed shared memory
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,n,d,directed", [(5, 300, 2, False), (4, 500, 2, True), (3, 257, 3, True),
+                                            (7, 1000, 2, False), (2, 2000, 2, True), (20, 640, 2, True)])
+def test_cluster_kernel_vs_oracle_and_vs_cta_per_slice(T, n, d, directed):
+    L = _L()
+    rng, X, Y = _net(T, n, d, directed, seed=11 * n + T)
+    ic = np.array([0.6, 0.35]) if directed else np.array([0.6])
+    step = 0.02 / n if directed else 0.12
+    hy = dict(tau_sq=float(np.mean(X[0] * X[0])), sigma_sq=0.001 / n) if directed else dict(tau_sq=2.0, sigma_sq=0.1)
+    engines = []
+    for no_cluster in (0, 1):
+        e, Xs, radii = _engine(T, n, d, directed, 1, X, Y, rng)
+        e.set_option(L.OPT_SWEEP_MODE, L.SWEEP_SLICE)
+        e.set_option(L.OPT_NO_CLUSTER, no_cluster)
+        engines.append(e)
+    tun = O.TunerState((T, n), step, tune=4, tune_interval=2)
+    Xo = Xs[0].copy()
+    for s in range(3):
+        eps, logu = rng.randn(1, T, n, d), np.log(rng.rand(1, T, n))
+        out = O.sweep_latent(Xo, ic, tun, eps[0], logu[0], Y=Y, radii=None if radii is None else radii[0],
+                             is_directed=directed, **hy)
+        for e in engines:
+            acc, ratio = e.sweep_latent(eps, logu, want_stats=True)
+            assert np.array_equal(acc[0], out["accepted"]), s
+            assert np.array_equal(e.get(L.F_X)[0], Xo)
+            assert np.allclose(ratio[0], out["ratio"], rtol=1e-8, atol=1e-8)
+    assert engines[0].counters()["cluster_sweeps"] == 3 and engines[1].counters()["cluster_sweeps"] == 0
+    assert np.array_equal(engines[0].get(L.F_X_STEP)[0], tun.step)
+    assert 0.03 < out["accepted"].mean() < 0.97
+
+
+def test_cluster_kernel_native_rng_chain_equals_cta_per_slice_chain():
+    L = _L()
+    T, n, d = 6, 400, 2
+    outs = []
+    for no_cluster in (0, 1):
+        rng, X, Y = _net(T, n, d, True, seed=5)
+        e, _, _ = _engine(T, n, d, True, 2, X, Y, rng, tune=500, tune_interval=3)
+        e.set_option(L.OPT_SWEEP_MODE, L.SWEEP_SLICE)
+        e.set_option(L.OPT_NO_CLUSTER, no_cluster)
+        e.run_sweeps(6)
+        outs.append([e.get(f) for f in (L.F_X, L.F_INTERCEPT, L.F_RADII)])
+        assert (e.counters()["cluster_sweeps"] > 0) == (no_cluster == 0)
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)

@@ -20,7 +20,7 @@ for wl in cfg4 cfg3 cfg5; do
   ncu -i /tmp/prof_$wl.ncu-rep --page details > gpurun_out/${TAG}_prof_${wl}_details.txt 2>/dev/null
 done
 if [ "$2" = "rows" ]; then
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_rows -s 2 -c 1 -o /tmp/prof_rows \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:^k_rows$ -s 2 -c 1 -o /tmp/prof_rows \
      python bench.py --workload cfg4 --no-others --no-e2e --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/${TAG}_prof_rows.log 2>&1
   ncu -i /tmp/prof_rows.ncu-rep --page raw --csv > gpurun_out/${TAG}_prof_rows_raw.csv 2>/dev/null
   ncu -i /tmp/prof_rows.ncu-rep --page details > gpurun_out/${TAG}_prof_rows_details.txt 2>/dev/null
