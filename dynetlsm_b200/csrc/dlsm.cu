@@ -323,7 +323,7 @@ SweepParams sweep_params(dlsm_handle *h)
 
 size_t sweep_smem(const dlsm_handle *h, bool xs)
 {
-    const size_t x = (size_t)h->cfg.T * h->cfg.n * h->cfg.d * sizeof(double);
+    const size_t x = (size_t)h->cfg.T * sweep_rows_padded(h->lk == kUndirected, h->cfg.n) * h->cfg.d * sizeof(double);
     const int warps = h->cfg.T < 16 ? h->cfg.T : 16;
     return (xs ? x : 0) + warps * sweep_stage_doubles(h->cfg.d) * sizeof(double) +
            (size_t)h->cfg.T * sizeof(int) + 16;
@@ -423,7 +423,7 @@ size_t cluster_smem(const dlsm_handle *h)
 {
     const dlsm_config &c = h->cfg;
     return (size_t)c.n * (c.d + (h->lk == kUndirected ? 0 : 1)) * sizeof(double) +
-           (sweep_stage_doubles(c.d) + 2 * (size_t)kMaxTeam * 2) * sizeof(double) + 16;
+           (sweep_stage_doubles(c.d) + 2 * (size_t)kMaxTeam * 2) * sizeof(double) + 32;
 }
 
 template <int LK, int D>
@@ -650,7 +650,7 @@ int ensure_rows(dlsm_handle *h)
     h->rows_ns = 7 / h->rows_ipc + 2;
     if (h->rows_ns > c.T) h->rows_ns = c.T;
     CU(h, cudaMalloc((void **)&h->d_rows, cells * 8));
-    CU(h, cudaMalloc((void **)&h->d_scr, cells * 8));
+    CU(h, cudaMalloc((void **)&h->d_scr, slices * sweep_rows_padded(true, c.n) * 8));
     CU(h, cudaMalloc((void **)&h->d_rows_own, slices * h->rows_half * h->rows_R * 2 * 32 * 8));
     CU(h, cudaMalloc((void **)&h->d_rows_part, (slices * ((size_t)nb * (nb - 1) / 2) * 32 + 32) * 8));
     CU(h, cudaMalloc((void **)&h->d_accflag, (size_t)c.n_chains * 4));

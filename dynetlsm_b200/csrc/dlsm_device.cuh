@@ -121,7 +121,12 @@ __device__ const double d_exp_tab[64] = {DLSM_EXP_TAB(DLSM_X)};
 __device__ const double d_expp_tab[64] = {DLSM_EXPP_TAB(DLSM_X)};
 #define DLSM_X2(r, l) {r, l},
 __device__ __align__(16) const double2 d_rl_tab[129] = {DLSM_RL_TAB(DLSM_X2)}; // {R[i], -log R[i]}
+__device__ const double d_exp32_tab[32] = {DLSM_EXP32_TAB(DLSM_X)};                     // 2^(-j/32)
+__device__ __align__(16) const double2 d_rl32_tab[33] = {DLSM_RL32_TAB(DLSM_X2)};         // {R[i], -log R[i]}, R[i] ~ 1/(1+i/32)
 #undef DLSM_X2
+static const double h_exp32_tab[32] = {DLSM_EXP32_TAB(DLSM_X)};
+static const double h_rcp32_tab[33] = {DLSM_RCP32_TAB(DLSM_X)};
+static const double h_log32_tab[33] = {DLSM_LOG32_TAB(DLSM_X)};
 static const double h_exp_tab[64] = {DLSM_EXP_TAB(DLSM_X)};
 static const double h_expp_tab[64] = {DLSM_EXPP_TAB(DLSM_X)};
 static const double h_rcp_tab[129] = {DLSM_RCP_TAB(DLSM_X)};
@@ -136,18 +141,73 @@ static const double h_log_tab[129] = {DLSM_LOG_TAB(DLSM_X)};
      1.0 / 7.0, -1.0 / 6.0, 0.2, -0.25, 1.0 / 3.0, -0.5}
 __constant__ double d_spc[16] = DLSM_SP_CONSTS;
 static const double h_spc[16] = DLSM_SP_CONSTS;
+// constants of the small-table softplus (fast_log1pexp_neg below)
+#define DLSM_SP2_CONSTS                                                                         \
+    {DLSM_NE2_OVER_LN2, 6755399441055744.0 /* 1.5*2^52 */, DLSM_LN2_OVER_NE2, 1.0,               \
+     1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5,                                       \
+     -1.0 / 8.0, 1.0 / 7.0, -1.0 / 6.0, 0.2, -0.25, 1.0 / 3.0, -0.5}
+__constant__ double d_sp2[16] = DLSM_SP2_CONSTS;
+static const double h_sp2[16] = DLSM_SP2_CONSTS;
 
 // log1p(exp(-|eta|)): the part of softplus that is left after splitting off max(eta, 0).
-// Branch-free and select-free on purpose (the sweep kernel is issue-bound, ncu profiles/r1):
-// independent evaluations in one thread interleave freely.  21 fp64 instructions, 2 table loads.
-//   t = e^{-a}:  a = n ln2/64 - r, |r| <= ln2/128;  t = 2^{-(n>>6)} 2^{-(n&63)/64} e^r   (deg 5)
-//   log1p(t):    y = 1 + t;  i = round(128 (y-1)), R = 1/(1 + i/128);  z = y R - 1, |z| <= 1/256;
-//                log y = -log R + (z - z^2/2 + ... + z^6/6)
+// Branch-free and select-free on purpose (the sweep kernels are issue- and L1-bound, ncu
+// profiles/r2a): independent evaluations in one thread interleave freely.  23 fp64 instructions and
+// two table loads whose 32 lanes touch at most 2 + 5 cache lines (256-byte and 528-byte tables; the
+// first generation, kept as _v1 below, used 512 bytes + 2 KB = 4 + 16 lines per warp and was the
+// kernel's L1 bottleneck).
+//   t = e^{-a}:  a = n ln2/32 - r, |r| <= ln2/64;  t = 2^{-(n>>5)} 2^{-(n&31)/32} e^r   (degree 6;
+//                one-step reduction: the rounding of ln2/32 costs < 4e-17 ABSOLUTE in t)
+//   log1p(t):    y = 1 + t;  i = round(32 (y-1)), R = fl(1/(1 + i/32));  z = y R - 1, |z| <= 1/64;
+//                log y = -log R + (z - z^2/2 + ... - z^8/8)
 // The rounding of y = 1 + t (<= 1.1e-16 absolute) is NOT compensated: the result is accurate to
 // ~2e-16 ABSOLUTE, which is what sums of O(1) terms need (relative accuracy in the far tail,
 // where the term is < 1e-9, is ~1e-7); tests/test_host_numerics.py.
 // n is clamped (unsigned) so that a > ~690 -- where t < 1e-300 -- cannot wrap the exponent.
 __host__ __device__ __forceinline__ double fast_log1pexp_neg(double a /* = |eta| */)
+{
+#ifdef __CUDA_ARCH__
+    const double *ET = d_exp32_tab, *K = d_sp2;
+#else
+    const double *ET = h_exp32_tab, *RT = h_rcp32_tab, *LT = h_log32_tab, *K = h_sp2;
+#endif
+    const double kf = fma(a, K[0], K[1]); // round(a * 32/ln2) lands in the low mantissa bits
+    union { double f; long long i; unsigned u[2]; } cv;
+    cv.f = kf;
+    const unsigned n = cv.u[0];
+    const double nf = kf - K[1];
+    const double r = fma(nf, K[2], -a);
+    double p = fma(r, K[4], K[5]);
+    p = fma(r, p, K[6]);
+    p = fma(r, p, K[7]);
+    p = fma(r, p, K[8]);
+    p = fma(r, p, K[3]);
+    p = fma(r, p, K[3]);
+    cv.f = p * ET[n & 31u];
+    const unsigned sh = n >> 5;
+    cv.u[1] -= (sh < 1000u ? sh : 1000u) << 20; // * 2^-(n>>5)
+    const double y = K[3] + cv.f;
+    cv.f = y;
+    unsigned i = (cv.u[1] - 0x3ff00000u + 0x4000u) >> 15; // 0..32
+    i = i < 32u ? i : 32u; // NaN / garbage never indexes out of the table
+#ifdef __CUDA_ARCH__
+    const double2 rl = __ldg(&d_rl32_tab[i]); // reciprocal and log in one 128-bit load
+    const double Ri = rl.x, Li = rl.y;
+#else
+    const double Ri = RT[i], Li = LT[i];
+#endif
+    const double z = fma(y, Ri, -K[3]);
+    double q = fma(z, K[9], K[10]);
+    q = fma(z, q, K[11]);
+    q = fma(z, q, K[12]);
+    q = fma(z, q, K[13]);
+    q = fma(z, q, K[14]);
+    q = fma(z, q, K[15]);
+    q = fma(z, q, K[3]);
+    return fma(z, q, Li);
+}
+
+// first generation (64- and 129-entry tables, degrees 5 and 6), kept for A/B measurements
+__host__ __device__ __forceinline__ double fast_log1pexp_neg_v1(double a /* = |eta| */)
 {
 #ifdef __CUDA_ARCH__
     const double *ET = d_exp_tab, *K = d_spc;

@@ -331,7 +331,9 @@ __device__ __forceinline__ double ld_cg(const double *p) { return __ldcg(p); }
 __device__ __forceinline__ void st_cg(double *p, double v) { __stcg(p, v); }
 
 // proposal-only pass: returns l_j(xn) (warp-uniform); scr[i] = term(x_i, xn) for every i != j
-template <int LK, int DM, bool INTR>
+// PAD: the slice is padded to a multiple of 128 rows with far-away dummy nodes whose adjacency bits
+// are 0 (their terms are exactly 0), so only the trip that holds the self pair needs a mask
+template <int LK, int DM, bool INTR, bool PAD = false>
 __device__ __forceinline__ double node_loglik1(const NetView &net, const double *Xt, const double *rinv,
                                                int t, int j, const double (&xn)[DM], double b0, double b1,
                                                int lane, double *scr)
@@ -347,7 +349,7 @@ __device__ __forceinline__ double node_loglik1(const NetView &net, const double 
             const int i0 = base + lane, i1 = i0 + 32, i2 = i0 + 64, i3 = i0 + 96;
             const double y0 = ymask(w.x, lane), y1 = ymask(w.y, lane), y2 = ymask(w.z, lane), y3 = ymask(w.w, lane);
             double xa[DM], xb[DM], xc[DM], xd[DM];
-            if (INTR && base + 128 <= n && (unsigned)(j - base) >= 128u) { // interior trip: no masks
+            if ((PAD || (INTR && base + 128 <= n)) && (unsigned)(j - base) >= 128u) { // interior trip: no masks
                 load_pos<DM>(Xt + (size_t)i0 * d, d, xa);
                 load_pos<DM>(Xt + (size_t)i1 * d, d, xb);
                 load_pos<DM>(Xt + (size_t)i2 * d, d, xc);
@@ -360,22 +362,22 @@ __device__ __forceinline__ double node_loglik1(const NetView &net, const double 
                 a0 += t0; a1 += t1; a2 += t2; a3 += t3;
                 continue;
             }
-            load_pos<DM>(Xt + (size_t)(i0 < n ? i0 : n - 1) * d, d, xa);
-            load_pos<DM>(Xt + (size_t)(i1 < n ? i1 : n - 1) * d, d, xb);
-            load_pos<DM>(Xt + (size_t)(i2 < n ? i2 : n - 1) * d, d, xc);
-            load_pos<DM>(Xt + (size_t)(i3 < n ? i3 : n - 1) * d, d, xd);
+            load_pos<DM>(Xt + (size_t)((PAD || i0 < n) ? i0 : n - 1) * d, d, xa);
+            load_pos<DM>(Xt + (size_t)((PAD || i1 < n) ? i1 : n - 1) * d, d, xb);
+            load_pos<DM>(Xt + (size_t)((PAD || i2 < n) ? i2 : n - 1) * d, d, xc);
+            load_pos<DM>(Xt + (size_t)((PAD || i3 < n) ? i3 : n - 1) * d, d, xd);
             const double t0 = logit_term(y0, b0 - fast_dist<DM>(xa, xn, d));
             const double t1 = logit_term(y1, b0 - fast_dist<DM>(xb, xn, d));
             const double t2 = logit_term(y2, b0 - fast_dist<DM>(xc, xn, d));
             const double t3 = logit_term(y3, b0 - fast_dist<DM>(xd, xn, d));
-            if (i0 < n) st_cg(scr + i0, t0);
-            if (i1 < n) st_cg(scr + i1, t1);
-            if (i2 < n) st_cg(scr + i2, t2);
-            if (i3 < n) st_cg(scr + i3, t3);
-            a0 = fma(vmask((i0 < n) && (i0 != j)), t0, a0);
-            a1 = fma(vmask((i1 < n) && (i1 != j)), t1, a1);
-            a2 = fma(vmask((i2 < n) && (i2 != j)), t2, a2);
-            a3 = fma(vmask((i3 < n) && (i3 != j)), t3, a3);
+            if (PAD || i0 < n) st_cg(scr + i0, t0);
+            if (PAD || i1 < n) st_cg(scr + i1, t1);
+            if (PAD || i2 < n) st_cg(scr + i2, t2);
+            if (PAD || i3 < n) st_cg(scr + i3, t3);
+            a0 = fma(vmask((PAD || i0 < n) && (i0 != j)), t0, a0);
+            a1 = fma(vmask((PAD || i1 < n) && (i1 != j)), t1, a1);
+            a2 = fma(vmask((PAD || i2 < n) && (i2 != j)), t2, a2);
+            a3 = fma(vmask((PAD || i3 < n) && (i3 != j)), t3, a3);
         }
         return warp_sum((a0 + a1) + (a2 + a3));
     } else {
@@ -537,6 +539,9 @@ __device__ __forceinline__ double prior_prev(const SweepParams &p, int c, int t,
 
 // per-warp staging area of one 32-node block (shared memory)
 __host__ __device__ inline size_t sweep_stage_doubles(int d) { return (size_t)32 * (d + 5); }
+// rows per slice of the chain kernel's shared-memory copy (padding: see k_sweep)
+__host__ __device__ inline int sweep_rows_padded(bool pad, int n) { return pad ? ((n + 127) & ~127) : n; }
+constexpr double kFarAway = 1.0e6; // coordinate of the padding nodes: exp(-|beta - dist|) underflows to 0
 
 // ---------------------------------------------------------------------------------------------
 // k_sweep: one latent-position sweep of every chain.
@@ -564,10 +569,17 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
     double *Xg = p.X + (size_t)c * chain_elems;
     double *Xc;
     double *stage_base;
+    // rows per slice as laid out in Xc: undirected chains in shared memory are padded to a multiple of
+    // 128 rows with far-away dummy nodes (no adjacency bits, terms exactly 0), see node_loglik1<PAD>
+    const int ns = sweep_rows_padded(XS && LK == kUndirected, n);
     if (XS) {
         Xc = reinterpret_cast<double *>(smem_raw);
-        stage_base = Xc + chain_elems;
-        for (size_t e = threadIdx.x; e < chain_elems; e += blockDim.x) Xc[e] = Xg[e];
+        stage_base = Xc + (size_t)T * ns * d;
+        const int per = ns * d;
+        for (int e = threadIdx.x; e < T * per; e += blockDim.x) {
+            const int tt = e / per, r = e - tt * per;
+            Xc[e] = (r < n * d) ? Xg[(size_t)tt * n * d + r] : kFarAway;
+        }
     } else {
         Xc = Xg;
         stage_base = reinterpret_cast<double *>(smem_raw);
@@ -588,10 +600,11 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
     bool nonfinite = false;
 
     double full_acc = 0.0; // lower-triangle terms of this warp's slices at the kept states
+    constexpr bool kPad = XS && LK == kUndirected;
     for (int t = warp; t < T; t += nwarps) {
-        double *Xt = Xc + (size_t)t * n * d;
+        double *Xt = Xc + (size_t)t * ns * d;
         double *rows_t = RS ? p.rows + ((size_t)c * T + t) * n : nullptr; // row-sum cache of this slice
-        double *scr_t = RS ? p.scr + ((size_t)c * T + t) * n : nullptr;
+        double *scr_t = RS ? p.scr + ((size_t)c * T + t) * sweep_rows_padded(true, n) : nullptr;
         for (int jb = 0; jb < n; jb += 32) {
             // ---------------- lane-parallel preparation for node jl = jb + lane ----------------
             const int jl = jb + lane;
@@ -628,7 +641,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
                 double nn = 0.0, no = 0.0;
                 if (t < T - 1) { // X[t+1, jl] is still last sweep's value: slice t+1 trails this one
                     double xnx[DM];
-                    const volatile double *q = Xc + ((size_t)(t + 1) * n + jl) * d;
+                    const volatile double *q = Xc + ((size_t)(t + 1) * ns + jl) * d;
 #pragma unroll
                     for (int k = 0; k < DM; k++) xnx[k] = (k < d) ? q[k] : 0.0;
                     nn = prior_next<DM>(p, c, t, jl, x, xnx);
@@ -656,7 +669,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
                 if (RS && LK != kCaseControl) {
                     // proposal only; the current position's sum comes from the row-sum cache
                     ll_old = ld_cg(rows_t + j);
-                    ll_new = node_loglik1<LK == kCaseControl ? kDirected : LK, DM, (MAXT == 320 && MINB == 2)>(
+                    ll_new = node_loglik1<LK == kCaseControl ? kDirected : LK, DM, (MAXT == 320 && MINB == 2), kPad>(
                         p.net, Xt, rinv, t, j, x, b0, b1, lane, scr_t);
                 } else if (LK != kCaseControl)
                     node_loglik2<LK, DM, true, (MAXT == 320 && MINB == 2)>(p.net, Xt, rinv, c, t, j, x, x0, b0,
@@ -672,7 +685,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
                 if (t > 0) { // wavefront: X[t-1, j] must be this sweep's value (uniform poll)
                     while (progress[t - 1] <= j) { __nanosleep(DLSM_SPIN_NS); } /* poll shared memory, yielding issue slots */
                     __threadfence_block();
-                    const volatile double *q = Xc + ((size_t)(t - 1) * n + j) * d;
+                    const volatile double *q = Xc + ((size_t)(t - 1) * ns + j) * d;
 #pragma unroll
                     for (int k = 0; k < DM; k++) if (k < d) xp[k] = q[k];
                 }
@@ -741,16 +754,23 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep(const SweepParams p)
             // serial per-column accumulation = numpy's order, bit-identical to k_center
             double *mean = stage_base; // the staging area is free now
             if ((int)threadIdx.x < d) {
-                const size_t rows = (size_t)T * n;
                 double sacc = 0.0;
-                for (size_t r = 0; r < rows; r++) sacc = __dadd_rn(sacc, Xc[r * d + threadIdx.x]);
-                mean[threadIdx.x] = __ddiv_rn(sacc, (double)rows);
+                for (int tt = 0; tt < T; tt++) {
+                    const double *Xr = Xc + (size_t)tt * ns * d + threadIdx.x;
+                    for (int r = 0; r < n; r++) sacc = __dadd_rn(sacc, Xr[(size_t)r * d]);
+                }
+                mean[threadIdx.x] = __ddiv_rn(sacc, (double)((size_t)T * n));
             }
             __syncthreads();
-            for (size_t e = threadIdx.x; e < chain_elems; e += blockDim.x)
-                Xg[e] = __dsub_rn(Xc[e], mean[e % d]);
+            for (int e = threadIdx.x; e < T * n * d; e += blockDim.x) {
+                const int tt = e / (n * d), r = e - tt * (n * d);
+                Xg[e] = __dsub_rn(Xc[(size_t)tt * ns * d + r], mean[r % d]);
+            }
         } else {
-            for (size_t e = threadIdx.x; e < chain_elems; e += blockDim.x) Xg[e] = Xc[e];
+            for (int e = threadIdx.x; e < T * n * d; e += blockDim.x) {
+                const int tt = e / (n * d), r = e - tt * (n * d);
+                Xg[e] = Xc[(size_t)tt * ns * d + r];
+            }
         }
     }
 }
@@ -1174,7 +1194,7 @@ __global__ void __launch_bounds__(576) k_sweep_slice_ws(const SweepParams p, int
         for (int e = threadIdx.x; e < n * d; e += blockDim.x) Xt[e] = Xg[e];
         if (LK != kUndirected) {
             double *s_rinv = stage_base;
-            stage_base += n;
+            stage_base += (n + 1) & ~1; // keep the stage 16-byte aligned (double2 loads)
             for (int e = threadIdx.x; e < n; e += blockDim.x) s_rinv[e] = rinv[e];
             rinv = s_rinv;
         }
@@ -1452,12 +1472,12 @@ __global__ void __launch_bounds__(512, 1) k_sweep_slice_cl(const SweepParams p, 
     double *Xchain = p.X + (size_t)c * T * n * d;
     double *Xg = Xchain + (size_t)t * n * d;
     double *Xt = reinterpret_cast<double *>(smem_raw);
-    double *stage_base = Xt + (size_t)n * d;
+    double *stage_base = Xt + (((size_t)n * d + 1) & ~(size_t)1);
     const double *rinv = nullptr;
     for (int e = threadIdx.x; e < n * d; e += blockDim.x) Xt[e] = Xg[e];
     if (LK != kUndirected) {
         double *s_rinv = stage_base;
-        stage_base += n;
+        stage_base += (n + 1) & ~1; // keep the stage 16-byte aligned (double2 loads)
         const double *rg = p.rinv + (size_t)c * n;
         for (int e = threadIdx.x; e < n; e += blockDim.x) s_rinv[e] = rg[e];
         rinv = s_rinv;

@@ -9,7 +9,7 @@ NCCL, gloo on CPU in the tests).
 """
 import numpy as np
 
-__all__ = ["autocorr", "ess", "split_rhat", "geweke_z", "pool_traces", "summarize"]
+__all__ = ["autocorr", "ess", "split_rhat", "geweke_z", "geweke_zp", "pool_traces", "summarize"]
 
 
 def autocorr(x):
@@ -78,6 +78,13 @@ def geweke_z(x, n_burn=0, first=0.1, last=0.5):
         return acov[0] + 2 * np.sum((1 - np.arange(1, L + 1) / (L + 1)) * acov[1:])
     den = s0(a) / a.size + s0(b) / b.size
     return float((a.mean() - b.mean()) / np.sqrt(den)) if den > 0 else float("nan")
+
+
+def geweke_zp(x, n_burn=0, first=0.1, last=0.5):
+    """(z, two-sided p-value) as the reference's ``geweke_diag`` returns them (trace_utils.py:59-115)."""
+    from math import erfc, sqrt
+    z = geweke_z(x, n_burn, first, last)
+    return z, (erfc(abs(z) / sqrt(2.0)) if z == z else float("nan"))
 
 
 def pool_traces(local, group=None):

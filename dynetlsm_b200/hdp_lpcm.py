@@ -10,11 +10,14 @@ chain reproduces the reference's.  With ``sampler='device'`` (default) that bloc
 log-posterior and the stored samples are produced on the device as well (``dlsm_hdp_update``,
 ``dlsm_run_traced``) and ``fit`` makes no host round trip per sweep.
 
-Post-processing that the reference delegates to its ``model_selection`` package (approximate BIC,
-posterior-expected VI) is outside the accelerated path: ``selection_type`` is accepted, and the
-reported point estimate is the maximum-a-posteriori draw after burn-in; co-clustering
-probabilities, posterior means and the Procrustes alignment of the traces are computed as in the
-reference (hdp_lpcm.py:1141-1153, label_utils.py:40-62).
+The point estimate follows the reference's ``selection_type`` (hdp_lpcm.py:1089-1138): 'vi'
+(default) minimises the posterior-expected variation of information over the co-clustering
+probabilities -- which the device accumulates while sampling --, 'bic' / 'map' go through the
+approximate BIC per model size (``model_selection.py``; the network log-likelihoods it needs are
+evaluated by the device kernels).  ``bic_``, ``models_``, ``counts_``, ``best_k_``,
+``posterior_group_ids_`` / ``posterior_group_counts_``, co-clustering probabilities, posterior
+means and the Procrustes alignment of the traces are produced as in the reference
+(hdp_lpcm.py:1085-1170, label_utils.py:40-82).
 """
 import numpy as np
 from sklearn.utils import check_array, check_random_state
@@ -24,6 +27,7 @@ from .case_control_likelihood import DirectedCaseControlSampler
 from .hdp_updates import HDPHyper, conjugate_updates, hdp_log_prior
 from .host_init import longitudinal_kmeans, longitudinal_procrustes_rotation
 from .lsm import DynamicNetworkLSM, _Driver, _FittedNetworkMixin
+from . import model_selection as MS
 
 __all__ = ["DynamicNetworkHDPLPCM"]
 
@@ -53,6 +57,8 @@ class DynamicNetworkHDPLPCM(_FittedNetworkMixin):
         replay = self.sampler == "replay"
         if self.sampler not in ("device", "replay"):
             raise ValueError("`sampler` must be 'device' or 'replay', got {}".format(self.sampler))
+        if self.selection_type not in ("vi", "bic", "map"):
+            raise ValueError("Selection type not recognized")       # hdp_lpcm.py:1122
         T, n, _ = Y.shape
         K, d = self.n_components, self.n_features
         rng = check_random_state(self.random_state)
@@ -284,25 +290,6 @@ class DynamicNetworkHDPLPCM(_FittedNetworkMixin):
         nb = min(self.n_burn_, self.Xs_.shape[0] - 1)
         T, n = self.Y_fit_.shape[:2]
         K = self.n_components
-        best = nb + int(np.argmax(self.logps_[nb:]))
-        self.selected_id_ = best
-        self.logp_ = self.logps_[best]
-        self.X_ = self.Xs_[best].copy()
-        self.intercept_ = self.intercepts_[best]
-        self.lambda_ = self.lambdas_[best]
-        if self.is_directed:
-            self.radii_ = self.radiis_[best]
-        # relabel to the active components and renormalise their weights (label_utils.py:10-37)
-        active, z = np.unique(self.zs_[best].ravel(), return_inverse=True)
-        self.z_ = z.reshape(T, n)
-        self.beta_ = self.betas_[best, active] / self.betas_[best, active].sum()
-        w = self.weights_[best]
-        self.init_weights_ = w[0, 0, active] / w[0, 0, active].sum()
-        self.trans_weights_ = np.zeros((T, active.size, active.size))
-        for t in range(1, T):
-            sub = w[t, active][:, active]
-            self.trans_weights_[t] = sub / np.sum(sub, axis=1).reshape(-1, 1)
-        self.mu_, self.sigma_ = self.mus_[best, active], self.sigmas_[best, active]
         # co-clustering probabilities over the post-burn-in draws (label_utils.py:40-62)
         self.cooccurrence_probas_ = np.zeros((T, n, n))
         dev = getattr(self, "_device_cooc", None)
@@ -316,21 +303,64 @@ class DynamicNetworkHDPLPCM(_FittedNetworkMixin):
                 flat = ind.transpose(1, 0, 2).reshape(n, -1)     # (n, S' K): one GEMM per time step
                 self.cooccurrence_probas_[t] = (flat @ flat.T).astype(np.float64) / ind.shape[0]
         self._device_cooc = None
-        self.counts_ = np.array([np.unique(zz).size for zz in self.zs_[nb:]])
+
+        # model sizes and their approximate BIC (hdp_lpcm.py:1089-1090), then the point estimate
+        loglik = MS._device_loglik(self)
+        try:
+            self.bic_, self.models_, self.counts_ = MS.select_bic(self, loglik)
+            if self.selection_type == "vi":
+                best = MS.minimize_posterior_expected_vi(self, loglik)
+        finally:
+            loglik.engine.close()
+        if self.selection_type == "vi":
+            self.selected_id_ = best
+            self.logp_ = self.logps_[best]
+            self.X_ = self.Xs_[best]
+            self.intercept_ = self.intercepts_[best]
+            self.lambda_ = self.lambdas_[best]
+            if self.is_directed:
+                self.radii_ = self.radiis_[best]
+            (self.z_, self.beta_, self.init_weights_, self.trans_weights_, self.mu_,
+             self.sigma_) = MS.renormalized(self, best)
+        else:
+            if self.selection_type == "bic":
+                mid = int(np.argmin(self.bic_[:, 1]))
+                self.best_k_ = int(self.bic_[mid, 0])
+            else:                                               # 'map': the most frequent model size
+                self.best_k_ = int(np.argmax(np.bincount(self.counts_)))
+                mid = int(np.argwhere(self.bic_[:, 0] == self.best_k_)[0, 0])
+            mk = self.models_[mid]
+            self.selected_id_ = int(self.bic_[mid, 3])
+            self.logp_ = self.logps_[self.selected_id_]
+            self.X_, self.intercept_, self.mu_, self.sigma_ = mk.X, mk.intercept, mk.mu, mk.sigma
+            if self.is_directed:
+                self.radii_ = mk.radii
+            self.z_ = np.unique(mk.z.ravel(), return_inverse=True)[1].reshape(T, n)
+            self.beta_, self.init_weights_, self.trans_weights_ = mk.beta, mk.init_weights, mk.trans_weights
+            self.lambda_ = mk.lmbda
         # rotate every stored sample onto the point estimate (hdp_lpcm.py:1141-1146)
+        ref = self.X_.copy()
         for idx in range(self.Xs_.shape[0]):
-            self.Xs_[idx], R = longitudinal_procrustes_rotation(self.X_, self.Xs_[idx])
+            self.Xs_[idx], R = longitudinal_procrustes_rotation(ref, self.Xs_[idx])
             self.mus_[idx] = np.dot(self.mus_[idx], R)
         self.X_mean_ = self.Xs_[nb:].mean(axis=0)
         self.lambda_mean_ = self.lambdas_[nb:].mean(axis=0)
         self.intercepts_mean_ = self.intercepts_[nb:].mean(axis=0)
         if self.is_directed:
             self.radii_mean_ = self.radiis_[nb:].mean(axis=0)
-        from .diagnostics import geweke_z
-        self.logp_geweke_ = geweke_z(self.logps_, nb)
-        self.lambda_geweke_ = geweke_z(self.lambdas_[:, 0], nb)
+        # posterior distribution of the number of groups per time step (hdp_lpcm.py:1161-1167)
+        ct = MS.cluster_counts_t(self.zs_[nb:], K)
+        self.posterior_group_ids_, self.posterior_group_counts_ = [], []
+        for t in range(T):
+            ids, freq = MS.posterior_group_counts(ct[t])
+            self.posterior_group_ids_.append(ids)
+            self.posterior_group_counts_.append(freq)
+        # Geweke diagnostics as (z, p) pairs (hdp_lpcm.py:1169-1185, trace_utils.py:59-115)
+        from .diagnostics import geweke_zp
+        self.logp_geweke_ = geweke_zp(self.logps_, nb)
+        self.lambda_geweke_ = geweke_zp(self.lambdas_[:, 0], nb)
         if self.is_directed:
-            self.intercept_in_geweke_ = geweke_z(self.intercepts_[:, 0], nb)
-            self.intercept_out_geweke_ = geweke_z(self.intercepts_[:, 1], nb)
+            self.intercept_in_geweke_ = geweke_zp(self.intercepts_[:, 0], nb)
+            self.intercept_out_geweke_ = geweke_zp(self.intercepts_[:, 1], nb)
         else:
-            self.intercept_geweke_ = geweke_z(self.intercepts_[:, 0], nb)
+            self.intercept_geweke_ = geweke_zp(self.intercepts_[:, 0], nb)
