@@ -11,13 +11,18 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "libdlsm.so")
-SRC = [os.path.join(HERE, "csrc", f) for f in ("dlsm.cu", "dlsm_kernels.cuh", "dlsm_device.cuh",
-                                              "dlsm_tables.cuh", "dlsm_hdp.cuh", "dlsm_trace.cuh")]
-SRC.append(os.path.join(ROOT, "include", "dlsm.h"))
+LIB_PATH = os.environ.get("DLSM_LIB") or os.path.join(HERE, "libdlsm.so")   # DLSM_LIB: A/B builds (tools/)
+CSRC = os.path.join(HERE, "csrc")
+# translation units -> the headers each depends on (mtime-based rebuild of the unit's object file)
+HEADERS = [os.path.join(CSRC, f) for f in ("dlsm_kernels.cuh", "dlsm_device.cuh", "dlsm_tables.cuh",
+                                            "dlsm_hdp.cuh", "dlsm_trace.cuh", "dlsm_blk.h")]
+HEADERS.append(os.path.join(ROOT, "include", "dlsm.h"))
+UNITS = [os.path.join(CSRC, "dlsm.cu"), os.path.join(CSRC, "dlsm_blk.cu")]
+SRC = UNITS + HEADERS
+OBJ_DIR = os.path.join(HERE, "build")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
 
 
 class DlsmError(RuntimeError):
@@ -27,13 +32,23 @@ class DlsmError(RuntimeError):
 
 
 def build(force=False, verbose=False):
-    """Compile libdlsm.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    if (not force and os.path.exists(LIB_PATH) and
-            all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in SRC)):
-        return LIB_PATH
+    """Compile libdlsm.so in-tree for sm_100a (nvcc cross-compiles without a GPU): one object file
+    per translation unit, compiled concurrently, rebuilt only when the unit or a header changed."""
+    newest_hdr = max(os.path.getmtime(s) for s in HEADERS)
+    os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SRC[0]]
-    subprocess.check_call(cmd)
+    procs, objs = [], []
+    for u in UNITS:
+        o = os.path.join(OBJ_DIR, os.path.basename(u)[:-3] + ".o")
+        objs.append(o)
+        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(u), newest_hdr):
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", o, u]
+            procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+    if procs or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(o) for o in objs):
+        subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs)
     return LIB_PATH
 
 

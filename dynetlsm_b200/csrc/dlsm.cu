@@ -4,6 +4,7 @@
 #include "dlsm_kernels.cuh"
 #include "dlsm_hdp.cuh"
 #include "dlsm_trace.cuh"
+#include "dlsm_blk.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -66,8 +67,9 @@ struct dlsm_handle {
     int32_t *d_accflag = nullptr;
     bool rows_valid = false;
     int rows_nb = 0, rows_half = 0, rows_R = 1, rows_L = 0, rows_ipc = 0, rows_ns = 1, rows_grid = 1;
-    int cluster_cs = -1;            // CTAs per (chain, slice) cluster of k_sweep_slice_cl (-1: not probed, 0: none)
-    int cluster_ncomp = 0;
+    int cluster_cs = -1;            // CTAs per (chain, slice) cluster (-1: not probed, 0: none)
+    int cluster_ncomp = 0;          // compute warps per CTA (per-node cluster kernel) / warps per CTA (block kernel)
+    bool cluster_blk = false;       // block-speculative kernel (k_sweep_blk) rather than the per-node one
     // developer options (dlsm_set_option; environment defaults are read ONCE, in dlsm_create)
     int64_t opt[DLSM_OPT_COUNT_] = {0};
     // rng
@@ -267,7 +269,7 @@ void read_env_options(dlsm_handle *h)
     h->opt[DLSM_OPT_HDP_SEGMENTED] = on("DLSM_HDP_SEGMENTED");
     h->opt[DLSM_OPT_NO_EARLY_X] = on("DLSM_NO_EARLY_X");
     h->opt[DLSM_OPT_NO_ROWSUM_CACHE] = on("DLSM_NO_ROWSUM");
-    h->opt[DLSM_OPT_NO_CLUSTER] = on("DLSM_NO_CLUSTER");
+    if (const char *m = getenv("DLSM_NO_CLUSTER")) h->opt[DLSM_OPT_NO_CLUSTER] = atoll(m) > 0 ? atoll(m) : 1;
     if (const char *m = getenv("DLSM_TRACE_CHUNK_BYTES")) h->opt[DLSM_OPT_TRACE_CHUNK_BYTES] = atoll(m);
     apply_sweep_mode(h);
 }
@@ -466,22 +468,34 @@ int cluster_dispatch(dlsm_handle *h, const SweepParams *p, int CS, int ncomp, in
 }
 
 // CTAs per cluster: the largest size whose C*T clusters can all be resident (they form a wavefront
-// over the slices), so that one chain spreads over as many SMs as the part has; 0 = not applicable
+// over the slices), so that one chain spreads over as many SMs as the part has; 0 = not applicable.
+// DLSM_OPT_NO_CLUSTER: 0 block-speculative kernel (k_sweep_blk), 1 no clusters, 2 per-node kernel.
 int cluster_size(dlsm_handle *h)
 {
     if (h->cluster_cs >= 0) return h->cluster_cs;
     h->cluster_cs = 0;
     const dlsm_config &c = h->cfg;
     const int CT = c.n_chains * c.T;
-    if (h->lk == kCaseControl || h->no_pipeline || h->opt[DLSM_OPT_NO_CLUSTER] || CT * 2 > h->sm_count ||
-        cluster_smem(h) > kMaxSmem)
+    const int64_t mode = h->opt[DLSM_OPT_NO_CLUSTER];
+    if (h->lk == kCaseControl || h->no_pipeline || mode == 1 || CT * 2 > h->sm_count) return 0;
+    h->cluster_blk = mode != 2;
+    if (h->cluster_blk ? blk_smem_bytes(c.n, c.d, h->lk == kDirected, h->W) > kMaxSmem : cluster_smem(h) > kMaxSmem)
         return 0;
     const int chunks = (c.n + (h->lk == kUndirected ? 63 : 31)) / (h->lk == kUndirected ? 64 : 32);
     for (int CS = h->sm_count / CT < 8 ? h->sm_count / CT : 8; CS >= 2; CS--) {
-        int ncomp = (chunks + CS - 1) / CS;
-        ncomp = ncomp < 1 ? 1 : (ncomp > 15 ? 15 : ncomp);
-        int active = 0;
-        if (cluster_dispatch(h, nullptr, CS, ncomp, &active) != DLSM_OK) { cudaGetLastError(); continue; }
+        int ncomp, active = 0;
+        if (h->cluster_blk) {
+            ncomp = 16; // 16 warps per CTA: CS * 16 <= 128 column shares
+            SweepParams p = sweep_params(h);
+            if (blk_launch(p, h->lk == kDirected, CS, ncomp, nullptr, nullptr, h->stream, &active) != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+        } else {
+            ncomp = (chunks + CS - 1) / CS;
+            ncomp = ncomp < 1 ? 1 : (ncomp > 15 ? 15 : ncomp);
+            if (cluster_dispatch(h, nullptr, CS, ncomp, &active) != DLSM_OK) { cudaGetLastError(); continue; }
+        }
         if (active >= CT) {
             h->cluster_cs = CS;
             h->cluster_ncomp = ncomp;
@@ -522,7 +536,10 @@ int launch_slice_lk(dlsm_handle *h, const SweepParams &p)
     if (LK == kCaseControl && !h->no_pipeline) return launch_cc_batch(h, p);
     if (LK != kCaseControl && cluster_size(h) >= 2) {
         h->ctr.cluster_sweeps += 1;
-        return cluster_dispatch(h, &p, h->cluster_cs, h->cluster_ncomp, nullptr);
+        if (!h->cluster_blk) return cluster_dispatch(h, &p, h->cluster_cs, h->cluster_ncomp, nullptr);
+        CU(h, blk_launch(p, LK == kDirected, h->cluster_cs, h->cluster_ncomp, h->d_progress, h->d_ticket,
+                         h->stream, nullptr));
+        return DLSM_OK;
     }
     const int nw = slice_warps(h);
     const bool xs = slice_smem(h, true, nw + 1) + 4096 <= kMaxSmem / 2;
@@ -626,7 +643,7 @@ size_t rows_smem(const dlsm_handle *h)
 {
     const dlsm_config &c = h->cfg;
     const int ns = 7 / (((c.n + 31) / 32 + 1) / 2 * (((c.n + 31) / 32 + 1 + 16) / 17)) + 2;
-    return (size_t)(ns < c.T ? ns : c.T) * c.n * (c.d + (h->lk == kDirected ? 1 : 0)) * sizeof(double);
+    return (size_t)(ns < c.T ? ns : c.T) * (((size_t)c.n * (c.d + (h->lk == kDirected ? 1 : 0)) + 1) & ~(size_t)1) * sizeof(double);
 }
 
 bool rows_enabled(const dlsm_handle *h)
@@ -900,6 +917,7 @@ int dlsm_set_option(dlsm_handle *h, int option, int64_t value)
     if (option == DLSM_OPT_FFBS_KERNEL && (value < DLSM_FFBS_AUTO || value > DLSM_FFBS_WARP))
         FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_FFBS_KERNEL takes a dlsm_ffbs_kernel value");
     if (value < 0) FAIL(h, DLSM_ERR_INVALID, "option values are non-negative");
+    if (option == DLSM_OPT_NO_CLUSTER && value > 2) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_NO_CLUSTER takes 0, 1 or 2");
     h->opt[option] = value;
     h->rows_valid = false;
     h->cluster_cs = -1;

@@ -117,12 +117,12 @@ __device__ __forceinline__ double log1pexp_naive(double eta) { return log(1.0 + 
 // relative parity bound on the summed log-likelihoods.
 // ---------------------------------------------------------------------------------------------
 #define DLSM_X(v) v,
-__device__ const double d_exp_tab[64] = {DLSM_EXP_TAB(DLSM_X)};
-__device__ const double d_expp_tab[64] = {DLSM_EXPP_TAB(DLSM_X)};
+static __device__ const double d_exp_tab[64] = {DLSM_EXP_TAB(DLSM_X)};
+static __device__ const double d_expp_tab[64] = {DLSM_EXPP_TAB(DLSM_X)};
 #define DLSM_X2(r, l) {r, l},
-__device__ __align__(16) const double2 d_rl_tab[129] = {DLSM_RL_TAB(DLSM_X2)}; // {R[i], -log R[i]}
-__device__ const double d_exp32_tab[32] = {DLSM_EXP32_TAB(DLSM_X)};                     // 2^(-j/32)
-__device__ __align__(16) const double2 d_rl32_tab[33] = {DLSM_RL32_TAB(DLSM_X2)};         // {R[i], -log R[i]}, R[i] ~ 1/(1+i/32)
+static __device__ __align__(16) const double2 d_rl_tab[129] = {DLSM_RL_TAB(DLSM_X2)}; // {R[i], -log R[i]}
+static __device__ const double d_exp32_tab[32] = {DLSM_EXP32_TAB(DLSM_X)};                     // 2^(-j/32)
+static __device__ __align__(16) const double2 d_rl32_tab[33] = {DLSM_RL32_TAB(DLSM_X2)};         // {R[i], -log R[i]}, R[i] ~ 1/(1+i/32)
 #undef DLSM_X2
 static const double h_exp32_tab[32] = {DLSM_EXP32_TAB(DLSM_X)};
 static const double h_rcp32_tab[33] = {DLSM_RCP32_TAB(DLSM_X)};
@@ -139,14 +139,14 @@ static const double h_log_tab[129] = {DLSM_LOG_TAB(DLSM_X)};
     {DLSM_32_OVER_LN2, 6755399441055744.0 /* 1.5*2^52 */, DLSM_LN2_32_HI, DLSM_LN2_32_LO,        \
      1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0,                                  \
      1.0 / 7.0, -1.0 / 6.0, 0.2, -0.25, 1.0 / 3.0, -0.5}
-__constant__ double d_spc[16] = DLSM_SP_CONSTS;
+static __constant__ double d_spc[16] = DLSM_SP_CONSTS;
 static const double h_spc[16] = DLSM_SP_CONSTS;
 // constants of the small-table softplus (fast_log1pexp_neg below)
 #define DLSM_SP2_CONSTS                                                                         \
     {DLSM_NE2_OVER_LN2, 6755399441055744.0 /* 1.5*2^52 */, DLSM_LN2_OVER_NE2, 1.0,               \
      1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5,                                       \
      -1.0 / 8.0, 1.0 / 7.0, -1.0 / 6.0, 0.2, -0.25, 1.0 / 3.0, -0.5}
-__constant__ double d_sp2[16] = DLSM_SP2_CONSTS;
+static __constant__ double d_sp2[16] = DLSM_SP2_CONSTS;
 static const double h_sp2[16] = DLSM_SP2_CONSTS;
 
 // log1p(exp(-|eta|)): the part of softplus that is left after splitting off max(eta, 0).
@@ -251,10 +251,15 @@ __host__ __device__ __forceinline__ double fast_log1pexp_neg_v1(double a /* = |e
 // log(1 + e^eta) = max(eta, 0) + log1p(e^{-|eta|}); max(eta,0) = (eta + |eta|)/2 keeps NaN alive.
 // |abs error| < 1e-15 everywhere, relative error < 1e-15 in the negative tail
 // (tests/test_host_numerics.py).
+#ifdef DLSM_SOFTPLUS_V1 // A/B builds: the first-generation (large-table) evaluation everywhere
+#define DLSM_L1PEN fast_log1pexp_neg_v1
+#else
+#define DLSM_L1PEN fast_log1pexp_neg
+#endif
 __host__ __device__ __forceinline__ double fast_log1pexp(double eta)
 {
     const double a = fabs(eta);
-    return fma(0.5, a, 0.5 * eta) + fast_log1pexp_neg(a);
+    return fma(0.5, a, 0.5 * eta) + DLSM_L1PEN(a);
 }
 
 // One Bernoulli-logit term  y*eta - log(1 + e^eta)  with y in {0,1} passed as ym = y - 1/2:
@@ -263,7 +268,7 @@ __host__ __device__ __forceinline__ double fast_log1pexp(double eta)
 __host__ __device__ __forceinline__ double logit_term(double ym, double eta)
 {
     const double a = fabs(eta);
-    return fma(ym, eta, fma(-0.5, a, -fast_log1pexp_neg(a)));
+    return fma(ym, eta, fma(-0.5, a, -DLSM_L1PEN(a)));
 }
 
 // Branch-free fp64 exp(x) on the same tables (relative error < 1e-15 for |x| < 700; flushes to 0

@@ -963,7 +963,7 @@ __global__ void __launch_bounds__(512) k_sweep_slice(const SweepParams p, int *p
 // nodes long, so one CTA per (chain, slice) runs a warp per node of the batch instead of a team per
 // node: the sweep is the same Markov transition, ~10x faster.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cc_deps(NetView net, int sets, int32_t *dep)
+static __global__ void __launch_bounds__(256) k_cc_deps(NetView net, int sets, int32_t *dep)
 {
     const int lane = threadIdx.x & 31;
     const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1679,7 +1679,7 @@ __global__ void k_debug_draws(const SweepParams p, double *eps_out, double *logu
 // ---------------------------------------------------------------------------------------------
 // X -= np.mean(X, axis=(0,1))  (lsm.py:501): serial accumulation per column = numpy's order
 // ---------------------------------------------------------------------------------------------
-__global__ void k_center(double *X, int T, int n, int d)
+static __global__ void k_center(double *X, int T, int n, int d)
 {
     __shared__ double mean[kMaxD];
     double *Xc = X + (size_t)blockIdx.x * T * n * d;
@@ -1710,7 +1710,7 @@ __global__ void k_center(double *X, int T, int n, int d)
 //                        bounded by the serial DADD chain (~8 cycles per row), not by load latency
 //   k_center_mean_tree   device loop only: per-(chain, block) partial sums + a fixed-order total;
 //                        deterministic, but not numpy's rounding
-__global__ void __launch_bounds__(256) k_center_mean_exact(const double *X, int T, int n, int d, double *means)
+static __global__ void __launch_bounds__(256) k_center_mean_exact(const double *X, int T, int n, int d, double *means)
 {
     __shared__ double buf[2048 * kMaxD / 4]; // 2048 rows at d = 2, 512 rows at d = 8
     const double *Xc = X + (size_t)blockIdx.x * T * n * d;
@@ -1740,7 +1740,7 @@ __global__ void __launch_bounds__(256) k_center_mean_exact(const double *X, int 
 __device__ __forceinline__ double block_sum(double v, double *sh);
 
 // grid (B, C): partial[c][b][k] = sum over the rows of block b
-__global__ void __launch_bounds__(256) k_center_partial(const double *X, int T, int n, int d, double *partial)
+static __global__ void __launch_bounds__(256) k_center_partial(const double *X, int T, int n, int d, double *partial)
 {
     __shared__ double sh[8];
     const int B = gridDim.x, b = blockIdx.x, c = blockIdx.y;
@@ -1760,7 +1760,7 @@ __global__ void __launch_bounds__(256) k_center_partial(const double *X, int T, 
     }
 }
 
-__global__ void k_center_total(const double *partial, int B, int d, double rows, double *means)
+static __global__ void k_center_total(const double *partial, int B, int d, double rows, double *means)
 {
     const int c = blockIdx.x, k = threadIdx.x;
     if (k >= d) return;
@@ -1770,7 +1770,7 @@ __global__ void k_center_total(const double *partial, int B, int d, double rows,
 }
 
 // grid (B, C): X -= mean (exactly rounded subtraction, as numpy's in-place -=)
-__global__ void __launch_bounds__(256) k_center_apply(double *X, int T, int n, int d, const double *means)
+static __global__ void __launch_bounds__(256) k_center_apply(double *X, int T, int n, int d, const double *means)
 {
     __shared__ double mean[kMaxD];
     const int c = blockIdx.y;
@@ -1782,7 +1782,7 @@ __global__ void __launch_bounds__(256) k_center_apply(double *X, int T, int n, i
         Xc[e] = __dsub_rn(Xc[e], mean[e % d]);
 }
 
-__global__ void k_rinv(const double *radii, double *rinv, size_t total)
+static __global__ void k_rinv(const double *radii, double *rinv, size_t total)
 {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g < total) rinv[g] = 1.0 / radii[g];
@@ -1792,7 +1792,7 @@ __global__ void k_rinv(const double *radii, double *rinv, size_t total)
 // adjacency bit-packing from the dense fp64 Y the reference's fit() takes (lsm.py:319-343)
 // one warp per 32-column word, ballot over the lanes; bad[0] set if an entry is not 0/1
 // ---------------------------------------------------------------------------------------------
-__global__ void k_pack_rows(const double *Y, int n, int W, uint32_t *bits, int *bad)
+static __global__ void k_pack_rows(const double *Y, int n, int W, uint32_t *bits, int *bad)
 {
     // Y: one time slice [n][n]; bits [n][W]
     const size_t gw = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1807,7 +1807,7 @@ __global__ void k_pack_rows(const double *Y, int n, int W, uint32_t *bits, int *
     if (lane == 0) bits[(size_t)i * W + w] = word;
 }
 
-__global__ void k_pack_cols(const double *Y, int n, int W, uint32_t *bits)
+static __global__ void k_pack_cols(const double *Y, int n, int W, uint32_t *bits)
 {
     // bits[i][w] bit b = Y[w*32+b][i]; thread per (w, i) with i fastest (coalesced reads)
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1846,7 +1846,7 @@ __device__ __forceinline__ void ld256(const double *p, double &a, double &b, dou
 }
 
 // G[c][t][j] = {X[c,t,j,0], X[c,t,j,1], rinv[c,j], 0}
-__global__ void k_pack_gather(const double *X, const double *rinv, double *G, int C, int T, int n)
+static __global__ void k_pack_gather(const double *X, const double *rinv, double *G, int C, int T, int n)
 {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t total = (size_t)C * T * n;
@@ -2073,7 +2073,7 @@ __global__ void __launch_bounds__(256) k_rows(const RowsParams p)
     const int items = T * p.ipc;
     const int first = blockIdx.x * 8, last = (first + 7 < items ? first + 7 : items - 1);
     const int t0 = first / p.ipc, t1 = last / p.ipc;
-    const int per = n * (d + (LK == kDirected ? 1 : 0)); // doubles staged per slice
+    const int per = (n * (d + (LK == kDirected ? 1 : 0)) + 1) & ~1; // doubles staged per slice (16-byte aligned)
     double *Xs = reinterpret_cast<double *>(smem_raw);
     for (int sl = 0; sl <= t1 - t0; sl++) {
         const double *Xg = p.X + ((size_t)c * T + t0 + sl) * n * d;
@@ -2175,7 +2175,7 @@ __global__ void __launch_bounds__(256) k_rows(const RowsParams p)
 
 // rows[c][t][j] <- the row sums k_rows left in (own, part), for every chain whose flag is set
 // (flag == nullptr: all chains); one warp per (slice, row block), fixed summation order
-__global__ void __launch_bounds__(256) k_rows_commit(const int32_t *flag, int T, int n, int nb, int half, int R,
+static __global__ void __launch_bounds__(256) k_rows_commit(const int32_t *flag, int T, int n, int nb, int half, int R,
                                                      const double *own, const double *part, double *rows)
 {
     const int c = blockIdx.y, lane = threadIdx.x & 31;
@@ -2217,7 +2217,7 @@ struct ScalarMH {
     int32_t *accflag;        // optional [C]: this step's decision (k_rows_commit reads it)
 };
 
-__global__ void k_intercept_propose(const ScalarMH p)
+static __global__ void k_intercept_propose(const ScalarMH p)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= p.C) return;
@@ -2239,7 +2239,7 @@ __global__ void k_intercept_propose(const ScalarMH p)
     bv[2] = b0; bv[3] = b1;                                       // variant 1: current
 }
 
-__global__ void k_intercept_finalize(const ScalarMH p)
+static __global__ void k_intercept_finalize(const ScalarMH p)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= p.C) return;
@@ -2274,7 +2274,7 @@ __global__ void k_intercept_finalize(const ScalarMH p)
 }
 
 // current-state probe: bvar = current intercepts for both variants
-__global__ void k_bvar_current(int C, const double *intercept, double *bvar)
+static __global__ void k_bvar_current(int C, const double *intercept, double *bvar)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -2282,7 +2282,7 @@ __global__ void k_bvar_current(int C, const double *intercept, double *bvar)
     bvar[c * 4 + 1] = bvar[c * 4 + 3] = intercept[c * 2 + 1];
 }
 
-__global__ void k_sum_partials(int C, int nblk, const double *partial, double *out2, double *out_first = nullptr)
+static __global__ void k_sum_partials(int C, int nblk, const double *partial, double *out2, double *out_first = nullptr)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -2326,7 +2326,7 @@ __device__ __forceinline__ double block_sum(double v, double *sh)
     return s;
 }
 
-__global__ void __launch_bounds__(256) k_radii_finalize(const RadiiMH p)
+static __global__ void __launch_bounds__(256) k_radii_finalize(const RadiiMH p)
 {
     __shared__ double sh[8];
     __shared__ int s_acc;
@@ -2401,7 +2401,7 @@ __device__ inline double gamma_mt(double shape, uint64_t seed, uint32_t site, ui
     return boost * dd;
 }
 
-__global__ void __launch_bounds__(256) k_radii_propose(int n, const double *radii,
+static __global__ void __launch_bounds__(256) k_radii_propose(int n, const double *radii,
                                                        const double *step, double *prop,
                                                        double *prop_rinv, uint64_t seed,
                                                        uint32_t sweep, uint32_t chain_offset,
@@ -2480,7 +2480,7 @@ __device__ inline double np_sum_k(const double *a, int n)
     return res;
 }
 
-__global__ void __launch_bounds__(128) k_ffbs(const LabelParams p)
+static __global__ void __launch_bounds__(128) k_ffbs(const LabelParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = p.T, n = p.n, d = p.d, K = p.K;

@@ -147,7 +147,9 @@ typedef enum {
     DLSM_OPT_TRACE_CHUNK_BYTES = 9, /* device bytes of one trace-ring chunk (0 = 512 MB or free/8) */
     DLSM_OPT_NO_ROWSUM_CACHE = 10,  /* 1: the device loop evaluates proposal AND current position of every
                                        node-update afresh instead of keeping per-node row sums */
-    DLSM_OPT_NO_CLUSTER = 11,       /* 1: never spread a (chain, slice) over a thread-block cluster */
+    DLSM_OPT_NO_CLUSTER = 11,       /* few (chain, slice) pairs, long rows: 0 = block-speculative sweep on a
+                                       thread-block cluster per pair (k_sweep_blk), 1 = no clusters (CTA per
+                                       pair), 2 = per-node cluster kernel (k_sweep_slice_cl) */
     DLSM_OPT_COUNT_
 } dlsm_option;
 typedef enum {
