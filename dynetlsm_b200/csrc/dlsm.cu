@@ -269,6 +269,9 @@ void read_env_options(dlsm_handle *h)
     h->opt[DLSM_OPT_HDP_SEGMENTED] = on("DLSM_HDP_SEGMENTED");
     h->opt[DLSM_OPT_NO_EARLY_X] = on("DLSM_NO_EARLY_X");
     h->opt[DLSM_OPT_NO_ROWSUM_CACHE] = on("DLSM_NO_ROWSUM");
+    if (const char *m = getenv("DLSM_CHAIN_KERNEL"))
+        h->opt[DLSM_OPT_CHAIN_KERNEL] = !strcmp(m, "block") ? DLSM_CHAIN_BLOCK
+                                        : !strcmp(m, "node") ? DLSM_CHAIN_NODE : DLSM_CHAIN_NODE_ROWSUM;
     if (const char *m = getenv("DLSM_NO_CLUSTER")) h->opt[DLSM_OPT_NO_CLUSTER] = atoll(m) > 0 ? atoll(m) : 1;
     if (const char *m = getenv("DLSM_TRACE_CHUNK_BYTES")) h->opt[DLSM_OPT_TRACE_CHUNK_BYTES] = atoll(m);
     apply_sweep_mode(h);
@@ -557,6 +560,12 @@ bool use_slice_kernel(const dlsm_handle *h)
     return h->cfg.n >= 256 && warps_chain_mode < (size_t)h->sm_count * 16;
 }
 
+// which kernel serves the one-CTA-per-chain mapping (exact likelihoods): DLSM_OPT_CHAIN_KERNEL
+bool chain_blk(const dlsm_handle *h)
+{
+    return h->lk != kCaseControl && h->opt[DLSM_OPT_CHAIN_KERNEL] == DLSM_CHAIN_BLOCK;
+}
+
 int launch_sweep(dlsm_handle *h, const SweepParams &p)
 {
     begin_phase(h, 0);
@@ -565,6 +574,11 @@ int launch_sweep(dlsm_handle *h, const SweepParams &p)
         if (h->lk == kUndirected) rc = launch_slice_lk<kUndirected>(h, p);
         else if (h->lk == kDirected) rc = launch_slice_lk<kDirected>(h, p);
         else rc = launch_slice_lk<kCaseControl>(h, p);
+    } else if (chain_blk(h)) {
+        // block-speculative chain kernel (k_sweep_cb): 32 nodes per step, lanes = rows
+        cudaError_t ce = cb_launch(p, h->lk == kDirected, h->stream);
+        if (ce != cudaSuccess) { end_phase(h); CU(h, ce); }
+        rc = DLSM_OK;
     } else {
         if (h->lk == kUndirected) rc = launch_sweep_lk<kUndirected>(h, p);
         else if (h->lk == kDirected) rc = launch_sweep_lk<kDirected>(h, p);
@@ -649,6 +663,7 @@ size_t rows_smem(const dlsm_handle *h)
 bool rows_enabled(const dlsm_handle *h)
 {
     return h->lk != kCaseControl && !use_slice_kernel(h) && !h->opt[DLSM_OPT_NO_ROWSUM_CACHE] &&
+           h->opt[DLSM_OPT_CHAIN_KERNEL] == DLSM_CHAIN_NODE_ROWSUM &&
            !h->opt[DLSM_OPT_NO_TRACKED_LOGLIK] && rows_smem(h) <= kMaxSmem;
 }
 
@@ -918,6 +933,7 @@ int dlsm_set_option(dlsm_handle *h, int option, int64_t value)
         FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_FFBS_KERNEL takes a dlsm_ffbs_kernel value");
     if (value < 0) FAIL(h, DLSM_ERR_INVALID, "option values are non-negative");
     if (option == DLSM_OPT_NO_CLUSTER && value > 2) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_NO_CLUSTER takes 0, 1 or 2");
+    if (option == DLSM_OPT_CHAIN_KERNEL && value > DLSM_CHAIN_BLOCK) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_CHAIN_KERNEL takes a dlsm_chain_kernel value");
     h->opt[option] = value;
     h->rows_valid = false;
     h->cluster_cs = -1;

@@ -360,6 +360,271 @@ __global__ void __launch_bounds__(512, 1) k_sweep_blk(const SweepParams p, int *
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_sweep_cb: the block-speculative sweep for MANY chains -- one CTA per chain, one warp per time
+// slice (the mapping of k_sweep), 32 nodes per step instead of one.
+// Lane l of the slice's warp is row node j = jb + l.  The warp walks ALL columns i of the slice
+// once per block: x_i is a broadcast shared-memory load, the adjacency bit comes from the lane's
+// own bit-row (one 128-bit load per 128 columns), both MH evaluations D(x_i, x'_j), D(x_i, x_j)
+// accumulate in the lane -- no warp reductions, no masks, no clamped indices.  The block's own 32
+// columns enter at their OLD positions; the nodes are then resolved in order by the same warp:
+// lane j decides from its sums, and an accepted node pushes (new - old) terms to the lanes behind
+// it (4 dyads per lane per accepted node).  Same decisions as the node-by-node sweep (sums differ
+// in order only); the wavefront over the slices advances a block at a time.
+// The full-network log-likelihood of the state the sweep leaves behind is tracked as in k_sweep:
+// the sums over the columns i < j of the kept variant (lo_*), added up over all node-updates.
+// grid = C, block = 32 * min(T, 16); dynamic smem = [T*n*d doubles] + nwarps * 32*d doubles + T ints
+// ---------------------------------------------------------------------------------------------
+template <int LK, int D, bool XS, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_sweep_cb(const SweepParams p)
+{
+    constexpr int DM = (D == 0) ? kMaxD : D;
+    constexpr bool kDir = LK != kUndirected;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = p.net.T, n = p.net.n, d = (D == 0) ? p.net.d : D, W = p.net.W;
+    const int c = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const size_t chain_elems = (size_t)T * n * d;
+    double *Xg = p.X + (size_t)c * chain_elems;
+    double *Xc, *stage_base;
+    if (XS) {
+        Xc = reinterpret_cast<double *>(smem_raw);
+        stage_base = Xc + ((chain_elems + 1) & ~(size_t)1);
+        for (size_t e = threadIdx.x; e < chain_elems; e += blockDim.x) Xc[e] = Xg[e];
+    } else {
+        Xc = Xg;
+        stage_base = reinterpret_cast<double *>(smem_raw);
+    }
+    double *st_prop = stage_base + (size_t)warp * 32 * d;
+    volatile int *progress = reinterpret_cast<volatile int *>(stage_base + (size_t)nwarps * 32 * d);
+    for (int t = threadIdx.x; t < T; t += blockDim.x) progress[t] = 0;
+    __syncthreads();
+
+    const double b0 = p.intercept[c * 2 + 0], b1 = p.intercept[c * 2 + 1];
+    const double *rinv = kDir ? p.rinv + (size_t)c * n : nullptr;
+    const uint32_t chain_id = (uint32_t)c + p.chain_offset;
+    bool nonfinite = false;
+    double full_acc = 0.0;
+
+    for (int t = warp; t < T; t += nwarps) {
+        double *Xt = Xc + (size_t)t * n * d;
+        for (int jb = 0; jb < n; jb += 32) {
+            const int jend = (n - jb) < 32 ? (n - jb) : 32;
+            const bool vrow = lane < jend;
+            const int jl = vrow ? jb + lane : jb;
+            const size_t gs = ((size_t)c * T + t) * n + jl;
+            // ---- lane-parallel preparation ----
+            double xn[DM], xo[DM], logu = 0.0, inv = 0.0, nn = 0.0, no = 0.0;
+            double my_step = p.step[gs];
+            int my_nacc = p.nacc[gs], my_nsteps = p.nsteps[gs], my_until = p.until[gs], zc = 0;
+            load_pos<DM>(Xt + (size_t)jl * d, d, xo);
+            {
+                double eps[DM];
+                if (p.eps) {
+#pragma unroll
+                    for (int k = 0; k < DM; k++) eps[k] = (k < d) ? p.eps[gs * d + k] : 0.0;
+                    logu = p.logu[gs];
+                } else {
+                    latent_draws<DM>(p.seed, (uint32_t)(t * n + jl), p.sweep, chain_id, d, eps, logu);
+                }
+#pragma unroll
+                for (int k = 0; k < DM; k++) {
+                    xn[k] = (k < d) ? __dadd_rn(xo[k], __dmul_rn(my_step, eps[k])) : 0.0;
+                    if (k < d) st_prop[lane * d + k] = xn[k];
+                }
+                inv = (t == 0) ? 1.0 / p.tau_sq : 1.0 / p.sigma_sq;
+                if (p.prior != 0) {
+                    zc = p.z[((size_t)c * T + t) * n + jl];
+                    inv = 1.0 / p.sigma[(size_t)c * p.K + zc];
+                }
+                if (t < T - 1) { // X[t+1, j] is still last sweep's value: slice t+1 trails this one
+                    double xnx[DM];
+                    const volatile double *q = Xc + ((size_t)(t + 1) * n + jl) * d;
+#pragma unroll
+                    for (int k = 0; k < DM; k++) xnx[k] = (k < d) ? q[k] : 0.0;
+                    nn = prior_next<DM>(p, c, t, jl, xn, xnx);
+                    no = prior_next<DM>(p, c, t, jl, xo, xnx);
+                }
+            }
+            __syncwarp();
+            // ---- all columns of the slice: sums over i < jb (lo) and i >= jb + 32 (hi) ----
+            const double rj = kDir ? rinv[jl] : 0.0;
+            const uint32_t *rowb = p.net.rowbits + ((size_t)t * n + jl) * W;
+            const uint32_t *colb = kDir ? p.net.colbits + ((size_t)t * n + jl) * W : nullptr;
+            double lo_n = 0.0, lo_o = 0.0, hi_n = 0.0, hi_o = 0.0;
+            uint32_t wrb = 0, wcb = 0; // the block's own word
+            auto column = [&](int i, uint32_t wr, uint32_t wc, double &an, double &ao) {
+                double xi[DM];
+                load_pos<DM>(Xt + (size_t)i * d, d, xi);
+                const double ri = kDir ? __ldg(rinv + i) : 0.0;
+                const double yr = ymask(wr, i & 31), yc = ymask(wc, i & 31);
+                an += dyad<LK, DM>(xi, ri, xn, rj, yr, yc, b0, b1, d);
+                ao += dyad<LK, DM>(xi, ri, xo, rj, yr, yc, b0, b1, d);
+            };
+            for (int w4 = 0; w4 * 32 < n; w4 += 4) {
+                const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(rowb + w4));
+                uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
+                if (kDir) c4 = __ldg(reinterpret_cast<const uint4 *>(colb + w4));
+                const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w}, cw[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int base = (w4 + k) * 32;
+                    if (base >= n) break;
+                    if (base == jb) { wrb = rw[k]; wcb = cw[k]; continue; }
+                    const int cnt = (n - base) < 32 ? (n - base) : 32;
+                    double a_n = 0.0, a_o = 0.0, b_n = 0.0, b_o = 0.0;
+                    int ii = 0;
+                    for (; ii + 1 < cnt; ii += 2) { // two columns per trip: four independent chains
+                        column(base + ii, rw[k], cw[k], a_n, a_o);
+                        column(base + ii + 1, rw[k], cw[k], b_n, b_o);
+                    }
+                    if (ii < cnt) column(base + ii, rw[k], cw[k], a_n, a_o);
+                    if (base < jb) { lo_n += a_n + b_n; lo_o += a_o + b_o; }
+                    else { hi_n += a_n + b_n; hi_o += a_o + b_o; }
+                }
+            }
+            // the block's own columns at their old positions: below the row -> lo, above -> hi
+            for (int ic = 0; ic < jend; ic++) {
+                double tn = 0.0, to = 0.0;
+                column(jb + ic, wrb, wcb, tn, to);
+                if (ic < lane) { lo_n += tn; lo_o += to; }
+                else if (ic > lane) { hi_n += tn; hi_o += to; }
+            }
+            // ---- wavefront: the whole block of slice t-1 must be final ----
+            double xp[DM];
+#pragma unroll
+            for (int k = 0; k < DM; k++) xp[k] = 0.0;
+            if (t > 0) {
+                while (progress[t - 1] < jb + jend) { __nanosleep(DLSM_SPIN_NS); }
+                __threadfence_block();
+                const volatile double *q = Xc + ((size_t)(t - 1) * n + jl) * d;
+#pragma unroll
+                for (int k = 0; k < DM; k++) if (k < d) xp[k] = q[k];
+            }
+            const double pr_n = prior_prev<DM>(p, c, t, zc, inv, xn, xp);
+            const double pr_o = prior_prev<DM>(p, c, t, zc, inv, xo, xp);
+            // ---- resolve the block's nodes in order ----
+            unsigned mask = 0u;
+            double my_ratio = 0.0;
+            for (int jj = 0; jj < jend; jj++) {
+                int acc = 0;
+                if (lane == jj) {
+                    double lp_new = __dsub_rn(lo_n + hi_n, pr_n), lp_old = __dsub_rn(lo_o + hi_o, pr_o);
+                    if (t < T - 1) {
+                        lp_new = __dsub_rn(lp_new, nn);
+                        lp_old = __dsub_rn(lp_old, no);
+                    }
+                    my_ratio = __dsub_rn(lp_new, lp_old);
+                    acc = (logu >= my_ratio) ? 0 : 1; // metropolis.py:50 (NaN accepts)
+                    nonfinite |= !(my_ratio == my_ratio) || my_ratio - my_ratio != 0.0;
+                    full_acc += acc ? lo_n : lo_o; // dyads {i < j} at the kept state
+                }
+                acc = __shfl_sync(kFull, acc, jj);
+                if (acc) { // the rows behind trade node jj's old terms for its new ones (it is below them)
+                    mask |= 1u << jj;
+                    double xin[DM], xio[DM];
+                    load_pos<DM>(st_prop + jj * d, d, xin);
+                    load_pos<DM>(Xt + (size_t)(jb + jj) * d, d, xio);
+                    const double ri = kDir ? __ldg(rinv + jb + jj) : 0.0;
+                    const double yr = ymask(wrb, jj), yc = ymask(wcb, jj);
+                    const double dn = dyad<LK, DM>(xin, ri, xn, rj, yr, yc, b0, b1, d) -
+                                      dyad<LK, DM>(xio, ri, xn, rj, yr, yc, b0, b1, d);
+                    const double dd = dyad<LK, DM>(xin, ri, xo, rj, yr, yc, b0, b1, d) -
+                                      dyad<LK, DM>(xio, ri, xo, rj, yr, yc, b0, b1, d);
+                    if (lane > jj) { lo_n += dn; lo_o += dd; }
+                }
+            }
+            // ---- commit, bookkeeping ----
+            const int my_acc = (mask >> lane) & 1u;
+            if (vrow) {
+                if (my_acc) {
+#pragma unroll
+                    for (int k = 0; k < DM; k++) if (k < d) Xt[(size_t)jl * d + k] = xn[k];
+                }
+                if (p.ratio) p.ratio[gs] = my_ratio;
+                if (p.accepted) p.accepted[gs] = my_acc;
+                metropolis_bookkeep(my_step, my_nacc, my_nsteps, my_until, p.tune, p.tune_interval, my_acc, false);
+                p.step[gs] = my_step; p.nacc[gs] = my_nacc; p.nsteps[gs] = my_nsteps; p.until[gs] = my_until;
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) progress[t] = jb + jend;
+            __syncwarp();
+        }
+    }
+    if (nonfinite) atomicOr(p.flags, 1u);
+    if (p.ll_cur) { // full-network log-likelihood of the post-sweep state, summed in warp order
+        full_acc = warp_sum(full_acc);
+        __syncthreads();
+        double *wsum = stage_base;
+        if (lane == 0) wsum[warp] = full_acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double sacc = 0.0;
+            for (int w = 0; w < nwarps; w++) sacc += wsum[w];
+            p.ll_cur[c] = sacc;
+        }
+    }
+    if (XS) {
+        __syncthreads();
+        if (p.fuse_center) { // X -= mean(X, axis=(0,1)), numpy's serial order (bit-identical to k_center)
+            double *mean = stage_base;
+            __syncthreads();
+            if ((int)threadIdx.x < d) {
+                const size_t rows = (size_t)T * n;
+                double sacc = 0.0;
+                for (size_t r = 0; r < rows; r++) sacc = __dadd_rn(sacc, Xc[r * d + threadIdx.x]);
+                mean[threadIdx.x] = __ddiv_rn(sacc, (double)rows);
+            }
+            __syncthreads();
+            for (size_t e = threadIdx.x; e < chain_elems; e += blockDim.x) Xg[e] = __dsub_rn(Xc[e], mean[e % d]);
+        } else {
+            for (size_t e = threadIdx.x; e < chain_elems; e += blockDim.x) Xg[e] = Xc[e];
+        }
+    }
+}
+
+size_t cb_smem_bytes(int T, int n, int d, bool xs)
+{
+    const int warps = T < 16 ? T : 16;
+    const size_t x = (((size_t)T * n * d + 1) & ~(size_t)1) * sizeof(double);
+    return (xs ? x : 0) + (size_t)warps * 32 * d * sizeof(double) + (size_t)T * sizeof(int) + 64;
+}
+
+template <int LK, int D, bool XS, int MAXT, int MINB>
+static cudaError_t cb_launch_t(const SweepParams &p, int warps, cudaStream_t stream)
+{
+    const size_t smem = cb_smem_bytes(p.net.T, p.net.n, p.net.d, XS);
+    auto kern = k_sweep_cb<LK, D, XS, MAXT, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<p.C, warps * 32, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int LK, int D, bool XS>
+static cudaError_t cb_launch_x(const SweepParams &p, int ctas_per_sm_by_smem, cudaStream_t stream)
+{
+    const int warps = p.net.T < 16 ? p.net.T : 16;
+    if (warps <= 9 && ctas_per_sm_by_smem >= 3) return cb_launch_t<LK, D, XS, 288, 3>(p, warps, stream);
+    if (warps <= 10 && ctas_per_sm_by_smem >= 2) return cb_launch_t<LK, D, XS, 320, 2>(p, warps, stream);
+    return cb_launch_t<LK, D, XS, 512, 1>(p, warps, stream);
+}
+
+cudaError_t cb_launch(const SweepParams &p, bool directed, cudaStream_t stream)
+{
+    const size_t max_smem = 227 * 1024;
+    const bool xs = cb_smem_bytes(p.net.T, p.net.n, p.net.d, true) <= max_smem;
+    int per_sm = (int)(max_smem / (cb_smem_bytes(p.net.T, p.net.n, p.net.d, xs) + 1024));
+    if (p.C <= 148) per_sm = 1; // at most one chain per SM: all the registers
+    const bool d2 = p.net.d == 2;
+#define CB(LK)                                                                                     \
+    (d2 ? (xs ? cb_launch_x<LK, 2, true>(p, per_sm, stream) : cb_launch_x<LK, 2, false>(p, per_sm, stream)) \
+        : (xs ? cb_launch_x<LK, 0, true>(p, per_sm, stream) : cb_launch_x<LK, 0, false>(p, per_sm, stream)))
+    return directed ? CB(kDirected) : CB(kUndirected);
+#undef CB
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 size_t blk_smem_bytes(int n, int d, bool directed, int W)

@@ -133,7 +133,8 @@ int dlsm_synchronize(dlsm_handle *h);
  * variable that only supplies its DEFAULT, read once by dlsm_create (never on the sweep path):
  * DLSM_SWEEP_MODE=chain|chain-dense|slice|slice-plain, DLSM_FFBS=thread|warp, DLSM_FFBS_SMEM,
  * DLSM_FFBS_PER_SM=<n>, DLSM_NO_GATHER_PACK, DLSM_NO_LLCUR, DLSM_CENTER_EXACT, DLSM_HDP_SEGMENTED,
- * DLSM_NO_EARLY_X, DLSM_TRACE_CHUNK_BYTES=<bytes>, DLSM_NO_ROWSUM, DLSM_NO_CLUSTER. */
+ * DLSM_NO_EARLY_X, DLSM_TRACE_CHUNK_BYTES=<bytes>, DLSM_NO_ROWSUM, DLSM_NO_CLUSTER=1|2,
+ * DLSM_CHAIN_KERNEL=rowsum|node|block. */
 typedef enum {
     DLSM_OPT_SWEEP_MODE = 0,        /* dlsm_sweep_mode: which latent-sweep kernel (default: heuristic) */
     DLSM_OPT_FFBS_KERNEL = 1,       /* dlsm_ffbs_kernel: label kernel mapping */
@@ -150,6 +151,7 @@ typedef enum {
     DLSM_OPT_NO_CLUSTER = 11,       /* few (chain, slice) pairs, long rows: 0 = block-speculative sweep on a
                                        thread-block cluster per pair (k_sweep_blk), 1 = no clusters (CTA per
                                        pair), 2 = per-node cluster kernel (k_sweep_slice_cl) */
+    DLSM_OPT_CHAIN_KERNEL = 12,     /* dlsm_chain_kernel: the one-CTA-per-chain sweep kernel (exact likelihoods) */
     DLSM_OPT_COUNT_
 } dlsm_option;
 typedef enum {
@@ -157,6 +159,11 @@ typedef enum {
     DLSM_SWEEP_SLICE_PLAIN = 4
 } dlsm_sweep_mode;
 typedef enum { DLSM_FFBS_AUTO = 0, DLSM_FFBS_THREAD = 1, DLSM_FFBS_WARP = 2 } dlsm_ffbs_kernel;
+typedef enum {
+    DLSM_CHAIN_NODE_ROWSUM = 0, /* node by node; the device loop evaluates proposals only (row-sum cache) */
+    DLSM_CHAIN_NODE = 1,        /* node by node, proposal and current position evaluated afresh (k_sweep) */
+    DLSM_CHAIN_BLOCK = 2        /* 32 nodes per step, lanes = rows (k_sweep_cb) */
+} dlsm_chain_kernel;
 int dlsm_set_option(dlsm_handle *h, int option, int64_t value);
 
 /* ---- network -------------------------------------------------------------------------- */

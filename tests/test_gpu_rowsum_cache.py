@@ -179,3 +179,56 @@ def test_cluster_kernel_native_rng_chain_equals_cta_per_slice_chain():
     for other in outs[1:]:
         for a, b in zip(outs[0], other):
             assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------
+# block-speculative chain kernel (k_sweep_cb): one CTA per chain, 32 nodes per step
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,n,d,directed,K,C_", [(9, 120, 2, False, 10, 3), (4, 70, 3, False, 0, 2), (10, 500, 2, False, 10, 150),
+                                                 (5, 90, 2, True, 0, 2), (3, 257, 2, True, 6, 2), (2, 1500, 2, False, 0, 1),
+                                                 (1, 33, 2, False, 0, 2), (3, 31, 2, True, 0, 200), (17, 40, 2, False, 0, 2)])
+def test_block_chain_kernel_replay_vs_oracle(T, n, d, directed, K, C_):
+    """Recorded draws through k_sweep_cb: the oracle's decisions and states, bit for bit."""
+    L = _L()
+    rng, X, Y = _net(T, n, d, directed, seed=13 * n + T)
+    e, Xs, radii = _engine(T, n, d, directed, C_, X, Y, rng, K=K)
+    e.set_option(L.OPT_SWEEP_MODE, L.SWEEP_CHAIN if C_ <= 148 else L.SWEEP_CHAIN_DENSE)
+    e.set_option(L.OPT_CHAIN_KERNEL, L.CHAIN_BLOCK)
+    ic = np.array([0.6, 0.35]) if directed else np.array([0.6])
+    step = 0.02 / n if directed else 0.12
+    hy = dict(tau_sq=float(np.mean(X[0] * X[0])), sigma_sq=0.001 / n) if directed else dict(tau_sq=2.0, sigma_sq=0.1)
+    mix = None
+    if K:
+        mix = dict(mu=e.get(L.F_MU)[0], sigma=e.get(L.F_SIGMA)[0], lmbda=0.8, z=e.get(L.F_Z)[0].astype(np.int64))
+    check = sorted(set([0, C_ // 2, C_ - 1]))
+    tun = {c: O.TunerState((T, n), step, tune=4, tune_interval=2) for c in check}
+    Xo = {c: Xs[c].copy() for c in check}
+    for s in range(3 if n < 500 else 2):
+        eps, logu = rng.randn(C_, T, n, d), np.log(rng.rand(C_, T, n))
+        acc, ratio = e.sweep_latent(eps, logu, want_stats=True)
+        got = e.get(L.F_X)
+        for c in check:
+            out = O.sweep_latent(Xo[c], ic, tun[c], eps[c], logu[c], Y=Y, radii=None if radii is None else radii[c],
+                                 is_directed=directed, mixture=mix, **hy)
+            assert np.array_equal(acc[c], out["accepted"]), (s, c, int((acc[c] != out["accepted"]).sum()))
+            assert np.array_equal(got[c], Xo[c])
+            assert np.allclose(ratio[c], out["ratio"], rtol=1e-8, atol=1e-8)
+        assert 0.03 < acc.mean() < 0.97
+    assert np.array_equal(e.get(L.F_X_STEP)[check[0]], tun[check[0]].step)
+
+
+@pytest.mark.parametrize("T,n,d,directed,K", [(9, 120, 2, False, 10), (10, 500, 2, False, 10), (5, 90, 2, True, 0)])
+def test_block_chain_kernel_device_loop_equals_node_kernel_loop(T, n, d, directed, K):
+    L = _L()
+    outs = []
+    for kern in (L.CHAIN_BLOCK, L.CHAIN_NODE):
+        rng, X, Y = _net(T, n, d, directed, seed=3 * n + T)
+        e, _, _ = _engine(T, n, d, directed, 3, X, Y, rng, K=K, tune=500, tune_interval=3)
+        e.set_option(L.OPT_SWEEP_MODE, L.SWEEP_CHAIN)
+        e.set_option(L.OPT_CHAIN_KERNEL, kern)
+        e.run_sweeps(3 if n >= 500 else 8, skip_hdp=True)
+        outs.append([e.get(f) for f in (L.F_X, L.F_INTERCEPT)] + ([e.get(L.F_RADII)] if directed else []) +
+                    ([e.get(L.F_Z)] if K else []))
+        assert np.allclose(e.get(L.F_LOGLIK), e.loglik_full(), rtol=1e-11, atol=0)
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
