@@ -271,7 +271,8 @@ void read_env_options(dlsm_handle *h)
     h->opt[DLSM_OPT_NO_ROWSUM_CACHE] = on("DLSM_NO_ROWSUM");
     if (const char *m = getenv("DLSM_CHAIN_KERNEL"))
         h->opt[DLSM_OPT_CHAIN_KERNEL] = !strcmp(m, "block") ? DLSM_CHAIN_BLOCK
-                                        : !strcmp(m, "node") ? DLSM_CHAIN_NODE : DLSM_CHAIN_NODE_ROWSUM;
+                                        : !strcmp(m, "node") ? DLSM_CHAIN_NODE
+                                        : !strcmp(m, "rowsum") ? DLSM_CHAIN_NODE_ROWSUM : DLSM_CHAIN_AUTO;
     if (const char *m = getenv("DLSM_NO_CLUSTER")) h->opt[DLSM_OPT_NO_CLUSTER] = atoll(m) > 0 ? atoll(m) : 1;
     if (const char *m = getenv("DLSM_TRACE_CHUNK_BYTES")) h->opt[DLSM_OPT_TRACE_CHUNK_BYTES] = atoll(m);
     apply_sweep_mode(h);
@@ -550,21 +551,33 @@ int launch_slice_lk(dlsm_handle *h, const SweepParams &p)
     return xs ? launch_slice_t<LK, 0, true>(h, p, nw) : launch_slice_t<LK, 0, false>(h, p, nw);
 }
 
-// A warp per slice fills the GPU once there are a few chains per SM; below that (or when rows are
-// long) the CTA-per-slice kernel spreads one chain over T SMs and a row over up to 16 warps.
+// Which mapping serves a sweep (measured, profiles/r2b_ab_variants.json, r2c_*):
+//   * few (chain, slice) pairs with long rows (C*T*2 <= SMs, n >= 256; cfg 3): a thread-block cluster per
+//     pair, 32 nodes per cluster barrier (k_sweep_blk);
+//   * otherwise one CTA per chain, one warp per slice: the block-speculative kernel (k_sweep_cb) up to
+//     two chains per SM (its lanes carry independent rows: it needs no co-resident warps to hide
+//     latency), the node-by-node kernel beyond that (with the row-sum cache for long rows);
+//   * case-control lists: CTA per (chain, slice) kernels when a warp per slice cannot fill the part.
 bool use_slice_kernel(const dlsm_handle *h)
 {
     if (h->sweep_mode == 1) return false;
     if (h->sweep_mode == 2) return true;
     const size_t warps_chain_mode = (size_t)h->cfg.n_chains * (h->cfg.T < 16 ? h->cfg.T : 16);
-    return h->cfg.n >= 256 && warps_chain_mode < (size_t)h->sm_count * 16;
+    if (h->lk == kCaseControl) return h->cfg.n >= 256 && warps_chain_mode < (size_t)h->sm_count * 16;
+    return h->cfg.n >= 256 && h->cfg.n_chains * h->cfg.T * 2 <= h->sm_count && h->opt[DLSM_OPT_NO_CLUSTER] != 1;
+}
+
+int chain_kernel(const dlsm_handle *h)
+{
+    const int64_t k = h->opt[DLSM_OPT_CHAIN_KERNEL];
+    if (k != DLSM_CHAIN_AUTO) return (int)k;
+    // (DLSM_SWEEP_CHAIN_DENSE = "as if there were many chains": the node-by-node kernels)
+    if (h->cfg.n_chains <= 2 * h->sm_count && !h->dense_build) return DLSM_CHAIN_BLOCK;
+    return h->cfg.n >= 256 ? DLSM_CHAIN_NODE_ROWSUM : DLSM_CHAIN_NODE;
 }
 
 // which kernel serves the one-CTA-per-chain mapping (exact likelihoods): DLSM_OPT_CHAIN_KERNEL
-bool chain_blk(const dlsm_handle *h)
-{
-    return h->lk != kCaseControl && h->opt[DLSM_OPT_CHAIN_KERNEL] == DLSM_CHAIN_BLOCK;
-}
+bool chain_blk(const dlsm_handle *h) { return h->lk != kCaseControl && chain_kernel(h) == DLSM_CHAIN_BLOCK; }
 
 int launch_sweep(dlsm_handle *h, const SweepParams &p)
 {
@@ -663,7 +676,7 @@ size_t rows_smem(const dlsm_handle *h)
 bool rows_enabled(const dlsm_handle *h)
 {
     return h->lk != kCaseControl && !use_slice_kernel(h) && !h->opt[DLSM_OPT_NO_ROWSUM_CACHE] &&
-           h->opt[DLSM_OPT_CHAIN_KERNEL] == DLSM_CHAIN_NODE_ROWSUM &&
+           chain_kernel(h) == DLSM_CHAIN_NODE_ROWSUM &&
            !h->opt[DLSM_OPT_NO_TRACKED_LOGLIK] && rows_smem(h) <= kMaxSmem;
 }
 

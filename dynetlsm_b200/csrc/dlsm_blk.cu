@@ -70,7 +70,7 @@ __device__ __forceinline__ double dyad(const double (&xi)[DM], double ri, const 
 
 // shared-memory carve-up (doubles unless noted); every CTA uses the same layout
 struct BlkLayout {
-    size_t x, rinv, prop, x0, logu, nn, no, inv, zc, slots, ctab, bits, total;
+    size_t x, rinv, prop, x0, logu, nn, no, inv, zc, slots, red, ctab, bits, total;
 };
 __host__ __device__ inline BlkLayout blk_layout(int n, int d, bool directed, int W)
 {
@@ -86,6 +86,7 @@ __host__ __device__ inline BlkLayout blk_layout(int n, int d, bool directed, int
     L.inv = o; o += 32;
     L.zc = o; o += 16;                                   // 32 ints
     L.slots = o; o += (size_t)kBlkMaxTeam * 32 * 2;      // leader: [team][32][2]
+    L.red = o; o += 16 * 32 * 2;                         // leader: [warp][32][2] second-stage partial sums
     L.ctab = o; o += 32 * 32 * 4;                        // leader: [column][row][4]
     L.bits = o; o += (size_t)2 * 2 * 32 * W / 2;         // [buffer][row/col][32][W] uint32
     L.total = o;
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_blk(const SweepParams p, int *
     constexpr int DM = (D == 0) ? kMaxD : D;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar[2]; // adjacency bits of block b land on s_bar[b & 1]
-    __shared__ int s_ticket, s_mask;
+    __shared__ int s_ticket, s_mask, s_ready; // s_ready: blocks whose decisions have reached this CTA
     const int T = p.net.T, n = p.net.n, d = (D == 0) ? p.net.d : D, W = p.net.W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int rank = (int)cl_rank(), CS = (int)cl_size();
@@ -110,12 +111,13 @@ __global__ void __launch_bounds__(512, 1) k_sweep_blk(const SweepParams p, int *
     double *Xt = sm + L.x, *s_rinv = sm + L.rinv, *st_prop = sm + L.prop, *st_x0 = sm + L.x0;
     double *st_logu = sm + L.logu, *st_nn = sm + L.nn, *st_no = sm + L.no, *st_inv = sm + L.inv;
     int *st_zc = reinterpret_cast<int *>(sm + L.zc);
-    double *slots = sm + L.slots, *ctab = sm + L.ctab;
+    double *slots = sm + L.slots, *ctab = sm + L.ctab, *red = sm + L.red;
     uint32_t *bits = reinterpret_cast<uint32_t *>(sm + L.bits); // [2][2][32][W]
 
     if (threadIdx.x == 0) {
         if (leader) s_ticket = (int)atomicAdd(ticket, 1u);
         s_mask = 0;
+        s_ready = 0;
         mbar_init(smem_addr(&s_bar[0]), 1);
         mbar_init(smem_addr(&s_bar[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -213,6 +215,20 @@ __global__ void __launch_bounds__(512, 1) k_sweep_blk(const SweepParams p, int *
 
         // ---- 2. parallel phase: lane = row node jb + lane, this warp's columns ----
         const bool vrow = lane < jend;
+        // leader, warp 0: if slice t-1 has already resolved this block (the usual case: it runs ahead),
+        // fetch its positions now -- the L2 round trips hide under the parallel phase
+        double xp[DM];
+#pragma unroll
+        for (int k = 0; k < DM; k++) xp[k] = 0.0;
+        bool have_xp = (t == 0);
+        if (leader && warp == 0 && t > 0 && ld_acquire_gpu(prog + t - 1) >= jb + jend) {
+            have_xp = true;
+            if (vrow) {
+                const volatile double *q = Xchain + ((size_t)(t - 1) * n + jl) * d;
+#pragma unroll
+                for (int k = 0; k < DM; k++) if (k < d) xp[k] = q[k];
+            }
+        }
         double xn[DM], xo[DM];
         load_pos<DM>(st_prop + lane * d, d, xn);
         load_pos<DM>(st_x0 + lane * d, d, xo);
@@ -281,12 +297,19 @@ __global__ void __launch_bounds__(512, 1) k_sweep_blk(const SweepParams p, int *
         }
         cl_sync(); // ---- 3. A: partial sums and the in-block table are in the leader's shared memory ----
 
-        // ---- 4. serial phase: one warp of the leader ----
+        // ---- 4. serial phase: the leader adds the partial sums with all its warps, one warp decides ----
+        if (leader) {
+            double r_n = 0.0, r_o = 0.0;
+            for (int w = warp; w < team; w += nwarps) { // team order within a warp's share
+                r_n += slots[(w * 32 + lane) * 2];
+                r_o += slots[(w * 32 + lane) * 2 + 1];
+            }
+            red[(warp * 32 + lane) * 2] = r_n;
+            red[(warp * 32 + lane) * 2 + 1] = r_o;
+            __syncthreads();
+        }
         if (leader && warp == 0) {
-            double xp[DM];
-#pragma unroll
-            for (int k = 0; k < DM; k++) xp[k] = 0.0;
-            if (t > 0) { // the whole block of slice t-1 must be final (wavefront at block granularity)
+            if (!have_xp) { // the whole block of slice t-1 must be final (wavefront at block granularity)
                 while (ld_acquire_gpu(prog + t - 1) < jb + jend) { __nanosleep(DLSM_SPIN_NS); }
                 if (vrow) {
                     const volatile double *q = Xchain + ((size_t)(t - 1) * n + jl) * d;
@@ -301,14 +324,23 @@ __global__ void __launch_bounds__(512, 1) k_sweep_blk(const SweepParams p, int *
                 pr_n = prior_prev<DM>(p, c, t, zc, inv, xn, xp);
                 pr_o = prior_prev<DM>(p, c, t, zc, inv, xo, xp);
                 nn = st_nn[lane]; no = st_no[lane]; logu = st_logu[lane];
-                for (int w = 0; w < team; w++) { // partial sums in team order
-                    A_n += slots[(w * 32 + lane) * 2];
-                    A_o += slots[(w * 32 + lane) * 2 + 1];
+                for (int w = 0; w < nwarps; w++) { // second stage, warp order
+                    A_n += red[(w * 32 + lane) * 2];
+                    A_o += red[(w * 32 + lane) * 2 + 1];
                 }
-                for (int ic = 0; ic < jend; ic++) { // every in-block column at its OLD position
-                    A_n += ctab[(ic * 32 + lane) * 4];
-                    A_o += ctab[(ic * 32 + lane) * 4 + 1];
+                double c_n = 0.0, c_o = 0.0, e_n = 0.0, e_o = 0.0;
+                for (int ic = 0; ic + 1 < jend; ic += 2) { // every in-block column at its OLD position
+                    c_n += ctab[(ic * 32 + lane) * 4];
+                    c_o += ctab[(ic * 32 + lane) * 4 + 1];
+                    e_n += ctab[((ic + 1) * 32 + lane) * 4];
+                    e_o += ctab[((ic + 1) * 32 + lane) * 4 + 1];
                 }
+                if (jend & 1) {
+                    c_n += ctab[((jend - 1) * 32 + lane) * 4];
+                    c_o += ctab[((jend - 1) * 32 + lane) * 4 + 1];
+                }
+                A_n += c_n + e_n;
+                A_o += c_o + e_o;
             }
             unsigned mask = 0u;
             for (int jj = 0; jj < jend; jj++) {
@@ -333,6 +365,12 @@ __global__ void __launch_bounds__(512, 1) k_sweep_blk(const SweepParams p, int *
                     }
                 }
             }
+            // the decisions leave first (one word per CTA, then its ready counter with release
+            // semantics): the other CTAs start the next block while the bookkeeping below still runs
+            if (lane < CS) {
+                cl_st_s32(cl_map(smem_addr(&s_mask), (uint32_t)lane), (int)mask);
+                cl_st_release_s32(cl_map(smem_addr(&s_ready), (uint32_t)lane), blk + 1);
+            }
             const int my_acc = (mask >> lane) & 1u;
             if (vrow) {
                 if (my_acc) {
@@ -344,11 +382,11 @@ __global__ void __launch_bounds__(512, 1) k_sweep_blk(const SweepParams p, int *
                 metropolis_bookkeep(my_step, my_nacc, my_nsteps, my_until, p.tune, p.tune_interval, my_acc, false);
                 p.step[gs] = my_step; p.nacc[gs] = my_nacc; p.nsteps[gs] = my_nsteps; p.until[gs] = my_until;
             }
-            if (lane < CS) cl_st_s32(cl_map(smem_addr(&s_mask), (uint32_t)lane), (int)mask);
             __syncwarp();
             if (lane == 0) st_release_gpu(prog + t, jb + jend); // slice t+1 may resolve this block
         }
-        cl_sync(); // ---- 5. B: every CTA knows the decisions ----
+        // ---- 5. every CTA waits for the decisions of this block (local poll) and commits them ----
+        while (cl_ld_acquire_local_s32(smem_addr(&s_ready)) < blk + 1) { __nanosleep(DLSM_SPIN_NS); }
         if (warp == 0 && vrow && ((unsigned)s_mask >> lane) & 1u) {
 #pragma unroll
             for (int k = 0; k < DM; k++) if (k < d) Xt[(size_t)jl * d + k] = xn[k];

@@ -160,9 +160,10 @@ typedef enum {
 } dlsm_sweep_mode;
 typedef enum { DLSM_FFBS_AUTO = 0, DLSM_FFBS_THREAD = 1, DLSM_FFBS_WARP = 2 } dlsm_ffbs_kernel;
 typedef enum {
-    DLSM_CHAIN_NODE_ROWSUM = 0, /* node by node; the device loop evaluates proposals only (row-sum cache) */
-    DLSM_CHAIN_NODE = 1,        /* node by node, proposal and current position evaluated afresh (k_sweep) */
-    DLSM_CHAIN_BLOCK = 2        /* 32 nodes per step, lanes = rows (k_sweep_cb) */
+    DLSM_CHAIN_AUTO = 0,        /* block kernel up to two chains per SM, else row-sum cache for n >= 256, else node */
+    DLSM_CHAIN_NODE_ROWSUM = 1, /* node by node; the device loop evaluates proposals only (row-sum cache) */
+    DLSM_CHAIN_NODE = 2,        /* node by node, proposal and current position evaluated afresh (k_sweep) */
+    DLSM_CHAIN_BLOCK = 3        /* 32 nodes per step, lanes = rows (k_sweep_cb) */
 } dlsm_chain_kernel;
 int dlsm_set_option(dlsm_handle *h, int option, int64_t value);
 

@@ -73,6 +73,7 @@ def test_k_rows_equals_the_per_node_and_full_network_probes(T, n, d, directed):
     rng, X, Y = _net(T, n, d, directed, seed=n)
     e, _, _ = _engine(T, n, d, directed, 2, X, Y, rng)
     e.set_option(L.OPT_SWEEP_MODE, L.SWEEP_CHAIN)
+    e.set_option(L.OPT_CHAIN_KERNEL, L.CHAIN_NODE_ROWSUM)
     rows = e.rowsums()
     fresh = e.loglik_partial()
     assert np.allclose(rows, fresh, rtol=1e-11, atol=0)
@@ -87,6 +88,7 @@ def test_cached_sweep_makes_the_oracle_decisions_on_the_device_draws(T, n, d, di
     C_ = 3
     e, Xs, radii = _engine(T, n, d, directed, C_, X, Y, rng)
     e.set_option(L.OPT_SWEEP_MODE, L.SWEEP_CHAIN)
+    e.set_option(L.OPT_CHAIN_KERNEL, L.CHAIN_NODE_ROWSUM)
     ic = np.array([0.6, 0.35]) if directed else np.array([0.6])
     hy = dict(tau_sq=float(np.mean(X[0] * X[0])), sigma_sq=0.001 / n) if directed else dict(tau_sq=2.0, sigma_sq=0.1)
     tun = [O.TunerState((T, n), 0.02 / n if directed else 0.12, tune=4, tune_interval=2) for _ in range(C_)]
@@ -115,8 +117,7 @@ def test_device_loop_chain_is_the_two_variant_chain(T, n, d, directed, K):
         rng, X, Y = _net(T, n, d, directed, seed=3 * n + T)
         e, _, _ = _engine(T, n, d, directed, 3, X, Y, rng, K=K, tune=500, tune_interval=3)
         e.set_option(L.OPT_SWEEP_MODE, L.SWEEP_CHAIN)
-        if not cached:
-            e.set_option(L.OPT_NO_ROWSUM_CACHE, 1)
+        e.set_option(L.OPT_CHAIN_KERNEL, L.CHAIN_NODE_ROWSUM if cached else L.CHAIN_NODE)
         e.run_sweeps(3 if n >= 500 else 8, skip_hdp=True)
         outs.append([e.get(f) for f in (L.F_X, L.F_INTERCEPT, L.F_LOGLIK)] +
                     ([e.get(L.F_RADII)] if directed else []) + ([e.get(L.F_Z)] if K else []))
