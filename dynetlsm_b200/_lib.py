@@ -15,9 +15,9 @@ LIB_PATH = os.environ.get("DLSM_LIB") or os.path.join(HERE, "libdlsm.so")   # DL
 CSRC = os.path.join(HERE, "csrc")
 # translation units -> the headers each depends on (mtime-based rebuild of the unit's object file)
 HEADERS = [os.path.join(CSRC, f) for f in ("dlsm_kernels.cuh", "dlsm_device.cuh", "dlsm_tables.cuh",
-                                            "dlsm_hdp.cuh", "dlsm_trace.cuh", "dlsm_blk.h")]
+                                            "dlsm_hdp.cuh", "dlsm_trace.cuh", "dlsm_blk.h", "dlsm_graph.h", "dlsm_cc.h")]
 HEADERS.append(os.path.join(ROOT, "include", "dlsm.h"))
-UNITS = [os.path.join(CSRC, "dlsm.cu"), os.path.join(CSRC, "dlsm_blk.cu")]
+UNITS = [os.path.join(CSRC, f) for f in ("dlsm.cu", "dlsm_blk.cu", "dlsm_graph.cu", "dlsm_cc.cu")]
 SRC = UNITS + HEADERS
 OBJ_DIR = os.path.join(HERE, "build")
 
@@ -96,13 +96,14 @@ EXPORTS = [
     "dlsm_sample_labels", "dlsm_set_hdp_prior", "dlsm_hdp_update", "dlsm_run_sweeps", "dlsm_loglik_partial", "dlsm_loglik_full",
     "dlsm_gaussian_likelihood", "dlsm_debug_set_counts", "dlsm_debug_draws", "dlsm_enable_timing", "dlsm_get_counters",
     "dlsm_resample_controls", "dlsm_get_controls", "dlsm_edge_probas", "dlsm_cooccurrence", "dlsm_logp", "dlsm_set_procrustes_ref", "dlsm_procrustes", "dlsm_run_traced", "dlsm_host_alloc", "dlsm_host_free",
-    "dlsm_set_option", "dlsm_debug_rowsums",
+    "dlsm_set_option", "dlsm_debug_rowsums", "dlsm_set_network_edges", "dlsm_edge_list_dims",
+    "dlsm_get_edge_lists",
 ]
 
 # dlsm_option / dlsm_sweep_mode / dlsm_ffbs_kernel (include/dlsm.h)
 (OPT_SWEEP_MODE, OPT_FFBS_KERNEL, OPT_FFBS_SMEM_STAGE, OPT_FFBS_CTAS_PER_SM, OPT_NO_GATHER_PACK,
  OPT_NO_TRACKED_LOGLIK, OPT_CENTER_EXACT, OPT_HDP_SEGMENTED, OPT_NO_EARLY_X, OPT_TRACE_CHUNK_BYTES,
- OPT_NO_ROWSUM_CACHE, OPT_NO_CLUSTER, OPT_CHAIN_KERNEL) = range(13)
+ OPT_NO_ROWSUM_CACHE, OPT_NO_CLUSTER, OPT_CHAIN_KERNEL, OPT_CC_KERNEL) = range(14)
 CHAIN_AUTO, CHAIN_NODE_ROWSUM, CHAIN_NODE, CHAIN_BLOCK = range(4)
 SWEEP_AUTO, SWEEP_CHAIN, SWEEP_CHAIN_DENSE, SWEEP_SLICE, SWEEP_SLICE_PLAIN = range(5)
 FFBS_AUTO, FFBS_THREAD, FFBS_WARP = range(3)
@@ -139,6 +140,9 @@ def load():
     L.dlsm_set_network_dense.argtypes = [vp, dp]
     L.dlsm_set_edge_lists.argtypes = [vp, ip, ip, C.c_int32, ip, C.c_int32]
     L.dlsm_set_controls.argtypes = [vp, ip, ip, C.c_int32, C.c_int32]
+    L.dlsm_set_network_edges.argtypes = [vp, ip, C.c_size_t]
+    L.dlsm_edge_list_dims.argtypes = [vp, ip, ip]
+    L.dlsm_get_edge_lists.argtypes = [vp, ip, ip, ip]
     L.dlsm_set_state.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.dlsm_get_state.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.dlsm_set_hyper.argtypes = [vp, C.POINTER(Hyper)]
@@ -318,6 +322,25 @@ class Engine(object):
         dg = _i32(degrees, (self.T, self.n, 2))
         ie, oe = _i32(in_edges), _i32(out_edges)
         self._ck(self.L.dlsm_set_edge_lists(self.h, _ip(dg), _ip(ie), ie.shape[2], _ip(oe), oe.shape[2]))
+
+    def set_network_edges(self, edges):
+        """Sparse network: (E, 3) int rows (t, sender, receiver); the case-control edge lists are built
+        on the device (dlsm_set_network_edges)."""
+        ed = _i32(edges)
+        if ed.ndim != 2 or ed.shape[1] != 3:
+            raise ValueError("edges must have shape (n_edges, 3): (t, sender, receiver)")
+        self._ck(self.L.dlsm_set_network_edges(self.h, _ip(ed), ed.shape[0]))
+
+    def get_edge_lists(self):
+        """(degrees (T,n,2), in_edges (T,n,max_in), out_edges (T,n,max_out)) as held by the device."""
+        mi, mo = C.c_int32(0), C.c_int32(0)
+        self._ck(self.L.dlsm_edge_list_dims(self.h, C.byref(mi), C.byref(mo)))
+        dg = np.empty((self.T, self.n, 2), np.int32)
+        ie = np.zeros((self.T, self.n, mi.value), np.int32)
+        oe = np.zeros((self.T, self.n, mo.value), np.int32)
+        self._ck(self.L.dlsm_get_edge_lists(self.h, _ip(dg), _ip(ie) if mi.value else None,
+                                            _ip(oe) if mo.value else None))
+        return dg, ie, oe
 
     def set_controls(self, ctrl_in, ctrl_out):
         ci, co = _i32(ctrl_in), _i32(ctrl_out)

@@ -12,7 +12,40 @@ import numbers
 import numpy as np
 from sklearn.utils import check_random_state
 
-__all__ = ["DirectedCaseControlSampler"]
+__all__ = ["DirectedCaseControlSampler", "SparseNetwork"]
+
+
+class SparseNetwork(object):
+    """A directed dynamic network given by its ties: ``edges`` (E, 3) integer rows (t, sender,
+    receiver), every tie once, no self ties.  ``fit`` accepts it in place of the dense (T, n, n)
+    tensor when the case-control likelihood is used (``n_control`` set): the degree / edge-list
+    bookkeeping of ``DirectedCaseControlSampler.init`` (case_control_likelihood.py:37-73) is then
+    built on the device (``dlsm_set_network_edges``), so networks whose dense tensor cannot exist
+    (n = 50 000: 200 GB) go through the estimator."""
+
+    def __init__(self, edges, n_time_steps, n_nodes):
+        self.edges = np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 3)
+        self.shape = (int(n_time_steps), int(n_nodes), int(n_nodes))
+
+    @classmethod
+    def from_dense(cls, Y):
+        Y = np.asarray(Y)
+        return cls(np.argwhere(Y == 1), Y.shape[0], Y.shape[1])
+
+    @classmethod
+    def from_scipy(cls, matrices):
+        """A sequence of T scipy.sparse matrices (n, n); entry (i, j) != 0 is a tie i -> j."""
+        rows = []
+        for t, m in enumerate(matrices):
+            coo = m.tocoo()
+            keep = (coo.data != 0) & (coo.row != coo.col)
+            rows.append(np.stack([np.full(int(keep.sum()), t), coo.row[keep], coo.col[keep]], axis=1))
+        return cls(np.concatenate(rows) if rows else np.zeros((0, 3)), len(matrices), matrices[0].shape[0])
+
+    def toarray(self):
+        Y = np.zeros(self.shape)
+        Y[self.edges[:, 0], self.edges[:, 1], self.edges[:, 2]] = 1.0
+        return Y
 
 
 class DirectedCaseControlSampler(object):

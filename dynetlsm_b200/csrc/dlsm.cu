@@ -5,6 +5,8 @@
 #include "dlsm_hdp.cuh"
 #include "dlsm_trace.cuh"
 #include "dlsm_blk.h"
+#include "dlsm_graph.h"
+#include "dlsm_cc.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -66,6 +68,7 @@ struct dlsm_handle {
     double *d_rows = nullptr, *d_scr = nullptr, *d_rows_own = nullptr, *d_rows_part = nullptr;
     int32_t *d_accflag = nullptr;
     bool rows_valid = false;
+    int sweeps_since_set = 0;       // device-loop sweeps since the state last changed from outside
     int rows_nb = 0, rows_half = 0, rows_R = 1, rows_L = 0, rows_ipc = 0, rows_ns = 1, rows_grid = 1;
     int cluster_cs = -1;            // CTAs per (chain, slice) cluster (-1: not probed, 0: none)
     int cluster_ncomp = 0;          // compute warps per CTA (per-node cluster kernel) / warps per CTA (block kernel)
@@ -273,6 +276,7 @@ void read_env_options(dlsm_handle *h)
         h->opt[DLSM_OPT_CHAIN_KERNEL] = !strcmp(m, "block") ? DLSM_CHAIN_BLOCK
                                         : !strcmp(m, "node") ? DLSM_CHAIN_NODE
                                         : !strcmp(m, "rowsum") ? DLSM_CHAIN_NODE_ROWSUM : DLSM_CHAIN_AUTO;
+    h->opt[DLSM_OPT_CC_KERNEL] = on("DLSM_CC_V1");
     if (const char *m = getenv("DLSM_NO_CLUSTER")) h->opt[DLSM_OPT_NO_CLUSTER] = atoll(m) > 0 ? atoll(m) : 1;
     if (const char *m = getenv("DLSM_TRACE_CHUNK_BYTES")) h->opt[DLSM_OPT_TRACE_CHUNK_BYTES] = atoll(m);
     apply_sweep_mode(h);
@@ -526,6 +530,18 @@ int launch_cc_batch(dlsm_handle *h, const SweepParams &p)
     }
     CU(h, cudaMemsetAsync(h->d_progress, 0, CT * sizeof(int), h->stream));
     CU(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
+    if (c.d == 2 && h->n_control <= 128 && !h->opt[DLSM_OPT_CC_KERNEL] &&
+        cc2_smem_bytes(h->max_in, h->max_out, h->n_control) <= kMaxSmem) {
+        // second generation: list indices staged per 32-node block, 256-bit gather records
+        const size_t cells = (size_t)c.n_chains * c.T * c.n;
+        if (!h->d_gather) CU(h, cudaMalloc((void **)&h->d_gather, cells * 4 * sizeof(double)));
+        k_pack_gather<<<(unsigned)((cells + 255) / 256), 256, 0, h->stream>>>((const double *)p.X, (const double *)h->rinv,
+                                                                              h->d_gather, c.n_chains, c.T, c.n);
+        CHECK_LAUNCH(h);
+        h->ctr.kernel_launches += 1;
+        CU(h, cc2_launch(p, h->d_gather, h->d_progress, h->d_ticket, h->d_cc_dep, h->stream));
+        return DLSM_OK;
+    }
     const int nw = 16;
     const size_t smem = sweep_stage_doubles(c.d) * sizeof(double) + 64 * sizeof(int) + 16;
     if (c.d == 2) k_sweep_cc<2><<<(unsigned)CT, nw * 32, smem, h->stream>>>(p, h->d_progress, h->d_ticket, h->d_cc_dep);
@@ -948,7 +964,7 @@ int dlsm_set_option(dlsm_handle *h, int option, int64_t value)
     if (option == DLSM_OPT_NO_CLUSTER && value > 2) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_NO_CLUSTER takes 0, 1 or 2");
     if (option == DLSM_OPT_CHAIN_KERNEL && value > DLSM_CHAIN_BLOCK) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_CHAIN_KERNEL takes a dlsm_chain_kernel value");
     h->opt[option] = value;
-    h->rows_valid = false;
+    h->rows_valid = false, h->sweeps_since_set = 0;
     h->cluster_cs = -1;
     if (option == DLSM_OPT_SWEEP_MODE) apply_sweep_mode(h);
     return DLSM_OK;
@@ -998,7 +1014,7 @@ int dlsm_set_network_dense(dlsm_handle *h, const double *Y)
     CHECK_LAUNCH(h);
     if (bad) FAIL(h, DLSM_ERR_NONBINARY, "adjacency must be 0/1 (weighted or missing (-1) dyads are not supported on the device path)");
     h->have_net = true;
-    h->rows_valid = false;
+    h->rows_valid = false, h->sweeps_since_set = 0;
     return DLSM_OK;
 }
 
@@ -1023,6 +1039,52 @@ int dlsm_set_edge_lists(dlsm_handle *h, const int32_t *degrees, const int32_t *i
     h->have_edges = true;
     h->cc_dep_valid = false;
     return DLSM_OK;
+}
+
+int dlsm_set_network_edges(dlsm_handle *h, const int32_t *edges, size_t n_edges)
+{
+    if (!h || (n_edges > 0 && !edges)) return DLSM_ERR_INVALID;
+    if (h->lk != kCaseControl) FAIL(h, DLSM_ERR_INVALID, "an edge-list network needs the case-control likelihood");
+    CU(h, cudaSetDevice(h->cfg.device));
+    int32_t *d_edges = nullptr;
+    CU(h, cudaMalloc((void **)&d_edges, (n_edges * 3 + 1) * sizeof(int32_t)));
+    cudaError_t e = cudaMemcpyAsync(d_edges, edges, n_edges * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
+    int32_t *deg = nullptr, *in_e = nullptr, *out_e = nullptr;
+    int max_in = 0, max_out = 0, status = 0;
+    if (e == cudaSuccess)
+        e = graph_build_edge_lists(d_edges, n_edges, h->cfg.T, h->cfg.n, &deg, &in_e, &max_in, &out_e, &max_out,
+                                   &status, h->stream);
+    cudaFree(d_edges);
+    CU(h, e);
+    if (status == 1) FAIL(h, DLSM_ERR_INVALID, "edge list: an index is out of range or a tie is a self loop");
+    if (status == 2) FAIL(h, DLSM_ERR_INVALID, "edge list: a tie is listed twice");
+    cudaFree(h->deg); cudaFree(h->in_edges); cudaFree(h->out_edges);
+    h->deg = deg; h->in_edges = in_e; h->out_edges = out_e;
+    h->max_in = max_in; h->max_out = max_out;
+    h->have_edges = true;
+    h->cc_dep_valid = false;
+    h->ctr.kernel_launches += 4;
+    return DLSM_OK;
+}
+
+int dlsm_edge_list_dims(dlsm_handle *h, int32_t *max_in, int32_t *max_out)
+{
+    if (!h || !max_in || !max_out) return DLSM_ERR_INVALID;
+    if (!h->have_edges) FAIL(h, DLSM_ERR_NOTSET, "no edge lists on the device");
+    *max_in = h->max_in; *max_out = h->max_out;
+    return DLSM_OK;
+}
+
+int dlsm_get_edge_lists(dlsm_handle *h, int32_t *degrees, int32_t *in_edges, int32_t *out_edges)
+{
+    if (!h || !degrees) return DLSM_ERR_INVALID;
+    if (!h->have_edges) FAIL(h, DLSM_ERR_NOTSET, "no edge lists on the device");
+    CU(h, cudaSetDevice(h->cfg.device));
+    const size_t TN = (size_t)h->cfg.T * h->cfg.n;
+    int rc = download(h, degrees, h->deg, TN * 2 * 4);
+    if (rc == DLSM_OK && in_edges && h->max_in) rc = download(h, in_edges, h->in_edges, TN * h->max_in * 4);
+    if (rc == DLSM_OK && out_edges && h->max_out) rc = download(h, out_edges, h->out_edges, TN * h->max_out * 4);
+    return rc;
 }
 
 int dlsm_set_controls(dlsm_handle *h, const int32_t *ctrl_in, const int32_t *ctrl_out,
@@ -1101,7 +1163,7 @@ int dlsm_set_state(dlsm_handle *h, int field, const void *host, size_t bytes)
     CU(h, cudaSetDevice(h->cfg.device));
     int rc = upload(h, h->field[field], host, bytes);
     if (rc != DLSM_OK) return rc;
-    if (field == DLSM_F_X || field == DLSM_F_INTERCEPT || field == DLSM_F_RADII) h->rows_valid = false;
+    if (field == DLSM_F_X || field == DLSM_F_INTERCEPT || field == DLSM_F_RADII) h->rows_valid = false, h->sweeps_since_set = 0;
     if (field == DLSM_F_RADII) rc = update_rinv(h);
     if (rc != DLSM_OK) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
@@ -1153,7 +1215,7 @@ int dlsm_sweep_latent(dlsm_handle *h, const double *eps, const double *logu, int
     if (rc != DLSM_OK) return rc;
     const size_t N = (size_t)h->cfg.n_chains * h->cfg.T * h->cfg.n;
     SweepParams p = sweep_params(h);
-    h->rows_valid = false; // the function-level sweep evaluates both variants and keeps no row sums
+    h->rows_valid = false, h->sweeps_since_set = 0; // the function-level sweep evaluates both variants and keeps no row sums
     if (eps || accepted || ratio) {
         rc = ensure_replay_buffers(h);
         if (rc != DLSM_OK) return rc;
@@ -1263,7 +1325,7 @@ int dlsm_sample_intercepts(dlsm_handle *h, const double *eps, const double *logu
     if (rc != DLSM_OK) return rc;
     const size_t C = h->cfg.n_chains, m = h->cfg.is_directed ? 2 : 1;
     double *d_eps = nullptr, *d_logu = nullptr;
-    h->rows_valid = false;
+    h->rows_valid = false, h->sweeps_since_set = 0;
     if (eps) {
         d_eps = h->d_small; d_logu = h->d_small + C * 2;
         if ((rc = upload(h, d_eps, eps, C * m * 8)) != DLSM_OK) return rc;
@@ -1334,7 +1396,7 @@ int dlsm_sample_radii(dlsm_handle *h, const double *proposal, const double *logu
     int rc = need_inputs(h);
     if (rc != DLSM_OK) return rc;
     const size_t C = h->cfg.n_chains, n = h->cfg.n;
-    h->rows_valid = false;
+    h->rows_valid = false, h->sweeps_since_set = 0;
     if (proposal) {
         if ((rc = upload(h, h->d_rprop, proposal, C * n * 8)) != DLSM_OK) return rc;
         if ((rc = upload(h, h->d_small, logu, C * 8)) != DLSM_OK) return rc;
@@ -1534,7 +1596,11 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
     bool use_cur = !use_slice_kernel(h) && h->lk != kCaseControl && !h->opt[DLSM_OPT_NO_TRACKED_LOGLIK];
     p.ll_cur = use_cur ? F<double>(h, DLSM_F_LOGLIK) : nullptr;
     // ... and keeps the per-node row sums, so that a node-update evaluates its proposal only
-    const bool rows = use_cur && rows_enabled(h);
+    // (the first sweep after the state came in from outside -- dlsm_set_state, a function-level call --
+    //  runs on the two-variant kernel: building the cache costs a k_rows pass, which only pays when
+    //  further sweeps follow on the device)
+    const bool rows = use_cur && rows_enabled(h) && (h->rows_valid || h->sweeps_since_set > 0);
+    h->sweeps_since_set += 1;
     if (rows) {
         if ((rc = ensure_rows(h)) != DLSM_OK) return rc;
         if (!h->rows_valid) {

@@ -22,7 +22,7 @@ from scipy.special import expit
 from sklearn.utils import check_array, check_random_state
 
 from . import _lib as L
-from .case_control_likelihood import DirectedCaseControlSampler
+from .case_control_likelihood import DirectedCaseControlSampler, SparseNetwork
 from .host_init import (calculate_distances, directed_intercept_mle, generalized_mds,
                         initialize_radii, longitudinal_procrustes_rotation, scale_intercept_mle)
 
@@ -42,13 +42,18 @@ class _Driver(object):
         self.T, self.n, self.d, self.C = T, n, n_features, n_chains
         self.replay, self.rng = replay, rng
         self.is_directed, self.cc = is_directed, case_control_sampler
+        sparse = isinstance(Y, SparseNetwork)
         self.engine = L.Engine(T=T, n=n, d=n_features, n_chains=n_chains, K=mixture_K,
                                is_directed=is_directed, case_control=self.cc is not None,
                                mixture=mixture_K > 0, device=device, tune=tune,
                                tune_interval=tune_interval,
                                intercept_tune_interval=intercept_tune_interval,
                                radii_tune=radii_tune, radii_tune_interval=100)
-        if self.cc is None:
+        if sparse:
+            # ties in, degree / edge lists built on the device and mirrored under the reference's names
+            self.engine.set_network_edges(Y.edges)
+            self.cc.init_from_edges(*self.engine.get_edge_lists(), sample=False)
+        elif self.cc is None:
             self.engine.set_network(Y)
         else:
             self.engine.set_edge_lists(self.cc.degrees_, self.cc.in_edges_, self.cc.out_edges_)
@@ -161,8 +166,9 @@ class _FittedNetworkMixin(object):
         if not hasattr(self, "X_"):
             raise ValueError("Model not fit.")
         n = self.Y_fit_.shape[1]
+        Y = self.Y_fit_.toarray() if isinstance(self.Y_fit_, SparseNetwork) else self.Y_fit_
         mask = ~np.eye(n, dtype=bool) if self.is_directed else np.triu(np.ones((n, n), bool), 1)
-        return roc_auc_score(self.Y_fit_[:, mask].ravel(), self.probas_[:, mask].ravel())
+        return roc_auc_score(Y[:, mask].ravel(), self.probas_[:, mask].ravel())
 
 
 class DynamicNetworkLSM(_FittedNetworkMixin):
@@ -283,21 +289,34 @@ class DynamicNetworkLSM(_FittedNetworkMixin):
             ci, co = e.get_controls()
             cc.control_nodes_in_, cc.control_nodes_out_ = ci[0].astype(np.int64), co[0].astype(np.int64)
 
-    def fit(self, Y):
-        """Sample from the posterior given the dynamic network ``Y`` (T, n, n), entries 0/1."""
+    def fit(self, Y, X_init=None, radii_init=None, intercept_init=None):
+        """Sample from the posterior given the dynamic network ``Y``: a dense (T, n, n) array with
+        entries 0/1, or -- with the case-control likelihood (``n_control``) -- a ``SparseNetwork`` /
+        a sequence of T scipy.sparse matrices.  The reference's starting values (generalised MDS on
+        shortest-path distances, lsm.py:385-413) need the dense tensor; a sparse network starts from
+        ``X_init`` (T, n, d), ``radii_init`` (n,), ``intercept_init`` (2,) or, where those are not
+        given, from a random walk under the model's own prior, degree-proportional radii and
+        intercepts (1, 1)."""
         if self.sampler not in ("device", "replay"):
             raise ValueError("`sampler` must be 'device' or 'replay', got {}".format(self.sampler))
         replay = self.sampler == "replay"
         if replay and self.n_chains != 1:
             raise ValueError("sampler='replay' reproduces one reference chain; use n_chains=1")
+        if isinstance(Y, (list, tuple)) and len(Y) and hasattr(Y[0], "tocoo"):
+            Y = SparseNetwork.from_scipy(Y)
+        sparse = isinstance(Y, SparseNetwork)
+        if sparse and (self.n_control is None or not self.is_directed or replay):
+            raise ValueError("a sparse network needs the case-control likelihood of the directed model "
+                             "(is_directed=True, n_control=...) and sampler='device'")
         n_time_steps, n_nodes, _ = Y.shape
         rng = check_random_state(self.random_state)
-        Y = check_array(Y, dtype=np.float64, ensure_all_finite="allow-nan", ensure_2d=False,
-                        allow_nd=True, copy=self.copy)
-        if np.any(Y == -1) or np.any(np.isnan(Y)):
-            raise NotImplementedError("missing dyads (-1 / NaN) are not supported by the device "
-                                      "sampler; impute them first (the reference's "
-                                      "SimpleNetworkImputer is outside the accelerated path)")
+        if not sparse:
+            Y = check_array(Y, dtype=np.float64, ensure_all_finite="allow-nan", ensure_2d=False,
+                            allow_nd=True, copy=self.copy)
+            if np.any(Y == -1) or np.any(np.isnan(Y)):
+                raise NotImplementedError("missing dyads (-1 / NaN) are not supported by the device "
+                                          "sampler; impute them first (the reference's "
+                                          "SimpleNetworkImputer is outside the accelerated path)")
         self.Y_fit_ = Y
         n_iter_procrustes = 0
         if self.tune is not None:
@@ -309,16 +328,32 @@ class DynamicNetworkLSM(_FittedNetworkMixin):
         S, C, m = self.n_iter, self.n_chains, (2 if self.is_directed else 1)
 
         # ---- initial values on the host (lsm.py:385-413) ----
-        X = generalized_mds(Y, n_features=self.n_features, is_directed=self.is_directed,
-                            random_state=rng)
         radii = None
-        if self.is_directed:
-            radii = initialize_radii(Y)
-            intercept = np.array(directed_intercept_mle(Y, X, radii))
+        if sparse:
+            if X_init is not None:
+                X = np.array(X_init, dtype=np.float64)
+            else:   # a random walk at the scale the reference initialises directed models at (1 / n)
+                X = np.empty((n_time_steps, n_nodes, self.n_features))
+                X[0] = rng.randn(n_nodes, self.n_features) / n_nodes
+                for t in range(1, n_time_steps):
+                    X[t] = X[t - 1] + np.sqrt(self.sigma_sq) / n_nodes * rng.randn(n_nodes, self.n_features)
+            if radii_init is not None:
+                radii = np.array(radii_init, dtype=np.float64)
+            else:   # initialize_radii (latent_space.py): share of the ties a node takes part in
+                cnt = np.bincount(Y.edges[:, 1], minlength=n_nodes) + np.bincount(Y.edges[:, 2], minlength=n_nodes)
+                radii = (0.5 * cnt + 1e-5 * max(1, Y.edges.shape[0])) / max(1, Y.edges.shape[0])
+                radii /= radii.sum()
+            intercept = np.array([1.0, 1.0]) if intercept_init is None else np.array(intercept_init, dtype=np.float64)
         else:
-            scale, b = scale_intercept_mle(Y, X)
-            intercept = np.array([b])
-            X *= np.exp(scale)
+            X = generalized_mds(Y, n_features=self.n_features, is_directed=self.is_directed,
+                                random_state=rng)
+            if self.is_directed:
+                radii = initialize_radii(Y)
+                intercept = np.array(directed_intercept_mle(Y, X, radii))
+            else:
+                scale, b = scale_intercept_mle(Y, X)
+                intercept = np.array([b])
+                X *= np.exp(scale)
         X -= np.mean(X, axis=(0, 1))
         if isinstance(self.tau_sq, str) and self.tau_sq == "auto":
             self.tau_sq = np.mean(X[0] * X[0])
@@ -332,7 +367,8 @@ class DynamicNetworkLSM(_FittedNetworkMixin):
                                  "supported for directed networks.")
             self.case_control_sampler_ = DirectedCaseControlSampler(
                 n_control=self.n_control, n_resample=self.n_resample_control, random_state=rng)
-            self.case_control_sampler_.init(Y, sample=replay)   # device mode draws them on the GPU
+            if not sparse:   # (a sparse network's lists are built on the device, in _Driver)
+                self.case_control_sampler_.init(Y, sample=replay)   # device mode draws the controls on the GPU
 
         # ---- device state ----
         drv = _Driver(Y, self.n_features, C, self.is_directed, self.case_control_sampler_, 0,

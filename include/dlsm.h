@@ -134,7 +134,7 @@ int dlsm_synchronize(dlsm_handle *h);
  * DLSM_SWEEP_MODE=chain|chain-dense|slice|slice-plain, DLSM_FFBS=thread|warp, DLSM_FFBS_SMEM,
  * DLSM_FFBS_PER_SM=<n>, DLSM_NO_GATHER_PACK, DLSM_NO_LLCUR, DLSM_CENTER_EXACT, DLSM_HDP_SEGMENTED,
  * DLSM_NO_EARLY_X, DLSM_TRACE_CHUNK_BYTES=<bytes>, DLSM_NO_ROWSUM, DLSM_NO_CLUSTER=1|2,
- * DLSM_CHAIN_KERNEL=rowsum|node|block. */
+ * DLSM_CHAIN_KERNEL=rowsum|node|block, DLSM_CC_V1. */
 typedef enum {
     DLSM_OPT_SWEEP_MODE = 0,        /* dlsm_sweep_mode: which latent-sweep kernel (default: heuristic) */
     DLSM_OPT_FFBS_KERNEL = 1,       /* dlsm_ffbs_kernel: label kernel mapping */
@@ -152,6 +152,7 @@ typedef enum {
                                        thread-block cluster per pair (k_sweep_blk), 1 = no clusters (CTA per
                                        pair), 2 = per-node cluster kernel (k_sweep_slice_cl) */
     DLSM_OPT_CHAIN_KERNEL = 12,     /* dlsm_chain_kernel: the one-CTA-per-chain sweep kernel (exact likelihoods) */
+    DLSM_OPT_CC_KERNEL = 13,        /* 1: first-generation batch-parallel case-control sweep (k_sweep_cc) */
     DLSM_OPT_COUNT_
 } dlsm_option;
 typedef enum {
@@ -176,6 +177,15 @@ int dlsm_set_network_dense(dlsm_handle *h, const double *Y);
  * in_edges (T,n,max_in), out_edges (T,n,max_out), zero-padded. */
 int dlsm_set_edge_lists(dlsm_handle *h, const int32_t *degrees, const int32_t *in_edges,
                         int32_t max_in, const int32_t *out_edges, int32_t max_out);
+/* The same bookkeeping built ON THE DEVICE from the ties themselves: edges (n_edges, 3) int32 rows
+ * (t, sender, receiver), any order, every tie once, no self ties.  Produces what the reference derives
+ * from the dense tensor -- degrees, in/out lists in ascending order, zero-padded to the largest degree
+ * (case_control_likelihood.py:44-70) -- in O(n_edges) work.  dlsm_edge_list_dims / dlsm_get_edge_lists
+ * read the lists back (degrees (T,n,2), in_edges (T,n,max_in), out_edges (T,n,max_out); list pointers
+ * may be NULL). */
+int dlsm_set_network_edges(dlsm_handle *h, const int32_t *edges, size_t n_edges);
+int dlsm_edge_list_dims(dlsm_handle *h, int32_t *max_in, int32_t *max_out);
+int dlsm_get_edge_lists(dlsm_handle *h, int32_t *degrees, int32_t *in_edges, int32_t *out_edges);
 /* control sets (case_control_likelihood.py:75-112): (S,T,n,n_control), -1 padded, where S = 1
  * (shared by all chains) or S = n_chains */
 int dlsm_set_controls(dlsm_handle *h, const int32_t *ctrl_in, const int32_t *ctrl_out,

@@ -201,7 +201,7 @@ def _sparse_directed(rng, T, n, out_deg):
     return deg, in_e, out_e
 
 
-@pytest.mark.parametrize("mode", ["chain", "slice", "slice-plain"])
+@pytest.mark.parametrize("mode", ["chain", "slice", "slice-v1", "slice-plain"])
 @pytest.mark.parametrize("T,n,m,per_chain", [(3, 400, 8, False), (2, 150, 5, True), (4, 70, 20, False)])
 def test_case_control_sweep_all_mappings(T, n, m, per_chain, mode, monkeypatch):
     """The case-control sweep (directed_likelihoods_fast.pyx:83-182 inside
@@ -210,6 +210,9 @@ def test_case_control_sweep_all_mappings(T, n, m, per_chain, mode, monkeypatch):
     concurrently, k_sweep_cc) and the serial CTA-per-slice kernel ("slice-plain") all make the
     oracle's decisions and leave its positions."""
     L = _L()
+    if mode == "slice-v1":        # first-generation batch-parallel kernel (k_sweep_cc); "slice" = k_sweep_cc2
+        monkeypatch.setenv("DLSM_CC_V1", "1")
+        mode = "slice"
     monkeypatch.setenv("DLSM_SWEEP_MODE", mode)
     rng = np.random.RandomState(n + m)
     d, C_ = 2, 2
@@ -288,3 +291,36 @@ def test_device_loop_centring_tree_vs_exact(monkeypatch):
     assert np.all(np.abs(outs[0].mean(axis=(1, 2))) < 1e-15)
     assert np.allclose(outs[0], outs[1], rtol=0, atol=1e-14)
     assert not np.allclose(outs[0], X0 - X0.mean(axis=(1, 2), keepdims=True), atol=1e-6)   # it moved
+
+
+# ------------------------------------------------------------------------------------------
+# sparse network input: the case-control edge lists built on the device from the ties
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,n,density,seed", [(3, 40, 0.2, 1), (2, 300, 0.02, 2), (4, 65, 0.6, 3), (1, 5, 0.0, 4)])
+def test_device_edge_lists_equal_the_host_sampler_init(T, n, density, seed):
+    """dlsm_set_network_edges (count / fill / sort on the device) == DirectedCaseControlSampler.init
+    on the dense tensor (the reference's construction, case_control_likelihood.py:37-73)."""
+    from dynetlsm_b200 import _lib as L
+    from dynetlsm_b200.case_control_likelihood import DirectedCaseControlSampler
+    rng = np.random.RandomState(seed)
+    Y = (rng.rand(T, n, n) < density).astype(np.float64)
+    for t in range(T):
+        np.fill_diagonal(Y[t], 0)
+    host = DirectedCaseControlSampler(n_control=5, random_state=0).init(Y, sample=False)
+    edges = np.argwhere(Y == 1).astype(np.int32)
+    edges = edges[rng.permutation(edges.shape[0])]           # any order
+    e = L.Engine(T=T, n=n, d=2, is_directed=True, case_control=True)
+    e.set_network_edges(edges)
+    dg, ie, oe = e.get_edge_lists()
+    assert np.array_equal(dg, host.degrees_)
+    assert ie.shape == host.in_edges_.shape and np.array_equal(ie, host.in_edges_)
+    assert oe.shape == host.out_edges_.shape and np.array_equal(oe, host.out_edges_)
+    if edges.shape[0]:
+        bad = edges.copy(); bad[0, 2] = bad[0, 1]             # a self tie
+        with pytest.raises(L.DlsmError):
+            e.set_network_edges(bad)
+        with pytest.raises(L.DlsmError):
+            e.set_network_edges(np.concatenate([edges, edges[:1]]))   # a tie listed twice
+        bad = edges.copy(); bad[0, 0] = T
+        with pytest.raises(L.DlsmError):
+            e.set_network_edges(bad)

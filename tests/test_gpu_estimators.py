@@ -166,3 +166,78 @@ def test_hdp_device_chains_match_replay_in_distribution():
     truth = np.random.RandomState(7).randint(0, 2, 36)   # the generator's communities
     same = truth[:, None] == truth[None, :]
     assert ca[0][same].mean() > ca[0][~same].mean() + 0.2  # and both recover the communities
+
+
+def test_sparse_network_fit_builds_the_case_control_lists_on_the_device():
+    """fit() on a SparseNetwork (ties only, the way a network too large for a dense tensor arrives):
+    the degree / edge lists mirrored under the reference's attribute names equal the host
+    construction from the dense tensor (case_control_likelihood.py:37-73), the chain runs on the
+    case-control kernels and gives a finite, improving log-posterior."""
+    from dynetlsm_b200 import DynamicNetworkLSM
+    from dynetlsm_b200.case_control_likelihood import DirectedCaseControlSampler, SparseNetwork
+    rng = np.random.RandomState(4)
+    T, n = 3, 60
+    Xtrue = np.cumsum(rng.randn(T, n, 2) * np.array([1.0, 0.05, 0.05])[:, None, None], axis=0) / n
+    dist = np.sqrt(((Xtrue[:, :, None] - Xtrue[:, None]) ** 2).sum(-1))
+    radii = rng.dirichlet(np.ones(n) * 10)
+    eta = 0.5 * (1 - dist / radii[None, None, :]) + 0.5 * (1 - dist / radii[None, :, None])
+    Y = (rng.rand(T, n, n) < 1 / (1 + np.exp(-eta))).astype(np.float64)
+    for t in range(T):
+        np.fill_diagonal(Y[t], 0)
+    net = SparseNetwork.from_dense(Y)
+    assert np.array_equal(net.toarray(), Y)
+    m = DynamicNetworkLSM(n_iter=60, tune=40, burn=40, is_directed=True, n_control=10, n_resample_control=20,
+                          step_size_X=0.05 / n, sigma_sq=1e-4, tau_sq="auto", random_state=1, n_chains=2)
+    m.fit(net, X_init=Xtrue + 0.1 / n * rng.randn(T, n, 2), radii_init=radii, intercept_init=[0.4, 0.6])
+    host = DirectedCaseControlSampler(n_control=10, random_state=0).init(Y, sample=False)
+    cc = m.case_control_sampler_
+    assert np.array_equal(cc.degrees_, host.degrees_)
+    assert np.array_equal(cc.in_edges_, host.in_edges_) and np.array_equal(cc.out_edges_, host.out_edges_)
+    assert m.Xs_.shape == (140, T, n, 2) and np.all(np.isfinite(m.logps_))
+    assert cc.control_nodes_in_.shape == (T, n, 10)
+    assert m.logps_[70:].mean() > m.logps_[:10].mean() - 50
+    # a sequence of scipy.sparse matrices is accepted as well; without starting values the chain still runs
+    import scipy.sparse as sp
+    m2 = DynamicNetworkLSM(n_iter=10, tune=10, burn=10, is_directed=True, n_control=10, step_size_X=0.05 / n,
+                           sigma_sq=1e-4, tau_sq="auto", random_state=2)
+    m2.fit([sp.csr_matrix(Y[t]) for t in range(T)])
+    assert np.all(np.isfinite(m2.logps_)) and np.array_equal(m2.case_control_sampler_.degrees_, host.degrees_)
+    with pytest.raises(ValueError):
+        DynamicNetworkLSM(n_iter=5, is_directed=True).fit(net)      # no case-control likelihood
+
+
+@pytest.mark.parametrize("selection,thin", [("vi", None), ("bic", None), ("map", None), ("vi", 4)])
+def test_hdp_selection_types_and_thinning(selection, thin):
+    """The reference's point-estimate selection on the device traces (hdp_lpcm.py:1089-1170):
+    'vi' = minimum posterior-expected VI over the co-clustering probabilities, 'bic' / 'map' through
+    the approximate BIC table; burn-in counted in STORED samples when the trace is thinned
+    (hdp_lpcm.py:458-465)."""
+    from dynetlsm_b200 import DynamicNetworkHDPLPCM
+    from dynetlsm_b200 import model_selection as MS
+    Y = _splitting_network(n=30, T=3, seed=3)
+    m = DynamicNetworkHDPLPCM(n_iter=120, tune=60, burn=60, n_components=5, selection_type=selection, thin=thin,
+                              random_state=3).fit(Y)
+    S = 240 if thin is None else 60
+    nb = 120 if thin is None else 30
+    assert m.zs_.shape[0] == S and m.n_burn_ == nb
+    assert m.bic_.shape[1] == 4 and len(m.models_) == m.bic_.shape[0] and m.counts_.shape == (S - nb,)
+    assert set(m.bic_[:, 0].astype(int)) == set(np.unique(m.counts_))
+    assert len(m.posterior_group_ids_) == 3 and all(c.sum() == S - nb for c in m.posterior_group_counts_)
+    assert m.cooccurrence_probas_.shape == (3, 30, 30) and np.allclose(np.diagonal(m.cooccurrence_probas_, axis1=1, axis2=2), 1)
+    if selection == "vi":
+        vis = MS.expected_vi_trace(m.zs_[nb:], m.cooccurrence_probas_, 5)
+        assert m.selected_id_ >= nb and vis[m.selected_id_ - nb] == vis.min()
+    else:
+        k = m.best_k_
+        row = m.bic_[m.bic_[:, 0] == k][0]
+        assert m.selected_id_ == int(row[3])
+        if selection == "bic":
+            assert row[1] == m.bic_[:, 1].min()
+        else:
+            assert k == np.argmax(np.bincount(m.counts_))
+    assert m.z_.max() + 1 == m.mu_.shape[0] == m.sigma_.shape[0] == m.init_weights_.shape[0]
+    assert np.allclose(m.init_weights_.sum(), 1) and np.allclose(m.trans_weights_[1:].sum(axis=2), 1)
+    z, pval = m.logp_geweke_
+    assert np.isfinite(z) and 0 <= pval <= 1
+    with pytest.raises(ValueError):
+        DynamicNetworkHDPLPCM(n_iter=5, selection_type="aic").fit(Y)
