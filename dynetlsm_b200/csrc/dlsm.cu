@@ -276,7 +276,7 @@ void read_env_options(dlsm_handle *h)
         h->opt[DLSM_OPT_CHAIN_KERNEL] = !strcmp(m, "block") ? DLSM_CHAIN_BLOCK
                                         : !strcmp(m, "node") ? DLSM_CHAIN_NODE
                                         : !strcmp(m, "rowsum") ? DLSM_CHAIN_NODE_ROWSUM : DLSM_CHAIN_AUTO;
-    h->opt[DLSM_OPT_CC_KERNEL] = on("DLSM_CC_V1");
+    h->opt[DLSM_OPT_CC_KERNEL] = on("DLSM_CC_V2") ? 2 : 0;
     if (const char *m = getenv("DLSM_NO_CLUSTER")) h->opt[DLSM_OPT_NO_CLUSTER] = atoll(m) > 0 ? atoll(m) : 1;
     if (const char *m = getenv("DLSM_TRACE_CHUNK_BYTES")) h->opt[DLSM_OPT_TRACE_CHUNK_BYTES] = atoll(m);
     apply_sweep_mode(h);
@@ -530,7 +530,7 @@ int launch_cc_batch(dlsm_handle *h, const SweepParams &p)
     }
     CU(h, cudaMemsetAsync(h->d_progress, 0, CT * sizeof(int), h->stream));
     CU(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
-    if (c.d == 2 && h->n_control <= 128 && !h->opt[DLSM_OPT_CC_KERNEL] &&
+    if (c.d == 2 && h->n_control <= 128 && h->opt[DLSM_OPT_CC_KERNEL] == 2 &&
         cc2_smem_bytes(h->max_in, h->max_out, h->n_control) <= kMaxSmem) {
         // second generation: list indices staged per 32-node block, 256-bit gather records
         const size_t cells = (size_t)c.n_chains * c.T * c.n;

@@ -195,7 +195,8 @@ def test_sparse_network_fit_builds_the_case_control_lists_on_the_device():
     assert np.array_equal(cc.in_edges_, host.in_edges_) and np.array_equal(cc.out_edges_, host.out_edges_)
     assert m.Xs_.shape == (140, T, n, 2) and np.all(np.isfinite(m.logps_))
     assert cc.control_nodes_in_.shape == (T, n, 10)
-    assert m.logps_[70:].mean() > m.logps_[:10].mean() - 50
+    assert m.logps_[70:].mean() > m.logps_[:10].mean() - 0.1 * abs(m.logps_[:10].mean())   # (a noisy estimator: controls are redrawn)
+    assert not np.array_equal(m.Xs_[-1], m.Xs_[0])
     # a sequence of scipy.sparse matrices is accepted as well; without starting values the chain still runs
     import scipy.sparse as sp
     m2 = DynamicNetworkLSM(n_iter=10, tune=10, burn=10, is_directed=True, n_control=10, step_size_X=0.05 / n,
