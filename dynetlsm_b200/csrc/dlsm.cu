@@ -73,6 +73,7 @@ struct dlsm_handle {
     int cluster_cs = -1;            // CTAs per (chain, slice) cluster (-1: not probed, 0: none)
     int cluster_ncomp = 0;          // compute warps per CTA (per-node cluster kernel) / warps per CTA (block kernel)
     bool cluster_blk = false;       // block-speculative kernel (k_sweep_blk) rather than the per-node one
+    int cc3_ok = -1;                // 2-CTA-cluster case-control sweep: all C*T clusters co-resident? (-1: not probed)
     // developer options (dlsm_set_option; environment defaults are read ONCE, in dlsm_create)
     int64_t opt[DLSM_OPT_COUNT_] = {0};
     // rng
@@ -276,7 +277,7 @@ void read_env_options(dlsm_handle *h)
         h->opt[DLSM_OPT_CHAIN_KERNEL] = !strcmp(m, "block") ? DLSM_CHAIN_BLOCK
                                         : !strcmp(m, "node") ? DLSM_CHAIN_NODE
                                         : !strcmp(m, "rowsum") ? DLSM_CHAIN_NODE_ROWSUM : DLSM_CHAIN_AUTO;
-    h->opt[DLSM_OPT_CC_KERNEL] = on("DLSM_CC_V2") ? 2 : 0;
+    if (const char *m = getenv("DLSM_CC_KERNEL")) h->opt[DLSM_OPT_CC_KERNEL] = atoll(m);
     if (const char *m = getenv("DLSM_NO_CLUSTER")) h->opt[DLSM_OPT_NO_CLUSTER] = atoll(m) > 0 ? atoll(m) : 1;
     if (const char *m = getenv("DLSM_TRACE_CHUNK_BYTES")) h->opt[DLSM_OPT_TRACE_CHUNK_BYTES] = atoll(m);
     apply_sweep_mode(h);
@@ -530,7 +531,22 @@ int launch_cc_batch(dlsm_handle *h, const SweepParams &p)
     }
     CU(h, cudaMemsetAsync(h->d_progress, 0, CT * sizeof(int), h->stream));
     CU(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
-    if (c.d == 2 && h->n_control <= 128 && h->opt[DLSM_OPT_CC_KERNEL] == 2 &&
+    // DLSM_OPT_CC_KERNEL: 0 auto (the 2-CTA-cluster kernel where all clusters are co-resident), 1 k_sweep_cc,
+    // 2 k_sweep_cc2, 3 k_sweep_cc3
+    const int64_t cck = h->opt[DLSM_OPT_CC_KERNEL];
+    if (c.d == 2 && h->n_control <= 128 && (cck == 0 || cck == 3)) {
+        if (h->cc3_ok < 0) {
+            int active = 0;
+            h->cc3_ok = (cc3_launch(p, nullptr, nullptr, nullptr, h->stream, &active) == cudaSuccess &&
+                         active >= (int)CT) ? 1 : 0;
+            cudaGetLastError();
+        }
+        if (h->cc3_ok) {
+            CU(h, cc3_launch(p, h->d_progress, h->d_ticket, h->d_cc_dep, h->stream, nullptr));
+            return DLSM_OK;
+        }
+    }
+    if (c.d == 2 && h->n_control <= 128 && cck == 2 &&
         cc2_smem_bytes(h->max_in, h->max_out, h->n_control) <= kMaxSmem) {
         // second generation: list indices staged per 32-node block, 256-bit gather records
         const size_t cells = (size_t)c.n_chains * c.T * c.n;
@@ -962,10 +978,12 @@ int dlsm_set_option(dlsm_handle *h, int option, int64_t value)
         FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_FFBS_KERNEL takes a dlsm_ffbs_kernel value");
     if (value < 0) FAIL(h, DLSM_ERR_INVALID, "option values are non-negative");
     if (option == DLSM_OPT_NO_CLUSTER && value > 2) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_NO_CLUSTER takes 0, 1 or 2");
+    if (option == DLSM_OPT_CC_KERNEL && value > 3) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_CC_KERNEL takes 0..3");
     if (option == DLSM_OPT_CHAIN_KERNEL && value > DLSM_CHAIN_BLOCK) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_CHAIN_KERNEL takes a dlsm_chain_kernel value");
     h->opt[option] = value;
     h->rows_valid = false, h->sweeps_since_set = 0;
     h->cluster_cs = -1;
+    h->cc3_ok = -1;
     if (option == DLSM_OPT_SWEEP_MODE) apply_sweep_mode(h);
     return DLSM_OK;
 }

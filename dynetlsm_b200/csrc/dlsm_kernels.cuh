@@ -236,8 +236,25 @@ __device__ __forceinline__ void node_loglik2(const NetView &net, const double *X
                 }
             }
         };
-        edge_list(ie, indeg, true);  // :108-119
-        edge_list(oe, outdeg, false); // :122-133
+        if (nteam == 1 && indeg <= 16 && outdeg <= 16) {
+            // short lists (the sparse networks this likelihood is for): both in one trip, the in-list on
+            // lanes 0-15 and the out-list on lanes 16-31 -- one pair evaluation per lane instead of four
+            const bool out_side = lane >= 16;
+            const int q = lane & 15;
+            const bool live = q < (out_side ? outdeg : indeg);
+            const int k = live ? (out_side ? oe[q] : ie[q]) : j;
+            double xk[DM];
+            load_pos<DM>(Xt + (size_t)k * d, d, xk);
+            const double rk = rinv[k];
+            const double dn = fast_dist<DM>(xk, xn, d), dd = fast_dist<DM>(xk, xo, d);
+            const double r_recv = out_side ? rk : rj, r_send = out_side ? rj : rk; // in-list: k sends to node
+            const double tn = logit_term(0.5, eta_directed(b0, b1, dn, r_recv, r_send));
+            const double to = logit_term(0.5, eta_directed(b0, b1, dd, r_recv, r_send));
+            if (live) { e_n += tn; e_o += to; }
+        } else {
+            edge_list(ie, indeg, true);  // :108-119
+            edge_list(oe, outdeg, false); // :122-133
+        }
         int m = net.n_control, m_out;
         if (nteam == 1 && net.n_control <= 128) {
             // all control indices of the node in registers with one round trip (4 + 4 loads)

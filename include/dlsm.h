@@ -134,7 +134,7 @@ int dlsm_synchronize(dlsm_handle *h);
  * DLSM_SWEEP_MODE=chain|chain-dense|slice|slice-plain, DLSM_FFBS=thread|warp, DLSM_FFBS_SMEM,
  * DLSM_FFBS_PER_SM=<n>, DLSM_NO_GATHER_PACK, DLSM_NO_LLCUR, DLSM_CENTER_EXACT, DLSM_HDP_SEGMENTED,
  * DLSM_NO_EARLY_X, DLSM_TRACE_CHUNK_BYTES=<bytes>, DLSM_NO_ROWSUM, DLSM_NO_CLUSTER=1|2,
- * DLSM_CHAIN_KERNEL=rowsum|node|block, DLSM_CC_V2. */
+ * DLSM_CHAIN_KERNEL=rowsum|node|block, DLSM_CC_KERNEL=1|2|3. */
 typedef enum {
     DLSM_OPT_SWEEP_MODE = 0,        /* dlsm_sweep_mode: which latent-sweep kernel (default: heuristic) */
     DLSM_OPT_FFBS_KERNEL = 1,       /* dlsm_ffbs_kernel: label kernel mapping */
@@ -152,9 +152,10 @@ typedef enum {
                                        thread-block cluster per pair (k_sweep_blk), 1 = no clusters (CTA per
                                        pair), 2 = per-node cluster kernel (k_sweep_slice_cl) */
     DLSM_OPT_CHAIN_KERNEL = 12,     /* dlsm_chain_kernel: the one-CTA-per-chain sweep kernel (exact likelihoods) */
-    DLSM_OPT_CC_KERNEL = 13,        /* 2: the batch-parallel case-control sweep with per-block list staging and
-                                       256-bit gather records (k_sweep_cc2; measured 7 % slower than k_sweep_cc
-                                       at cfg 5, kept as a tested variant) */
+    DLSM_OPT_CC_KERNEL = 13,        /* batch-parallel case-control sweep: 0 = auto (k_sweep_cc3, a 2-CTA cluster per
+                                       (chain, slice), where all clusters are co-resident, else k_sweep_cc),
+                                       1 = k_sweep_cc, 2 = k_sweep_cc2 (per-block list staging, 256-bit gather
+                                       records), 3 = k_sweep_cc3 */
     DLSM_OPT_COUNT_
 } dlsm_option;
 typedef enum {

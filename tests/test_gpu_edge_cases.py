@@ -201,7 +201,7 @@ def _sparse_directed(rng, T, n, out_deg):
     return deg, in_e, out_e
 
 
-@pytest.mark.parametrize("mode", ["chain", "slice", "slice-v2", "slice-plain"])
+@pytest.mark.parametrize("mode", ["chain", "slice", "slice-v1", "slice-v2", "slice-plain"])
 @pytest.mark.parametrize("T,n,m,per_chain", [(3, 400, 8, False), (2, 150, 5, True), (4, 70, 20, False)])
 def test_case_control_sweep_all_mappings(T, n, m, per_chain, mode, monkeypatch):
     """The case-control sweep (directed_likelihoods_fast.pyx:83-182 inside
@@ -210,8 +210,8 @@ def test_case_control_sweep_all_mappings(T, n, m, per_chain, mode, monkeypatch):
     concurrently, k_sweep_cc) and the serial CTA-per-slice kernel ("slice-plain") all make the
     oracle's decisions and leave its positions."""
     L = _L()
-    if mode == "slice-v2":        # k_sweep_cc2 (per-block list staging); "slice" = k_sweep_cc
-        monkeypatch.setenv("DLSM_CC_V2", "1")
+    if mode in ("slice-v1", "slice-v2"):   # k_sweep_cc / k_sweep_cc2; "slice" = auto = the 2-CTA-cluster kernel k_sweep_cc3
+        monkeypatch.setenv("DLSM_CC_KERNEL", mode[-1])
         mode = "slice"
     monkeypatch.setenv("DLSM_SWEEP_MODE", mode)
     rng = np.random.RandomState(n + m)
