@@ -15,9 +15,9 @@ LIB_PATH = os.environ.get("DLSM_LIB") or os.path.join(HERE, "libdlsm.so")   # DL
 CSRC = os.path.join(HERE, "csrc")
 # translation units -> the headers each depends on (mtime-based rebuild of the unit's object file)
 HEADERS = [os.path.join(CSRC, f) for f in ("dlsm_kernels.cuh", "dlsm_device.cuh", "dlsm_tables.cuh",
-                                            "dlsm_hdp.cuh", "dlsm_trace.cuh", "dlsm_blk.h", "dlsm_graph.h", "dlsm_cc.h")]
+                                            "dlsm_hdp.cuh", "dlsm_trace.cuh", "dlsm_blk.h", "dlsm_graph.h", "dlsm_cc.h", "dlsm_ccd.h")]
 HEADERS.append(os.path.join(ROOT, "include", "dlsm.h"))
-UNITS = [os.path.join(CSRC, f) for f in ("dlsm.cu", "dlsm_blk.cu", "dlsm_graph.cu", "dlsm_cc.cu")]
+UNITS = [os.path.join(CSRC, f) for f in ("dlsm.cu", "dlsm_blk.cu", "dlsm_graph.cu", "dlsm_cc.cu", "dlsm_ccd.cu")]
 SRC = UNITS + HEADERS
 OBJ_DIR = os.path.join(HERE, "build")
 

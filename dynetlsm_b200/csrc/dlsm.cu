@@ -7,6 +7,7 @@
 #include "dlsm_blk.h"
 #include "dlsm_graph.h"
 #include "dlsm_cc.h"
+#include "dlsm_ccd.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -106,6 +107,8 @@ struct dlsm_handle {
     uint32_t *d_cooc = nullptr;     // [T][n][n] co-clustering counts accumulated by dlsm_run_traced
     uint64_t cooc_samples = 0;
     double *d_gather = nullptr;     // [C][T][n][4] packed {x, y, 1/r, 0} records of the case-control kernels
+    CcdWork *ccd = nullptr;         // buffers of the dataflow case-control sweep (dlsm_ccd.cu)
+    double *d_radii_terms = nullptr; // [C][chunks][6] Dirichlet terms / gamma totals of the radii MH
     double *d_center = nullptr;     // means [C][8] + partial sums [C][128][8] of the long-chain centring
     double *d_proc_ref = nullptr;   // [C][T][n][d] reference configuration of the in-loop Procrustes
     bool have_proc_ref = false;
@@ -519,6 +522,17 @@ int launch_cc_batch(dlsm_handle *h, const SweepParams &p)
 {
     const dlsm_config &c = h->cfg;
     const size_t CT = (size_t)c.n_chains * c.T;
+    // DLSM_OPT_CC_KERNEL: 0 auto (the dataflow kernel), 1 k_sweep_cc, 2 k_sweep_cc2, 3 k_sweep_cc3 (runs of
+    // mutually independent nodes), 4 k_sweep_ccd (dataflow over nodes, double-buffered positions)
+    const int64_t cck = h->opt[DLSM_OPT_CC_KERNEL];
+    if (c.d == 2 && h->n_control <= 128 && (cck == 0 || cck == 4)) {
+        const size_t cells = CT * c.n;
+        if (!h->d_gather) CU(h, cudaMalloc((void **)&h->d_gather, cells * 4 * sizeof(double)));
+        int launches = 0;
+        CU(h, ccd_launch(p, h->d_gather, &h->ccd, h->sm_count, h->stream, &launches));
+        h->ctr.kernel_launches += launches - 1;
+        return DLSM_OK;
+    }
     if (!h->cc_dep_valid) {
         const size_t cells = (size_t)h->ctrl_sets * c.T * c.n;
         cudaFree(h->d_cc_dep);
@@ -531,10 +545,7 @@ int launch_cc_batch(dlsm_handle *h, const SweepParams &p)
     }
     CU(h, cudaMemsetAsync(h->d_progress, 0, CT * sizeof(int), h->stream));
     CU(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
-    // DLSM_OPT_CC_KERNEL: 0 auto (the 2-CTA-cluster kernel where all clusters are co-resident), 1 k_sweep_cc,
-    // 2 k_sweep_cc2, 3 k_sweep_cc3
-    const int64_t cck = h->opt[DLSM_OPT_CC_KERNEL];
-    if (c.d == 2 && h->n_control <= 128 && (cck == 0 || cck == 3)) {
+    if (c.d == 2 && h->n_control <= 128 && cck == 3) {
         if (h->cc3_ok < 0) {
             int active = 0;
             h->cc3_ok = (cc3_launch(p, nullptr, nullptr, nullptr, h->stream, &active) == cudaSuccess &&
@@ -787,7 +798,7 @@ int refresh_rows(dlsm_handle *h)
                            (const double *)F<double>(h, DLSM_F_INTERCEPT), h->d_bvar);
     if (rc == DLSM_OK) rc = launch_rows(h, h->rinv);
     if (rc == DLSM_OK)
-        rc = launch_simple(h, k_sum_partials, dim3((C + 127) / 128), dim3(128), 0, C, rows_nblk(h),
+        rc = launch_simple(h, k_sum_partials, dim3((C + 3) / 4), dim3(128), 0, C, rows_nblk(h),
                            (const double *)h->d_partial, h->d_ll2, F<double>(h, DLSM_F_LOGLIK));
     if (rc == DLSM_OK) rc = commit_rows(h, nullptr);
     if (rc == DLSM_OK) h->rows_valid = true;
@@ -959,6 +970,8 @@ void dlsm_destroy(dlsm_handle *h)
     cudaFree(h->d_center);
     cudaFree(h->d_cooc);
     cudaFree(h->d_gather);
+    ccd_free(h->ccd);
+    cudaFree(h->d_radii_terms);
     cudaFree(h->d_proc_ref);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -978,7 +991,7 @@ int dlsm_set_option(dlsm_handle *h, int option, int64_t value)
         FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_FFBS_KERNEL takes a dlsm_ffbs_kernel value");
     if (value < 0) FAIL(h, DLSM_ERR_INVALID, "option values are non-negative");
     if (option == DLSM_OPT_NO_CLUSTER && value > 2) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_NO_CLUSTER takes 0, 1 or 2");
-    if (option == DLSM_OPT_CC_KERNEL && value > 3) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_CC_KERNEL takes 0..3");
+    if (option == DLSM_OPT_CC_KERNEL && value > 4) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_CC_KERNEL takes 0..4");
     if (option == DLSM_OPT_CHAIN_KERNEL && value > DLSM_CHAIN_BLOCK) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_CHAIN_KERNEL takes a dlsm_chain_kernel value");
     h->opt[option] = value;
     h->rows_valid = false, h->sweeps_since_set = 0;
@@ -1325,7 +1338,7 @@ static int intercepts_async(dlsm_handle *h, const double *d_eps, const double *d
         if (rows) rc = launch_rows(h, h->rinv); // the proposal's log-likelihood AND its row sums
         else rc = launch_full(h, h->rinv, h->rinv, use_cur ? 1 : 2);
         if (rc != DLSM_OK) return rc;
-        if ((rc = launch_simple(h, k_intercept_finalize, g1, b1, 0, p)) != DLSM_OK) return rc;
+        if ((rc = launch_simple(h, k_intercept_finalize, dim3((C + 3) / 4), b1, 0, p)) != DLSM_OK) return rc; // warp per chain
         if (rows && (rc = commit_rows(h, h->d_accflag)) != DLSM_OK) return rc; // accepted chains adopt them
     }
     end_phase(h);
@@ -1364,11 +1377,16 @@ static int radii_async(dlsm_handle *h, bool native, const double *d_logu, int32_
     begin_phase(h, 1);
     int rc;
     const uint32_t site0 = (uint32_t)((size_t)h->cfg.T * n + 8);
+    const int chunks = (n + kRadiiChunk - 1) / kRadiiChunk;
+    if (!h->d_radii_terms) CU(h, cudaMalloc((void **)&h->d_radii_terms, (size_t)C * chunks * 6 * sizeof(double)));
     if (native) {
-        rc = launch_simple(h, k_radii_propose, dim3(C), dim3(256), 0, n,
+        rc = launch_simple(h, k_radii_gammas, dim3(chunks, C), dim3(256), 0, n,
                            (const double *)F<double>(h, DLSM_F_RADII),
-                           (const double *)F<double>(h, DLSM_F_R_STEP), h->d_rprop, h->d_rprop_inv,
+                           (const double *)F<double>(h, DLSM_F_R_STEP), h->d_rprop, h->d_radii_terms,
                            h->seed, h->sweep_idx[kRngRadii], (uint32_t)h->chain_offset, site0);
+        if (rc != DLSM_OK) return rc;
+        rc = launch_simple(h, k_radii_propose, dim3(C), dim3(1024), 0, n, chunks, (const double *)h->d_radii_terms,
+                           h->d_rprop, h->d_rprop_inv);
     } else {
         const size_t total = (size_t)C * n;
         rc = launch_simple(h, k_rinv, dim3((unsigned)((total + 255) / 256)), dim3(256), 0,
@@ -1397,7 +1415,9 @@ static int radii_async(dlsm_handle *h, bool native, const double *d_logu, int32_
     p.chain_offset = (uint32_t)h->chain_offset; p.site = site0;
     p.accepted = d_acc; p.ratio = d_ratio; p.flags = h->d_flags;
     p.ll_cur = use_cur ? F<double>(h, DLSM_F_LOGLIK) : nullptr; p.use_cur = use_cur ? 1 : 0;
-    rc = launch_simple(h, k_radii_finalize, dim3(C), dim3(256), 0, p);
+    rc = launch_simple(h, k_radii_terms, dim3(chunks, C), dim3(256), 0, p, h->d_radii_terms);
+    if (rc != DLSM_OK) return rc;
+    rc = launch_simple(h, k_radii_finalize, dim3(C), dim3(256), 0, p, (const double *)h->d_radii_terms, chunks);
     if (rc == DLSM_OK && rows) rc = commit_rows(h, h->d_accflag);
     end_phase(h);
     if (native) h->sweep_idx[kRngRadii] += 1;
@@ -1694,7 +1714,7 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
                            (const double *)F<double>(h, DLSM_F_INTERCEPT), h->d_bvar);
         if (rc == DLSM_OK) rc = launch_full(h, h->rinv, h->rinv, 1);
         if (rc == DLSM_OK)
-            rc = launch_simple(h, k_sum_partials, dim3((C + 127) / 128), dim3(128), 0, C, h->full_nblk,
+            rc = launch_simple(h, k_sum_partials, dim3((C + 3) / 4), dim3(128), 0, C, h->full_nblk,
                                (const double *)h->d_partial, h->d_ll2, F<double>(h, DLSM_F_LOGLIK));
         if (rc != DLSM_OK) return rc;
         tl_end(h);
@@ -1750,7 +1770,7 @@ static int logp_async(dlsm_handle *h, double *out_dev, bool ll_tracked)
                            (const double *)F<double>(h, DLSM_F_INTERCEPT), h->d_bvar);
         if (rc != DLSM_OK) return rc;
         if ((rc = launch_full(h, h->rinv, h->rinv, 1)) != DLSM_OK) return rc;
-        rc = launch_simple(h, k_sum_partials, dim3((c.n_chains + 127) / 128), dim3(128), 0, c.n_chains,
+        rc = launch_simple(h, k_sum_partials, dim3((c.n_chains + 3) / 4), dim3(128), 0, c.n_chains,
                            h->full_nblk, (const double *)h->d_partial, h->d_ll2, (double *)nullptr);
         if (rc != DLSM_OK) return rc;
         p.ll = h->d_ll2; p.ll_stride = 2;
@@ -2118,7 +2138,7 @@ int dlsm_loglik_full(dlsm_handle *h, double *out)
                        (const double *)F<double>(h, DLSM_F_INTERCEPT), h->d_bvar);
     if (rc != DLSM_OK) return rc;
     if ((rc = launch_full(h, h->rinv, h->rinv)) != DLSM_OK) return rc;
-    rc = launch_simple(h, k_sum_partials, dim3((C + 127) / 128), dim3(128), 0, C, h->full_nblk,
+    rc = launch_simple(h, k_sum_partials, dim3((C + 3) / 4), dim3(128), 0, C, h->full_nblk,
                        (const double *)h->d_partial, h->d_ll2, (double *)nullptr);
     if (rc != DLSM_OK) return rc;
     std::vector<double> tmp((size_t)C * 2);

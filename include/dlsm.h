@@ -152,10 +152,11 @@ typedef enum {
                                        thread-block cluster per pair (k_sweep_blk), 1 = no clusters (CTA per
                                        pair), 2 = per-node cluster kernel (k_sweep_slice_cl) */
     DLSM_OPT_CHAIN_KERNEL = 12,     /* dlsm_chain_kernel: the one-CTA-per-chain sweep kernel (exact likelihoods) */
-    DLSM_OPT_CC_KERNEL = 13,        /* batch-parallel case-control sweep: 0 = auto (k_sweep_cc3, a 2-CTA cluster per
-                                       (chain, slice), where all clusters are co-resident, else k_sweep_cc),
-                                       1 = k_sweep_cc, 2 = k_sweep_cc2 (per-block list staging, 256-bit gather
-                                       records), 3 = k_sweep_cc3 */
+    DLSM_OPT_CC_KERNEL = 13,        /* case-control sweep of (chain, slice) pairs: 0 = auto (k_sweep_ccd: dataflow
+                                       over nodes, positions double-buffered for the sweep, d = 2 and <= 128
+                                       controls; else k_sweep_cc), 1 = k_sweep_cc (runs of mutually independent
+                                       nodes), 2 = k_sweep_cc2 (per-block list staging, 256-bit gather records),
+                                       3 = k_sweep_cc3 (2-CTA cluster per pair), 4 = k_sweep_ccd */
     DLSM_OPT_COUNT_
 } dlsm_option;
 typedef enum {

@@ -201,16 +201,17 @@ def _sparse_directed(rng, T, n, out_deg):
     return deg, in_e, out_e
 
 
-@pytest.mark.parametrize("mode", ["chain", "slice", "slice-v1", "slice-v2", "slice-plain"])
+@pytest.mark.parametrize("mode", ["chain", "slice", "slice-v1", "slice-v2", "slice-v3", "slice-plain"])
 @pytest.mark.parametrize("T,n,m,per_chain", [(3, 400, 8, False), (2, 150, 5, True), (4, 70, 20, False)])
 def test_case_control_sweep_all_mappings(T, n, m, per_chain, mode, monkeypatch):
     """The case-control sweep (directed_likelihoods_fast.pyx:83-182 inside
     sample_latent_positions.py:92-146) with recorded draws against the oracle: warp per slice
     ("chain"), batch-parallel CTA per slice ("slice": runs of mutually independent nodes updated
-    concurrently, k_sweep_cc) and the serial CTA-per-slice kernel ("slice-plain") all make the
-    oracle's decisions and leave its positions."""
+    concurrently, k_sweep_cc / _cc2 / _cc3; auto = the dataflow kernel k_sweep_ccd, which hands nodes to
+    warps in index order and waits per dependency) and the serial CTA-per-slice kernel ("slice-plain")
+    all make the oracle's decisions and leave its positions."""
     L = _L()
-    if mode in ("slice-v1", "slice-v2"):   # k_sweep_cc / k_sweep_cc2; "slice" = auto = the 2-CTA-cluster kernel k_sweep_cc3
+    if mode in ("slice-v1", "slice-v2", "slice-v3"):   # k_sweep_cc / _cc2 / _cc3; "slice" = auto = the dataflow kernel k_sweep_ccd
         monkeypatch.setenv("DLSM_CC_KERNEL", mode[-1])
         mode = "slice"
     monkeypatch.setenv("DLSM_SWEEP_MODE", mode)
