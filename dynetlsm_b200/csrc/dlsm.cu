@@ -670,7 +670,8 @@ int launch_full(dlsm_handle *h, const double *rinv0, const double *rinv1, int nv
     p.rinv0 = rinv0; p.rinv1 = rinv1;
     p.partial = h->d_partial;
     p.flags = h->d_flags;
-    if (h->lk == kCaseControl && h->cfg.d == 2 && nv == 1 && !h->opt[DLSM_OPT_NO_GATHER_PACK]) {
+    p.same_r = (nv == 2 && rinv0 == rinv1) ? 1 : 0;
+    if (h->lk == kCaseControl && h->cfg.d == 2 && (nv == 1 || p.same_r) && !h->opt[DLSM_OPT_NO_GATHER_PACK]) {
         // positions and reciprocal radii of this evaluation as 32-byte records: one 256-bit load
         // per gathered node instead of two loads (the kernel is bound by L1 gather wavefronts)
         const size_t cells = (size_t)h->cfg.n_chains * h->cfg.T * h->cfg.n;
@@ -1308,8 +1309,12 @@ int dlsm_center(dlsm_handle *h)
 }
 
 // device-side part of sample_intercepts; d_eps/d_logu are device pointers or null (native)
+// use_cur: the tracked log-likelihood (DLSM_F_LOGLIK) is current, evaluate proposals only.
+// seed_cur: it is NOT current yet -- the first step evaluates proposal and current state in one pass
+// (two variants per gathered record) and leaves the kept one in DLSM_F_LOGLIK for the steps after it.
 static int intercepts_async(dlsm_handle *h, const double *d_eps, const double *d_logu,
-                            int32_t *d_acc, double *d_ratio, bool use_cur = false, bool rows = false)
+                            int32_t *d_acc, double *d_ratio, bool use_cur = false, bool rows = false,
+                            bool seed_cur = false)
 {
     const int C = h->cfg.n_chains, m = h->cfg.is_directed ? 2 : 1;
     const dim3 g1((C + 127) / 128), b1(128);
@@ -1332,11 +1337,12 @@ static int intercepts_async(dlsm_handle *h, const double *d_eps, const double *d
         p.chain_offset = (uint32_t)h->chain_offset;
         p.site = (uint32_t)((size_t)h->cfg.T * h->cfg.n);
         p.accepted = d_acc; p.ratio = d_ratio; p.flags = h->d_flags;
-        p.ll_cur = use_cur ? F<double>(h, DLSM_F_LOGLIK) : nullptr; p.use_cur = use_cur ? 1 : 0;
+        const bool cur_now = use_cur || (seed_cur && i > 0);
+        p.ll_cur = (cur_now || seed_cur) ? F<double>(h, DLSM_F_LOGLIK) : nullptr; p.use_cur = cur_now ? 1 : 0;
         int rc = launch_simple(h, k_intercept_propose, g1, b1, 0, p);
         if (rc != DLSM_OK) return rc;
         if (rows) rc = launch_rows(h, h->rinv); // the proposal's log-likelihood AND its row sums
-        else rc = launch_full(h, h->rinv, h->rinv, use_cur ? 1 : 2);
+        else rc = launch_full(h, h->rinv, h->rinv, cur_now ? 1 : 2);
         if (rc != DLSM_OK) return rc;
         if ((rc = launch_simple(h, k_intercept_finalize, dim3((C + 3) / 4), b1, 0, p)) != DLSM_OK) return rc; // warp per chain
         if (rows && (rc = commit_rows(h, h->d_accflag)) != DLSM_OK) return rc; // accepted chains adopt them
@@ -1707,7 +1713,12 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
     // kernels) one evaluation of the current state serves all the MH steps of this sweep: 1 + 3
     // variant evaluations instead of 3 x 2.
     const bool any_mh = !(flags & 2u) || (h->cfg.is_directed && !(flags & 4u));
-    if (!use_cur && any_mh && !h->opt[DLSM_OPT_NO_TRACKED_LOGLIK]) {
+    // case-control lists: the full-network kernel is bound by its random 32-byte gathers, a second
+    // variant on the same records is nearly free -- the first intercept step evaluates the current
+    // state along with its proposal instead of a pass of its own
+    const bool seed_cur = !use_cur && !(flags & 2u) && h->lk == kCaseControl && h->cfg.d == 2 &&
+                          !h->opt[DLSM_OPT_NO_TRACKED_LOGLIK] && !h->opt[DLSM_OPT_NO_GATHER_PACK];
+    if (!use_cur && any_mh && !seed_cur && !h->opt[DLSM_OPT_NO_TRACKED_LOGLIK]) {
         const int C = h->cfg.n_chains;
         tl_begin(h, "loglik(current)");
         rc = launch_simple(h, k_bvar_current, dim3((C + 127) / 128), dim3(128), 0, C,
@@ -1722,8 +1733,10 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
     }
     if (tracked) *tracked = use_cur;
     tl_begin(h, "intercepts");
-    if (!(flags & 2u) && (rc = intercepts_async(h, nullptr, nullptr, nullptr, nullptr, use_cur, rows)) != DLSM_OK) return rc;
+    if (!(flags & 2u) && (rc = intercepts_async(h, nullptr, nullptr, nullptr, nullptr, use_cur, rows, seed_cur)) != DLSM_OK) return rc;
     tl_end(h);
+    if (seed_cur) use_cur = true;
+    if (tracked) *tracked = use_cur;
     tl_begin(h, "radii");
     if (h->cfg.is_directed && !(flags & 4u) &&
         (rc = radii_async(h, true, nullptr, nullptr, nullptr, use_cur, rows)) != DLSM_OK)

@@ -1854,6 +1854,7 @@ struct FullParams {
     double *partial;        // [C][T*tiles][2]
     unsigned int *flags;
     const double *gather;   // optional [C][T][n][4] = {x0, x1, 1/r (variant 0), 0}: d = 2 case-control rows
+    int same_r;             // both variants use rinv0 (then the gather records serve NV = 2 as well)
 };
 
 // one 256-bit load (LDG.E.256 on sm_100a): a whole 32-byte gather record with a single L1 wavefront
@@ -1874,6 +1875,13 @@ static __global__ void k_pack_gather(const double *X, const double *rinv, double
     double4 o = make_double4(x.x, x.y, rinv[c * n + j], 0.0);
     reinterpret_cast<double4 *>(G)[g] = o;
 }
+
+// (the packed case-control rows inline the two wrappers of the table-driven softplus)
+#ifdef DLSM_NAIVE_SOFTPLUS
+constexpr bool kFusedSoftplusForms = false;
+#else
+constexpr bool kFusedSoftplusForms = true;
+#endif
 
 // NV = 2: proposal and current variants; NV = 1: proposal only (the device loop tracks the current
 // state's log-likelihood itself, see SweepParams::ll_cur)
@@ -1964,52 +1972,64 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
                                 ((size_t)(p.net.ctrl_per_chain ? c : 0) * T * n + r) * p.net.n_control;
             const double ri0 = r0[i], ri1 = (NV == 2) ? r1[i] : 0.0;
             double e0 = 0.0, e1 = 0.0, c0 = 0.0, c1 = 0.0;
-            const double *Gt = (D == 2 && NV == 1 && p.gather)
+            // gather records serve one variant, or two that share the radii (intercept MH: the proposal
+            // and the current state differ in the intercepts only)
+            const double *Gt = (D == 2 && p.gather && (NV == 1 || p.same_r))
                                    ? p.gather + ((size_t)c * T + t) * n * 4 : nullptr;
             auto terms = [&](int k, double &v0, double &v1) {
-                double xk[DM], rk0;
-                if (D == 2 && NV == 1 && Gt) {
+                double xk[DM], rk0, rk1;
+                if (D == 2 && Gt) {
                     double pad;
                     ld256(Gt + (size_t)k * 4, xk[0], xk[DM > 1 ? 1 : 0], rk0, pad);
+                    rk1 = rk0;
                 } else {
                     load_pos<DM>(Xt + (size_t)k * d, d, xk);
                     rk0 = r0[k];
+                    rk1 = (NV == 2) ? r1[k] : 0.0;
                 }
                 const double dist = fast_dist<DM>(xk, xi, d);
                 v0 = eta_directed(b00, b01, dist, rk0, ri0);
-                v1 = (NV == 2) ? eta_directed(b10, b11, dist, r1[k], ri1) : 0.0;
+                v1 = (NV == 2) ? eta_directed(b10, b11, dist, rk1, ri1) : 0.0;
             };
             int m = p.net.n_control;
-            if (p.net.n_control <= 128 && outdeg <= 64) {
-                // every list index of the row in registers after ONE round trip (2 + 4 loads), then
-                // clamped, masked gathers: the L2 latencies of a row overlap instead of chaining
-                int eo[2], cq[4];
-#pragma unroll
-                for (int u = 0; u < 2; u++) eo[u] = (u * 32 + lane < outdeg) ? oe[u * 32 + lane] : i;
-#pragma unroll
-                for (int u = 0; u < 4; u++) cq[u] = (u * 32 + lane < p.net.n_control) ? co[u * 32 + lane] : 0;
+            if (kFusedSoftplusForms && p.net.n_control + outdeg <= 128) {
+                // One slot space per row: controls [0, nc), then the out-edges [nc, nc + outdeg) -- 110 entries
+                // of cfg 5 fill 4 trips of 32 lanes instead of 2 (edges) + 4 (controls).  Every list index
+                // of the row is in registers after ONE round trip, then clamped, masked gathers: the L2
+                // latencies of a row overlap instead of chaining.  A lane evaluates the expensive part
+                // L = log1p(e^-|eta|) once and wraps it as an edge term or as a control term.
+                const int nc = p.net.n_control, slots = nc + outdeg;
+                int kq[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const unsigned bal = __ballot_sync(kFull, u * 32 + lane < p.net.n_control && cq[u] == -1);
-                    if (bal && m == p.net.n_control) m = u * 32 + __ffs(bal) - 1;
+                    const int q = u * 32 + lane;
+                    kq[u] = q < nc ? co[q] : (q < slots ? oe[q - nc] : i);
                 }
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
+                for (int u = 0; u < 4; u++) {
+                    const unsigned bal = __ballot_sync(kFull, u * 32 + lane < nc && kq[u] == -1);
+                    if (bal && m == nc) m = u * 32 + __ffs(bal) - 1;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int q = u * 32 + lane;
+                    const bool is_ctrl = q < m, is_edge = q >= nc && q < slots;
                     double v0, v1;
-                    terms(eo[u], v0, v1);
-                    if (u * 32 + lane < outdeg) {
-                        e0 += logit_term(0.5, v0);
-                        if (NV == 2) e1 += logit_term(0.5, v1);
+                    terms((is_ctrl || is_edge) ? kq[u] : i, v0, v1);
+                    {
+                        const double a = fabs(v0), L = DLSM_L1PEN(a);
+                        const double te = fma(0.5, v0, fma(-0.5, a, -L)); // logit_term(0.5, v0)
+                        const double tc = fma(0.5, a, 0.5 * v0) + L;      // log1pexp(v0)
+                        if (is_edge) e0 += te;
+                        if (is_ctrl) c0 += tc;
                     }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const bool ok = u * 32 + lane < m;
-                    double v0, v1;
-                    terms(ok ? cq[u] : i, v0, v1);
-                    const double l0 = log1pexp(v0);
-                    if (ok) c0 += l0;
-                    if (NV == 2) { const double l1 = log1pexp(v1); if (ok) c1 += l1; }
+                    if (NV == 2) {
+                        const double a = fabs(v1), L = DLSM_L1PEN(a);
+                        const double te = fma(0.5, v1, fma(-0.5, a, -L));
+                        const double tc = fma(0.5, a, 0.5 * v1) + L;
+                        if (is_edge) e1 += te;
+                        if (is_ctrl) c1 += tc;
+                    }
                 }
             } else {
                 for (int q = lane; q < outdeg; q += 32) {
@@ -2031,8 +2051,8 @@ __global__ void __launch_bounds__(256) k_full(const FullParams p)
                     if (NV == 2) c1 += log1pexp(v1);
                 }
             }
-            e0 = warp_sum(e0); e1 = warp_sum(e1);
-            c0 = warp_sum(c0); c1 = warp_sum(c1);
+            warp_sum2(e0, c0, lane);
+            if (NV == 2) warp_sum2(e1, c1, lane);
             if (lane == 0) {
                 const double adj = (double)(n - outdeg - 1) / (double)m;
                 a0 += e0 - adj * c0;
@@ -2079,7 +2099,10 @@ struct RowsParams {
 };
 
 template <int LK, int D>
-__global__ void __launch_bounds__(256) k_rows(const RowsParams p)
+#ifndef DLSM_ROWS_MINB
+#define DLSM_ROWS_MINB 2
+#endif
+__global__ void __launch_bounds__(256, DLSM_ROWS_MINB) k_rows(const RowsParams p)
 {
     constexpr int DM = (D == 0) ? kMaxD : D;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -202,7 +202,7 @@ def _sparse_directed(rng, T, n, out_deg):
 
 
 @pytest.mark.parametrize("mode", ["chain", "slice", "slice-v1", "slice-v2", "slice-v3", "slice-plain"])
-@pytest.mark.parametrize("T,n,m,per_chain", [(3, 400, 8, False), (2, 150, 5, True), (4, 70, 20, False)])
+@pytest.mark.parametrize("T,n,m,per_chain", [(3, 400, 8, False), (2, 150, 5, True), (4, 70, 20, False), (2, 300, 128, True)])
 def test_case_control_sweep_all_mappings(T, n, m, per_chain, mode, monkeypatch):
     """The case-control sweep (directed_likelihoods_fast.pyx:83-182 inside
     sample_latent_positions.py:92-146) with recorded draws against the oracle: warp per slice
@@ -325,3 +325,98 @@ def test_device_edge_lists_equal_the_host_sampler_init(T, n, density, seed):
         bad = edges.copy(); bad[0, 0] = T
         with pytest.raises(L.DlsmError):
             e.set_network_edges(bad)
+
+
+def test_intercept_and_radii_mh_long_chain_case_control_vs_oracle():
+    """n = 6 000 > one Dirichlet chunk (k_radii_terms: 2 048 nodes per CTA) and T n / 64 = 282
+    likelihood partials per chain (warp-per-chain sums): the intercept and radii MH steps
+    (sample_coefficients.py:12-121 around directed_likelihoods_fast.pyx:208-270) replayed against the
+    oracle, decisions and ratios."""
+    L = _L()
+    T, n, d, m, C_ = 3, 6000, 2, 30, 2
+    rng = np.random.RandomState(6000)
+    deg, in_e, out_e = _sparse_directed(rng, T, n, 5.0)
+    e = L.Engine(T=T, n=n, d=d, n_chains=C_, is_directed=True, case_control=True, tune=4, tune_interval=2,
+                 intercept_tune_interval=(2, 2), radii_tune=None)
+    e.set_edge_lists(deg, in_e, out_e)
+    e.set_rng(5)
+    e.resample_controls(m, per_chain=True)
+    ci, co = e.get_controls()
+    X = rng.randn(C_, T, n, d) * 0.02
+    radii = rng.dirichlet(np.ones(n) * 5, size=C_)
+    ic = np.tile([[0.4, 0.7]], (C_, 1))
+    e.set(L.F_X, X); e.set(L.F_RADII, radii); e.set(L.F_INTERCEPT, ic)
+    e.set_hyper(tau_sq=0.5, sigma_sq=0.002, intercept_prior=np.array([0.4, 0.7]), intercept_variance_prior=2.0)
+    e.set_tuner(0.004, step_intercept=0.003, step_radii=200000.0)
+    itun = [O.TunerState((2,), 0.003, tune=4, tune_interval=2) for _ in range(C_)]
+    rtun = [O.TunerState((1,), 200000.0, tune=None, tune_interval=100) for _ in range(C_)]
+    seen = set()
+    for s in range(3):
+        ieps, ilogu = rng.randn(C_, 2), np.log(rng.rand(C_, 2))
+        iacc, iratio = e.sample_intercepts(ieps, ilogu, want_stats=True)
+        prop = np.stack([rng.dirichlet(200000.0 * radii[c]) for c in range(C_)])
+        rlogu = np.log(rng.rand(C_))
+        racc, rratio = e.sample_radii(prop, rlogu, want_stats=True)
+        for c in range(C_):
+            cc = dict(in_edges=in_e, out_edges=out_e, degrees=deg, ctrl_in=ci[c].astype(np.int64),
+                      ctrl_out=co[c].astype(np.int64))
+            io = O.sample_intercepts(X[c], ic[c], itun[c], ieps[c], ilogu[c], np.array([0.4, 0.7]), 2.0,
+                                     radii=radii[c], is_directed=True, case_control=cc)
+            assert np.array_equal(iacc[c], io["accepted"])
+            assert np.allclose(iratio[c], io["ratio"], rtol=1e-8, atol=1e-8)
+            ro = O.sample_radii(X[c], ic[c], radii[c], rtun[c], prop[c], float(rlogu[c]), case_control=cc)
+            assert int(racc[c]) == ro["accepted"]
+            assert abs(rratio[c] - ro["ratio"]) <= 1e-8 * max(1.0, abs(ro["ratio"]))
+            seen.update((int(a) for a in io["accepted"]))
+            seen.add(2 + ro["accepted"])
+        assert np.array_equal(e.get(L.F_INTERCEPT), ic)
+        assert np.array_equal(e.get(L.F_RADII), radii)
+    assert len(seen) >= 2      # the replay saw both outcomes somewhere
+
+
+@pytest.mark.parametrize("cc_kernel", ["auto", "1"])
+def test_case_control_sweep_hub_node_long_and_ragged_lists(cc_kernel, monkeypatch):
+    """A hub with in-degree n - 4 in one slice: its in-list (296 entries) does not fit the dataflow
+    kernel's 256-slot register layout (generic list walk), only 3 in-controls exist (sentinel-terminated
+    control lists, directed_likelihoods_fast.pyx:137), and every other node has the hub in its out-list.
+    Recorded draws, decisions and positions against the oracle for the dataflow kernel (auto) and the
+    run-based kernel."""
+    L = _L()
+    from dynetlsm_b200 import DirectedCaseControlSampler
+    if cc_kernel != "auto":
+        monkeypatch.setenv("DLSM_CC_KERNEL", cc_kernel)
+    monkeypatch.setenv("DLSM_SWEEP_MODE", "slice")
+    rng = np.random.RandomState(300)
+    T, n, d, C_ = 2, 300, 2, 2
+    Y = _net(rng, T, n, True, 0.015)
+    Y[1, :, 7] = 1; Y[1, 7, 7] = 0; Y[1, 0:3, 7] = 0      # in-degree n - 4: only 3 in-controls exist
+    cc = DirectedCaseControlSampler(n_control=6, n_resample=None, random_state=np.random.RandomState(1)).init(Y)
+    n_in = (cc.control_nodes_in_ != -1).sum(axis=2)
+    n_out = (cc.control_nodes_out_ != -1).sum(axis=2)
+    assert n_in[1, 7] == 3 and (n_out >= n_in).all()      # ragged, without the reference's out-of-bounds pattern
+    assert cc.in_edges_.shape[2] >= 296
+    e = L.Engine(T=T, n=n, d=d, n_chains=C_, is_directed=True, case_control=True, tune=2, tune_interval=1)
+    e.set_edge_lists(cc.degrees_, cc.in_edges_, cc.out_edges_)
+    e.set_controls(cc.control_nodes_in_, cc.control_nodes_out_)
+    X = rng.randn(C_, T, n, d) * 0.02
+    radii = rng.dirichlet(np.ones(n) * 5, size=C_)
+    ic = np.tile([[0.4, 0.7]], (C_, 1))
+    e.set(L.F_X, X); e.set(L.F_RADII, radii); e.set(L.F_INTERCEPT, ic)
+    e.set_hyper(tau_sq=0.5, sigma_sq=0.002)
+    e.set_tuner(0.004)
+    Xo = X.copy()
+    tuners = [O.TunerState((T, n), 0.004, tune=2, tune_interval=1) for _ in range(C_)]
+    lists = dict(in_edges=cc.in_edges_, out_edges=cc.out_edges_, degrees=cc.degrees_,
+                 ctrl_in=cc.control_nodes_in_.astype(np.int64), ctrl_out=cc.control_nodes_out_.astype(np.int64))
+    for s in range(3):
+        eps = rng.randn(C_, T, n, d)
+        logu = np.log(rng.rand(C_, T, n))
+        acc, _ = e.sweep_latent(eps, logu, want_stats=True)
+        got = e.get(L.F_X)
+        for c in range(C_):
+            out = O.sweep_latent(Xo[c], ic[c], tuners[c], eps[c], logu[c], radii=radii[c], is_directed=True,
+                                 tau_sq=0.5, sigma_sq=0.002, case_control=lists)
+            assert np.array_equal(acc[c], out["accepted"]), (s, c)
+            assert np.array_equal(got[c], Xo[c])
+        assert 0.05 < acc.mean() < 0.98
+    assert e.counters()["ub_flags"] == 0
