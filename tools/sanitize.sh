@@ -3,7 +3,8 @@
 #   racecheck (shared-memory hazards) and memcheck on small instances of
 #   - the chain kernels (wavefront flags in shared memory): k_sweep, k_sweep<RS>, k_sweep_cb
 #   - the cluster kernels (DSMEM slots, mbarriers, st.release.cluster flags): k_sweep_blk, k_sweep_slice_cl
-#   - the CTA-per-slice kernels (global st.release / ld.acquire flags + ticket): k_sweep_slice_ws, k_sweep_cc
+#   - the CTA-per-slice kernels (global st.release / ld.acquire flags + ticket): k_sweep_slice_ws, k_sweep_cc, _cc3
+#   - the dataflow case-control kernel (global-memory records with sentinels, atomic tickets): k_sweep_ccd
 # Output: gpurun_out/sanitize_<tool>.log (copied to profiles/ by hand).
 cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out

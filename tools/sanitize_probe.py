@@ -42,7 +42,7 @@ def run(tag, T, n, C_, directed, opts, sweeps=2, K=0):
     e.close()
 
 
-def run_cc(tag, T, n, C_):
+def run_cc(tag, T, n, C_, cc_kernel=0):
     rng = np.random.RandomState(2)
     deg = np.zeros((T, n, 2), np.int32)
     out_e = np.zeros((T, n, 6), np.int32)
@@ -61,6 +61,7 @@ def run_cc(tag, T, n, C_):
             in_e[t, j, :len(ins[t][j])] = ins[t][j]; deg[t, j, 0] = len(ins[t][j])
     e = L.Engine(T=T, n=n, d=2, n_chains=C_, is_directed=True, case_control=True)
     e.set_option(L.OPT_SWEEP_MODE, L.SWEEP_SLICE)
+    e.set_option(L.OPT_CC_KERNEL, cc_kernel)
     e.set_edge_lists(deg, in_e, out_e)
     e.set_rng(5)
     e.resample_controls(8, per_chain=True)
@@ -81,4 +82,6 @@ if __name__ == "__main__":
     run("k_sweep_blk (cluster, block-speculative)", 3, 130, 1, True, [SL, (L.OPT_NO_CLUSTER, 0)])
     run("k_sweep_slice_cl (cluster, per node)", 3, 130, 1, False, [SL, (L.OPT_NO_CLUSTER, 2)])
     run("k_sweep_slice_ws (CTA per slice)", 2, 200, 1, True, [SL, (L.OPT_NO_CLUSTER, 1)])
-    run_cc("k_sweep_cc (case-control batches)", 2, 60, 2)
+    run_cc("k_sweep_cc (case-control batches)", 2, 60, 2, cc_kernel=1)
+    run_cc("k_sweep_cc3 (case-control batches, 2-CTA cluster)", 2, 60, 2, cc_kernel=3)
+    run_cc("k_sweep_ccd (case-control dataflow) + k_ccd_prep / k_ccd_post", 2, 60, 2, cc_kernel=0)
