@@ -74,6 +74,7 @@ struct dlsm_handle {
     int cluster_cs = -1;            // CTAs per (chain, slice) cluster (-1: not probed, 0: none)
     int cluster_ncomp = 0;          // compute warps per CTA (per-node cluster kernel) / warps per CTA (block kernel)
     bool cluster_blk = false;       // block-speculative kernel (k_sweep_blk) rather than the per-node one
+    bool cluster_win = false;       // ... with the two-block window (k_sweep_blkw)
     int cc3_ok = -1;                // 2-CTA-cluster case-control sweep: all C*T clusters co-resident? (-1: not probed)
     // developer options (dlsm_set_option; environment defaults are read ONCE, in dlsm_create)
     int64_t opt[DLSM_OPT_COUNT_] = {0};
@@ -481,7 +482,8 @@ int cluster_dispatch(dlsm_handle *h, const SweepParams *p, int CS, int ncomp, in
 
 // CTAs per cluster: the largest size whose C*T clusters can all be resident (they form a wavefront
 // over the slices), so that one chain spreads over as many SMs as the part has; 0 = not applicable.
-// DLSM_OPT_NO_CLUSTER: 0 block-speculative kernel (k_sweep_blk), 1 no clusters, 2 per-node kernel.
+// DLSM_OPT_NO_CLUSTER: 0 block-speculative kernel with a two-block window (k_sweep_blkw), 1 no clusters,
+// 2 per-node kernel (k_sweep_slice_cl), 3 block-speculative kernel without the window (k_sweep_blk).
 int cluster_size(dlsm_handle *h)
 {
     if (h->cluster_cs >= 0) return h->cluster_cs;
@@ -491,6 +493,9 @@ int cluster_size(dlsm_handle *h)
     const int64_t mode = h->opt[DLSM_OPT_NO_CLUSTER];
     if (h->lk == kCaseControl || h->no_pipeline || mode == 1 || CT * 2 > h->sm_count) return 0;
     h->cluster_blk = mode != 2;
+    // the block-speculative kernel with the two-block window (k_sweep_blkw) unless DLSM_OPT_NO_CLUSTER = 3
+    // asks for the plain one (k_sweep_blk)
+    h->cluster_win = mode == 0 && blkw_smem_bytes(c.n, c.d, h->lk == kDirected, h->W) <= kMaxSmem;
     if (h->cluster_blk ? blk_smem_bytes(c.n, c.d, h->lk == kDirected, h->W) > kMaxSmem : cluster_smem(h) > kMaxSmem)
         return 0;
     const int chunks = (c.n + (h->lk == kUndirected ? 63 : 31)) / (h->lk == kUndirected ? 64 : 32);
@@ -499,7 +504,8 @@ int cluster_size(dlsm_handle *h)
         if (h->cluster_blk) {
             ncomp = 16; // 16 warps per CTA: CS * 16 <= 128 column shares
             SweepParams p = sweep_params(h);
-            if (blk_launch(p, h->lk == kDirected, CS, ncomp, nullptr, nullptr, h->stream, &active) != cudaSuccess) {
+            if ((h->cluster_win ? blkw_launch(p, h->lk == kDirected, CS, nullptr, nullptr, h->stream, &active)
+                                : blk_launch(p, h->lk == kDirected, CS, ncomp, nullptr, nullptr, h->stream, &active)) != cudaSuccess) {
                 cudaGetLastError();
                 continue;
             }
@@ -584,6 +590,10 @@ int launch_slice_lk(dlsm_handle *h, const SweepParams &p)
     if (LK != kCaseControl && cluster_size(h) >= 2) {
         h->ctr.cluster_sweeps += 1;
         if (!h->cluster_blk) return cluster_dispatch(h, &p, h->cluster_cs, h->cluster_ncomp, nullptr);
+        if (h->cluster_win) {
+            CU(h, blkw_launch(p, LK == kDirected, h->cluster_cs, h->d_progress, h->d_ticket, h->stream, nullptr));
+            return DLSM_OK;
+        }
         CU(h, blk_launch(p, LK == kDirected, h->cluster_cs, h->cluster_ncomp, h->d_progress, h->d_ticket,
                          h->stream, nullptr));
         return DLSM_OK;
@@ -991,7 +1001,7 @@ int dlsm_set_option(dlsm_handle *h, int option, int64_t value)
     if (option == DLSM_OPT_FFBS_KERNEL && (value < DLSM_FFBS_AUTO || value > DLSM_FFBS_WARP))
         FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_FFBS_KERNEL takes a dlsm_ffbs_kernel value");
     if (value < 0) FAIL(h, DLSM_ERR_INVALID, "option values are non-negative");
-    if (option == DLSM_OPT_NO_CLUSTER && value > 2) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_NO_CLUSTER takes 0, 1 or 2");
+    if (option == DLSM_OPT_NO_CLUSTER && value > 3) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_NO_CLUSTER takes 0..3");
     if (option == DLSM_OPT_CC_KERNEL && value > 4) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_CC_KERNEL takes 0..4");
     if (option == DLSM_OPT_CHAIN_KERNEL && value > DLSM_CHAIN_BLOCK) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_CHAIN_KERNEL takes a dlsm_chain_kernel value");
     h->opt[option] = value;

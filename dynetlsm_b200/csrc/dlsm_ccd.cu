@@ -44,7 +44,7 @@
 
 namespace dlsm {
 
-constexpr int kCcdThreads = 640; // 20 warps per SM at <= 102 registers (A/B: 768 threads at <= 85)
+constexpr int kCcdThreads = 640; // 20 warps per SM at <= 102 registers (768 threads at 80 registers measured: +-0)
 constexpr int kPrepStride = 8;   // doubles per prep record
 constexpr int kCcdSlots = 256;   // list entries of a node whose indices are held in registers (8 per lane)
 constexpr unsigned long long kSentinel = 0xFFF8DEADBEEF0001ull; // "undecided" coordinate of a k_sweep_ccd record
@@ -57,7 +57,6 @@ struct CcdWork {
     size_t cells = 0, pairs = 0;
     int grid = 0;
     int group = 0;           // chains per launch of the sweep kernel (0 = heuristic)
-    int threads = kCcdThreads;
 };
 
 struct CcdView {
@@ -417,19 +416,19 @@ cudaError_t ccd_launch(const SweepParams &p, double *G, CcdWork **work, int sm_c
     if (!w) {
         w = new CcdWork;
         w->cells = cells; w->pairs = pairs;
-        *work = w;
-        if ((e = cudaMalloc((void **)&w->Nw, cells * 4 * sizeof(double))) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void **)&w->prep, cells * kPrepStride * sizeof(double))) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void **)&w->state, cells * sizeof(int))) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void **)&w->next, pairs * sizeof(int))) != cudaSuccess) return e;
         if (const char *g = getenv("DLSM_CCD_GROUP")) w->group = atoi(g); // (A/B runs; read once)
-        if (const char *g = getenv("DLSM_CCD_THREADS")) w->threads = atoi(g) == 768 ? 768 : kCcdThreads;
         int per_sm = 0;
-        if (w->threads == 768) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_ccd<768>, 768, 0);
-        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_ccd<kCcdThreads>, kCcdThreads, 0);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        e = cudaMalloc((void **)&w->Nw, cells * 4 * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc((void **)&w->prep, cells * kPrepStride * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc((void **)&w->state, cells * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc((void **)&w->next, pairs * sizeof(int));
+        if (e == cudaSuccess) {
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_ccd<kCcdThreads>, kCcdThreads, 0);
+        }
+        if (e == cudaSuccess && per_sm < 1) e = cudaErrorLaunchOutOfResources;
+        if (e != cudaSuccess) { ccd_free(w); return e; } // nothing half-built is kept
         w->grid = sm_count * per_sm; // all CTAs resident: a waiting warp's inputs are always being produced
+        *work = w;
     }
     CcdView B;
     B.G = G; B.Nw = w->Nw; B.prep = w->prep; B.state = w->state; B.next = w->next;
@@ -440,14 +439,13 @@ cudaError_t ccd_launch(const SweepParams &p, double *G, CcdWork **work, int sm_c
     // at random and should stay in L2, and a pair wants >= ~64 warps to cover its dependency graph's
     // parallelism; more warps per pair wait more often for a node that is still in flight.  Measured at
     // cfg 5: 8 chains per launch 13.6 ms, 4 chains 13.4 ms (profiles/r2d_ab_cfg5.json).
-    const int warps = w->grid * (w->threads / 32);
+    const int warps = w->grid * (kCcdThreads / 32);
     int group = w->group > 0 ? w->group : (warps / 64) / p.net.T;
     group = group < 1 ? 1 : (group > p.C ? p.C : group);
     int nl = 2;
     for (int c0 = 0; c0 < p.C; c0 += group, nl++) {
         const int gc = c0 + group <= p.C ? group : p.C - c0;
-        if (w->threads == 768) k_sweep_ccd<768><<<(unsigned)w->grid, 768, 0, stream>>>(p, B, c0 * p.net.T, gc * p.net.T);
-        else k_sweep_ccd<kCcdThreads><<<(unsigned)w->grid, kCcdThreads, 0, stream>>>(p, B, c0 * p.net.T, gc * p.net.T);
+        k_sweep_ccd<kCcdThreads><<<(unsigned)w->grid, kCcdThreads, 0, stream>>>(p, B, c0 * p.net.T, gc * p.net.T);
     }
     k_ccd_post<<<nb, 256, 0, stream>>>(p, B);
     if (launches) *launches = nl;

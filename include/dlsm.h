@@ -149,8 +149,10 @@ typedef enum {
     DLSM_OPT_NO_ROWSUM_CACHE = 10,  /* 1: the device loop evaluates proposal AND current position of every
                                        node-update afresh instead of keeping per-node row sums */
     DLSM_OPT_NO_CLUSTER = 11,       /* few (chain, slice) pairs, long rows: 0 = block-speculative sweep on a
-                                       thread-block cluster per pair (k_sweep_blk), 1 = no clusters (CTA per
-                                       pair), 2 = per-node cluster kernel (k_sweep_slice_cl) */
+                                       thread-block cluster per pair with a two-block window (k_sweep_blkw),
+                                       1 = no clusters (CTA per pair), 2 = per-node cluster kernel
+                                       (k_sweep_slice_cl), 3 = block-speculative sweep without the window
+                                       (k_sweep_blk) */
     DLSM_OPT_CHAIN_KERNEL = 12,     /* dlsm_chain_kernel: the one-CTA-per-chain sweep kernel (exact likelihoods) */
     DLSM_OPT_CC_KERNEL = 13,        /* case-control sweep of (chain, slice) pairs: 0 = auto (k_sweep_ccd: dataflow
                                        over nodes, positions double-buffered for the sweep, d = 2 and <= 128

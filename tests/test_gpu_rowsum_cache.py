@@ -144,7 +144,7 @@ def test_cluster_kernel_vs_oracle_and_vs_cta_per_slice(T, n, d, directed):
     step = 0.02 / n if directed else 0.12
     hy = dict(tau_sq=float(np.mean(X[0] * X[0])), sigma_sq=0.001 / n) if directed else dict(tau_sq=2.0, sigma_sq=0.1)
     engines = []
-    for no_cluster in (0, 2, 1):   # block-speculative cluster kernel, per-node cluster kernel, CTA per slice
+    for no_cluster in (0, 3, 2, 1):   # block-speculative cluster kernel with / without the two-block window, per-node cluster kernel, CTA per slice
         e, Xs, radii = _engine(T, n, d, directed, 1, X, Y, rng)
         e.set_option(L.OPT_SWEEP_MODE, L.SWEEP_SLICE)
         e.set_option(L.OPT_NO_CLUSTER, no_cluster)
@@ -160,7 +160,7 @@ def test_cluster_kernel_vs_oracle_and_vs_cta_per_slice(T, n, d, directed):
             assert np.array_equal(acc[0], out["accepted"]), s
             assert np.array_equal(e.get(L.F_X)[0], Xo)
             assert np.allclose(ratio[0], out["ratio"], rtol=1e-8, atol=1e-8)
-    assert [e.counters()["cluster_sweeps"] for e in engines] == [3, 3, 0]
+    assert [e.counters()["cluster_sweeps"] for e in engines] == [3, 3, 3, 0]
     assert np.array_equal(engines[0].get(L.F_X_STEP)[0], tun.step)
     assert 0.03 < out["accepted"].mean() < 0.97
 
@@ -169,7 +169,7 @@ def test_cluster_kernel_native_rng_chain_equals_cta_per_slice_chain():
     L = _L()
     T, n, d = 6, 400, 2
     outs = []
-    for no_cluster in (0, 1, 2):
+    for no_cluster in (0, 1, 2, 3):
         rng, X, Y = _net(T, n, d, True, seed=5)
         e, _, _ = _engine(T, n, d, True, 2, X, Y, rng, tune=500, tune_interval=3)
         e.set_option(L.OPT_SWEEP_MODE, L.SWEEP_SLICE)

@@ -79,7 +79,8 @@ if __name__ == "__main__":
     run("k_sweep (node, two-variant)", 4, 70, 3, False, [CH, (L.OPT_CHAIN_KERNEL, L.CHAIN_NODE)], K=4)
     run("k_sweep (row-sum cache) + k_rows", 4, 70, 3, False, [CH, (L.OPT_CHAIN_KERNEL, L.CHAIN_NODE_ROWSUM)])
     run("k_sweep_cb (block chain kernel)", 4, 70, 3, True, [CH, (L.OPT_CHAIN_KERNEL, L.CHAIN_BLOCK)])
-    run("k_sweep_blk (cluster, block-speculative)", 3, 130, 1, True, [SL, (L.OPT_NO_CLUSTER, 0)])
+    run("k_sweep_blkw (cluster, block-speculative, two-block window)", 3, 130, 1, True, [SL, (L.OPT_NO_CLUSTER, 0)])
+    run("k_sweep_blk (cluster, block-speculative)", 3, 130, 1, True, [SL, (L.OPT_NO_CLUSTER, 3)])
     run("k_sweep_slice_cl (cluster, per node)", 3, 130, 1, False, [SL, (L.OPT_NO_CLUSTER, 2)])
     run("k_sweep_slice_ws (CTA per slice)", 2, 200, 1, True, [SL, (L.OPT_NO_CLUSTER, 1)])
     run_cc("k_sweep_cc (case-control batches)", 2, 60, 2, cc_kernel=1)
