@@ -75,6 +75,7 @@ struct dlsm_handle {
     int cluster_ncomp = 0;          // compute warps per CTA (per-node cluster kernel) / warps per CTA (block kernel)
     bool cluster_blk = false;       // block-speculative kernel (k_sweep_blk) rather than the per-node one
     bool cluster_win = false;       // ... with the two-block window (k_sweep_blkw)
+    double *d_ll_slices = nullptr;  // [C][T] per-slice log-likelihood sums of k_sweep_blkw
     int cc3_ok = -1;                // 2-CTA-cluster case-control sweep: all C*T clusters co-resident? (-1: not probed)
     // developer options (dlsm_set_option; environment defaults are read ONCE, in dlsm_create)
     int64_t opt[DLSM_OPT_COUNT_] = {0};
@@ -504,7 +505,7 @@ int cluster_size(dlsm_handle *h)
         if (h->cluster_blk) {
             ncomp = 16; // 16 warps per CTA: CS * 16 <= 128 column shares
             SweepParams p = sweep_params(h);
-            if ((h->cluster_win ? blkw_launch(p, h->lk == kDirected, CS, nullptr, nullptr, h->stream, &active)
+            if ((h->cluster_win ? blkw_launch(p, h->lk == kDirected, CS, nullptr, nullptr, nullptr, h->stream, &active)
                                 : blk_launch(p, h->lk == kDirected, CS, ncomp, nullptr, nullptr, h->stream, &active)) != cudaSuccess) {
                 cudaGetLastError();
                 continue;
@@ -583,6 +584,23 @@ int launch_cc_batch(dlsm_handle *h, const SweepParams &p)
     return DLSM_OK;
 }
 
+static __global__ void k_sum_slices(int C, int T, const double *in, double *out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int t = 0; t < T; t++) s += in[(size_t)c * T + t];
+    out[c] = s;
+}
+
+bool use_slice_kernel(const dlsm_handle *h);
+
+// the sweep kernel of this handle tracks the post-sweep log-likelihood although it is a slice kernel
+static bool cluster_tracks_loglik(dlsm_handle *h)
+{
+    return use_slice_kernel(h) && h->lk != kCaseControl && cluster_size(h) >= 2 && h->cluster_win;
+}
+
 template <int LK>
 int launch_slice_lk(dlsm_handle *h, const SweepParams &p)
 {
@@ -591,7 +609,18 @@ int launch_slice_lk(dlsm_handle *h, const SweepParams &p)
         h->ctr.cluster_sweeps += 1;
         if (!h->cluster_blk) return cluster_dispatch(h, &p, h->cluster_cs, h->cluster_ncomp, nullptr);
         if (h->cluster_win) {
-            CU(h, blkw_launch(p, LK == kDirected, h->cluster_cs, h->d_progress, h->d_ticket, h->stream, nullptr));
+            // the kernel also hands over the full-network log-likelihood of the state it leaves behind
+            // (per-slice sums, added in slice order)
+            if (p.ll_cur && !h->d_ll_slices)
+                CU(h, cudaMalloc((void **)&h->d_ll_slices, (size_t)h->cfg.n_chains * h->cfg.T * sizeof(double)));
+            CU(h, blkw_launch(p, LK == kDirected, h->cluster_cs, h->d_progress, h->d_ticket,
+                              p.ll_cur ? h->d_ll_slices : nullptr, h->stream, nullptr));
+            if (p.ll_cur) {
+                const int C = h->cfg.n_chains;
+                k_sum_slices<<<(C + 127) / 128, 128, 0, h->stream>>>(C, h->cfg.T, (const double *)h->d_ll_slices, p.ll_cur);
+                CHECK_LAUNCH(h);
+                h->ctr.kernel_launches += 1;
+            }
             return DLSM_OK;
         }
         CU(h, blk_launch(p, LK == kDirected, h->cluster_cs, h->cluster_ncomp, h->d_progress, h->d_ticket,
@@ -982,6 +1011,7 @@ void dlsm_destroy(dlsm_handle *h)
     cudaFree(h->d_cooc);
     cudaFree(h->d_gather);
     ccd_free(h->ccd);
+    cudaFree(h->d_ll_slices);
     cudaFree(h->d_radii_terms);
     cudaFree(h->d_proc_ref);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -1647,7 +1677,8 @@ static int one_sweep(dlsm_handle *h, uint32_t flags, bool *tracked)
     p.fuse_center = fuse ? 1 : 0;
     // the chain kernel also hands over the full-network log-likelihood of the state it leaves
     // behind, so the intercept / radii MH below evaluates only its proposals
-    bool use_cur = !use_slice_kernel(h) && h->lk != kCaseControl && !h->opt[DLSM_OPT_NO_TRACKED_LOGLIK];
+    bool use_cur = (!use_slice_kernel(h) || cluster_tracks_loglik(h)) && h->lk != kCaseControl &&
+                   !h->opt[DLSM_OPT_NO_TRACKED_LOGLIK];
     p.ll_cur = use_cur ? F<double>(h, DLSM_F_LOGLIK) : nullptr;
     // ... and keeps the per-node row sums, so that a node-update evaluates its proposal only
     // (the first sweep after the state came in from outside -- dlsm_set_state, a function-level call --

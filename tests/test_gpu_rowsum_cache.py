@@ -177,6 +177,8 @@ def test_cluster_kernel_native_rng_chain_equals_cta_per_slice_chain():
         e.run_sweeps(6)
         outs.append([e.get(f) for f in (L.F_X, L.F_INTERCEPT, L.F_RADII)])
         assert (e.counters()["cluster_sweeps"] > 0) == (no_cluster != 1)
+        # (the windowed cluster kernel tracks the log-likelihood itself: dyads {i < j} at the kept states)
+        assert np.allclose(e.get(L.F_LOGLIK), e.loglik_full(), rtol=1e-11, atol=0)
     for other in outs[1:]:
         for a, b in zip(outs[0], other):
             assert np.array_equal(a, b)
