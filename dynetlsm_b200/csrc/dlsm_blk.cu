@@ -973,16 +973,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_cb(const SweepParams p)
                     const int cnt = (n - base) < 32 ? (n - base) : 32;
                     double a_n = 0.0, a_o = 0.0, b_n = 0.0, b_o = 0.0;
                     int ii = 0;
-                    if (MINB == 1) { // a whole SM per chain: four columns per trip, eight independent chains
-                        double c_n = 0.0, c_o = 0.0, e_n = 0.0, e_o = 0.0;
-                        for (; ii + 3 < cnt; ii += 4) {
-                            column(base + ii, rw[k], cw[k], a_n, a_o);
-                            column(base + ii + 1, rw[k], cw[k], b_n, b_o);
-                            column(base + ii + 2, rw[k], cw[k], c_n, c_o);
-                            column(base + ii + 3, rw[k], cw[k], e_n, e_o);
-                        }
-                        a_n += c_n; a_o += c_o; b_n += e_n; b_o += e_o;
-                    }
+                    // (four columns per trip / eight chains per lane on a 204-register build, tried for chains that
+                    //  have an SM to themselves: 15.1 ms instead of 2.75 ms at cfg 4 with 128 chains -- removed)
                     for (; ii + 1 < cnt; ii += 2) { // two columns per trip: four independent chains
                         column(base + ii, rw[k], cw[k], a_n, a_o);
                         column(base + ii + 1, rw[k], cw[k], b_n, b_o);
@@ -1117,7 +1109,6 @@ static cudaError_t cb_launch_x(const SweepParams &p, int ctas_per_sm_by_smem, cu
     const int warps = p.net.T < 16 ? p.net.T : 16;
     if (warps <= 9 && ctas_per_sm_by_smem >= 3) return cb_launch_t<LK, D, XS, 288, 3>(p, warps, stream);
     if (warps <= 10 && ctas_per_sm_by_smem >= 2) return cb_launch_t<LK, D, XS, 320, 2>(p, warps, stream);
-    if (warps <= 10) return cb_launch_t<LK, D, XS, 320, 1>(p, warps, stream); // up to 204 registers
     return cb_launch_t<LK, D, XS, 512, 1>(p, warps, stream);
 }
 
