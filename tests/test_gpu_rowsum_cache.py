@@ -136,7 +136,8 @@ def test_device_loop_chain_is_the_two_variant_chain(T, n, d, directed, K):
 # partial sums through distributed shared memory
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("T,n,d,directed", [(5, 300, 2, False), (4, 500, 2, True), (3, 257, 3, True),
-                                            (7, 1000, 2, False), (2, 2000, 2, True), (20, 640, 2, True)])
+                                            (7, 1000, 2, False), (2, 2000, 2, True), (20, 640, 2, True),
+                                            (70, 256, 2, True), (37, 290, 2, False)])   # clusters of 2 and 4 CTAs
 def test_cluster_kernel_vs_oracle_and_vs_cta_per_slice(T, n, d, directed):
     L = _L()
     rng, X, Y = _net(T, n, d, directed, seed=11 * n + T)
@@ -162,6 +163,36 @@ def test_cluster_kernel_vs_oracle_and_vs_cta_per_slice(T, n, d, directed):
             assert np.allclose(ratio[0], out["ratio"], rtol=1e-8, atol=1e-8)
     assert [e.counters()["cluster_sweeps"] for e in engines] == [3, 3, 3, 0]
     assert np.array_equal(engines[0].get(L.F_X_STEP)[0], tun.step)
+    assert 0.03 < out["accepted"].mean() < 0.97
+
+
+@pytest.mark.parametrize("T,n,K", [(4, 300, 6), (10, 500, 10)])
+def test_cluster_kernels_mixture_prior_vs_oracle(T, n, K):
+    """The HDP-LPCM sweep (mixture prior, sample_latent_positions.py:149-206) of a single long-row chain
+    -- what DynamicNetworkHDPLPCM.fit(n_chains=1) runs for n >= 256 -- on every (chain, slice) kernel,
+    recorded draws, the oracle's decisions and positions."""
+    L = _L()
+    d = 2
+    rng, X, Y = _net(T, n, d, False, seed=7 * n + K)
+    engines = []
+    for no_cluster in (0, 3, 2, 1):
+        e, Xs, _ = _engine(T, n, d, False, 1, X, Y, rng, K=K)
+        e.set_option(L.OPT_SWEEP_MODE, L.SWEEP_SLICE)
+        e.set_option(L.OPT_NO_CLUSTER, no_cluster)
+        engines.append(e)
+    e0 = engines[0]
+    mix = dict(mu=e0.get(L.F_MU)[0], sigma=e0.get(L.F_SIGMA)[0], lmbda=0.8, z=e0.get(L.F_Z)[0].astype(np.int64))
+    tun = O.TunerState((T, n), 0.12, tune=4, tune_interval=2)
+    Xo = Xs[0].copy()
+    ic = np.array([0.6])
+    for s in range(2):
+        eps, logu = rng.randn(1, T, n, d), np.log(rng.rand(1, T, n))
+        out = O.sweep_latent(Xo, ic, tun, eps[0], logu[0], Y=Y, tau_sq=2.0, sigma_sq=0.1, mixture=mix)
+        for e in engines:
+            acc, ratio = e.sweep_latent(eps, logu, want_stats=True)
+            assert np.array_equal(acc[0], out["accepted"]), s
+            assert np.array_equal(e.get(L.F_X)[0], Xo)
+    assert [e.counters()["cluster_sweeps"] for e in engines] == [2, 2, 2, 0]
     assert 0.03 < out["accepted"].mean() < 0.97
 
 
