@@ -125,8 +125,13 @@ __device__ inline double concentration(Stream &g, double alpha, double n_cluster
 //   PART 0 = both.
 // dynamic smem: ints m[T*K*K], wover[T*K], gstart[T*K*K]; doubles mbar[K], newbeta[K], scal[16], rowlog[T*K],
 // bins[rows][2*K*d + K], totals[2*K*d + K]
+// DLSM_HDP_EMIS_MINB: CTAs per SM the emission-side build is compiled for (9 lets 9 x 148 = 1 332 chains
+// run as one wave; the default build needs 64 registers = 8 CTAs)
+#ifndef DLSM_HDP_EMIS_MINB
+#define DLSM_HDP_EMIS_MINB 1
+#endif
 template <int PART>
-__global__ void __launch_bounds__(128) k_hdp_update(const HdpParams p)
+__global__ void __launch_bounds__(128, PART == 1 ? DLSM_HDP_EMIS_MINB : 1) k_hdp_update(const HdpParams p)
 {
     constexpr bool kEmis = PART != 2, kTrans = PART != 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
