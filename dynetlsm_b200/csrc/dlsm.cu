@@ -280,6 +280,7 @@ void read_env_options(dlsm_handle *h)
     h->opt[DLSM_OPT_NO_ROWSUM_CACHE] = on("DLSM_NO_ROWSUM");
     if (const char *m = getenv("DLSM_CHAIN_KERNEL"))
         h->opt[DLSM_OPT_CHAIN_KERNEL] = !strcmp(m, "block") ? DLSM_CHAIN_BLOCK
+                                        : !strcmp(m, "block2") ? DLSM_CHAIN_BLOCK_PAIR
                                         : !strcmp(m, "node") ? DLSM_CHAIN_NODE
                                         : !strcmp(m, "rowsum") ? DLSM_CHAIN_NODE_ROWSUM : DLSM_CHAIN_AUTO;
     if (const char *m = getenv("DLSM_CC_KERNEL")) h->opt[DLSM_OPT_CC_KERNEL] = atoll(m);
@@ -659,7 +660,10 @@ int chain_kernel(const dlsm_handle *h)
 }
 
 // which kernel serves the one-CTA-per-chain mapping (exact likelihoods): DLSM_OPT_CHAIN_KERNEL
-bool chain_blk(const dlsm_handle *h) { return h->lk != kCaseControl && chain_kernel(h) == DLSM_CHAIN_BLOCK; }
+bool chain_blk(const dlsm_handle *h)
+{
+    return h->lk != kCaseControl && (chain_kernel(h) == DLSM_CHAIN_BLOCK || chain_kernel(h) == DLSM_CHAIN_BLOCK_PAIR);
+}
 
 int launch_sweep(dlsm_handle *h, const SweepParams &p)
 {
@@ -671,7 +675,7 @@ int launch_sweep(dlsm_handle *h, const SweepParams &p)
         else rc = launch_slice_lk<kCaseControl>(h, p);
     } else if (chain_blk(h)) {
         // block-speculative chain kernel (k_sweep_cb): 32 nodes per step, lanes = rows
-        cudaError_t ce = cb_launch(p, h->lk == kDirected, h->stream);
+        cudaError_t ce = cb_launch(p, h->lk == kDirected, h->stream, chain_kernel(h) == DLSM_CHAIN_BLOCK_PAIR);
         if (ce != cudaSuccess) { end_phase(h); CU(h, ce); }
         rc = DLSM_OK;
     } else {
@@ -1033,7 +1037,7 @@ int dlsm_set_option(dlsm_handle *h, int option, int64_t value)
     if (value < 0) FAIL(h, DLSM_ERR_INVALID, "option values are non-negative");
     if (option == DLSM_OPT_NO_CLUSTER && value > 3) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_NO_CLUSTER takes 0..3");
     if (option == DLSM_OPT_CC_KERNEL && value > 4) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_CC_KERNEL takes 0..4");
-    if (option == DLSM_OPT_CHAIN_KERNEL && value > DLSM_CHAIN_BLOCK) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_CHAIN_KERNEL takes a dlsm_chain_kernel value");
+    if (option == DLSM_OPT_CHAIN_KERNEL && value > DLSM_CHAIN_BLOCK_PAIR) FAIL(h, DLSM_ERR_INVALID, "DLSM_OPT_CHAIN_KERNEL takes a dlsm_chain_kernel value");
     h->opt[option] = value;
     h->rows_valid = false, h->sweeps_since_set = 0;
     h->cluster_cs = -1;

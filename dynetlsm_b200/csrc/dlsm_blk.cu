@@ -24,6 +24,7 @@
 //
 // Exact: the decisions are those of the sequential sweep (sums differ in order only, ~1e-13 relative).
 #include "dlsm_kernels.cuh"
+#include "dlsm_dyad.cuh"
 #include "dlsm_blk.h"
 
 #include <cstdio>
@@ -63,17 +64,6 @@ __device__ __forceinline__ void mbar_wait_cta(uint32_t addr, uint32_t parity)
 __device__ __forceinline__ void cl_st_s32(uint32_t addr, int v)
 {
     asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-
-// the dyad {row node j, column node i}: both directions for the directed model
-//   yr: bit Y[j, i] (j sends), yc: bit Y[i, j] (i sends), as y - 1/2
-template <int LK, int DM>
-__device__ __forceinline__ double dyad(const double (&xi)[DM], double ri, const double (&xj)[DM], double rj,
-                                       double yr, double yc, double b0, double b1, int d)
-{
-    const double dist = fast_dist<DM>(xi, xj, d);
-    if (LK == kUndirected) return logit_term(yr, b0 - dist);
-    return logit_term(yr, eta_directed(b0, b1, dist, ri, rj)) + logit_term(yc, eta_directed(b0, b1, dist, rj, ri));
 }
 
 // shared-memory carve-up (doubles unless noted); every CTA uses the same layout
@@ -1112,10 +1102,13 @@ static cudaError_t cb_launch_x(const SweepParams &p, int ctas_per_sm_by_smem, cu
     return cb_launch_t<LK, D, XS, 512, 1>(p, warps, stream);
 }
 
-cudaError_t cb_launch(const SweepParams &p, bool directed, cudaStream_t stream)
+cudaError_t cb_launch(const SweepParams &p, bool directed, cudaStream_t stream, bool allow_pair)
 {
     const size_t max_smem = 227 * 1024;
     const bool xs = cb_smem_bytes(p.net.T, p.net.n, p.net.d, true) <= max_smem;
+    // a chain with an SM to itself: two warps per slice (k_sweep_cbp, dlsm_cbp.cu)
+    if (allow_pair && p.C <= 148 && p.net.d == 2 && cbp_applicable(p.net.T, p.net.n, p.net.d))
+        return cbp_launch(p, directed, stream);
     int per_sm = (int)(max_smem / (cb_smem_bytes(p.net.T, p.net.n, p.net.d, xs) + 1024));
     if (p.C <= 148) per_sm = 1; // at most one chain per SM: all the registers
     const bool d2 = p.net.d == 2;

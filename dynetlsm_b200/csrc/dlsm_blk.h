@@ -18,6 +18,10 @@ cudaError_t blkw_launch(const SweepParams &p, bool directed, int CS, int *progre
                         double *ll_slices, cudaStream_t stream, int *max_active);
 size_t blkw_smem_bytes(int n, int d, bool directed, int W);
 // k_sweep_cb: block-speculative sweep, one CTA per chain / one warp per slice (many chains)
-cudaError_t cb_launch(const SweepParams &p, bool directed, cudaStream_t stream);
+// allow_pair: chains that have an SM to themselves (C <= 148, d = 2, T <= 15) run on k_sweep_cbp
+cudaError_t cb_launch(const SweepParams &p, bool directed, cudaStream_t stream, bool allow_pair = false);
+// k_sweep_cbp (dlsm_cbp.cu): the same sweep with TWO warps per slice, one chain per SM
+bool cbp_applicable(int T, int n, int d);
+cudaError_t cbp_launch(const SweepParams &p, bool directed, cudaStream_t stream);
 size_t cb_smem_bytes(int T, int n, int d, bool xs);
 } // namespace dlsm

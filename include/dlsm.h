@@ -134,7 +134,7 @@ int dlsm_synchronize(dlsm_handle *h);
  * DLSM_SWEEP_MODE=chain|chain-dense|slice|slice-plain, DLSM_FFBS=thread|warp, DLSM_FFBS_SMEM,
  * DLSM_FFBS_PER_SM=<n>, DLSM_NO_GATHER_PACK, DLSM_NO_LLCUR, DLSM_CENTER_EXACT, DLSM_HDP_SEGMENTED,
  * DLSM_NO_EARLY_X, DLSM_TRACE_CHUNK_BYTES=<bytes>, DLSM_NO_ROWSUM, DLSM_NO_CLUSTER=1|2,
- * DLSM_CHAIN_KERNEL=rowsum|node|block, DLSM_CC_KERNEL=1|2|3. */
+ * DLSM_CHAIN_KERNEL=rowsum|node|block|block2, DLSM_CC_KERNEL=1|2|3|4. */
 typedef enum {
     DLSM_OPT_SWEEP_MODE = 0,        /* dlsm_sweep_mode: which latent-sweep kernel (default: heuristic) */
     DLSM_OPT_FFBS_KERNEL = 1,       /* dlsm_ffbs_kernel: label kernel mapping */
@@ -170,7 +170,10 @@ typedef enum {
     DLSM_CHAIN_AUTO = 0,        /* block kernel up to two chains per SM, else row-sum cache for n >= 256, else node */
     DLSM_CHAIN_NODE_ROWSUM = 1, /* node by node; the device loop evaluates proposals only (row-sum cache) */
     DLSM_CHAIN_NODE = 2,        /* node by node, proposal and current position evaluated afresh (k_sweep) */
-    DLSM_CHAIN_BLOCK = 3        /* 32 nodes per step, lanes = rows (k_sweep_cb) */
+    DLSM_CHAIN_BLOCK = 3,       /* 32 nodes per step, lanes = rows (k_sweep_cb) */
+    DLSM_CHAIN_BLOCK_PAIR = 4   /* the same with two warps per slice where a chain has an SM to itself
+                                   (k_sweep_cbp; C <= 148, d = 2, T <= 15; measured: -2 % at n = 500, +40 % at
+                                   n = 120 -- an A/B switch, not a default) */
 } dlsm_chain_kernel;
 int dlsm_set_option(dlsm_handle *h, int option, int64_t value);
 

@@ -221,13 +221,16 @@ def test_cluster_kernel_native_rng_chain_equals_cta_per_slice_chain():
 @pytest.mark.parametrize("T,n,d,directed,K,C_", [(9, 120, 2, False, 10, 3), (4, 70, 3, False, 0, 2), (10, 500, 2, False, 10, 150),
                                                  (5, 90, 2, True, 0, 2), (3, 257, 2, True, 6, 2), (2, 1500, 2, False, 0, 1),
                                                  (1, 33, 2, False, 0, 2), (3, 31, 2, True, 0, 200), (17, 40, 2, False, 0, 2)])
-def test_block_chain_kernel_replay_vs_oracle(T, n, d, directed, K, C_):
-    """Recorded draws through k_sweep_cb: the oracle's decisions and states, bit for bit."""
+@pytest.mark.parametrize("kern", ["block", "block-pair"])
+def test_block_chain_kernel_replay_vs_oracle(T, n, d, directed, K, C_, kern):
+    """Recorded draws through k_sweep_cb (one warp per slice) and k_sweep_cbp ("block-pair": two warps per
+    slice where a chain has an SM to itself: C <= 148, d = 2, T <= 15): the oracle's decisions and
+    states, bit for bit."""
     L = _L()
     rng, X, Y = _net(T, n, d, directed, seed=13 * n + T)
     e, Xs, radii = _engine(T, n, d, directed, C_, X, Y, rng, K=K)
     e.set_option(L.OPT_SWEEP_MODE, L.SWEEP_CHAIN if C_ <= 148 else L.SWEEP_CHAIN_DENSE)
-    e.set_option(L.OPT_CHAIN_KERNEL, L.CHAIN_BLOCK)
+    e.set_option(L.OPT_CHAIN_KERNEL, L.CHAIN_BLOCK if kern == "block" else L.CHAIN_BLOCK_PAIR)
     ic = np.array([0.6, 0.35]) if directed else np.array([0.6])
     step = 0.02 / n if directed else 0.12
     hy = dict(tau_sq=float(np.mean(X[0] * X[0])), sigma_sq=0.001 / n) if directed else dict(tau_sq=2.0, sigma_sq=0.1)
@@ -255,7 +258,7 @@ def test_block_chain_kernel_replay_vs_oracle(T, n, d, directed, K, C_):
 def test_block_chain_kernel_device_loop_equals_node_kernel_loop(T, n, d, directed, K):
     L = _L()
     outs = []
-    for kern in (L.CHAIN_BLOCK, L.CHAIN_NODE):
+    for kern in (L.CHAIN_BLOCK, L.CHAIN_NODE, L.CHAIN_BLOCK_PAIR):
         rng, X, Y = _net(T, n, d, directed, seed=3 * n + T)
         e, _, _ = _engine(T, n, d, directed, 3, X, Y, rng, K=K, tune=500, tune_interval=3)
         e.set_option(L.OPT_SWEEP_MODE, L.SWEEP_CHAIN)
@@ -264,5 +267,6 @@ def test_block_chain_kernel_device_loop_equals_node_kernel_loop(T, n, d, directe
         outs.append([e.get(f) for f in (L.F_X, L.F_INTERCEPT)] + ([e.get(L.F_RADII)] if directed else []) +
                     ([e.get(L.F_Z)] if K else []))
         assert np.allclose(e.get(L.F_LOGLIK), e.loglik_full(), rtol=1e-11, atol=0)
-    for a, b in zip(*outs):
-        assert np.array_equal(a, b)
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)
