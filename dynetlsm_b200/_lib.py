@@ -15,9 +15,9 @@ LIB_PATH = os.environ.get("DLSM_LIB") or os.path.join(HERE, "libdlsm.so")   # DL
 CSRC = os.path.join(HERE, "csrc")
 # translation units -> the headers each depends on (mtime-based rebuild of the unit's object file)
 HEADERS = [os.path.join(CSRC, f) for f in ("dlsm_kernels.cuh", "dlsm_device.cuh", "dlsm_tables.cuh",
-                                            "dlsm_hdp.cuh", "dlsm_trace.cuh", "dlsm_blk.h", "dlsm_graph.h", "dlsm_cc.h", "dlsm_ccd.h", "dlsm_dyad.cuh")]
+                                            "dlsm_hdp.cuh", "dlsm_trace.cuh", "dlsm_blk.h", "dlsm_graph.h", "dlsm_cc.h", "dlsm_ccd.h", "dlsm_dyad.cuh", "dlsm_fullr.h")]
 HEADERS.append(os.path.join(ROOT, "include", "dlsm.h"))
-UNITS = [os.path.join(CSRC, f) for f in ("dlsm.cu", "dlsm_blk.cu", "dlsm_graph.cu", "dlsm_cc.cu", "dlsm_ccd.cu", "dlsm_cbp.cu")]
+UNITS = [os.path.join(CSRC, f) for f in ("dlsm.cu", "dlsm_blk.cu", "dlsm_graph.cu", "dlsm_cc.cu", "dlsm_ccd.cu", "dlsm_cbp.cu", "dlsm_fullr.cu")]
 SRC = UNITS + HEADERS
 OBJ_DIR = os.path.join(HERE, "build")
 
@@ -103,7 +103,7 @@ EXPORTS = [
 # dlsm_option / dlsm_sweep_mode / dlsm_ffbs_kernel (include/dlsm.h)
 (OPT_SWEEP_MODE, OPT_FFBS_KERNEL, OPT_FFBS_SMEM_STAGE, OPT_FFBS_CTAS_PER_SM, OPT_NO_GATHER_PACK,
  OPT_NO_TRACKED_LOGLIK, OPT_CENTER_EXACT, OPT_HDP_SEGMENTED, OPT_NO_EARLY_X, OPT_TRACE_CHUNK_BYTES,
- OPT_NO_ROWSUM_CACHE, OPT_NO_CLUSTER, OPT_CHAIN_KERNEL, OPT_CC_KERNEL) = range(14)
+ OPT_NO_ROWSUM_CACHE, OPT_NO_CLUSTER, OPT_CHAIN_KERNEL, OPT_CC_KERNEL, OPT_FULL_KERNEL) = range(15)
 CHAIN_AUTO, CHAIN_NODE_ROWSUM, CHAIN_NODE, CHAIN_BLOCK, CHAIN_BLOCK_PAIR = range(5)
 SWEEP_AUTO, SWEEP_CHAIN, SWEEP_CHAIN_DENSE, SWEEP_SLICE, SWEEP_SLICE_PLAIN = range(5)
 FFBS_AUTO, FFBS_THREAD, FFBS_WARP = range(3)

@@ -8,6 +8,7 @@
 #include "dlsm_graph.h"
 #include "dlsm_cc.h"
 #include "dlsm_ccd.h"
+#include "dlsm_fullr.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -284,6 +285,7 @@ void read_env_options(dlsm_handle *h)
                                         : !strcmp(m, "node") ? DLSM_CHAIN_NODE
                                         : !strcmp(m, "rowsum") ? DLSM_CHAIN_NODE_ROWSUM : DLSM_CHAIN_AUTO;
     if (const char *m = getenv("DLSM_CC_KERNEL")) h->opt[DLSM_OPT_CC_KERNEL] = atoll(m);
+    if (const char *m = getenv("DLSM_FULL_KERNEL")) h->opt[DLSM_OPT_FULL_KERNEL] = atoll(m);
     if (const char *m = getenv("DLSM_NO_CLUSTER")) h->opt[DLSM_OPT_NO_CLUSTER] = atoll(m) > 0 ? atoll(m) : 1;
     if (const char *m = getenv("DLSM_TRACE_CHUNK_BYTES")) h->opt[DLSM_OPT_TRACE_CHUNK_BYTES] = atoll(m);
     apply_sweep_mode(h);
@@ -727,6 +729,15 @@ int launch_full(dlsm_handle *h, const double *rinv0, const double *rinv1, int nv
     dim3 grid(h->cfg.T * h->full_tiles, h->cfg.n_chains);
     const size_t smem = (h->lk == kCaseControl) ? 0 : (size_t)h->cfg.n * h->cfg.d * sizeof(double);
     const bool d2 = h->cfg.d == 2;
+    // one variant of an exact likelihood, d = 2, long rows: lanes = rows, broadcast columns (k_full_lr;
+    // cfg 3: 0.346 -> 0.30 ms per pass; at n = 120 its 10 work items per slice do not fill the CTAs: +6 %)
+    if (h->lk != kCaseControl && d2 && nv == 1 && h->opt[DLSM_OPT_FULL_KERNEL] != 1 &&
+        (h->cfg.n >= 256 || h->opt[DLSM_OPT_FULL_KERNEL] == 2) &&
+        fullr_smem_bytes(h->cfg.n, h->lk == kDirected) <= kMaxSmem) {
+        CU(h, fullr_launch(p, h->lk == kDirected, grid, h->stream));
+        h->ctr.kernel_launches += 1;
+        return DLSM_OK;
+    }
 #define LAUNCH_FULL_NV(LK, D, NV)                                                                \
     do {                                                                                         \
         CU(h, cudaFuncSetAttribute(k_full<LK, D, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -270,3 +270,27 @@ def test_block_chain_kernel_device_loop_equals_node_kernel_loop(T, n, d, directe
     for other in outs[1:]:
         for a, b in zip(outs[0], other):
             assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------
+# k_full_lr: the one-variant full-network log-likelihood with lanes = rows (intercept / radii MH of the
+# device loop) against the folded-rows kernel k_full
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,n,directed,C_", [(3, 33, False, 2), (9, 120, False, 3), (4, 257, True, 2),
+                                             (2, 500, False, 5), (3, 1000, True, 1), (2, 2000, True, 1)])
+def test_full_network_kernel_lanes_are_rows_equals_folded_rows(T, n, directed, C_):
+    L = _L()
+    outs = []
+    for full_kernel in (2, 1):       # k_full_lr at any n, k_full
+        rng, X, Y = _net(T, n, 2, directed, seed=5 * n + T)
+        e, _, _ = _engine(T, n, 2, directed, C_, X, Y, rng, tune=500, tune_interval=3)
+        e.set_option(L.OPT_FULL_KERNEL, full_kernel)
+        e.run_sweeps(4)
+        assert np.allclose(e.get(L.F_LOGLIK), e.loglik_full(), rtol=1e-11, atol=0)   # tracked through the MH steps
+        outs.append([e.get(f) for f in (L.F_X, L.F_INTERCEPT)] + ([e.get(L.F_RADII)] if directed else []) +
+                    [e.get(L.F_LOGLIK)])
+    for a, b in zip(*outs):
+        if a.ndim == 1:
+            assert np.allclose(a, b, rtol=1e-11, atol=0)
+        else:
+            assert np.array_equal(a, b)      # same decisions: the two kernels differ in summation order only
