@@ -383,3 +383,28 @@ def test_device_cooccurrence_equals_host_counts():
     assert ns == 15
     assert np.array_equal(counts, (z[:, :, :, :, None] == z[:, :, :, None, :]).sum(axis=(0, 1)).astype(np.uint32))
     assert e.cooccurrence()[1] == 0
+
+
+@pytest.mark.parametrize("name,directed", [("lsm_undirected_monks.npz", False), ("lsm_directed_monks.npz", True)])
+def test_logp_against_the_reference_trace(name, directed):
+    """k_logp pinned DIRECTLY on the reference: the stored samples of a reference fit (positions,
+    intercepts, radii; oracle/make_golden.py) are put on the device and dlsm_logp must return the
+    reference's own logps_ (lsm.py:576-625)."""
+    import os
+    L = _L()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+    Y = g["Y"].astype(np.float64)
+    T, n, _ = Y.shape
+    Xs, ics, want = g["Xs"], g["intercepts"], g["logps"]
+    S = min(len(want), 12)
+    e = L.Engine(T=T, n=n, d=Xs.shape[-1], n_chains=S, is_directed=directed)
+    e.set_network(Y)
+    e.set(L.F_X, np.ascontiguousarray(Xs[:S]))
+    ic = np.zeros((S, 2)); ic[:, :ics.shape[1]] = ics[:S]
+    e.set(L.F_INTERCEPT, ic)
+    if directed:
+        e.set(L.F_RADII, np.ascontiguousarray(g["radiis"][:S]))
+    e.set_hyper(tau_sq=float(g["tau_sq"]), sigma_sq=float(g["sigma_sq"]),
+                intercept_prior=np.asarray(g["intercept_prior"], dtype=np.float64),
+                intercept_variance_prior=float(g["intercept_variance_prior"]))
+    assert np.allclose(e.logp(), want[:S], rtol=1e-10, atol=0)
