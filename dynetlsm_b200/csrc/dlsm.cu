@@ -286,6 +286,7 @@ void read_env_options(dlsm_handle *h)
                                         : !strcmp(m, "rowsum") ? DLSM_CHAIN_NODE_ROWSUM : DLSM_CHAIN_AUTO;
     if (const char *m = getenv("DLSM_CC_KERNEL")) h->opt[DLSM_OPT_CC_KERNEL] = atoll(m);
     if (const char *m = getenv("DLSM_FULL_KERNEL")) h->opt[DLSM_OPT_FULL_KERNEL] = atoll(m);
+    if (const char *m = getenv("DLSM_CCD_GROUP")) h->opt[DLSM_OPT_CCD_GROUP] = atoll(m);
     if (const char *m = getenv("DLSM_NO_CLUSTER")) h->opt[DLSM_OPT_NO_CLUSTER] = atoll(m) > 0 ? atoll(m) : 1;
     if (const char *m = getenv("DLSM_TRACE_CHUNK_BYTES")) h->opt[DLSM_OPT_TRACE_CHUNK_BYTES] = atoll(m);
     apply_sweep_mode(h);
@@ -539,7 +540,7 @@ int launch_cc_batch(dlsm_handle *h, const SweepParams &p)
         const size_t cells = CT * c.n;
         if (!h->d_gather) CU(h, cudaMalloc((void **)&h->d_gather, cells * 4 * sizeof(double)));
         int launches = 0;
-        CU(h, ccd_launch(p, h->d_gather, &h->ccd, h->sm_count, h->stream, &launches));
+        CU(h, ccd_launch(p, h->d_gather, &h->ccd, h->sm_count, (int)h->opt[DLSM_OPT_CCD_GROUP], h->stream, &launches));
         h->ctr.kernel_launches += launches - 1;
         return DLSM_OK;
     }

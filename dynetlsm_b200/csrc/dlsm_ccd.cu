@@ -39,7 +39,6 @@
 #include "dlsm_kernels.cuh"
 #include "dlsm_ccd.h"
 
-#include <cstdlib>
 #include <cstring>
 
 namespace dlsm {
@@ -56,7 +55,6 @@ struct CcdWork {
     int *next = nullptr;     // [C][T]       ticket counters
     size_t cells = 0, pairs = 0;
     int grid = 0;
-    int group = 0;           // chains per launch of the sweep kernel (0 = heuristic)
 };
 
 struct CcdView {
@@ -406,8 +404,8 @@ void ccd_free(CcdWork *w)
     delete w;
 }
 
-cudaError_t ccd_launch(const SweepParams &p, double *G, CcdWork **work, int sm_count, cudaStream_t stream,
-                       int *launches)
+cudaError_t ccd_launch(const SweepParams &p, double *G, CcdWork **work, int sm_count, int chains_per_launch,
+                       cudaStream_t stream, int *launches)
 {
     const size_t pairs = (size_t)p.C * p.net.T, cells = pairs * p.net.n;
     cudaError_t e;
@@ -416,7 +414,6 @@ cudaError_t ccd_launch(const SweepParams &p, double *G, CcdWork **work, int sm_c
     if (!w) {
         w = new CcdWork;
         w->cells = cells; w->pairs = pairs;
-        if (const char *g = getenv("DLSM_CCD_GROUP")) w->group = atoi(g); // (A/B runs; read once)
         int per_sm = 0;
         e = cudaMalloc((void **)&w->Nw, cells * 4 * sizeof(double));
         if (e == cudaSuccess) e = cudaMalloc((void **)&w->prep, cells * kPrepStride * sizeof(double));
@@ -440,7 +437,7 @@ cudaError_t ccd_launch(const SweepParams &p, double *G, CcdWork **work, int sm_c
     // parallelism; more warps per pair wait more often for a node that is still in flight.  Measured at
     // cfg 5: 8 chains per launch 13.6 ms, 4 chains 13.4 ms (profiles/r2d_ab_cfg5.json).
     const int warps = w->grid * (kCcdThreads / 32);
-    int group = w->group > 0 ? w->group : (warps / 64) / p.net.T;
+    int group = chains_per_launch > 0 ? chains_per_launch : (warps / 64) / p.net.T;
     group = group < 1 ? 1 : (group > p.C ? p.C : group);
     int nl = 2;
     for (int c0 = 0; c0 < p.C; c0 += group, nl++) {
