@@ -103,7 +103,7 @@ EXPORTS = [
 # dlsm_option / dlsm_sweep_mode / dlsm_ffbs_kernel (include/dlsm.h)
 (OPT_SWEEP_MODE, OPT_FFBS_KERNEL, OPT_FFBS_SMEM_STAGE, OPT_FFBS_CTAS_PER_SM, OPT_NO_GATHER_PACK,
  OPT_NO_TRACKED_LOGLIK, OPT_CENTER_EXACT, OPT_HDP_SEGMENTED, OPT_NO_EARLY_X, OPT_TRACE_CHUNK_BYTES,
- OPT_NO_ROWSUM_CACHE, OPT_NO_CLUSTER, OPT_CHAIN_KERNEL, OPT_CC_KERNEL, OPT_FULL_KERNEL, OPT_CCD_GROUP) = range(16)
+ OPT_NO_ROWSUM_CACHE, OPT_NO_CLUSTER, OPT_CHAIN_KERNEL, OPT_CC_KERNEL, OPT_FULL_KERNEL, OPT_CCD_GROUP, OPT_FFBS_NO_L2_WINDOW) = range(17)
 CHAIN_AUTO, CHAIN_NODE_ROWSUM, CHAIN_NODE, CHAIN_BLOCK, CHAIN_BLOCK_PAIR = range(5)
 SWEEP_AUTO, SWEEP_CHAIN, SWEEP_CHAIN_DENSE, SWEEP_SLICE, SWEEP_SLICE_PLAIN = range(5)
 FFBS_AUTO, FFBS_THREAD, FFBS_WARP = range(3)

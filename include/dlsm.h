@@ -134,7 +134,8 @@ int dlsm_synchronize(dlsm_handle *h);
  * DLSM_SWEEP_MODE=chain|chain-dense|slice|slice-plain, DLSM_FFBS=thread|warp, DLSM_FFBS_SMEM,
  * DLSM_FFBS_PER_SM=<n>, DLSM_NO_GATHER_PACK, DLSM_NO_LLCUR, DLSM_CENTER_EXACT, DLSM_HDP_SEGMENTED,
  * DLSM_NO_EARLY_X, DLSM_TRACE_CHUNK_BYTES=<bytes>, DLSM_NO_ROWSUM, DLSM_NO_CLUSTER=1|2,
- * DLSM_CHAIN_KERNEL=rowsum|node|block|block2, DLSM_CC_KERNEL=1|2|3|4, DLSM_FULL_KERNEL=1|2, DLSM_CCD_GROUP=<chains>. */
+ * DLSM_CHAIN_KERNEL=rowsum|node|block|block2, DLSM_CC_KERNEL=1|2|3|4, DLSM_FULL_KERNEL=1|2, DLSM_CCD_GROUP=<chains>,
+ * DLSM_FFBS_NO_L2_WINDOW. */
 typedef enum {
     DLSM_OPT_SWEEP_MODE = 0,        /* dlsm_sweep_mode: which latent-sweep kernel (default: heuristic) */
     DLSM_OPT_FFBS_KERNEL = 1,       /* dlsm_ffbs_kernel: label kernel mapping */
@@ -164,6 +165,7 @@ typedef enum {
                                        rows, lanes = columns), 2 = k_full_lr at any n */
     DLSM_OPT_CCD_GROUP = 15,        /* chains per launch of the dataflow case-control sweep (0 = heuristic: about 64
                                        warps per (chain, slice) pair) */
+    DLSM_OPT_FFBS_NO_L2_WINDOW = 16, /* 1: no persisting-L2 access-policy window over the label kernel's global stage */
     DLSM_OPT_COUNT_
 } dlsm_option;
 typedef enum {
