@@ -1018,6 +1018,11 @@ void dlsm_destroy(dlsm_handle *h)
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->l2_persist_set) { // give the persisting-L2 set-aside of the label kernel's stage back to the device
+        cudaDeviceSynchronize();
+        cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    }
     for (auto &e : h->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (int f = 0; f < DLSM_F_COUNT_; f++) cudaFree(h->field[f]);
     void *ptrs[] = {h->rowbits, h->colbits, h->deg, h->in_edges, h->out_edges, h->ctrl_in,
