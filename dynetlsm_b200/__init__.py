@@ -10,5 +10,6 @@ from . import _lib  # noqa: F401
 from ._lib import Engine, DlsmError, device_count  # noqa: F401
 from .lsm import DynamicNetworkLSM  # noqa: F401,E402
 from .hdp_lpcm import DynamicNetworkHDPLPCM  # noqa: F401,E402
+from .lpcm import DynamicNetworkLPCM  # noqa: F401,E402
 from .metropolis import Metropolis  # noqa: F401,E402
 from .case_control_likelihood import DirectedCaseControlSampler  # noqa: F401,E402

@@ -18,7 +18,7 @@ from scipy.stats import truncnorm
 
 TINY = np.finfo("float64").tiny
 
-__all__ = ["HDPHyper", "conjugate_updates", "hdp_log_prior"]
+__all__ = ["HDPHyper", "conjugate_updates", "mixture_updates", "hdp_log_prior", "mixture_log_prior"]
 
 
 class HDPHyper(object):
@@ -83,22 +83,12 @@ def _mbar(rng, m, beta, kappa, alpha):
     return np.sum(m_bar, axis=(0, 1)) + m[0, 0], w
 
 
-def conjugate_updates(rng, hp, X, z, n, nk, mu, sigma, lmbda, beta, weights):
-    """Everything between the label draw and the stored sample of one sweep
-    (hdp_lpcm.py:881-1023).  ``n`` (T,K,K) transition counts, ``nk`` (T,K) occupancies come from
-    the device label kernel.  mu, sigma, weights are updated in place; returns (beta, lmbda)."""
+def mixture_updates(rng, hp, X, z, nk, mu, sigma, lmbda):
+    """Cluster means, variances, blending coefficient and the two scale hyper-priors: the block
+    the HDP sampler (hdp_lpcm.py:899-977) and the finite mixture (lpcm.py:582-656) share, in the
+    reference's draw order.  mu, sigma are updated in place; returns lmbda."""
     T, n_nodes, d = X.shape
     K = sigma.shape[0]
-    m = _tables(rng, n, beta, hp.alpha_init, hp.alpha, hp.kappa)
-    m_bar, w_over = _mbar(rng, m, beta, kappa=hp.kappa, alpha=hp.alpha)
-
-    beta = rng.dirichlet((hp.gamma / K) + m_bar)
-    weights[0, 0] = _clipped_dirichlet(rng, hp.alpha_init * beta + nk[0])
-    base = hp.alpha * beta + hp.kappa * np.eye(K)
-    for t in range(1, T):
-        for k in range(K):
-            weights[t, k] = _clipped_dirichlet(rng, base[k] + n[t, k])
-
     member = [[z[t] == k for k in range(K)] for t in range(T)]
     # cluster means
     for k in range(K):
@@ -154,6 +144,26 @@ def conjugate_updates(rng, hp, X, z, n, nk, mu, sigma, lmbda, beta, weights):
         for k in range(K):
             sc += 0.5 * (1. / sigma[k])
         hp.b = rng.gamma(shape=0.5 * (hp.c0 + K * hp.a), scale=1. / sc)
+    return lmbda
+
+
+def conjugate_updates(rng, hp, X, z, n, nk, mu, sigma, lmbda, beta, weights):
+    """Everything between the label draw and the stored sample of one sweep
+    (hdp_lpcm.py:881-1023).  ``n`` (T,K,K) transition counts, ``nk`` (T,K) occupancies come from
+    the device label kernel.  mu, sigma, weights are updated in place; returns (beta, lmbda)."""
+    T, n_nodes, d = X.shape
+    K = sigma.shape[0]
+    m = _tables(rng, n, beta, hp.alpha_init, hp.alpha, hp.kappa)
+    m_bar, w_over = _mbar(rng, m, beta, kappa=hp.kappa, alpha=hp.alpha)
+
+    beta = rng.dirichlet((hp.gamma / K) + m_bar)
+    weights[0, 0] = _clipped_dirichlet(rng, hp.alpha_init * beta + nk[0])
+    base = hp.alpha * beta + hp.kappa * np.eye(K)
+    for t in range(1, T):
+        for k in range(K):
+            weights[t, k] = _clipped_dirichlet(rng, base[k] + n[t, k])
+
+    lmbda = mixture_updates(rng, hp, X, z, nk, mu, sigma, lmbda)
     # concentration parameters
     hp.gamma = _concentration(rng, hp.gamma, np.sum(m_bar > 0), np.sum(m_bar),
                               hp.gamma_prior_shape, hp.gamma_prior_rate)
@@ -185,6 +195,18 @@ def hdp_log_prior(hp, K, X, intercept, intercept_prior, intercept_variance_prior
     for t in range(1, T):
         for k in range(K):
             lp += _dirichlet_logpdf(weights[t, k], hp.alpha * beta + deltas[k])
+    return lp + mixture_log_prior(hp, X, intercept, intercept_prior, intercept_variance_prior, mu, sigma,
+                                  z, weights, lmbda, radii=radii)
+
+
+def mixture_log_prior(hp, X, intercept, intercept_prior, intercept_variance_prior, mu, sigma, z,
+                      weights, lmbda, radii=None):
+    """The terms hdp_lpcm.py:1208-1280 and lpcm.py:785-852 have in common: label Markov chains under
+    ``weights`` (T, K, K; row [0, 0] the initial distribution), intercept prior, latent positions
+    given the mixture, cluster means / variances, lambda, radii, scale hyper-priors."""
+    T, n_nodes, _ = X.shape
+    K = sigma.shape[0]
+    lp = 0.0
     # label Markov chains (hdp_lpcm.py:1208-1212), vectorised over nodes
     lp += np.sum(np.log(weights[0, 0, z[0]]))
     for t in range(1, T):
