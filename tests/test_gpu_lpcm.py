@@ -47,9 +47,11 @@ def test_lpcm_replay_reproduces_the_reference_fit_undirected():
 
 
 def test_lpcm_replay_directed_monks_vi_selection():
-    """Directed model with radii, point estimate by posterior-expected VI.  The chain must be a
-    valid one; where the host initialisation reproduces the reference bit for bit (it does for the
-    undirected model above) the labels follow the reference chain as well."""
+    """Directed model with radii, point estimate by posterior-expected VI.  Directed initial values
+    are not bit-comparable with the reference (its intercept MLE reads an uninitialised
+    accumulator, SURVEY.md K10 / host_init.directed_intercept_mle), so the chain is checked for
+    validity and self-consistency; the sweeps themselves are pinned by the teacher-forced replays
+    of tests/test_gpu_parity.py and the host block by tests/test_lpcm_host.py."""
     from dynetlsm_b200 import DynamicNetworkLPCM
     g = load_golden("lpcm_directed_monks.npz")
     Y = g["Y"].astype(np.float64)
@@ -65,14 +67,8 @@ def test_lpcm_replay_directed_monks_vi_selection():
     assert m.n_burn_ <= m.selected_id_ <= S                               # VI scans post-burn-in samples
     assert np.allclose(np.diagonal(m.cooccurrence_probas_, axis1=1, axis2=2), 1.0)
     assert m.z_.shape == (T, n) and m.radii_.shape == (n,)
-    exact = (np.array_equal(m.zs_[1:], g["z_out"]) and np.array_equal(m.radiis_[1:], g["radii_out"])
-             and np.array_equal(m.intercepts_[1:], g["intercept_out"]))
-    print("lpcm directed replay follows the reference chain exactly:", exact)
-    if exact:
-        assert m.selected_id_ == int(g["selected_id"])
-        assert np.allclose(m.logps_, g["logps"], rtol=1e-9, atol=0)
-    # the public logp() of a stored sample agrees with the trace
-    i = m.selected_id_
+    # the public logp() of the selected sample agrees with the trace (positions were rotated after
+    # sampling, the joint density is invariant to it; mu_ was rotated with them)
     lp = m.logp(m.X_, m.intercept_, m.mu_, m.sigma_, m.z_, m.init_weight_, m.trans_weight_, m.lambda_,
                 radii=m.radii_)
     assert np.isfinite(lp)
