@@ -1,5 +1,5 @@
 """Wall-clock of the public estimators' fit() on the bench workloads (sweeps/s through the user API,
-traces included).  usage: python tools/fit_timing.py [lsm|hdp] [n_iter] [n_chains]"""
+traces included).  usage: python tools/fit_timing.py [lsm|hdp|lpcm] [n_iter] [n_chains]"""
 import sys
 import time
 import warnings
@@ -9,7 +9,7 @@ import numpy as np
 sys.path.insert(0, ".")
 warnings.filterwarnings("ignore")
 import bench  # noqa: E402
-from dynetlsm_b200 import DynamicNetworkHDPLPCM, DynamicNetworkLSM  # noqa: E402
+from dynetlsm_b200 import DynamicNetworkHDPLPCM, DynamicNetworkLPCM, DynamicNetworkLSM  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "lsm"
 n_iter = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
@@ -17,6 +17,9 @@ chains = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 if which == "lsm":
     w = bench.make_workload("cfg1")
     m = DynamicNetworkLSM(n_iter=n_iter, tune=n_iter // 2, burn=n_iter // 2, random_state=42, n_chains=chains)
+elif which == "lpcm":    # finite mixture: device hot path + host Dirichlet / conjugate block per sweep
+    w = bench.make_workload("cfg2")
+    m = DynamicNetworkLPCM(n_components=10, n_iter=n_iter, tune=n_iter // 2, burn=n_iter // 2, random_state=42)
 else:
     w = bench.make_workload("cfg2")
     m = DynamicNetworkHDPLPCM(n_components=10, n_iter=n_iter, tune=n_iter // 2, burn=n_iter // 2,
