@@ -188,7 +188,8 @@ class DynamicNetworkLPCM(_FittedNetworkMixin):
                 e.set(L.F_MU, mus[it][None]); e.set(L.F_SIGMA, sigmas[it][None])
                 e.set(L.F_LAMBDA, lambdas[it])
                 e.set(L.F_WEIGHTS, stacked_weights(init_w[it], trans_w[it], T)[None])
-                e.set(L.F_Z, zs[it][None])
+                if it == 0 or replay:      # afterwards the labels on the device are the ones just drawn
+                    e.set(L.F_Z, zs[it][None])
 
             def log_post(it):
                 lp = lpcm_log_prior(hp, Xs[it], ics[it], self.intercept_prior,
@@ -211,12 +212,17 @@ class DynamicNetworkLPCM(_FittedNetworkMixin):
                         if cc.n_resample is not None and cc.n_iter % cc.n_resample == 0:
                             drv.draw_controls()
                         cc.n_iter += 1
-                drv.sweep_latent()
-                e.center()
-                drv.sample_intercepts()
-                if self.is_directed:
-                    drv.sample_radii()
-                drv.sample_labels()
+                if replay:
+                    drv.sweep_latent()
+                    e.center()
+                    drv.sample_intercepts()
+                    if self.is_directed:
+                        drv.sample_radii()
+                    drv.sample_labels()
+                else:
+                    # one call: sweep -> centre -> {intercept / radii MH || label FFBS on the side
+                    # stream}; no HDP prior is set on this handle, so the device loop stops there
+                    e.run_sweeps(1)
                 X = e.get(L.F_X)[0]
                 z = e.get(L.F_Z)[0].astype(np.int64)
                 cnt = e.get(L.F_NCOUNT)[0]

@@ -102,3 +102,36 @@ def test_lpcm_thinning_counts_burn_in_in_stored_samples():
     m = DynamicNetworkLPCM(n_iter=40, burn=20, tune=20, thin=4, n_components=2, random_state=1).fit(Y)
     assert m.n_burn_ == 10 and m.zs_.shape[0] == 20
     assert m.X_mean_.shape == (2, 30, 2)
+
+
+def test_lpcm_device_rng_matches_replay_in_distribution():
+    """Device-RNG fits (Philox hot path in ONE dlsm_run_sweeps call per sweep, label block on the side
+    stream) against reference-equivalent replay fits on a two-community network: intercept, blending
+    coefficient and the co-clustering matrix agree within Monte-Carlo error (SURVEY 8d parity iv)."""
+    from dynetlsm_b200 import DynamicNetworkLPCM
+    from dynetlsm_b200.diagnostics import ess
+    from test_gpu_estimators import _splitting_network
+    Y = _splitting_network(n=36, T=3, seed=7)
+    kw = dict(n_iter=700, tune=300, burn=300, n_features=2, n_components=3)
+    devs = [DynamicNetworkLPCM(random_state=s, sampler="device", **kw).fit(Y) for s in (5, 6, 7)]
+    reps = [DynamicNetworkLPCM(random_state=s, sampler="replay", **kw).fit(Y) for s in (11, 12)]
+    nb = 600
+    a = np.stack([r.intercepts_[nb:, 0] for r in devs])
+    b = np.stack([r.intercepts_[nb:, 0] for r in reps])
+    se = np.sqrt(a.var() / max(ess(a), 10) + b.var() / max(ess(b), 10))
+    print("lpcm device vs replay: intercept", a.mean(), b.mean(), "se", se)
+    assert abs(a.mean() - b.mean()) < 5 * se + 0.05, (a.mean(), b.mean(), se)
+    la = np.mean([r.lambdas_[nb:, 0].mean() for r in devs])
+    lb = np.mean([r.lambdas_[nb:, 0].mean() for r in reps])
+    print("lpcm device vs replay: lambda", la, lb)
+    assert abs(la - lb) < 0.05, (la, lb)
+
+    def cooc(zs):                                     # (S, T, n) -> (T, n, n), invariant to label switching
+        return (zs[:, :, :, None] == zs[:, :, None, :]).mean(axis=0)
+    ca = np.mean([cooc(r.zs_[nb:]) for r in devs], axis=0)
+    cb = np.mean([cooc(r.zs_[nb:]) for r in reps], axis=0)
+    print("lpcm device vs replay: co-clustering mean abs diff", np.abs(ca - cb).mean())
+    assert np.abs(ca - cb).mean() < 0.08, np.abs(ca - cb).mean()
+    truth = np.random.RandomState(7).randint(0, 2, 36)   # the generator's communities
+    same = truth[:, None] == truth[None, :]
+    assert ca[0][same].mean() > ca[0][~same].mean() + 0.2
