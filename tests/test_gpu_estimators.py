@@ -242,3 +242,16 @@ def test_hdp_selection_types_and_thinning(selection, thin):
     assert np.isfinite(z) and 0 <= pval <= 1
     with pytest.raises(ValueError):
         DynamicNetworkHDPLPCM(n_iter=5, selection_type="aic").fit(Y)
+
+
+@pytest.mark.parametrize("sampler", ["device", "replay"])
+def test_hdp_case_control_likelihood_runs_in_both_modes(sampler):
+    """Directed HDP-LPCM on the case-control likelihood (hdp_lpcm.py:722-733, 826-829), control sets
+    redrawn every 8 sweeps: the chain runs, stays finite and never reads past a control list."""
+    from dynetlsm_b200 import DynamicNetworkHDPLPCM
+    g = load_golden("lsm_casecontrol_monks.npz")
+    Y = g["Y"].astype(np.float64)
+    m = DynamicNetworkHDPLPCM(n_iter=20, tune=20, burn=10, tune_interval=6, n_components=4, is_directed=True,
+                              n_control=5, n_resample_control=8, random_state=11, sampler=sampler).fit(Y)
+    assert m.Xs_.shape == (50, 3, 18, 2) and np.isfinite(m.logps_).all()
+    assert m.sampler_counters_["ub_flags"] == 0

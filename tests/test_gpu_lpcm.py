@@ -135,3 +135,22 @@ def test_lpcm_device_rng_matches_replay_in_distribution():
     truth = np.random.RandomState(7).randint(0, 2, 36)   # the generator's communities
     same = truth[:, None] == truth[None, :]
     assert ca[0][same].mean() > ca[0][~same].mean() + 0.2
+
+
+@pytest.mark.parametrize("sampler", ["replay", "device"])
+def test_lpcm_case_control_likelihood_runs_in_both_modes(sampler):
+    """Directed finite mixture on the case-control likelihood (lpcm.py:404-415, 525-527): control
+    sets redrawn every 8 sweeps (host RandomState in replay mode, device Philox otherwise)."""
+    from dynetlsm_b200 import DynamicNetworkLPCM
+    g = load_golden("lsm_casecontrol_monks.npz")
+    Y = g["Y"].astype(np.float64)
+    m = DynamicNetworkLPCM(n_iter=20, tune=20, burn=10, tune_interval=6, n_components=3, is_directed=True,
+                           n_control=5, n_resample_control=8, random_state=11, sampler=sampler).fit(Y)
+    T, n = Y.shape[:2]
+    assert m.Xs_.shape == (50, T, n, 2) and m.radiis_.shape == (50, n)
+    assert np.allclose(m.radiis_.sum(axis=1), 1.0) and np.isfinite(m.logps_).all()
+    cc = m.case_control_sampler_
+    assert np.array_equal(cc.in_edges_, g["cc_in_edges"])
+    assert cc.control_nodes_in_.shape[:2] == (T, n) and cc.control_nodes_out_.shape[:2] == (T, n)
+    assert m.sampler_counters_["ub_flags"] == 0
+    assert not np.array_equal(m.zs_[-1], m.zs_[0]) or not np.array_equal(m.Xs_[-1], m.Xs_[0])
