@@ -29,6 +29,10 @@ from . import model_selection as MS
 __all__ = ["DynamicNetworkLPCM", "lpcm_conjugate_updates", "lpcm_log_prior", "stacked_weights"]
 
 
+class _NotOnDevicePath(NotImplementedError, AttributeError):
+    """Raised by the forecast properties; an AttributeError too, so hasattr() / inspect stay usable."""
+
+
 class MixtureHyper(object):
     """Hyper-parameter state the reference keeps on the estimator (lpcm.py:394-471)."""
 
@@ -311,6 +315,14 @@ class DynamicNetworkLPCM(_FittedNetworkMixin):
                             self.intercept_variance_prior, mu, sigma, z, init_weights, trans_weights,
                             lmbda, radii=radii)
         return float(np.ravel(ll + lp)[0])
+
+    def forecast_probas(self, n_samples=5000):
+        """lpcm.py:229-318 build on forecast.pyx, which is outside the accelerated path."""
+        raise _NotOnDevicePath("one-step-ahead forecasts (forecast.pyx) are not part of the device path")
+
+    forecast_probas_map_ = property(forecast_probas)
+    forecast_probas_plugin_ = property(forecast_probas)
+    forecast_probas_marginalized_ = property(forecast_probas)
 
     def delete_traces(self):
         """lpcm.py:858-873."""
