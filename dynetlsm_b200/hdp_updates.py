@@ -89,20 +89,27 @@ def mixture_updates(rng, hp, X, z, nk, mu, sigma, lmbda):
     reference's draw order.  mu, sigma are updated in place; returns lmbda."""
     T, n_nodes, d = X.shape
     K = sigma.shape[0]
-    member = [[z[t] == k for k in range(K)] for t in range(T)]
+    # members of (t, k) gathered once: x_t - (1 - lambda) x_{t-1} serves the mean and the variance draw
+    # (same operands in the same order as the reference's masked expressions)
+    resid = [[None] * K for _ in range(T)]
+    for t in range(T):
+        zt = z[t]
+        for k in range(K):
+            if nk[t, k] > 0:
+                idx = np.flatnonzero(zt == k)
+                resid[t][k] = X[t][idx] if t == 0 else X[t][idx] - (1 - lmbda) * X[t - 1][idx]
     # cluster means
     for k in range(K):
         prec = 1 / hp.mean_variance_prior
         acc = np.zeros(d)
         for t in range(T):
             if nk[t, k] > 0:
-                msk = member[t][k]
                 if t == 0:
                     prec += nk[0, k] / sigma[k]
-                    acc += (1 / sigma[k]) * np.sum(X[t, msk], axis=0)
+                    acc += (1 / sigma[k]) * np.sum(resid[t][k], axis=0)
                 else:
                     prec += (lmbda ** 2 / sigma[k]) * nk[t, k]
-                    acc += (lmbda / sigma[k]) * np.sum(X[t, msk] - (1 - lmbda) * X[t - 1, msk], axis=0)
+                    acc += (lmbda / sigma[k]) * np.sum(resid[t][k], axis=0)
         var = 1 / prec
         acc *= var
         mu[k] = rng.multivariate_normal(mean=acc, cov=var * np.eye(d))
@@ -112,11 +119,10 @@ def mixture_updates(rng, hp, X, z, nk, mu, sigma, lmbda):
         rate = 0.5 * hp.b
         for t in range(T):
             if nk[t, k] > 0:
-                msk = member[t][k]
                 if t == 0:
-                    rate += 0.5 * np.sum((X[t, msk] - mu[k]) ** 2)
+                    rate += 0.5 * np.sum((resid[t][k] - mu[k]) ** 2)
                 else:
-                    rate += 0.5 * np.sum((X[t, msk] - (1 - lmbda) * X[t - 1, msk] - lmbda * mu[k]) ** 2)
+                    rate += 0.5 * np.sum((resid[t][k] - lmbda * mu[k]) ** 2)
         sigma[k] = 1. / rng.gamma(shape=shape, scale=1. / rate)
     # blending coefficient lambda ~ truncated normal on (0, 1)
     ml = 0.0
