@@ -82,6 +82,8 @@ def run_lpcm(Y, keep, **kw):
     rec["cooccurrence_probas"] = model.cooccurrence_probas_.copy()
     rec["z_hat"] = model.z_.astype(np.int32)
     rec["a"] = np.float64(model.a)
+    rec["intercept_prior"] = np.atleast_1d(np.asarray(model.intercept_prior, dtype=np.float64)).copy()
+    rec["intercept_variance_prior"] = np.float64(model.intercept_variance_prior)
     for nm in ("a0_", "b0_", "c0_", "d0_", "dirichlet_prior_"):
         rec[nm] = np.float64(getattr(model, nm))
     return rec, model

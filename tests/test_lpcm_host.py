@@ -60,28 +60,35 @@ def test_stacked_weights_feed_the_hdp_label_kernel_layout():
     assert np.array_equal(w[1], tw) and np.array_equal(w[2], tw)
 
 
-def test_log_prior_differences_follow_the_reference_trace():
-    """logps = network log-likelihood + prior; the network term of consecutive stored samples is
-    not available on the CPU, but the Dirichlet part is: perturbing only the weights must move the
-    log-prior by the Dirichlet + label-chain terms of lpcm.py:774-787."""
-    from scipy import stats
+@pytest.mark.parametrize("name,directed", [("lpcm_undirected_split.npz", False),
+                                           ("lpcm_directed_monks.npz", True)])
+def test_joint_log_posterior_matches_the_reference_logps(name, directed):
+    """logps_[s] of the reference (lpcm.py:770-856) = network log-likelihood + every prior term.  The
+    network term comes from the C oracle (K4 / K5, pinned on the reference's kernels in
+    tests/test_oracle_golden.py); adding the product's ``lpcm_log_prior`` must give the recorded
+    log-posterior of every stored sample, rtol 1e-10."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import pyoracle as O
     from dynetlsm_b200.lpcm import lpcm_log_prior
-    g = load_golden("lpcm_undirected_split.npz")
+    g = load_golden(name)
     S, T, n, d = g["X_centered"].shape
-    hp = _hyper(g, False, n, d)
-    s = 5
-    hp.mean_variance_prior = np.array([g["mean_variance_prior"][s]])
-    hp.b = float(g["b"][s])
-    z = g["z_out"][s].astype(np.int64)
-    args = (g["X_centered"][s], g["intercept_out"][s], np.array([1.0]), 2.0, g["mu_next"][s], g["sigma_next"][s], z)
-    K = g["sigma_in"].shape[1]
-    a = lpcm_log_prior(hp, *args, g["init_next"][s], g["trans_next"][s], g["lmbda_next"][s])
-    flat_i, flat_t = np.full(K, 1. / K), np.full((K, K), 1. / K)
-    b = lpcm_log_prior(hp, *args, flat_i, flat_t, g["lmbda_next"][s])
-    want = stats.dirichlet.logpdf(g["init_next"][s], np.ones(K)) - stats.dirichlet.logpdf(flat_i, np.ones(K))
-    for k in range(K):
-        want += stats.dirichlet.logpdf(g["trans_next"][s][k], np.ones(K)) - stats.dirichlet.logpdf(flat_t[k], np.ones(K))
-    want += np.sum(np.log(g["init_next"][s][z[0]])) - n * np.log(1. / K)
-    for t in range(1, T):
-        want += np.sum(np.log(g["trans_next"][s][z[t - 1], z[t]])) - n * np.log(1. / K)
-    assert np.allclose(np.ravel(a - b)[0], want, rtol=1e-10, atol=1e-9)
+    hp = _hyper(g, directed, n, d)
+    Y = g["Y"].astype(np.float64)
+    ip, ivp = g["intercept_prior"], float(g["intercept_variance_prior"])
+    for s in range(S):
+        hp.mean_variance_prior = np.array([g["mean_variance_prior"][s]])
+        hp.b = float(g["b"][s])
+        X, ic = g["X_centered"][s], g["intercept_out"][s]
+        dist = O.calculate_distances(X)
+        if directed:
+            ll = O.directed_network_loglikelihood(Y, dist, g["radii_out"][s], ic[0], ic[1])
+        else:
+            ll = O.undirected_network_loglikelihood(Y, dist, ic[0])
+        lp = lpcm_log_prior(hp, X, ic, ip, ivp, g["mu_next"][s], g["sigma_next"][s],
+                            g["z_out"][s].astype(np.int64), g["init_next"][s], g["trans_next"][s],
+                            g["lmbda_next"][s], radii=g["radii_out"][s] if directed else None)
+        got = float(np.ravel(ll + lp)[0])
+        assert np.isclose(got, g["logp"][s], rtol=1e-10, atol=0), (s, got, g["logp"][s])
+        assert g["logp"][s] == g["logps"][s + 1]
