@@ -293,6 +293,12 @@ def run_hdp(Y, keep, **kw):
             cur["lmbda_next"] = np.array(lmbda, dtype=np.float64).copy()
             cur["w_next"] = weights.copy()
             cur["beta_next"] = beta.copy()
+            # hyper-parameters in force when the log-posterior of this sample was taken
+            cur["hyper_next"] = np.array([np.ravel(v_)[0] for v_ in (
+                self.gamma, self.alpha_init, self.alpha, self.kappa, self.mean_variance_prior_, self.b_)],
+                dtype=np.float64)
+            if k.get("radii") is not None:
+                cur["radii_logp"] = np.asarray(k["radii"], dtype=np.float64).copy()
             sweeps.append(cur)
             REC.cur = None
         return v
@@ -309,6 +315,8 @@ def run_hdp(Y, keep, **kw):
     rec["tune"] = np.int32(model.tune)
     rec["tune_interval"] = np.int32(model.tune_interval)
     rec["logps"] = model.logps_[:keep + 1].copy()
+    rec["hdp_prior"] = np.array([model.a, model.a0_, model.b0_, model.c0_, model.d0_, model.lambda_prior,
+                                 model.lambda_variance_prior], dtype=np.float64)
     return rec, model
 
 

@@ -1,0 +1,47 @@
+"""The HDP estimator's joint log-posterior on the host (``hdp_updates.hdp_log_prior``) against the
+reference's own ``logps_`` (hdp_lpcm.py:1188-1280) recorded in tests/golden/hdp_*.npz: network
+log-likelihood from the C oracle (K4 / K5, themselves pinned on the reference's kernels) + the
+product's prior terms must reproduce every stored sample's value, rtol 1e-10.  Together with
+tests/test_gpu_trace.py (device ``k_logp`` == ``hdp_log_prior``) this anchors the device
+log-posterior of the mixture model directly on reference outputs.  No GPU, no reference tree.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+
+
+@pytest.mark.parametrize("name,directed", [("hdp_undirected_split.npz", False),
+                                           ("hdp_directed_monks.npz", True)])
+def test_hdp_joint_log_posterior_matches_the_reference_logps(name, directed):
+    import pyoracle as O
+    from dynetlsm_b200.hdp_updates import HDPHyper, hdp_log_prior
+    g = load_golden(name)
+    S, T, n, d = g["X_centered"].shape
+    K = g["sigma_next"].shape[1]
+    a, a0, b0, c0, d0, lam0, lamv = [float(v) for v in g["hdp_prior"]]
+    Y = g["Y"].astype(np.float64)
+    ip, ivp = g["intercept_prior"], float(g["intercept_variance_prior"])
+    for s in range(S):
+        gamma, alpha_init, alpha, kappa, mvp, b = [float(v) for v in g["hyper_next"][s]]
+        hp = HDPHyper(gamma, alpha_init, alpha, kappa, np.array([mvp]), b, a, a0, b0, c0, d0, lam0, lamv,
+                      1.0, 0.1, 1.0, 1.0, 5, 0.1, True, True)
+        X, ic = g["X_centered"][s], g["intercept_out"][s]
+        dist = O.calculate_distances(X)
+        if directed:
+            radii = g["radii_logp"][s]
+            ll = O.directed_network_loglikelihood(Y, dist, radii, ic[0], ic[1])
+        else:
+            radii = None
+            ll = O.undirected_network_loglikelihood(Y, dist, ic[0])
+        lp = hdp_log_prior(hp, K, X, ic, ip, ivp, g["mu_next"][s], g["sigma_next"][s],
+                           g["z_out"][s].astype(np.int64), g["w_next"][s], g["beta_next"][s],
+                           g["lmbda_next"][s], radii=radii)
+        got = float(np.ravel(ll + lp)[0])
+        assert np.isclose(got, g["logp"][s], rtol=1e-10, atol=0), (s, got, g["logp"][s])
+        assert g["logp"][s] == g["logps"][s + 1]
