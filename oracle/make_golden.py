@@ -208,6 +208,9 @@ def wrap_blocks(mod, mixture):
             cur["w"] = w.copy()
             z, n, nk, resp = orig_lab(X, mu, sigma, lmbda, w, random_state=random_state)
             T, nn = z.shape
+            st = random_state.get_state()      # the RandomState entering the conjugate block
+            cur["rng_keys"], cur["rng_pos"] = st[1].copy(), np.int64(st[2])
+            cur["rng_has_gauss"], cur["rng_gauss"] = np.int64(st[3]), np.float64(st[4])
             cur["U"] = np.array([c[0] for c in REC.cat]).reshape(nn, T)
             cur["probas"] = np.array([c[1] for c in REC.cat]).reshape(nn, T, -1)
             cur["z_out"] = z.astype(np.int32)

@@ -45,3 +45,34 @@ def test_hdp_joint_log_posterior_matches_the_reference_logps(name, directed):
         got = float(np.ravel(ll + lp)[0])
         assert np.isclose(got, g["logp"][s], rtol=1e-10, atol=0), (s, got, g["logp"][s])
         assert g["logp"][s] == g["logps"][s + 1]
+
+
+@pytest.mark.parametrize("name", ["hdp_undirected_split.npz", "hdp_directed_monks.npz"])
+def test_hdp_conjugate_block_reproduces_the_reference_draws(name):
+    """The host restatement of hdp_lpcm.py:881-1023 (``hdp_updates.conjugate_updates``: auxiliary
+    tables, beta, initial / transition weights, means, variances, lambda, scale hyper-priors,
+    concentration parameters) on the reference's inputs and RandomState of every recorded sweep:
+    every draw bit for bit.  (Sweep 0 is skipped: the initial beta is not part of the record.)"""
+    from dynetlsm_b200.hdp_updates import HDPHyper, conjugate_updates
+    g = load_golden(name)
+    S = g["X_centered"].shape[0]
+    a, a0, b0, c0, d0, lam0, lamv = [float(v) for v in g["hdp_prior"]]
+    for s in range(1, S):
+        rng = np.random.RandomState(0)
+        rng.set_state(("MT19937", g["rng_keys"][s], int(g["rng_pos"][s]),
+                       int(g["rng_has_gauss"][s]), float(g["rng_gauss"][s])))
+        gamma, alpha_init, alpha, kappa, mvp, b = [float(v) for v in g["hyper_next"][s - 1]]
+        hp = HDPHyper(gamma, alpha_init, alpha, kappa, np.array([mvp]), b, a, a0, b0, c0, d0, lam0, lamv,
+                      1.0, 0.1, 1.0, 1.0, 5, 0.1, True, True)
+        mu, sigma, w = g["mu"][s].copy(), g["sigma"][s].copy(), g["w"][s].copy()
+        beta, lm = conjugate_updates(rng, hp, g["X_centered"][s], g["z_out"][s].astype(np.int64),
+                                     g["n_out"][s], g["nk_out"][s].astype(np.int64), mu, sigma,
+                                     np.atleast_1d(g["lmbda"][s]).astype(np.float64).copy(),
+                                     g["beta_next"][s - 1].copy(), w)
+        assert np.array_equal(beta, g["beta_next"][s]), s
+        assert np.array_equal(w, g["w_next"][s]), s
+        assert np.array_equal(mu, g["mu_next"][s]) and np.array_equal(sigma, g["sigma_next"][s]), s
+        assert np.array_equal(np.ravel(lm), np.ravel(g["lmbda_next"][s])), s
+        got = np.array([np.ravel(v)[0] for v in (hp.gamma, hp.alpha_init, hp.alpha, hp.kappa,
+                                                 hp.mean_variance_prior, hp.b)])
+        assert np.array_equal(got, g["hyper_next"][s]), (s, got, g["hyper_next"][s])
