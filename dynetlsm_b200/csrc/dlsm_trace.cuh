@@ -33,12 +33,21 @@ __device__ __forceinline__ double clip_tiny(double v) { return v > 2.22507385850
 __device__ inline double dirichlet_logpdf_row(const double *x, const double *base, double scale,
                                               int hot, double extra, double flat, int K)
 {
+    // the reference clips a vector only when one of its entries is <= 0, and then ALL of them
+    // (np.clip on the whole array): a subnormal weight in a row without zeros keeps its value
+    bool a_nonpos = false, x_nonpos = false;
+    for (int k = 0; k < K; k++) {
+        double a = base ? scale * base[k] : flat;
+        if (k == hot) a += extra;
+        a_nonpos |= !(a > 0.0);
+        x_nonpos |= !(x[k] > 0.0);
+    }
     double sa = 0.0, sl = 0.0, sx = 0.0;
     for (int k = 0; k < K; k++) {
         double a = base ? scale * base[k] : flat;
         if (k == hot) a += extra;
-        a = clip_tiny(a);
-        const double xv = clip_tiny(x[k]);
+        if (a_nonpos) a = clip_tiny(a);
+        const double xv = x_nonpos ? clip_tiny(x[k]) : x[k];
         sa += a;
         sl += lgamma(a);
         const double am1 = a - 1.0;

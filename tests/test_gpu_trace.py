@@ -408,3 +408,37 @@ def test_logp_against_the_reference_trace(name, directed):
                 intercept_prior=np.asarray(g["intercept_prior"], dtype=np.float64),
                 intercept_variance_prior=float(g["intercept_variance_prior"]))
     assert np.allclose(e.logp(), want[:S], rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("name,directed", [("hdp_undirected_split.npz", False), ("hdp_directed_monks.npz", True)])
+def test_logp_hdp_against_the_reference_trace(name, directed):
+    """k_logp's mixture branch pinned DIRECTLY on the reference: stored samples of a reference
+    HDP-LPCM fit (state + the hyper-parameters in force, oracle/make_golden.py) are put on the device,
+    one per chain, and dlsm_logp must return the reference's own logps_ (hdp_lpcm.py:1188-1280)."""
+    import os
+    L = _L()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+    Y = g["Y"].astype(np.float64)
+    T, n, _ = Y.shape
+    S = min(g["logp"].shape[0], 12)
+    K, d = g["mu_next"].shape[1:]
+    e = L.Engine(T=T, n=n, d=d, n_chains=S, K=K, mixture=True, is_directed=directed)
+    e.set_network(Y)
+    e.set(L.F_X, np.ascontiguousarray(g["X_centered"][:S]))
+    ic = np.zeros((S, 2)); ic[:, :g["intercept_out"].shape[1]] = g["intercept_out"][:S]
+    e.set(L.F_INTERCEPT, ic)
+    if directed:
+        e.set(L.F_RADII, np.ascontiguousarray(g["radii_logp"][:S]))
+    e.set(L.F_MU, np.ascontiguousarray(g["mu_next"][:S])); e.set(L.F_SIGMA, np.ascontiguousarray(g["sigma_next"][:S]))
+    e.set(L.F_LAMBDA, np.ascontiguousarray(g["lmbda_next"][:S].reshape(S)))
+    e.set(L.F_WEIGHTS, np.ascontiguousarray(g["w_next"][:S])); e.set(L.F_BETA, np.ascontiguousarray(g["beta_next"][:S]))
+    e.set(L.F_Z, np.ascontiguousarray(g["z_out"][:S]))
+    hy = np.zeros((S, 8)); hy[:, :6] = g["hyper_next"][:S]
+    e.set(L.F_HYPER, hy)
+    a, a0, b0, c0, d0, lam0, lamv = [float(v) for v in g["hdp_prior"]]
+    e.set_hdp_prior(a, a0, b0, c0, d0, lam0, lamv, 1.0, 0.1, 1.0, 1.0, 5, 0.1, True, True)
+    e.set_hyper(intercept_prior=np.asarray(g["intercept_prior"], dtype=np.float64),
+                intercept_variance_prior=float(g["intercept_variance_prior"]))
+    got = e.logp()
+    e.close()
+    assert np.allclose(got, g["logp"][:S], rtol=1e-10, atol=0), (got, g["logp"][:S])
