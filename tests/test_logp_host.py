@@ -76,3 +76,27 @@ def test_hdp_conjugate_block_reproduces_the_reference_draws(name):
         got = np.array([np.ravel(v)[0] for v in (hp.gamma, hp.alpha_init, hp.alpha, hp.kappa,
                                                  hp.mean_variance_prior, hp.b)])
         assert np.array_equal(got, g["hyper_next"][s]), (s, got, g["hyper_next"][s])
+
+
+@pytest.mark.parametrize("name,directed", [("lsm_undirected_monks.npz", False),
+                                           ("lsm_directed_monks.npz", True)])
+def test_lsm_joint_log_posterior_matches_the_reference_logps(name, directed):
+    """Same pin for the plain latent space model (lsm.py:576-625): C-oracle network term +
+    ``DynamicNetworkLSM._log_prior`` (what the replay loop stores in ``logps_``) on the reference's
+    stored samples."""
+    import pyoracle as O
+    from dynetlsm_b200 import DynamicNetworkLSM
+    g = load_golden(name)
+    Y = g["Y"].astype(np.float64)
+    m = DynamicNetworkLSM(is_directed=directed, tau_sq=float(g["tau_sq"]), sigma_sq=float(g["sigma_sq"]),
+                          intercept_prior=np.asarray(g["intercept_prior"], dtype=np.float64),
+                          intercept_variance_prior=float(g["intercept_variance_prior"]))
+    Xs, ics, want = g["Xs"], g["intercepts"], g["logps"]
+    for s in range(min(len(want), 40)):
+        dist = O.calculate_distances(Xs[s])
+        if directed:
+            ll = O.directed_network_loglikelihood(Y, dist, g["radiis"][s], ics[s, 0], ics[s, 1])
+        else:
+            ll = O.undirected_network_loglikelihood(Y, dist, ics[s, 0])
+        got = float(np.ravel(ll + m._log_prior(Xs[s], ics[s]))[0])
+        assert np.isclose(got, want[s], rtol=1e-10, atol=0), (s, got, want[s])
